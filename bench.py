@@ -1,0 +1,346 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the oceanic gravity hot path on B200.
+
+Metric (BASELINE.json): pairwise gravitational interactions per second, reported in G/s, of the softened
+direct-sum field build (K1), with the fraction of FP32 peak at 20 flop per interaction.
+
+Workload
+  N = 1 : BASELINE.json configs[1] — 64^3 (+1 origin) Cartesian grid from a synthetic 10M-particle
+          GIZMO-format snapshot, Plummer-softened direct sum, one B200.  A step is one pass of the field build
+          over one snapshot (2.62e12 interactions).
+  N > 1 : the same grid; every rank holds its own 10M-particle source shard (1e7*N particles in total, 8e7 at
+          N = 8 ~ configs[4]'s "1e8-particle snapshot sharded"), computes the full-grid partial field, then one
+          NCCL all-reduce (sum, fp64, 3*(64^3+1)) over NVLink and the frame subtraction.  Per-GPU work is fixed:
+          "scaling": "weak".   `--workload c5` runs configs[4] itself (128^3 grid, 1e8 particles split over N).
+
+  value : whole-job interactions/s with inputs (FP32 recentred sources/targets) resident in HBM.
+  e2e   : same metric through the C-ABI host call ocg_field_build_host (N=1) / the device calls fed from pinned
+          host tensors (N>1): FP64 host buffers in, H2D, recentre, K1, [all-reduce], K1b, D2H of the field.
+  --impl reference : the reference's CPU path (the FP64 OpenMP port in oracle/, all host threads) on a bounded
+          sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FLOP_PER_INTERACTION = 20.0  # GPU-Gems-3 ch.31 convention, acc only
+G_KPC = 4.398600413517813e-09
+CENTER = np.array([8.0, 0.0, 0.0])
+HALF = 0.6
+STAR_SOFT, DARK_SOFT = 11.2e-3, 112.0e-3  # kpc (test_options:25-26)
+
+
+# ----------------------------------------------------------------------------------- inputs ----
+def make_sources(n, seed):
+    """FP64 (pos [n,3], mass [n], plummer eps [n]) in the reference's source order star|dark|gas."""
+    from oc_nbody_b200.synthetic import make_snapshot
+    snap = make_snapshot(n, seed=seed)
+    pos = np.concatenate([snap[s]["position"] for s in ("star", "dark", "gas")])
+    mass = np.concatenate([snap[s]["mass"] for s in ("star", "dark", "gas")])
+    soft = np.concatenate([np.full(len(snap["star"]["mass"]), STAR_SOFT), np.full(len(snap["dark"]["mass"]), DARK_SOFT),
+                           2.8e-3 * snap["gas"]["smooth.length"]]) / 2.8  # Plummer-equivalent epsilon of the spline h
+    return np.ascontiguousarray(pos), np.ascontiguousarray(mass), np.ascontiguousarray(soft)
+
+
+def make_targets(n_grid):
+    from oc_nbody_b200.grid_cartesian import grid
+    g = grid(HALF, HALF, HALF, HALF / n_grid)
+    g.gen_evolved_grid(CENTER)
+    return g
+
+
+# ------------------------------------------------------------------------------ clock sampler ----
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()  # the exact PID we started
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])), mx.append(float(f[2])), pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for k, nm in enumerate(names):
+                if f[5 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "power_w_max": float(max(pw)),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------ CPU baseline ----
+def cpu_sample_rate(tgt_pos, src_pos, src_mass, src_eps, seconds):
+    """Time the oracle's vectorised FP64 direct sum (all host threads) on a bounded sample of the workload.
+    Returns (interactions/s, description, threads)."""
+    import oracle
+    n_t = min(4097, tgt_pos.shape[0])
+    tp = np.ascontiguousarray(tgt_pos[:: max(1, tgt_pos.shape[0] // n_t)][:n_t])
+    e2 = src_eps * src_eps
+    n_cal = min(20000, src_pos.shape[0])
+    t0 = time.perf_counter()
+    oracle.field_direct_fast(src_pos[:n_cal], src_mass[:n_cal], e2[:n_cal], tp, G_KPC)
+    cal = max(time.perf_counter() - t0, 1e-4)
+    rate0 = n_cal * tp.shape[0] / cal
+    n_s = int(min(src_pos.shape[0], max(n_cal, rate0 * seconds / tp.shape[0])))
+    t0 = time.perf_counter()
+    oracle.field_direct_fast(src_pos[:n_s], src_mass[:n_s], e2[:n_s], tp, G_KPC)
+    dt = time.perf_counter() - t0
+    desc = "%d grid targets x %d sources of the workload, FP64 OpenMP direct sum (oracle/ocg_oracle.c), %.1f s" % (
+        tp.shape[0], n_s, dt)
+    return n_s * tp.shape[0] / dt, desc, oracle.num_threads()
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU path = the oracle port (the reference itself cannot be imported:
+    SURVEY §0.3), all host threads, each step a bounded sample of the N=1 workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    g = make_targets(args.grid)
+    n_sample_src = min(args.n_src, 400000)
+    pos, mass, eps = make_sources(n_sample_src, seed=1776)
+    rates, desc, threads = [], "", 1
+    per_step = max(2.0, min(20.0, 120.0 / max(1, args.steps + args.warmup)))
+    for i in range(args.warmup + args.steps):
+        r, desc, threads = cpu_sample_rate(g.evolved_grid, pos, mass, eps, per_step)
+        if i >= args.warmup:
+            rates.append(r)
+    val = float(np.mean(rates)) / 1e9
+    inter_step = float(len(g)) * args.n_src
+    line = {
+        "impl": "reference", "metric": "pairwise_grav_interactions_per_sec", "value": val, "unit": "G/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": inter_step / (val * 1e9) * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args, 1),
+        "cpu_baseline": {"value": val, "unit": "G/s", "cores": threads, "kind": "port", "sample": desc},
+        "e2e": {"value": val, "unit": "G/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "ms_per_step extrapolates the sampled rate to the full step (a direct sum's rate is size independent)",
+    }
+    print(json.dumps(line))
+
+
+def workload_config(args, n_gpus):
+    return {"workload": "%s: %d^3+1 grid targets x %d synthetic snapshot particles per GPU (%d total), Plummer-softened "
+                        "direct-sum field build" % ("configs[4]" if args.workload == "c5" else "configs[1]", args.grid,
+                                                    args.n_src_rank, args.n_src_rank * n_gpus),
+            "grid": args.grid, "n_targets": args.grid ** 3 + 1, "n_sources_per_gpu": args.n_src_rank,
+            "n_sources_total": args.n_src_rank * n_gpus, "softening": "plummer, per-source epsilon",
+            "parallelism": "source-sharded x%d + NCCL all-reduce(fp64)" % n_gpus if n_gpus > 1 else "single GPU",
+            "l2_policy": "inputs larger than L2 (%.0f MB of sources per GPU vs 126 MB L2)" % (args.n_src_rank * 20 / 1e6)}
+
+
+# ------------------------------------------------------------------------------------ main ----
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c2", choices=["c2", "c5"])
+    ap.add_argument("--n-src", type=float, default=None, help="override particles per GPU (debug)")
+    ap.add_argument("--grid", type=int, default=None, help="override grid nodes per axis (debug)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--variant", default="auto", help="auto | tptN | scalar-tptN (debug)")
+    args = ap.parse_args()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.workload == "c5":
+        args.grid = args.grid or 128
+        args.n_src_rank = int(args.n_src or 1e8 / world)
+    else:
+        args.grid = args.grid or 64
+        args.n_src_rank = int(args.n_src or 1e7)
+    args.n_src = args.n_src_rank
+    if args.warmup < 3:
+        args.warmup = 3  # timing rule: W >= 3
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: oc_nbody_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    from oc_nbody_b200 import Context
+    ctx = Context(local_rank)
+    if args.variant != "auto":
+        sc = 1 if args.variant.startswith("scalar") else 0
+        ctx.lib.ocg_debug_set_variant(int(args.variant[-1]), sc)
+    dev = torch.device("cuda", local_rank)
+
+    g = make_targets(args.grid)
+    n_tgt = len(g)
+    pos, mass, eps = make_sources(args.n_src_rank, seed=1776 + rank)
+    n_src = pos.shape[0]
+    inter_rank = float(n_src) * n_tgt
+    inter_total = inter_rank * world
+
+    # pinned host buffers (e2e path) and resident device inputs (value path)
+    h_pos, h_mass, h_eps = (torch.from_numpy(a).pin_memory() for a in (pos, mass, eps))
+    h_tgt = torch.from_numpy(np.ascontiguousarray(g.evolved_grid)).pin_memory()
+    d_src = torch.empty((n_src, 4), dtype=torch.float32, device=dev)
+    d_eps = torch.empty(n_src, dtype=torch.float32, device=dev)
+    d_tgt = torch.empty((n_tgt, 4), dtype=torch.float32, device=dev)
+    ctx.recentre_f64(h_pos.to(dev), h_mass.to(dev), CENTER, d_src)
+    ctx.cast_f64_f32(h_eps.to(dev), d_eps)
+    ctx.recentre_f64(h_tgt.to(dev), None, CENTER, d_tgt)
+    acc = torch.empty((3, n_tgt), dtype=torch.float64, device=dev)
+    torch.cuda.synchronize()
+
+    def step_resident():
+        ctx.field_direct(d_src, d_eps, d_tgt, 0, G_KPC, acc)
+        if world > 1:
+            dist.all_reduce(acc)
+        ctx.frame_subtract(acc, g.origin_row)
+
+    def step_e2e():
+        if world == 1:
+            return ctx.field_build_host(h_pos.numpy(), h_mass.numpy(), h_eps.numpy(), h_tgt.numpy(), CENTER, g.origin_row, 0,
+                                        G_KPC)
+        p64, m64, e64 = h_pos.to(dev, non_blocking=True), h_mass.to(dev, non_blocking=True), h_eps.to(dev, non_blocking=True)
+        t64 = h_tgt.to(dev, non_blocking=True)
+        ctx.recentre_f64(p64, m64, CENTER, d_src)
+        ctx.cast_f64_f32(e64, d_eps)
+        ctx.recentre_f64(t64, None, CENTER, d_tgt)
+        ctx.field_direct(d_src, d_eps, d_tgt, 0, G_KPC, acc)
+        dist.all_reduce(acc)
+        ctx.frame_subtract(acc, g.origin_row)
+        return acc.cpu().numpy()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, kernel_ms=None):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for _ in range(steps):
+            fn()
+            if kernel_ms is not None:
+                kernel_ms.append(ctx.last_direct_kernel_ms())
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    # ---- resident (device-timed) ----
+    for _ in range(args.warmup):
+        step_resident()
+    ctx.set_kernel_timing(True)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = ctx.launch_count()
+    kernel_ms = []
+    total_ms = timed(step_resident, args.steps, kernel_ms)
+    launches = ctx.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    ctx.set_kernel_timing(False)
+    ms_per_step = total_ms / args.steps
+    value = inter_total / (ms_per_step * 1e-3) / 1e9
+    result_check = float(acc[:, g.origin_row].abs().max().item())
+
+    # ---- end to end (host buffers) ----
+    for _ in range(1):
+        step_e2e()
+    e2e_ms = timed(step_e2e, args.steps) / args.steps
+    e2e_value = inter_total / (e2e_ms * 1e-3) / 1e9
+    h2d = n_src * (24 + 8 + 8) + n_tgt * 24
+    d2h = n_tgt * 24
+
+    # ---- roofline of the dominant kernel (direct_sum_kernel), FP32 pipe ----
+    k_ms = float(np.mean(kernel_ms))
+    achieved = FLOP_PER_INTERACTION * inter_rank / (k_ms * 1e-3) / 1e12
+    nominal = ctx.sm_count * 128 * 2 * ctx.sm_clock_khz * 1e3 / 1e12
+    ffma = ctx.probe_throughput(0)
+    ffma2 = ctx.probe_throughput(1)
+    roofline = {"bound": "fp32", "achieved": achieved, "peak": nominal, "unit": "TFLOP/s", "frac": achieved / nominal,
+                "traffic": None, "kernel": "direct_sum_kernel", "kernel_ms": k_ms, "kernel_share_of_step": k_ms / ms_per_step,
+                "peak_kind": "nominal FP32: %d SM x 128 lanes x 2 flop x %.3f GHz (MEASURED_PEAKS.json has no FP32 entry)" % (
+                    ctx.sm_count, ctx.sm_clock_khz / 1e6),
+                "peak_measured_ffma": ffma, "peak_measured_ffma2": ffma2, "frac_of_measured": achieved / max(ffma, ffma2),
+                "flop_per_interaction": FLOP_PER_INTERACTION,
+                "interactions_per_launch": inter_rank}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    cpu = None
+    if not args.no_cpu_baseline:
+        r, desc, threads = cpu_sample_rate(g.evolved_grid, pos[:400000], mass[:400000], eps[:400000], 12.0)
+        cpu = {"value": r / 1e9, "unit": "G/s", "cores": threads, "kind": "port", "sample": desc}
+    line = {
+        "metric": "pairwise_grav_interactions_per_sec", "value": value, "unit": "G/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak" if args.workload == "c2" else "strong",
+        "vs_baseline": None, "dtype": "f32 pair arithmetic, f64 accumulation", "data": "synthetic",
+        "config": workload_config(args, world),
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": "G/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "api": "ocg_field_build_host (C ABI, host buffers)" if world == 1 else
+                       "pinned host tensors -> ocg_recentre_f64/ocg_field_direct/all_reduce/ocg_frame_subtract -> host"},
+        "gpu_launches": launches,
+        "roofline": roofline,
+        "cpu_baseline": cpu,
+        "pct_fp32_peak": 100.0 * achieved / nominal,
+        "origin_row_abs_max": result_check,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

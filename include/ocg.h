@@ -1,0 +1,173 @@
+/*
+ * ocg.h — C ABI of liboc_nbody_b200 ("oceanic gravity"), the B200 (sm_100a) drop-in for
+ * the gravity hot path of gusbeane/oc_nbody ("oceanic").
+ *
+ * Every entry point is plain C: pointers, sizes, scalars; int status return
+ * (0 = OCG_OK, <0 = error, text via ocg_last_error()).  Nothing throws, nothing exits
+ * (contrast the reference's sys.exit(0) at gizmo_interface.py:461).
+ *
+ * Pointer convention
+ *   *_dev  : device pointer owned by the caller (e.g. torch tensor .data_ptr()); written in place.
+ *   *_host : host pointer owned by the caller (e.g. numpy array .ctypes.data).
+ * The library only allocates scratch tied to the ocg_ctx; ocg_destroy() frees it.
+ * One ctx per GPU per process; a ctx is not thread-safe (the reference's only caller is the
+ * single-threaded AMUSE Bridge, oc_nbody.py:49 `use_threading=False`).
+ * All device-pointer calls are asynchronous on `stream` (a cudaStream_t passed as void*;
+ * NULL = the legacy default stream).  Host-pointer calls return after the result is on the host.
+ *
+ * The library is unit-agnostic: lengths and masses in, G as an argument.
+ *   field path  : kpc, Msun, G = 4.300917270036279e-06 kpc (km/s)^2/Msun * (km/s per kpc/Myr)...
+ *                 the reference uses G in kpc^2 km s^-1 Myr^-1 Msun^-1 (gizmo_interface.py:70)
+ *                 = 4.498502151469554e-12 kpc^3/Myr^2/Msun * 977.79222 = 4.3986004e-09.
+ *   cluster path: pc, Msun, G = 4.30091727e-03 pc (km/s)^2 / Msun.
+ *
+ * Reference interface replaced by each entry point is cited as (file:line) into gusbeane/oc_nbody.
+ */
+#ifndef OCG_H
+#define OCG_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OCG_VERSION 100 /* 0.1.0 */
+
+/* status codes */
+#define OCG_OK 0
+#define OCG_ERR_INVALID (-1) /* bad argument */
+#define OCG_ERR_CUDA (-2)    /* CUDA runtime error; see ocg_last_error */
+#define OCG_ERR_NOMEM (-3)   /* scratch allocation failed */
+#define OCG_ERR_NODEVICE (-4)
+
+/* softening kernels (gizmo_interface.py:530-550,561 pass a per-source length to pykdgrav) */
+#define OCG_KERNEL_PLUMMER 0 /* K = (r^2 + s^2)^(-3/2); s = soft                           */
+#define OCG_KERNEL_SPLINE 1  /* cubic-spline, compact support h = soft (pykdgrav ForceKernel) */
+
+typedef struct ocg_ctx ocg_ctx;
+
+/* ---- context ---------------------------------------------------------------------------- */
+int ocg_version(void);
+int ocg_create(int device, ocg_ctx** out);
+int ocg_destroy(ocg_ctx* ctx);
+/* Last error text of this ctx ("" if none). ctx may be NULL: returns the text of the last failed ocg_create. */
+const char* ocg_last_error(const ocg_ctx* ctx);
+/* Device facts used by the roofline report. */
+int ocg_device_info(ocg_ctx* ctx, int* sm_count, int* sm_clock_khz, int64_t* global_mem_bytes);
+/* Counts kernels this library launched on this ctx since creation (bench.py "gpu_launches"). */
+int64_t ocg_launch_count(const ocg_ctx* ctx);
+/* Milliseconds (cudaEvent, on `stream`) spent inside the dominant kernel of the most recent
+ * ocg_field_direct / ocg_self_gravity call; the call synchronises `stream`. <0 on error. */
+double ocg_last_direct_kernel_ms(ocg_ctx* ctx);
+/* Enable(1)/disable(0) event timing around the direct-sum kernel (default off). */
+int ocg_set_kernel_timing(ocg_ctx* ctx, int enabled);
+
+/* ---- K0: recentre fp64 -> fp32 ------------------------------------------------
+ * out_xyzw[i] = (float)(pos[i] - center) , w = (float)mass[i] (or 0 when mass_dev == NULL).
+ * pos_dev is [n][3] fp64 row-major, exactly the `np.float64(r)` array the reference hands to
+ * pykdgrav (gizmo_interface.py:561) or `grid.evolved_grid` (gizmo_interface.py:564).            */
+int ocg_recentre_f64(ocg_ctx* ctx, const double* pos_dev, const double* mass_dev, int64_t n,
+                     const double center[3], float* out_xyzw_dev, void* stream);
+/* out[i] = (float)in[i] */
+int ocg_cast_f64_f32(ocg_ctx* ctx, const double* in_dev, int64_t n, float* out_dev, void* stream);
+
+/* ---- K1: field build, softened direct sum ---------------------------------------------------
+ * Replaces ConstructKDTree + GetAccelParallel (gizmo_interface.py:561,564,566) in the theta->0
+ * limit:  acc[c][t] (+)= G * sum_s m_s K(|x_s-x_t|, soft_s) (x_s-x_t)[c]
+ *         pot[t]    (+)= G * sum_s m_s P(|x_s-x_t|, soft_s)            (P<0)
+ * src_xyzm_dev : [n_src][4] fp32 (x,y,z,m)  recentred (ocg_recentre_f64)
+ * src_soft_dev : [n_src] fp32 softening length per source; NULL = all zero (Newtonian)
+ * tgt_xyzw_dev : [n_tgt][4] fp32 (x,y,z,ignored)
+ * acc_dev      : [3][n_tgt] fp64 (component-major: the three arrays the reference returns at
+ *                gizmo_interface.py:573); pot_dev: [n_tgt] fp64 or NULL.
+ * accumulate   : 0 overwrite, 1 add to what is there (source chunks streamed through HBM).
+ * Pairs with r == 0 contribute nothing unless Plummer with soft > 0 (then acc 0, pot -m/soft). */
+int ocg_field_direct(ocg_ctx* ctx, const float* src_xyzm_dev, const float* src_soft_dev,
+                     int64_t n_src, const float* tgt_xyzw_dev, int64_t n_tgt, int kernel, double G,
+                     double* acc_dev, double* pot_dev, int accumulate, void* stream);
+
+/* ---- K1b: frame subtraction (gizmo_interface.py:566,569-571) --------------------------------
+ * acc[c][t] -= acc[c][center_row] for all t (the centre row becomes exactly 0).               */
+int ocg_frame_subtract(ocg_ctx* ctx, double* acc_dev, int64_t n_tgt, int64_t center_row,
+                       void* stream);
+
+/* ---- K1 host form: the whole of _populate_grid_acceleration_ (gizmo_interface.py:512-573) ---
+ * Host fp64 in, host fp64 out; does H2D, recentre on `center`, K1, optional K1b, D2H.
+ * src_pos_host [n_src][3], src_mass_host [n_src], src_soft_host [n_src] (NULL = 0),
+ * tgt_pos_host [n_tgt][3] (= grid.evolved_grid), center[3] (= grid.ss_evolved_position),
+ * center_row: row of tgt that sits at `center` (the appended origin, grid_cartesian.py:66-67)
+ * or -1 for no subtraction. acc_host [3][n_tgt]; pot_host [n_tgt] or NULL.                     */
+int ocg_field_build_host(ocg_ctx* ctx, const double* src_pos_host, const double* src_mass_host,
+                         const double* src_soft_host, int64_t n_src, const double* tgt_pos_host,
+                         int64_t n_tgt, const double center[3], int64_t center_row, int kernel,
+                         double G, double* acc_host, double* pot_host);
+
+/* ---- K2: pack / blend grid planes ------------------------------------------------------------
+ * Pack one snapshot's field (fp64 [3][n_node] acc, optional [n_node] pot) into the node-record
+ * layout K3 gathers from: rec[node] = float4(ax, ay, az, phi).  n_node = nx*ny*nz + 1
+ * (grid_cartesian.py:59-69: C order, x outer, z inner, origin appended).                        */
+int ocg_pack_planes(ocg_ctx* ctx, const double* acc_dev, const double* pot_dev, int64_t n_node,
+                    float* rec_dev, void* stream);
+/* Materialised time blend (gizmo_interface.py:607-620 in its linear form):
+ * out[c][i] = (1-w_b)*rec_a[i][c] + w_b*rec_b[i][c]  for c in 0..2 (acc) ; pot_out nullable.   */
+int ocg_grid_time_blend(ocg_ctx* ctx, const float* rec_a_dev, const float* rec_b_dev, double w_b,
+                        int64_t n_node, double* acc_out_dev, double* pot_out_dev, void* stream);
+
+/* ---- K3: get_gravity_at_point (gizmo_interface.py:677-717) as trilinear + linear-in-time -----
+ * Grid lattice: nodes along axis d are node_d[i] + origin[cluster][d], i in [0,n[d]), with
+ * node_d the fp64 np.linspace arrays of grid_cartesian.py:29-31 (device copies).
+ * Cell along d = searchsorted(node_d + origin_d, x, side='right') - 1 clamped to [0, n[d]-2]
+ * (bit-exact with the oracle); weights linear, unclamped (linear extrapolation outside).
+ * rec_a_dev/rec_b_dev: [n_cluster][n_node] float4 records of the two bracketing snapshots,
+ * w_b in [0,1] the weight of b.  star_{x,y,z}_dev fp64 [n_star] (the three vectors BRIDGE passes,
+ * unwrapped to kpc).  star_cluster_dev: int32 [n_star] cluster of each star, NULL = all 0.
+ * origin_dev: fp64 [n_cluster][3] (evolve_grid, gizmo_interface.py:640-642).
+ * Outputs fp64: acc_out_dev [3][n_star]; pot_out_dev [n_star] nullable.                         */
+typedef struct ocg_grid_desc {
+  int32_t n[3];           /* nodes per axis (grid_cartesian.py:25-27) */
+  int32_t n_cluster;      /* number of independent grids in the batch */
+  const double* node_dev[3]; /* fp64 node coordinates per axis, device */
+  const double* origin_dev;  /* fp64 [n_cluster][3], device */
+} ocg_grid_desc;
+
+int ocg_grid_interp(ocg_ctx* ctx, const ocg_grid_desc* grid, const float* rec_a_dev,
+                    const float* rec_b_dev, double w_b, const double* star_x_dev,
+                    const double* star_y_dev, const double* star_z_dev,
+                    const int32_t* star_cluster_dev, int64_t n_star, double* acc_out_dev,
+                    double* pot_out_dev, int32_t* cell_out_dev /* [3][n_star] nullable */,
+                    void* stream);
+
+/* ---- K4: cluster self-gravity (ph4 force loop behind oc_code.py:218-229) ---------------------
+ * Plummer direct sum inside each segment (cluster) of a batch.
+ * pos_dev fp64 [3][n] component-major, mass_dev fp64 [n]; seg_offsets_host int64 [n_seg+1]
+ * (host array; NULL with n_seg == 1 means one segment [0,n)).  eps2 = epsilon_squared
+ * (oc_code.py:225).  Each segment is recentred on its first particle before rounding to fp32.
+ * tgt_begin/tgt_end: the rank's shard of targets (global particle indices); outputs are written
+ * for that range only, at the same global indices.  Self term excluded.
+ * acc_dev fp64 [3][n]; pot_dev fp64 [n] nullable.                                               */
+int ocg_self_gravity(ocg_ctx* ctx, const double* pos_dev, const double* mass_dev, int64_t n,
+                     const int64_t* seg_offsets_host, int32_t n_seg, double eps2, double G,
+                     int64_t tgt_begin, int64_t tgt_end, double* acc_dev, double* pot_dev,
+                     void* stream);
+
+/* ---- K5: BRIDGE kick / drift (amuse.couple.bridge kick + leapfrog drift, oc_nbody.py:56) ----
+ * vel[c][i] += dt * acc[c][i]   ;   pos[c][i] += dt * vel[c][i] * vel_to_len
+ * All fp64 [3][n] component-major; mul and add rounded separately (no FMA) so that a numpy
+ * `v + a*dt` reproduces the bits.                                                               */
+int ocg_kick(ocg_ctx* ctx, double* vel_dev, const double* acc_dev, int64_t n, double dt,
+             void* stream);
+int ocg_drift(ocg_ctx* ctx, double* pos_dev, const double* vel_dev, int64_t n, double dt,
+              double vel_to_len, void* stream);
+/* acc_sum = a + scale_b * b  (combine self-gravity with the tidal kick in other units) */
+int ocg_axpy(ocg_ctx* ctx, double* y_dev, const double* x_dev, double a, int64_t n, void* stream);
+
+/* ---- probes (roofline denominators measured live by bench.py) ------------------------------- */
+/* Runs an FFMA-only kernel (packed=0: FFMA, packed=1: FFMA2) over the whole GPU and returns
+ * achieved TFLOP/s (2 flop per lane-FMA). which: 0 FFMA, 1 FFMA2, 2 MUFU.RSQ (G ops/s).     */
+double ocg_probe_throughput(ocg_ctx* ctx, int which);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OCG_H */

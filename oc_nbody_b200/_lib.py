@@ -1,0 +1,237 @@
+"""ctypes binding of liboc_nbody_b200.so (the C ABI declared in include/ocg.h).
+
+There is NO CPU fallback: if the shared library is missing or no B200 is visible the calls raise.
+torch tensors are used purely as device buffers (``.data_ptr()``) and for the current stream.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "liboc_nbody_b200.so")
+
+KERNEL_PLUMMER = 0
+KERNEL_SPLINE = 1
+KERNELS = {"plummer": KERNEL_PLUMMER, "spline": KERNEL_SPLINE}
+
+# every symbol include/ocg.h declares (tests check the library exports them all)
+ABI_SYMBOLS = [
+    "ocg_version", "ocg_create", "ocg_destroy", "ocg_last_error", "ocg_device_info", "ocg_launch_count",
+    "ocg_last_direct_kernel_ms", "ocg_set_kernel_timing", "ocg_recentre_f64", "ocg_cast_f64_f32",
+    "ocg_field_direct", "ocg_frame_subtract", "ocg_field_build_host", "ocg_pack_planes", "ocg_grid_time_blend",
+    "ocg_grid_interp", "ocg_self_gravity", "ocg_kick", "ocg_drift", "ocg_axpy", "ocg_probe_throughput",
+]
+
+
+class OcgError(RuntimeError):
+    pass
+
+
+class _GridDesc(ctypes.Structure):
+    _fields_ = [("n", ctypes.c_int32 * 3), ("n_cluster", ctypes.c_int32), ("node_dev", ctypes.c_void_p * 3),
+                ("origin_dev", ctypes.c_void_p)]
+
+
+_lib = None
+
+
+def load_library():
+    """dlopen the in-tree CUDA library; raises (never falls back) if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise OcgError("%s is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                       "(oc_nbody_b200 has no CPU fallback)" % LIB_PATH)
+    L = ctypes.CDLL(LIB_PATH)
+    vp, i32, i64, dbl = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_double
+    L.ocg_version.restype = ctypes.c_int
+    L.ocg_create.argtypes = [ctypes.c_int, ctypes.POINTER(vp)]
+    L.ocg_destroy.argtypes = [vp]
+    L.ocg_last_error.restype = ctypes.c_char_p
+    L.ocg_last_error.argtypes = [vp]
+    L.ocg_device_info.argtypes = [vp, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int), ctypes.POINTER(i64)]
+    L.ocg_launch_count.restype = i64
+    L.ocg_launch_count.argtypes = [vp]
+    L.ocg_last_direct_kernel_ms.restype = dbl
+    L.ocg_last_direct_kernel_ms.argtypes = [vp]
+    L.ocg_set_kernel_timing.argtypes = [vp, ctypes.c_int]
+    L.ocg_recentre_f64.argtypes = [vp, vp, vp, i64, ctypes.POINTER(dbl), vp, vp]
+    L.ocg_cast_f64_f32.argtypes = [vp, vp, i64, vp, vp]
+    L.ocg_field_direct.argtypes = [vp, vp, vp, i64, vp, i64, ctypes.c_int, dbl, vp, vp, ctypes.c_int, vp]
+    L.ocg_frame_subtract.argtypes = [vp, vp, i64, i64, vp]
+    L.ocg_field_build_host.argtypes = [vp, vp, vp, vp, i64, vp, i64, ctypes.POINTER(dbl), i64, ctypes.c_int, dbl, vp, vp]
+    L.ocg_pack_planes.argtypes = [vp, vp, vp, i64, vp, vp]
+    L.ocg_grid_time_blend.argtypes = [vp, vp, vp, dbl, i64, vp, vp, vp]
+    L.ocg_grid_interp.argtypes = [vp, ctypes.POINTER(_GridDesc), vp, vp, dbl, vp, vp, vp, vp, i64, vp, vp, vp, vp]
+    L.ocg_self_gravity.argtypes = [vp, vp, vp, i64, vp, i32, dbl, dbl, i64, i64, vp, vp, vp]
+    L.ocg_kick.argtypes = [vp, vp, vp, i64, dbl, vp]
+    L.ocg_drift.argtypes = [vp, vp, vp, i64, dbl, dbl, vp]
+    L.ocg_axpy.argtypes = [vp, vp, vp, dbl, i64, vp]
+    L.ocg_probe_throughput.restype = dbl
+    L.ocg_probe_throughput.argtypes = [vp, ctypes.c_int]
+    L.ocg_debug_set_variant.argtypes = [ctypes.c_int, ctypes.c_int]
+    _lib = L
+    return L
+
+
+def _dptr(t):
+    """Device pointer of a torch CUDA tensor (or None)."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise OcgError("expected a CUDA tensor (device buffer), got a %s tensor" % t.device)
+    if not t.is_contiguous():
+        raise OcgError("device buffers must be contiguous")
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def _hptr(a):
+    return None if a is None else ctypes.c_void_p(a.ctypes.data)
+
+
+def _vec3(v):
+    return (ctypes.c_double * 3)(float(v[0]), float(v[1]), float(v[2]))
+
+
+class Context:
+    """One ocg_ctx: one GPU, one process, not thread-safe (include/ocg.h)."""
+
+    def __init__(self, device=0):
+        self.lib = load_library()
+        h = ctypes.c_void_p()
+        rc = self.lib.ocg_create(int(device), ctypes.byref(h))
+        if rc != 0:
+            raise OcgError("ocg_create(%d) failed (%d): %s" % (device, rc, self.lib.ocg_last_error(None).decode()))
+        self.h = h
+        self.device = int(device)
+        sm, khz, mem = ctypes.c_int(), ctypes.c_int(), ctypes.c_int64()
+        self.lib.ocg_device_info(h, ctypes.byref(sm), ctypes.byref(khz), ctypes.byref(mem))
+        self.sm_count, self.sm_clock_khz, self.global_mem = sm.value, khz.value, mem.value
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.ocg_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc, what):
+        if rc != 0:
+            raise OcgError("%s failed (%d): %s" % (what, rc, self.lib.ocg_last_error(self.h).decode()))
+
+    @staticmethod
+    def _stream():
+        import torch
+        return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    # ---- bookkeeping ----
+    def launch_count(self):
+        return int(self.lib.ocg_launch_count(self.h))
+
+    def set_kernel_timing(self, on):
+        self._ck(self.lib.ocg_set_kernel_timing(self.h, 1 if on else 0), "ocg_set_kernel_timing")
+
+    def last_direct_kernel_ms(self):
+        return float(self.lib.ocg_last_direct_kernel_ms(self.h))
+
+    def probe_throughput(self, which):
+        v = float(self.lib.ocg_probe_throughput(self.h, int(which)))
+        if v < 0:
+            raise OcgError("ocg_probe_throughput failed: %s" % self.lib.ocg_last_error(self.h).decode())
+        return v
+
+    # ---- device-buffer calls (torch tensors as buffers) ----
+    def recentre_f64(self, pos, mass, center, out):
+        n = pos.shape[0]
+        self._ck(self.lib.ocg_recentre_f64(self.h, _dptr(pos), _dptr(mass), n, _vec3(center), _dptr(out), self._stream()),
+                 "ocg_recentre_f64")
+
+    def cast_f64_f32(self, src, out):
+        self._ck(self.lib.ocg_cast_f64_f32(self.h, _dptr(src), src.numel(), _dptr(out), self._stream()), "ocg_cast_f64_f32")
+
+    def field_direct(self, src_xyzm, src_soft, tgt_xyzw, kernel, G, acc, pot=None, accumulate=False):
+        n_src, n_tgt = src_xyzm.shape[0], tgt_xyzw.shape[0]
+        self._ck(self.lib.ocg_field_direct(self.h, _dptr(src_xyzm), _dptr(src_soft), n_src, _dptr(tgt_xyzw), n_tgt,
+                                           int(kernel), float(G), _dptr(acc), _dptr(pot), 1 if accumulate else 0,
+                                           self._stream()), "ocg_field_direct")
+
+    def frame_subtract(self, acc, center_row):
+        self._ck(self.lib.ocg_frame_subtract(self.h, _dptr(acc), acc.shape[1], int(center_row), self._stream()),
+                 "ocg_frame_subtract")
+
+    def pack_planes(self, acc, pot, rec):
+        self._ck(self.lib.ocg_pack_planes(self.h, _dptr(acc), _dptr(pot), acc.shape[1], _dptr(rec), self._stream()),
+                 "ocg_pack_planes")
+
+    def grid_time_blend(self, rec_a, rec_b, w_b, acc_out, pot_out=None):
+        self._ck(self.lib.ocg_grid_time_blend(self.h, _dptr(rec_a), _dptr(rec_b), float(w_b), rec_a.shape[-2],
+                                              _dptr(acc_out), _dptr(pot_out), self._stream()), "ocg_grid_time_blend")
+
+    def grid_interp(self, n, nodes, origin, rec_a, rec_b, w_b, sx, sy, sz, star_cluster, acc_out, pot_out=None,
+                    cell_out=None):
+        d = _GridDesc()
+        for k in range(3):
+            d.n[k] = int(n[k])
+            d.node_dev[k] = nodes[k].data_ptr()
+        d.n_cluster = int(origin.shape[0])
+        d.origin_dev = origin.data_ptr()
+        self._ck(self.lib.ocg_grid_interp(self.h, ctypes.byref(d), _dptr(rec_a), _dptr(rec_b), float(w_b), _dptr(sx),
+                                          _dptr(sy), _dptr(sz), _dptr(star_cluster), sx.shape[0], _dptr(acc_out),
+                                          _dptr(pot_out), _dptr(cell_out), self._stream()), "ocg_grid_interp")
+
+    def self_gravity(self, pos, mass, eps2, G, acc, pot=None, seg_offsets=None, tgt_begin=0, tgt_end=None):
+        n = pos.shape[1]
+        if seg_offsets is None:
+            seg, n_seg = None, 1
+        else:
+            seg = np.ascontiguousarray(seg_offsets, dtype=np.int64)
+            n_seg = len(seg) - 1
+        tgt_end = n if tgt_end is None else tgt_end
+        self._ck(self.lib.ocg_self_gravity(self.h, _dptr(pos), _dptr(mass), n, _hptr(seg), n_seg, float(eps2), float(G),
+                                           int(tgt_begin), int(tgt_end), _dptr(acc), _dptr(pot), self._stream()),
+                 "ocg_self_gravity")
+
+    def kick(self, vel, acc, dt):
+        self._ck(self.lib.ocg_kick(self.h, _dptr(vel), _dptr(acc), vel.shape[1], float(dt), self._stream()), "ocg_kick")
+
+    def drift(self, pos, vel, dt, vel_to_len=1.0):
+        self._ck(self.lib.ocg_drift(self.h, _dptr(pos), _dptr(vel), pos.shape[1], float(dt), float(vel_to_len),
+                                    self._stream()), "ocg_drift")
+
+    def axpy(self, y, x, a):
+        self._ck(self.lib.ocg_axpy(self.h, _dptr(y), _dptr(x), float(a), y.numel(), self._stream()), "ocg_axpy")
+
+    # ---- host-buffer call (numpy in, numpy out; H2D/D2H inside) ----
+    def field_build_host(self, src_pos, src_mass, src_soft, tgt_pos, center, center_row, kernel, G, want_pot=False):
+        """_populate_grid_acceleration_ (gizmo_interface.py:512-573) in one call. Returns acc [3,n_tgt] (, pot)."""
+        sp = np.ascontiguousarray(src_pos, np.float64).reshape(-1, 3)
+        sm = np.ascontiguousarray(src_mass, np.float64)
+        ss = None if src_soft is None else np.ascontiguousarray(src_soft, np.float64)
+        tp = np.ascontiguousarray(tgt_pos, np.float64).reshape(-1, 3)
+        if sm.shape[0] != sp.shape[0] or (ss is not None and ss.shape[0] != sp.shape[0]):
+            raise OcgError("source position/mass/softening lengths differ: %d / %d / %s"
+                           % (sp.shape[0], sm.shape[0], None if ss is None else ss.shape[0]))
+        acc = np.empty((3, tp.shape[0]), np.float64)
+        pot = np.empty(tp.shape[0], np.float64) if want_pot else None
+        self._ck(self.lib.ocg_field_build_host(self.h, _hptr(sp), _hptr(sm), _hptr(ss), sp.shape[0], _hptr(tp), tp.shape[0],
+                                               _vec3(center), int(center_row), int(kernel), float(G), _hptr(acc),
+                                               _hptr(pot)), "ocg_field_build_host")
+        return (acc, pot) if want_pot else acc
+
+
+_default_ctx = {}
+
+
+def default_context(device=None):
+    """Process-wide ctx per device (LOCAL_RANK-aware)."""
+    if device is None:
+        device = int(os.environ.get("LOCAL_RANK", "0"))
+    if device not in _default_ctx:
+        _default_ctx[device] = Context(device)
+    return _default_ctx[device]

@@ -1,0 +1,179 @@
+"""Cluster N-body code: the B200 drop-in for the AMUSE ``ph4`` worker the reference instantiates in
+oc_code.py:218-229, behind the same gravity-code duck type the driver uses (oc_nbody.py:22-23,28,46-53,70):
+``.particles``, ``.parameters.epsilon_squared``, ``.evolve_model(t)``, ``.stop()``.
+
+Algorithm (BASELINE.json north_star): Plummer-softened direct-sum self-gravity (K4) + kick-drift-kick
+leapfrog (K5) in place of ph4's 4th-order Hermite with block time steps.  State lives in HBM as FP64
+component-major arrays in the field code's unit system (kpc, km/s, Myr, Msun) so that the BRIDGE kick (K3)
+consumes the positions without conversion or host copies.
+
+Also here: ``clean_ejections`` (oc_code.py:231-246) and the bound-subset centre of mass the driver feeds to
+``evolve_grid`` (oc_nbody.py:60-64).
+"""
+import numpy as np
+
+from . import _lib
+from .units import G_KPC_KMS_MYR, KMS_TO_PC_PER_MYR, to_value, units
+
+KMS_TO_KPC_PER_MYR = KMS_TO_PC_PER_MYR * 1e-3
+
+
+class _Parameters(object):
+    """``code.parameters.epsilon_squared = (softening | units.parsec)**2`` (oc_code.py:225-228)."""
+
+    def __init__(self):
+        self._eps2_kpc2 = 0.0
+
+    @property
+    def epsilon_squared(self):
+        return self._eps2_kpc2 | units.kpc ** 2
+
+    @epsilon_squared.setter
+    def epsilon_squared(self, q):
+        v = to_value(q, units.kpc ** 2)
+        if not v >= 0.0:
+            raise ValueError("epsilon_squared must be >= 0")
+        self._eps2_kpc2 = float(v)
+
+
+class ParticleView(object):
+    """Numpy-side view of the particle attributes with AMUSE-like unit-carrying accessors."""
+
+    def __init__(self, mass, pos_kpc, vel_kms, key=None):
+        self._m = np.asarray(mass, np.float64)
+        self._x = np.asarray(pos_kpc, np.float64)
+        self._v = np.asarray(vel_kms, np.float64)
+        self.key = np.arange(self._m.shape[0]) if key is None else np.asarray(key)
+
+    def __len__(self):
+        return self._m.shape[0]
+
+    mass = property(lambda s: s._m | units.MSun)
+    x = property(lambda s: s._x[0] | units.kpc)
+    y = property(lambda s: s._x[1] | units.kpc)
+    z = property(lambda s: s._x[2] | units.kpc)
+    vx = property(lambda s: s._v[0] | units.kms)
+    vy = property(lambda s: s._v[1] | units.kms)
+    vz = property(lambda s: s._v[2] | units.kms)
+    position = property(lambda s: s._x.T | units.kpc)
+    velocity = property(lambda s: s._v.T | units.kms)
+
+    def __getitem__(self, idx):
+        return ParticleView(self._m[idx], self._x[:, idx], self._v[:, idx], self.key[idx])
+
+    def copy(self):
+        return ParticleView(self._m.copy(), self._x.copy(), self._v.copy(), self.key.copy())
+
+    def center_of_mass(self):
+        return (self._x * self._m).sum(axis=1) / self._m.sum() | units.kpc
+
+    def center_of_mass_velocity(self):
+        return (self._v * self._m).sum(axis=1) / self._m.sum() | units.kms
+
+
+class cluster_code(object):
+    """Direct-sum leapfrog cluster integrator on one GPU (or a target shard of one, see distributed.py).
+
+    mass [n] Msun, pos [3,n] kpc, vel [3,n] km/s (floats or unit-carrying); ``softening_pc`` as in
+    oc_code.py:225; ``substeps`` leapfrog steps per evolve_model call (ph4 chooses its own block steps;
+    here the BRIDGE timestep is subdivided evenly)."""
+
+    def __init__(self, mass, pos, vel, softening_pc=0.01, substeps=1, eject_cut=None, ctx=None):
+        import torch
+        self.ctx = ctx or _lib.default_context()
+        self._dev = torch.device("cuda", self.ctx.device)
+        self.parameters = _Parameters()
+        self.parameters.epsilon_squared = (softening_pc | units.parsec) ** 2
+        self.substeps = int(substeps)
+        self.eject_cut = eject_cut  # pc, oc_code.py:241
+        self.G = G_KPC_KMS_MYR
+        self.model_time = 0.0
+        self.key = None
+        self._set_state_(np.asarray(to_value(mass, units.MSun), np.float64), np.asarray(to_value(pos, units.kpc), np.float64),
+                         np.asarray(to_value(vel, units.kms), np.float64))
+
+    # ---- state ----
+    def _set_state_(self, mass, pos, vel, key=None):
+        import torch
+        n = mass.shape[0]
+        if pos.shape != (3, n) or vel.shape != (3, n):
+            raise ValueError("pos and vel must be [3, n] with n = len(mass) = %d" % n)
+        self.n = n
+        self.mass = torch.from_numpy(np.ascontiguousarray(mass)).to(self._dev)
+        self.pos = torch.from_numpy(np.ascontiguousarray(pos)).to(self._dev)
+        self.vel = torch.from_numpy(np.ascontiguousarray(vel)).to(self._dev)
+        self.acc = torch.empty((3, n), dtype=torch.float64, device=self._dev)
+        self.pot = torch.empty(n, dtype=torch.float64, device=self._dev)
+        self.key = np.arange(n) if key is None else np.asarray(key)
+        self._acc_valid = False
+
+    @property
+    def particles(self):
+        return ParticleView(self.mass.cpu().numpy(), self.pos.cpu().numpy(), self.vel.cpu().numpy(), self.key)
+
+    def remove_particles(self, idx):
+        """Drop particles by index (system.particles.remove_particles, oc_code.py:241-242)."""
+        keep = np.ones(self.n, bool)
+        keep[np.asarray(idx, np.int64)] = False
+        p = self.particles
+        self._set_state_(p._m[keep], p._x[:, keep], p._v[:, keep], p.key[keep])
+
+    # ---- gravity ----
+    def compute_self_gravity(self, want_pot=False):
+        """K4 on the current positions -> self.acc (km/s/Myr) and optionally self.pot (kpc km/s/Myr)."""
+        self.ctx.self_gravity(self.pos, self.mass, self.parameters._eps2_kpc2, self.G, self.acc,
+                              self.pot if want_pot else None)
+        self._acc_valid = True
+        return self.acc
+
+    def evolve_model(self, t_end, timestep=None):
+        """Kick-drift-kick leapfrog under self-gravity from model_time to t_end (the BRIDGE drift,
+        oc_nbody.py:56 -> cluster_code.evolve_model)."""
+        t_end = float(to_value(t_end, units.Myr))
+        span = t_end - self.model_time
+        if span <= 0.0:
+            return
+        h = span / self.substeps
+        if not self._acc_valid:
+            self.compute_self_gravity()
+        for _ in range(self.substeps):
+            self.ctx.kick(self.vel, self.acc, 0.5 * h)
+            self.ctx.drift(self.pos, self.vel, h, KMS_TO_KPC_PER_MYR)
+            self.compute_self_gravity()
+            self.ctx.kick(self.vel, self.acc, 0.5 * h)
+        self.model_time = t_end
+
+    def kick_velocities(self, ax, ay, az, dt_myr):
+        """BRIDGE kick from host-side accelerations (generic partner): v += dt * a."""
+        import torch
+        a = np.stack([np.asarray(to_value(c, units.kms / units.Myr), np.float64) for c in (ax, ay, az)])
+        self.ctx.kick(self.vel, torch.from_numpy(np.ascontiguousarray(a)).to(self._dev), dt_myr)
+
+    # ---- driver helpers ----
+    def clean_ejections(self, system=None):
+        """Remove stars farther than `eject_cut` pc from the median position (oc_code.py:231-246)."""
+        if self.eject_cut is None:
+            return None
+        x_pc = self.pos.cpu().numpy().T * 1000.0
+        dist = np.linalg.norm(x_pc - np.median(x_pc, axis=0), axis=1)
+        keys = np.where(dist > float(self.eject_cut))[0]
+        if len(keys):
+            self.remove_particles(keys)
+        return keys
+
+    def bound_center_of_mass(self):
+        """Centre of mass (kpc) of the bound subset: E_i = v_i^2/2 + phi_i < 0 in the cluster's COM frame
+        (oc_nbody.py:60-61: particles.bound_subset().center_of_mass())."""
+        self.compute_self_gravity(want_pot=True)
+        m = self.mass.cpu().numpy()
+        x = self.pos.cpu().numpy()
+        v = self.vel.cpu().numpy()
+        phi = self.pot.cpu().numpy() / KMS_TO_KPC_PER_MYR  # kpc km/s /Myr -> (km/s)^2
+        vc = v - (v * m).sum(axis=1, keepdims=True) / m.sum()
+        bound = 0.5 * (vc * vc).sum(axis=0) + phi < 0.0
+        if not bound.any():
+            bound[:] = True
+        return (x[:, bound] * m[bound]).sum(axis=1) / m[bound].sum()
+
+    def stop(self):
+        pass

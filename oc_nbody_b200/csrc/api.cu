@@ -1,0 +1,400 @@
+// Context, scratch, small element-wise kernels and the host-buffer form of the field build.
+#include "ocg_internal.cuh"
+
+#include <stdarg.h>
+#include <stdlib.h>
+
+static char g_create_err[512] = "";
+
+int ocg_fail(ocg_ctx* ctx, int code, const char* fmt, ...) {
+  char* dst = ctx ? ctx->err : g_create_err;
+  size_t cap = ctx ? sizeof(ctx->err) : sizeof(g_create_err);
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(dst, cap, fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+int ocg_scratch(ocg_ctx* ctx, int which, size_t bytes, void** out) {
+  if (bytes == 0) bytes = 256;
+  if (ctx->scratch_bytes[which] < bytes) {
+    if (ctx->scratch[which]) {
+      // buffers may still be in use by queued kernels: the free is stream-ordered by the runtime
+      // only after a device sync, so synchronise before releasing
+      cudaDeviceSynchronize();
+      cudaFree(ctx->scratch[which]);
+      ctx->scratch[which] = nullptr;
+      ctx->scratch_bytes[which] = 0;
+    }
+    size_t want = bytes + bytes / 8;  // head-room to avoid re-growing on small size changes
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      e = cudaMalloc(&p, bytes);
+      want = bytes;
+    }
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      return ocg_fail(ctx, OCG_ERR_NOMEM, "cudaMalloc of %zu bytes for scratch %d failed: %s", bytes,
+                      which, cudaGetErrorString(e));
+    }
+    ctx->scratch[which] = p;
+    ctx->scratch_bytes[which] = want;
+  }
+  *out = ctx->scratch[which];
+  return OCG_OK;
+}
+
+extern "C" int ocg_version(void) { return OCG_VERSION; }
+
+extern "C" int ocg_create(int device, ocg_ctx** out) {
+  if (!out) return ocg_fail(nullptr, OCG_ERR_INVALID, "ocg_create: out is NULL");
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return ocg_fail(nullptr, OCG_ERR_NODEVICE, "no CUDA device visible (%s); this library has no CPU fallback",
+                    e == cudaSuccess ? "count = 0" : cudaGetErrorString(e));
+  }
+  if (device < 0 || device >= ndev)
+    return ocg_fail(nullptr, OCG_ERR_INVALID, "device %d out of range [0,%d)", device, ndev);
+  cudaDeviceProp prop;
+  if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess)
+    return ocg_fail(nullptr, OCG_ERR_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+  if (prop.major < 10)
+    return ocg_fail(nullptr, OCG_ERR_NODEVICE,
+                    "device %d is sm_%d%d; this library is built for sm_100a (B200) only", device,
+                    prop.major, prop.minor);
+  ocg_ctx* ctx = (ocg_ctx*)calloc(1, sizeof(ocg_ctx));
+  if (!ctx) return ocg_fail(nullptr, OCG_ERR_NOMEM, "calloc failed");
+  ctx->device = device;
+  ctx->sm_count = prop.multiProcessorCount;
+  int khz = 0;
+  cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, device);
+  ctx->sm_clock_khz = khz;
+  ctx->global_mem = prop.totalGlobalMem;
+  OcgDeviceGuard g(device);
+  if ((e = cudaEventCreate(&ctx->ev0)) != cudaSuccess || (e = cudaEventCreate(&ctx->ev1)) != cudaSuccess) {
+    free(ctx);
+    return ocg_fail(nullptr, OCG_ERR_CUDA, "cudaEventCreate: %s", cudaGetErrorString(e));
+  }
+  *out = ctx;
+  return OCG_OK;
+}
+
+extern "C" int ocg_destroy(ocg_ctx* ctx) {
+  if (!ctx) return OCG_OK;
+  OcgDeviceGuard g(ctx->device);
+  cudaDeviceSynchronize();
+  for (int i = 0; i < OCG_SCR_N; ++i)
+    if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
+  cudaEventDestroy(ctx->ev0);
+  cudaEventDestroy(ctx->ev1);
+  free(ctx->items_host);
+  free(ctx);
+  return OCG_OK;
+}
+
+extern "C" const char* ocg_last_error(const ocg_ctx* ctx) { return ctx ? ctx->err : g_create_err; }
+
+extern "C" int ocg_device_info(ocg_ctx* ctx, int* sm_count, int* sm_clock_khz, int64_t* global_mem_bytes) {
+  if (!ctx) return OCG_ERR_INVALID;
+  if (sm_count) *sm_count = ctx->sm_count;
+  if (sm_clock_khz) *sm_clock_khz = ctx->sm_clock_khz;
+  if (global_mem_bytes) *global_mem_bytes = (int64_t)ctx->global_mem;
+  return OCG_OK;
+}
+
+extern "C" int64_t ocg_launch_count(const ocg_ctx* ctx) { return ctx ? ctx->launches : -1; }
+
+extern "C" int ocg_set_kernel_timing(ocg_ctx* ctx, int enabled) {
+  if (!ctx) return OCG_ERR_INVALID;
+  ctx->timing = enabled ? 1 : 0;
+  ctx->ev_valid = 0;
+  return OCG_OK;
+}
+
+extern "C" double ocg_last_direct_kernel_ms(ocg_ctx* ctx) {
+  if (!ctx || !ctx->ev_valid) return -1.0;
+  OcgDeviceGuard g(ctx->device);
+  if (cudaEventSynchronize(ctx->ev1) != cudaSuccess) return -1.0;
+  float ms = 0.f;
+  if (cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1) != cudaSuccess) return -1.0;
+  return (double)ms;
+}
+
+// ---------------------------------------------------------------------------- K0 kernels ----
+__global__ void recentre_kernel(const double* __restrict__ pos, const double* __restrict__ mass,
+                                long long n, double cx, double cy, double cz,
+                                float4* __restrict__ out) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  // subtraction in FP64 *before* rounding to FP32: |x - c| << |x|
+  float x = (float)(pos[3 * i + 0] - cx);
+  float y = (float)(pos[3 * i + 1] - cy);
+  float z = (float)(pos[3 * i + 2] - cz);
+  float m = mass ? (float)mass[i] : 0.f;
+  out[i] = make_float4(x, y, z, m);
+}
+
+__global__ void cast_kernel(const double* __restrict__ in, long long n, float* __restrict__ out) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (float)in[i];
+}
+
+static inline int nblocks(long long n, int b) { return (int)((n + b - 1) / b); }
+
+extern "C" int ocg_recentre_f64(ocg_ctx* ctx, const double* pos_dev, const double* mass_dev, int64_t n,
+                                const double center[3], float* out_xyzw_dev, void* stream) {
+  if (!ctx) return OCG_ERR_INVALID;
+  if (n < 0 || (n > 0 && (!pos_dev || !out_xyzw_dev || !center)))
+    return ocg_fail(ctx, OCG_ERR_INVALID, "ocg_recentre_f64: bad arguments");
+  if (n == 0) return OCG_OK;
+  OcgDeviceGuard g(ctx->device);
+  recentre_kernel<<<nblocks(n, 256), 256, 0, (cudaStream_t)stream>>>(
+      pos_dev, mass_dev, n, center[0], center[1], center[2], reinterpret_cast<float4*>(out_xyzw_dev));
+  OCG_CHECK_LAUNCH(ctx, "recentre_kernel");
+  return OCG_OK;
+}
+
+extern "C" int ocg_cast_f64_f32(ocg_ctx* ctx, const double* in_dev, int64_t n, float* out_dev, void* stream) {
+  if (!ctx) return OCG_ERR_INVALID;
+  if (n < 0 || (n > 0 && (!in_dev || !out_dev))) return ocg_fail(ctx, OCG_ERR_INVALID, "ocg_cast_f64_f32: bad arguments");
+  if (n == 0) return OCG_OK;
+  OcgDeviceGuard g(ctx->device);
+  cast_kernel<<<nblocks(n, 256), 256, 0, (cudaStream_t)stream>>>(in_dev, n, out_dev);
+  OCG_CHECK_LAUNCH(ctx, "cast_kernel");
+  return OCG_OK;
+}
+
+// ------------------------------------------------------------------------------------ K1 ----
+extern "C" int ocg_field_direct(ocg_ctx* ctx, const float* src_xyzm_dev, const float* src_soft_dev,
+                                int64_t n_src, const float* tgt_xyzw_dev, int64_t n_tgt, int kernel,
+                                double G, double* acc_dev, double* pot_dev, int accumulate, void* stream) {
+  if (!ctx) return OCG_ERR_INVALID;
+  if (n_src < 0 || n_tgt < 0) return ocg_fail(ctx, OCG_ERR_INVALID, "ocg_field_direct: negative size");
+  if (kernel != OCG_KERNEL_PLUMMER && kernel != OCG_KERNEL_SPLINE)
+    return ocg_fail(ctx, OCG_ERR_INVALID, "ocg_field_direct: unknown softening kernel %d", kernel);
+  if (n_tgt > 0 && (!tgt_xyzw_dev || !acc_dev)) return ocg_fail(ctx, OCG_ERR_INVALID, "ocg_field_direct: NULL target/output");
+  if (n_src > 0 && !src_xyzm_dev) return ocg_fail(ctx, OCG_ERR_INVALID, "ocg_field_direct: NULL sources");
+  OcgDeviceGuard g(ctx->device);
+  return ocg_direct_sum_impl(ctx, src_xyzm_dev, src_soft_dev, n_src, tgt_xyzw_dev, n_tgt, kernel, G,
+                             acc_dev, pot_dev, accumulate, (cudaStream_t)stream);
+}
+
+// ----------------------------------------------------------------------------------- K1b ----
+__global__ void frame_subtract_kernel(double* acc, long long n, long long row) {
+  __shared__ double c[3];
+  if (threadIdx.x < 3) c[threadIdx.x] = acc[threadIdx.x * n + row];
+  __syncthreads();
+  // every block reads the centre row before anyone overwrites it only if the row's own block does
+  // not race: the centre row is written last by construction (handled by the second kernel).
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= n || i == row) return;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) acc[k * n + i] = __dsub_rn(acc[k * n + i], c[k]);
+}
+__global__ void frame_zero_row_kernel(double* acc, long long n, long long row) {
+  if (threadIdx.x < 3) acc[threadIdx.x * n + row] = 0.0;  // x - x == 0 exactly
+}
+
+extern "C" int ocg_frame_subtract(ocg_ctx* ctx, double* acc_dev, int64_t n_tgt, int64_t center_row, void* stream) {
+  if (!ctx) return OCG_ERR_INVALID;
+  if (n_tgt <= 0) return OCG_OK;
+  if (!acc_dev || center_row < 0 || center_row >= n_tgt)
+    return ocg_fail(ctx, OCG_ERR_INVALID, "ocg_frame_subtract: centre row %lld outside [0,%lld)",
+                    (long long)center_row, (long long)n_tgt);
+  OcgDeviceGuard g(ctx->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  frame_subtract_kernel<<<nblocks(n_tgt, 256), 256, 0, st>>>(acc_dev, n_tgt, center_row);
+  OCG_CHECK_LAUNCH(ctx, "frame_subtract_kernel");
+  frame_zero_row_kernel<<<1, 32, 0, st>>>(acc_dev, n_tgt, center_row);
+  OCG_CHECK_LAUNCH(ctx, "frame_zero_row_kernel");
+  return OCG_OK;
+}
+
+// --------------------------------------------------------------- K1 host form (e2e path) ----
+extern "C" int ocg_field_build_host(ocg_ctx* ctx, const double* src_pos_host, const double* src_mass_host,
+                                    const double* src_soft_host, int64_t n_src, const double* tgt_pos_host,
+                                    int64_t n_tgt, const double center[3], int64_t center_row, int kernel,
+                                    double G, double* acc_host, double* pot_host) {
+  if (!ctx) return OCG_ERR_INVALID;
+  if (n_src < 0 || n_tgt < 0) return ocg_fail(ctx, OCG_ERR_INVALID, "ocg_field_build_host: negative size");
+  if (n_tgt == 0) return OCG_OK;
+  if (!tgt_pos_host || !acc_host || !center || (n_src > 0 && (!src_pos_host || !src_mass_host)))
+    return ocg_fail(ctx, OCG_ERR_INVALID, "ocg_field_build_host: NULL argument");
+  if (center_row >= n_tgt) return ocg_fail(ctx, OCG_ERR_INVALID, "ocg_field_build_host: centre row out of range");
+  if (kernel != OCG_KERNEL_PLUMMER && kernel != OCG_KERNEL_SPLINE)
+    return ocg_fail(ctx, OCG_ERR_INVALID, "ocg_field_build_host: unknown softening kernel %d", kernel);
+  OcgDeviceGuard g(ctx->device);
+  cudaStream_t st = 0;
+  double *d_pos, *d_mass, *d_soft = nullptr, *d_tpos, *d_out;
+  float *d_src, *d_sft = nullptr, *d_tgt;
+  int rc;
+  const int NCO = pot_host ? 4 : 3;
+  if ((rc = ocg_scratch(ctx, OCG_SCR_F64A, sizeof(double) * 3 * (size_t)(n_src > n_tgt ? n_src : n_tgt), (void**)&d_pos))) return rc;
+  if ((rc = ocg_scratch(ctx, OCG_SCR_F64B, sizeof(double) * (size_t)(n_src > 0 ? n_src : 1), (void**)&d_mass))) return rc;
+  if ((rc = ocg_scratch(ctx, OCG_SCR_SRC, sizeof(float) * 4 * (size_t)(n_src > 0 ? n_src : 1), (void**)&d_src))) return rc;
+  if ((rc = ocg_scratch(ctx, OCG_SCR_TGT, sizeof(float) * 4 * (size_t)n_tgt, (void**)&d_tgt))) return rc;
+  if ((rc = ocg_scratch(ctx, OCG_SCR_OUT, sizeof(double) * NCO * (size_t)n_tgt, (void**)&d_out))) return rc;
+  if (n_src > 0) {
+    OCG_CUDA(ctx, cudaMemcpyAsync(d_pos, src_pos_host, sizeof(double) * 3 * n_src, cudaMemcpyHostToDevice, st));
+    OCG_CUDA(ctx, cudaMemcpyAsync(d_mass, src_mass_host, sizeof(double) * n_src, cudaMemcpyHostToDevice, st));
+    if ((rc = ocg_recentre_f64(ctx, d_pos, d_mass, n_src, center, d_src, st))) return rc;
+    if (src_soft_host) {
+      if ((rc = ocg_scratch(ctx, OCG_SCR_F64C, sizeof(double) * (size_t)n_src, (void**)&d_soft))) return rc;
+      if ((rc = ocg_scratch(ctx, OCG_SCR_SOFT, sizeof(float) * (size_t)n_src, (void**)&d_sft))) return rc;
+      OCG_CUDA(ctx, cudaMemcpyAsync(d_soft, src_soft_host, sizeof(double) * n_src, cudaMemcpyHostToDevice, st));
+      if ((rc = ocg_cast_f64_f32(ctx, d_soft, n_src, d_sft, st))) return rc;
+    }
+  }
+  // targets reuse the FP64 staging buffer after the source recentre kernel has consumed it (same stream)
+  d_tpos = d_pos;
+  OCG_CUDA(ctx, cudaMemcpyAsync(d_tpos, tgt_pos_host, sizeof(double) * 3 * n_tgt, cudaMemcpyHostToDevice, st));
+  if ((rc = ocg_recentre_f64(ctx, d_tpos, nullptr, n_tgt, center, d_tgt, st))) return rc;
+  double* d_pot = pot_host ? d_out + 3 * n_tgt : nullptr;
+  if ((rc = ocg_direct_sum_impl(ctx, d_src, d_sft, n_src, d_tgt, n_tgt, kernel, G, d_out, d_pot, 0, st))) return rc;
+  if (center_row >= 0 && (rc = ocg_frame_subtract(ctx, d_out, n_tgt, center_row, st))) return rc;
+  OCG_CUDA(ctx, cudaMemcpyAsync(acc_host, d_out, sizeof(double) * 3 * n_tgt, cudaMemcpyDeviceToHost, st));
+  if (pot_host) OCG_CUDA(ctx, cudaMemcpyAsync(pot_host, d_pot, sizeof(double) * n_tgt, cudaMemcpyDeviceToHost, st));
+  OCG_CUDA(ctx, cudaStreamSynchronize(st));
+  return OCG_OK;
+}
+
+// ------------------------------------------------------------------------------------ K5 ----
+__global__ void kick_kernel(double* __restrict__ vel, const double* __restrict__ acc, long long n3, double dt) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i < n3) vel[i] = __dadd_rn(vel[i], __dmul_rn(acc[i], dt));
+}
+__global__ void drift_kernel(double* __restrict__ pos, const double* __restrict__ vel, long long n3, double dt,
+                             double vel_to_len) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i < n3) pos[i] = __dadd_rn(pos[i], __dmul_rn(__dmul_rn(vel[i], dt), vel_to_len));
+}
+__global__ void axpy_kernel(double* __restrict__ y, const double* __restrict__ x, double a, long long n) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i < n) y[i] = __dadd_rn(y[i], __dmul_rn(a, x[i]));
+}
+
+extern "C" int ocg_kick(ocg_ctx* ctx, double* vel_dev, const double* acc_dev, int64_t n, double dt, void* stream) {
+  if (!ctx) return OCG_ERR_INVALID;
+  if (n < 0 || (n > 0 && (!vel_dev || !acc_dev))) return ocg_fail(ctx, OCG_ERR_INVALID, "ocg_kick: bad arguments");
+  if (n == 0) return OCG_OK;
+  OcgDeviceGuard g(ctx->device);
+  kick_kernel<<<nblocks(3 * n, 256), 256, 0, (cudaStream_t)stream>>>(vel_dev, acc_dev, 3 * n, dt);
+  OCG_CHECK_LAUNCH(ctx, "kick_kernel");
+  return OCG_OK;
+}
+extern "C" int ocg_drift(ocg_ctx* ctx, double* pos_dev, const double* vel_dev, int64_t n, double dt,
+                         double vel_to_len, void* stream) {
+  if (!ctx) return OCG_ERR_INVALID;
+  if (n < 0 || (n > 0 && (!pos_dev || !vel_dev))) return ocg_fail(ctx, OCG_ERR_INVALID, "ocg_drift: bad arguments");
+  if (n == 0) return OCG_OK;
+  OcgDeviceGuard g(ctx->device);
+  drift_kernel<<<nblocks(3 * n, 256), 256, 0, (cudaStream_t)stream>>>(pos_dev, vel_dev, 3 * n, dt, vel_to_len);
+  OCG_CHECK_LAUNCH(ctx, "drift_kernel");
+  return OCG_OK;
+}
+extern "C" int ocg_axpy(ocg_ctx* ctx, double* y_dev, const double* x_dev, double a, int64_t n, void* stream) {
+  if (!ctx) return OCG_ERR_INVALID;
+  if (n < 0 || (n > 0 && (!y_dev || !x_dev))) return ocg_fail(ctx, OCG_ERR_INVALID, "ocg_axpy: bad arguments");
+  if (n == 0) return OCG_OK;
+  OcgDeviceGuard g(ctx->device);
+  axpy_kernel<<<nblocks(n, 256), 256, 0, (cudaStream_t)stream>>>(y_dev, x_dev, a, n);
+  OCG_CHECK_LAUNCH(ctx, "axpy_kernel");
+  return OCG_OK;
+}
+
+// -------------------------------------------------------------------------------- probes ----
+// Pure-issue micro-benchmarks: the "measured FP32 peak" the roofline fraction is quoted against.
+__global__ void __launch_bounds__(256) probe_ffma_kernel(float* out, int iters) {
+  float a[8], b = 1.0000001f + threadIdx.x * 1e-9f, c = 1e-9f;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) a[k] = threadIdx.x * 1e-6f + k;
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+#pragma unroll
+      for (int k = 0; k < 8; ++k) a[k] = fmaf(a[k], b, c);
+  }
+  float s = 0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) s += a[k];
+  if (s == 123.456f) out[0] = s;
+}
+__global__ void __launch_bounds__(256) probe_ffma2_kernel(float* out, int iters) {
+  unsigned long long a[8], b, c;
+  float bf = 1.0000001f + threadIdx.x * 1e-9f, cf = 1e-9f;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(b) : "f"(bf), "f"(bf * 1.0000001f));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(c) : "f"(cf), "f"(cf * 2.f));
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    float v = threadIdx.x * 1e-6f + k;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(a[k]) : "f"(v), "f"(v + 0.5f));
+  }
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+#pragma unroll
+      for (int k = 0; k < 8; ++k) asm volatile("fma.rn.ftz.f32x2 %0, %0, %1, %2;" : "+l"(a[k]) : "l"(b), "l"(c));
+  }
+  unsigned long long s = 0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) s ^= a[k];
+  if (s == 0x123456789ull) out[0] = (float)s;
+}
+__global__ void __launch_bounds__(256) probe_rsq_kernel(float* out, int iters) {
+  float a[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) a[k] = 1.0f + threadIdx.x * 1e-3f + k;
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+#pragma unroll
+      for (int k = 0; k < 8; ++k) asm volatile("rsqrt.approx.ftz.f32 %0, %0;" : "+f"(a[k]));
+  }
+  float s = 0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) s += a[k];
+  if (s == 123.456f) out[0] = s;
+}
+
+extern "C" double ocg_probe_throughput(ocg_ctx* ctx, int which) {
+  if (!ctx) return -1.0;
+  OcgDeviceGuard g(ctx->device);
+  float* d_out;
+  if (ocg_scratch(ctx, OCG_SCR_MISC, 256, (void**)&d_out)) return -1.0;
+  const int iters = which == 2 ? 2000 : 8000;
+  const int grid = ctx->sm_count * 8, block = 256;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  double best = 0.0;
+  for (int rep = 0; rep < 4; ++rep) {
+    cudaEventRecord(e0, 0);
+    if (which == 0) probe_ffma_kernel<<<grid, block>>>(d_out, iters);
+    else if (which == 1) probe_ffma2_kernel<<<grid, block>>>(d_out, iters);
+    else probe_rsq_kernel<<<grid, block>>>(d_out, iters);
+    cudaEventRecord(e1, 0);
+    if (cudaEventSynchronize(e1) != cudaSuccess) {
+      ocg_fail(ctx, OCG_ERR_CUDA, "probe kernel failed: %s", cudaGetErrorString(cudaGetLastError()));
+      best = -1.0;
+      break;
+    }
+    ctx->launches++;
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    double ops = (double)grid * block * (double)iters * 64.0;  // lane-instructions
+    double rate;
+    if (which == 0) rate = ops * 2.0 / (ms * 1e-3) / 1e12;        // TFLOP/s
+    else if (which == 1) rate = ops * 4.0 / (ms * 1e-3) / 1e12;   // TFLOP/s (2 FMAs per lane-instr)
+    else rate = ops / (ms * 1e-3) / 1e9;                          // G rsqrt/s
+    if (rep > 0 && rate > best) best = rate;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  return best;
+}

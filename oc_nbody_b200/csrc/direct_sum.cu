@@ -1,0 +1,821 @@
+// K1 / K4: softened pairwise gravity as a direct sum, hand-written for sm_100a.
+//
+// Replaces the field-build hot loop of the reference, ConstructKDTree + GetAccelParallel
+// (gizmo_interface.py:561,564,566 — a theta=0.5 monopole tree in un-vendored pykdgrav), with the
+// exact theta->0 sum, and the ph4 force loop behind oc_code.py:218-229.
+//
+// Design:
+//  * sources are re-laid once per call into component-major tiles (x|y|z|m|e2, OCG_TS each) and
+//    split into a FAST set (every target sees them as Plummer(e2) or pure Newtonian) and a NEAR set
+//    (spline sources whose support can reach the target box; singular e2==0 sources inside it);
+//  * the fast kernel streams tiles through a 4-stage shared-memory ring filled by one TMA bulk
+//    copy per tile (cp.async.bulk + mbarrier), a dedicated producer warp, 8 consumer warps;
+//  * the inner loop is packed FP32: FADD2/FFMA2/FMUL2 on two sources at a time + 2 MUFU.RSQ,
+//    12 FMA-pipe instructions per 2 interactions; FP32 partial sums live for one tile (512
+//    sources) and are folded into FP64 per-target accumulators;
+//  * work = (target tile x source chunk) items, statically strided over a persistent grid of
+//    2 CTAs/SM; chunk partials are summed in fixed order by a finish kernel => deterministic.
+#include "ocg_internal.cuh"
+
+#include <math.h>
+
+typedef unsigned long long u64;
+
+// ---------------------------------------------------------------- packed-fp32 + PTX helpers ----
+__device__ __forceinline__ u64 f2_pack(float lo, float hi) {
+  u64 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void f2_unpack(u64 v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ u64 f2_fma(u64 a, u64 b, u64 c) {
+  u64 d;
+  asm("fma.rn.ftz.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ u64 f2_add(u64 a, u64 b) {
+  u64 d;
+  asm("add.rn.ftz.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ u64 f2_mul(u64 a, u64 b) {
+  u64 d;
+  asm("mul.rn.ftz.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ float rsqrt_approx(float x) {
+  float y;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+// TMA 1-D bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP).
+__device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes,
+                                             uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+          "r"(smem_u32(dst_smem)),
+      "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+
+template <int TPT>
+__device__ __forceinline__ void decode_item(const DirectParams& p, int item, long long& tgt_begin,
+                                            int& tgt_count, long long& tile_begin, int& tile_count,
+                                            long long& slot) {
+  if (p.items) {
+    OcgWorkItem w = p.items[item];
+    tgt_begin = w.tgt_begin;
+    tgt_count = w.tgt_count;
+    tile_begin = w.tile_begin;
+    tile_count = w.tile_count;
+    slot = w.out_slot;
+  } else {
+    const int CT = OCG_CONSUMER_THREADS * TPT;
+    int chunk = item / p.n_ttiles;
+    int tt = item - chunk * p.n_ttiles;
+    tgt_begin = (long long)tt * CT;
+    long long rem = p.n_tgt - tgt_begin;
+    tgt_count = rem < CT ? (int)rem : CT;
+    tile_begin = (long long)chunk * p.tiles_per_chunk;
+    long long avail = (long long)(*p.n_fast_tiles) - tile_begin;
+    tile_count = avail <= 0 ? 0 : (avail < p.tiles_per_chunk ? (int)avail : p.tiles_per_chunk);
+    slot = chunk;
+  }
+}
+
+// ------------------------------------------------------------------------- the fast kernel ----
+// TPT   : targets per consumer thread
+// POT   : also accumulate the potential (4th component)
+// GUARD : tolerate r2 + e2 == 0 (self pairs when eps2 == 0): such pairs contribute nothing
+template <int TPT, bool POT, bool GUARD>
+__global__ void __launch_bounds__(OCG_CTA_THREADS, 2) direct_sum_kernel(const DirectParams p) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float* stage_base = reinterpret_cast<float*>(smem_raw);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_raw + OCG_NSTAGE * OCG_TILE_BYTES);
+  uint64_t* empty_bar = full_bar + OCG_NSTAGE;
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  const int lane = tid & 31;
+  constexpr int NC = POT ? 4 : 3;
+
+  if (tid == 0) {
+    for (int s = 0; s < OCG_NSTAGE; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], OCG_CONSUMER_WARPS);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  uint32_t it = 0;  // running tile counter: stage = it % NSTAGE, phase = (it / NSTAGE) & 1
+
+  if (warp == OCG_CONSUMER_WARPS) {
+    // ===== TMA producer warp: one elected lane streams source tiles into the ring =====
+    if (lane == 0) {
+      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+        long long tgt_begin, tile_begin, slot;
+        int tgt_count, tile_count;
+        decode_item<TPT>(p, item, tgt_begin, tgt_count, tile_begin, tile_count, slot);
+        const float* src = p.tiles + tile_begin * (long long)OCG_TILE_FLOATS;
+        for (int k = 0; k < tile_count; ++k, ++it) {
+          const uint32_t s = it % OCG_NSTAGE;
+          const uint32_t ph = (it / OCG_NSTAGE) & 1u;
+          mbar_wait(&empty_bar[s], ph ^ 1u);
+          mbar_expect_tx(&full_bar[s], OCG_TILE_BYTES);
+          tma_bulk_g2s(stage_base + s * OCG_TILE_FLOATS, src + (long long)k * OCG_TILE_FLOATS,
+                       OCG_TILE_BYTES, &full_bar[s]);
+        }
+      }
+    }
+    return;
+  }
+
+  // ===== consumer warps =====
+  for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+    long long tgt_begin, tile_begin, slot;
+    int tgt_count, tile_count;
+    decode_item<TPT>(p, item, tgt_begin, tgt_count, tile_begin, tile_count, slot);
+
+    // negated, duplicated target coordinates: dx = xs + (-xt)
+    u64 ntx[TPT], nty[TPT], ntz[TPT];
+    double dacc[TPT][NC];
+#pragma unroll
+    for (int t = 0; t < TPT; ++t) {
+      int local = t * OCG_CONSUMER_THREADS + tid;
+      long long gi = tgt_begin + (local < tgt_count ? local : tgt_count - 1);
+      float4 T = __ldg(&p.tgt[gi]);
+      ntx[t] = f2_pack(-T.x, -T.x);
+      nty[t] = f2_pack(-T.y, -T.y);
+      ntz[t] = f2_pack(-T.z, -T.z);
+#pragma unroll
+      for (int c = 0; c < NC; ++c) dacc[t][c] = 0.0;
+    }
+
+    for (int k = 0; k < tile_count; ++k, ++it) {
+      const uint32_t s = it % OCG_NSTAGE;
+      const uint32_t ph = (it / OCG_NSTAGE) & 1u;
+      mbar_wait(&full_bar[s], ph);
+
+      const float4* sx = reinterpret_cast<const float4*>(stage_base + s * OCG_TILE_FLOATS);
+      const float4* sy = sx + OCG_TS / 4;
+      const float4* sz = sy + OCG_TS / 4;
+      const float4* sm = sz + OCG_TS / 4;
+      const float4* se = sm + OCG_TS / 4;
+
+      u64 ax[TPT], ay[TPT], az[TPT], ap[TPT];
+#pragma unroll
+      for (int t = 0; t < TPT; ++t) ax[t] = ay[t] = az[t] = ap[t] = 0ull;
+
+#pragma unroll 2
+      for (int j = 0; j < OCG_TS / 4; ++j) {
+        const float4 X = sx[j], Y = sy[j], Z = sz[j], M = sm[j], E = se[j];
+        u64 xs[2] = {f2_pack(X.x, X.y), f2_pack(X.z, X.w)};
+        u64 ys[2] = {f2_pack(Y.x, Y.y), f2_pack(Y.z, Y.w)};
+        u64 zs[2] = {f2_pack(Z.x, Z.y), f2_pack(Z.z, Z.w)};
+        u64 ms[2] = {f2_pack(M.x, M.y), f2_pack(M.z, M.w)};
+        u64 es[2] = {f2_pack(E.x, E.y), f2_pack(E.z, E.w)};
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+#pragma unroll
+          for (int t = 0; t < TPT; ++t) {
+            u64 dx = f2_add(xs[q], ntx[t]);
+            u64 dy = f2_add(ys[q], nty[t]);
+            u64 dz = f2_add(zs[q], ntz[t]);
+            u64 r2 = f2_fma(dx, dx, es[q]);
+            r2 = f2_fma(dy, dy, r2);
+            r2 = f2_fma(dz, dz, r2);
+            float r2a, r2b;
+            f2_unpack(r2, r2a, r2b);
+            float ria, rib;
+            if (GUARD) {
+              ria = r2a > 0.f ? rsqrt_approx(r2a) : 0.f;
+              rib = r2b > 0.f ? rsqrt_approx(r2b) : 0.f;
+            } else {
+              ria = rsqrt_approx(r2a);
+              rib = rsqrt_approx(r2b);
+            }
+            u64 ri = f2_pack(ria, rib);
+            u64 ri2 = f2_mul(ri, ri);
+            u64 mri = f2_mul(ms[q], ri);
+            u64 sc = f2_mul(mri, ri2);
+            ax[t] = f2_fma(dx, sc, ax[t]);
+            ay[t] = f2_fma(dy, sc, ay[t]);
+            az[t] = f2_fma(dz, sc, az[t]);
+            if (POT) ap[t] = f2_add(ap[t], mri);
+          }
+        }
+      }
+
+      // this warp is done reading stage s: hand it back to the producer
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty_bar[s]);
+
+      // fold the tile's FP32 partial sums into the FP64 accumulators
+#pragma unroll
+      for (int t = 0; t < TPT; ++t) {
+        float lo, hi;
+        f2_unpack(ax[t], lo, hi);
+        dacc[t][0] += (double)lo + (double)hi;
+        f2_unpack(ay[t], lo, hi);
+        dacc[t][1] += (double)lo + (double)hi;
+        f2_unpack(az[t], lo, hi);
+        dacc[t][2] += (double)lo + (double)hi;
+        if (POT) {
+          f2_unpack(ap[t], lo, hi);
+          dacc[t][NC - 1] -= (double)lo + (double)hi;
+        }
+      }
+    }
+
+#pragma unroll
+    for (int t = 0; t < TPT; ++t) {
+      int local = t * OCG_CONSUMER_THREADS + tid;
+      if (local < tgt_count) {
+        long long gi = tgt_begin + local;
+#pragma unroll
+        for (int c = 0; c < NC; ++c)
+          p.partial[(slot * NC + c) * p.out_stride + gi] = dacc[t][c];
+      }
+    }
+  }
+}
+
+// --------------------------------------------------------------------- scalar FP32 variant ----
+// Same structure with plain FADD/FFMA/FMUL (13 issue slots per interaction). Kept as the
+// measured baseline the packed kernel is compared against (bench.py --variant scalar).
+template <int TPT, bool POT, bool GUARD>
+__global__ void __launch_bounds__(OCG_CTA_THREADS, 2) direct_sum_scalar_kernel(const DirectParams p) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float* stage_base = reinterpret_cast<float*>(smem_raw);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_raw + OCG_NSTAGE * OCG_TILE_BYTES);
+  uint64_t* empty_bar = full_bar + OCG_NSTAGE;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  constexpr int NC = POT ? 4 : 3;
+  if (tid == 0) {
+    for (int s = 0; s < OCG_NSTAGE; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], OCG_CONSUMER_WARPS);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  uint32_t it = 0;
+  if (warp == OCG_CONSUMER_WARPS) {
+    if (lane == 0) {
+      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+        long long tgt_begin, tile_begin, slot;
+        int tgt_count, tile_count;
+        decode_item<TPT>(p, item, tgt_begin, tgt_count, tile_begin, tile_count, slot);
+        const float* src = p.tiles + tile_begin * (long long)OCG_TILE_FLOATS;
+        for (int k = 0; k < tile_count; ++k, ++it) {
+          const uint32_t s = it % OCG_NSTAGE, ph = (it / OCG_NSTAGE) & 1u;
+          mbar_wait(&empty_bar[s], ph ^ 1u);
+          mbar_expect_tx(&full_bar[s], OCG_TILE_BYTES);
+          tma_bulk_g2s(stage_base + s * OCG_TILE_FLOATS, src + (long long)k * OCG_TILE_FLOATS,
+                       OCG_TILE_BYTES, &full_bar[s]);
+        }
+      }
+    }
+    return;
+  }
+  for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+    long long tgt_begin, tile_begin, slot;
+    int tgt_count, tile_count;
+    decode_item<TPT>(p, item, tgt_begin, tgt_count, tile_begin, tile_count, slot);
+    float tx[TPT], ty[TPT], tz[TPT];
+    double dacc[TPT][NC];
+#pragma unroll
+    for (int t = 0; t < TPT; ++t) {
+      int local = t * OCG_CONSUMER_THREADS + tid;
+      long long gi = tgt_begin + (local < tgt_count ? local : tgt_count - 1);
+      float4 T = __ldg(&p.tgt[gi]);
+      tx[t] = T.x, ty[t] = T.y, tz[t] = T.z;
+#pragma unroll
+      for (int c = 0; c < NC; ++c) dacc[t][c] = 0.0;
+    }
+    for (int k = 0; k < tile_count; ++k, ++it) {
+      const uint32_t s = it % OCG_NSTAGE, ph = (it / OCG_NSTAGE) & 1u;
+      mbar_wait(&full_bar[s], ph);
+      const float4* sx = reinterpret_cast<const float4*>(stage_base + s * OCG_TILE_FLOATS);
+      const float4* sy = sx + OCG_TS / 4;
+      const float4* sz = sy + OCG_TS / 4;
+      const float4* sm = sz + OCG_TS / 4;
+      const float4* se = sm + OCG_TS / 4;
+      float ax[TPT], ay[TPT], az[TPT], ap[TPT];
+#pragma unroll
+      for (int t = 0; t < TPT; ++t) ax[t] = ay[t] = az[t] = ap[t] = 0.f;
+#pragma unroll 2
+      for (int j = 0; j < OCG_TS / 4; ++j) {
+        const float4 X = sx[j], Y = sy[j], Z = sz[j], M = sm[j], E = se[j];
+        const float xs[4] = {X.x, X.y, X.z, X.w}, ys[4] = {Y.x, Y.y, Y.z, Y.w};
+        const float zs[4] = {Z.x, Z.y, Z.z, Z.w}, ms[4] = {M.x, M.y, M.z, M.w};
+        const float es[4] = {E.x, E.y, E.z, E.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+#pragma unroll
+          for (int t = 0; t < TPT; ++t) {
+            float dx = xs[q] - tx[t], dy = ys[q] - ty[t], dz = zs[q] - tz[t];
+            float r2 = fmaf(dx, dx, es[q]);
+            r2 = fmaf(dy, dy, r2);
+            r2 = fmaf(dz, dz, r2);
+            float ri = GUARD ? (r2 > 0.f ? rsqrt_approx(r2) : 0.f) : rsqrt_approx(r2);
+            float ri2 = ri * ri;
+            float mri = ms[q] * ri;
+            float sc = mri * ri2;
+            ax[t] = fmaf(dx, sc, ax[t]);
+            ay[t] = fmaf(dy, sc, ay[t]);
+            az[t] = fmaf(dz, sc, az[t]);
+            if (POT) ap[t] += mri;
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty_bar[s]);
+#pragma unroll
+      for (int t = 0; t < TPT; ++t) {
+        dacc[t][0] += (double)ax[t];
+        dacc[t][1] += (double)ay[t];
+        dacc[t][2] += (double)az[t];
+        if (POT) dacc[t][NC - 1] -= (double)ap[t];
+      }
+    }
+#pragma unroll
+    for (int t = 0; t < TPT; ++t) {
+      int local = t * OCG_CONSUMER_THREADS + tid;
+      if (local < tgt_count) {
+        long long gi = tgt_begin + local;
+#pragma unroll
+        for (int c = 0; c < NC; ++c)
+          p.partial[(slot * NC + c) * p.out_stride + gi] = dacc[t][c];
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------- source classification ----
+// misc scratch layout (ints unless noted)
+//   [0..5]  target bbox as ordered ints: minx,miny,minz,maxx,maxy,maxz
+//   [8]     n_fast   [9] n_near   [10] n_fast_tiles
+#define MISC_BBOX 0
+#define MISC_NFAST 8
+#define MISC_NNEAR 9
+#define MISC_NFAST_TILES 10
+#define MISC_INTS 16
+
+__device__ __forceinline__ int float_to_ordered(float f) {
+  int i = __float_as_int(f);
+  return i >= 0 ? i : i ^ 0x7fffffff;
+}
+__device__ __forceinline__ float ordered_to_float(int i) {
+  return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff);
+}
+
+__global__ void misc_init_kernel(int* misc) {
+  int i = threadIdx.x;
+  if (i < 3) misc[MISC_BBOX + i] = 0x7fffffff;       // +max ordered
+  else if (i < 6) misc[MISC_BBOX + i] = (int)0x80000000;  // -max ordered
+  else if (i < MISC_INTS) misc[i] = 0;
+}
+
+__global__ void bbox_kernel(const float4* __restrict__ tgt, long long n, int* misc) {
+  float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    float4 T = tgt[i];
+    mn[0] = fminf(mn[0], T.x), mn[1] = fminf(mn[1], T.y), mn[2] = fminf(mn[2], T.z);
+    mx[0] = fmaxf(mx[0], T.x), mx[1] = fmaxf(mx[1], T.y), mx[2] = fmaxf(mx[2], T.z);
+  }
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    for (int o = 16; o > 0; o >>= 1) {
+      mn[c] = fminf(mn[c], __shfl_xor_sync(0xffffffffu, mn[c], o));
+      mx[c] = fmaxf(mx[c], __shfl_xor_sync(0xffffffffu, mx[c], o));
+    }
+  }
+  if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      atomicMin(&misc[MISC_BBOX + c], float_to_ordered(mn[c]));
+      atomicMax(&misc[MISC_BBOX + 3 + c], float_to_ordered(mx[c]));
+    }
+  }
+}
+
+// Is source (x,y,z,soft) safe for the fast kernel for EVERY target inside the bbox?
+//   Plummer, e2 > 0       : always (r2 + e2 > 0)
+//   Plummer/spline, e2==0 : Newtonian; needs distance to the box > 0 (no singular pair)
+//   spline, h > 0         : needs distance to the box >= h (force is exactly Newtonian there)
+__device__ __forceinline__ bool source_is_fast(float x, float y, float z, float soft, int kernel,
+                                               const int* misc) {
+  const float e2 = soft * soft;
+  if (kernel == OCG_KERNEL_PLUMMER && e2 > 0.f) return true;
+  float bx0 = ordered_to_float(misc[MISC_BBOX + 0]), by0 = ordered_to_float(misc[MISC_BBOX + 1]);
+  float bz0 = ordered_to_float(misc[MISC_BBOX + 2]), bx1 = ordered_to_float(misc[MISC_BBOX + 3]);
+  float by1 = ordered_to_float(misc[MISC_BBOX + 4]), bz1 = ordered_to_float(misc[MISC_BBOX + 5]);
+  float dx = fmaxf(fmaxf(bx0 - x, x - bx1), 0.f);
+  float dy = fmaxf(fmaxf(by0 - y, y - by1), 0.f);
+  float dz = fmaxf(fmaxf(bz0 - z, z - bz1), 0.f);
+  float d2 = dx * dx + dy * dy + dz * dz;
+  // 1e-20: keeps m * r^-3 finite in FP32; (1 + 1e-5): FP32 rounding margin on the support test
+  return d2 > 1e-20f && d2 > e2 * 1.00001f;
+}
+
+#define CLS_BLOCK 1024
+
+__global__ void __launch_bounds__(CLS_BLOCK) classify_count_kernel(
+    const float4* __restrict__ src, const float* __restrict__ soft, long long n, int kernel,
+    const int* __restrict__ misc, int* __restrict__ counts) {
+  __shared__ int wsum[CLS_BLOCK / 32];
+  long long i = blockIdx.x * (long long)CLS_BLOCK + threadIdx.x;
+  bool fast = false;
+  if (i < n) {
+    float4 S = src[i];
+    fast = source_is_fast(S.x, S.y, S.z, soft ? soft[i] : 0.f, kernel, misc);
+  }
+  unsigned b = __ballot_sync(0xffffffffu, fast);
+  if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = __popc(b);
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    int v = wsum[threadIdx.x];
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (threadIdx.x == 0) counts[blockIdx.x] = v;
+  }
+}
+
+// Single-block exclusive scan of per-block fast counts (in place); totals to misc.
+__global__ void __launch_bounds__(1024) classify_scan_kernel(int* counts, int nblocks, long long n,
+                                                             int* misc) {
+  __shared__ long long carry;
+  __shared__ int wtot[32];
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int base = 0; base < nblocks; base += 1024) {
+    int i = base + threadIdx.x;
+    int v = i < nblocks ? counts[i] : 0;
+    int incl = v;
+    for (int o = 1; o < 32; o <<= 1) {
+      int u = __shfl_up_sync(0xffffffffu, incl, o);
+      if ((threadIdx.x & 31) >= o) incl += u;
+    }
+    if ((threadIdx.x & 31) == 31) wtot[threadIdx.x >> 5] = incl;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      int w = wtot[threadIdx.x], wi = w;
+      for (int o = 1; o < 32; o <<= 1) {
+        int u = __shfl_up_sync(0xffffffffu, wi, o);
+        if (threadIdx.x >= o) wi += u;
+      }
+      wtot[threadIdx.x] = wi - w;  // exclusive warp offsets
+    }
+    __syncthreads();
+    long long c = carry;
+    int excl = incl - v + wtot[threadIdx.x >> 5];
+    // counts[] holds ints: fast-source offsets fit because n_src < 2^31 per call (checked on host)
+    if (i < nblocks) counts[i] = (int)(c + excl);
+    __syncthreads();
+    if (threadIdx.x == 1023) carry = c + excl + v;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    long long nf = carry;
+    misc[MISC_NFAST] = (int)nf;
+    misc[MISC_NNEAR] = (int)(n - nf);
+    misc[MISC_NFAST_TILES] = (int)((nf + OCG_TS - 1) / OCG_TS);
+  }
+}
+
+// Stable scatter: fast sources -> tiles, near sources -> near list (float4 xyzm + float soft).
+__global__ void __launch_bounds__(CLS_BLOCK) classify_scatter_kernel(
+    const float4* __restrict__ src, const float* __restrict__ soft, long long n, int kernel,
+    const int* __restrict__ misc, const int* __restrict__ fast_off, float* __restrict__ tiles,
+    float4* __restrict__ near_xyzm, float* __restrict__ near_soft) {
+  __shared__ int wbase[CLS_BLOCK / 32];
+  long long i = blockIdx.x * (long long)CLS_BLOCK + threadIdx.x;
+  bool valid = i < n, fast = false;
+  float4 S = make_float4(0.f, 0.f, 0.f, 0.f);
+  float h = 0.f;
+  if (valid) {
+    S = src[i];
+    h = soft ? soft[i] : 0.f;
+    fast = source_is_fast(S.x, S.y, S.z, h, kernel, misc);
+  }
+  unsigned b = __ballot_sync(0xffffffffu, fast);
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (lane == 0) wbase[w] = __popc(b);
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    int v = wbase[threadIdx.x], incl = v;
+    for (int o = 1; o < 32; o <<= 1) {
+      int u = __shfl_up_sync(0xffffffffu, incl, o);
+      if (threadIdx.x >= o) incl += u;
+    }
+    wbase[threadIdx.x] = incl - v;
+  }
+  __syncthreads();
+  if (!valid) return;
+  int rank_fast = wbase[w] + __popc(b & ((1u << lane) - 1u));
+  long long block_start = blockIdx.x * (long long)CLS_BLOCK;
+  long long foff = fast_off[blockIdx.x];
+  if (fast) {
+    long long pos = foff + rank_fast;
+    long long tile = pos / OCG_TS;
+    int j = (int)(pos - tile * OCG_TS);
+    float* T = tiles + tile * (long long)OCG_TILE_FLOATS;
+    // spline sources that reach the fast set are Newtonian for every target: e2 = 0
+    float e2 = kernel == OCG_KERNEL_PLUMMER ? h * h : 0.f;
+    T[j] = S.x;
+    T[OCG_TS + j] = S.y;
+    T[2 * OCG_TS + j] = S.z;
+    T[3 * OCG_TS + j] = S.w;
+    T[4 * OCG_TS + j] = e2;
+  } else {
+    long long pos = (block_start - foff) + (threadIdx.x - rank_fast);
+    near_xyzm[pos] = S;
+    near_soft[pos] = h;
+  }
+}
+
+// Pad the tail of the last fast tile with zero-mass sources (contribute exactly 0).
+__global__ void pad_tiles_kernel(float* tiles, const int* misc) {
+  int nf = misc[MISC_NFAST];
+  int nt = misc[MISC_NFAST_TILES];
+  long long end = (long long)nt * OCG_TS;
+  for (long long pos = nf + threadIdx.x; pos < end; pos += blockDim.x) {
+    long long tile = pos / OCG_TS;
+    int j = (int)(pos - tile * OCG_TS);
+    float* T = tiles + tile * (long long)OCG_TILE_FLOATS;
+    T[j] = 0.f, T[OCG_TS + j] = 0.f, T[2 * OCG_TS + j] = 0.f;
+    T[3 * OCG_TS + j] = 0.f;
+    T[4 * OCG_TS + j] = 1.f;
+  }
+}
+
+// ------------------------------------------------------------------- finish: sum partials ----
+// out[c][t] (+)= G * sum_{slot < n_slots} partial[slot][c][t], slots summed in index order.
+__global__ void finish_kernel(const double* __restrict__ partial, long long stride, int n_slots,
+                              int nc_partial, double G, long long n_tgt, double* __restrict__ acc,
+                              double* __restrict__ pot, int accumulate) {
+  long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (t >= n_tgt) return;
+  for (int c = 0; c < nc_partial; ++c) {
+    double s = 0.0;
+    for (int k = 0; k < n_slots; ++k) s += partial[((long long)k * nc_partial + c) * stride + t];
+    s *= G;
+    double* dst = c < 3 ? acc + (long long)c * n_tgt + t : pot + t;
+    *dst = accumulate ? *dst + s : s;
+  }
+}
+
+// ---------------------------------------------------------------------- near (slow) kernel ----
+// Sources that may be inside their softening support, or singular. FP32 pair arithmetic with
+// exact sqrt/div, branches allowed, FP64 accumulation; adds G * sum straight into acc/pot.
+// Spline forms: pykdgrav ForceKernel / PotentialKernel (cubic spline of support h; Springel 2001).
+__device__ __forceinline__ void near_pair(float dx, float dy, float dz, float m, float h, int kernel,
+                                          float& fac, float& pfac) {
+  float r2 = dx * dx + dy * dy + dz * dz;
+  fac = 0.f, pfac = 0.f;
+  if (kernel == OCG_KERNEL_PLUMMER) {
+    float q2 = r2 + h * h;
+    if (q2 > 0.f) {
+      float ri = 1.0f / sqrtf(q2);
+      pfac = -m * ri;
+      fac = m * ri * ri * ri;
+    }
+    return;
+  }
+  if (!(r2 > 0.f)) return;
+  float r = sqrtf(r2);
+  if (r >= h) {
+    float ri = 1.0f / r;
+    pfac = -m * ri;
+    fac = m * ri * ri * ri;
+    return;
+  }
+  float hinv = 1.0f / h;
+  float q = r * hinv;
+  float h3 = hinv * hinv * hinv;
+  if (q <= 0.5f) {
+    fac = m * h3 * (10.666666666666666f + q * q * (32.0f * q - 38.4f));
+    pfac = m * hinv * (-2.8f + q * q * (5.333333333333333f + q * q * (6.4f * q - 9.6f)));
+  } else {
+    float q3 = q * q * q;
+    fac = m * h3 *
+          (21.333333333333332f - 48.0f * q + 38.4f * q * q - 10.666666666666666f * q3 -
+           0.06666666666666667f / q3);
+    pfac = m * hinv *
+           (-3.2f + 0.06666666666666667f / q +
+            q * q * (10.666666666666666f + q * (-16.0f + q * (9.6f - 2.1333333333333333f * q))));
+  }
+}
+
+#define NEAR_BLOCK 256
+__global__ void __launch_bounds__(NEAR_BLOCK) near_sum_kernel(
+    const float4* __restrict__ near_xyzm, const float* __restrict__ near_soft,
+    const int* __restrict__ misc, const float4* __restrict__ tgt, long long n_tgt, int kernel,
+    double G, double* __restrict__ acc, double* __restrict__ pot) {
+  const int n_near = misc[MISC_NNEAR];
+  if (n_near == 0) return;
+  __shared__ float4 sS[NEAR_BLOCK];
+  __shared__ float sH[NEAR_BLOCK];
+  long long t = blockIdx.x * (long long)NEAR_BLOCK + threadIdx.x;
+  float4 T = tgt[t < n_tgt ? t : n_tgt - 1];
+  double a0 = 0, a1 = 0, a2 = 0, ph = 0;
+  for (int base = 0; base < n_near; base += NEAR_BLOCK) {
+    int i = base + threadIdx.x;
+    __syncthreads();
+    if (i < n_near) {
+      sS[threadIdx.x] = near_xyzm[i];
+      sH[threadIdx.x] = near_soft[i];
+    }
+    __syncthreads();
+    int cnt = min(NEAR_BLOCK, n_near - base);
+    float f0 = 0, f1 = 0, f2 = 0, fp = 0;
+    for (int j = 0; j < cnt; ++j) {
+      float4 S = sS[j];
+      float dx = S.x - T.x, dy = S.y - T.y, dz = S.z - T.z, fac, pfac;
+      near_pair(dx, dy, dz, S.w, sH[j], kernel, fac, pfac);
+      f0 = fmaf(dx, fac, f0), f1 = fmaf(dy, fac, f1), f2 = fmaf(dz, fac, f2);
+      fp += pfac;
+    }
+    a0 += f0, a1 += f1, a2 += f2, ph += fp;
+  }
+  if (t < n_tgt) {
+    acc[t] += G * a0;
+    acc[n_tgt + t] += G * a1;
+    acc[2 * n_tgt + t] += G * a2;
+    if (pot) pot[t] += G * ph;
+  }
+}
+
+// ------------------------------------------------------------------------------ launchers ----
+static size_t direct_smem_bytes() { return OCG_NSTAGE * OCG_TILE_BYTES + 2 * OCG_NSTAGE * 8; }
+
+typedef void (*direct_fn)(const DirectParams);
+
+template <int TPT>
+static direct_fn pick_kernel(bool pot, bool guard, bool scalar) {
+  if (scalar) {
+    if (pot) return guard ? direct_sum_scalar_kernel<TPT, true, true> : direct_sum_scalar_kernel<TPT, true, false>;
+    return guard ? direct_sum_scalar_kernel<TPT, false, true> : direct_sum_scalar_kernel<TPT, false, false>;
+  }
+  if (pot) return guard ? direct_sum_kernel<TPT, true, true> : direct_sum_kernel<TPT, true, false>;
+  return guard ? direct_sum_kernel<TPT, false, true> : direct_sum_kernel<TPT, false, false>;
+}
+
+static int g_force_tpt = 0;     // 0 = heuristic
+static int g_force_scalar = 0;  // 1 = scalar FP32 variant
+extern "C" int ocg_debug_set_variant(int tpt, int scalar) {
+  g_force_tpt = tpt;
+  g_force_scalar = scalar;
+  return 0;
+}
+
+int ocg_pick_tpt(ocg_ctx* ctx, int64_t n_tgt) {
+  if (g_force_tpt == 1 || g_force_tpt == 2 || g_force_tpt == 4) return g_force_tpt;
+  // enough targets to give every resident CTA a full tile at TPT=2?
+  long long full = (long long)ctx->sm_count * 2 * OCG_CONSUMER_THREADS * 2;
+  return n_tgt >= full ? 2 : 1;
+}
+
+// Launch the fast kernel over a prepared parameter block.
+int ocg_launch_direct(ocg_ctx* ctx, DirectParams& p, int tpt, bool pot, bool guard, cudaStream_t st) {
+  direct_fn fn = tpt == 4 ? pick_kernel<4>(pot, guard, g_force_scalar)
+                          : (tpt == 2 ? pick_kernel<2>(pot, guard, g_force_scalar)
+                                      : pick_kernel<1>(pot, guard, g_force_scalar));
+  size_t smem = direct_smem_bytes();
+  OCG_CUDA(ctx, cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int grid = ctx->sm_count * 2;
+  if (grid > p.n_items) grid = p.n_items;
+  if (grid < 1) grid = 1;
+  if (ctx->timing) OCG_CUDA(ctx, cudaEventRecord(ctx->ev0, st));
+  fn<<<grid, OCG_CTA_THREADS, smem, st>>>(p);
+  OCG_CHECK_LAUNCH(ctx, "direct_sum_kernel");
+  if (ctx->timing) {
+    OCG_CUDA(ctx, cudaEventRecord(ctx->ev1, st));
+    ctx->ev_valid = 1;
+  }
+  return OCG_OK;
+}
+
+int ocg_direct_sum_impl(ocg_ctx* ctx, const float* src_xyzm, const float* src_soft, int64_t n_src,
+                        const float* tgt_xyzw, int64_t n_tgt, int kernel, double G, double* acc,
+                        double* pot, int accumulate, cudaStream_t st) {
+  if (n_tgt <= 0) return OCG_OK;
+  if (n_src >= (1ll << 31) - 2 * CLS_BLOCK)
+    return ocg_fail(ctx, OCG_ERR_INVALID, "n_src %lld too large for one call; stream in chunks with accumulate=1",
+                    (long long)n_src);
+  const bool want_pot = pot != nullptr;
+  const int NC = want_pot ? 4 : 3;
+  if (n_src <= 0) {
+    if (!accumulate) {
+      OCG_CUDA(ctx, cudaMemsetAsync(acc, 0, sizeof(double) * 3 * n_tgt, st));
+      if (pot) OCG_CUDA(ctx, cudaMemsetAsync(pot, 0, sizeof(double) * n_tgt, st));
+    }
+    return OCG_OK;
+  }
+
+  const int tpt = ocg_pick_tpt(ctx, n_tgt);
+  const int CT = OCG_CONSUMER_THREADS * tpt;
+  const long long n_ttiles = (n_tgt + CT - 1) / CT;
+  const long long n_tiles_max = (n_src + OCG_TS - 1) / OCG_TS;
+  // chunking: aim for >= 16 items per resident CTA slot
+  const long long slots = (long long)ctx->sm_count * 2;
+  long long n_chunks = (16 * slots + n_ttiles - 1) / n_ttiles;
+  if (n_chunks > n_tiles_max) n_chunks = n_tiles_max;
+  if (n_chunks > 1024) n_chunks = 1024;
+  if (n_chunks < 1) n_chunks = 1;
+  const long long tiles_per_chunk = (n_tiles_max + n_chunks - 1) / n_chunks;
+  n_chunks = (n_tiles_max + tiles_per_chunk - 1) / tiles_per_chunk;
+  if (n_ttiles * n_chunks > 0x7fffffffll) return ocg_fail(ctx, OCG_ERR_INVALID, "too many work items");
+
+  int* misc;
+  float* tiles;
+  double* partial;
+  float4* near_xyzm;
+  float* near_soft;
+  int* counts;
+  const long long n_cls_blocks = (n_src + CLS_BLOCK - 1) / CLS_BLOCK;
+  int rc;
+  if ((rc = ocg_scratch(ctx, OCG_SCR_MISC, MISC_INTS * sizeof(int), (void**)&misc))) return rc;
+  if ((rc = ocg_scratch(ctx, OCG_SCR_TILES, (size_t)n_tiles_max * OCG_TILE_BYTES, (void**)&tiles))) return rc;
+  if ((rc = ocg_scratch(ctx, OCG_SCR_PARTIAL, (size_t)n_chunks * NC * n_tgt * sizeof(double), (void**)&partial))) return rc;
+  if ((rc = ocg_scratch(ctx, OCG_SCR_NEAR, (size_t)n_src * 20, (void**)&near_xyzm))) return rc;
+  near_soft = reinterpret_cast<float*>(near_xyzm + n_src);
+  if ((rc = ocg_scratch(ctx, OCG_SCR_COUNTS, (size_t)n_cls_blocks * sizeof(int), (void**)&counts))) return rc;
+
+  const float4* src4 = reinterpret_cast<const float4*>(src_xyzm);
+  const float4* tgt4 = reinterpret_cast<const float4*>(tgt_xyzw);
+
+  misc_init_kernel<<<1, 32, 0, st>>>(misc);
+  OCG_CHECK_LAUNCH(ctx, "misc_init_kernel");
+  {
+    long long nb = (n_tgt + 255) / 256;
+    if (nb > ctx->sm_count * 8) nb = ctx->sm_count * 8;
+    bbox_kernel<<<(int)nb, 256, 0, st>>>(tgt4, n_tgt, misc);
+    OCG_CHECK_LAUNCH(ctx, "bbox_kernel");
+  }
+  classify_count_kernel<<<(int)n_cls_blocks, CLS_BLOCK, 0, st>>>(src4, src_soft, n_src, kernel, misc, counts);
+  OCG_CHECK_LAUNCH(ctx, "classify_count_kernel");
+  classify_scan_kernel<<<1, 1024, 0, st>>>(counts, (int)n_cls_blocks, n_src, misc);
+  OCG_CHECK_LAUNCH(ctx, "classify_scan_kernel");
+  classify_scatter_kernel<<<(int)n_cls_blocks, CLS_BLOCK, 0, st>>>(src4, src_soft, n_src, kernel, misc, counts,
+                                                                 tiles, near_xyzm, near_soft);
+  OCG_CHECK_LAUNCH(ctx, "classify_scatter_kernel");
+  pad_tiles_kernel<<<1, OCG_TS, 0, st>>>(tiles, misc);
+  OCG_CHECK_LAUNCH(ctx, "pad_tiles_kernel");
+
+  DirectParams p;
+  p.tiles = tiles;
+  p.tgt = tgt4;
+  p.partial = partial;
+  p.out_stride = n_tgt;
+  p.items = nullptr;
+  p.n_items = (int)(n_ttiles * n_chunks);
+  p.n_tgt = n_tgt;
+  p.n_ttiles = (int)n_ttiles;
+  p.tiles_per_chunk = (int)tiles_per_chunk;
+  p.n_fast_tiles = misc + MISC_NFAST_TILES;
+  if ((rc = ocg_launch_direct(ctx, p, tpt, want_pot, /*guard=*/false, st))) return rc;
+
+  {
+    long long nb = (n_tgt + 255) / 256;
+    finish_kernel<<<(int)nb, 256, 0, st>>>(partial, n_tgt, (int)n_chunks, NC, G, n_tgt, acc, pot, accumulate);
+    OCG_CHECK_LAUNCH(ctx, "finish_kernel");
+    long long nbn = (n_tgt + NEAR_BLOCK - 1) / NEAR_BLOCK;
+    near_sum_kernel<<<(int)nbn, NEAR_BLOCK, 0, st>>>(near_xyzm, near_soft, misc, tgt4, n_tgt, kernel, G, acc, pot);
+    OCG_CHECK_LAUNCH(ctx, "near_sum_kernel");
+  }
+  return OCG_OK;
+}

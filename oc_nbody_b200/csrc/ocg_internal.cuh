@@ -1,0 +1,111 @@
+// Internal declarations shared by the translation units of liboc_nbody_b200.
+// Not part of the ABI (see include/ocg.h).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/ocg.h"
+
+// ---- geometry of the direct-sum kernel (K1/K4) ------------------------------------------------
+// A source tile is TS sources stored component-major: x[TS] | y[TS] | z[TS] | m[TS] | e2[TS].
+// One tile = one cp.async.bulk (TMA 1-D bulk copy) of OCG_TILE_BYTES into one pipeline stage.
+#define OCG_TS 512
+#define OCG_TILE_FLOATS (5 * OCG_TS)
+#define OCG_TILE_BYTES (OCG_TILE_FLOATS * 4)
+#define OCG_NSTAGE 4
+#define OCG_CONSUMER_WARPS 8
+#define OCG_CONSUMER_THREADS (OCG_CONSUMER_WARPS * 32)
+#define OCG_CTA_THREADS (OCG_CONSUMER_THREADS + 32) /* + 1 TMA producer warp */
+
+// Work item of the direct-sum kernel: a tile of targets against a run of source tiles.
+struct OcgWorkItem {
+  long long tgt_begin;   // first target (global index into tgt array / output)
+  int tgt_count;         // targets in this item (<= CTA targets)
+  int tile_count;        // source tiles to stream
+  long long tile_begin;  // first source tile
+  long long out_slot;    // partial-sum slot: partial[(out_slot*NC + c)*out_stride + tgt]
+};
+
+enum { OCG_SCR_TILES = 0, OCG_SCR_PARTIAL, OCG_SCR_NEAR, OCG_SCR_ITEMS, OCG_SCR_MISC, OCG_SCR_TGT,
+       OCG_SCR_SRC, OCG_SCR_SOFT, OCG_SCR_F64A, OCG_SCR_F64B, OCG_SCR_F64C, OCG_SCR_OUT, OCG_SCR_COUNTS,
+       OCG_SCR_N };
+
+struct ocg_ctx {
+  int device;
+  int sm_count;
+  int sm_clock_khz;
+  size_t global_mem;
+  char err[1024];
+  void* scratch[OCG_SCR_N];
+  size_t scratch_bytes[OCG_SCR_N];
+  long long launches;
+  int timing;
+  cudaEvent_t ev0, ev1;
+  int ev_valid;
+  // cached host copy of the last uploaded item list (K4), to skip re-upload
+  OcgWorkItem* items_host;
+  size_t items_host_cap;
+  size_t items_uploaded;  // number of items currently in device list
+  unsigned long long items_hash;
+};
+
+// ---- error helpers ------------------------------------------------------------------------------
+int ocg_fail(ocg_ctx* ctx, int code, const char* fmt, ...);
+
+#define OCG_CUDA(ctx, expr)                                                              \
+  do {                                                                                   \
+    cudaError_t _e = (expr);                                                             \
+    if (_e != cudaSuccess)                                                               \
+      return ocg_fail((ctx), OCG_ERR_CUDA, "%s failed: %s (%s:%d)", #expr,              \
+                      cudaGetErrorString(_e), __FILE__, __LINE__);                       \
+  } while (0)
+
+#define OCG_CHECK_LAUNCH(ctx, name)                                                      \
+  do {                                                                                   \
+    cudaError_t _e = cudaGetLastError();                                                 \
+    if (_e != cudaSuccess)                                                               \
+      return ocg_fail((ctx), OCG_ERR_CUDA, "launch of %s failed: %s", name,             \
+                      cudaGetErrorString(_e));                                           \
+    (ctx)->launches++;                                                                   \
+  } while (0)
+
+// Grow-only scratch buffer tied to the ctx.
+int ocg_scratch(ocg_ctx* ctx, int which, size_t bytes, void** out);
+
+struct OcgDeviceGuard {
+  int prev;
+  bool changed;
+  explicit OcgDeviceGuard(int dev) : prev(-1), changed(false) {
+    if (cudaGetDevice(&prev) == cudaSuccess && prev != dev) {
+      cudaSetDevice(dev);
+      changed = true;
+    }
+  }
+  ~OcgDeviceGuard() {
+    if (changed) cudaSetDevice(prev);
+  }
+};
+
+// ---- parameter block of the direct-sum kernels (direct_sum.cu) -------------------------------
+struct DirectParams {
+  const float* tiles;        // packed source tiles
+  const float4* tgt;         // targets (x,y,z,-)
+  double* partial;           // [slot][NC][out_stride]
+  long long out_stride;      // rows of the partial buffer
+  const OcgWorkItem* items;  // list mode when non-null (K4), else arithmetic decode (K1)
+  int n_items;
+  long long n_tgt;           // arithmetic mode: item -> (chunk, target tile)
+  int n_ttiles;
+  int tiles_per_chunk;
+  const int* n_fast_tiles;   // device: number of fast tiles actually present
+};
+
+// ---- entry points implemented in other translation units ------------------------------------
+int ocg_pick_tpt(ocg_ctx* ctx, int64_t n_tgt);
+int ocg_launch_direct(ocg_ctx* ctx, DirectParams& p, int tpt, bool pot, bool guard, cudaStream_t st);
+int ocg_direct_sum_impl(ocg_ctx* ctx, const float* src_xyzm, const float* src_soft, int64_t n_src,
+                        const float* tgt_xyzw, int64_t n_tgt, int kernel, double G, double* acc,
+                        double* pot, int accumulate, cudaStream_t st);

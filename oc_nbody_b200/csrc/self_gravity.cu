@@ -1,0 +1,229 @@
+// K4: cluster self-gravity — Plummer-softened direct sum inside each cluster of a batch.
+// Replaces the force loop of the AMUSE ph4 worker the reference instantiates at
+// oc_code.py:218-229 (epsilon_squared = (softening pc)^2, oc_code.py:225).
+//
+// Same streaming kernel as the field build (direct_sum.cu); here sources == targets, the softening
+// is one scalar, segments (clusters) are independent, and each segment is recentred on its first
+// particle in FP64 before rounding to FP32 (cluster stars sit ~8 kpc from the origin of the
+// galaxy frame but ~pc from each other).
+#include "ocg_internal.cuh"
+
+#include <stdlib.h>
+
+// Re-lay FP64 particles into (a) padded per-segment source tiles and (b) float4 targets.
+// seg_off  : device int64 [n_seg+1] particle offsets; seg_tile : device int64 [n_seg+1] tile offsets
+__global__ void pack_cluster_kernel(const double* __restrict__ pos, const double* __restrict__ mass,
+                                    long long n, const long long* __restrict__ seg_off,
+                                    const long long* __restrict__ seg_tile, int n_seg, float e2,
+                                    float* __restrict__ tiles, float4* __restrict__ tgt) {
+  const long long total_tiles = seg_tile[n_seg];
+  const long long slot = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (slot >= total_tiles * OCG_TS) return;
+  const long long tile = slot / OCG_TS;
+  const int j = (int)(slot - tile * OCG_TS);
+  // segment owning this tile: last s with seg_tile[s] <= tile
+  int lo = 0, hi = n_seg;
+  while (hi - lo > 1) {
+    int mid = (lo + hi) >> 1;
+    if (seg_tile[mid] <= tile) lo = mid;
+    else hi = mid;
+  }
+  const long long first = seg_off[lo];
+  const long long idx = first + (tile - seg_tile[lo]) * OCG_TS + j;
+  float* T = tiles + tile * (long long)OCG_TILE_FLOATS;
+  if (idx < seg_off[lo + 1]) {
+    const double cx = pos[first], cy = pos[n + first], cz = pos[2 * n + first];
+    const float x = (float)(pos[idx] - cx), y = (float)(pos[n + idx] - cy), z = (float)(pos[2 * n + idx] - cz);
+    const float m = (float)mass[idx];
+    T[j] = x, T[OCG_TS + j] = y, T[2 * OCG_TS + j] = z, T[3 * OCG_TS + j] = m, T[4 * OCG_TS + j] = e2;
+    tgt[idx] = make_float4(x, y, z, m);
+  } else {
+    T[j] = 0.f, T[OCG_TS + j] = 0.f, T[2 * OCG_TS + j] = 0.f, T[3 * OCG_TS + j] = 0.f, T[4 * OCG_TS + j] = 1.f;
+  }
+}
+
+// out[c][t] = G * sum_slots partial ; potential gets the self term (-m/eps, included by the
+// kernel because targets == sources) removed with the very same FP32 expression the kernel used.
+__global__ void finish_self_kernel(const double* __restrict__ partial, long long stride, int n_slots, int nc,
+                                   double G, long long t0, long long t1, const float4* __restrict__ tgt, float e2,
+                                   double* __restrict__ acc, double* __restrict__ pot) {
+  long long t = t0 + blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (t >= t1) return;
+  for (int c = 0; c < nc; ++c) {
+    double s = 0.0;
+    for (int k = 0; k < n_slots; ++k) s += partial[((long long)k * nc + c) * stride + t];
+    if (c == 3 && e2 > 0.f) {
+      float ri;
+      asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(ri) : "f"(e2));
+      s += (double)(tgt[t].w * ri);
+    }
+    s *= G;
+    if (c < 3) acc[(long long)c * stride + t] = s;
+    else pot[t] = s;
+  }
+}
+
+static unsigned long long fnv1a(const void* data, size_t bytes, unsigned long long h) {
+  const unsigned char* p = (const unsigned char*)data;
+  for (size_t i = 0; i < bytes; ++i) {
+    h ^= p[i];
+    h *= 1099511628211ull;
+  }
+  return h;
+}
+
+extern "C" int ocg_self_gravity(ocg_ctx* ctx, const double* pos_dev, const double* mass_dev, int64_t n,
+                                const int64_t* seg_offsets_host, int32_t n_seg, double eps2, double G,
+                                int64_t tgt_begin, int64_t tgt_end, double* acc_dev, double* pot_dev,
+                                void* stream) {
+  if (!ctx) return OCG_ERR_INVALID;
+  if (n < 0 || n_seg < 1) return ocg_fail(ctx, OCG_ERR_INVALID, "ocg_self_gravity: n < 0 or n_seg < 1");
+  if (n == 0) return OCG_OK;
+  if (!pos_dev || !mass_dev || !acc_dev) return ocg_fail(ctx, OCG_ERR_INVALID, "ocg_self_gravity: NULL argument");
+  if (!(eps2 >= 0.0)) return ocg_fail(ctx, OCG_ERR_INVALID, "ocg_self_gravity: eps2 = %g must be >= 0", eps2);
+  if (tgt_begin < 0 || tgt_end > n || tgt_begin > tgt_end)
+    return ocg_fail(ctx, OCG_ERR_INVALID, "ocg_self_gravity: target range [%lld,%lld) outside [0,%lld)",
+                    (long long)tgt_begin, (long long)tgt_end, (long long)n);
+  int64_t one_seg[2] = {0, n};
+  if (!seg_offsets_host) {
+    if (n_seg != 1) return ocg_fail(ctx, OCG_ERR_INVALID, "ocg_self_gravity: seg_offsets is NULL but n_seg = %d", n_seg);
+    seg_offsets_host = one_seg;
+  }
+  if (seg_offsets_host[0] != 0 || seg_offsets_host[n_seg] != n)
+    return ocg_fail(ctx, OCG_ERR_INVALID, "ocg_self_gravity: seg_offsets must run from 0 to n");
+  for (int s = 0; s < n_seg; ++s)
+    if (seg_offsets_host[s + 1] < seg_offsets_host[s])
+      return ocg_fail(ctx, OCG_ERR_INVALID, "ocg_self_gravity: seg_offsets not monotone at %d", s);
+  if (tgt_begin == tgt_end) return OCG_OK;
+
+  OcgDeviceGuard g(ctx->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool want_pot = pot_dev != nullptr;
+  const int NC = want_pot ? 4 : 3;
+  const float e2f = (float)eps2;
+  const bool guard = !(e2f > 0.f);
+  const int64_t n_shard = tgt_end - tgt_begin;
+  const int tpt = ocg_pick_tpt(ctx, n_shard);
+  const int CT = OCG_CONSUMER_THREADS * tpt;
+
+  // ---- host-side plan: tile offsets per segment, chunk count, item list ----
+  long long* seg_tile = (long long*)malloc(sizeof(long long) * (2 * (size_t)n_seg + 2));
+  if (!seg_tile) return ocg_fail(ctx, OCG_ERR_NOMEM, "malloc failed");
+  long long* seg_off_ll = seg_tile + n_seg + 1;
+  long long total_tiles = 0, n_tt_total = 0, max_tiles = 1;
+  for (int s = 0; s <= n_seg; ++s) seg_off_ll[s] = seg_offsets_host[s];
+  for (int s = 0; s < n_seg; ++s) {
+    seg_tile[s] = total_tiles;
+    long long len = seg_off_ll[s + 1] - seg_off_ll[s];
+    long long nt = (len + OCG_TS - 1) / OCG_TS;
+    total_tiles += nt;
+    if (nt > max_tiles) max_tiles = nt;
+    long long a = seg_off_ll[s] > tgt_begin ? seg_off_ll[s] : tgt_begin;
+    long long b = seg_off_ll[s + 1] < tgt_end ? seg_off_ll[s + 1] : tgt_end;
+    if (b > a) n_tt_total += (b - a + CT - 1) / CT;
+  }
+  seg_tile[n_seg] = total_tiles;
+  const long long slots = (long long)ctx->sm_count * 2;
+  long long n_chunks = n_tt_total > 0 ? (16 * slots + n_tt_total - 1) / n_tt_total : 1;
+  if (n_chunks > max_tiles) n_chunks = max_tiles;
+  if (n_chunks > 256) n_chunks = 256;
+  if (n_chunks < 1) n_chunks = 1;
+  const long long n_items = n_tt_total * n_chunks;
+  if (n_items > 0x7fffffffll) {
+    free(seg_tile);
+    return ocg_fail(ctx, OCG_ERR_INVALID, "ocg_self_gravity: too many work items");
+  }
+  if ((size_t)n_items > ctx->items_host_cap) {
+    free(ctx->items_host);
+    ctx->items_host = (OcgWorkItem*)malloc(sizeof(OcgWorkItem) * (size_t)n_items);
+    ctx->items_host_cap = ctx->items_host ? (size_t)n_items : 0;
+    ctx->items_uploaded = 0;
+    if (!ctx->items_host) {
+      free(seg_tile);
+      return ocg_fail(ctx, OCG_ERR_NOMEM, "malloc of %lld work items failed", n_items);
+    }
+  }
+  // chunk-major order: CTAs resident together stream the same source tiles (L2 reuse)
+  long long w = 0;
+  for (long long c = 0; c < n_chunks; ++c) {
+    for (int s = 0; s < n_seg; ++s) {
+      long long a = seg_off_ll[s] > tgt_begin ? seg_off_ll[s] : tgt_begin;
+      long long b = seg_off_ll[s + 1] < tgt_end ? seg_off_ll[s + 1] : tgt_end;
+      if (b <= a) continue;
+      long long nt = seg_tile[s + 1] - seg_tile[s];
+      long long tpc = (nt + n_chunks - 1) / n_chunks;
+      long long tb = c * tpc, te = tb + tpc < nt ? tb + tpc : nt;
+      for (long long t0 = a; t0 < b; t0 += CT) {
+        OcgWorkItem& it = ctx->items_host[w++];
+        it.tgt_begin = t0;
+        it.tgt_count = (int)(b - t0 < CT ? b - t0 : CT);
+        it.tile_begin = seg_tile[s] + (tb < nt ? tb : nt);
+        it.tile_count = (int)(te > tb ? te - tb : 0);
+        it.out_slot = c;
+      }
+    }
+  }
+  unsigned long long h = fnv1a(ctx->items_host, sizeof(OcgWorkItem) * (size_t)n_items, 1469598103934665603ull);
+  h = fnv1a(seg_tile, sizeof(long long) * (2 * (size_t)n_seg + 2), h);
+
+  int rc;
+  float* tiles;
+  float4* tgt;
+  double* partial;
+  OcgWorkItem* d_items;
+  long long* d_seg;
+  const size_t seg_bytes = sizeof(long long) * (2 * (size_t)n_seg + 2);
+  const size_t items_bytes = sizeof(OcgWorkItem) * (size_t)n_items;
+  rc = ocg_scratch(ctx, OCG_SCR_TILES, (size_t)total_tiles * OCG_TILE_BYTES, (void**)&tiles);
+  if (!rc) rc = ocg_scratch(ctx, OCG_SCR_TGT, sizeof(float4) * (size_t)n, (void**)&tgt);
+  if (!rc) rc = ocg_scratch(ctx, OCG_SCR_PARTIAL, sizeof(double) * (size_t)n_chunks * NC * (size_t)n, (void**)&partial);
+  void* items_raw = nullptr;
+  const size_t before = ctx->scratch_bytes[OCG_SCR_ITEMS];
+  if (!rc) rc = ocg_scratch(ctx, OCG_SCR_ITEMS, items_bytes + seg_bytes + 64, &items_raw);
+  if (rc) {
+    free(seg_tile);
+    return rc;
+  }
+  d_items = (OcgWorkItem*)items_raw;
+  d_seg = (long long*)((char*)items_raw + ((items_bytes + 63) / 64) * 64);
+  const bool reuse = before == ctx->scratch_bytes[OCG_SCR_ITEMS] && ctx->items_uploaded == (size_t)n_items &&
+                     ctx->items_hash == h;
+  if (!reuse) {
+    // synchronous small copies: the plan changes only when the segment layout or shard changes
+    cudaError_t e = cudaMemcpyAsync(d_items, ctx->items_host, items_bytes, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_seg, seg_tile, seg_bytes, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);  // seg_tile is freed below
+    if (e != cudaSuccess) {
+      free(seg_tile);
+      return ocg_fail(ctx, OCG_ERR_CUDA, "upload of the work plan failed: %s", cudaGetErrorString(e));
+    }
+    ctx->items_uploaded = (size_t)n_items;
+    ctx->items_hash = h;
+  }
+  free(seg_tile);
+  const long long* d_seg_tile = d_seg;
+  const long long* d_seg_off = d_seg + n_seg + 1;
+
+  {
+    long long nslots = total_tiles * OCG_TS;
+    pack_cluster_kernel<<<(int)((nslots + 255) / 256), 256, 0, st>>>(pos_dev, mass_dev, n, d_seg_off, d_seg_tile,
+                                                                    n_seg, guard ? 0.f : e2f, tiles, tgt);
+    OCG_CHECK_LAUNCH(ctx, "pack_cluster_kernel");
+  }
+  DirectParams p;
+  p.tiles = tiles;
+  p.tgt = tgt;
+  p.partial = partial;
+  p.out_stride = n;
+  p.items = d_items;
+  p.n_items = (int)n_items;
+  p.n_tgt = n;
+  p.n_ttiles = 0;
+  p.tiles_per_chunk = 0;
+  p.n_fast_tiles = nullptr;
+  if ((rc = ocg_launch_direct(ctx, p, tpt, want_pot, guard, st))) return rc;
+  finish_self_kernel<<<(int)((n_shard + 255) / 256), 256, 0, st>>>(partial, n, (int)n_chunks, NC, G, tgt_begin,
+                                                                  tgt_end, tgt, guard ? 0.f : e2f, acc_dev, pot_dev);
+  OCG_CHECK_LAUNCH(ctx, "finish_self_kernel");
+  return OCG_OK;
+}

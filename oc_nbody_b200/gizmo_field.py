@@ -1,0 +1,281 @@
+"""External-field code: the B200 drop-in for the hot path of the reference's ``gizmo_interface``.
+
+Duck type preserved (what amuse.couple.bridge.Bridge and oc_nbody.py call):
+  ``get_gravity_at_point(eps, x, y, z)``   gizmo_interface.py:677-717
+  ``get_potential_at_point(eps, x, y, z)`` new per BASELINE.json north_star (no reference body exists)
+  ``evolve_model(time, timestep=None)``    gizmo_interface.py:622-638
+  ``evolve_grid(pos)``                     gizmo_interface.py:640-642
+plus the attributes other reference modules read (``grid``, ``time_in_Myr``, ``chosen_id``,
+``chosen_evolved_position`` ...).
+
+What runs where
+  * field build  : per snapshot, K1 direct sum on the GPU for every grid point (+ appended origin), frame
+                   acceleration subtracted (gizmo_interface.py:512-573), stacked to
+                   ``grid.snapshot_acceleration_{x,y,z}[Nsnap, Ngrid+1]`` (gizmo_interface.py:501-506);
+  * evolve_model : O(1) — picks the bracketing snapshots and the linear weight; the blend is fused into
+                   the interpolation kernel instead of 3*(Ngrid+1) Python-level splev calls through a
+                   process pool (gizmo_interface.py:607-620);
+  * kick         : K3 trilinear gather at the star positions (replaces the per-star kNN + 3 RBF solves of
+                   gizmo_interface.py:661-675,696-704).
+
+Snapshot ingestion (gizmo_analysis/h5py), starting-star selection and the axisymmetric/agama mode are out
+of scope: snapshots are handed in as dict-likes with the fields the reference reads.
+"""
+import numpy as np
+
+from . import _lib
+from .grid_cartesian import grid
+from .units import G_KPC_KMS_MYR, KMS_TO_PC_PER_MYR, to_value, units
+
+KMS_TO_KPC_PER_MYR = KMS_TO_PC_PER_MYR * 1e-3
+
+_DEFAULTS = dict(
+    grid_x_size_in_kpc=0.6, grid_y_size_in_kpc=0.6, grid_z_size_in_kpc=0.6, grid_resolution=0.6 / 16,
+    star_softening_in_pc=11.2, dark_softening_in_pc=112.0, star_char_mass=None, dark_char_mass=None,
+    softening_kernel="spline", plummer_eps_over_h=1.0 / 2.8, theta=0.5, fine_grid=False, with_potential=True,
+)
+
+
+class gizmo_field(object):
+    """Time-varying tidal field on a Cartesian grid that rides with the cluster.
+
+    Parameters
+    ----------
+    options : dict or an ``options_reader``-like object with ``set_options(obj)`` (options.py:151-153)
+    snapshots : sequence of dict-likes with 'star'/'dark'/'gas' species (synthetic.make_snapshot)
+    chosen_positions : [Nsnap, 3] kpc, centre of the grid in each snapshot (the tracked star's position,
+        gizmo_interface.py:464-468); default: ``grid_center`` for all snapshots
+    time_in_Myr : [Nsnap] snapshot times relative to the start (gizmo_interface.py:329-335)
+    chosen_id : id of the tracked star, excluded from the sources (gizmo_interface.py:515)
+    """
+
+    def __init__(self, options, snapshots, chosen_positions=None, time_in_Myr=None, chosen_id=-1, grid_center=(8.0, 0.0, 0.0),
+                 ctx=None, build=True):
+        for k, v in _DEFAULTS.items():
+            setattr(self, k, v)
+        if hasattr(options, "set_options"):
+            options.set_options(self)
+        else:
+            for k, v in dict(options or {}).items():
+                setattr(self, k, v)
+        if self.softening_kernel not in _lib.KERNELS:
+            raise ValueError("softening_kernel must be one of %r" % (sorted(_lib.KERNELS),))
+        if self.fine_grid:
+            raise NotImplementedError("nested fine grid is a SURVEY §8(f) 'next' row")
+        self.G = G_KPC_KMS_MYR  # kpc^2 km/s /Myr /Msun, the unit of gizmo_interface.py:70
+        self.ctx = ctx or _lib.default_context()
+        self.snapshots = list(snapshots)
+        nsnap = len(self.snapshots)
+        if nsnap < 1:
+            raise ValueError("need at least one snapshot")
+        self.chosen_id = chosen_id
+        if chosen_positions is None:
+            chosen_positions = np.tile(np.asarray(grid_center, np.float64), (nsnap, 1))
+        self.chosen_snapshot_positions = np.asarray(chosen_positions, np.float64).reshape(nsnap, 3)
+        if time_in_Myr is None:
+            t0 = self.snapshots[0].snapshot["time"]
+            time_in_Myr = [1000.0 * (s.snapshot["time"] - t0) for s in self.snapshots]
+        self.time_in_Myr = np.asarray(time_in_Myr, np.float64)
+        if nsnap > 1 and not np.all(np.diff(self.time_in_Myr) > 0):
+            raise ValueError("snapshot times must be strictly increasing")
+        self.chosen_evolved_position = self.chosen_snapshot_positions[0].copy()
+        self.chosen_evolved_velocity = np.zeros(3)
+        self._origin = np.zeros(3)
+        self._bracket = (0, min(1, nsnap - 1), 0.0)
+        self._blend_cache = None
+        self._dev = None
+        if build:
+            self._init_grid_()
+            self.evolve_model(0.0 | units.Myr)
+
+    # ------------------------------------------------------------------ field build (init time) ----
+    def _source_arrays_(self, snap):
+        """Source assembly (gizmo_interface.py:515-558): star(-chosen) + dark + gas, per-species softening in kpc."""
+        star, dark, gas = snap["star"], snap["dark"], snap["gas"]
+        ss_key = np.where(star["id"] != self.chosen_id)[0]
+        pos = np.concatenate((star.prop("host.distance.principal")[ss_key], dark.prop("host.distance.principal"),
+                              gas.prop("host.distance.principal")))
+        mass = np.concatenate((star["mass"][ss_key], dark["mass"], gas["mass"]))
+        if self.star_char_mass is not None:
+            # indexed with ss_key — the evident intent of gizmo_interface.py:531-534
+            s_soft = np.power(star["mass"][ss_key] / float(self.star_char_mass), 1.0 / 3.0) / 1000.0
+        else:
+            s_soft = np.full(len(ss_key), float(self.star_softening_in_pc) / 1000.0)
+        if self.dark_char_mass is not None:
+            d_soft = np.power(dark["mass"] / float(self.dark_char_mass), 1.0 / 3.0) / 1000.0
+        else:
+            d_soft = np.full(len(dark["mass"]), float(self.dark_softening_in_pc) / 1000.0)
+        g_soft = 2.8 * gas["smooth.length"] / 1000.0
+        soft = np.concatenate((s_soft, d_soft, g_soft))
+        if self.softening_kernel == "plummer":
+            soft = soft * float(self.plummer_eps_over_h)
+        return np.float64(pos), np.float64(mass), np.float64(soft)
+
+    def _populate_grid_acceleration_(self, snap, grid, want_pot=False):
+        """One snapshot's field on the (shifted) grid, frame acceleration removed
+        (gizmo_interface.py:512-573). Returns acc_x, acc_y, acc_z (, pot) as FP64 [Ngrid+1]."""
+        r, m, soft = self._source_arrays_(snap)
+        out = self.ctx.field_build_host(r, m, soft, grid.evolved_grid, grid.ss_evolved_position, grid.origin_row,
+                                        _lib.KERNELS[self.softening_kernel], self.G, want_pot=want_pot)
+        acc, pot = out if want_pot else (out, None)
+        if want_pot:
+            return acc[0], acc[1], acc[2], pot
+        return acc[0], acc[1], acc[2]
+
+    def _init_grid_(self):
+        """Per-snapshot grid loop (gizmo_interface.py:393-510, minus the pickle caches)."""
+        self.grid = grid(self.grid_x_size_in_kpc, self.grid_y_size_in_kpc, self.grid_z_size_in_kpc, self.grid_resolution)
+        ax, ay, az, ph = [], [], [], []
+        for i, snap in enumerate(self.snapshots):
+            self.grid.gen_evolved_grid(self.chosen_snapshot_positions[i])
+            res = self._populate_grid_acceleration_(snap, self.grid, want_pot=self.with_potential)
+            ax.append(res[0]), ay.append(res[1]), az.append(res[2])
+            if self.with_potential:
+                ph.append(res[3])
+        self.grid.snapshot_acceleration_x = np.array(ax)
+        self.grid.snapshot_acceleration_y = np.array(ay)
+        self.grid.snapshot_acceleration_z = np.array(az)
+        self.grid.snapshot_potential = np.array(ph) if self.with_potential else None
+        self.grid.gen_evolved_grid(self._origin)
+        self._upload_planes_()
+
+    def set_snapshot_fields(self, acc_x, acc_y, acc_z, pot=None):
+        """Install pre-computed fields ([Nsnap, Ngrid+1] each, e.g. loaded from the reference's caches)."""
+        if not hasattr(self, "grid"):
+            self.grid = grid(self.grid_x_size_in_kpc, self.grid_y_size_in_kpc, self.grid_z_size_in_kpc, self.grid_resolution)
+        self.grid.snapshot_acceleration_x = np.asarray(acc_x, np.float64)
+        self.grid.snapshot_acceleration_y = np.asarray(acc_y, np.float64)
+        self.grid.snapshot_acceleration_z = np.asarray(acc_z, np.float64)
+        self.grid.snapshot_potential = None if pot is None else np.asarray(pot, np.float64)
+        self.with_potential = pot is not None
+        self._upload_planes_()
+
+    def _upload_planes_(self):
+        """FP64 [Nsnap, Ngrid+1] x3 -> float4 node records per snapshot in HBM (K2 pack)."""
+        import torch
+        dev = torch.device("cuda", self.ctx.device)
+        g = self.grid
+        nsnap, nnode = g.snapshot_acceleration_x.shape
+        if nnode != len(g):
+            raise ValueError("field arrays have %d nodes, grid has %d" % (nnode, len(g)))
+        rec = torch.empty((nsnap, nnode, 4), dtype=torch.float32, device=dev)
+        for i in range(nsnap):
+            acc = torch.from_numpy(np.stack([g.snapshot_acceleration_x[i], g.snapshot_acceleration_y[i],
+                                             g.snapshot_acceleration_z[i]])).to(dev)
+            pot = None if g.snapshot_potential is None else torch.from_numpy(np.ascontiguousarray(g.snapshot_potential[i])).to(dev)
+            self.ctx.pack_planes(acc, pot, rec[i])
+        self._dev = dict(rec=rec, nodes=[torch.from_numpy(np.ascontiguousarray(a)).to(dev) for a in g.nodes],
+                         origin=torch.zeros((1, 3), dtype=torch.float64, device=dev), device=dev)
+        self._set_origin_(self._origin)
+
+    # ---------------------------------------------------------------------- per-step state ----
+    def _set_origin_(self, pos):
+        import torch
+        self._origin = np.asarray(pos, np.float64).reshape(3).copy()
+        if self._dev is not None:
+            self._dev["origin"].copy_(torch.from_numpy(self._origin.reshape(1, 3)))
+        self._blend_cache = None
+
+    def evolve_model(self, time, timestep=None):
+        """Advance the field to `time`: choose the bracketing snapshots and the linear weight.
+        (The reference evaluates 3*(Ngrid+1) splines here, gizmo_interface.py:607-638.)  The grid origin set
+        by evolve_grid is kept — the reference resets the coordinates but not its KD-tree."""
+        t = float(to_value(time, units.Myr))
+        self.time = t
+        times = self.time_in_Myr
+        if len(times) == 1:
+            self._bracket = (0, 0, 0.0)
+        else:
+            i = int(np.searchsorted(times, t, side="right")) - 1
+            i = min(max(i, 0), len(times) - 2)
+            w = (t - times[i]) / (times[i + 1] - times[i])
+            self._bracket = (i, i + 1, float(min(max(w, 0.0), 1.0)))
+        if len(times) > 1:
+            a, b, w = self._bracket
+            p = self.chosen_snapshot_positions
+            self.chosen_evolved_position = (1.0 - w) * p[a] + w * p[b]
+        self._blend_cache = None
+
+    def evolve_grid(self, pos):
+        """Re-origin the grid at the cluster's bound centre of mass (gizmo_interface.py:640-642)."""
+        self.grid.gen_evolved_grid(np.asarray(pos, np.float64))
+        self._set_origin_(pos)
+
+    # materialised blend, for code that reads grid.evolved_acceleration_* (gizmo_interface.py:618-620)
+    def _blend_(self):
+        if self._blend_cache is None:
+            import torch
+            a, b, w = self._bracket
+            rec = self._dev["rec"]
+            n = rec.shape[1]
+            acc = torch.empty((3, n), dtype=torch.float64, device=self._dev["device"])
+            pot = torch.empty(n, dtype=torch.float64, device=self._dev["device"])
+            self.ctx.grid_time_blend(rec[a], rec[b] if b != a else None, w, acc, pot)
+            self._blend_cache = (acc.cpu().numpy(), pot.cpu().numpy())
+        return self._blend_cache
+
+    @property
+    def evolved_acceleration(self):
+        return self._blend_()[0]
+
+    @property
+    def evolved_potential(self):
+        return self._blend_()[1]
+
+    # ---------------------------------------------------------------------------- the kick ----
+    def _interp_device_(self, sx, sy, sz, want_pot):
+        """K3 on device tensors (FP64 kpc). Returns acc [3,n] (, pot [n]) device tensors."""
+        import torch
+        d = self._dev
+        n = sx.shape[0]
+        acc = torch.empty((3, n), dtype=torch.float64, device=d["device"])
+        pot = torch.empty(n, dtype=torch.float64, device=d["device"]) if want_pot else None
+        a, b, w = self._bracket
+        rec = d["rec"]
+        self.ctx.grid_interp(self.grid.shape, d["nodes"], d["origin"], rec[a], rec[b] if b != a else None, w, sx, sy, sz,
+                             None, acc, pot)
+        return acc, pot
+
+    def _interp_host_(self, x, y, z, want_pot):
+        import torch
+        scalar = not hasattr(x, "__iter__") and np.ndim(x) == 0
+        xs = [torch.from_numpy(np.atleast_1d(np.asarray(v, np.float64)).copy()).to(self._dev["device"]) for v in (x, y, z)]
+        if not (xs[0].shape == xs[1].shape == xs[2].shape):
+            raise ValueError("x, y, z must have the same length")
+        acc, pot = self._interp_device_(xs[0], xs[1], xs[2], want_pot)
+        acc = acc.cpu().numpy()
+        pot = pot.cpu().numpy() if want_pot else None
+        return scalar, acc, pot
+
+    def get_gravity_at_point(self, eps, xlist, ylist, zlist):
+        """Acceleration at the given points (kpc) in km/s/Myr; `eps` is accepted and ignored, as in the reference.
+        Scalar and 1-D forms (gizmo_interface.py:696-717)."""
+        x, y, z = (to_value(v, units.kpc) for v in (xlist, ylist, zlist))
+        scalar, acc, _ = self._interp_host_(x, y, z, False)
+        u = units.kms / units.Myr
+        if scalar:
+            return float(acc[0, 0]) | u, float(acc[1, 0]) | u, float(acc[2, 0]) | u
+        return acc[0] | u, acc[1] | u, acc[2] | u
+
+    def get_potential_at_point(self, eps, xlist, ylist, zlist):
+        """Potential of the snapshot particles at the given points in (km/s)^2 (AMUSE's convention for
+        get_potential_at_point); the uniform frame term removed from the accelerations is not integrated in."""
+        if not self.with_potential:
+            raise RuntimeError("field was built with with_potential=False")
+        x, y, z = (to_value(v, units.kpc) for v in (xlist, ylist, zlist))
+        scalar, _, pot = self._interp_host_(x, y, z, True)
+        pot = pot / KMS_TO_KPC_PER_MYR  # kpc km/s /Myr -> (km/s)^2
+        u = units.kms ** 2
+        return (float(pot[0]) | u) if scalar else (pot | u)
+
+    def kick_device(self, pos_kpc, vel_kms, dt_myr):
+        """Fused BRIDGE half-kick on device state (FP64 [3,n] tensors): v += dt * a_tidal(x). No host copies."""
+        acc, _ = self._interp_device_(pos_kpc[0], pos_kpc[1], pos_kpc[2], False)
+        self.ctx.kick(vel_kms, acc, dt_myr)
+
+    def stop(self):
+        pass
+
+
+# the name the reference's driver imports (oc_nbody.py:11)
+gizmo_interface = gizmo_field

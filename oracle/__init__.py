@@ -1,0 +1,252 @@
+"""CPU ORACLE for the oceanic gravity hot path — TEST INFRASTRUCTURE ONLY.
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` / ``--impl reference``
+legs may import this package.  The product (``oc_nbody_b200``) never does: it has no CPU fallback and
+fails loudly when its CUDA library is missing.
+
+PARITY UNPINNED BY THE REFERENCE: gusbeane/oc_nbody has no tests, golden vectors or fixtures for this
+path and cannot be imported.  What is pinned, and how, is listed in the header
+of ``oracle/ocg_oracle.c`` and in DESIGN.md §Oracle.
+
+The arithmetic lives in ``ocg_oracle.c`` (FP64, OpenMP); this module is the numpy-facing loader plus
+the pieces that are clearer in numpy (grid layout, time bracketing, the BRIDGE step order).
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SRC = os.path.join(_HERE, "ocg_oracle.c")
+_OUT = os.path.join(_HERE, "_build", "libocg_oracle.so")
+_lib = None
+
+KERNEL_PLUMMER = 0
+KERNEL_SPLINE = 1
+
+
+def _cpu_tag():
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith("model name"):
+                    return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
+def build(force=False):
+    """gcc -O3 -march=native -fopenmp -ffp-contract=off; rebuilt when the source or the host CPU changes
+    (the prebuilt file travels to the GPU box, whose CPU may differ from the build container's)."""
+    os.makedirs(os.path.dirname(_OUT), exist_ok=True)
+    stamp = _OUT + ".stamp"
+    tag = "%s|%d" % (_cpu_tag(), int(os.path.getmtime(_SRC)))
+    if not force and os.path.exists(_OUT) and os.path.exists(stamp) and open(stamp).read() == tag:
+        return _OUT
+    base = ["gcc", "-O3", "-fopenmp", "-fPIC", "-shared", "-ffp-contract=off", "-fno-math-errno", "-std=c11"]
+    for extra in (["-march=native"], []):
+        res = subprocess.run(base + extra + ["-o", _OUT, _SRC, "-lm"], capture_output=True, text=True)
+        if res.returncode == 0:
+            break
+    else:
+        raise RuntimeError("building the oracle failed:\n" + res.stderr)
+    with open(stamp, "w") as f:
+        f.write(tag)
+    return _OUT
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = ctypes.CDLL(build())
+        _lib.oracle_spline_force.restype = ctypes.c_double
+        _lib.oracle_spline_force.argtypes = [ctypes.c_double, ctypes.c_double]
+        _lib.oracle_spline_pot.restype = ctypes.c_double
+        _lib.oracle_spline_pot.argtypes = [ctypes.c_double, ctypes.c_double]
+        _lib.oracle_num_threads.restype = ctypes.c_int
+    return _lib
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+
+
+def _c(a, dt):
+    return None if a is None else np.ascontiguousarray(a, dtype=dt)
+
+
+def num_threads():
+    return int(lib().oracle_num_threads())
+
+
+# ------------------------------------------------------------------------------------------------
+def recentre(pos, mass, center):
+    """(float32)(pos - center) | mass -> [n,4] float32; the rounding the GPU path applies."""
+    pos = _c(pos, np.float64).reshape(-1, 3)
+    mass = _c(mass, np.float64)
+    center = _c(center, np.float64)
+    out = np.empty((pos.shape[0], 4), np.float32)
+    lib().oracle_recentre(_p(pos), _p(mass), ctypes.c_int64(pos.shape[0]), _p(center), _p(out))
+    return out
+
+
+def spline_force(r, h):
+    return lib().oracle_spline_force(float(r), float(h))
+
+
+def spline_pot(r, h):
+    return lib().oracle_spline_pot(float(r), float(h))
+
+
+def field_direct(src_xyzm, src_soft, tgt_xyzw, kernel, G, want_pot=False):
+    """FP64 direct sum on FP32-rounded inputs (gizmo_interface.py:561-566 at theta -> 0).
+    Returns acc [3,n_tgt] (and pot [n_tgt])."""
+    src = _c(src_xyzm, np.float32).reshape(-1, 4)
+    soft = _c(src_soft, np.float32)
+    tgt = _c(tgt_xyzw, np.float32).reshape(-1, 4)
+    acc = np.zeros((3, tgt.shape[0]), np.float64)
+    pot = np.zeros(tgt.shape[0], np.float64) if want_pot else None
+    lib().oracle_field_direct(_p(src), _p(soft), ctypes.c_int64(src.shape[0]), _p(tgt), ctypes.c_int64(tgt.shape[0]),
+                              ctypes.c_int(kernel), ctypes.c_double(G), _p(acc), _p(pot))
+    return (acc, pot) if want_pot else acc
+
+
+def field_direct_fast(src_pos, src_mass, src_e2, tgt_pos, G):
+    """Vectorisable Plummer sum for the timed CPU baseline (bench.py). FP64 SoA inputs."""
+    sp = _c(src_pos, np.float64).reshape(-1, 3)
+    sx, sy, sz = (np.ascontiguousarray(sp[:, k]) for k in range(3))
+    sm = _c(src_mass, np.float64)
+    se = _c(src_e2, np.float64)
+    tg = _c(tgt_pos, np.float64).reshape(-1, 3)
+    acc = np.zeros((3, tg.shape[0]), np.float64)
+    lib().oracle_field_direct_fast(_p(sx), _p(sy), _p(sz), _p(sm), _p(se), ctypes.c_int64(sp.shape[0]), _p(tg),
+                                   ctypes.c_int64(tg.shape[0]), ctypes.c_double(G), _p(acc))
+    return acc
+
+
+def frame_subtract(acc, row):
+    """acc[:, i] -= acc[:, row] (gizmo_interface.py:566,569-571)."""
+    acc = np.array(acc, np.float64, order="C", copy=True)
+    lib().oracle_frame_subtract(_p(acc), ctypes.c_int64(acc.shape[1]), ctypes.c_int64(row))
+    return acc
+
+
+def self_gravity(pos, mass, eps2, G, seg_offsets=None, t0=0, t1=None, want_pot=False):
+    """Plummer self-gravity per segment (ph4 force loop behind oc_code.py:218-229). pos [3,n] fp64."""
+    pos = _c(pos, np.float64)
+    n = pos.shape[1]
+    mass = _c(mass, np.float64)
+    seg = np.array([0, n], np.int64) if seg_offsets is None else _c(seg_offsets, np.int64)
+    t1 = n if t1 is None else t1
+    acc = np.zeros((3, n), np.float64)
+    pot = np.zeros(n, np.float64) if want_pot else None
+    lib().oracle_self_gravity(_p(pos), _p(mass), ctypes.c_int64(n), _p(seg), ctypes.c_int32(len(seg) - 1),
+                              ctypes.c_double(eps2), ctypes.c_double(G), ctypes.c_int64(t0), ctypes.c_int64(t1),
+                              _p(acc), _p(pot))
+    return (acc, pot) if want_pot else acc
+
+
+def pack_planes(acc, pot=None):
+    acc = _c(acc, np.float64)
+    n = acc.shape[1]
+    pot = _c(pot, np.float64)
+    rec = np.empty((n, 4), np.float32)
+    lib().oracle_pack_planes(_p(acc), _p(pot), ctypes.c_int64(n), _p(rec))
+    return rec
+
+
+def time_blend(rec_a, rec_b, wb, want_pot=False):
+    ra = _c(rec_a, np.float32).reshape(-1, 4)
+    rb = None if rec_b is None else _c(rec_b, np.float32).reshape(-1, 4)
+    n = ra.shape[0]
+    acc = np.empty((3, n), np.float64)
+    pot = np.empty(n, np.float64) if want_pot else None
+    lib().oracle_time_blend(_p(ra), _p(rb), ctypes.c_double(wb), ctypes.c_int64(n), _p(acc), _p(pot))
+    return (acc, pot) if want_pot else acc
+
+
+def grid_interp(nodes, origin, rec_a, rec_b, wb, sx, sy, sz, star_cluster=None, want_pot=False, want_cell=False):
+    """Trilinear + linear-in-time evaluation at star positions (get_gravity_at_point,
+    gizmo_interface.py:677-717, with the north_star's interpolation). nodes = (xg, yg, zg) fp64."""
+    xg, yg, zg = (_c(a, np.float64) for a in nodes)
+    origin = _c(origin, np.float64).reshape(-1, 3)
+    ra = _c(rec_a, np.float32)
+    rb = None if rec_b is None else _c(rec_b, np.float32)
+    sx, sy, sz = (_c(a, np.float64) for a in (sx, sy, sz))
+    scl = _c(star_cluster, np.int32)
+    n = sx.shape[0]
+    nn = np.array([len(xg), len(yg), len(zg)], np.int32)
+    acc = np.empty((3, n), np.float64)
+    pot = np.empty(n, np.float64) if want_pot else None
+    cell = np.empty((3, n), np.int32) if want_cell else None
+    lib().oracle_grid_interp(_p(nn), ctypes.c_int32(origin.shape[0]), _p(xg), _p(yg), _p(zg), _p(origin), _p(ra), _p(rb),
+                             ctypes.c_double(wb), _p(sx), _p(sy), _p(sz), _p(scl), ctypes.c_int64(n), _p(acc), _p(pot),
+                             _p(cell))
+    out = [acc]
+    if want_pot:
+        out.append(pot)
+    if want_cell:
+        out.append(cell)
+    return out[0] if len(out) == 1 else tuple(out)
+
+
+def kick(vel, acc, dt):
+    vel = np.array(vel, np.float64, order="C", copy=True)
+    acc = _c(acc, np.float64)
+    lib().oracle_kick(_p(vel), _p(acc), ctypes.c_int64(vel.shape[1]), ctypes.c_double(dt))
+    return vel
+
+
+def drift(pos, vel, dt, vel_to_len=1.0):
+    pos = np.array(pos, np.float64, order="C", copy=True)
+    vel = _c(vel, np.float64)
+    lib().oracle_drift(_p(pos), _p(vel), ctypes.c_int64(pos.shape[1]), ctypes.c_double(dt), ctypes.c_double(vel_to_len))
+    return pos
+
+
+# ---------------------------------------------------------------------------- numpy restatements ----
+def grid_layout(x_size, y_size, z_size, resolution):
+    """Restatement of grid_cartesian.py:16-32,59-69: n = int(L/res) nodes of np.linspace(-L, L, n) per
+    axis, points in C order (x outer, z inner), one origin row appended.
+    Returns (x_grid, y_grid, z_grid, init_grid[nx*ny*nz+1, 3])."""
+    n = [int(L / resolution) for L in (x_size, y_size, z_size)]
+    axes = [np.linspace(-L, L, num=k) for L, k in zip((x_size, y_size, z_size), n)]
+    rows = []
+    for xi in axes[0]:
+        for yj in axes[1]:
+            for zk in axes[2]:
+                rows.append((xi, yj, zk))
+    rows.append((0.0, 0.0, 0.0))
+    return axes[0], axes[1], axes[2], np.array(rows, np.float64).reshape(-1, 3)
+
+
+def time_bracket(times, t):
+    """Linear-in-time bracket for snapshot times (north_star's substitute for the per-node cubic splines of
+    gizmo_interface.py:587-620): index i with times[i] <= t < times[i+1] (clamped), weight of snapshot i+1."""
+    times = np.asarray(times, np.float64)
+    if len(times) == 1:
+        return 0, 0, 0.0
+    i = int(np.searchsorted(times, t, side="right")) - 1
+    i = min(max(i, 0), len(times) - 2)
+    w = (t - times[i]) / (times[i + 1] - times[i])
+    w = min(max(w, 0.0), 1.0)
+    return i, i + 1, float(w)
+
+
+def bridge_step(pos_pc, vel_kms, mass, eps2_pc2, G_pc, dt_myr, tidal_acc, kms_myr_to_pc):
+    """One BRIDGE step in the order amuse.couple.bridge runs it for oc_nbody.py:49-56:
+    K(dt/2) by the field code, D(dt) of the cluster under self-gravity, K(dt/2).
+
+    The drift is a kick-drift-kick leapfrog (north_star's substitute for ph4's Hermite).
+    pos [3,n] pc, vel [3,n] km/s; tidal_acc(pos_pc) -> [3,n] km/s/Myr; self-gravity in (km/s)^2/pc is
+    converted to km/s/Myr by ``kms_myr_to_pc`` (pc travelled per Myr at 1 km/s)."""
+    v = kick(vel_kms, tidal_acc(pos_pc), 0.5 * dt_myr)
+    a = self_gravity(pos_pc, mass, eps2_pc2, G_pc) * kms_myr_to_pc
+    v = kick(v, a, 0.5 * dt_myr)
+    x = drift(pos_pc, v, dt_myr, kms_myr_to_pc)
+    a = self_gravity(x, mass, eps2_pc2, G_pc) * kms_myr_to_pc
+    v = kick(v, a, 0.5 * dt_myr)
+    v = kick(v, tidal_acc(x), 0.5 * dt_myr)
+    return x, v

@@ -1,0 +1,284 @@
+/*
+ * ocg_oracle.c — CPU ORACLE for the oceanic gravity hot path.  TEST INFRASTRUCTURE ONLY.
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+ * load this file's library; the product (oc_nbody_b200/) never does and has no CPU fallback.
+ *
+ * PARITY UNPINNED BY THE REFERENCE: gusbeane/oc_nbody ships no tests, golden vectors or fixtures
+ * (SURVEY.md §4, §8c), cannot be imported (analysis.py:573 SyntaxError; amuse/pykdgrav/rbf absent)
+ * and the arithmetic of its field build lives in un-vendored, un-pinned pykdgrav.  What IS pinned:
+ *   - the grid layout, against the real grid_cartesian.py imported in the build container
+ *     (tests/golden/grid_*.npz, made by tests/golden/make_golden.py);
+ *   - the spline kernel, restated from pykdgrav's published ForceKernel/PotentialKernel
+ *     (M. Grudic, pykdgrav/pytreegrav kernel.py; cubic spline of Springel et al. 2001 with
+ *     support radius h), checked for continuity/Newtonian limits and against scipy quadrature of
+ *     the spline density in tests/test_oracle.py;
+ *   - analytic known answers (two-body, shell theorem, homogeneous sphere, affine fields).
+ *
+ * Every function is the FP64 restatement of one step of the reference with the north_star's
+ * algorithm substitutions (direct sum for the theta=0.5 tree, trilinear for RBF, linear-in-time
+ * for the cubic spline, leapfrog for ph4) — see SURVEY.md §0 table.
+ *
+ * Build: gcc -O3 -fopenmp -ffp-contract=off (no FMA contraction: oracle_grid_interp and the
+ * kick/drift must round every mul and add separately, like the CUDA kernels do).
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#define KERNEL_PLUMMER 0
+#define KERNEL_SPLINE 1
+
+int oracle_num_threads(void) {
+#ifdef _OPENMP
+  return omp_get_max_threads();
+#else
+  return 1;
+#endif
+}
+
+/* (float)(pos - center): the FP32 rounding the GPU path applies after recentring in FP64
+ * (SURVEY §7 H3).  pos [n][3] fp64 -> out [n][4] fp32 (x,y,z,m). */
+void oracle_recentre(const double* pos, const double* mass, int64_t n, const double* center, float* out) {
+  for (int64_t i = 0; i < n; ++i) {
+    out[4 * i + 0] = (float)(pos[3 * i + 0] - center[0]);
+    out[4 * i + 1] = (float)(pos[3 * i + 1] - center[1]);
+    out[4 * i + 2] = (float)(pos[3 * i + 2] - center[2]);
+    out[4 * i + 3] = mass ? (float)mass[i] : 0.0f;
+  }
+}
+
+/* pykdgrav ForceKernel(r, h): (mass fraction enclosed)/r^3 of a cubic-spline blob of support h. */
+static inline double spline_force(double r, double h) {
+  if (r >= h) return 1.0 / (r * r * r);
+  double hinv = 1.0 / h, q = r * hinv;
+  if (q <= 0.5) return (32.0 / 3.0 + q * q * (32.0 * q - 38.4)) * hinv * hinv * hinv;
+  return (64.0 / 3.0 - 48.0 * q + 38.4 * q * q - (32.0 / 3.0) * q * q * q - (1.0 / 15.0) / (q * q * q)) * hinv * hinv * hinv;
+}
+/* pykdgrav PotentialKernel(r, h) (negative). */
+static inline double spline_pot(double r, double h) {
+  if (r >= h) return -1.0 / r;
+  double hinv = 1.0 / h, q = r * hinv;
+  if (q <= 0.5) return (-2.8 + q * q * (16.0 / 3.0 + q * q * (6.4 * q - 9.6))) * hinv;
+  return (-3.2 + (1.0 / 15.0) / q + q * q * (32.0 / 3.0 + q * (-16.0 + q * (9.6 - (32.0 / 15.0) * q)))) * hinv;
+}
+double oracle_spline_force(double r, double h) { return spline_force(r, h); }
+double oracle_spline_pot(double r, double h) { return spline_pot(r, h); }
+
+/* Field build, direct sum (gizmo_interface.py:561,564,566 at theta -> 0):
+ *   acc[c][t] = G sum_s m_s K(|x_s - x_t|, soft_s) (x_s - x_t)[c]     pot[t] = G sum_s m_s P(...)
+ * Inputs are the SAME FP32-rounded arrays the GPU consumes; all arithmetic FP64.
+ * Pair rule: Plummer: skipped iff r^2 + soft^2 == 0; spline: skipped iff r == 0. */
+void oracle_field_direct(const float* src_xyzm, const float* src_soft, int64_t n_src, const float* tgt_xyzw,
+                         int64_t n_tgt, int kernel, double G, double* acc, double* pot) {
+#pragma omp parallel for schedule(static)
+  for (int64_t t = 0; t < n_tgt; ++t) {
+    const double tx = tgt_xyzw[4 * t], ty = tgt_xyzw[4 * t + 1], tz = tgt_xyzw[4 * t + 2];
+    double ax = 0, ay = 0, az = 0, ph = 0;
+    if (kernel == KERNEL_PLUMMER) {
+      for (int64_t s = 0; s < n_src; ++s) {
+        const double dx = src_xyzm[4 * s] - tx, dy = src_xyzm[4 * s + 1] - ty, dz = src_xyzm[4 * s + 2] - tz;
+        const double m = src_xyzm[4 * s + 3];
+        const double e = src_soft ? (double)src_soft[s] : 0.0;
+        const double r2 = dx * dx + dy * dy + dz * dz + e * e;
+        if (r2 > 0.0) {
+          const double ri = 1.0 / sqrt(r2);
+          const double f = m * ri * ri * ri;
+          ax += f * dx, ay += f * dy, az += f * dz;
+          ph -= m * ri;
+        }
+      }
+    } else {
+      for (int64_t s = 0; s < n_src; ++s) {
+        const double dx = src_xyzm[4 * s] - tx, dy = src_xyzm[4 * s + 1] - ty, dz = src_xyzm[4 * s + 2] - tz;
+        const double m = src_xyzm[4 * s + 3];
+        const double h = src_soft ? (double)src_soft[s] : 0.0;
+        const double r2 = dx * dx + dy * dy + dz * dz;
+        if (r2 > 0.0) {
+          const double r = sqrt(r2);
+          double f, p;
+          if (r >= h) {
+            const double ri = 1.0 / r;
+            f = ri * ri * ri, p = -ri;
+          } else {
+            f = spline_force(r, h), p = spline_pot(r, h);
+          }
+          ax += m * f * dx, ay += m * f * dy, az += m * f * dz;
+          ph += m * p;
+        }
+      }
+    }
+    acc[t] = G * ax, acc[n_tgt + t] = G * ay, acc[2 * n_tgt + t] = G * az;
+    if (pot) pot[t] = G * ph;
+  }
+}
+
+/* Throughput-oriented variant of the Plummer sum for the timed CPU baseline: identical maths, sources
+ * pre-split into SoA FP64 so gcc can vectorise the inner loop.  Used by bench.py only. */
+void oracle_field_direct_fast(const double* sx, const double* sy, const double* sz, const double* sm,
+                              const double* se2, int64_t n_src, const double* tgt_xyz, int64_t n_tgt, double G,
+                              double* acc) {
+#pragma omp parallel for schedule(dynamic, 16)
+  for (int64_t t = 0; t < n_tgt; ++t) {
+    const double tx = tgt_xyz[3 * t], ty = tgt_xyz[3 * t + 1], tz = tgt_xyz[3 * t + 2];
+    double ax = 0, ay = 0, az = 0;
+#pragma omp simd reduction(+ : ax, ay, az)
+    for (int64_t s = 0; s < n_src; ++s) {
+      const double dx = sx[s] - tx, dy = sy[s] - ty, dz = sz[s] - tz;
+      const double r2 = dx * dx + dy * dy + dz * dz + se2[s];
+      const double ri = 1.0 / sqrt(r2);
+      const double f = sm[s] * ri * ri * ri;
+      ax += f * dx, ay += f * dy, az += f * dz;
+    }
+    acc[t] = G * ax, acc[n_tgt + t] = G * ay, acc[2 * n_tgt + t] = G * az;
+  }
+}
+
+/* Frame subtraction (gizmo_interface.py:566,569-571). acc [3][n]. */
+void oracle_frame_subtract(double* acc, int64_t n, int64_t row) {
+  for (int c = 0; c < 3; ++c) {
+    const double v = acc[c * n + row];
+    for (int64_t i = 0; i < n; ++i) acc[c * n + i] = acc[c * n + i] - v;
+  }
+}
+
+/* Cluster self-gravity (ph4 force loop, oc_code.py:218-229, eps2 = oc_code.py:225), batch of
+ * segments.  pos [3][n] fp64, mass [n]; each segment recentred on its first particle then rounded
+ * to FP32 exactly as the GPU path does; pair sums in FP64; self pair excluded by index; a pair
+ * with r^2 + eps2 == 0 contributes nothing. Outputs only for [t0, t1). */
+void oracle_self_gravity(const double* pos, const double* mass, int64_t n, const int64_t* seg_off, int32_t n_seg,
+                         double eps2, double G, int64_t t0, int64_t t1, double* acc, double* pot) {
+  float* r = (float*)malloc(sizeof(float) * 4 * (size_t)n);
+  for (int s = 0; s < n_seg; ++s) {
+    const int64_t a = seg_off[s], b = seg_off[s + 1];
+    if (b <= a) continue;
+    const double cx = pos[a], cy = pos[n + a], cz = pos[2 * n + a];
+    for (int64_t i = a; i < b; ++i) {
+      r[4 * i] = (float)(pos[i] - cx), r[4 * i + 1] = (float)(pos[n + i] - cy), r[4 * i + 2] = (float)(pos[2 * n + i] - cz);
+      r[4 * i + 3] = (float)mass[i];
+    }
+  }
+  const double e2 = (double)(float)eps2;
+  for (int s = 0; s < n_seg; ++s) {
+    const int64_t a = seg_off[s], b = seg_off[s + 1];
+    const int64_t lo = a > t0 ? a : t0, hi = b < t1 ? b : t1;
+#pragma omp parallel for schedule(static)
+    for (int64_t i = lo; i < hi; ++i) {
+      double ax = 0, ay = 0, az = 0, ph = 0;
+      const double tx = r[4 * i], ty = r[4 * i + 1], tz = r[4 * i + 2];
+      for (int64_t j = a; j < b; ++j) {
+        if (j == i) continue;
+        const double dx = r[4 * j] - tx, dy = r[4 * j + 1] - ty, dz = r[4 * j + 2] - tz;
+        const double r2 = dx * dx + dy * dy + dz * dz + e2;
+        if (r2 > 0.0) {
+          const double ri = 1.0 / sqrt(r2), m = r[4 * j + 3];
+          const double f = m * ri * ri * ri;
+          ax += f * dx, ay += f * dy, az += f * dz;
+          ph -= m * ri;
+        }
+      }
+      acc[i] = G * ax, acc[n + i] = G * ay, acc[2 * n + i] = G * az;
+      if (pot) pot[i] = G * ph;
+    }
+  }
+  free(r);
+}
+
+/* Cell along one axis = searchsorted(node + o, x, side='right') - 1 clamped to [0, n-2]
+ * (the bit-exact cell-selection rule; nodes = np.linspace of grid_cartesian.py:29-31,
+ * shifted by evolve_grid's position, gizmo_interface.py:640-642 / grid_cartesian.py:55-57). */
+static int find_cell(const double* node, int n, double o, double x) {
+  int lo = 0, hi = n; /* first index with node+o > x */
+  while (lo < hi) {
+    int mid = (lo + hi) / 2;
+    if (node[mid] + o > x) hi = mid;
+    else lo = mid + 1;
+  }
+  int i = lo - 1;
+  if (i < 0) i = 0;
+  if (i > n - 2) i = n - 2;
+  return i;
+}
+
+static inline double lerp2(double a, double wa, double b, double wb) { return a * wa + b * wb; }
+
+/* get_gravity_at_point (gizmo_interface.py:677-717) as trilinear-in-space, linear-in-time.
+ * rec_a/rec_b: [n_cluster][nx*ny*nz+1][4] FP32 node records (ax,ay,az,phi) of the bracketing
+ * snapshots (rec_b may be NULL), wb weight of b.  Operation order identical to the CUDA kernel. */
+void oracle_grid_interp(const int32_t* nn, int32_t n_cluster, const double* nodex, const double* nodey,
+                        const double* nodez, const double* origin, const float* rec_a, const float* rec_b, double wb,
+                        const double* sx, const double* sy, const double* sz, const int32_t* scl, int64_t n_star,
+                        double* acc, double* pot, int32_t* cell) {
+  (void)n_cluster;
+  const int nx = nn[0], ny = nn[1], nz = nn[2];
+  const int64_t nyz = (int64_t)ny * nz, n_node = (int64_t)nx * nyz + 1;
+  const double wa = 1.0 - wb;
+#pragma omp parallel for schedule(static)
+  for (int64_t s = 0; s < n_star; ++s) {
+    const int cl = scl ? scl[s] : 0;
+    const double* o = origin + 3 * (int64_t)cl;
+    const int i = find_cell(nodex, nx, o[0], sx[s]);
+    const int j = find_cell(nodey, ny, o[1], sy[s]);
+    const int k = find_cell(nodez, nz, o[2], sz[s]);
+    const double x0 = nodex[i] + o[0], x1 = nodex[i + 1] + o[0];
+    const double y0 = nodey[j] + o[1], y1 = nodey[j + 1] + o[1];
+    const double z0 = nodez[k] + o[2], z1 = nodez[k + 1] + o[2];
+    const double tx = (sx[s] - x0) / (x1 - x0), ty = (sy[s] - y0) / (y1 - y0), tz = (sz[s] - z0) / (z1 - z0);
+    const double ux = 1.0 - tx, uy = 1.0 - ty, uz = 1.0 - tz;
+    const int64_t base = (int64_t)cl * n_node + ((int64_t)i * ny + j) * nz + k;
+    double v[8][4];
+    for (int c = 0; c < 8; ++c) {
+      const int64_t off = (int64_t)(c >> 2) * nyz + (int64_t)((c >> 1) & 1) * nz + (c & 1);
+      const float* a = rec_a + 4 * (base + off);
+      if (rec_b) {
+        const float* b = rec_b + 4 * (base + off);
+        for (int q = 0; q < 4; ++q) v[c][q] = lerp2((double)a[q], wa, (double)b[q], wb);
+      } else {
+        for (int q = 0; q < 4; ++q) v[c][q] = (double)a[q];
+      }
+    }
+    const int ncomp = pot ? 4 : 3;
+    for (int q = 0; q < ncomp; ++q) {
+      const double c00 = lerp2(v[0][q], uz, v[1][q], tz), c01 = lerp2(v[2][q], uz, v[3][q], tz);
+      const double c10 = lerp2(v[4][q], uz, v[5][q], tz), c11 = lerp2(v[6][q], uz, v[7][q], tz);
+      const double c0 = lerp2(c00, uy, c01, ty), c1 = lerp2(c10, uy, c11, ty);
+      const double r = lerp2(c0, ux, c1, tx);
+      if (q < 3) acc[(int64_t)q * n_star + s] = r;
+      else pot[s] = r;
+    }
+    if (cell) cell[s] = i, cell[n_star + s] = j, cell[2 * n_star + s] = k;
+  }
+}
+
+/* rec[i] = (float)(ax, ay, az, phi) — the FP32 node records K3 reads. acc [3][n]. */
+void oracle_pack_planes(const double* acc, const double* pot, int64_t n, float* rec) {
+  for (int64_t i = 0; i < n; ++i) {
+    rec[4 * i] = (float)acc[i], rec[4 * i + 1] = (float)acc[n + i], rec[4 * i + 2] = (float)acc[2 * n + i];
+    rec[4 * i + 3] = pot ? (float)pot[i] : 0.0f;
+  }
+}
+
+/* Linear time blend of node records (gizmo_interface.py:607-620 in linear form). */
+void oracle_time_blend(const float* ra, const float* rb, double wb, int64_t n, double* acc, double* pot) {
+  const double wa = 1.0 - wb;
+  for (int64_t i = 0; i < n; ++i) {
+    const float* a = ra + 4 * i;
+    const float* b = rb ? rb + 4 * i : a;
+    acc[i] = lerp2((double)a[0], wa, (double)b[0], wb);
+    acc[n + i] = lerp2((double)a[1], wa, (double)b[1], wb);
+    acc[2 * n + i] = lerp2((double)a[2], wa, (double)b[2], wb);
+    if (pot) pot[i] = lerp2((double)a[3], wa, (double)b[3], wb);
+  }
+}
+
+/* BRIDGE kick and leapfrog drift (oc_nbody.py:56 via amuse.couple.bridge): separately rounded. */
+void oracle_kick(double* vel, const double* acc, int64_t n, double dt) {
+  for (int64_t i = 0; i < 3 * n; ++i) vel[i] = vel[i] + acc[i] * dt;
+}
+void oracle_drift(double* pos, const double* vel, int64_t n, double dt, double vel_to_len) {
+  for (int64_t i = 0; i < 3 * n; ++i) pos[i] = pos[i] + (vel[i] * dt) * vel_to_len;
+}

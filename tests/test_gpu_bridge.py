@@ -1,0 +1,137 @@
+"""GPU integration: the plugin classes (field code, cluster code, Bridge) against the oracle pipeline.
+Config 1 of BASELINE.json in miniature: 1k-star Plummer cluster BRIDGE-kicked by a 16^3 grid field."""
+import numpy as np
+import pytest
+
+import oracle
+from util import TOL, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def oracle_field(field, snap, center, want_pot=True):
+    """The oracle's version of _populate_grid_acceleration_ for one snapshot."""
+    r, m, soft = field._source_arrays_(snap)
+    g = field.grid
+    tgt = g.init_grid + center
+    s32 = oracle.recentre(r, m, center)
+    t32 = oracle.recentre(tgt, None, center)
+    kern = oracle.KERNEL_SPLINE if field.softening_kernel == "spline" else oracle.KERNEL_PLUMMER
+    raw, pot = oracle.field_direct(s32, soft.astype(np.float32), t32, kern, field.G, want_pot=True)
+    return raw, oracle.frame_subtract(raw, g.origin_row), pot
+
+
+@pytest.fixture(scope="module")
+def small_world(ctx):
+    from oc_nbody_b200.gizmo_field import gizmo_field
+    from oc_nbody_b200.synthetic import advance_snapshot, make_snapshot
+    snap0 = make_snapshot(40000, seed=1776)
+    snap1 = advance_snapshot(snap0, 23.0)
+    opts = dict(grid_x_size_in_kpc=0.06, grid_y_size_in_kpc=0.06, grid_z_size_in_kpc=0.06, grid_resolution=0.06 / 8,
+                softening_kernel="spline")
+    centers = np.array([[8.0, 0.0, 0.0], [7.99, 0.19, 0.0]])
+    field = gizmo_field(opts, [snap0, snap1], chosen_positions=centers, chosen_id=5, ctx=ctx)
+    return field, (snap0, snap1), centers
+
+
+def test_field_code_build_matches_oracle(small_world):
+    field, snaps, centers = small_world
+    g = field.grid
+    assert g.snapshot_acceleration_x.shape == (2, 8 ** 3 + 1)
+    for i in range(2):
+        raw, sub, pot = oracle_field(field, snaps[i], centers[i])
+        got = np.stack([g.snapshot_acceleration_x[i], g.snapshot_acceleration_y[i], g.snapshot_acceleration_z[i]])
+        assert np.all(got[:, g.origin_row] == 0.0)
+        assert rel_err(got + raw[:, g.origin_row:g.origin_row + 1], raw) <= TOL
+        assert np.max(np.abs(g.snapshot_potential[i] - pot) / np.abs(pot)) <= TOL
+
+
+def test_get_gravity_at_point_forms(small_world):
+    from oc_nbody_b200.units import units
+    field, _, _ = small_world
+    rng = np.random.default_rng(3)
+    g = field.grid
+    field.evolve_grid(np.array([8.0, 0.0, 0.0]))
+    field.evolve_model(9.2 | units.Myr)
+    a, b, w = field._bracket
+    assert (a, b) == (0, 1) and abs(w - 0.4) < 1e-12
+    p = rng.uniform(-0.05, 0.05, (257, 3)) + np.array([8.0, 0.0, 0.0])
+    ax, ay, az = field.get_gravity_at_point(0 | units.kpc, p[:, 0] | units.kpc, p[:, 1] | units.kpc, p[:, 2] | units.kpc)
+    got = np.stack([c.value_in(units.kms / units.Myr) for c in (ax, ay, az)])
+    # oracle on the arrays the field code itself exposes (fp64 stacks -> fp32 records)
+    recs = [oracle.pack_planes(np.stack([g.snapshot_acceleration_x[i], g.snapshot_acceleration_y[i],
+                                         g.snapshot_acceleration_z[i]]), g.snapshot_potential[i]) for i in range(2)]
+    ref, refpot = oracle.grid_interp(g.nodes, np.array([[8.0, 0.0, 0.0]]), recs[0], recs[1], w, p[:, 0], p[:, 1], p[:, 2],
+                                     want_pot=True)
+    assert np.array_equal(got, ref)
+    # scalar form, parsec input
+    sx, sy, sz = field.get_gravity_at_point(0 | units.kpc, p[0, 0] * 1e3 | units.parsec, p[0, 1] * 1e3 | units.parsec,
+                                            p[0, 2] * 1e3 | units.parsec)
+    assert abs(sx.value_in(units.kms / units.Myr) - ref[0, 0]) <= 1e-9 * abs(ref[0, 0])
+    phi = field.get_potential_at_point(0 | units.kpc, p[:, 0] | units.kpc, p[:, 1] | units.kpc, p[:, 2] | units.kpc)
+    assert np.allclose(phi.value_in(units.kms ** 2), refpot / 1.022712165045695e-3, rtol=1e-14)
+    # materialised blend equals the oracle's
+    assert np.array_equal(field.evolved_acceleration, oracle.time_blend(recs[0], recs[1], w))
+    # bare floats (already kpc) are accepted too
+    fx, _, _ = field.get_gravity_at_point(0.0, p[:, 0], p[:, 1], p[:, 2])
+    assert np.array_equal(fx.value_in(units.kms / units.Myr), ref[0])
+
+
+def test_bridge_steps_match_oracle(small_world, ctx):
+    """K(dt/2) D(dt) K(dt/2) for a few steps: device-resident path and generic-partner path vs the CPU BRIDGE."""
+    from oc_nbody_b200.bridge import Bridge
+    from oc_nbody_b200.cluster import KMS_TO_KPC_PER_MYR, cluster_code
+    from oc_nbody_b200.synthetic import make_plummer_cluster
+    from oc_nbody_b200.units import units
+    field, _, _ = small_world
+    g = field.grid
+    pos_pc, vel, mass = make_plummer_cluster(1024)
+    center = np.array([8.0, 0.0, 0.0])
+    pos = pos_pc * 1e-3 + center[:, None]
+    field.evolve_grid(center)
+    field.evolve_model(0.0 | units.Myr)
+    dt, nstep = 0.1, 3
+    eps2 = (0.01e-3) ** 2
+    recs = [oracle.pack_planes(np.stack([g.snapshot_acceleration_x[i], g.snapshot_acceleration_y[i],
+                                         g.snapshot_acceleration_z[i]]), g.snapshot_potential[i]) for i in range(2)]
+
+    # CPU BRIDGE with the oracle pieces; field time advances inside the drift like amuse's bridge does
+    x, v, t = pos.copy(), vel.copy(), 0.0
+    for _ in range(nstep):
+        def tidal(xx, tt):
+            _, _, w = oracle.time_bracket(field.time_in_Myr, tt)
+            return oracle.grid_interp(g.nodes, center[None], recs[0], recs[1], w, xx[0], xx[1], xx[2])
+        v = oracle.kick(v, tidal(x, t), 0.5 * dt)
+        a = oracle.self_gravity(x, mass, eps2, field.G)
+        v = oracle.kick(v, a, 0.5 * dt)
+        x = oracle.drift(x, v, dt, KMS_TO_KPC_PER_MYR)
+        a = oracle.self_gravity(x, mass, eps2, field.G)
+        v = oracle.kick(v, a, 0.5 * dt)
+        t += dt
+        v = oracle.kick(v, tidal(x, t), 0.5 * dt)
+
+    for generic in (False, True):
+        cl = cluster_code(mass, pos, vel, softening_pc=0.01, ctx=ctx)
+        field.evolve_model(0.0 | units.Myr)
+        partner = field
+        if generic:
+            class Wrapped(object):  # hides kick_device: forces the public get_gravity_at_point path
+                def get_gravity_at_point(self, *a):
+                    return field.get_gravity_at_point(*a)
+
+                def evolve_model(self, *a, **k):
+                    return field.evolve_model(*a, **k)
+            partner = Wrapped()
+        system = Bridge(timestep=dt | units.Myr, use_threading=False)
+        system.add_system(cl, (partner,))
+        system.add_system(partner)
+        for i in range(nstep + 1):
+            system.evolve_model(i * dt | units.Myr, timestep=dt | units.Myr)
+        p = system.particles
+        gx = p.position.value_in(units.kpc).T - center[:, None]
+        gv = p.velocity.value_in(units.kms).T
+        # offsets from the cluster centre (pc scale) and velocities both within 1e-5
+        assert rel_err(gx, x - center[:, None]) <= TOL
+        assert rel_err(gv, v) <= TOL
+    com = cl.bound_center_of_mass()
+    assert np.linalg.norm(com - center) < 2e-3

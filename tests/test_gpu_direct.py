@@ -1,0 +1,199 @@
+"""GPU parity: K1 field build and K4 self-gravity through the C ABI vs the FP64 oracle."""
+import numpy as np
+import pytest
+
+import oracle
+from util import TOL, dev, grid_targets, random_sources, rel_err, rel_err_scalar
+
+pytestmark = pytest.mark.gpu
+G = 4.3986004135e-09
+
+
+def run_k1(ctx, src, soft, tgt, kernel, want_pot=False, accumulate_parts=1):
+    import torch
+    n_tgt = tgt.shape[0]
+    acc = torch.full((3, n_tgt), 7.0, dtype=torch.float64, device="cuda")
+    pot = torch.full((n_tgt,), 7.0, dtype=torch.float64, device="cuda") if want_pot else None
+    d_tgt = dev(tgt)
+    bounds = np.linspace(0, src.shape[0], accumulate_parts + 1).astype(int)
+    for k in range(accumulate_parts):
+        s, e = bounds[k], bounds[k + 1]
+        ctx.field_direct(dev(src[s:e]), None if soft is None else dev(soft[s:e]), d_tgt, kernel, G, acc, pot,
+                         accumulate=(k > 0))
+    torch.cuda.synchronize()
+    return acc.cpu().numpy(), (pot.cpu().numpy() if want_pot else None)
+
+
+@pytest.mark.parametrize("kernel", [oracle.KERNEL_PLUMMER, oracle.KERNEL_SPLINE])
+@pytest.mark.parametrize("n_src,n_grid", [(20000, 12), (1537, 5), (513, 3)])
+def test_field_direct_parity(ctx, kernel, n_src, n_grid):
+    rng = np.random.default_rng(1776 + n_src)
+    src, soft = random_sources(rng, n_src, box=2.0)
+    tgt = grid_targets(n_grid)
+    acc, pot = run_k1(ctx, src, soft, tgt, kernel, want_pot=True)
+    ref, pref = oracle.field_direct(src, soft, tgt, kernel, G, want_pot=True)
+    assert rel_err(acc, ref) <= TOL
+    assert rel_err_scalar(pot, pref) <= TOL
+
+
+def test_field_direct_sources_inside_support(ctx):
+    """Spline sources sitting inside the grid box with supports that cover many targets (the near set)."""
+    rng = np.random.default_rng(7)
+    src, soft = random_sources(rng, 4000, box=0.4, soft_lo=0.05, soft_hi=0.8)
+    tgt = grid_targets(9)
+    for kernel in (oracle.KERNEL_SPLINE, oracle.KERNEL_PLUMMER):
+        acc, pot = run_k1(ctx, src, soft, tgt, kernel, want_pot=True)
+        ref, pref = oracle.field_direct(src, soft, tgt, kernel, G, want_pot=True)
+        assert rel_err(acc, ref) <= TOL
+        assert rel_err_scalar(pot, pref) <= TOL
+
+
+def test_field_direct_no_potential_and_accumulate(ctx):
+    rng = np.random.default_rng(11)
+    src, soft = random_sources(rng, 9000, box=3.0)
+    tgt = grid_targets(7)
+    ref = oracle.field_direct(src, soft, tgt, oracle.KERNEL_PLUMMER, G)
+    acc1, _ = run_k1(ctx, src, soft, tgt, oracle.KERNEL_PLUMMER)
+    acc3, _ = run_k1(ctx, src, soft, tgt, oracle.KERNEL_PLUMMER, accumulate_parts=3)
+    assert rel_err(acc1, ref) <= TOL
+    assert rel_err(acc3, ref) <= TOL
+
+
+def test_field_direct_deterministic(ctx):
+    rng = np.random.default_rng(12)
+    src, soft = random_sources(rng, 30000, box=3.0)
+    tgt = grid_targets(10)
+    a, _ = run_k1(ctx, src, soft, tgt, oracle.KERNEL_SPLINE)
+    b, _ = run_k1(ctx, src, soft, tgt, oracle.KERNEL_SPLINE)
+    assert np.array_equal(a, b)
+
+
+def test_field_direct_edge_cases(ctx):
+    import torch
+    rng = np.random.default_rng(13)
+    tgt = grid_targets(4)
+    # no sources: overwrite with zeros
+    acc = torch.full((3, tgt.shape[0]), 3.0, dtype=torch.float64, device="cuda")
+    ctx.field_direct(torch.empty((0, 4), dtype=torch.float32, device="cuda"), None, dev(tgt), 0, G, acc)
+    assert float(acc.abs().max()) == 0.0
+    # one source, one target, no softening array (Newtonian two-body known answer)
+    src = np.array([[0.3, -0.4, 1.2, 5.0e4]], np.float32)
+    one = np.array([[0.0, 0.0, 0.0, 0.0]], np.float32)
+    acc, pot = run_k1(ctx, src, None, one, oracle.KERNEL_PLUMMER, want_pot=True)
+    r = np.sqrt(np.float64(src[0, 0]) ** 2 + np.float64(src[0, 1]) ** 2 + np.float64(src[0, 2]) ** 2)
+    exact = G * np.float64(src[0, 3]) * src[0, :3].astype(np.float64) / r ** 3
+    assert np.max(np.abs(acc[:, 0] - exact) / np.abs(exact)) <= TOL
+    assert abs(pot[0] + G * np.float64(src[0, 3]) / r) / (G * src[0, 3] / r) <= TOL
+    # coincident target and unsoftened source contributes nothing (r == 0 rule) in both kernels
+    src = np.concatenate([random_sources(rng, 700, box=1.0)[0], np.array([[0.0, 0.0, 0.0, 1e9]], np.float32)])
+    soft = np.concatenate([np.full(700, 0.05, np.float32), np.zeros(1, np.float32)])
+    for kernel in (oracle.KERNEL_PLUMMER, oracle.KERNEL_SPLINE):
+        acc, pot = run_k1(ctx, src, soft, tgt, kernel, want_pot=True)
+        ref, pref = oracle.field_direct(src, soft, tgt, kernel, G, want_pot=True)
+        assert np.all(np.isfinite(acc)) and np.all(np.isfinite(pot))
+        assert rel_err(acc, ref) <= TOL
+        assert rel_err_scalar(pot, pref) <= TOL
+
+
+@pytest.mark.parametrize("tpt,scalar", [(1, 0), (2, 0), (1, 1), (2, 1)])
+def test_field_direct_variants(ctx, tpt, scalar):
+    """Every compiled variant of the streaming kernel (targets/thread, packed vs scalar FP32)."""
+    rng = np.random.default_rng(21)
+    src, soft = random_sources(rng, 11000, box=2.0)
+    tgt = grid_targets(11)
+    ref, pref = oracle.field_direct(src, soft, tgt, oracle.KERNEL_PLUMMER, G, want_pot=True)
+    ctx.lib.ocg_debug_set_variant(tpt, scalar)
+    try:
+        acc, pot = run_k1(ctx, src, soft, tgt, oracle.KERNEL_PLUMMER, want_pot=True)
+    finally:
+        ctx.lib.ocg_debug_set_variant(0, 0)
+    assert rel_err(acc, ref) <= TOL
+    assert rel_err_scalar(pot, pref) <= TOL
+
+
+def test_frame_subtract_and_host_form(ctx):
+    import torch
+    rng = np.random.default_rng(31)
+    center = np.array([8.0, 0.1, -0.2])
+    n_src = 6000
+    pos = rng.normal(0, 4.0, (n_src, 3)) + center * 0.5
+    mass = np.exp(rng.uniform(np.log(1e3), np.log(1e5), n_src))
+    soft = np.exp(rng.uniform(np.log(0.004), np.log(0.3), n_src))
+    tgt4 = grid_targets(6)
+    tgt = tgt4[:, :3].astype(np.float64) + center
+    row = tgt.shape[0] - 1
+    acc = ctx.field_build_host(pos, mass, soft, tgt, center, row, oracle.KERNEL_SPLINE, G)
+    assert np.all(acc[:, row] == 0.0)
+    s32 = oracle.recentre(pos, mass, center)
+    t32 = oracle.recentre(tgt, None, center)
+    raw = oracle.field_direct(s32, soft.astype(np.float32), t32, oracle.KERNEL_SPLINE, G)
+    ref = oracle.frame_subtract(raw, row)
+    # gate on the raw field: add the frame term back
+    assert rel_err(acc + raw[:, row:row + 1], raw) <= TOL
+    # report-only residual metric
+    print("tidal residual rel err:", rel_err(acc, ref))
+    # device K1b alone
+    d = dev(raw.copy())
+    ctx.frame_subtract(d, row)
+    torch.cuda.synchronize()
+    assert np.array_equal(d.cpu().numpy(), ref)
+
+
+@pytest.mark.parametrize("n,eps_pc", [(1024, 0.01), (777, 0.0), (4100, 0.05)])
+def test_self_gravity_parity(ctx, n, eps_pc):
+    import torch
+    from oc_nbody_b200.synthetic import make_plummer_cluster
+    pos_pc, _, mass = make_plummer_cluster(n, seed=n)
+    pos = pos_pc * 1e-3 + np.array([[8.0], [0.01], [-0.02]])  # kpc, far from the origin
+    eps2 = (eps_pc * 1e-3) ** 2
+    acc = torch.empty((3, n), dtype=torch.float64, device="cuda")
+    pot = torch.empty(n, dtype=torch.float64, device="cuda")
+    ctx.self_gravity(dev(pos), dev(mass), eps2, G, acc, pot)
+    torch.cuda.synchronize()
+    ref, pref = oracle.self_gravity(pos, mass, eps2, G, want_pot=True)
+    assert rel_err(acc.cpu().numpy(), ref) <= TOL
+    assert rel_err_scalar(pot.cpu().numpy(), pref) <= TOL
+
+
+def test_self_gravity_segments_and_shards(ctx):
+    """Ragged batch of clusters; target range sharded as two ranks would do it."""
+    import torch
+    from oc_nbody_b200.synthetic import make_plummer_cluster
+    sizes = [300, 1, 513, 1024, 0, 77]
+    seg = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    n = int(seg[-1])
+    pos = np.empty((3, n))
+    mass = np.empty(n)
+    for k, sz in enumerate(sizes):
+        if sz == 0:
+            continue
+        p, _, m = make_plummer_cluster(max(sz, 2), seed=100 + k)
+        ang = 2 * np.pi * k / len(sizes)
+        pos[:, seg[k]:seg[k + 1]] = p[:, :sz] * 1e-3 + 8.0 * np.array([[np.cos(ang)], [np.sin(ang)], [0.0]])
+        mass[seg[k]:seg[k + 1]] = m[:sz]
+    eps2 = (0.01e-3) ** 2
+    ref, pref = oracle.self_gravity(pos, mass, eps2, G, seg_offsets=seg, want_pot=True)
+    acc = torch.zeros((3, n), dtype=torch.float64, device="cuda")
+    pot = torch.zeros(n, dtype=torch.float64, device="cuda")
+    half = n // 2
+    for a, b in ((0, half), (half, n)):
+        ctx.self_gravity(dev(pos), dev(mass), eps2, G, acc, pot, seg_offsets=seg, tgt_begin=a, tgt_end=b)
+    torch.cuda.synchronize()
+    assert rel_err(acc.cpu().numpy(), ref) <= TOL
+    assert rel_err_scalar(pot.cpu().numpy()[pref != 0], pref[pref != 0]) <= TOL
+    # lone particle: exactly zero
+    assert np.all(acc.cpu().numpy()[:, seg[1]] == 0.0)
+
+
+def test_errors_are_reported_not_fatal(ctx):
+    import torch
+    from oc_nbody_b200 import OcgError
+    acc = torch.empty((3, 4), dtype=torch.float64, device="cuda")
+    with pytest.raises(OcgError, match="unknown softening kernel"):
+        ctx.field_direct(torch.zeros((2, 4), dtype=torch.float32, device="cuda"), None,
+                         torch.zeros((4, 4), dtype=torch.float32, device="cuda"), 9, G, acc)
+    with pytest.raises(OcgError, match="centre row"):
+        ctx.frame_subtract(acc, 17)
+    with pytest.raises(OcgError, match="eps2"):
+        ctx.self_gravity(torch.zeros((3, 4), dtype=torch.float64, device="cuda"),
+                         torch.ones(4, dtype=torch.float64, device="cuda"), -1.0, G, acc)

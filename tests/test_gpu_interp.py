@@ -1,0 +1,116 @@
+"""GPU parity: K2/K3/K5 are FP64 with separately rounded ops -> bit-exact against the oracle."""
+import numpy as np
+import pytest
+
+import oracle
+from util import dev
+
+pytestmark = pytest.mark.gpu
+
+
+def make_planes(rng, nodes, n_cluster, nsnap=2):
+    n_node = len(nodes[0]) * len(nodes[1]) * len(nodes[2]) + 1
+    acc = rng.normal(0, 1e-2, (nsnap, n_cluster, 3, n_node))
+    pot = rng.normal(-50, 1.0, (nsnap, n_cluster, n_node))
+    rec = np.empty((nsnap, n_cluster, n_node, 4), np.float32)
+    for s in range(nsnap):
+        for c in range(n_cluster):
+            rec[s, c] = oracle.pack_planes(acc[s, c], pot[s, c])
+    return acc, pot, rec
+
+
+def star_cloud(rng, nodes, origin, n):
+    """random interior points + exact nodes + faces + outside the lattice, per cluster"""
+    ncl = origin.shape[0]
+    scl = rng.integers(0, ncl, n).astype(np.int32)
+    half = np.array([a[-1] for a in nodes])
+    p = rng.uniform(-1.15, 1.15, (n, 3)) * half + origin[scl]
+    k = n // 8
+    for d in range(3):  # exactly on evolved nodes (node + origin, the value the kernels compare against)
+        idx = rng.integers(0, len(nodes[d]), k)
+        p[:k, d] = nodes[d][idx] + origin[scl[:k], d]
+    p[k:2 * k, 0] = nodes[0][0] + origin[scl[k:2 * k], 0]      # low face
+    p[2 * k:3 * k, 2] = nodes[2][-1] + origin[scl[2 * k:3 * k], 2]  # high face
+    p[3 * k:3 * k + 3] = origin[scl[3 * k:3 * k + 3]] + 100.0 * half   # far outside
+    return p, scl
+
+
+@pytest.mark.parametrize("shape,ncl", [((16, 16, 16), 1), ((32, 32, 32), 5), ((7, 12, 3), 3), ((2, 2, 2), 2)])
+def test_grid_interp_bit_exact(ctx, shape, ncl):
+    import torch
+    rng = np.random.default_rng(sum(shape) + ncl)
+    nodes = [np.linspace(-L, L, n) for L, n in zip((0.6, 0.45, 0.3), shape)]
+    origin = rng.normal(0, 3.0, (ncl, 3))
+    _, _, rec = make_planes(rng, nodes, ncl)
+    n = 20000
+    p, scl = star_cloud(rng, nodes, origin, n)
+    for wb in (0.0, 0.37, 1.0):
+        ref_acc, ref_pot, ref_cell = oracle.grid_interp(nodes, origin, rec[0], rec[1], wb, p[:, 0], p[:, 1], p[:, 2], scl,
+                                                        want_pot=True, want_cell=True)
+        acc = torch.empty((3, n), dtype=torch.float64, device="cuda")
+        pot = torch.empty(n, dtype=torch.float64, device="cuda")
+        cell = torch.empty((3, n), dtype=torch.int32, device="cuda")
+        ctx.grid_interp(shape, [dev(a) for a in nodes], dev(origin), dev(rec[0]), dev(rec[1]), wb,
+                        dev(p[:, 0].copy()), dev(p[:, 1].copy()), dev(p[:, 2].copy()), dev(scl), acc, pot, cell)
+        torch.cuda.synchronize()
+        assert np.array_equal(cell.cpu().numpy(), ref_cell)
+        assert np.array_equal(acc.cpu().numpy(), ref_acc)
+        assert np.array_equal(pot.cpu().numpy(), ref_pot)
+        # independent check of the cell rule: numpy searchsorted on the evolved node arrays
+        for d in range(3):
+            ev = nodes[d][None, :] + origin[:, d:d + 1]
+            want = np.array([np.searchsorted(ev[c], x, side="right") - 1 for c, x in zip(scl[:2000], p[:2000, d])])
+            want = np.clip(want, 0, shape[d] - 2)
+            assert np.array_equal(ref_cell[d, :2000], want)
+
+
+def test_grid_interp_affine_field_exact(ctx):
+    """Trilinear interpolation reproduces an affine field (to FP64 rounding), single snapshot, no cluster ids."""
+    import torch
+    rng = np.random.default_rng(5)
+    nodes = [np.linspace(-0.6, 0.6, 16)] * 3
+    X, Y, Z = np.meshgrid(*nodes, indexing="ij")
+    A = rng.normal(0, 1, (4, 3))
+    b = rng.normal(0, 1, 4)
+    vals = [(A[q, 0] * X + A[q, 1] * Y + A[q, 2] * Z + b[q]).reshape(-1) for q in range(4)]
+    rec = np.zeros((1, 16 ** 3 + 1, 4), np.float64)
+    for q in range(4):
+        rec[0, :-1, q] = vals[q]
+    rec32 = rec.astype(np.float32)
+    n = 5000
+    p = rng.uniform(-0.6, 0.6, (n, 3))
+    acc = torch.empty((3, n), dtype=torch.float64, device="cuda")
+    pot = torch.empty(n, dtype=torch.float64, device="cuda")
+    ctx.grid_interp((16, 16, 16), [dev(a) for a in nodes], dev(np.zeros((1, 3))), dev(rec32[0]), None, 0.0,
+                    dev(p[:, 0].copy()), dev(p[:, 1].copy()), dev(p[:, 2].copy()), None, acc, pot)
+    torch.cuda.synchronize()
+    got = np.concatenate([acc.cpu().numpy(), pot.cpu().numpy()[None]])
+    want = A @ p.T + b[:, None]
+    assert np.max(np.abs(got - want)) < 5e-7  # FP32 storage of the node values bounds the error
+
+
+def test_pack_blend_kick_drift_bit_exact(ctx):
+    import torch
+    rng = np.random.default_rng(6)
+    n = 4097
+    acc = rng.normal(0, 1e-2, (3, n))
+    pot = rng.normal(-10, 1, n)
+    rec = torch.empty((n, 4), dtype=torch.float32, device="cuda")
+    ctx.pack_planes(dev(acc), dev(pot), rec)
+    ref_rec = oracle.pack_planes(acc, pot)
+    assert np.array_equal(rec.cpu().numpy(), ref_rec)
+    rec_b = oracle.pack_planes(acc * 1.1 + 1e-4, pot * 0.9)
+    out = torch.empty((3, n), dtype=torch.float64, device="cuda")
+    outp = torch.empty(n, dtype=torch.float64, device="cuda")
+    ctx.grid_time_blend(rec, dev(rec_b), 0.3, out, outp)
+    ra, rp = oracle.time_blend(ref_rec, rec_b, 0.3, want_pot=True)
+    assert np.array_equal(out.cpu().numpy(), ra) and np.array_equal(outp.cpu().numpy(), rp)
+    vel = rng.normal(0, 1, (3, n))
+    pos = rng.normal(8, 1e-3, (3, n))
+    dv, dp = dev(vel), dev(pos)
+    ctx.kick(dv, dev(acc), 0.05)
+    ctx.drift(dp, dv, 0.1, 1.022712165045695e-3)
+    torch.cuda.synchronize()
+    rv = oracle.kick(vel, acc, 0.05)
+    rp = oracle.drift(pos, rv, 0.1, 1.022712165045695e-3)
+    assert np.array_equal(dv.cpu().numpy(), rv) and np.array_equal(dp.cpu().numpy(), rp)
