@@ -72,6 +72,7 @@ def load_library():
     L.ocg_probe_throughput.restype = dbl
     L.ocg_probe_throughput.argtypes = [vp, ctypes.c_int]
     L.ocg_debug_set_variant.argtypes = [ctypes.c_int, ctypes.c_int]
+    L.ocg_debug_set_precise_near.argtypes = [ctypes.c_int]
     _lib = L
     return L
 

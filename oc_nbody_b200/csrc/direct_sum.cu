@@ -118,6 +118,17 @@ __device__ __forceinline__ void decode_item(const DirectParams& p, int item, lon
 // TPT   : targets per consumer thread
 // POT   : also accumulate the potential (4th component)
 // GUARD : tolerate r2 + e2 == 0 (self pairs when eps2 == 0): such pairs contribute nothing
+//
+// Per pair of sources and target (12 FMA-pipe + 2 MUFU instructions):
+//   d   = xs + (-xt)                     3 FADD2
+//   r2  = dx*dx + dy*dy + dz*dz + e2     3 FFMA2
+//   r6  = (r2*r2)*r2                     2 FMUL2
+//   y3  = rsqrt(r6) = r^-3               2 MUFU.RSQ   (ONE approximate op per r^-3: ~3x less error
+//   sc  = m * y3                         1 FMUL2       than cubing an approximate r^-1)
+//   a  += d * sc                         3 FFMA2
+//   phi += sc * r2  (= m/r)              1 FFMA2      (POT only)
+// Coordinates are pre-scaled by a power of two so that r6 stays inside the FP32 range; GUARD keeps
+// the classic rsqrt(r2)^3 form (no range assumption when eps2 == 0).
 template <int TPT, bool POT, bool GUARD>
 __global__ void __launch_bounds__(OCG_CTA_THREADS, 2) direct_sum_kernel(const DirectParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -171,11 +182,13 @@ __global__ void __launch_bounds__(OCG_CTA_THREADS, 2) direct_sum_kernel(const Di
     // negated, duplicated target coordinates: dx = xs + (-xt)
     u64 ntx[TPT], nty[TPT], ntz[TPT];
     double dacc[TPT][NC];
+    const float scale = p.scale_ptr ? *p.scale_ptr : p.scale_val;
 #pragma unroll
     for (int t = 0; t < TPT; ++t) {
       int local = t * OCG_CONSUMER_THREADS + tid;
       long long gi = tgt_begin + (local < tgt_count ? local : tgt_count - 1);
       float4 T = __ldg(&p.tgt[gi]);
+      T.x *= scale, T.y *= scale, T.z *= scale;  // power of two: exact
       ntx[t] = f2_pack(-T.x, -T.x);
       nty[t] = f2_pack(-T.y, -T.y);
       ntz[t] = f2_pack(-T.z, -T.z);
@@ -216,24 +229,27 @@ __global__ void __launch_bounds__(OCG_CTA_THREADS, 2) direct_sum_kernel(const Di
             u64 r2 = f2_fma(dx, dx, es[q]);
             r2 = f2_fma(dy, dy, r2);
             r2 = f2_fma(dz, dz, r2);
-            float r2a, r2b;
-            f2_unpack(r2, r2a, r2b);
-            float ria, rib;
+            u64 sc;
             if (GUARD) {
-              ria = r2a > 0.f ? rsqrt_approx(r2a) : 0.f;
-              rib = r2b > 0.f ? rsqrt_approx(r2b) : 0.f;
+              float r2a, r2b;
+              f2_unpack(r2, r2a, r2b);
+              float ria = r2a > 0.f ? rsqrt_approx(r2a) : 0.f;
+              float rib = r2b > 0.f ? rsqrt_approx(r2b) : 0.f;
+              u64 ri = f2_pack(ria, rib);
+              u64 mri = f2_mul(ms[q], ri);
+              sc = f2_mul(mri, f2_mul(ri, ri));
+              if (POT) ap[t] = f2_add(ap[t], mri);
             } else {
-              ria = rsqrt_approx(r2a);
-              rib = rsqrt_approx(r2b);
+              u64 r6 = f2_mul(f2_mul(r2, r2), r2);
+              float r6a, r6b;
+              f2_unpack(r6, r6a, r6b);
+              u64 y3 = f2_pack(rsqrt_approx(r6a), rsqrt_approx(r6b));
+              sc = f2_mul(ms[q], y3);
+              if (POT) ap[t] = f2_fma(sc, r2, ap[t]);
             }
-            u64 ri = f2_pack(ria, rib);
-            u64 ri2 = f2_mul(ri, ri);
-            u64 mri = f2_mul(ms[q], ri);
-            u64 sc = f2_mul(mri, ri2);
             ax[t] = f2_fma(dx, sc, ax[t]);
             ay[t] = f2_fma(dy, sc, ay[t]);
             az[t] = f2_fma(dz, sc, az[t]);
-            if (POT) ap[t] = f2_add(ap[t], mri);
           }
         }
       }
@@ -316,12 +332,13 @@ __global__ void __launch_bounds__(OCG_CTA_THREADS, 2) direct_sum_scalar_kernel(c
     decode_item<TPT>(p, item, tgt_begin, tgt_count, tile_begin, tile_count, slot);
     float tx[TPT], ty[TPT], tz[TPT];
     double dacc[TPT][NC];
+    const float scale = p.scale_ptr ? *p.scale_ptr : p.scale_val;
 #pragma unroll
     for (int t = 0; t < TPT; ++t) {
       int local = t * OCG_CONSUMER_THREADS + tid;
       long long gi = tgt_begin + (local < tgt_count ? local : tgt_count - 1);
       float4 T = __ldg(&p.tgt[gi]);
-      tx[t] = T.x, ty[t] = T.y, tz[t] = T.z;
+      tx[t] = T.x * scale, ty[t] = T.y * scale, tz[t] = T.z * scale;
 #pragma unroll
       for (int c = 0; c < NC; ++c) dacc[t][c] = 0.0;
     }
@@ -350,14 +367,20 @@ __global__ void __launch_bounds__(OCG_CTA_THREADS, 2) direct_sum_scalar_kernel(c
             float r2 = fmaf(dx, dx, es[q]);
             r2 = fmaf(dy, dy, r2);
             r2 = fmaf(dz, dz, r2);
-            float ri = GUARD ? (r2 > 0.f ? rsqrt_approx(r2) : 0.f) : rsqrt_approx(r2);
-            float ri2 = ri * ri;
-            float mri = ms[q] * ri;
-            float sc = mri * ri2;
+            float sc;
+            if (GUARD) {
+              float ri = r2 > 0.f ? rsqrt_approx(r2) : 0.f;
+              float mri = ms[q] * ri;
+              sc = mri * (ri * ri);
+              if (POT) ap[t] += mri;
+            } else {
+              float y3 = rsqrt_approx((r2 * r2) * r2);
+              sc = ms[q] * y3;
+              if (POT) ap[t] = fmaf(sc, r2, ap[t]);
+            }
             ax[t] = fmaf(dx, sc, ax[t]);
             ay[t] = fmaf(dy, sc, ay[t]);
             az[t] = fmaf(dz, sc, az[t]);
-            if (POT) ap[t] += mri;
           }
         }
       }
@@ -385,14 +408,32 @@ __global__ void __launch_bounds__(OCG_CTA_THREADS, 2) direct_sum_scalar_kernel(c
 }
 
 // ---------------------------------------------------------------- source classification ----
-// misc scratch layout (ints unless noted)
-//   [0..5]  target bbox as ordered ints: minx,miny,minz,maxx,maxy,maxz
-//   [8]     n_fast   [9] n_near   [10] n_fast_tiles
+// Every source goes to exactly one of two sets:
+//   FAST : handled by the streaming FP32 kernel as Plummer(e2) or pure Newtonian (e2 = 0);
+//   NEAR : handled pair by pair in FP64 by near_sum_kernel.
+// A source is NEAR when (a) correctness demands it — a spline source whose support h can reach the
+// target box, or a source whose r^6 could leave the FP32 range for some target — or (b) accuracy
+// profits from it — it lies within the "precision radius" D of the target box, where single pair terms
+// are large compared with the net field and FP32 rounding of them would dominate the error budget.
+// D is the largest of 0.5, 0.25, ... x (box extent) for which the NEAR set stays below a small cap
+// (so the FP64 work is <~1% of the total); it is chosen on the device from a distance histogram.
+//
+// All distances here are in SCALED units: lengths x scale, scale = 2^k with the largest extent of the
+// target box mapped into (0.5, 1].  misc scratch layout (32 ints):
+//   [0..5]  target bbox as ordered ints: min xyz, max xyz (unscaled)
+//   [8] n_fast  [9] n_near  [10] n_fast_tiles  [11] scale (float bits)  [12] D^2 scaled (float bits)
+//   [16..31] histogram: hist[b] = #sources with scaled box distance < 0.5 * 2^-b
 #define MISC_BBOX 0
 #define MISC_NFAST 8
 #define MISC_NNEAR 9
 #define MISC_NFAST_TILES 10
-#define MISC_INTS 16
+#define MISC_SCALE 11
+#define MISC_D2 12
+#define MISC_HIST 16
+#define MISC_NBINS 12
+#define MISC_INTS 32
+
+#define R2_MIN_SCALED 1e-12f  /* r^6 >= 1e-36 stays a normal FP32 number */
 
 __device__ __forceinline__ int float_to_ordered(float f) {
   int i = __float_as_int(f);
@@ -404,7 +445,7 @@ __device__ __forceinline__ float ordered_to_float(int i) {
 
 __global__ void misc_init_kernel(int* misc) {
   int i = threadIdx.x;
-  if (i < 3) misc[MISC_BBOX + i] = 0x7fffffff;       // +max ordered
+  if (i < 3) misc[MISC_BBOX + i] = 0x7fffffff;            // +max ordered
   else if (i < 6) misc[MISC_BBOX + i] = (int)0x80000000;  // -max ordered
   else if (i < MISC_INTS) misc[i] = 0;
 }
@@ -433,26 +474,77 @@ __global__ void bbox_kernel(const float4* __restrict__ tgt, long long n, int* mi
   }
 }
 
-// Is source (x,y,z,soft) safe for the fast kernel for EVERY target inside the bbox?
-//   Plummer, e2 > 0       : always (r2 + e2 > 0)
-//   Plummer/spline, e2==0 : Newtonian; needs distance to the box > 0 (no singular pair)
-//   spline, h > 0         : needs distance to the box >= h (force is exactly Newtonian there)
-__device__ __forceinline__ bool source_is_fast(float x, float y, float z, float soft, int kernel,
-                                               const int* misc) {
-  const float e2 = soft * soft;
-  if (kernel == OCG_KERNEL_PLUMMER && e2 > 0.f) return true;
+// scale = 2^k such that the largest box extent lands in (0.5, 1]; a degenerate box (one target, or
+// all targets coincident) falls back to the sources' typical distance via scale_hint (host, from eps).
+__global__ void scale_kernel(int* misc, float fallback_len) {
+  float ext = 0.f;
+  for (int c = 0; c < 3; ++c)
+    ext = fmaxf(ext, ordered_to_float(misc[MISC_BBOX + 3 + c]) - ordered_to_float(misc[MISC_BBOX + c]));
+  if (!(ext > 0.f) || !isfinite(ext)) ext = fallback_len;
+  int e;
+  frexpf(ext, &e);  // ext = f * 2^e, f in [0.5, 1)
+  float sc = ldexpf(1.0f, -e);
+  if (!(sc > 0.f) || !isfinite(sc)) sc = 1.0f;
+  misc[MISC_SCALE] = __float_as_int(sc);
+}
+
+// scaled squared distance from a source to the target box
+__device__ __forceinline__ float box_dist2_scaled(float x, float y, float z, const int* misc, float sc) {
   float bx0 = ordered_to_float(misc[MISC_BBOX + 0]), by0 = ordered_to_float(misc[MISC_BBOX + 1]);
   float bz0 = ordered_to_float(misc[MISC_BBOX + 2]), bx1 = ordered_to_float(misc[MISC_BBOX + 3]);
   float by1 = ordered_to_float(misc[MISC_BBOX + 4]), bz1 = ordered_to_float(misc[MISC_BBOX + 5]);
-  float dx = fmaxf(fmaxf(bx0 - x, x - bx1), 0.f);
-  float dy = fmaxf(fmaxf(by0 - y, y - by1), 0.f);
-  float dz = fmaxf(fmaxf(bz0 - z, z - bz1), 0.f);
-  float d2 = dx * dx + dy * dy + dz * dz;
-  // 1e-20: keeps m * r^-3 finite in FP32; (1 + 1e-5): FP32 rounding margin on the support test
-  return d2 > 1e-20f && d2 > e2 * 1.00001f;
+  float dx = fmaxf(fmaxf(bx0 - x, x - bx1), 0.f) * sc;
+  float dy = fmaxf(fmaxf(by0 - y, y - by1), 0.f) * sc;
+  float dz = fmaxf(fmaxf(bz0 - z, z - bz1), 0.f) * sc;
+  return dx * dx + dy * dy + dz * dz;
+}
+
+// (a)-type criterion only: must this source be handled pair by pair?
+__device__ __forceinline__ bool source_must_be_near(float d2, float soft_scaled, int kernel) {
+  const float e2 = soft_scaled * soft_scaled;
+  if (kernel == OCG_KERNEL_SPLINE) return !(d2 > R2_MIN_SCALED && d2 > e2 * 1.00001f);
+  return !(e2 > R2_MIN_SCALED || d2 > R2_MIN_SCALED);
 }
 
 #define CLS_BLOCK 1024
+
+// distance histogram of the sources that are not already NEAR by criterion (a)
+__global__ void __launch_bounds__(CLS_BLOCK) classify_hist_kernel(
+    const float4* __restrict__ src, const float* __restrict__ soft, long long n, int kernel, int* misc) {
+  __shared__ int h[MISC_NBINS];
+  if (threadIdx.x < MISC_NBINS) h[threadIdx.x] = 0;
+  __syncthreads();
+  const float sc = __int_as_float(misc[MISC_SCALE]);
+  long long i = blockIdx.x * (long long)CLS_BLOCK + threadIdx.x;
+  if (i < n) {
+    float4 S = src[i];
+    float d2 = box_dist2_scaled(S.x, S.y, S.z, misc, sc);
+    if (!source_must_be_near(d2, (soft ? soft[i] : 0.f) * sc, kernel)) {
+      // largest b with d < 0.5 * 2^-b  <=>  d2 < 0.25 * 4^-b
+      float lim = 0.25f;
+      for (int b = 0; b < MISC_NBINS && d2 < lim; ++b, lim *= 0.25f) atomicAdd(&h[b], 1);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < MISC_NBINS && h[threadIdx.x]) atomicAdd(&misc[MISC_HIST + threadIdx.x], h[threadIdx.x]);
+}
+
+__global__ void choose_radius_kernel(int* misc, int cap) {
+  float d2 = 0.f, lim = 0.25f;
+  for (int b = 0; b < MISC_NBINS; ++b, lim *= 0.25f)
+    if (misc[MISC_HIST + b] <= cap) {
+      d2 = lim;
+      break;
+    }
+  misc[MISC_D2] = __float_as_int(d2);
+}
+
+__device__ __forceinline__ bool source_is_fast(float x, float y, float z, float soft, int kernel, const int* misc) {
+  const float sc = __int_as_float(misc[MISC_SCALE]);
+  const float d2 = box_dist2_scaled(x, y, z, misc, sc);
+  if (source_must_be_near(d2, soft * sc, kernel)) return false;
+  return !(d2 < __int_as_float(misc[MISC_D2]));
+}
 
 __global__ void __launch_bounds__(CLS_BLOCK) classify_count_kernel(
     const float4* __restrict__ src, const float* __restrict__ soft, long long n, int kernel,
@@ -475,8 +567,7 @@ __global__ void __launch_bounds__(CLS_BLOCK) classify_count_kernel(
 }
 
 // Single-block exclusive scan of per-block fast counts (in place); totals to misc.
-__global__ void __launch_bounds__(1024) classify_scan_kernel(int* counts, int nblocks, long long n,
-                                                             int* misc) {
+__global__ void __launch_bounds__(1024) classify_scan_kernel(int* counts, int nblocks, long long n, int* misc) {
   __shared__ long long carry;
   __shared__ int wtot[32];
   if (threadIdx.x == 0) carry = 0;
@@ -502,7 +593,7 @@ __global__ void __launch_bounds__(1024) classify_scan_kernel(int* counts, int nb
     __syncthreads();
     long long c = carry;
     int excl = incl - v + wtot[threadIdx.x >> 5];
-    // counts[] holds ints: fast-source offsets fit because n_src < 2^31 per call (checked on host)
+    // ints suffice: n_src < 2^31 per call (checked on the host)
     if (i < nblocks) counts[i] = (int)(c + excl);
     __syncthreads();
     if (threadIdx.x == 1023) carry = c + excl + v;
@@ -516,7 +607,7 @@ __global__ void __launch_bounds__(1024) classify_scan_kernel(int* counts, int nb
   }
 }
 
-// Stable scatter: fast sources -> tiles, near sources -> near list (float4 xyzm + float soft).
+// Stable scatter: fast sources -> scaled tiles, near sources -> near list (float4 xyzm + float soft).
 __global__ void __launch_bounds__(CLS_BLOCK) classify_scatter_kernel(
     const float4* __restrict__ src, const float* __restrict__ soft, long long n, int kernel,
     const int* __restrict__ misc, const int* __restrict__ fast_off, float* __restrict__ tiles,
@@ -549,15 +640,18 @@ __global__ void __launch_bounds__(CLS_BLOCK) classify_scatter_kernel(
   long long block_start = blockIdx.x * (long long)CLS_BLOCK;
   long long foff = fast_off[blockIdx.x];
   if (fast) {
+    const float sc = __int_as_float(misc[MISC_SCALE]);
     long long pos = foff + rank_fast;
     long long tile = pos / OCG_TS;
     int j = (int)(pos - tile * OCG_TS);
     float* T = tiles + tile * (long long)OCG_TILE_FLOATS;
-    // spline sources that reach the fast set are Newtonian for every target: e2 = 0
-    float e2 = kernel == OCG_KERNEL_PLUMMER ? h * h : 0.f;
-    T[j] = S.x;
-    T[OCG_TS + j] = S.y;
-    T[2 * OCG_TS + j] = S.z;
+    // spline sources that reach the fast set are Newtonian for every target: e2 = 0;
+    // Plummer sources whose scaled e2 is negligible are far enough (d2 > R2_MIN) to drop it too
+    float hs = h * sc;
+    float e2 = kernel == OCG_KERNEL_PLUMMER ? hs * hs : 0.f;
+    T[j] = S.x * sc;
+    T[OCG_TS + j] = S.y * sc;
+    T[2 * OCG_TS + j] = S.z * sc;
     T[3 * OCG_TS + j] = S.w;
     T[4 * OCG_TS + j] = e2;
   } else {
@@ -583,64 +677,59 @@ __global__ void pad_tiles_kernel(float* tiles, const int* misc) {
 }
 
 // ------------------------------------------------------------------- finish: sum partials ----
-// out[c][t] (+)= G * sum_{slot < n_slots} partial[slot][c][t], slots summed in index order.
+// out[c][t] (+)= G * s^2 * sum_{slot} partial[slot][c][t]  (potential: G * s), slots in index order.
+// (partials are in scaled units: acc' = acc / s^2, phi' = phi / s.)
 __global__ void finish_kernel(const double* __restrict__ partial, long long stride, int n_slots,
-                              int nc_partial, double G, long long n_tgt, double* __restrict__ acc,
-                              double* __restrict__ pot, int accumulate) {
+                              int nc_partial, double G, const int* __restrict__ misc, long long n_tgt,
+                              double* __restrict__ acc, double* __restrict__ pot, int accumulate) {
   long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (t >= n_tgt) return;
+  const double sc = (double)__int_as_float(misc[MISC_SCALE]);
   for (int c = 0; c < nc_partial; ++c) {
     double s = 0.0;
     for (int k = 0; k < n_slots; ++k) s += partial[((long long)k * nc_partial + c) * stride + t];
-    s *= G;
+    s *= c < 3 ? G * sc * sc : G * sc;
     double* dst = c < 3 ? acc + (long long)c * n_tgt + t : pot + t;
     *dst = accumulate ? *dst + s : s;
   }
 }
 
-// ---------------------------------------------------------------------- near (slow) kernel ----
-// Sources that may be inside their softening support, or singular. FP32 pair arithmetic with
-// exact sqrt/div, branches allowed, FP64 accumulation; adds G * sum straight into acc/pot.
+// ---------------------------------------------------------------------- near (FP64) kernel ----
+// Pair-by-pair FP64 evaluation of the NEAR set; adds G * sum straight into acc/pot.
 // Spline forms: pykdgrav ForceKernel / PotentialKernel (cubic spline of support h; Springel 2001).
-__device__ __forceinline__ void near_pair(float dx, float dy, float dz, float m, float h, int kernel,
-                                          float& fac, float& pfac) {
-  float r2 = dx * dx + dy * dy + dz * dz;
-  fac = 0.f, pfac = 0.f;
+__device__ __forceinline__ void near_pair(double dx, double dy, double dz, double m, double h, int kernel,
+                                          double& fac, double& pfac) {
+  const double r2 = dx * dx + dy * dy + dz * dz;
+  fac = 0.0, pfac = 0.0;
   if (kernel == OCG_KERNEL_PLUMMER) {
-    float q2 = r2 + h * h;
-    if (q2 > 0.f) {
-      float ri = 1.0f / sqrtf(q2);
+    const double q2 = r2 + h * h;
+    if (q2 > 0.0) {
+      const double ri = rsqrt(q2);
       pfac = -m * ri;
       fac = m * ri * ri * ri;
     }
     return;
   }
-  if (!(r2 > 0.f)) return;
-  float r = sqrtf(r2);
+  if (!(r2 > 0.0)) return;
+  const double r = sqrt(r2);
   if (r >= h) {
-    float ri = 1.0f / r;
+    const double ri = 1.0 / r;
     pfac = -m * ri;
     fac = m * ri * ri * ri;
     return;
   }
-  float hinv = 1.0f / h;
-  float q = r * hinv;
-  float h3 = hinv * hinv * hinv;
-  if (q <= 0.5f) {
-    fac = m * h3 * (10.666666666666666f + q * q * (32.0f * q - 38.4f));
-    pfac = m * hinv * (-2.8f + q * q * (5.333333333333333f + q * q * (6.4f * q - 9.6f)));
+  const double hinv = 1.0 / h, q = r * hinv, h3 = hinv * hinv * hinv;
+  if (q <= 0.5) {
+    fac = m * h3 * (32.0 / 3.0 + q * q * (32.0 * q - 38.4));
+    pfac = m * hinv * (-2.8 + q * q * (16.0 / 3.0 + q * q * (6.4 * q - 9.6)));
   } else {
-    float q3 = q * q * q;
-    fac = m * h3 *
-          (21.333333333333332f - 48.0f * q + 38.4f * q * q - 10.666666666666666f * q3 -
-           0.06666666666666667f / q3);
-    pfac = m * hinv *
-           (-3.2f + 0.06666666666666667f / q +
-            q * q * (10.666666666666666f + q * (-16.0f + q * (9.6f - 2.1333333333333333f * q))));
+    const double q3 = q * q * q;
+    fac = m * h3 * (64.0 / 3.0 - 48.0 * q + 38.4 * q * q - (32.0 / 3.0) * q3 - (1.0 / 15.0) / q3);
+    pfac = m * hinv * (-3.2 + (1.0 / 15.0) / q + q * q * (32.0 / 3.0 + q * (-16.0 + q * (9.6 - (32.0 / 15.0) * q))));
   }
 }
 
-#define NEAR_BLOCK 256
+#define NEAR_BLOCK 128
 __global__ void __launch_bounds__(NEAR_BLOCK) near_sum_kernel(
     const float4* __restrict__ near_xyzm, const float* __restrict__ near_soft,
     const int* __restrict__ misc, const float4* __restrict__ tgt, long long n_tgt, int kernel,
@@ -650,7 +739,8 @@ __global__ void __launch_bounds__(NEAR_BLOCK) near_sum_kernel(
   __shared__ float4 sS[NEAR_BLOCK];
   __shared__ float sH[NEAR_BLOCK];
   long long t = blockIdx.x * (long long)NEAR_BLOCK + threadIdx.x;
-  float4 T = tgt[t < n_tgt ? t : n_tgt - 1];
+  const float4 T = tgt[t < n_tgt ? t : n_tgt - 1];
+  const double tx = T.x, ty = T.y, tz = T.z;
   double a0 = 0, a1 = 0, a2 = 0, ph = 0;
   for (int base = 0; base < n_near; base += NEAR_BLOCK) {
     int i = base + threadIdx.x;
@@ -660,16 +750,15 @@ __global__ void __launch_bounds__(NEAR_BLOCK) near_sum_kernel(
       sH[threadIdx.x] = near_soft[i];
     }
     __syncthreads();
-    int cnt = min(NEAR_BLOCK, n_near - base);
-    float f0 = 0, f1 = 0, f2 = 0, fp = 0;
+    const int cnt = min(NEAR_BLOCK, n_near - base);
     for (int j = 0; j < cnt; ++j) {
-      float4 S = sS[j];
-      float dx = S.x - T.x, dy = S.y - T.y, dz = S.z - T.z, fac, pfac;
-      near_pair(dx, dy, dz, S.w, sH[j], kernel, fac, pfac);
-      f0 = fmaf(dx, fac, f0), f1 = fmaf(dy, fac, f1), f2 = fmaf(dz, fac, f2);
-      fp += pfac;
+      const float4 S = sS[j];
+      const double dx = (double)S.x - tx, dy = (double)S.y - ty, dz = (double)S.z - tz;
+      double fac, pfac;
+      near_pair(dx, dy, dz, (double)S.w, (double)sH[j], kernel, fac, pfac);
+      a0 += dx * fac, a1 += dy * fac, a2 += dz * fac;
+      ph += pfac;
     }
-    a0 += f0, a1 += f1, a2 += f2, ph += fp;
   }
   if (t < n_tgt) {
     acc[t] += G * a0;
@@ -696,14 +785,19 @@ static direct_fn pick_kernel(bool pot, bool guard, bool scalar) {
 
 static int g_force_tpt = 0;     // 0 = heuristic
 static int g_force_scalar = 0;  // 1 = scalar FP32 variant
+static int g_precise_near = 1;  // 0 = no precision radius (criterion (a) only)
 extern "C" int ocg_debug_set_variant(int tpt, int scalar) {
   g_force_tpt = tpt;
   g_force_scalar = scalar;
   return 0;
 }
+extern "C" int ocg_debug_set_precise_near(int on) {
+  g_precise_near = on;
+  return 0;
+}
 
 int ocg_pick_tpt(ocg_ctx* ctx, int64_t n_tgt) {
-  if (g_force_tpt == 1 || g_force_tpt == 2 || g_force_tpt == 4) return g_force_tpt;
+  if (g_force_tpt == 1 || g_force_tpt == 2) return g_force_tpt;
   // enough targets to give every resident CTA a full tile at TPT=2?
   long long full = (long long)ctx->sm_count * 2 * OCG_CONSUMER_THREADS * 2;
   return n_tgt >= full ? 2 : 1;
@@ -711,9 +805,7 @@ int ocg_pick_tpt(ocg_ctx* ctx, int64_t n_tgt) {
 
 // Launch the fast kernel over a prepared parameter block.
 int ocg_launch_direct(ocg_ctx* ctx, DirectParams& p, int tpt, bool pot, bool guard, cudaStream_t st) {
-  direct_fn fn = tpt == 4 ? pick_kernel<4>(pot, guard, g_force_scalar)
-                          : (tpt == 2 ? pick_kernel<2>(pot, guard, g_force_scalar)
-                                      : pick_kernel<1>(pot, guard, g_force_scalar));
+  direct_fn fn = tpt == 2 ? pick_kernel<2>(pot, guard, g_force_scalar) : pick_kernel<1>(pot, guard, g_force_scalar);
   size_t smem = direct_smem_bytes();
   OCG_CUDA(ctx, cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int grid = ctx->sm_count * 2;
@@ -786,6 +878,17 @@ int ocg_direct_sum_impl(ocg_ctx* ctx, const float* src_xyzm, const float* src_so
     bbox_kernel<<<(int)nb, 256, 0, st>>>(tgt4, n_tgt, misc);
     OCG_CHECK_LAUNCH(ctx, "bbox_kernel");
   }
+  scale_kernel<<<1, 1, 0, st>>>(misc, 1.0f);
+  OCG_CHECK_LAUNCH(ctx, "scale_kernel");
+  if (g_precise_near) {
+    classify_hist_kernel<<<(int)n_cls_blocks, CLS_BLOCK, 0, st>>>(src4, src_soft, n_src, kernel, misc);
+    OCG_CHECK_LAUNCH(ctx, "classify_hist_kernel");
+    // cap the FP64 set at ~0.2% of the sources (>= 4096): its pair cost is ~5x the FP32 one
+    long long cap = n_src / 512;
+    if (cap < 4096) cap = 4096;
+    choose_radius_kernel<<<1, 1, 0, st>>>(misc, (int)cap);
+    OCG_CHECK_LAUNCH(ctx, "choose_radius_kernel");
+  }
   classify_count_kernel<<<(int)n_cls_blocks, CLS_BLOCK, 0, st>>>(src4, src_soft, n_src, kernel, misc, counts);
   OCG_CHECK_LAUNCH(ctx, "classify_count_kernel");
   classify_scan_kernel<<<1, 1024, 0, st>>>(counts, (int)n_cls_blocks, n_src, misc);
@@ -807,11 +910,13 @@ int ocg_direct_sum_impl(ocg_ctx* ctx, const float* src_xyzm, const float* src_so
   p.n_ttiles = (int)n_ttiles;
   p.tiles_per_chunk = (int)tiles_per_chunk;
   p.n_fast_tiles = misc + MISC_NFAST_TILES;
+  p.scale_ptr = reinterpret_cast<const float*>(misc + MISC_SCALE);
+  p.scale_val = 1.0f;
   if ((rc = ocg_launch_direct(ctx, p, tpt, want_pot, /*guard=*/false, st))) return rc;
 
   {
     long long nb = (n_tgt + 255) / 256;
-    finish_kernel<<<(int)nb, 256, 0, st>>>(partial, n_tgt, (int)n_chunks, NC, G, n_tgt, acc, pot, accumulate);
+    finish_kernel<<<(int)nb, 256, 0, st>>>(partial, n_tgt, (int)n_chunks, NC, G, misc, n_tgt, acc, pot, accumulate);
     OCG_CHECK_LAUNCH(ctx, "finish_kernel");
     long long nbn = (n_tgt + NEAR_BLOCK - 1) / NEAR_BLOCK;
     near_sum_kernel<<<(int)nbn, NEAR_BLOCK, 0, st>>>(near_xyzm, near_soft, misc, tgt4, n_tgt, kernel, G, acc, pot);

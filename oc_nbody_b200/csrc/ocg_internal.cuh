@@ -101,6 +101,8 @@ struct DirectParams {
   int n_ttiles;
   int tiles_per_chunk;
   const int* n_fast_tiles;   // device: number of fast tiles actually present
+  const float* scale_ptr;    // device: power-of-two length scale applied to targets (K1), or NULL
+  float scale_val;           // host-chosen scale when scale_ptr is NULL (K4)
 };
 
 // ---- entry points implemented in other translation units ------------------------------------

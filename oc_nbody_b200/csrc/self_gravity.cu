@@ -8,6 +8,7 @@
 // galaxy frame but ~pc from each other).
 #include "ocg_internal.cuh"
 
+#include <math.h>
 #include <stdlib.h>
 
 // Re-lay FP64 particles into (a) padded per-segment source tiles and (b) float4 targets.
@@ -15,7 +16,7 @@
 __global__ void pack_cluster_kernel(const double* __restrict__ pos, const double* __restrict__ mass,
                                     long long n, const long long* __restrict__ seg_off,
                                     const long long* __restrict__ seg_tile, int n_seg, float e2,
-                                    float* __restrict__ tiles, float4* __restrict__ tgt) {
+                                    float scale, float* __restrict__ tiles, float4* __restrict__ tgt) {
   const long long total_tiles = seg_tile[n_seg];
   const long long slot = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (slot >= total_tiles * OCG_TS) return;
@@ -35,29 +36,33 @@ __global__ void pack_cluster_kernel(const double* __restrict__ pos, const double
     const double cx = pos[first], cy = pos[n + first], cz = pos[2 * n + first];
     const float x = (float)(pos[idx] - cx), y = (float)(pos[n + idx] - cy), z = (float)(pos[2 * n + idx] - cz);
     const float m = (float)mass[idx];
-    T[j] = x, T[OCG_TS + j] = y, T[2 * OCG_TS + j] = z, T[3 * OCG_TS + j] = m, T[4 * OCG_TS + j] = e2;
+    // tiles hold scaled coordinates (scale = 2^k, exact); the kernel scales the targets itself
+    T[j] = x * scale, T[OCG_TS + j] = y * scale, T[2 * OCG_TS + j] = z * scale, T[3 * OCG_TS + j] = m;
+    T[4 * OCG_TS + j] = e2 * scale * scale;
     tgt[idx] = make_float4(x, y, z, m);
   } else {
     T[j] = 0.f, T[OCG_TS + j] = 0.f, T[2 * OCG_TS + j] = 0.f, T[3 * OCG_TS + j] = 0.f, T[4 * OCG_TS + j] = 1.f;
   }
 }
 
-// out[c][t] = G * sum_slots partial ; potential gets the self term (-m/eps, included by the
-// kernel because targets == sources) removed with the very same FP32 expression the kernel used.
+// out[c][t] = G * s^2 * sum_slots partial (potential: G * s; partials are in scaled units).  The
+// potential gets the self term (-m/eps, included by the kernel because targets == sources) removed
+// with the same FP32 expression the kernel used for it.
 __global__ void finish_self_kernel(const double* __restrict__ partial, long long stride, int n_slots, int nc,
-                                   double G, long long t0, long long t1, const float4* __restrict__ tgt, float e2,
-                                   double* __restrict__ acc, double* __restrict__ pot) {
+                                   double G, long long t0, long long t1, const float4* __restrict__ tgt, float e2s,
+                                   float scale, double* __restrict__ acc, double* __restrict__ pot) {
   long long t = t0 + blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (t >= t1) return;
+  const double sc = (double)scale;
   for (int c = 0; c < nc; ++c) {
     double s = 0.0;
     for (int k = 0; k < n_slots; ++k) s += partial[((long long)k * nc + c) * stride + t];
-    if (c == 3 && e2 > 0.f) {
-      float ri;
-      asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(ri) : "f"(e2));
-      s += (double)(tgt[t].w * ri);
+    if (c == 3 && e2s > 0.f) {
+      float y3;
+      asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y3) : "f"((e2s * e2s) * e2s));
+      s += (double)((tgt[t].w * y3) * e2s);
     }
-    s *= G;
+    s *= c < 3 ? G * sc * sc : G * sc;
     if (c < 3) acc[(long long)c * stride + t] = s;
     else pot[t] = s;
   }
@@ -102,6 +107,16 @@ extern "C" int ocg_self_gravity(ocg_ctx* ctx, const double* pos_dev, const doubl
   const int NC = want_pot ? 4 : 3;
   const float e2f = (float)eps2;
   const bool guard = !(e2f > 0.f);
+  // power-of-two length scale that puts eps at ~2^-8, so that r^6 >= eps^6 ~ 3.5e-15 stays far from the
+  // FP32 underflow threshold and separations up to ~1e8 eps stay below overflow (the guarded eps2 == 0
+  // form uses rsqrt(r2)^3 and needs no scale)
+  float scale = 1.0f;
+  if (!guard) {
+    int e;
+    frexpf(sqrtf(e2f), &e);
+    scale = ldexpf(1.0f, -8 - e);
+    if (!(scale > 0.f) || !isfinite(scale) || !(e2f * scale * scale > 0.f)) scale = 1.0f;
+  }
   const int64_t n_shard = tgt_end - tgt_begin;
   const int tpt = ocg_pick_tpt(ctx, n_shard);
   const int CT = OCG_CONSUMER_THREADS * tpt;
@@ -207,7 +222,7 @@ extern "C" int ocg_self_gravity(ocg_ctx* ctx, const double* pos_dev, const doubl
   {
     long long nslots = total_tiles * OCG_TS;
     pack_cluster_kernel<<<(int)((nslots + 255) / 256), 256, 0, st>>>(pos_dev, mass_dev, n, d_seg_off, d_seg_tile,
-                                                                    n_seg, guard ? 0.f : e2f, tiles, tgt);
+                                                                    n_seg, guard ? 0.f : e2f, scale, tiles, tgt);
     OCG_CHECK_LAUNCH(ctx, "pack_cluster_kernel");
   }
   DirectParams p;
@@ -221,9 +236,11 @@ extern "C" int ocg_self_gravity(ocg_ctx* ctx, const double* pos_dev, const doubl
   p.n_ttiles = 0;
   p.tiles_per_chunk = 0;
   p.n_fast_tiles = nullptr;
+  p.scale_ptr = nullptr;
+  p.scale_val = scale;
   if ((rc = ocg_launch_direct(ctx, p, tpt, want_pot, guard, st))) return rc;
   finish_self_kernel<<<(int)((n_shard + 255) / 256), 256, 0, st>>>(partial, n, (int)n_chunks, NC, G, tgt_begin,
-                                                                  tgt_end, tgt, guard ? 0.f : e2f, acc_dev, pot_dev);
+                                                                  tgt_end, tgt, guard ? 0.f : e2f * scale * scale, scale, acc_dev, pot_dev);
   OCG_CHECK_LAUNCH(ctx, "finish_self_kernel");
   return OCG_OK;
 }

@@ -37,7 +37,7 @@ def main():
     res = []
     for kernel in (0, 1):
         for scalar in (0, 1):
-            for tpt in (1, 2, 4):
+            for tpt in (1, 2):
                 for want_pot in (False, True):
                     ctx.lib.ocg_debug_set_variant(tpt, scalar)
                     best = 1e30
