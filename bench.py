@@ -113,22 +113,22 @@ class ClockSampler(object):
 
 # ------------------------------------------------------------------------------ CPU baseline ----
 def cpu_sample_rate(tgt_pos, src_pos, src_mass, src_eps, seconds):
-    """Time the oracle's vectorised FP64 direct sum (all host threads) on a bounded sample of the workload.
+    """Time the oracle's vectorised FP64 direct sum (all host threads) on a bounded sample of the workload:
+    all the sources handed in x a strided subset of the grid targets sized for ~`seconds` of CPU work.
     Returns (interactions/s, description, threads)."""
     import oracle
-    n_t = min(4097, tgt_pos.shape[0])
-    tp = np.ascontiguousarray(tgt_pos[:: max(1, tgt_pos.shape[0] // n_t)][:n_t])
     e2 = src_eps * src_eps
-    n_cal = min(20000, src_pos.shape[0])
+    n_s = src_pos.shape[0]
+    cal_t = np.ascontiguousarray(tgt_pos[:: max(1, tgt_pos.shape[0] // 512)][:512])
     t0 = time.perf_counter()
-    oracle.field_direct_fast(src_pos[:n_cal], src_mass[:n_cal], e2[:n_cal], tp, G_KPC)
-    cal = max(time.perf_counter() - t0, 1e-4)
-    rate0 = n_cal * tp.shape[0] / cal
-    n_s = int(min(src_pos.shape[0], max(n_cal, rate0 * seconds / tp.shape[0])))
+    oracle.field_direct_fast(src_pos, src_mass, e2, cal_t, G_KPC)
+    rate0 = n_s * cal_t.shape[0] / max(time.perf_counter() - t0, 1e-4)
+    n_t = int(min(tgt_pos.shape[0], max(512, rate0 * seconds / n_s)))
+    tp = np.ascontiguousarray(tgt_pos[:: max(1, tgt_pos.shape[0] // n_t)][:n_t])
     t0 = time.perf_counter()
-    oracle.field_direct_fast(src_pos[:n_s], src_mass[:n_s], e2[:n_s], tp, G_KPC)
+    oracle.field_direct_fast(src_pos, src_mass, e2, tp, G_KPC)
     dt = time.perf_counter() - t0
-    desc = "%d grid targets x %d sources of the workload, FP64 OpenMP direct sum (oracle/ocg_oracle.c), %.1f s" % (
+    desc = "%d of the grid targets x %d of the snapshot particles, FP64 OpenMP direct sum (oracle/ocg_oracle.c), %.1f s" % (
         tp.shape[0], n_s, dt)
     return n_s * tp.shape[0] / dt, desc, oracle.num_threads()
 
@@ -185,7 +185,7 @@ def main():
     ap.add_argument("--n-src", type=float, default=None, help="override particles per GPU (debug)")
     ap.add_argument("--grid", type=int, default=None, help="override grid nodes per axis (debug)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--variant", default="auto", help="auto | tptN | scalar-tptN (debug)")
+    ap.add_argument("--variant", default="auto", help="auto | kernel tuning-variant id (debug)")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -212,8 +212,7 @@ def main():
     from oc_nbody_b200 import Context
     ctx = Context(local_rank)
     if args.variant != "auto":
-        sc = 1 if args.variant.startswith("scalar") else 0
-        ctx.lib.ocg_debug_set_variant(int(args.variant[-1]), sc)
+        ctx.lib.ocg_debug_set_variant(int(args.variant))
     dev = torch.device("cuda", local_rank)
 
     g = make_targets(args.grid)

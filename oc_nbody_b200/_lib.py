@@ -71,7 +71,9 @@ def load_library():
     L.ocg_axpy.argtypes = [vp, vp, vp, dbl, i64, vp]
     L.ocg_probe_throughput.restype = dbl
     L.ocg_probe_throughput.argtypes = [vp, ctypes.c_int]
-    L.ocg_debug_set_variant.argtypes = [ctypes.c_int, ctypes.c_int]
+    L.ocg_debug_set_variant.argtypes = [ctypes.c_int]
+    L.ocg_debug_variant_name.restype = ctypes.c_char_p
+    L.ocg_debug_variant_name.argtypes = [ctypes.c_int]
     L.ocg_debug_set_precise_near.argtypes = [ctypes.c_int]
     _lib = L
     return L

@@ -1,9 +1,8 @@
-"""In-tree build of liboc_nbody_b200.so (CUDA, sm_100a) and of the CPU oracle.
+"""In-tree build of liboc_nbody_b200.so (CUDA, sm_100a).
 
-The product library is compiled with nvcc straight from ``oc_nbody_b200/csrc`` into
-``oc_nbody_b200/lib`` so that the built ``.so`` travels with the repository snapshot to the GPU box.
-nvcc cross-compiles without a GPU.  The oracle (``oracle/ocg_oracle.c``) is test infrastructure and is
-built by the same entry point only so that the checker exists where the tests run.
+The library is compiled with nvcc straight from ``oc_nbody_b200/csrc`` into ``oc_nbody_b200/lib`` so that the
+built ``.so`` travels with the repository snapshot to the GPU box.  nvcc cross-compiles without a GPU.
+(The CPU oracle is test infrastructure and builds itself: ``oracle.build()``.)
 """
 import os
 import shutil
@@ -54,23 +53,5 @@ def build_library(force=False, verbose=False):
     return LIB
 
 
-def build_oracle(force=False):
-    """Compile the C restatement used by the tests (never by the product path)."""
-    odir = os.path.join(ROOT, "oracle")
-    src = os.path.join(odir, "ocg_oracle.c")
-    out = os.path.join(odir, "_build", "libocg_oracle.so")
-    os.makedirs(os.path.dirname(out), exist_ok=True)
-    if not force and not _stale(out, [src]):
-        return out
-    cmd = ["gcc", "-O2", "-fopenmp", "-fPIC", "-shared", "-ffp-contract=off", "-std=c11", "-o", out, src, "-lm"]
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if res.returncode != 0:
-        sys.stderr.write(res.stdout + res.stderr)
-        raise RuntimeError("gcc failed building the oracle")
-    return out
-
-
 if __name__ == "__main__":
     print(build_library(force="--force" in sys.argv, verbose="-v" in sys.argv))
-    if os.path.exists(os.path.join(ROOT, "oracle", "ocg_oracle.c")):
-        print(build_oracle(force="--force" in sys.argv))

@@ -346,6 +346,35 @@ __global__ void __launch_bounds__(256) probe_ffma2_kernel(float* out, int iters)
   for (int k = 0; k < 8; ++k) s ^= a[k];
   if (s == 0x123456789ull) out[0] = (float)s;
 }
+// generic packed-op probe: OP 0 = add.f32x2 (both operands packed), 1 = mul.f32x2, 2 = add.f32x2 with a
+// duplicated (broadcast) operand, 3 = fma.f32x2 with a duplicated multiplier
+template <int OP>
+__global__ void __launch_bounds__(256) probe_packed_kernel(float* out, int iters) {
+  unsigned long long a[8], b, c;
+  float bf = 1.0000001f + threadIdx.x * 1e-9f, cf = 1e-9f + threadIdx.x * 1e-12f;
+  if (OP == 2 || OP == 3) asm("mov.b64 %0, {%1, %1};" : "=l"(b) : "f"(bf));
+  else asm("mov.b64 %0, {%1, %2};" : "=l"(b) : "f"(bf), "f"(bf * 1.0000001f));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(c) : "f"(cf), "f"(cf * 2.f));
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    float v = threadIdx.x * 1e-6f + k;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(a[k]) : "f"(v), "f"(v + 0.5f));
+  }
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        if (OP == 0 || OP == 2) asm volatile("add.rn.ftz.f32x2 %0, %0, %1;" : "+l"(a[k]) : "l"(b));
+        else if (OP == 1) asm volatile("mul.rn.ftz.f32x2 %0, %0, %1;" : "+l"(a[k]) : "l"(b));
+        else asm volatile("fma.rn.ftz.f32x2 %0, %0, %1, %2;" : "+l"(a[k]) : "l"(b), "l"(c));
+      }
+  }
+  unsigned long long s = 0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) s ^= a[k];
+  if (s == 0x123456789ull) out[0] = (float)s;
+}
 __global__ void __launch_bounds__(256) probe_rsq_kernel(float* out, int iters) {
   float a[8];
 #pragma unroll
@@ -360,6 +389,67 @@ __global__ void __launch_bounds__(256) probe_rsq_kernel(float* out, int iters) {
 #pragma unroll
   for (int k = 0; k < 8; ++k) s += a[k];
   if (s == 123.456f) out[0] = s;
+}
+
+// The inner-loop instruction mix of direct_sum_kernel on register-resident operands (no LDS, no TMA,
+// no barriers): the ceiling the schedule of 12 packed ops + 2 MUFU per pair can reach on this SM.
+template <int TPT>
+__global__ void __launch_bounds__(256, 2) probe_mix_kernel(float* out, int iters) {
+  typedef unsigned long long u64;
+  u64 xs[2], ys[2], zs[2], ms[2], es[2], ntx[TPT], nty[TPT], ntz[TPT], ax[TPT], ay[TPT], az[TPT];
+  const float t0 = threadIdx.x * 1e-3f;
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    asm("mov.b64 %0, {%1, %2};" : "=l"(xs[q]) : "f"(1.0f + q + t0), "f"(1.5f + q));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(ys[q]) : "f"(2.0f + q), "f"(2.5f + q + t0));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(zs[q]) : "f"(3.0f + q), "f"(3.5f + q));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(ms[q]) : "f"(1.0f), "f"(2.0f));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(es[q]) : "f"(0.01f), "f"(0.02f));
+  }
+#pragma unroll
+  for (int t = 0; t < TPT; ++t) {
+    asm("mov.b64 %0, {%1, %1};" : "=l"(ntx[t]) : "f"(-0.1f * t - t0));
+    asm("mov.b64 %0, {%1, %1};" : "=l"(nty[t]) : "f"(-0.2f * t));
+    asm("mov.b64 %0, {%1, %1};" : "=l"(ntz[t]) : "f"(-0.3f * t + t0));
+    ax[t] = ay[t] = az[t] = 0ull;
+  }
+  u64 step;
+  asm("mov.b64 %0, {%1, %1};" : "=l"(step) : "f"(1e-6f));
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int rep = 0; rep < 2; ++rep) {
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+#pragma unroll
+        for (int t = 0; t < TPT; ++t) {
+          u64 dx, dy, dz, r2, r6, y3, sc;
+          asm("add.rn.ftz.f32x2 %0, %1, %2;" : "=l"(dx) : "l"(xs[q]), "l"(ntx[t]));
+          asm("add.rn.ftz.f32x2 %0, %1, %2;" : "=l"(dy) : "l"(ys[q]), "l"(nty[t]));
+          asm("add.rn.ftz.f32x2 %0, %1, %2;" : "=l"(dz) : "l"(zs[q]), "l"(ntz[t]));
+          asm("fma.rn.ftz.f32x2 %0, %1, %1, %2;" : "=l"(r2) : "l"(dx), "l"(es[q]));
+          asm("fma.rn.ftz.f32x2 %0, %1, %1, %2;" : "=l"(r2) : "l"(dy), "l"(r2));
+          asm("fma.rn.ftz.f32x2 %0, %1, %1, %2;" : "=l"(r2) : "l"(dz), "l"(r2));
+          asm("mul.rn.ftz.f32x2 %0, %1, %1;" : "=l"(r6) : "l"(r2));
+          asm("mul.rn.ftz.f32x2 %0, %1, %2;" : "=l"(r6) : "l"(r6), "l"(r2));
+          float a, b;
+          asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(r6));
+          asm("rsqrt.approx.ftz.f32 %0, %0;" : "+f"(a));
+          asm("rsqrt.approx.ftz.f32 %0, %0;" : "+f"(b));
+          asm("mov.b64 %0, {%1, %2};" : "=l"(y3) : "f"(a), "f"(b));
+          asm("mul.rn.ftz.f32x2 %0, %1, %2;" : "=l"(sc) : "l"(ms[q]), "l"(y3));
+          asm("fma.rn.ftz.f32x2 %0, %1, %2, %0;" : "+l"(ax[t]) : "l"(dx), "l"(sc));
+          asm("fma.rn.ftz.f32x2 %0, %1, %2, %0;" : "+l"(ay[t]) : "l"(dy), "l"(sc));
+          asm("fma.rn.ftz.f32x2 %0, %1, %2, %0;" : "+l"(az[t]) : "l"(dz), "l"(sc));
+        }
+        // move the "sources" so nothing is loop invariant (1 packed add per 2*TPT interactions: not counted)
+        asm("add.rn.ftz.f32x2 %0, %0, %1;" : "+l"(xs[q]) : "l"(step));
+      }
+    }
+  }
+  u64 s = 0;
+#pragma unroll
+  for (int t = 0; t < TPT; ++t) s ^= ax[t] ^ ay[t] ^ az[t];
+  if (s == 0x123456789ull) out[0] = (float)s;
 }
 
 extern "C" double ocg_probe_throughput(ocg_ctx* ctx, int which) {
@@ -377,7 +467,13 @@ extern "C" double ocg_probe_throughput(ocg_ctx* ctx, int which) {
     cudaEventRecord(e0, 0);
     if (which == 0) probe_ffma_kernel<<<grid, block>>>(d_out, iters);
     else if (which == 1) probe_ffma2_kernel<<<grid, block>>>(d_out, iters);
-    else probe_rsq_kernel<<<grid, block>>>(d_out, iters);
+    else if (which == 2) probe_rsq_kernel<<<grid, block>>>(d_out, iters);
+    else if (which == 3) probe_packed_kernel<0><<<grid, block>>>(d_out, iters);
+    else if (which == 4) probe_packed_kernel<1><<<grid, block>>>(d_out, iters);
+    else if (which == 5) probe_packed_kernel<2><<<grid, block>>>(d_out, iters);
+    else if (which == 6) probe_packed_kernel<3><<<grid, block>>>(d_out, iters);
+    else if (which == 7) probe_mix_kernel<2><<<ctx->sm_count * 2, block>>>(d_out, iters / 4);
+    else probe_mix_kernel<1><<<ctx->sm_count * 2, block>>>(d_out, iters / 4);
     cudaEventRecord(e1, 0);
     if (cudaEventSynchronize(e1) != cudaSuccess) {
       ocg_fail(ctx, OCG_ERR_CUDA, "probe kernel failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -390,8 +486,14 @@ extern "C" double ocg_probe_throughput(ocg_ctx* ctx, int which) {
     double ops = (double)grid * block * (double)iters * 64.0;  // lane-instructions
     double rate;
     if (which == 0) rate = ops * 2.0 / (ms * 1e-3) / 1e12;        // TFLOP/s
-    else if (which == 1) rate = ops * 4.0 / (ms * 1e-3) / 1e12;   // TFLOP/s (2 FMAs per lane-instr)
-    else rate = ops / (ms * 1e-3) / 1e9;                          // G rsqrt/s
+    else if (which == 1 || which == 6) rate = ops * 4.0 / (ms * 1e-3) / 1e12;  // TFLOP/s (2 FMAs per lane-instr)
+    else if (which == 2) rate = ops / (ms * 1e-3) / 1e9;                       // G rsqrt/s
+    else if (which >= 7) {
+      // interactions/s at 20 flop: per iteration 2 reps x 2 pairs x TPT targets x 2 sources per lane
+      const int tpt = which == 7 ? 2 : 1;
+      double inter = (double)ctx->sm_count * 2 * block * (double)(iters / 4) * (2 * 2 * tpt * 2);
+      rate = inter * 20.0 / (ms * 1e-3) / 1e12;
+    } else rate = ops * 2.0 / (ms * 1e-3) / 1e12;  // packed add / mul: 2 flop per lane-instruction
     if (rep > 0 && rate > best) best = rate;
   }
   cudaEventDestroy(e0);

@@ -1,0 +1,335 @@
+// The streaming direct-sum kernel (K1 fast set, K4), templated over its tuning axes.
+// Included by direct_sum.cu only.
+#pragma once
+#include "ocg_internal.cuh"
+
+typedef unsigned long long u64;
+
+// ---------------------------------------------------------------- packed-fp32 + PTX helpers ----
+__device__ __forceinline__ u64 f2_pack(float lo, float hi) {
+  u64 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void f2_unpack(u64 v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ u64 f2_fma(u64 a, u64 b, u64 c) {
+  u64 d;
+  asm("fma.rn.ftz.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ u64 f2_add(u64 a, u64 b) {
+  u64 d;
+  asm("add.rn.ftz.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ u64 f2_mul(u64 a, u64 b) {
+  u64 d;
+  asm("mul.rn.ftz.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ float rsqrt_approx(float x) {
+  float y;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+// TMA 1-D bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP).
+__device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+// ---------------------------------------------------------------------------- work items ----
+template <int TPT>
+__device__ __forceinline__ void decode_item(const DirectParams& p, int item, long long& tgt_begin, int& tgt_count,
+                                            long long& tile_begin, int& tile_count, long long& slot) {
+  if (p.items) {
+    OcgWorkItem w = p.items[item];
+    tgt_begin = w.tgt_begin;
+    tgt_count = w.tgt_count;
+    tile_begin = w.tile_begin;
+    tile_count = w.tile_count;
+    slot = w.out_slot;
+  } else {
+    const int CT = OCG_CONSUMER_THREADS * TPT;
+    int chunk = item / p.n_ttiles;
+    int tt = item - chunk * p.n_ttiles;
+    tgt_begin = (long long)tt * CT;
+    long long rem = p.n_tgt - tgt_begin;
+    tgt_count = rem < CT ? (int)rem : CT;
+    tile_begin = (long long)chunk * p.tiles_per_chunk;
+    long long avail = (long long)(*p.n_fast_tiles) - tile_begin;
+    tile_count = avail <= 0 ? 0 : (avail < p.tiles_per_chunk ? (int)avail : p.tiles_per_chunk);
+    slot = chunk;
+  }
+}
+
+// ------------------------------------------------------------------ one tile, packed FP32 ----
+// Per pair of sources and target: 12 FMA-pipe + 2 MUFU instructions
+//   d   = xs + (-xt)                     3 FADD2
+//   r2  = dx*dx + dy*dy + dz*dz + e2     3 FFMA2
+//   r6  = (r2*r2)*r2                     2 FMUL2
+//   y3  = rsqrt(r6) = r^-3               2 MUFU.RSQ   (ONE approximate op per r^-3: ~3x less error
+//   sc  = m * y3                         1 FMUL2       than cubing an approximate r^-1)
+//   a  += d * sc                         3 FFMA2
+//   phi += sc * r2  (= m/r)              1 FFMA2      (POT only)
+// Coordinates are pre-scaled by a power of two so that r6 stays inside the FP32 range; GUARD keeps
+// the classic rsqrt(r2)^3 form (no range assumption when eps2 == 0) and skips r2 + e2 == 0 pairs.
+template <int TPT, bool POT, bool GUARD, int UNR>
+__device__ __forceinline__ void tile_packed(const float* __restrict__ stage, const float (&tx)[TPT],
+                                            const float (&ty)[TPT], const float (&tz)[TPT],
+                                            double (&dacc)[TPT][POT ? 4 : 3]) {
+  const float4* sx = reinterpret_cast<const float4*>(stage);
+  const float4* sy = sx + OCG_TS / 4;
+  const float4* sz = sy + OCG_TS / 4;
+  const float4* sm = sz + OCG_TS / 4;
+  const float4* se = sm + OCG_TS / 4;
+  u64 ntx[TPT], nty[TPT], ntz[TPT], ax[TPT], ay[TPT], az[TPT], ap[TPT];
+#pragma unroll
+  for (int t = 0; t < TPT; ++t) {
+    // negated + duplicated target coordinate; ptxas folds it into a broadcast operand (R.F32)
+    ntx[t] = f2_pack(-tx[t], -tx[t]), nty[t] = f2_pack(-ty[t], -ty[t]), ntz[t] = f2_pack(-tz[t], -tz[t]);
+    ax[t] = ay[t] = az[t] = ap[t] = 0ull;
+  }
+#pragma unroll UNR
+  for (int j = 0; j < OCG_TS / 4; ++j) {
+    const float4 X = sx[j], Y = sy[j], Z = sz[j], M = sm[j], E = se[j];
+    const u64 xs[2] = {f2_pack(X.x, X.y), f2_pack(X.z, X.w)};
+    const u64 ys[2] = {f2_pack(Y.x, Y.y), f2_pack(Y.z, Y.w)};
+    const u64 zs[2] = {f2_pack(Z.x, Z.y), f2_pack(Z.z, Z.w)};
+    const u64 ms[2] = {f2_pack(M.x, M.y), f2_pack(M.z, M.w)};
+    const u64 es[2] = {f2_pack(E.x, E.y), f2_pack(E.z, E.w)};
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+#pragma unroll
+      for (int t = 0; t < TPT; ++t) {
+        const u64 dx = f2_add(xs[q], ntx[t]);
+        const u64 dy = f2_add(ys[q], nty[t]);
+        const u64 dz = f2_add(zs[q], ntz[t]);
+        u64 r2 = f2_fma(dx, dx, es[q]);
+        r2 = f2_fma(dy, dy, r2);
+        r2 = f2_fma(dz, dz, r2);
+        u64 sc;
+        if (GUARD) {
+          float r2a, r2b;
+          f2_unpack(r2, r2a, r2b);
+          const float ria = r2a > 0.f ? rsqrt_approx(r2a) : 0.f;
+          const float rib = r2b > 0.f ? rsqrt_approx(r2b) : 0.f;
+          const u64 ri = f2_pack(ria, rib);
+          const u64 mri = f2_mul(ms[q], ri);
+          sc = f2_mul(mri, f2_mul(ri, ri));
+          if (POT) ap[t] = f2_add(ap[t], mri);
+        } else {
+          const u64 r6 = f2_mul(f2_mul(r2, r2), r2);
+          float r6a, r6b;
+          f2_unpack(r6, r6a, r6b);
+          const u64 y3 = f2_pack(rsqrt_approx(r6a), rsqrt_approx(r6b));
+          sc = f2_mul(ms[q], y3);
+          if (POT) ap[t] = f2_fma(sc, r2, ap[t]);
+        }
+        ax[t] = f2_fma(dx, sc, ax[t]);
+        ay[t] = f2_fma(dy, sc, ay[t]);
+        az[t] = f2_fma(dz, sc, az[t]);
+      }
+    }
+  }
+  // fold the tile's FP32 partial sums (even / odd sources) into the FP64 accumulators
+#pragma unroll
+  for (int t = 0; t < TPT; ++t) {
+    float lo, hi;
+    f2_unpack(ax[t], lo, hi);
+    dacc[t][0] += (double)lo + (double)hi;
+    f2_unpack(ay[t], lo, hi);
+    dacc[t][1] += (double)lo + (double)hi;
+    f2_unpack(az[t], lo, hi);
+    dacc[t][2] += (double)lo + (double)hi;
+    if (POT) {
+      f2_unpack(ap[t], lo, hi);
+      dacc[t][POT ? 3 : 0] -= (double)lo + (double)hi;
+    }
+  }
+}
+
+// ------------------------------------------------------------------ one tile, scalar FP32 ----
+// Same maths with plain FADD/FFMA/FMUL (13 issue slots per interaction): the measured baseline.
+template <int TPT, bool POT, bool GUARD, int UNR>
+__device__ __forceinline__ void tile_scalar(const float* __restrict__ stage, const float (&tx)[TPT],
+                                            const float (&ty)[TPT], const float (&tz)[TPT],
+                                            double (&dacc)[TPT][POT ? 4 : 3]) {
+  const float4* sx = reinterpret_cast<const float4*>(stage);
+  const float4* sy = sx + OCG_TS / 4;
+  const float4* sz = sy + OCG_TS / 4;
+  const float4* sm = sz + OCG_TS / 4;
+  const float4* se = sm + OCG_TS / 4;
+  float ax[TPT], ay[TPT], az[TPT], ap[TPT];
+#pragma unroll
+  for (int t = 0; t < TPT; ++t) ax[t] = ay[t] = az[t] = ap[t] = 0.f;
+#pragma unroll UNR
+  for (int j = 0; j < OCG_TS / 4; ++j) {
+    const float4 X = sx[j], Y = sy[j], Z = sz[j], M = sm[j], E = se[j];
+    const float xs[4] = {X.x, X.y, X.z, X.w}, ys[4] = {Y.x, Y.y, Y.z, Y.w};
+    const float zs[4] = {Z.x, Z.y, Z.z, Z.w}, ms[4] = {M.x, M.y, M.z, M.w};
+    const float es[4] = {E.x, E.y, E.z, E.w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+#pragma unroll
+      for (int t = 0; t < TPT; ++t) {
+        const float dx = xs[q] - tx[t], dy = ys[q] - ty[t], dz = zs[q] - tz[t];
+        float r2 = fmaf(dx, dx, es[q]);
+        r2 = fmaf(dy, dy, r2);
+        r2 = fmaf(dz, dz, r2);
+        float sc;
+        if (GUARD) {
+          const float ri = r2 > 0.f ? rsqrt_approx(r2) : 0.f;
+          const float mri = ms[q] * ri;
+          sc = mri * (ri * ri);
+          if (POT) ap[t] += mri;
+        } else {
+          const float y3 = rsqrt_approx((r2 * r2) * r2);
+          sc = ms[q] * y3;
+          if (POT) ap[t] = fmaf(sc, r2, ap[t]);
+        }
+        ax[t] = fmaf(dx, sc, ax[t]);
+        ay[t] = fmaf(dy, sc, ay[t]);
+        az[t] = fmaf(dz, sc, az[t]);
+      }
+    }
+  }
+#pragma unroll
+  for (int t = 0; t < TPT; ++t) {
+    dacc[t][0] += (double)ax[t];
+    dacc[t][1] += (double)ay[t];
+    dacc[t][2] += (double)az[t];
+    if (POT) dacc[t][POT ? 3 : 0] -= (double)ap[t];
+  }
+}
+
+// ------------------------------------------------------------------------------ the kernel ----
+// TPT    : targets per consumer thread (1 or 2)
+// POT    : also accumulate the potential (4th component)
+// GUARD  : see above
+// PACKED : FADD2/FFMA2/FMUL2 (true) or scalar FP32 (false)
+// DED    : a dedicated 9th warp issues the TMA copies (false: lane 0 of warp 0 does; 256-thread CTA)
+// MINB   : CTAs per SM the register allocation is bounded for
+// UNR    : unroll of the 4-source group loop
+template <int TPT, bool POT, bool GUARD, bool PACKED, bool DED, int MINB, int UNR>
+__global__ void __launch_bounds__(OCG_CONSUMER_THREADS + (DED ? 32 : 0), MINB) direct_sum_kernel(const DirectParams p) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float* stage_base = reinterpret_cast<float*>(smem_raw);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_raw + OCG_NSTAGE * OCG_TILE_BYTES);
+  uint64_t* empty_bar = full_bar + OCG_NSTAGE;
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  const int lane = tid & 31;
+  constexpr int NC = POT ? 4 : 3;
+
+  if (tid == 0) {
+    for (int s = 0; s < OCG_NSTAGE; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], OCG_CONSUMER_WARPS);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  uint32_t it = 0;  // running tile counter: stage = it % NSTAGE, phase = (it / NSTAGE) & 1
+
+  auto issue_tile = [&](uint32_t n, const float* src) {
+    const uint32_t s = n % OCG_NSTAGE, ph = (n / OCG_NSTAGE) & 1u;
+    mbar_wait(&empty_bar[s], ph ^ 1u);
+    mbar_expect_tx(&full_bar[s], OCG_TILE_BYTES);
+    tma_bulk_g2s(stage_base + s * OCG_TILE_FLOATS, src, OCG_TILE_BYTES, &full_bar[s]);
+  };
+
+  if (DED && warp == OCG_CONSUMER_WARPS) {
+    // ===== dedicated TMA producer warp: one elected lane streams source tiles into the ring =====
+    if (lane == 0) {
+      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+        long long tgt_begin, tile_begin, slot;
+        int tgt_count, tile_count;
+        decode_item<TPT>(p, item, tgt_begin, tgt_count, tile_begin, tile_count, slot);
+        const float* src = p.tiles + tile_begin * (long long)OCG_TILE_FLOATS;
+        for (int k = 0; k < tile_count; ++k, ++it) issue_tile(it, src + (long long)k * OCG_TILE_FLOATS);
+      }
+    }
+    return;
+  }
+
+  // ===== consumer warps =====
+  const float scale = p.scale_ptr ? *p.scale_ptr : p.scale_val;
+  for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+    long long tgt_begin, tile_begin, slot;
+    int tgt_count, tile_count;
+    decode_item<TPT>(p, item, tgt_begin, tgt_count, tile_begin, tile_count, slot);
+    const float* src = p.tiles + tile_begin * (long long)OCG_TILE_FLOATS;
+
+    if (!DED && tid == 0) {  // prologue of the ring for this item
+      const int pre = tile_count < OCG_NSTAGE - 1 ? tile_count : OCG_NSTAGE - 1;
+      for (int k = 0; k < pre; ++k) issue_tile(it + k, src + (long long)k * OCG_TILE_FLOATS);
+    }
+
+    float tx[TPT], ty[TPT], tz[TPT];
+    double dacc[TPT][NC];
+#pragma unroll
+    for (int t = 0; t < TPT; ++t) {
+      const int local = t * OCG_CONSUMER_THREADS + tid;
+      const long long gi = tgt_begin + (local < tgt_count ? local : tgt_count - 1);
+      const float4 T = __ldg(&p.tgt[gi]);
+      tx[t] = T.x * scale, ty[t] = T.y * scale, tz[t] = T.z * scale;  // power of two: exact
+#pragma unroll
+      for (int c = 0; c < NC; ++c) dacc[t][c] = 0.0;
+    }
+
+    for (int k = 0; k < tile_count; ++k, ++it) {
+      if (!DED && tid == 0 && k + OCG_NSTAGE - 1 < tile_count)
+        issue_tile(it + OCG_NSTAGE - 1, src + (long long)(k + OCG_NSTAGE - 1) * OCG_TILE_FLOATS);
+      const uint32_t s = it % OCG_NSTAGE, ph = (it / OCG_NSTAGE) & 1u;
+      mbar_wait(&full_bar[s], ph);
+      const float* stage = stage_base + s * OCG_TILE_FLOATS;
+      if (PACKED) tile_packed<TPT, POT, GUARD, UNR>(stage, tx, ty, tz, dacc);
+      else tile_scalar<TPT, POT, GUARD, UNR>(stage, tx, ty, tz, dacc);
+      // this warp is done reading stage s: hand it back to the producer
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty_bar[s]);
+    }
+
+#pragma unroll
+    for (int t = 0; t < TPT; ++t) {
+      const int local = t * OCG_CONSUMER_THREADS + tid;
+      if (local < tgt_count) {
+        const long long gi = tgt_begin + local;
+#pragma unroll
+        for (int c = 0; c < NC; ++c) p.partial[(slot * NC + c) * p.out_stride + gi] = dacc[t][c];
+      }
+    }
+  }
+}

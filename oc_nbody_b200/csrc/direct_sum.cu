@@ -19,393 +19,7 @@
 
 #include <math.h>
 
-typedef unsigned long long u64;
-
-// ---------------------------------------------------------------- packed-fp32 + PTX helpers ----
-__device__ __forceinline__ u64 f2_pack(float lo, float hi) {
-  u64 r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-  return r;
-}
-__device__ __forceinline__ void f2_unpack(u64 v, float& lo, float& hi) {
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
-}
-__device__ __forceinline__ u64 f2_fma(u64 a, u64 b, u64 c) {
-  u64 d;
-  asm("fma.rn.ftz.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-  return d;
-}
-__device__ __forceinline__ u64 f2_add(u64 a, u64 b) {
-  u64 d;
-  asm("add.rn.ftz.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-  return d;
-}
-__device__ __forceinline__ u64 f2_mul(u64 a, u64 b) {
-  u64 d;
-  asm("mul.rn.ftz.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-  return d;
-}
-__device__ __forceinline__ float rsqrt_approx(float x) {
-  float y;
-  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) {
-  return (uint32_t)__cvta_generic_to_shared(p);
-}
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
-               "r"(bytes)
-               : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t done;
-  do {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-        "selp.u32 %0, 1, 0, p;\n"
-        "}\n"
-        : "=r"(done)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-  } while (!done);
-}
-// TMA 1-D bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP).
-__device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes,
-                                             uint64_t* bar) {
-  asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
-          "r"(smem_u32(dst_smem)),
-      "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
-      : "memory");
-}
-
-template <int TPT>
-__device__ __forceinline__ void decode_item(const DirectParams& p, int item, long long& tgt_begin,
-                                            int& tgt_count, long long& tile_begin, int& tile_count,
-                                            long long& slot) {
-  if (p.items) {
-    OcgWorkItem w = p.items[item];
-    tgt_begin = w.tgt_begin;
-    tgt_count = w.tgt_count;
-    tile_begin = w.tile_begin;
-    tile_count = w.tile_count;
-    slot = w.out_slot;
-  } else {
-    const int CT = OCG_CONSUMER_THREADS * TPT;
-    int chunk = item / p.n_ttiles;
-    int tt = item - chunk * p.n_ttiles;
-    tgt_begin = (long long)tt * CT;
-    long long rem = p.n_tgt - tgt_begin;
-    tgt_count = rem < CT ? (int)rem : CT;
-    tile_begin = (long long)chunk * p.tiles_per_chunk;
-    long long avail = (long long)(*p.n_fast_tiles) - tile_begin;
-    tile_count = avail <= 0 ? 0 : (avail < p.tiles_per_chunk ? (int)avail : p.tiles_per_chunk);
-    slot = chunk;
-  }
-}
-
-// ------------------------------------------------------------------------- the fast kernel ----
-// TPT   : targets per consumer thread
-// POT   : also accumulate the potential (4th component)
-// GUARD : tolerate r2 + e2 == 0 (self pairs when eps2 == 0): such pairs contribute nothing
-//
-// Per pair of sources and target (12 FMA-pipe + 2 MUFU instructions):
-//   d   = xs + (-xt)                     3 FADD2
-//   r2  = dx*dx + dy*dy + dz*dz + e2     3 FFMA2
-//   r6  = (r2*r2)*r2                     2 FMUL2
-//   y3  = rsqrt(r6) = r^-3               2 MUFU.RSQ   (ONE approximate op per r^-3: ~3x less error
-//   sc  = m * y3                         1 FMUL2       than cubing an approximate r^-1)
-//   a  += d * sc                         3 FFMA2
-//   phi += sc * r2  (= m/r)              1 FFMA2      (POT only)
-// Coordinates are pre-scaled by a power of two so that r6 stays inside the FP32 range; GUARD keeps
-// the classic rsqrt(r2)^3 form (no range assumption when eps2 == 0).
-template <int TPT, bool POT, bool GUARD>
-__global__ void __launch_bounds__(OCG_CTA_THREADS, 2) direct_sum_kernel(const DirectParams p) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  float* stage_base = reinterpret_cast<float*>(smem_raw);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_raw + OCG_NSTAGE * OCG_TILE_BYTES);
-  uint64_t* empty_bar = full_bar + OCG_NSTAGE;
-
-  const int tid = threadIdx.x;
-  const int warp = tid >> 5;
-  const int lane = tid & 31;
-  constexpr int NC = POT ? 4 : 3;
-
-  if (tid == 0) {
-    for (int s = 0; s < OCG_NSTAGE; ++s) {
-      mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], OCG_CONSUMER_WARPS);
-    }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();
-
-  uint32_t it = 0;  // running tile counter: stage = it % NSTAGE, phase = (it / NSTAGE) & 1
-
-  if (warp == OCG_CONSUMER_WARPS) {
-    // ===== TMA producer warp: one elected lane streams source tiles into the ring =====
-    if (lane == 0) {
-      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-        long long tgt_begin, tile_begin, slot;
-        int tgt_count, tile_count;
-        decode_item<TPT>(p, item, tgt_begin, tgt_count, tile_begin, tile_count, slot);
-        const float* src = p.tiles + tile_begin * (long long)OCG_TILE_FLOATS;
-        for (int k = 0; k < tile_count; ++k, ++it) {
-          const uint32_t s = it % OCG_NSTAGE;
-          const uint32_t ph = (it / OCG_NSTAGE) & 1u;
-          mbar_wait(&empty_bar[s], ph ^ 1u);
-          mbar_expect_tx(&full_bar[s], OCG_TILE_BYTES);
-          tma_bulk_g2s(stage_base + s * OCG_TILE_FLOATS, src + (long long)k * OCG_TILE_FLOATS,
-                       OCG_TILE_BYTES, &full_bar[s]);
-        }
-      }
-    }
-    return;
-  }
-
-  // ===== consumer warps =====
-  for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-    long long tgt_begin, tile_begin, slot;
-    int tgt_count, tile_count;
-    decode_item<TPT>(p, item, tgt_begin, tgt_count, tile_begin, tile_count, slot);
-
-    // negated, duplicated target coordinates: dx = xs + (-xt)
-    u64 ntx[TPT], nty[TPT], ntz[TPT];
-    double dacc[TPT][NC];
-    const float scale = p.scale_ptr ? *p.scale_ptr : p.scale_val;
-#pragma unroll
-    for (int t = 0; t < TPT; ++t) {
-      int local = t * OCG_CONSUMER_THREADS + tid;
-      long long gi = tgt_begin + (local < tgt_count ? local : tgt_count - 1);
-      float4 T = __ldg(&p.tgt[gi]);
-      T.x *= scale, T.y *= scale, T.z *= scale;  // power of two: exact
-      ntx[t] = f2_pack(-T.x, -T.x);
-      nty[t] = f2_pack(-T.y, -T.y);
-      ntz[t] = f2_pack(-T.z, -T.z);
-#pragma unroll
-      for (int c = 0; c < NC; ++c) dacc[t][c] = 0.0;
-    }
-
-    for (int k = 0; k < tile_count; ++k, ++it) {
-      const uint32_t s = it % OCG_NSTAGE;
-      const uint32_t ph = (it / OCG_NSTAGE) & 1u;
-      mbar_wait(&full_bar[s], ph);
-
-      const float4* sx = reinterpret_cast<const float4*>(stage_base + s * OCG_TILE_FLOATS);
-      const float4* sy = sx + OCG_TS / 4;
-      const float4* sz = sy + OCG_TS / 4;
-      const float4* sm = sz + OCG_TS / 4;
-      const float4* se = sm + OCG_TS / 4;
-
-      u64 ax[TPT], ay[TPT], az[TPT], ap[TPT];
-#pragma unroll
-      for (int t = 0; t < TPT; ++t) ax[t] = ay[t] = az[t] = ap[t] = 0ull;
-
-#pragma unroll 2
-      for (int j = 0; j < OCG_TS / 4; ++j) {
-        const float4 X = sx[j], Y = sy[j], Z = sz[j], M = sm[j], E = se[j];
-        u64 xs[2] = {f2_pack(X.x, X.y), f2_pack(X.z, X.w)};
-        u64 ys[2] = {f2_pack(Y.x, Y.y), f2_pack(Y.z, Y.w)};
-        u64 zs[2] = {f2_pack(Z.x, Z.y), f2_pack(Z.z, Z.w)};
-        u64 ms[2] = {f2_pack(M.x, M.y), f2_pack(M.z, M.w)};
-        u64 es[2] = {f2_pack(E.x, E.y), f2_pack(E.z, E.w)};
-#pragma unroll
-        for (int q = 0; q < 2; ++q) {
-#pragma unroll
-          for (int t = 0; t < TPT; ++t) {
-            u64 dx = f2_add(xs[q], ntx[t]);
-            u64 dy = f2_add(ys[q], nty[t]);
-            u64 dz = f2_add(zs[q], ntz[t]);
-            u64 r2 = f2_fma(dx, dx, es[q]);
-            r2 = f2_fma(dy, dy, r2);
-            r2 = f2_fma(dz, dz, r2);
-            u64 sc;
-            if (GUARD) {
-              float r2a, r2b;
-              f2_unpack(r2, r2a, r2b);
-              float ria = r2a > 0.f ? rsqrt_approx(r2a) : 0.f;
-              float rib = r2b > 0.f ? rsqrt_approx(r2b) : 0.f;
-              u64 ri = f2_pack(ria, rib);
-              u64 mri = f2_mul(ms[q], ri);
-              sc = f2_mul(mri, f2_mul(ri, ri));
-              if (POT) ap[t] = f2_add(ap[t], mri);
-            } else {
-              u64 r6 = f2_mul(f2_mul(r2, r2), r2);
-              float r6a, r6b;
-              f2_unpack(r6, r6a, r6b);
-              u64 y3 = f2_pack(rsqrt_approx(r6a), rsqrt_approx(r6b));
-              sc = f2_mul(ms[q], y3);
-              if (POT) ap[t] = f2_fma(sc, r2, ap[t]);
-            }
-            ax[t] = f2_fma(dx, sc, ax[t]);
-            ay[t] = f2_fma(dy, sc, ay[t]);
-            az[t] = f2_fma(dz, sc, az[t]);
-          }
-        }
-      }
-
-      // this warp is done reading stage s: hand it back to the producer
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&empty_bar[s]);
-
-      // fold the tile's FP32 partial sums into the FP64 accumulators
-#pragma unroll
-      for (int t = 0; t < TPT; ++t) {
-        float lo, hi;
-        f2_unpack(ax[t], lo, hi);
-        dacc[t][0] += (double)lo + (double)hi;
-        f2_unpack(ay[t], lo, hi);
-        dacc[t][1] += (double)lo + (double)hi;
-        f2_unpack(az[t], lo, hi);
-        dacc[t][2] += (double)lo + (double)hi;
-        if (POT) {
-          f2_unpack(ap[t], lo, hi);
-          dacc[t][NC - 1] -= (double)lo + (double)hi;
-        }
-      }
-    }
-
-#pragma unroll
-    for (int t = 0; t < TPT; ++t) {
-      int local = t * OCG_CONSUMER_THREADS + tid;
-      if (local < tgt_count) {
-        long long gi = tgt_begin + local;
-#pragma unroll
-        for (int c = 0; c < NC; ++c)
-          p.partial[(slot * NC + c) * p.out_stride + gi] = dacc[t][c];
-      }
-    }
-  }
-}
-
-// --------------------------------------------------------------------- scalar FP32 variant ----
-// Same structure with plain FADD/FFMA/FMUL (13 issue slots per interaction). Kept as the
-// measured baseline the packed kernel is compared against (bench.py --variant scalar).
-template <int TPT, bool POT, bool GUARD>
-__global__ void __launch_bounds__(OCG_CTA_THREADS, 2) direct_sum_scalar_kernel(const DirectParams p) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  float* stage_base = reinterpret_cast<float*>(smem_raw);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_raw + OCG_NSTAGE * OCG_TILE_BYTES);
-  uint64_t* empty_bar = full_bar + OCG_NSTAGE;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  constexpr int NC = POT ? 4 : 3;
-  if (tid == 0) {
-    for (int s = 0; s < OCG_NSTAGE; ++s) {
-      mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], OCG_CONSUMER_WARPS);
-    }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();
-  uint32_t it = 0;
-  if (warp == OCG_CONSUMER_WARPS) {
-    if (lane == 0) {
-      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-        long long tgt_begin, tile_begin, slot;
-        int tgt_count, tile_count;
-        decode_item<TPT>(p, item, tgt_begin, tgt_count, tile_begin, tile_count, slot);
-        const float* src = p.tiles + tile_begin * (long long)OCG_TILE_FLOATS;
-        for (int k = 0; k < tile_count; ++k, ++it) {
-          const uint32_t s = it % OCG_NSTAGE, ph = (it / OCG_NSTAGE) & 1u;
-          mbar_wait(&empty_bar[s], ph ^ 1u);
-          mbar_expect_tx(&full_bar[s], OCG_TILE_BYTES);
-          tma_bulk_g2s(stage_base + s * OCG_TILE_FLOATS, src + (long long)k * OCG_TILE_FLOATS,
-                       OCG_TILE_BYTES, &full_bar[s]);
-        }
-      }
-    }
-    return;
-  }
-  for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-    long long tgt_begin, tile_begin, slot;
-    int tgt_count, tile_count;
-    decode_item<TPT>(p, item, tgt_begin, tgt_count, tile_begin, tile_count, slot);
-    float tx[TPT], ty[TPT], tz[TPT];
-    double dacc[TPT][NC];
-    const float scale = p.scale_ptr ? *p.scale_ptr : p.scale_val;
-#pragma unroll
-    for (int t = 0; t < TPT; ++t) {
-      int local = t * OCG_CONSUMER_THREADS + tid;
-      long long gi = tgt_begin + (local < tgt_count ? local : tgt_count - 1);
-      float4 T = __ldg(&p.tgt[gi]);
-      tx[t] = T.x * scale, ty[t] = T.y * scale, tz[t] = T.z * scale;
-#pragma unroll
-      for (int c = 0; c < NC; ++c) dacc[t][c] = 0.0;
-    }
-    for (int k = 0; k < tile_count; ++k, ++it) {
-      const uint32_t s = it % OCG_NSTAGE, ph = (it / OCG_NSTAGE) & 1u;
-      mbar_wait(&full_bar[s], ph);
-      const float4* sx = reinterpret_cast<const float4*>(stage_base + s * OCG_TILE_FLOATS);
-      const float4* sy = sx + OCG_TS / 4;
-      const float4* sz = sy + OCG_TS / 4;
-      const float4* sm = sz + OCG_TS / 4;
-      const float4* se = sm + OCG_TS / 4;
-      float ax[TPT], ay[TPT], az[TPT], ap[TPT];
-#pragma unroll
-      for (int t = 0; t < TPT; ++t) ax[t] = ay[t] = az[t] = ap[t] = 0.f;
-#pragma unroll 2
-      for (int j = 0; j < OCG_TS / 4; ++j) {
-        const float4 X = sx[j], Y = sy[j], Z = sz[j], M = sm[j], E = se[j];
-        const float xs[4] = {X.x, X.y, X.z, X.w}, ys[4] = {Y.x, Y.y, Y.z, Y.w};
-        const float zs[4] = {Z.x, Z.y, Z.z, Z.w}, ms[4] = {M.x, M.y, M.z, M.w};
-        const float es[4] = {E.x, E.y, E.z, E.w};
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-#pragma unroll
-          for (int t = 0; t < TPT; ++t) {
-            float dx = xs[q] - tx[t], dy = ys[q] - ty[t], dz = zs[q] - tz[t];
-            float r2 = fmaf(dx, dx, es[q]);
-            r2 = fmaf(dy, dy, r2);
-            r2 = fmaf(dz, dz, r2);
-            float sc;
-            if (GUARD) {
-              float ri = r2 > 0.f ? rsqrt_approx(r2) : 0.f;
-              float mri = ms[q] * ri;
-              sc = mri * (ri * ri);
-              if (POT) ap[t] += mri;
-            } else {
-              float y3 = rsqrt_approx((r2 * r2) * r2);
-              sc = ms[q] * y3;
-              if (POT) ap[t] = fmaf(sc, r2, ap[t]);
-            }
-            ax[t] = fmaf(dx, sc, ax[t]);
-            ay[t] = fmaf(dy, sc, ay[t]);
-            az[t] = fmaf(dz, sc, az[t]);
-          }
-        }
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&empty_bar[s]);
-#pragma unroll
-      for (int t = 0; t < TPT; ++t) {
-        dacc[t][0] += (double)ax[t];
-        dacc[t][1] += (double)ay[t];
-        dacc[t][2] += (double)az[t];
-        if (POT) dacc[t][NC - 1] -= (double)ap[t];
-      }
-    }
-#pragma unroll
-    for (int t = 0; t < TPT; ++t) {
-      int local = t * OCG_CONSUMER_THREADS + tid;
-      if (local < tgt_count) {
-        long long gi = tgt_begin + local;
-#pragma unroll
-        for (int c = 0; c < NC; ++c)
-          p.partial[(slot * NC + c) * p.out_stride + gi] = dacc[t][c];
-      }
-    }
-  }
-}
+#include "direct_kernel.cuh"
 
 // ---------------------------------------------------------------- source classification ----
 // Every source goes to exactly one of two sets:
@@ -773,46 +387,82 @@ static size_t direct_smem_bytes() { return OCG_NSTAGE * OCG_TILE_BYTES + 2 * OCG
 
 typedef void (*direct_fn)(const DirectParams);
 
-template <int TPT>
-static direct_fn pick_kernel(bool pot, bool guard, bool scalar) {
-  if (scalar) {
-    if (pot) return guard ? direct_sum_scalar_kernel<TPT, true, true> : direct_sum_scalar_kernel<TPT, true, false>;
-    return guard ? direct_sum_scalar_kernel<TPT, false, true> : direct_sum_scalar_kernel<TPT, false, false>;
+// A tuning variant of the streaming kernel. fn[pot][guard]; sweep-only variants fill fn[0][0] only.
+struct DirectVariant {
+  const char* name;
+  int tpt, minb;
+  bool ded;
+  direct_fn fn[2][2];
+};
+#define OCG_FULL(TPT, PACKED, DED, MINB, UNR)                                                            \
+  {                                                                                                      \
+    {direct_sum_kernel<TPT, false, false, PACKED, DED, MINB, UNR>,                                       \
+     direct_sum_kernel<TPT, false, true, PACKED, DED, MINB, UNR>},                                       \
+    {direct_sum_kernel<TPT, true, false, PACKED, DED, MINB, UNR>,                                        \
+     direct_sum_kernel<TPT, true, true, PACKED, DED, MINB, UNR>}                                         \
   }
-  if (pot) return guard ? direct_sum_kernel<TPT, true, true> : direct_sum_kernel<TPT, true, false>;
-  return guard ? direct_sum_kernel<TPT, false, true> : direct_sum_kernel<TPT, false, false>;
-}
+#define OCG_ONE(TPT, PACKED, DED, MINB, UNR)                                                             \
+  {                                                                                                      \
+    {direct_sum_kernel<TPT, false, false, PACKED, DED, MINB, UNR>, nullptr}, { nullptr, nullptr }        \
+  }
+static const DirectVariant g_variants[] = {
+    /* 0 */ {"tpt2 packed ded minb2 unr2", 2, 2, true, OCG_FULL(2, true, true, 2, 2)},
+    /* 1 */ {"tpt1 packed ded minb2 unr2", 1, 2, true, OCG_FULL(1, true, true, 2, 2)},
+    /* 2 */ {"tpt2 scalar ded minb2 unr2", 2, 2, true, OCG_FULL(2, false, true, 2, 2)},
+    /* 3 */ {"tpt1 scalar ded minb2 unr2", 1, 2, true, OCG_FULL(1, false, true, 2, 2)},
+    /* 4 */ {"tpt2 packed inl minb2 unr2", 2, 2, false, OCG_FULL(2, true, false, 2, 2)},
+    /* 5 */ {"tpt1 packed inl minb3 unr2", 1, 3, false, OCG_ONE(1, true, false, 3, 2)},
+    /* 6 */ {"tpt1 packed inl minb4 unr2", 1, 4, false, OCG_ONE(1, true, false, 4, 2)},
+    /* 7 */ {"tpt2 packed inl minb3 unr2", 2, 3, false, OCG_ONE(2, true, false, 3, 2)},
+    /* 8 */ {"tpt2 packed inl minb2 unr4", 2, 2, false, OCG_ONE(2, true, false, 2, 4)},
+    /* 9 */ {"tpt1 packed inl minb3 unr4", 1, 3, false, OCG_ONE(1, true, false, 3, 4)},
+    /* 10 */ {"tpt2 packed ded minb2 unr1", 2, 2, true, OCG_ONE(2, true, true, 2, 1)},
+    /* 11 */ {"tpt2 packed inl minb2 unr1", 2, 2, false, OCG_ONE(2, true, false, 2, 1)},
+    /* 12 */ {"tpt1 packed inl minb2 unr2", 1, 2, false, OCG_ONE(1, true, false, 2, 2)},
+    /* 13 */ {"tpt1 packed inl minb3 unr1", 1, 3, false, OCG_ONE(1, true, false, 3, 1)},
+    /* 14 */ {"tpt2 packed ded minb2 unr4", 2, 2, true, OCG_ONE(2, true, true, 2, 4)},
+};
+static const int g_n_variants = (int)(sizeof(g_variants) / sizeof(g_variants[0]));
+#define OCG_DEFAULT_VARIANT_BIG 4   /* many targets: measured best on B200 (tools/probe.py) */
+#define OCG_DEFAULT_VARIANT_SMALL 1 /* few targets: one per thread spreads them over more CTAs */
 
-static int g_force_tpt = 0;     // 0 = heuristic
-static int g_force_scalar = 0;  // 1 = scalar FP32 variant
-static int g_precise_near = 1;  // 0 = no precision radius (criterion (a) only)
-extern "C" int ocg_debug_set_variant(int tpt, int scalar) {
-  g_force_tpt = tpt;
-  g_force_scalar = scalar;
-  return 0;
+static int g_force_variant = -1;  // -1 = heuristic
+static int g_precise_near = 1;    // 0 = no precision radius (criterion (a) only)
+extern "C" int ocg_debug_set_variant(int id) {
+  if (id >= g_n_variants) return OCG_ERR_INVALID;
+  g_force_variant = id;
+  return g_n_variants;
 }
+extern "C" const char* ocg_debug_variant_name(int id) { return id >= 0 && id < g_n_variants ? g_variants[id].name : ""; }
 extern "C" int ocg_debug_set_precise_near(int on) {
   g_precise_near = on;
   return 0;
 }
 
-int ocg_pick_tpt(ocg_ctx* ctx, int64_t n_tgt) {
-  if (g_force_tpt == 1 || g_force_tpt == 2) return g_force_tpt;
-  // enough targets to give every resident CTA a full tile at TPT=2?
+int ocg_pick_variant(ocg_ctx* ctx, int64_t n_tgt) {
+  if (g_force_variant >= 0) return g_force_variant;
+  // enough targets to give every resident CTA a full tile at 2 targets per thread?
   long long full = (long long)ctx->sm_count * 2 * OCG_CONSUMER_THREADS * 2;
-  return n_tgt >= full ? 2 : 1;
+  return n_tgt >= full ? OCG_DEFAULT_VARIANT_BIG : OCG_DEFAULT_VARIANT_SMALL;
 }
+int ocg_variant_tpt(int v) { return g_variants[v].tpt; }
+int ocg_variant_slots(ocg_ctx* ctx, int v) { return ctx->sm_count * g_variants[v].minb; }
 
 // Launch the fast kernel over a prepared parameter block.
-int ocg_launch_direct(ocg_ctx* ctx, DirectParams& p, int tpt, bool pot, bool guard, cudaStream_t st) {
-  direct_fn fn = tpt == 2 ? pick_kernel<2>(pot, guard, g_force_scalar) : pick_kernel<1>(pot, guard, g_force_scalar);
+int ocg_launch_direct(ocg_ctx* ctx, DirectParams& p, int variant, bool pot, bool guard, cudaStream_t st) {
+  const DirectVariant* v = &g_variants[variant];
+  if (!v->fn[pot][guard]) {
+    // sweep-only variant asked for a pot/guard form it does not carry: use the production one of equal TPT
+    v = &g_variants[v->tpt == 2 ? OCG_DEFAULT_VARIANT_BIG : OCG_DEFAULT_VARIANT_SMALL];
+  }
+  direct_fn fn = v->fn[pot][guard];
   size_t smem = direct_smem_bytes();
   OCG_CUDA(ctx, cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int grid = ctx->sm_count * 2;
+  int grid = ctx->sm_count * v->minb;
   if (grid > p.n_items) grid = p.n_items;
   if (grid < 1) grid = 1;
   if (ctx->timing) OCG_CUDA(ctx, cudaEventRecord(ctx->ev0, st));
-  fn<<<grid, OCG_CTA_THREADS, smem, st>>>(p);
+  fn<<<grid, OCG_CONSUMER_THREADS + (v->ded ? 32 : 0), smem, st>>>(p);
   OCG_CHECK_LAUNCH(ctx, "direct_sum_kernel");
   if (ctx->timing) {
     OCG_CUDA(ctx, cudaEventRecord(ctx->ev1, st));
@@ -838,13 +488,14 @@ int ocg_direct_sum_impl(ocg_ctx* ctx, const float* src_xyzm, const float* src_so
     return OCG_OK;
   }
 
-  const int tpt = ocg_pick_tpt(ctx, n_tgt);
+  const int variant = ocg_pick_variant(ctx, n_tgt);
+  const int tpt = ocg_variant_tpt(variant);
   const int CT = OCG_CONSUMER_THREADS * tpt;
   const long long n_ttiles = (n_tgt + CT - 1) / CT;
   const long long n_tiles_max = (n_src + OCG_TS - 1) / OCG_TS;
-  // chunking: aim for >= 16 items per resident CTA slot
-  const long long slots = (long long)ctx->sm_count * 2;
-  long long n_chunks = (16 * slots + n_ttiles - 1) / n_ttiles;
+  // chunking: aim for >= 64 equal-cost items per resident CTA slot (static striding; tail loss < 1%)
+  const long long slots = ocg_variant_slots(ctx, variant);
+  long long n_chunks = (64 * slots + n_ttiles - 1) / n_ttiles;
   if (n_chunks > n_tiles_max) n_chunks = n_tiles_max;
   if (n_chunks > 1024) n_chunks = 1024;
   if (n_chunks < 1) n_chunks = 1;
@@ -912,7 +563,7 @@ int ocg_direct_sum_impl(ocg_ctx* ctx, const float* src_xyzm, const float* src_so
   p.n_fast_tiles = misc + MISC_NFAST_TILES;
   p.scale_ptr = reinterpret_cast<const float*>(misc + MISC_SCALE);
   p.scale_val = 1.0f;
-  if ((rc = ocg_launch_direct(ctx, p, tpt, want_pot, /*guard=*/false, st))) return rc;
+  if ((rc = ocg_launch_direct(ctx, p, variant, want_pot, /*guard=*/false, st))) return rc;
 
   {
     long long nb = (n_tgt + 255) / 256;

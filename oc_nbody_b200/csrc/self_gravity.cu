@@ -118,7 +118,8 @@ extern "C" int ocg_self_gravity(ocg_ctx* ctx, const double* pos_dev, const doubl
     if (!(scale > 0.f) || !isfinite(scale) || !(e2f * scale * scale > 0.f)) scale = 1.0f;
   }
   const int64_t n_shard = tgt_end - tgt_begin;
-  const int tpt = ocg_pick_tpt(ctx, n_shard);
+  const int variant = ocg_pick_variant(ctx, n_shard);
+  const int tpt = ocg_variant_tpt(variant);
   const int CT = OCG_CONSUMER_THREADS * tpt;
 
   // ---- host-side plan: tile offsets per segment, chunk count, item list ----
@@ -138,7 +139,7 @@ extern "C" int ocg_self_gravity(ocg_ctx* ctx, const double* pos_dev, const doubl
     if (b > a) n_tt_total += (b - a + CT - 1) / CT;
   }
   seg_tile[n_seg] = total_tiles;
-  const long long slots = (long long)ctx->sm_count * 2;
+  const long long slots = ocg_variant_slots(ctx, variant);
   long long n_chunks = n_tt_total > 0 ? (16 * slots + n_tt_total - 1) / n_tt_total : 1;
   if (n_chunks > max_tiles) n_chunks = max_tiles;
   if (n_chunks > 256) n_chunks = 256;
@@ -238,7 +239,7 @@ extern "C" int ocg_self_gravity(ocg_ctx* ctx, const double* pos_dev, const doubl
   p.n_fast_tiles = nullptr;
   p.scale_ptr = nullptr;
   p.scale_val = scale;
-  if ((rc = ocg_launch_direct(ctx, p, tpt, want_pot, guard, st))) return rc;
+  if ((rc = ocg_launch_direct(ctx, p, variant, want_pot, guard, st))) return rc;
   finish_self_kernel<<<(int)((n_shard + 255) / 256), 256, 0, st>>>(partial, n, (int)n_chunks, NC, G, tgt_begin,
                                                                   tgt_end, tgt, guard ? 0.f : e2f * scale * scale, scale, acc_dev, pot_dev);
   OCG_CHECK_LAUNCH(ctx, "finish_self_kernel");

@@ -63,7 +63,7 @@ class gizmo_field(object):
         if self.fine_grid:
             raise NotImplementedError("nested fine grid is a SURVEY §8(f) 'next' row")
         self.G = G_KPC_KMS_MYR  # kpc^2 km/s /Myr /Msun, the unit of gizmo_interface.py:70
-        self.ctx = ctx or _lib.default_context()
+        self._ctx = ctx  # created lazily: host-side logic (source assembly, time bracketing) needs no GPU
         self.snapshots = list(snapshots)
         nsnap = len(self.snapshots)
         if nsnap < 1:
@@ -87,6 +87,12 @@ class gizmo_field(object):
         if build:
             self._init_grid_()
             self.evolve_model(0.0 | units.Myr)
+
+    @property
+    def ctx(self):
+        if self._ctx is None:
+            self._ctx = _lib.default_context()
+        return self._ctx
 
     # ------------------------------------------------------------------ field build (init time) ----
     def _source_arrays_(self, snap):

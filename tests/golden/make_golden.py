@@ -1,0 +1,56 @@
+"""Generates tests/golden/*.npz from the REAL reference, imported in the build container.
+
+Run here (where /root/reference exists):  python tests/golden/make_golden.py
+The GPU box has no /root/reference: tests only read the committed .npz files.
+
+What can be generated: only `grid_cartesian.py` is importable (numpy only).  Everything else on the hot path
+needs amuse / pykdgrav / rbf / gizmo_analysis, which are absent, and gizmo_interface.py cannot be imported at all
+(analysis.py:573 SyntaxError) — SURVEY.md §0.3.  The reference's time interpolation is scipy's splrep/splev
+(gizmo_interface.py:587-597,38-44), which IS runnable: a fixture of it pins the cubic-in-time "next" row.
+"""
+import importlib.util
+import os
+
+import numpy as np
+from scipy import interpolate
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF = "/root/reference/grid_cartesian.py"
+
+
+def main():
+    spec = importlib.util.spec_from_file_location("ref_grid_cartesian", REF)
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)
+    cases = [(0.6, 0.6, 0.6, 0.6 / 16), (0.6, 0.6, 0.6, 0.6 / 4), (0.6, 0.3, 0.45, 0.011), (1.0, 1.0, 1.0, 0.13),
+             (0.6, 0.6, 0.6, 0.005 * 6)]
+    out = {}
+    for k, (lx, ly, lz, res) in enumerate(cases):
+        g = ref.grid(lx, ly, lz, res)
+        g.gen_evolved_grid(np.array([8.0, -0.25, 0.125]))
+        out["case%d_args" % k] = np.array([lx, ly, lz, res])
+        out["case%d_n" % k] = np.array([g.x_n, g.y_n, g.z_n])
+        out["case%d_x_grid" % k] = g.x_grid
+        out["case%d_y_grid" % k] = g.y_grid
+        out["case%d_z_grid" % k] = g.z_grid
+        out["case%d_init_grid" % k] = g.init_grid
+        out["case%d_evolved_grid" % k] = g.evolved_grid
+    out["n_cases"] = np.array(len(cases))
+    np.savez_compressed(os.path.join(HERE, "grid_reference.npz"), **out)
+
+    # the reference's time interpolation mechanism, as-is: splrep per grid point, splev at t
+    rng = np.random.default_rng(1776)
+    times = np.array([0.0, 22.0, 45.5, 68.0, 91.2, 113.9])
+    series = rng.normal(0.0, 1e-2, (len(times), 40)) + np.sin(times[:, None] / 35.0)
+    t_eval = np.array([0.0, 3.3, 22.0, 50.1, 100.0, 113.9])
+    vals = np.empty((len(t_eval), series.shape[1]))
+    for i in range(series.shape[1]):
+        tck = interpolate.splrep(times, series[:, i])
+        vals[:, i] = [float(interpolate.splev(t, tck)) for t in t_eval]
+    np.savez_compressed(os.path.join(HERE, "time_spline_reference.npz"), times=times, series=series, t_eval=t_eval,
+                        values=vals)
+    print("wrote golden fixtures to", HERE)
+
+
+if __name__ == "__main__":
+    main()

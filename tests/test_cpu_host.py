@@ -1,0 +1,163 @@
+"""CPU: host-side logic of the plugin mirror and the C-ABI surface (no compute calls without a GPU)."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    import oc_nbody_b200
+    from oc_nbody_b200._lib import ABI_SYMBOLS
+    L = oc_nbody_b200.load_library()
+    header = open(os.path.join(ROOT, "include", "ocg.h")).read()
+    declared = sorted(set(re.findall(r"\b(ocg_[a-z0-9_]+)\s*\(", header)))
+    assert declared == sorted(ABI_SYMBOLS)
+    for name in declared:
+        assert hasattr(L, name), name
+    assert L.ocg_version() == 100
+
+
+def test_no_cpu_fallback():
+    """Without a GPU the product refuses to run instead of silently computing on the host."""
+    import torch
+    import oc_nbody_b200
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(oc_nbody_b200.OcgError, match="no CPU fallback"):
+        oc_nbody_b200.Context(0)
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "oc_nbody_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(import|from)\s+oracle\b", text, re.M), f
+                assert "ocg_oracle" not in text.replace("oracle/ocg_oracle.c", ""), f
+
+
+def test_units_shim():
+    from oc_nbody_b200.units import G_KPC_KMS_MYR, G_PC_KMS2, Quantity, to_value, units
+    q = np.array([1.0, 2.0]) | units.parsec
+    assert isinstance(q, Quantity) and np.allclose(q.value_in(units.kpc), [1e-3, 2e-3])
+    assert np.isclose(((0.01 | units.parsec) ** 2).value_in(units.kpc ** 2), 1e-10)
+    assert np.isclose((1.0 | units.kms).value_in(units.kpc / units.Myr), 1.022712165045695e-3)
+    assert [3.0, 4.0] | units.kms  # a plain list, as the reference returns (gizmo_interface.py:706)
+    with pytest.raises(ValueError):
+        q.value_in(units.Myr)
+    assert to_value(3.5, units.kpc) == 3.5
+    # G in the unit of gizmo_interface.py:70, and in pc (km/s)^2/Msun
+    assert np.isclose(G_KPC_KMS_MYR, 4.3986004e-09, rtol=1e-7) and np.isclose(G_PC_KMS2, 4.30091727e-3, rtol=1e-7)
+
+
+def test_synthetic_inputs_are_seeded_and_shaped_like_gizmo():
+    from oc_nbody_b200.synthetic import advance_snapshot, make_plummer_cluster, make_snapshot
+    a, b = make_snapshot(5000), make_snapshot(5000)
+    for sp in ("star", "dark", "gas"):
+        assert np.array_equal(a[sp]["position"], b[sp]["position"]) and np.array_equal(a[sp]["mass"], b[sp]["mass"])
+        assert a[sp].prop("host.distance.principal").shape[1] == 3
+    assert len(a["star"]["mass"]) == 1000 and len(a["gas"]["mass"]) == 1500 and len(a["dark"]["mass"]) == 2500
+    assert "smooth.length" in a["gas"] and a.snapshot["index"] == 577
+    assert np.max(np.linalg.norm(a["dark"]["position"], axis=1)) <= 50.0
+    c = advance_snapshot(a, 23.0)
+    assert np.allclose(np.hypot(*c["star"]["position"][:, :2].T), np.hypot(*a["star"]["position"][:, :2].T))
+    assert np.isclose(c.snapshot["time"] - a.snapshot["time"], 0.023)
+    pos, vel, m = make_plummer_cluster(2000)
+    assert pos.shape == (3, 2000) and np.allclose(pos.mean(axis=1), 0, atol=1e-12)
+    r = np.sqrt((pos ** 2).sum(0))
+    assert 0.6 < np.median(r) / 0.8 < 1.7  # half-mass radius of a Plummer sphere ~ 1.3 a
+
+
+def _field(opts=None, nsnap=3):
+    from oc_nbody_b200.gizmo_field import gizmo_field
+    from oc_nbody_b200.synthetic import advance_snapshot, make_snapshot
+    snaps = [make_snapshot(2000)]
+    for _ in range(nsnap - 1):
+        snaps.append(advance_snapshot(snaps[-1], 23.0))
+    return gizmo_field(opts or {}, snaps, chosen_id=7, build=False), snaps
+
+
+def test_source_assembly_follows_the_reference_rules():
+    """gizmo_interface.py:515-558: star(-chosen)+dark+gas order, softening rules, the Q4 fix."""
+    f, snaps = _field()
+    r, m, h = f._source_arrays_(snaps[0])
+    ns, nd, ng = 400 - 1, 1000, 600
+    assert r.shape == (ns + nd + ng, 3) and m.shape == h.shape == (ns + nd + ng,)
+    assert r.dtype == m.dtype == h.dtype == np.float64
+    assert np.array_equal(r[ns], snaps[0]["dark"]["position"][0])
+    assert np.allclose(h[:ns], 11.2e-3) and np.allclose(h[ns:ns + nd], 112e-3)
+    assert np.allclose(h[ns + nd:], 2.8e-3 * snaps[0]["gas"]["smooth.length"])
+    assert 7 not in snaps[0]["star"]["id"][np.where(snaps[0]["star"]["id"] != 7)[0]]
+    f2, _ = _field(dict(star_char_mass=7100.0, dark_char_mass=35000.0, softening_kernel="plummer"))
+    r2, m2, h2 = f2._source_arrays_(snaps[0])
+    assert h2.shape == m2.shape  # Q4: the reference's un-indexed branch is one entry too long
+    assert np.allclose(h2[:ns], np.cbrt(m2[:ns] / 7100.0) / 1000.0 / 2.8)
+
+
+def test_evolve_model_brackets_and_follows_the_grid():
+    from oc_nbody_b200.units import units
+    f, _ = _field()
+    assert np.allclose(f.time_in_Myr, [0.0, 23.0, 46.0])
+    f.evolve_model(34.5 | units.Myr)
+    assert f._bracket[:2] == (1, 2) and np.isclose(f._bracket[2], 0.5)
+    f.evolve_model(1e3 | units.Myr)
+    assert f._bracket == (1, 2, 1.0)
+    f.evolve_model(11.5)  # bare float = Myr
+    assert f._bracket[:2] == (0, 1) and np.isclose(f._bracket[2], 0.5)
+    with pytest.raises(ValueError):
+        _field(dict(softening_kernel="cubic"))
+    with pytest.raises(NotImplementedError):
+        _field(dict(fine_grid=True))
+
+
+def test_bridge_orders_kicks_and_drifts_like_amuse():
+    """K(dt/2) D(dt) K(dt/2) with the field's time advanced inside the drift; first call at t = 0 is a no-op
+    (oc_nbody.py:55-56)."""
+    from oc_nbody_b200.bridge import Bridge
+    from oc_nbody_b200.units import units
+    log = []
+
+    class Cluster(object):
+        class P(object):
+            x = y = z = np.zeros(3) | units.kpc
+        particles = P()
+
+        def kick_velocities(self, ax, ay, az, dt):
+            log.append(("kick", round(dt, 6), float(ax.value_in(units.kms / units.Myr)[0])))
+
+        def evolve_model(self, t):
+            log.append(("drift-cluster", round(t.value_in(units.Myr), 6)))
+
+    class Field(object):
+        t = 0.0
+
+        def get_gravity_at_point(self, eps, x, y, z):
+            a = np.full(3, self.t) | units.kms / units.Myr
+            return a, a, a
+
+        def evolve_model(self, t):
+            self.t = t.value_in(units.Myr)
+            log.append(("drift-field", round(self.t, 6)))
+
+    c, f = Cluster(), Field()
+    b = Bridge(timestep=0.1 | units.Myr, use_threading=False)
+    b.add_system(c, (f,))
+    b.add_system(f)
+    b.evolve_model(0.0 | units.Myr, timestep=0.1 | units.Myr)
+    assert log == []
+    b.evolve_model(0.1 | units.Myr, timestep=0.1 | units.Myr)
+    assert log == [("kick", 0.05, 0.0), ("drift-cluster", 0.1), ("drift-field", 0.1), ("kick", 0.05, 0.1)]
+    with pytest.raises(NotImplementedError):
+        Bridge(use_threading=True)
+
+
+def test_shard_bounds():
+    from oc_nbody_b200.distributed import shard_bounds, shard_range
+    b = shard_bounds(10, 4)
+    assert list(b) == [0, 3, 6, 8, 10]
+    assert shard_range(10_000_000, 7, 8) == (8750000, 10000000)
+    assert list(shard_bounds(3, 5)) == [0, 1, 2, 3, 3, 3]

@@ -95,18 +95,19 @@ def test_field_direct_edge_cases(ctx):
         assert rel_err_scalar(pot, pref) <= TOL
 
 
-@pytest.mark.parametrize("tpt,scalar", [(1, 0), (2, 0), (1, 1), (2, 1)])
-def test_field_direct_variants(ctx, tpt, scalar):
-    """Every compiled variant of the streaming kernel (targets/thread, packed vs scalar FP32)."""
+@pytest.mark.parametrize("variant", list(range(15)))
+def test_field_direct_variants(ctx, variant):
+    """Every compiled tuning variant of the streaming kernel (targets/thread, packed vs scalar FP32,
+    dedicated vs in-line TMA producer, occupancy bound, unroll)."""
     rng = np.random.default_rng(21)
     src, soft = random_sources(rng, 11000, box=2.0)
     tgt = grid_targets(11)
     ref, pref = oracle.field_direct(src, soft, tgt, oracle.KERNEL_PLUMMER, G, want_pot=True)
-    ctx.lib.ocg_debug_set_variant(tpt, scalar)
+    assert ctx.lib.ocg_debug_set_variant(variant) == 15
     try:
         acc, pot = run_k1(ctx, src, soft, tgt, oracle.KERNEL_PLUMMER, want_pot=True)
     finally:
-        ctx.lib.ocg_debug_set_variant(0, 0)
+        ctx.lib.ocg_debug_set_variant(-1)
     assert rel_err(acc, ref) <= TOL
     assert rel_err_scalar(pot, pref) <= TOL
 

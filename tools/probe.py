@@ -35,21 +35,22 @@ def main():
     inter = float(n_src) * tgt.shape[0]
     ctx.set_kernel_timing(True)
     res = []
-    for kernel in (0, 1):
-        for scalar in (0, 1):
-            for tpt in (1, 2):
-                for want_pot in (False, True):
-                    ctx.lib.ocg_debug_set_variant(tpt, scalar)
-                    best = 1e30
-                    for rep in range(3):
-                        ctx.field_direct(d_src, d_soft, d_tgt, kernel, 1.0, acc, pot if want_pot else None)
-                        torch.cuda.synchronize()
-                        best = min(best, ctx.last_direct_kernel_ms())
-                    r = dict(kernel=kernel, scalar=scalar, tpt=tpt, pot=want_pot, ms=best, ginter_s=inter / best / 1e6,
-                             tflops20=20 * inter / best / 1e9)
-                    res.append(r)
-                    print(json.dumps(r), flush=True)
-    ctx.lib.ocg_debug_set_variant(0, 0)
+    nvar = ctx.lib.ocg_debug_set_variant(-1)
+    for kernel, want_pot in ((0, False), (0, True), (1, False)):
+        for v in range(nvar):
+            if (want_pot or kernel == 1) and v > 1:
+                continue
+            ctx.lib.ocg_debug_set_variant(v)
+            best = 1e30
+            for rep in range(3):
+                ctx.field_direct(d_src, d_soft, d_tgt, kernel, 1.0, acc, pot if want_pot else None)
+                torch.cuda.synchronize()
+                best = min(best, ctx.last_direct_kernel_ms())
+            r = dict(variant=v, name=ctx.lib.ocg_debug_variant_name(v).decode(), kernel=kernel, pot=want_pot, ms=best,
+                     ginter_s=inter / best / 1e6, pct_peak=100 * 20 * inter / best / 1e9 / out["nominal_tflops"])
+            res.append(r)
+            print(json.dumps(r), flush=True)
+    ctx.lib.ocg_debug_set_variant(-1)
     out["variants"] = res
     os.makedirs("gpurun_out", exist_ok=True)
     with open("gpurun_out/probe.json", "w") as f:

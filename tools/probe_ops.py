@@ -1,0 +1,7 @@
+import sys, os, json
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from oc_nbody_b200 import default_context
+ctx = default_context(0)
+names = ["FFMA (TFLOP/s)", "FFMA2 (TFLOP/s)", "MUFU.RSQ (G/s)", "FADD2 (TFLOP/s, 2 flop/lane-instr)", "FMUL2", "FADD2 broadcast operand", "FFMA2 broadcast multiplier (TFLOP/s, 4 flop)", "inner-loop mix TPT=2 registers only (TFLOP/s at 20 flop)", "inner-loop mix TPT=1 registers only"]
+out = {n: ctx.probe_throughput(i) for i, n in enumerate(names)}
+print(json.dumps(out, indent=1))
