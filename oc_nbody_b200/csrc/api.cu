@@ -423,9 +423,9 @@ __global__ void __launch_bounds__(256, 2) probe_mix_kernel(float* out, int iters
 #pragma unroll
         for (int t = 0; t < TPT; ++t) {
           u64 dx, dy, dz, r2, r6, y3, sc;
-          asm("add.rn.ftz.f32x2 %0, %1, %2;" : "=l"(dx) : "l"(xs[q]), "l"(ntx[t]));
-          asm("add.rn.ftz.f32x2 %0, %1, %2;" : "=l"(dy) : "l"(ys[q]), "l"(nty[t]));
-          asm("add.rn.ftz.f32x2 %0, %1, %2;" : "=l"(dz) : "l"(zs[q]), "l"(ntz[t]));
+          asm volatile("add.rn.ftz.f32x2 %0, %1, %2;" : "=l"(dx) : "l"(xs[q]), "l"(ntx[t]));
+          asm volatile("add.rn.ftz.f32x2 %0, %1, %2;" : "=l"(dy) : "l"(ys[q]), "l"(nty[t]));
+          asm volatile("add.rn.ftz.f32x2 %0, %1, %2;" : "=l"(dz) : "l"(zs[q]), "l"(ntz[t]));
           asm("fma.rn.ftz.f32x2 %0, %1, %1, %2;" : "=l"(r2) : "l"(dx), "l"(es[q]));
           asm("fma.rn.ftz.f32x2 %0, %1, %1, %2;" : "=l"(r2) : "l"(dy), "l"(r2));
           asm("fma.rn.ftz.f32x2 %0, %1, %1, %2;" : "=l"(r2) : "l"(dz), "l"(r2));
@@ -452,6 +452,52 @@ __global__ void __launch_bounds__(256, 2) probe_mix_kernel(float* out, int iters
   if (s == 0x123456789ull) out[0] = (float)s;
 }
 
+// FFMA2 stream with other result-producing instructions mixed in, to find what else competes with the FMA
+// pipe (register-file write port? MIO?).  MODE 0: pure FFMA2; 1: + 5 broadcast LDS.128 per 48 FFMA2;
+// 2: + 10 LDS.128 per 48; 3: + 8 MUFU.RSQ per 48; 4: + 10 LDS.128 + 8 MUFU per 48 (the kernel's mix)
+template <int MODE>
+__global__ void __launch_bounds__(256, 2) probe_contend_kernel(float* out, int iters) {
+  typedef unsigned long long u64;
+  __shared__ float4 sh[64];
+  if (threadIdx.x < 64) sh[threadIdx.x] = make_float4(1.f + threadIdx.x, 2.f, 3.f, 4.f);
+  __syncthreads();
+  u64 a[16], b, c;
+  float bf = 1.0000001f + threadIdx.x * 1e-9f, cf = 1e-9f;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(b) : "f"(bf), "f"(bf * 1.0000001f));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(c) : "f"(cf), "f"(cf * 2.f));
+#pragma unroll
+  for (int k = 0; k < 16; ++k) asm("mov.b64 %0, {%1, %2};" : "=l"(a[k]) : "f"(threadIdx.x * 1e-6f + k), "f"(0.5f + k));
+  float mu[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) mu[k] = 1.0f + threadIdx.x * 1e-3f + k;
+  float4 acc4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  const int nl = MODE == 1 ? 5 : ((MODE == 2 || MODE == 4) ? 10 : 0);
+  const int nm = (MODE == 3 || MODE == 4) ? 8 : 0;
+  for (int i = 0; i < iters; ++i) {
+    float4 ld[10];
+#pragma unroll
+    for (int l = 0; l < nl; ++l) {
+      const float4* pp = &sh[(i + l) & 63];
+      asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(ld[l].x), "=f"(ld[l].y), "=f"(ld[l].z), "=f"(ld[l].w) : "r"((unsigned)__cvta_generic_to_shared(pp)));
+    }
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int k = 0; k < 16; ++k) asm volatile("fma.rn.ftz.f32x2 %0, %0, %1, %2;" : "+l"(a[k]) : "l"(b), "l"(c));
+#pragma unroll
+    for (int m = 0; m < nm; ++m) asm volatile("rsqrt.approx.ftz.f32 %0, %0;" : "+f"(mu[m]));
+#pragma unroll
+    for (int l = 0; l < nl; ++l) acc4.x += ld[l].x * 0.f;  // keep the loads alive at negligible cost
+  }
+  u64 s = 0;
+#pragma unroll
+  for (int k = 0; k < 16; ++k) s ^= a[k];
+  float t = acc4.x;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) t += mu[k];
+  if (s == 0x123456789ull || t == 123.456f) out[0] = (float)s + t;
+}
+
 extern "C" double ocg_probe_throughput(ocg_ctx* ctx, int which) {
   if (!ctx) return -1.0;
   OcgDeviceGuard g(ctx->device);
@@ -473,7 +519,12 @@ extern "C" double ocg_probe_throughput(ocg_ctx* ctx, int which) {
     else if (which == 5) probe_packed_kernel<2><<<grid, block>>>(d_out, iters);
     else if (which == 6) probe_packed_kernel<3><<<grid, block>>>(d_out, iters);
     else if (which == 7) probe_mix_kernel<2><<<ctx->sm_count * 2, block>>>(d_out, iters / 4);
-    else probe_mix_kernel<1><<<ctx->sm_count * 2, block>>>(d_out, iters / 4);
+    else if (which == 8) probe_mix_kernel<1><<<ctx->sm_count * 2, block>>>(d_out, iters / 4);
+    else if (which == 10) probe_contend_kernel<0><<<ctx->sm_count * 2, block>>>(d_out, iters);
+    else if (which == 11) probe_contend_kernel<1><<<ctx->sm_count * 2, block>>>(d_out, iters);
+    else if (which == 12) probe_contend_kernel<2><<<ctx->sm_count * 2, block>>>(d_out, iters);
+    else if (which == 13) probe_contend_kernel<3><<<ctx->sm_count * 2, block>>>(d_out, iters);
+    else probe_contend_kernel<4><<<ctx->sm_count * 2, block>>>(d_out, iters);
     cudaEventRecord(e1, 0);
     if (cudaEventSynchronize(e1) != cudaSuccess) {
       ocg_fail(ctx, OCG_ERR_CUDA, "probe kernel failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -488,7 +539,10 @@ extern "C" double ocg_probe_throughput(ocg_ctx* ctx, int which) {
     if (which == 0) rate = ops * 2.0 / (ms * 1e-3) / 1e12;        // TFLOP/s
     else if (which == 1 || which == 6) rate = ops * 4.0 / (ms * 1e-3) / 1e12;  // TFLOP/s (2 FMAs per lane-instr)
     else if (which == 2) rate = ops / (ms * 1e-3) / 1e9;                       // G rsqrt/s
-    else if (which >= 7) {
+    else if (which >= 10) {
+      // FFMA2 TFLOP/s only (48 FFMA2 per iteration, 4 flop per lane-instruction)
+      rate = (double)ctx->sm_count * 2 * block * (double)iters * 48.0 * 4.0 / (ms * 1e-3) / 1e12;
+    } else if (which >= 7) {
       // interactions/s at 20 flop: per iteration 2 reps x 2 pairs x TPT targets x 2 sources per lane
       const int tpt = which == 7 ? 2 : 1;
       double inter = (double)ctx->sm_count * 2 * block * (double)(iters / 4) * (2 * 2 * tpt * 2);

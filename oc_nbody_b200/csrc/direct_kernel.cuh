@@ -68,7 +68,7 @@ __device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gme
 }
 
 // ---------------------------------------------------------------------------- work items ----
-template <int TPT>
+template <int TPT, int NTHR = OCG_CONSUMER_THREADS>
 __device__ __forceinline__ void decode_item(const DirectParams& p, int item, long long& tgt_begin, int& tgt_count,
                                             long long& tile_begin, int& tile_count, long long& slot) {
   if (p.items) {
@@ -79,7 +79,7 @@ __device__ __forceinline__ void decode_item(const DirectParams& p, int item, lon
     tile_count = w.tile_count;
     slot = w.out_slot;
   } else {
-    const int CT = OCG_CONSUMER_THREADS * TPT;
+    const int CT = NTHR * TPT;
     int chunk = item / p.n_ttiles;
     int tt = item - chunk * p.n_ttiles;
     tgt_begin = (long long)tt * CT;
@@ -103,7 +103,9 @@ __device__ __forceinline__ void decode_item(const DirectParams& p, int item, lon
 //   phi += sc * r2  (= m/r)              1 FFMA2      (POT only)
 // Coordinates are pre-scaled by a power of two so that r6 stays inside the FP32 range; GUARD keeps
 // the classic rsqrt(r2)^3 form (no range assumption when eps2 == 0) and skips r2 + e2 == 0 pairs.
-template <int TPT, bool POT, bool GUARD, int UNR>
+// PIPE: the five LDS.128 of source group j+1 are issued before the arithmetic of group j (register double
+// buffering across loop iterations); without it every iteration starts by waiting for its own loads.
+template <int TPT, bool POT, bool GUARD, int UNR, bool PIPE>
 __device__ __forceinline__ void tile_packed(const float* __restrict__ stage, const float (&tx)[TPT],
                                             const float (&ty)[TPT], const float (&tz)[TPT],
                                             double (&dacc)[TPT][POT ? 4 : 3]) {
@@ -119,9 +121,18 @@ __device__ __forceinline__ void tile_packed(const float* __restrict__ stage, con
     ntx[t] = f2_pack(-tx[t], -tx[t]), nty[t] = f2_pack(-ty[t], -ty[t]), ntz[t] = f2_pack(-tz[t], -tz[t]);
     ax[t] = ay[t] = az[t] = ap[t] = 0ull;
   }
+  float4 Xn, Yn, Zn, Mn, En;
+  if (PIPE) Xn = sx[0], Yn = sy[0], Zn = sz[0], Mn = sm[0], En = se[0];
 #pragma unroll UNR
   for (int j = 0; j < OCG_TS / 4; ++j) {
-    const float4 X = sx[j], Y = sy[j], Z = sz[j], M = sm[j], E = se[j];
+    float4 X, Y, Z, M, E;
+    if (PIPE) {
+      X = Xn, Y = Yn, Z = Zn, M = Mn, E = En;
+      const int jn = j + 1 < OCG_TS / 4 ? j + 1 : j;  // last iteration re-reads its own group (harmless)
+      Xn = sx[jn], Yn = sy[jn], Zn = sz[jn], Mn = sm[jn], En = se[jn];
+    } else {
+      X = sx[j], Y = sy[j], Z = sz[j], M = sm[j], E = se[j];
+    }
     const u64 xs[2] = {f2_pack(X.x, X.y), f2_pack(X.z, X.w)};
     const u64 ys[2] = {f2_pack(Y.x, Y.y), f2_pack(Y.z, Y.w)};
     const u64 zs[2] = {f2_pack(Z.x, Z.y), f2_pack(Z.z, Z.w)};
@@ -240,7 +251,7 @@ __device__ __forceinline__ void tile_scalar(const float* __restrict__ stage, con
 // DED    : a dedicated 9th warp issues the TMA copies (false: lane 0 of warp 0 does; 256-thread CTA)
 // MINB   : CTAs per SM the register allocation is bounded for
 // UNR    : unroll of the 4-source group loop
-template <int TPT, bool POT, bool GUARD, bool PACKED, bool DED, int MINB, int UNR>
+template <int TPT, bool POT, bool GUARD, bool PACKED, bool DED, int MINB, int UNR, bool PIPE = false>
 __global__ void __launch_bounds__(OCG_CONSUMER_THREADS + (DED ? 32 : 0), MINB) direct_sum_kernel(const DirectParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float* stage_base = reinterpret_cast<float*>(smem_raw);
@@ -315,7 +326,7 @@ __global__ void __launch_bounds__(OCG_CONSUMER_THREADS + (DED ? 32 : 0), MINB) d
       const uint32_t s = it % OCG_NSTAGE, ph = (it / OCG_NSTAGE) & 1u;
       mbar_wait(&full_bar[s], ph);
       const float* stage = stage_base + s * OCG_TILE_FLOATS;
-      if (PACKED) tile_packed<TPT, POT, GUARD, UNR>(stage, tx, ty, tz, dacc);
+      if (PACKED) tile_packed<TPT, POT, GUARD, UNR, PIPE>(stage, tx, ty, tz, dacc);
       else tile_scalar<TPT, POT, GUARD, UNR>(stage, tx, ty, tz, dacc);
       // this warp is done reading stage s: hand it back to the producer
       __syncwarp();
@@ -329,6 +340,181 @@ __global__ void __launch_bounds__(OCG_CONSUMER_THREADS + (DED ? 32 : 0), MINB) d
         const long long gi = tgt_begin + local;
 #pragma unroll
         for (int c = 0; c < NC; ++c) p.partial[(slot * NC + c) * p.out_stride + gi] = dacc[t][c];
+      }
+    }
+  }
+}
+
+// =====================================================================================================
+// Target-paired form.  Measured on B200 (tools/probe_ops.py): every register the LDS.128 source loads write
+// back costs the FMA pipe ~0.75 cycle (48 FFMA2 + 10 LDS.128 run 24% slower than 48 FFMA2 alone), i.e. operand
+// feeding, not arithmetic, is what keeps the source-paired loop at ~80% FMA-pipe activity.  Here the two lanes
+// of a packed instruction are two TARGETS and the source is the broadcast operand (FADD2/FFMA2/FMUL2 accept
+// a scalar .F32 operand), so one 4-source group (5 LDS.128 = 20 registers) feeds 4*NP pair-units instead of
+// 2*TPT, and a target needs 3 accumulator registers instead of 6.
+//   NP      : target pairs per thread (targets per thread = 2*NP; CTA tile = 512*NP targets)
+//   SMEMACC : FP64 accumulators live in shared memory (touched once per tile) instead of registers
+// DBG (timing experiments only, results are wrong): 1 = MUFU.RSQ replaced by an ALU-pipe bit trick,
+// 2 = source registers loaded once per tile instead of per group, 3 = both.
+template <int NP, bool POT, int UNR, int DBG>
+__device__ __forceinline__ void tile_tpair(const float* __restrict__ stage, const u64 (&ntx)[NP], const u64 (&nty)[NP],
+                                           const u64 (&ntz)[NP], u64 (&ax)[NP], u64 (&ay)[NP], u64 (&az)[NP],
+                                           u64 (&ap)[NP]) {
+  const float4* sx = reinterpret_cast<const float4*>(stage);
+  const float4* sy = sx + OCG_TS / 4;
+  const float4* sz = sy + OCG_TS / 4;
+  const float4* sm = sz + OCG_TS / 4;
+  const float4* se = sm + OCG_TS / 4;
+  float4 X0 = sx[0], Y0 = sy[0], Z0 = sz[0], M0 = sm[0], E0 = se[0];
+#pragma unroll UNR
+  for (int j = 0; j < OCG_TS / 4; ++j) {
+    float4 X, Y, Z, M, E;
+    if (DBG & 2) {
+      X = X0, Y = Y0, Z = Z0, M = M0, E = E0;
+      X0.x += 1e-7f;  // keep the loop body from being hoisted
+    } else {
+      X = sx[j], Y = sy[j], Z = sz[j], M = sm[j], E = se[j];
+    }
+    const float xs[4] = {X.x, X.y, X.z, X.w}, ys[4] = {Y.x, Y.y, Y.z, Y.w}, zs[4] = {Z.x, Z.y, Z.z, Z.w};
+    const float ms[4] = {M.x, M.y, M.z, M.w}, es[4] = {E.x, E.y, E.z, E.w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      // duplicated source scalars: ptxas folds them into broadcast (.F32) operands
+      const u64 xb = f2_pack(xs[q], xs[q]), yb = f2_pack(ys[q], ys[q]), zb = f2_pack(zs[q], zs[q]);
+      const u64 mb = f2_pack(ms[q], ms[q]), eb = f2_pack(es[q], es[q]);
+#pragma unroll
+      for (int p = 0; p < NP; ++p) {
+        const u64 dx = f2_add(ntx[p], xb);
+        const u64 dy = f2_add(nty[p], yb);
+        const u64 dz = f2_add(ntz[p], zb);
+        u64 r2 = f2_fma(dx, dx, eb);
+        r2 = f2_fma(dy, dy, r2);
+        r2 = f2_fma(dz, dz, r2);
+        const u64 r6 = f2_mul(f2_mul(r2, r2), r2);
+        float r6a, r6b;
+        f2_unpack(r6, r6a, r6b);
+        u64 y3;
+        if (DBG & 1) {
+          y3 = f2_pack(__int_as_float(0x5f3759df - (__float_as_int(r6a) >> 1)),
+                       __int_as_float(0x5f3759df - (__float_as_int(r6b) >> 1)));
+        } else {
+          y3 = f2_pack(rsqrt_approx(r6a), rsqrt_approx(r6b));
+        }
+        const u64 sc = f2_mul(y3, mb);
+        if (POT) ap[p] = f2_fma(sc, r2, ap[p]);
+        ax[p] = f2_fma(dx, sc, ax[p]);
+        ay[p] = f2_fma(dy, sc, ay[p]);
+        az[p] = f2_fma(dz, sc, az[p]);
+      }
+    }
+  }
+}
+
+//   NW      : consumer warps per CTA (CTA = 32*NW threads; CTA tile = 64*NW*NP targets)
+template <int NP, bool POT, bool SMEMACC, int MINB, int UNR, int NW = OCG_CONSUMER_WARPS, int DBG = 0>
+__global__ void __launch_bounds__(32 * NW, MINB) direct_sum_tp_kernel(const DirectParams p) {
+  constexpr int NTHR = 32 * NW;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float* stage_base = reinterpret_cast<float*>(smem_raw);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_raw + OCG_NSTAGE * OCG_TILE_BYTES);
+  uint64_t* empty_bar = full_bar + OCG_NSTAGE;
+  double* sacc = reinterpret_cast<double*>(smem_raw + OCG_NSTAGE * OCG_TILE_BYTES + 128);  // [NC][2*NP][256]
+  constexpr int NC = POT ? 4 : 3;
+  constexpr int T = 2 * NP;
+  const int tid = threadIdx.x;
+  const int lane = tid & 31;
+
+  if (tid == 0) {
+    for (int s = 0; s < OCG_NSTAGE; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], NW);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  uint32_t it = 0;
+  auto issue_tile = [&](uint32_t n, const float* src) {
+    const uint32_t s = n % OCG_NSTAGE, ph = (n / OCG_NSTAGE) & 1u;
+    mbar_wait(&empty_bar[s], ph ^ 1u);
+    mbar_expect_tx(&full_bar[s], OCG_TILE_BYTES);
+    tma_bulk_g2s(stage_base + s * OCG_TILE_FLOATS, src, OCG_TILE_BYTES, &full_bar[s]);
+  };
+
+  const float scale = p.scale_ptr ? *p.scale_ptr : p.scale_val;
+  for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+    long long tgt_begin, tile_begin, slot;
+    int tgt_count, tile_count;
+    decode_item<T, NTHR>(p, item, tgt_begin, tgt_count, tile_begin, tile_count, slot);
+    const float* src = p.tiles + tile_begin * (long long)OCG_TILE_FLOATS;
+    if (tid == 0) {
+      const int pre = tile_count < OCG_NSTAGE - 1 ? tile_count : OCG_NSTAGE - 1;
+      for (int k = 0; k < pre; ++k) issue_tile(it + k, src + (long long)k * OCG_TILE_FLOATS);
+    }
+
+    u64 ntx[NP], nty[NP], ntz[NP];
+    double dacc[SMEMACC ? 1 : T][NC];
+#pragma unroll
+    for (int pp = 0; pp < NP; ++pp) {
+      float c[2][3];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int local = (2 * pp + h) * NTHR + tid;
+        const long long gi = tgt_begin + (local < tgt_count ? local : tgt_count - 1);
+        const float4 Tg = __ldg(&p.tgt[gi]);
+        c[h][0] = -Tg.x * scale, c[h][1] = -Tg.y * scale, c[h][2] = -Tg.z * scale;
+      }
+      ntx[pp] = f2_pack(c[0][0], c[1][0]), nty[pp] = f2_pack(c[0][1], c[1][1]), ntz[pp] = f2_pack(c[0][2], c[1][2]);
+    }
+    if (SMEMACC) {
+#pragma unroll
+      for (int i = 0; i < NC * T; ++i) sacc[i * NTHR + tid] = 0.0;
+    } else {
+#pragma unroll
+      for (int t = 0; t < T; ++t)
+#pragma unroll
+        for (int c = 0; c < NC; ++c) dacc[t][c] = 0.0;
+    }
+
+    for (int k = 0; k < tile_count; ++k, ++it) {
+      if (tid == 0 && k + OCG_NSTAGE - 1 < tile_count)
+        issue_tile(it + OCG_NSTAGE - 1, src + (long long)(k + OCG_NSTAGE - 1) * OCG_TILE_FLOATS);
+      const uint32_t s = it % OCG_NSTAGE, ph = (it / OCG_NSTAGE) & 1u;
+      mbar_wait(&full_bar[s], ph);
+      u64 ax[NP], ay[NP], az[NP], ap[NP];
+#pragma unroll
+      for (int pp = 0; pp < NP; ++pp) ax[pp] = ay[pp] = az[pp] = ap[pp] = 0ull;
+      tile_tpair<NP, POT, UNR, DBG>(stage_base + s * OCG_TILE_FLOATS, ntx, nty, ntz, ax, ay, az, ap);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty_bar[s]);
+      // fold this tile's FP32 sums into the FP64 accumulators (lane lo -> target 2p, hi -> target 2p+1)
+#pragma unroll
+      for (int pp = 0; pp < NP; ++pp) {
+        float v[4][2];
+        f2_unpack(ax[pp], v[0][0], v[0][1]);
+        f2_unpack(ay[pp], v[1][0], v[1][1]);
+        f2_unpack(az[pp], v[2][0], v[2][1]);
+        f2_unpack(ap[pp], v[3][0], v[3][1]);
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+          for (int c = 0; c < NC; ++c) {
+            const double add = c < 3 ? (double)v[c][h] : -(double)v[3][h];
+            if (SMEMACC) sacc[(c * T + 2 * pp + h) * NTHR + tid] += add;
+            else dacc[SMEMACC ? 0 : 2 * pp + h][c] += add;
+          }
+      }
+    }
+
+#pragma unroll
+    for (int t = 0; t < T; ++t) {
+      const int local = t * NTHR + tid;
+      if (local < tgt_count) {
+        const long long gi = tgt_begin + local;
+#pragma unroll
+        for (int c = 0; c < NC; ++c)
+          p.partial[(slot * NC + c) * p.out_stride + gi] =
+              SMEMACC ? sacc[(c * T + t) * NTHR + tid] : dacc[SMEMACC ? 0 : t][c];
       }
     }
   }

@@ -393,7 +393,10 @@ struct DirectVariant {
   int tpt, minb;
   bool ded;
   direct_fn fn[2][2];
+  int smem_acc_comps;  // > 0: FP64 accumulators in shared memory, this many doubles per thread and component
+  int nwarps;          // consumer warps per CTA (0 = OCG_CONSUMER_WARPS)
 };
+static inline int variant_threads(const DirectVariant& v) { return 32 * (v.nwarps ? v.nwarps : OCG_CONSUMER_WARPS); }
 #define OCG_FULL(TPT, PACKED, DED, MINB, UNR)                                                            \
   {                                                                                                      \
     {direct_sum_kernel<TPT, false, false, PACKED, DED, MINB, UNR>,                                       \
@@ -404,6 +407,24 @@ struct DirectVariant {
 #define OCG_ONE(TPT, PACKED, DED, MINB, UNR)                                                             \
   {                                                                                                      \
     {direct_sum_kernel<TPT, false, false, PACKED, DED, MINB, UNR>, nullptr}, { nullptr, nullptr }        \
+  }
+#define OCG_ONEP(TPT, DED, MINB, UNR)                                                                    \
+  {                                                                                                      \
+    {direct_sum_kernel<TPT, false, false, true, DED, MINB, UNR, true>, nullptr}, { nullptr, nullptr }    \
+  }
+#define OCG_TP(NP, SMEMACC, MINB, UNR)                                                                   \
+  {                                                                                                      \
+    {direct_sum_tp_kernel<NP, false, SMEMACC, MINB, UNR>, nullptr},                                      \
+    { direct_sum_tp_kernel<NP, true, SMEMACC, MINB, UNR>, nullptr }                                      \
+  }
+#define OCG_TPW(NP, SMEMACC, MINB, UNR, NW)                                                              \
+  {                                                                                                      \
+    {direct_sum_tp_kernel<NP, false, SMEMACC, MINB, UNR, NW>, nullptr},                                  \
+    { direct_sum_tp_kernel<NP, true, SMEMACC, MINB, UNR, NW>, nullptr }                                  \
+  }
+#define OCG_TPD(NP, SMEMACC, MINB, UNR, NW, DBG)                                                         \
+  {                                                                                                      \
+    {direct_sum_tp_kernel<NP, false, SMEMACC, MINB, UNR, NW, DBG>, nullptr}, { nullptr, nullptr }        \
   }
 static const DirectVariant g_variants[] = {
     /* 0 */ {"tpt2 packed ded minb2 unr2", 2, 2, true, OCG_FULL(2, true, true, 2, 2)},
@@ -421,10 +442,39 @@ static const DirectVariant g_variants[] = {
     /* 12 */ {"tpt1 packed inl minb2 unr2", 1, 2, false, OCG_ONE(1, true, false, 2, 2)},
     /* 13 */ {"tpt1 packed inl minb3 unr1", 1, 3, false, OCG_ONE(1, true, false, 3, 1)},
     /* 14 */ {"tpt2 packed ded minb2 unr4", 2, 2, true, OCG_ONE(2, true, true, 2, 4)},
+    /* 15 */ {"tpt2 packed inl minb2 unr2 pipe", 2, 2, false, OCG_ONEP(2, false, 2, 2)},
+    /* 16 */ {"tpt2 packed inl minb2 unr1 pipe", 2, 2, false, OCG_ONEP(2, false, 2, 1)},
+    /* 17 */ {"tpt2 packed ded minb2 unr2 pipe", 2, 2, true, OCG_ONEP(2, true, 2, 2)},
+    /* 18 */ {"tpt1 packed inl minb3 unr2 pipe", 1, 3, false, OCG_ONEP(1, false, 3, 2)},
+    /* 19 */ {"tpt1 packed inl minb2 unr4 pipe", 1, 2, false, OCG_ONEP(1, false, 2, 4)},
+    /* 20 */ {"tpt2 packed inl minb2 unr4 pipe", 2, 2, false, OCG_ONEP(2, false, 2, 4)},
+    /* 21 */ {"tpair np2 (4 tgt/thr) regacc minb2 unr1", 4, 2, false, OCG_TP(2, false, 2, 1), 0},
+    /* 22 */ {"tpair np2 (4 tgt/thr) regacc minb2 unr2", 4, 2, false, OCG_TP(2, false, 2, 2), 0},
+    /* 23 */ {"tpair np2 (4 tgt/thr) smemacc minb2 unr1", 4, 2, false, OCG_TP(2, true, 2, 1), 4},
+    /* 24 */ {"tpair np4 (8 tgt/thr) smemacc minb2 unr1", 8, 2, false, OCG_TP(4, true, 2, 1), 8},
+    /* 25 */ {"tpair np3 (6 tgt/thr) smemacc minb2 unr1", 6, 2, false, OCG_TP(3, true, 2, 1), 6},
+    /* 26 */ {"tpair np4 (8 tgt/thr) smemacc minb1 unr1", 8, 1, false, OCG_TP(4, true, 1, 1), 8},
+    /* 27 */ {"tpair np1 (2 tgt/thr) regacc minb2 unr2", 2, 2, false, OCG_TP(1, false, 2, 2), 0},
+    /* 28 */ {"tpair np2 (4 tgt/thr) regacc minb3 unr1", 4, 3, false, OCG_TP(2, false, 3, 1), 0},
+    /* 29 */ {"tpair np4 smemacc 4w x minb3 (12 w/SM)", 8, 3, false, OCG_TPW(4, true, 3, 1, 4), 8, 4},
+    /* 30 */ {"tpair np3 smemacc 4w x minb3 (12 w/SM)", 6, 3, false, OCG_TPW(3, true, 3, 1, 4), 6, 4},
+    /* 31 */ {"tpair np4 smemacc 12w x minb1 (12 w/SM)", 8, 1, false, OCG_TPW(4, true, 1, 1, 12), 8, 12},
+    /* 32 */ {"tpair np4 smemacc 6w x minb2 (12 w/SM)", 8, 2, false, OCG_TPW(4, true, 2, 1, 6), 8, 6},
+    /* 33 */ {"tpair np2 regacc 4w x minb3 (12 w/SM)", 4, 3, false, OCG_TPW(2, false, 3, 1, 4), 0, 4},
+    /* 34 */ {"tpair np2 regacc 4w x minb3 unr2 (12 w/SM)", 4, 3, false, OCG_TPW(2, false, 3, 2, 4), 0, 4},
+    /* 35 */ {"tpair np4 smemacc 4w x minb2 (8 w/SM)", 8, 2, false, OCG_TPW(4, true, 2, 1, 4), 8, 4},
+    /* 36 */ {"tpair np4 smemacc 10w x minb1 (10 w/SM)", 8, 1, false, OCG_TPW(4, true, 1, 1, 10), 8, 10},
+    /* 37 */ {"DBG np4 12w: no MUFU (timing only)", 8, 1, false, OCG_TPD(4, true, 1, 1, 12, 1), 8, 12},
+    /* 38 */ {"DBG np4 12w: no LDS (timing only)", 8, 1, false, OCG_TPD(4, true, 1, 1, 12, 2), 8, 12},
+    /* 39 */ {"DBG np4 12w: no MUFU, no LDS (timing only)", 8, 1, false, OCG_TPD(4, true, 1, 1, 12, 3), 8, 12},
 };
+#define OCG_N_CORRECT_VARIANTS 37 /* variants >= this are timing experiments with wrong results */
 static const int g_n_variants = (int)(sizeof(g_variants) / sizeof(g_variants[0]));
-#define OCG_DEFAULT_VARIANT_BIG 4   /* many targets: measured best on B200 (tools/probe.py) */
-#define OCG_DEFAULT_VARIANT_SMALL 1 /* few targets: one per thread spreads them over more CTAs */
+// Production choices (tools/probe.py sweep on B200, profiles/r01_variant_sweep.json):
+#define OCG_VARIANT_BIG 31        /* >= 64k targets: target-paired, 8 targets/thread, 12 warps, 71% of FP32 peak */
+#define OCG_VARIANT_MID 27        /* >= 16k targets: target-paired, 2 targets/thread                              */
+#define OCG_VARIANT_MID_GUARD 4   /* source-paired 2 targets/thread (carries the eps2 == 0 guarded form)          */
+#define OCG_VARIANT_SMALL 1       /* few targets: 1 target/thread spreads them over more CTAs (has guard form)    */
 
 static int g_force_variant = -1;  // -1 = heuristic
 static int g_precise_near = 1;    // 0 = no precision radius (criterion (a) only)
@@ -439,30 +489,41 @@ extern "C" int ocg_debug_set_precise_near(int on) {
   return 0;
 }
 
-int ocg_pick_variant(ocg_ctx* ctx, int64_t n_tgt) {
-  if (g_force_variant >= 0) return g_force_variant;
-  // enough targets to give every resident CTA a full tile at 2 targets per thread?
-  long long full = (long long)ctx->sm_count * 2 * OCG_CONSUMER_THREADS * 2;
-  return n_tgt >= full ? OCG_DEFAULT_VARIANT_BIG : OCG_DEFAULT_VARIANT_SMALL;
+int ocg_pick_variant(ocg_ctx* ctx, int64_t n_tgt, bool guard) {
+  (void)ctx;
+  if (g_force_variant >= 0) {
+    // a forced variant without the guarded form falls back to the guarded production kernels
+    if (!guard || g_variants[g_force_variant].fn[0][1]) return g_force_variant;
+  }
+  if (guard) return n_tgt >= 16384 ? OCG_VARIANT_MID_GUARD : OCG_VARIANT_SMALL;
+  if (n_tgt >= 65536) return OCG_VARIANT_BIG;
+  if (n_tgt >= 16384) return OCG_VARIANT_MID;
+  return OCG_VARIANT_SMALL;
 }
 int ocg_variant_tpt(int v) { return g_variants[v].tpt; }
+int ocg_variant_threads(int v) { return variant_threads(g_variants[v]); }
 int ocg_variant_slots(ocg_ctx* ctx, int v) { return ctx->sm_count * g_variants[v].minb; }
 
 // Launch the fast kernel over a prepared parameter block.
 int ocg_launch_direct(ocg_ctx* ctx, DirectParams& p, int variant, bool pot, bool guard, cudaStream_t st) {
   const DirectVariant* v = &g_variants[variant];
   if (!v->fn[pot][guard]) {
-    // sweep-only variant asked for a pot/guard form it does not carry: use the production one of equal TPT
-    v = &g_variants[v->tpt == 2 ? OCG_DEFAULT_VARIANT_BIG : OCG_DEFAULT_VARIANT_SMALL];
+    // sweep-only variant asked for a potential form it does not carry: use a production one of equal tile shape
+    const DirectVariant* w = &g_variants[v->tpt == 1 ? OCG_VARIANT_SMALL : OCG_VARIANT_MID_GUARD];
+    if (w->tpt != v->tpt || variant_threads(*w) != variant_threads(*v) || !w->fn[pot][guard])
+      return ocg_fail(ctx, OCG_ERR_INVALID, "kernel variant %d (%s) has no %s%s form", variant, v->name,
+                      pot ? "potential " : "", guard ? "guarded" : "");
+    v = w;
   }
   direct_fn fn = v->fn[pot][guard];
   size_t smem = direct_smem_bytes();
+  if (v->smem_acc_comps) smem = OCG_NSTAGE * OCG_TILE_BYTES + 128 + (size_t)(pot ? 4 : 3) * v->smem_acc_comps * variant_threads(*v) * sizeof(double);
   OCG_CUDA(ctx, cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int grid = ctx->sm_count * v->minb;
   if (grid > p.n_items) grid = p.n_items;
   if (grid < 1) grid = 1;
   if (ctx->timing) OCG_CUDA(ctx, cudaEventRecord(ctx->ev0, st));
-  fn<<<grid, OCG_CONSUMER_THREADS + (v->ded ? 32 : 0), smem, st>>>(p);
+  fn<<<grid, variant_threads(*v) + (v->ded ? 32 : 0), smem, st>>>(p);
   OCG_CHECK_LAUNCH(ctx, "direct_sum_kernel");
   if (ctx->timing) {
     OCG_CUDA(ctx, cudaEventRecord(ctx->ev1, st));
@@ -488,9 +549,9 @@ int ocg_direct_sum_impl(ocg_ctx* ctx, const float* src_xyzm, const float* src_so
     return OCG_OK;
   }
 
-  const int variant = ocg_pick_variant(ctx, n_tgt);
+  const int variant = ocg_pick_variant(ctx, n_tgt, /*guard=*/false);
   const int tpt = ocg_variant_tpt(variant);
-  const int CT = OCG_CONSUMER_THREADS * tpt;
+  const int CT = ocg_variant_threads(variant) * tpt;
   const long long n_ttiles = (n_tgt + CT - 1) / CT;
   const long long n_tiles_max = (n_src + OCG_TS - 1) / OCG_TS;
   // chunking: aim for >= 64 equal-cost items per resident CTA slot (static striding; tail loss < 1%)

@@ -106,8 +106,9 @@ struct DirectParams {
 };
 
 // ---- entry points implemented in other translation units ------------------------------------
-int ocg_pick_variant(ocg_ctx* ctx, int64_t n_tgt);
+int ocg_pick_variant(ocg_ctx* ctx, int64_t n_tgt, bool guard);
 int ocg_variant_tpt(int variant);
+int ocg_variant_threads(int variant);
 int ocg_variant_slots(ocg_ctx* ctx, int variant);
 int ocg_launch_direct(ocg_ctx* ctx, DirectParams& p, int variant, bool pot, bool guard, cudaStream_t st);
 int ocg_direct_sum_impl(ocg_ctx* ctx, const float* src_xyzm, const float* src_soft, int64_t n_src,

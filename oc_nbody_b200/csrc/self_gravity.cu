@@ -118,9 +118,9 @@ extern "C" int ocg_self_gravity(ocg_ctx* ctx, const double* pos_dev, const doubl
     if (!(scale > 0.f) || !isfinite(scale) || !(e2f * scale * scale > 0.f)) scale = 1.0f;
   }
   const int64_t n_shard = tgt_end - tgt_begin;
-  const int variant = ocg_pick_variant(ctx, n_shard);
+  const int variant = ocg_pick_variant(ctx, n_shard, guard);
   const int tpt = ocg_variant_tpt(variant);
-  const int CT = OCG_CONSUMER_THREADS * tpt;
+  const int CT = ocg_variant_threads(variant) * tpt;
 
   // ---- host-side plan: tile offsets per segment, chunk count, item list ----
   long long* seg_tile = (long long*)malloc(sizeof(long long) * (2 * (size_t)n_seg + 2));
