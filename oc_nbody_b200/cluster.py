@@ -89,8 +89,13 @@ class cluster_code(object):
         self.G = G_KPC_KMS_MYR
         self.model_time = 0.0
         self.key = None
-        self._set_state_(np.asarray(to_value(mass, units.MSun), np.float64), np.asarray(to_value(pos, units.kpc), np.float64),
-                         np.asarray(to_value(vel, units.kms), np.float64))
+        def unwrap(v, unit):
+            # [3, n] array / quantity, or a sequence of three per-axis vectors (AMUSE's particles.x, .y, .z)
+            if isinstance(v, (list, tuple)) and len(v) == 3:
+                return np.stack([np.asarray(to_value(c, unit), np.float64) for c in v])
+            return np.asarray(to_value(v, unit), np.float64)
+
+        self._set_state_(np.asarray(to_value(mass, units.MSun), np.float64), unwrap(pos, units.kpc), unwrap(vel, units.kms))
 
     # ---- state ----
     def _set_state_(self, mass, pos, vel, key=None):

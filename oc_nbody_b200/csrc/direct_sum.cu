@@ -489,15 +489,22 @@ extern "C" int ocg_debug_set_precise_near(int on) {
   return 0;
 }
 
-int ocg_pick_variant(ocg_ctx* ctx, int64_t n_tgt, bool guard) {
+// n_tgt: targets in the call (or shard); seg_len: typical length of one independent target run (= n_tgt for the
+// field build, the cluster size for batched self-gravity) — a tile never spans two runs.
+int ocg_pick_variant(ocg_ctx* ctx, int64_t n_tgt, int64_t seg_len, bool guard) {
   (void)ctx;
   if (g_force_variant >= 0) {
     // a forced variant without the guarded form falls back to the guarded production kernels
     if (!guard || g_variants[g_force_variant].fn[0][1]) return g_force_variant;
   }
-  if (guard) return n_tgt >= 16384 ? OCG_VARIANT_MID_GUARD : OCG_VARIANT_SMALL;
-  if (n_tgt >= 65536) return OCG_VARIANT_BIG;
-  if (n_tgt >= 16384) return OCG_VARIANT_MID;
+  auto waste_ok = [&](int v) {
+    const long long ct = (long long)variant_threads(g_variants[v]) * g_variants[v].tpt;
+    const long long padded = (seg_len + ct - 1) / ct * ct;
+    return padded * 8 <= seg_len * 9;  // <= 12.5% of the tile slots idle
+  };
+  if (guard) return (n_tgt >= 16384 && waste_ok(OCG_VARIANT_MID_GUARD)) ? OCG_VARIANT_MID_GUARD : OCG_VARIANT_SMALL;
+  if (n_tgt >= 65536 && waste_ok(OCG_VARIANT_BIG)) return OCG_VARIANT_BIG;
+  if (n_tgt >= 16384 && waste_ok(OCG_VARIANT_MID)) return OCG_VARIANT_MID;
   return OCG_VARIANT_SMALL;
 }
 int ocg_variant_tpt(int v) { return g_variants[v].tpt; }
@@ -549,7 +556,7 @@ int ocg_direct_sum_impl(ocg_ctx* ctx, const float* src_xyzm, const float* src_so
     return OCG_OK;
   }
 
-  const int variant = ocg_pick_variant(ctx, n_tgt, /*guard=*/false);
+  const int variant = ocg_pick_variant(ctx, n_tgt, n_tgt, /*guard=*/false);
   const int tpt = ocg_variant_tpt(variant);
   const int CT = ocg_variant_threads(variant) * tpt;
   const long long n_ttiles = (n_tgt + CT - 1) / CT;

@@ -2,10 +2,10 @@
 // (gizmo_interface.py:677-717), as trilinear-in-space + linear-in-time interpolation on the
 // regular lattice of grid_cartesian.py:16-32,59-69.
 //
-// HBM-bound gather: one float4 record (ax, ay, az, phi) per node per snapshot, z-adjacent corners
-// share a 32-byte sector; all arithmetic in FP64 with separately rounded mul/add (no FMA
-// contraction) in a fixed order so the oracle (oracle/ocg_oracle.c: oracle_grid_interp) reproduces
-// the bits.
+// Memory-bound gather: one float4 record (ax, ay, az, phi) per node per snapshot, z-adjacent corners
+// share a 32-byte sector.  Every operation is individually rounded (no FMA contraction) in a fixed
+// order — FP32 for the time blend of the FP32 records, FP64 for cell selection, weights and the
+// trilinear blend — so the oracle (oracle/ocg_oracle.c: oracle_grid_interp) reproduces the bits.
 #include "ocg_internal.cuh"
 
 __global__ void pack_planes_kernel(const double* __restrict__ acc, const double* __restrict__ pot,
@@ -19,16 +19,24 @@ __device__ __forceinline__ double lerp_rn(double a, double wa, double b, double 
   return __dadd_rn(__dmul_rn(a, wa), __dmul_rn(b, wb));
 }
 
-__global__ void time_blend_kernel(const float4* __restrict__ ra, const float4* __restrict__ rb, double wb,
+// v = a*(1-w) + b*w on the FP32 records, every op rounded to FP32 — the same blend K3 fuses.
+__global__ void time_blend_kernel(const float4* __restrict__ ra, const float4* __restrict__ rb, float wb,
                                   long long n, double* __restrict__ acc, double* __restrict__ pot) {
   long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const double wa = __dsub_rn(1.0, wb);
-  float4 a = ra[i], b = rb ? rb[i] : a;
-  acc[i] = lerp_rn((double)a.x, wa, (double)b.x, wb);
-  acc[n + i] = lerp_rn((double)a.y, wa, (double)b.y, wb);
-  acc[2 * n + i] = lerp_rn((double)a.z, wa, (double)b.z, wb);
-  if (pot) pot[i] = lerp_rn((double)a.w, wa, (double)b.w, wb);
+  const float wa = __fsub_rn(1.0f, wb);
+  float4 a = ra[i];
+  if (rb) {
+    const float4 b = rb[i];
+    a.x = __fadd_rn(__fmul_rn(a.x, wa), __fmul_rn(b.x, wb));
+    a.y = __fadd_rn(__fmul_rn(a.y, wa), __fmul_rn(b.y, wb));
+    a.z = __fadd_rn(__fmul_rn(a.z, wa), __fmul_rn(b.z, wb));
+    a.w = __fadd_rn(__fmul_rn(a.w, wa), __fmul_rn(b.w, wb));
+  }
+  acc[i] = (double)a.x;
+  acc[n + i] = (double)a.y;
+  acc[2 * n + i] = (double)a.z;
+  if (pot) pot[i] = (double)a.w;
 }
 
 static inline int nblocks(long long n, int b) { return (int)((n + b - 1) / b); }
@@ -52,7 +60,7 @@ extern "C" int ocg_grid_time_blend(ocg_ctx* ctx, const float* rec_a_dev, const f
   if (n_node == 0) return OCG_OK;
   OcgDeviceGuard g(ctx->device);
   time_blend_kernel<<<nblocks(n_node, 256), 256, 0, (cudaStream_t)stream>>>(
-      reinterpret_cast<const float4*>(rec_a_dev), reinterpret_cast<const float4*>(rec_b_dev), w_b, n_node,
+      reinterpret_cast<const float4*>(rec_a_dev), reinterpret_cast<const float4*>(rec_b_dev), (float)w_b, n_node,
       acc_out_dev, pot_out_dev);
   OCG_CHECK_LAUNCH(ctx, "time_blend_kernel");
   return OCG_OK;
@@ -66,7 +74,7 @@ struct InterpParams {
   const double* origin;
   const float4* rec_a;
   const float4* rec_b;
-  double wb;
+  float wb;  // weight of snapshot b, rounded to FP32 (the time blend is FP32 arithmetic)
   const double* sx;
   const double* sy;
   const double* sz;
@@ -75,100 +83,127 @@ struct InterpParams {
   double* acc;
   double* pot;
   int* cell;
-  int nodes_in_smem;
 };
 
 // Cell along one axis: i = searchsorted(node + o, x, side='right') - 1, clamped to [0, n-2].
 // The arithmetic estimate only seeds the search; the result is decided by comparisons against
 // the (node[i] + o) values, which the oracle forms with the same single FP64 addition.
-__device__ __forceinline__ int find_cell(const double* __restrict__ node, int n, double o, double x,
-                                         double& x0, double& x1) {
+__device__ __forceinline__ int find_cell(const double* __restrict__ node, int n, double o, double x) {
   const double lo = __dadd_rn(node[0], o);
   const double hi = __dadd_rn(node[n - 1], o);
   int i = 0;
   if (x == x && n > 2) {  // not NaN
-    double f = (x - lo) / (hi - lo) * (double)(n - 1);
+    // seed only (any rounding will do): reciprocal via FP32 keeps the FP64 divide off this path
+    double f = (x - lo) * (double)((float)(n - 1) / (float)(hi - lo));
     if (f >= (double)(n - 2)) i = n - 2;
     else if (f > 0.0) i = (int)f;
   }
   while (i > 0 && x < __dadd_rn(node[i], o)) --i;
   while (i < n - 2 && x >= __dadd_rn(node[i + 1], o)) ++i;
-  x0 = __dadd_rn(node[i], o);
-  x1 = __dadd_rn(node[i + 1], o);
   return i;
 }
 
-__global__ void __launch_bounds__(256) grid_interp_kernel(const InterpParams p) {
-  extern __shared__ double s_nodes[];
+__device__ __forceinline__ float lerp_rn_f(float a, float wa, float b, float wb) {
+  return __fadd_rn(__fmul_rn(a, wa), __fmul_rn(b, wb));
+}
+
+// One thread per star.  Arithmetic contract (identical in oracle/ocg_oracle.c: oracle_grid_interp):
+//   cell      : FP64 comparisons against node[i] + origin (bit-exact searchsorted)
+//   weight    : t = (x - (node[i] + origin)) * inv[i],  inv[i] = 1 / (node[i+1] - node[i])      FP64
+//   time blend: v = a*(1-w) + b*w on the FP32 records, every op rounded to FP32               FP32
+//   trilinear : z, then y, then x lerps of the 8 corner values, every op rounded to FP64        FP64
+// SMEM_NODES: node and inverse-spacing tables staged in shared memory (else read from global).
+template <bool SMEM_NODES, int MINB>
+__global__ void __launch_bounds__(256, MINB) grid_interp_kernel(const InterpParams p) {
+  extern __shared__ double s_tab[];
   const double* nd[3];
-  if (p.nodes_in_smem) {
+  const double* iv[3];
+  if (SMEM_NODES) {
     int off = 0;
     for (int d = 0; d < 3; ++d) {
-      for (int i = threadIdx.x; i < p.n[d]; i += blockDim.x) s_nodes[off + i] = p.node[d][i];
-      nd[d] = s_nodes + off;
-      off += p.n[d];
+      double* sn = s_tab + off;
+      double* si = sn + p.n[d];
+      for (int i = threadIdx.x; i < p.n[d]; i += blockDim.x) {
+        sn[i] = p.node[d][i];
+        si[i] = i + 1 < p.n[d] ? __ddiv_rn(1.0, __dsub_rn(p.node[d][i + 1], p.node[d][i])) : 0.0;
+      }
+      nd[d] = sn, iv[d] = si;
+      off += 2 * p.n[d];
     }
     __syncthreads();
   } else {
     nd[0] = p.node[0], nd[1] = p.node[1], nd[2] = p.node[2];
+    iv[0] = iv[1] = iv[2] = nullptr;
   }
-  long long s = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (s >= p.n_star) return;
-
+  // grid-stride over stars: the tables above are staged once per resident block, not once per 256 stars
+  for (long long s = blockIdx.x * (long long)blockDim.x + threadIdx.x; s < p.n_star;
+       s += (long long)gridDim.x * blockDim.x) {
   const int cl = p.scl ? p.scl[s] : 0;
   const double* org = p.origin + 3 * (long long)cl;
-  const double x = p.sx[s], y = p.sy[s], z = p.sz[s];
-  double x0, x1, y0, y1, z0, z1;
-  const int i = find_cell(nd[0], p.n[0], org[0], x, x0, x1);
-  const int j = find_cell(nd[1], p.n[1], org[1], y, y0, y1);
-  const int k = find_cell(nd[2], p.n[2], org[2], z, z0, z1);
-  const double tx = __ddiv_rn(__dsub_rn(x, x0), __dsub_rn(x1, x0));
-  const double ty = __ddiv_rn(__dsub_rn(y, y0), __dsub_rn(y1, y0));
-  const double tz = __ddiv_rn(__dsub_rn(z, z0), __dsub_rn(z1, z0));
-  const double ux = __dsub_rn(1.0, tx), uy = __dsub_rn(1.0, ty), uz = __dsub_rn(1.0, tz);
+  const double pos[3] = {p.sx[s], p.sy[s], p.sz[s]};
+  int c3[3];
+  double t[3], u[3];
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    const double o = org[d];
+    const int i = find_cell(nd[d], p.n[d], o, pos[d]);
+    const double inv = SMEM_NODES ? iv[d][i] : __ddiv_rn(1.0, __dsub_rn(nd[d][i + 1], nd[d][i]));
+    t[d] = __dmul_rn(__dsub_rn(pos[d], __dadd_rn(nd[d][i], o)), inv);
+    u[d] = __dsub_rn(1.0, t[d]);
+    c3[d] = i;
+  }
 
   const long long nyz = (long long)p.n[1] * p.n[2];
   const long long n_node = (long long)p.n[0] * nyz + 1;  // + appended origin row
-  const long long base = (long long)cl * n_node + ((long long)i * p.n[1] + j) * p.n[2] + k;
+  const long long base = (long long)cl * n_node + ((long long)c3[0] * p.n[1] + c3[1]) * p.n[2] + c3[2];
   const float4* A = p.rec_a + base;
   const float4* B = p.rec_b ? p.rec_b + base : nullptr;
-  const double wb = p.wb, wa = __dsub_rn(1.0, wb);
+  const float wb = p.wb, wa = __fsub_rn(1.0f, wb);
 
-  // corner order: (di,dj,dk) = 000,001,010,011,100,101,110,111
-  double v[8][4];
+  // corner order: (di,dj,dk) = 000,001,010,011,100,101,110,111 ; time blend in FP32
+  float4 v[8];
 #pragma unroll
   for (int c = 0; c < 8; ++c) {
     const long long off = (long long)(c >> 2) * nyz + (long long)((c >> 1) & 1) * p.n[2] + (c & 1);
     const float4 a = __ldg(A + off);
     if (B) {
       const float4 b = __ldg(B + off);
-      v[c][0] = lerp_rn((double)a.x, wa, (double)b.x, wb);
-      v[c][1] = lerp_rn((double)a.y, wa, (double)b.y, wb);
-      v[c][2] = lerp_rn((double)a.z, wa, (double)b.z, wb);
-      v[c][3] = lerp_rn((double)a.w, wa, (double)b.w, wb);
+      v[c] = make_float4(lerp_rn_f(a.x, wa, b.x, wb), lerp_rn_f(a.y, wa, b.y, wb), lerp_rn_f(a.z, wa, b.z, wb),
+                         lerp_rn_f(a.w, wa, b.w, wb));
     } else {
-      v[c][0] = a.x, v[c][1] = a.y, v[c][2] = a.z, v[c][3] = a.w;
+      v[c] = a;
     }
   }
   const int ncomp = p.pot ? 4 : 3;
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
     if (q >= ncomp) break;
-    const double c00 = lerp_rn(v[0][q], uz, v[1][q], tz);
-    const double c01 = lerp_rn(v[2][q], uz, v[3][q], tz);
-    const double c10 = lerp_rn(v[4][q], uz, v[5][q], tz);
-    const double c11 = lerp_rn(v[6][q], uz, v[7][q], tz);
-    const double c0 = lerp_rn(c00, uy, c01, ty);
-    const double c1 = lerp_rn(c10, uy, c11, ty);
-    const double r = lerp_rn(c0, ux, c1, tx);
+    double w[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) w[c] = (double)(q == 0 ? v[c].x : (q == 1 ? v[c].y : (q == 2 ? v[c].z : v[c].w)));
+    const double c00 = lerp_rn(w[0], u[2], w[1], t[2]);
+    const double c01 = lerp_rn(w[2], u[2], w[3], t[2]);
+    const double c10 = lerp_rn(w[4], u[2], w[5], t[2]);
+    const double c11 = lerp_rn(w[6], u[2], w[7], t[2]);
+    const double c0 = lerp_rn(c00, u[1], c01, t[1]);
+    const double c1 = lerp_rn(c10, u[1], c11, t[1]);
+    const double r = lerp_rn(c0, u[0], c1, t[0]);
     if (q < 3) p.acc[(long long)q * p.n_star + s] = r;
     else p.pot[s] = r;
   }
   if (p.cell) {
-    p.cell[s] = i;
-    p.cell[p.n_star + s] = j;
-    p.cell[2 * p.n_star + s] = k;
+    p.cell[s] = c3[0];
+    p.cell[p.n_star + s] = c3[1];
+    p.cell[2 * p.n_star + s] = c3[2];
   }
+  }
+}
+
+static int g_interp_variant = 2;  // 0: <=128 regs (2 blocks/SM), 1: <=80 regs (3), 2: <=64 regs (4: fastest, latency-bound)
+extern "C" int ocg_debug_set_interp_variant(int v) {
+  if (v < 0 || v > 2) return OCG_ERR_INVALID;
+  g_interp_variant = v;
+  return OCG_OK;
 }
 
 extern "C" int ocg_grid_interp(ocg_ctx* ctx, const ocg_grid_desc* grid, const float* rec_a_dev,
@@ -194,15 +229,26 @@ extern "C" int ocg_grid_interp(ocg_ctx* ctx, const ocg_grid_desc* grid, const fl
   p.origin = grid->origin_dev;
   p.rec_a = reinterpret_cast<const float4*>(rec_a_dev);
   p.rec_b = reinterpret_cast<const float4*>(rec_b_dev);
-  p.wb = rec_b_dev ? w_b : 0.0;
+  p.wb = rec_b_dev ? (float)w_b : 0.0f;
   p.sx = star_x_dev, p.sy = star_y_dev, p.sz = star_z_dev;
   p.scl = star_cluster_dev;
   p.n_star = n_star;
   p.acc = acc_out_dev, p.pot = pot_out_dev, p.cell = cell_out_dev;
   long long nn = (long long)grid->n[0] + grid->n[1] + grid->n[2];
-  p.nodes_in_smem = nn <= 4096;
-  size_t smem = p.nodes_in_smem ? (size_t)nn * sizeof(double) : 0;
-  grid_interp_kernel<<<nblocks(n_star, 256), 256, smem, (cudaStream_t)stream>>>(p);
+  // persistent launch: as many blocks as are resident at once (a multiple of the SM count), grid-stride inside
+  const bool in_smem = nn <= 2048;
+  const size_t smem = in_smem ? (size_t)nn * 2 * sizeof(double) : 0;
+  typedef void (*interp_fn)(const InterpParams);
+  static const interp_fn fns[3][2] = {{grid_interp_kernel<false, 2>, grid_interp_kernel<true, 2>},
+                                      {grid_interp_kernel<false, 3>, grid_interp_kernel<true, 3>},
+                                      {grid_interp_kernel<false, 4>, grid_interp_kernel<true, 4>}};
+  interp_fn fn = fns[g_interp_variant][in_smem ? 1 : 0];
+  int occ = 0;
+  OCG_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, 256, smem));
+  if (occ < 1) occ = 1;
+  int grid_blocks = nblocks(n_star, 256);
+  if (grid_blocks > ctx->sm_count * occ) grid_blocks = ctx->sm_count * occ;
+  fn<<<grid_blocks, 256, smem, (cudaStream_t)stream>>>(p);
   OCG_CHECK_LAUNCH(ctx, "grid_interp_kernel");
   return OCG_OK;
 }

@@ -118,7 +118,9 @@ extern "C" int ocg_self_gravity(ocg_ctx* ctx, const double* pos_dev, const doubl
     if (!(scale > 0.f) || !isfinite(scale) || !(e2f * scale * scale > 0.f)) scale = 1.0f;
   }
   const int64_t n_shard = tgt_end - tgt_begin;
-  const int variant = ocg_pick_variant(ctx, n_shard, guard);
+  // the tile shape follows the typical cluster size, not the batch size: a 4096-star cluster would fill only
+  // 1 1/3 of the 3072-target tiles of the big-grid kernel
+  const int variant = ocg_pick_variant(ctx, n_shard, (n + n_seg - 1) / n_seg, guard);
   const int tpt = ocg_variant_tpt(variant);
   const int CT = ocg_variant_threads(variant) * tpt;
 

@@ -205,10 +205,21 @@ static int find_cell(const double* node, int n, double o, double x) {
 }
 
 static inline double lerp2(double a, double wa, double b, double wb) { return a * wa + b * wb; }
+/* FP32 blend, every operation rounded to FP32 (this file is compiled with -ffp-contract=off; the volatile
+ * stores keep x87-style excess precision out of the picture on any host). */
+static inline float lerp2f(float a, float wa, float b, float wb) {
+  volatile float p = a * wa, q = b * wb;
+  volatile float r = p + q;
+  return r;
+}
 
 /* get_gravity_at_point (gizmo_interface.py:677-717) as trilinear-in-space, linear-in-time.
  * rec_a/rec_b: [n_cluster][nx*ny*nz+1][4] FP32 node records (ax,ay,az,phi) of the bracketing
- * snapshots (rec_b may be NULL), wb weight of b.  Operation order identical to the CUDA kernel. */
+ * snapshots (rec_b may be NULL), wb weight of b.  Arithmetic contract (same as the CUDA kernel):
+ *   cell   : searchsorted on node + origin (FP64)
+ *   weight : t = (x - (node[i] + origin)) * inv[i], inv[i] = 1/(node[i+1] - node[i])            FP64
+ *   time   : v = a*(1-w) + b*w on the FP32 records with w = (float)wb, each op rounded to FP32
+ *   space  : z, y, x lerps of the 8 corner values, each op rounded to FP64 */
 void oracle_grid_interp(const int32_t* nn, int32_t n_cluster, const double* nodex, const double* nodey,
                         const double* nodez, const double* origin, const float* rec_a, const float* rec_b, double wb,
                         const double* sx, const double* sy, const double* sz, const int32_t* scl, int64_t n_star,
@@ -216,7 +227,9 @@ void oracle_grid_interp(const int32_t* nn, int32_t n_cluster, const double* node
   (void)n_cluster;
   const int nx = nn[0], ny = nn[1], nz = nn[2];
   const int64_t nyz = (int64_t)ny * nz, n_node = (int64_t)nx * nyz + 1;
-  const double wa = 1.0 - wb;
+  const float wbf = rec_b ? (float)wb : 0.0f;
+  volatile float waf_v = 1.0f - wbf;
+  const float waf = waf_v;
 #pragma omp parallel for schedule(static)
   for (int64_t s = 0; s < n_star; ++s) {
     const int cl = scl ? scl[s] : 0;
@@ -224,10 +237,9 @@ void oracle_grid_interp(const int32_t* nn, int32_t n_cluster, const double* node
     const int i = find_cell(nodex, nx, o[0], sx[s]);
     const int j = find_cell(nodey, ny, o[1], sy[s]);
     const int k = find_cell(nodez, nz, o[2], sz[s]);
-    const double x0 = nodex[i] + o[0], x1 = nodex[i + 1] + o[0];
-    const double y0 = nodey[j] + o[1], y1 = nodey[j + 1] + o[1];
-    const double z0 = nodez[k] + o[2], z1 = nodez[k + 1] + o[2];
-    const double tx = (sx[s] - x0) / (x1 - x0), ty = (sy[s] - y0) / (y1 - y0), tz = (sz[s] - z0) / (z1 - z0);
+    const double tx = (sx[s] - (nodex[i] + o[0])) * (1.0 / (nodex[i + 1] - nodex[i]));
+    const double ty = (sy[s] - (nodey[j] + o[1])) * (1.0 / (nodey[j + 1] - nodey[j]));
+    const double tz = (sz[s] - (nodez[k] + o[2])) * (1.0 / (nodez[k + 1] - nodez[k]));
     const double ux = 1.0 - tx, uy = 1.0 - ty, uz = 1.0 - tz;
     const int64_t base = (int64_t)cl * n_node + ((int64_t)i * ny + j) * nz + k;
     double v[8][4];
@@ -236,7 +248,7 @@ void oracle_grid_interp(const int32_t* nn, int32_t n_cluster, const double* node
       const float* a = rec_a + 4 * (base + off);
       if (rec_b) {
         const float* b = rec_b + 4 * (base + off);
-        for (int q = 0; q < 4; ++q) v[c][q] = lerp2((double)a[q], wa, (double)b[q], wb);
+        for (int q = 0; q < 4; ++q) v[c][q] = (double)lerp2f(a[q], waf, b[q], wbf);
       } else {
         for (int q = 0; q < 4; ++q) v[c][q] = (double)a[q];
       }
@@ -264,14 +276,15 @@ void oracle_pack_planes(const double* acc, const double* pot, int64_t n, float* 
 
 /* Linear time blend of node records (gizmo_interface.py:607-620 in linear form). */
 void oracle_time_blend(const float* ra, const float* rb, double wb, int64_t n, double* acc, double* pot) {
-  const double wa = 1.0 - wb;
+  const float wbf = rb ? (float)wb : 0.0f;
+  volatile float waf_v = 1.0f - wbf;
+  const float waf = waf_v;
   for (int64_t i = 0; i < n; ++i) {
     const float* a = ra + 4 * i;
-    const float* b = rb ? rb + 4 * i : a;
-    acc[i] = lerp2((double)a[0], wa, (double)b[0], wb);
-    acc[n + i] = lerp2((double)a[1], wa, (double)b[1], wb);
-    acc[2 * n + i] = lerp2((double)a[2], wa, (double)b[2], wb);
-    if (pot) pot[i] = lerp2((double)a[3], wa, (double)b[3], wb);
+    float v[4];
+    for (int q = 0; q < 4; ++q) v[q] = rb ? lerp2f(a[q], waf, rb[4 * i + q], wbf) : a[q];
+    acc[i] = (double)v[0], acc[n + i] = (double)v[1], acc[2 * n + i] = (double)v[2];
+    if (pot) pot[i] = (double)v[3];
   }
 }
 
