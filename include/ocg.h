@@ -16,10 +16,10 @@
  * NULL = the legacy default stream).  Host-pointer calls return after the result is on the host.
  *
  * The library is unit-agnostic: lengths and masses in, G as an argument.
- *   field path  : kpc, Msun, G = 4.300917270036279e-06 kpc (km/s)^2/Msun * (km/s per kpc/Myr)...
- *                 the reference uses G in kpc^2 km s^-1 Myr^-1 Msun^-1 (gizmo_interface.py:70)
- *                 = 4.498502151469554e-12 kpc^3/Myr^2/Msun * 977.79222 = 4.3986004e-09.
- *   cluster path: pc, Msun, G = 4.30091727e-03 pc (km/s)^2 / Msun.
+ *   field path  : kpc, Msun and the reference's G in kpc^2 km s^-1 Myr^-1 Msun^-1 (gizmo_interface.py:70)
+ *                 = 4.3986004e-09, giving accelerations in km/s/Myr (gizmo_interface.py:706-708);
+ *   cluster path: the same system (kpc, km/s, Myr, Msun) so the BRIDGE kick needs no conversion,
+ *                 or e.g. pc, Msun, G = 4.30091727e-03 pc (km/s)^2 / Msun.
  *
  * Reference interface replaced by each entry point is cited as (file:line) into gusbeane/oc_nbody.
  */
@@ -137,6 +137,17 @@ int ocg_grid_interp(ocg_ctx* ctx, const ocg_grid_desc* grid, const float* rec_a_
                     const int32_t* star_cluster_dev, int64_t n_star, double* acc_out_dev,
                     double* pot_out_dev, int32_t* cell_out_dev /* [3][n_star] nullable */,
                     void* stream);
+
+/* The same evaluation with 1..4 record planes blended in time: v = ((r0*w0 + r1*w1) + r2*w2) + r3*w3 in FP32.
+ * With the four non-zero cubic B-spline basis weights and the matching coefficient planes this is the
+ * reference's own time interpolation (splrep/splev per grid point, gizmo_interface.py:587-620): all grid
+ * points share one knot vector, so splev collapses to this blend.
+ * rec_dev: HOST array of n_rec device pointers, each [n_cluster][n_node] float4; weights: HOST array [n_rec]. */
+int ocg_grid_interp_multi(ocg_ctx* ctx, const ocg_grid_desc* grid, const float* const* rec_dev,
+                          const double* weights, int32_t n_rec, const double* star_x_dev,
+                          const double* star_y_dev, const double* star_z_dev,
+                          const int32_t* star_cluster_dev, int64_t n_star, double* acc_out_dev,
+                          double* pot_out_dev, int32_t* cell_out_dev, void* stream);
 
 /* ---- K4: cluster self-gravity (ph4 force loop behind oc_code.py:218-229) ---------------------
  * Plummer direct sum inside each segment (cluster) of a batch.

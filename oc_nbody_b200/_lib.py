@@ -20,7 +20,7 @@ ABI_SYMBOLS = [
     "ocg_version", "ocg_create", "ocg_destroy", "ocg_last_error", "ocg_device_info", "ocg_launch_count",
     "ocg_last_direct_kernel_ms", "ocg_set_kernel_timing", "ocg_recentre_f64", "ocg_cast_f64_f32",
     "ocg_field_direct", "ocg_frame_subtract", "ocg_field_build_host", "ocg_pack_planes", "ocg_grid_time_blend",
-    "ocg_grid_interp", "ocg_self_gravity", "ocg_kick", "ocg_drift", "ocg_axpy", "ocg_probe_throughput",
+    "ocg_grid_interp", "ocg_grid_interp_multi", "ocg_self_gravity", "ocg_kick", "ocg_drift", "ocg_axpy", "ocg_probe_throughput",
 ]
 
 
@@ -65,6 +65,8 @@ def load_library():
     L.ocg_pack_planes.argtypes = [vp, vp, vp, i64, vp, vp]
     L.ocg_grid_time_blend.argtypes = [vp, vp, vp, dbl, i64, vp, vp, vp]
     L.ocg_grid_interp.argtypes = [vp, ctypes.POINTER(_GridDesc), vp, vp, dbl, vp, vp, vp, vp, i64, vp, vp, vp, vp]
+    L.ocg_grid_interp_multi.argtypes = [vp, ctypes.POINTER(_GridDesc), vp, ctypes.POINTER(dbl), i32, vp, vp, vp, vp, i64, vp, vp,
+                                        vp, vp]
     L.ocg_self_gravity.argtypes = [vp, vp, vp, i64, vp, i32, dbl, dbl, i64, i64, vp, vp, vp]
     L.ocg_kick.argtypes = [vp, vp, vp, i64, dbl, vp]
     L.ocg_drift.argtypes = [vp, vp, vp, i64, dbl, dbl, vp]
@@ -187,6 +189,20 @@ class Context:
         self._ck(self.lib.ocg_grid_interp(self.h, ctypes.byref(d), _dptr(rec_a), _dptr(rec_b), float(w_b), _dptr(sx),
                                           _dptr(sy), _dptr(sz), _dptr(star_cluster), sx.shape[0], _dptr(acc_out),
                                           _dptr(pot_out), _dptr(cell_out), self._stream()), "ocg_grid_interp")
+
+    def grid_interp_multi(self, n, nodes, origin, recs, weights, sx, sy, sz, star_cluster, acc_out, pot_out=None):
+        """K3 with 1..4 record planes and their time weights (cubic B-spline blend)."""
+        d = _GridDesc()
+        for k in range(3):
+            d.n[k] = int(n[k])
+            d.node_dev[k] = nodes[k].data_ptr()
+        d.n_cluster = int(origin.shape[0])
+        d.origin_dev = origin.data_ptr()
+        ptrs = (ctypes.c_void_p * len(recs))(*[_dptr(r).value for r in recs])
+        w = (ctypes.c_double * len(recs))(*[float(x) for x in weights])
+        self._ck(self.lib.ocg_grid_interp_multi(self.h, ctypes.byref(d), ptrs, w, len(recs), _dptr(sx), _dptr(sy), _dptr(sz),
+                                                _dptr(star_cluster), sx.shape[0], _dptr(acc_out), _dptr(pot_out), None,
+                                                self._stream()), "ocg_grid_interp_multi")
 
     def self_gravity(self, pos, mass, eps2, G, acc, pot=None, seg_offsets=None, tgt_begin=0, tgt_end=None):
         n = pos.shape[1]

@@ -72,9 +72,9 @@ struct InterpParams {
   int n_cluster;
   const double* node[3];
   const double* origin;
-  const float4* rec_a;
-  const float4* rec_b;
-  float wb;  // weight of snapshot b, rounded to FP32 (the time blend is FP32 arithmetic)
+  const float4* rec[4];  // 1..4 record planes blended in time (2: linear bracket, 4: cubic B-spline coefficients)
+  float w[4];            // their FP32 weights (the time blend is FP32 arithmetic)
+  int n_rec;
   const double* sx;
   const double* sy;
   const double* sz;
@@ -156,23 +156,25 @@ __global__ void __launch_bounds__(256, MINB) grid_interp_kernel(const InterpPara
   const long long nyz = (long long)p.n[1] * p.n[2];
   const long long n_node = (long long)p.n[0] * nyz + 1;  // + appended origin row
   const long long base = (long long)cl * n_node + ((long long)c3[0] * p.n[1] + c3[1]) * p.n[2] + c3[2];
-  const float4* A = p.rec_a + base;
-  const float4* B = p.rec_b ? p.rec_b + base : nullptr;
-  const float wb = p.wb, wa = __fsub_rn(1.0f, wb);
-
-  // corner order: (di,dj,dk) = 000,001,010,011,100,101,110,111 ; time blend in FP32
+  // corner order: (di,dj,dk) = 000,001,010,011,100,101,110,111
+  // time blend in FP32, left to right: v = ((r0*w0 + r1*w1) + r2*w2) + r3*w3 ; a single plane is taken as is
   float4 v[8];
 #pragma unroll
   for (int c = 0; c < 8; ++c) {
-    const long long off = (long long)(c >> 2) * nyz + (long long)((c >> 1) & 1) * p.n[2] + (c & 1);
-    const float4 a = __ldg(A + off);
-    if (B) {
-      const float4 b = __ldg(B + off);
-      v[c] = make_float4(lerp_rn_f(a.x, wa, b.x, wb), lerp_rn_f(a.y, wa, b.y, wb), lerp_rn_f(a.z, wa, b.z, wb),
-                         lerp_rn_f(a.w, wa, b.w, wb));
-    } else {
-      v[c] = a;
+    const long long off = base + (long long)(c >> 2) * nyz + (long long)((c >> 1) & 1) * p.n[2] + (c & 1);
+    float4 a = __ldg(p.rec[0] + off);
+    if (p.n_rec > 1) {
+      const float4 b = __ldg(p.rec[1] + off);
+      a = make_float4(lerp_rn_f(a.x, p.w[0], b.x, p.w[1]), lerp_rn_f(a.y, p.w[0], b.y, p.w[1]),
+                      lerp_rn_f(a.z, p.w[0], b.z, p.w[1]), lerp_rn_f(a.w, p.w[0], b.w, p.w[1]));
+      for (int r = 2; r < p.n_rec; ++r) {
+        const float4 e = __ldg(p.rec[r] + off);
+        const float wr = p.w[r];
+        a = make_float4(__fadd_rn(a.x, __fmul_rn(e.x, wr)), __fadd_rn(a.y, __fmul_rn(e.y, wr)),
+                        __fadd_rn(a.z, __fmul_rn(e.z, wr)), __fadd_rn(a.w, __fmul_rn(e.w, wr)));
+      }
     }
+    v[c] = a;
   }
   const int ncomp = p.pot ? 4 : 3;
 #pragma unroll
@@ -206,34 +208,33 @@ extern "C" int ocg_debug_set_interp_variant(int v) {
   return OCG_OK;
 }
 
-extern "C" int ocg_grid_interp(ocg_ctx* ctx, const ocg_grid_desc* grid, const float* rec_a_dev,
-                               const float* rec_b_dev, double w_b, const double* star_x_dev,
-                               const double* star_y_dev, const double* star_z_dev,
-                               const int32_t* star_cluster_dev, int64_t n_star, double* acc_out_dev,
-                               double* pot_out_dev, int32_t* cell_out_dev, void* stream) {
-  if (!ctx) return OCG_ERR_INVALID;
-  if (!grid) return ocg_fail(ctx, OCG_ERR_INVALID, "ocg_grid_interp: grid is NULL");
-  if (n_star < 0) return ocg_fail(ctx, OCG_ERR_INVALID, "ocg_grid_interp: negative n_star");
+static int interp_launch(ocg_ctx* ctx, const ocg_grid_desc* grid, const float* const* rec, const float* w, int n_rec,
+                         const double* sx, const double* sy, const double* sz, const int32_t* scl, int64_t n_star,
+                         double* acc, double* pot, int32_t* cell, void* stream, const char* who) {
+  if (!grid) return ocg_fail(ctx, OCG_ERR_INVALID, "%s: grid is NULL", who);
+  if (n_star < 0) return ocg_fail(ctx, OCG_ERR_INVALID, "%s: negative n_star", who);
   if (n_star == 0) return OCG_OK;
   for (int d = 0; d < 3; ++d)
     if (grid->n[d] < 2 || !grid->node_dev[d])
-      return ocg_fail(ctx, OCG_ERR_INVALID, "ocg_grid_interp: axis %d needs >= 2 nodes (got %d)", d, grid->n[d]);
-  if (grid->n_cluster < 1 || !grid->origin_dev || !rec_a_dev || !star_x_dev || !star_y_dev || !star_z_dev || !acc_out_dev)
-    return ocg_fail(ctx, OCG_ERR_INVALID, "ocg_grid_interp: NULL argument");
-  if (!(w_b >= 0.0 && w_b <= 1.0))
-    return ocg_fail(ctx, OCG_ERR_INVALID, "ocg_grid_interp: w_b = %g outside [0,1]", w_b);
+      return ocg_fail(ctx, OCG_ERR_INVALID, "%s: axis %d needs >= 2 nodes (got %d)", who, d, grid->n[d]);
+  if (grid->n_cluster < 1 || !grid->origin_dev || !sx || !sy || !sz || !acc)
+    return ocg_fail(ctx, OCG_ERR_INVALID, "%s: NULL argument", who);
+  if (n_rec < 1 || n_rec > 4) return ocg_fail(ctx, OCG_ERR_INVALID, "%s: n_rec = %d outside [1,4]", who, n_rec);
   OcgDeviceGuard g(ctx->device);
   InterpParams p;
   for (int d = 0; d < 3; ++d) p.n[d] = grid->n[d], p.node[d] = grid->node_dev[d];
   p.n_cluster = grid->n_cluster;
   p.origin = grid->origin_dev;
-  p.rec_a = reinterpret_cast<const float4*>(rec_a_dev);
-  p.rec_b = reinterpret_cast<const float4*>(rec_b_dev);
-  p.wb = rec_b_dev ? (float)w_b : 0.0f;
-  p.sx = star_x_dev, p.sy = star_y_dev, p.sz = star_z_dev;
-  p.scl = star_cluster_dev;
+  for (int r = 0; r < 4; ++r) {
+    p.rec[r] = r < n_rec ? reinterpret_cast<const float4*>(rec[r]) : nullptr;
+    p.w[r] = r < n_rec ? w[r] : 0.f;
+    if (r < n_rec && !rec[r]) return ocg_fail(ctx, OCG_ERR_INVALID, "%s: record plane %d is NULL", who, r);
+  }
+  p.n_rec = n_rec;
+  p.sx = sx, p.sy = sy, p.sz = sz;
+  p.scl = scl;
   p.n_star = n_star;
-  p.acc = acc_out_dev, p.pot = pot_out_dev, p.cell = cell_out_dev;
+  p.acc = acc, p.pot = pot, p.cell = cell;
   long long nn = (long long)grid->n[0] + grid->n[1] + grid->n[2];
   // persistent launch: as many blocks as are resident at once (a multiple of the SM count), grid-stride inside
   const bool in_smem = nn <= 2048;
@@ -251,4 +252,35 @@ extern "C" int ocg_grid_interp(ocg_ctx* ctx, const ocg_grid_desc* grid, const fl
   fn<<<grid_blocks, 256, smem, (cudaStream_t)stream>>>(p);
   OCG_CHECK_LAUNCH(ctx, "grid_interp_kernel");
   return OCG_OK;
+}
+
+extern "C" int ocg_grid_interp(ocg_ctx* ctx, const ocg_grid_desc* grid, const float* rec_a_dev,
+                               const float* rec_b_dev, double w_b, const double* star_x_dev,
+                               const double* star_y_dev, const double* star_z_dev,
+                               const int32_t* star_cluster_dev, int64_t n_star, double* acc_out_dev,
+                               double* pot_out_dev, int32_t* cell_out_dev, void* stream) {
+  if (!ctx) return OCG_ERR_INVALID;
+  if (!rec_a_dev) return ocg_fail(ctx, OCG_ERR_INVALID, "ocg_grid_interp: NULL argument");
+  if (!(w_b >= 0.0 && w_b <= 1.0))
+    return ocg_fail(ctx, OCG_ERR_INVALID, "ocg_grid_interp: w_b = %g outside [0,1]", w_b);
+  const float* rec[2] = {rec_a_dev, rec_b_dev};
+  const float wb = (float)w_b;
+  volatile float wa = 1.0f - wb;  // rounded to FP32, as the oracle does
+  const float w[2] = {wa, wb};
+  return interp_launch(ctx, grid, rec, w, rec_b_dev ? 2 : 1, star_x_dev, star_y_dev, star_z_dev, star_cluster_dev,
+                       n_star, acc_out_dev, pot_out_dev, cell_out_dev, stream, "ocg_grid_interp");
+}
+
+extern "C" int ocg_grid_interp_multi(ocg_ctx* ctx, const ocg_grid_desc* grid, const float* const* rec_dev,
+                                     const double* weights, int32_t n_rec, const double* star_x_dev,
+                                     const double* star_y_dev, const double* star_z_dev,
+                                     const int32_t* star_cluster_dev, int64_t n_star, double* acc_out_dev,
+                                     double* pot_out_dev, int32_t* cell_out_dev, void* stream) {
+  if (!ctx) return OCG_ERR_INVALID;
+  if (!rec_dev || !weights || n_rec < 1 || n_rec > 4)
+    return ocg_fail(ctx, OCG_ERR_INVALID, "ocg_grid_interp_multi: need 1..4 record planes and weights");
+  float w[4];
+  for (int r = 0; r < n_rec; ++r) w[r] = (float)weights[r];
+  return interp_launch(ctx, grid, rec_dev, w, n_rec, star_x_dev, star_y_dev, star_z_dev, star_cluster_dev, n_star,
+                       acc_out_dev, pot_out_dev, cell_out_dev, stream, "ocg_grid_interp_multi");
 }

@@ -33,6 +33,8 @@ _DEFAULTS = dict(
     grid_x_size_in_kpc=0.6, grid_y_size_in_kpc=0.6, grid_z_size_in_kpc=0.6, grid_resolution=0.6 / 16,
     star_softening_in_pc=11.2, dark_softening_in_pc=112.0, star_char_mass=None, dark_char_mass=None,
     softening_kernel="spline", plummer_eps_over_h=1.0 / 2.8, theta=0.5, fine_grid=False, with_potential=True,
+    # "linear" (BASELINE.json north_star) or "cubic" (the reference's own splrep/splev, gizmo_interface.py:587-620)
+    time_interpolation="linear",
 )
 
 
@@ -62,6 +64,8 @@ class gizmo_field(object):
             raise ValueError("softening_kernel must be one of %r" % (sorted(_lib.KERNELS),))
         if self.fine_grid:
             raise NotImplementedError("nested fine grid is a SURVEY §8(f) 'next' row")
+        if self.time_interpolation not in ("linear", "cubic"):
+            raise ValueError("time_interpolation must be 'linear' or 'cubic'")
         self.G = G_KPC_KMS_MYR  # kpc^2 km/s /Myr /Msun, the unit of gizmo_interface.py:70
         self._ctx = ctx  # created lazily: host-side logic (source assembly, time bracketing) needs no GPU
         self.snapshots = list(snapshots)
@@ -172,6 +176,19 @@ class gizmo_field(object):
             self.ctx.pack_planes(acc, pot, rec[i])
         self._dev = dict(rec=rec, nodes=[torch.from_numpy(np.ascontiguousarray(a)).to(dev) for a in g.nodes],
                          origin=torch.zeros((1, 3), dtype=torch.float64, device=dev), device=dev)
+        if self.time_interpolation == "cubic":
+            # one vectorised spline fit over all grid points (= splrep per point, gizmo_interface.py:591-597);
+            # the coefficient planes replace the snapshot planes as what K3 gathers from
+            from . import time_spline
+            stacks = [g.snapshot_acceleration_x, g.snapshot_acceleration_y, g.snapshot_acceleration_z]
+            stacks.append(g.snapshot_potential if g.snapshot_potential is not None else np.zeros_like(stacks[0]))
+            self._knots, coef = time_spline.fit(self.time_in_Myr, np.stack(stacks, axis=1))  # [Nsnap, 4, n_node]
+            self._coef = coef
+            crec = torch.empty((coef.shape[0], nnode, 4), dtype=torch.float32, device=dev)
+            for i in range(coef.shape[0]):
+                self.ctx.pack_planes(torch.from_numpy(np.ascontiguousarray(coef[i, :3])).to(dev),
+                                     torch.from_numpy(np.ascontiguousarray(coef[i, 3])).to(dev), crec[i])
+            self._dev["coef_rec"] = crec
         self._set_origin_(self._origin)
 
     # ---------------------------------------------------------------------- per-step state ----
@@ -200,6 +217,9 @@ class gizmo_field(object):
             a, b, w = self._bracket
             p = self.chosen_snapshot_positions
             self.chosen_evolved_position = (1.0 - w) * p[a] + w * p[b]
+        if self.time_interpolation == "cubic" and getattr(self, "_knots", None) is not None:
+            from . import time_spline
+            self._spline_first, self._spline_w = time_spline.basis(self._knots, t)
         self._blend_cache = None
 
     def evolve_grid(self, pos):
@@ -209,6 +229,10 @@ class gizmo_field(object):
 
     # materialised blend, for code that reads grid.evolved_acceleration_* (gizmo_interface.py:618-620)
     def _blend_(self):
+        if self._blend_cache is None and self.time_interpolation == "cubic":
+            f, w = self._spline_first, self._spline_w
+            v = np.tensordot(w, self._coef[f:f + 4], axes=1)  # FP64 on the host: [4, n_node]
+            self._blend_cache = (v[:3], v[3])
         if self._blend_cache is None:
             import torch
             a, b, w = self._bracket
@@ -236,6 +260,11 @@ class gizmo_field(object):
         n = sx.shape[0]
         acc = torch.empty((3, n), dtype=torch.float64, device=d["device"])
         pot = torch.empty(n, dtype=torch.float64, device=d["device"]) if want_pot else None
+        if self.time_interpolation == "cubic":
+            f = self._spline_first
+            self.ctx.grid_interp_multi(self.grid.shape, d["nodes"], d["origin"], [d["coef_rec"][f + j] for j in range(4)],
+                                       self._spline_w, sx, sy, sz, None, acc, pot)
+            return acc, pot
         a, b, w = self._bracket
         rec = d["rec"]
         self.ctx.grid_interp(self.grid.shape, d["nodes"], d["origin"], rec[a], rec[b] if b != a else None, w, sx, sy, sz,

@@ -192,6 +192,26 @@ def grid_interp(nodes, origin, rec_a, rec_b, wb, sx, sy, sz, star_cluster=None, 
     return out[0] if len(out) == 1 else tuple(out)
 
 
+def grid_interp_multi(nodes, origin, recs, weights, sx, sy, sz, star_cluster=None, want_pot=False):
+    """Same evaluation with 1..4 record planes blended in time (cubic B-spline coefficients: the reference's own
+    splrep/splev time interpolation, gizmo_interface.py:587-620, collapsed over the shared knot vector)."""
+    xg, yg, zg = (_c(a, np.float64) for a in nodes)
+    origin = _c(origin, np.float64).reshape(-1, 3)
+    recs = [_c(r, np.float32) for r in recs]
+    ptrs = (ctypes.c_void_p * len(recs))(*[r.ctypes.data for r in recs])
+    w = _c(weights, np.float64)
+    sx, sy, sz = (_c(a, np.float64) for a in (sx, sy, sz))
+    scl = _c(star_cluster, np.int32)
+    n = sx.shape[0]
+    nn = np.array([len(xg), len(yg), len(zg)], np.int32)
+    acc = np.empty((3, n), np.float64)
+    pot = np.empty(n, np.float64) if want_pot else None
+    lib().oracle_grid_interp_multi(_p(nn), ctypes.c_int32(origin.shape[0]), _p(xg), _p(yg), _p(zg), _p(origin), ptrs, _p(w),
+                                   ctypes.c_int32(len(recs)), _p(sx), _p(sy), _p(sz), _p(scl), ctypes.c_int64(n), _p(acc),
+                                   _p(pot), None)
+    return (acc, pot) if want_pot else acc
+
+
 def kick(vel, acc, dt):
     vel = np.array(vel, np.float64, order="C", copy=True)
     acc = _c(acc, np.float64)

@@ -213,23 +213,19 @@ static inline float lerp2f(float a, float wa, float b, float wb) {
   return r;
 }
 
-/* get_gravity_at_point (gizmo_interface.py:677-717) as trilinear-in-space, linear-in-time.
- * rec_a/rec_b: [n_cluster][nx*ny*nz+1][4] FP32 node records (ax,ay,az,phi) of the bracketing
- * snapshots (rec_b may be NULL), wb weight of b.  Arithmetic contract (same as the CUDA kernel):
+/* get_gravity_at_point (gizmo_interface.py:677-717) as trilinear-in-space interpolation of a time blend of
+ * 1..4 record planes.  rec[r]: [n_cluster][nx*ny*nz+1][4] FP32 node records (ax,ay,az,phi); w[r] FP32 weights.
+ * Arithmetic contract (same as the CUDA kernel):
  *   cell   : searchsorted on node + origin (FP64)
  *   weight : t = (x - (node[i] + origin)) * inv[i], inv[i] = 1/(node[i+1] - node[i])            FP64
- *   time   : v = a*(1-w) + b*w on the FP32 records with w = (float)wb, each op rounded to FP32
+ *   time   : v = ((r0*w0 + r1*w1) + r2*w2) + r3*w3 on the FP32 records, each op rounded to FP32
  *   space  : z, y, x lerps of the 8 corner values, each op rounded to FP64 */
-void oracle_grid_interp(const int32_t* nn, int32_t n_cluster, const double* nodex, const double* nodey,
-                        const double* nodez, const double* origin, const float* rec_a, const float* rec_b, double wb,
-                        const double* sx, const double* sy, const double* sz, const int32_t* scl, int64_t n_star,
-                        double* acc, double* pot, int32_t* cell) {
-  (void)n_cluster;
+static void grid_interp_core(const int32_t* nn, const double* nodex, const double* nodey, const double* nodez,
+                             const double* origin, const float* const* rec, const float* w, int n_rec,
+                             const double* sx, const double* sy, const double* sz, const int32_t* scl, int64_t n_star,
+                             double* acc, double* pot, int32_t* cell) {
   const int nx = nn[0], ny = nn[1], nz = nn[2];
   const int64_t nyz = (int64_t)ny * nz, n_node = (int64_t)nx * nyz + 1;
-  const float wbf = rec_b ? (float)wb : 0.0f;
-  volatile float waf_v = 1.0f - wbf;
-  const float waf = waf_v;
 #pragma omp parallel for schedule(static)
   for (int64_t s = 0; s < n_star; ++s) {
     const int cl = scl ? scl[s] : 0;
@@ -244,13 +240,18 @@ void oracle_grid_interp(const int32_t* nn, int32_t n_cluster, const double* node
     const int64_t base = (int64_t)cl * n_node + ((int64_t)i * ny + j) * nz + k;
     double v[8][4];
     for (int c = 0; c < 8; ++c) {
-      const int64_t off = (int64_t)(c >> 2) * nyz + (int64_t)((c >> 1) & 1) * nz + (c & 1);
-      const float* a = rec_a + 4 * (base + off);
-      if (rec_b) {
-        const float* b = rec_b + 4 * (base + off);
-        for (int q = 0; q < 4; ++q) v[c][q] = (double)lerp2f(a[q], waf, b[q], wbf);
-      } else {
-        for (int q = 0; q < 4; ++q) v[c][q] = (double)a[q];
+      const int64_t off = base + (int64_t)(c >> 2) * nyz + (int64_t)((c >> 1) & 1) * nz + (c & 1);
+      for (int q = 0; q < 4; ++q) {
+        float a = rec[0][4 * off + q];
+        if (n_rec > 1) {
+          a = lerp2f(a, w[0], rec[1][4 * off + q], w[1]);
+          for (int r = 2; r < n_rec; ++r) {
+            volatile float pr = rec[r][4 * off + q] * w[r];
+            volatile float sm = a + pr;
+            a = sm;
+          }
+        }
+        v[c][q] = (double)a;
       }
     }
     const int ncomp = pot ? 4 : 3;
@@ -264,6 +265,30 @@ void oracle_grid_interp(const int32_t* nn, int32_t n_cluster, const double* node
     }
     if (cell) cell[s] = i, cell[n_star + s] = j, cell[2 * n_star + s] = k;
   }
+}
+
+/* Linear-in-time form (north_star): planes a, b and the weight wb of b; wa = fl32(1 - fl32(wb)). */
+void oracle_grid_interp(const int32_t* nn, int32_t n_cluster, const double* nodex, const double* nodey,
+                        const double* nodez, const double* origin, const float* rec_a, const float* rec_b, double wb,
+                        const double* sx, const double* sy, const double* sz, const int32_t* scl, int64_t n_star,
+                        double* acc, double* pot, int32_t* cell) {
+  (void)n_cluster;
+  const float wbf = rec_b ? (float)wb : 0.0f;
+  volatile float waf_v = 1.0f - wbf;
+  const float w[2] = {waf_v, wbf};
+  const float* rec[2] = {rec_a, rec_b};
+  grid_interp_core(nn, nodex, nodey, nodez, origin, rec, w, rec_b ? 2 : 1, sx, sy, sz, scl, n_star, acc, pot, cell);
+}
+
+/* General form: n_rec planes with FP64 weights rounded to FP32 (cubic B-spline in time: 4 coefficient planes). */
+void oracle_grid_interp_multi(const int32_t* nn, int32_t n_cluster, const double* nodex, const double* nodey,
+                              const double* nodez, const double* origin, const float* const* rec, const double* weights,
+                              int32_t n_rec, const double* sx, const double* sy, const double* sz, const int32_t* scl,
+                              int64_t n_star, double* acc, double* pot, int32_t* cell) {
+  (void)n_cluster;
+  float w[4] = {0, 0, 0, 0};
+  for (int r = 0; r < n_rec; ++r) w[r] = (float)weights[r];
+  grid_interp_core(nn, nodex, nodey, nodez, origin, rec, w, n_rec, sx, sy, sz, scl, n_star, acc, pot, cell);
 }
 
 /* rec[i] = (float)(ax, ay, az, phi) — the FP32 node records K3 reads. acc [3][n]. */

@@ -187,6 +187,15 @@ def test_reference_time_spline_golden_is_reproduced_by_scipy():
     z = np.load(os.path.join(GOLD, "time_spline_reference.npz"))
     spl = make_interp_spline(z["times"], z["series"], k=3)
     assert np.allclose(spl(z["t_eval"]), z["values"], rtol=1e-12, atol=1e-14)
+    # the product's host module: one fit, then four basis weights per time (what the GPU blend consumes)
+    from oc_nbody_b200 import time_spline
+    knots, coef = time_spline.fit(z["times"], z["series"])
+    for k, x in enumerate(z["t_eval"]):
+        first, w = time_spline.basis(knots, x)
+        assert np.isclose(w.sum(), 1.0, rtol=1e-14)
+        assert np.allclose((w[:, None] * coef[first:first + 4]).sum(axis=0), z["values"][k], rtol=1e-12, atol=1e-14)
+    with pytest.raises(ValueError):
+        time_spline.fit(z["times"][:3], z["series"][:3])
     # and the north_star's linear-in-time substitute differs from it at the percent level (documented gap)
     lin = np.stack([np.interp(z["t_eval"], z["times"], z["series"][:, i]) for i in range(z["series"].shape[1])], 1)
     assert 1e-4 < np.max(np.abs(lin - z["values"])) < 0.2

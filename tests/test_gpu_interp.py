@@ -114,3 +114,53 @@ def test_pack_blend_kick_drift_bit_exact(ctx):
     rv = oracle.kick(vel, acc, 0.05)
     rp = oracle.drift(pos, rv, 0.1, 1.022712165045695e-3)
     assert np.array_equal(dv.cpu().numpy(), rv) and np.array_equal(dp.cpu().numpy(), rp)
+
+
+def test_grid_interp_multi_bit_exact_and_cubic_field_code(ctx):
+    """1..4 record planes (cubic B-spline in time = the reference's splrep/splev): kernel vs oracle bit-exact, and the
+    field code in time_interpolation='cubic' mode against scipy's splev per grid point."""
+    import torch
+    from scipy import interpolate
+    from oc_nbody_b200 import time_spline
+    from oc_nbody_b200.gizmo_field import gizmo_field
+    from oc_nbody_b200.units import units
+    rng = np.random.default_rng(17)
+    nodes = [np.linspace(-0.06, 0.06, 8)] * 3
+    origin = np.array([[8.0, 0.0, 0.0]])
+    n_node = 8 ** 3 + 1
+    recs = rng.normal(0, 1e-2, (4, n_node, 4)).astype(np.float32)
+    w = np.array([0.1, 0.55, 0.3, 0.05])
+    n = 5000
+    p = rng.uniform(-0.07, 0.07, (n, 3)) + origin
+    for nr in (1, 2, 3, 4):
+        ref_acc, ref_pot = oracle.grid_interp_multi(nodes, origin, list(recs[:nr]), w[:nr], p[:, 0], p[:, 1], p[:, 2],
+                                                    want_pot=True)
+        acc = torch.empty((3, n), dtype=torch.float64, device="cuda")
+        pot = torch.empty(n, dtype=torch.float64, device="cuda")
+        ctx.grid_interp_multi((8, 8, 8), [dev(a) for a in nodes], dev(origin), [dev(r) for r in recs[:nr]], w[:nr],
+                              dev(p[:, 0].copy()), dev(p[:, 1].copy()), dev(p[:, 2].copy()), None, acc, pot)
+        torch.cuda.synchronize()
+        assert np.array_equal(acc.cpu().numpy(), ref_acc) and np.array_equal(pot.cpu().numpy(), ref_pot)
+
+    # field code, cubic mode, 6 snapshots of a smooth synthetic field installed through set_snapshot_fields
+    class Snap(object):
+        snapshot = {"index": 0, "time": 0.0}
+    times = np.array([0.0, 22.0, 45.5, 68.0, 91.2, 113.9])
+    stacks = rng.normal(0, 1e-3, (4, 1, n_node)) + np.sin(times / 35.0)[None, :, None] * rng.normal(0, 1e-2, (4, 1, n_node))
+    f = gizmo_field(dict(grid_x_size_in_kpc=0.06, grid_y_size_in_kpc=0.06, grid_z_size_in_kpc=0.06, grid_resolution=0.06 / 8,
+                         time_interpolation="cubic"), [Snap() for _ in times], time_in_Myr=times, build=False, ctx=ctx)
+    f.set_snapshot_fields(stacks[0], stacks[1], stacks[2], pot=stacks[3])
+    f.evolve_grid(origin[0])
+    for t in (0.0, 30.3, 68.0, 100.0):
+        f.evolve_model(t | units.Myr)
+        ax, ay, az = f.get_gravity_at_point(0.0, p[:200, 0], p[:200, 1], p[:200, 2])
+        got = np.stack([c.value_in(units.kms / units.Myr) for c in (ax, ay, az)])
+        # the reference's way: splev of a per-node splrep (gizmo_interface.py:591-597,607-620), then trilinear
+        ev = np.empty((4, n_node))
+        for q in range(4):
+            for i in range(n_node):
+                ev[q, i] = interpolate.splev(t, interpolate.splrep(times, stacks[q][:, i]))
+        rec = oracle.pack_planes(ev[:3], ev[3])
+        want = oracle.grid_interp(nodes, origin, rec, None, 0.0, p[:200, 0], p[:200, 1], p[:200, 2])
+        assert np.max(np.abs(got - want)) <= 2e-6 * np.max(np.abs(want))   # FP32 coefficient planes
+        assert np.allclose(f.evolved_acceleration, ev[:3], rtol=1e-10, atol=1e-14)

@@ -76,6 +76,20 @@ def main():
                          frac_of_hbm_peak=alg / med / 1e6 / HBM_PEAK, bytes_if_every_record_read_once=moved,
                          stars=ncl * nstar, l2="flushed before every launch")
 
+    # same launch with the stars spread uniformly over each grid: every record is really fetched from HBM
+    # (with cluster-like concentration above, only the central ~1% of each grid is touched and the planes stay in L2)
+    pu = origin[scl] + rng.uniform(-0.05, 0.05, (ncl * nstar, 3))
+    ux, uy, uz = (torch.from_numpy(np.ascontiguousarray(pu[:, k])).to(dev) for k in range(3))
+
+    def k3u():
+        ctx.grid_interp((n, n, n), nodes, d_or, rec[0], rec[1], 0.37, ux, uy, uz, d_scl, acc, None)
+    med, best = timeit(k3u, flush=flush)
+    moved = ncl * (nstar * (24 + 4 + 24) + 2 * 16 * n ** 3)
+    out["k3_interp_c4_uniform_stars"] = dict(ms_median=med, ms_best=best, bytes_moved_min=moved, gbs_moved=moved / med / 1e6,
+                                             frac_of_hbm_peak_moved=moved / med / 1e6 / HBM_PEAK,
+                                             algorithmic_bytes=ncl * (nstar * 48 + 2 * 3 * 4 * n ** 3),
+                                             gbs=ncl * (nstar * 48 + 2 * 3 * 4 * n ** 3) / med / 1e6)
+
     # ---- K4 ----
     from oc_nbody_b200.synthetic import make_plummer_cluster
     for name, nseg, npc in (("k4_self_gravity_n65536", 1, 65536), ("k4_self_gravity_256x4096", 256, 4096),
