@@ -33,6 +33,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 FLOP_PER_INTERACTION = 20.0  # GPU-Gems-3 ch.31 convention, acc only
+# (workload, grid, sources per GPU) -> DRAM bytes moved by one launch of the streaming kernel (ncu, profiles/)
+NCU_DRAM_BYTES_PER_LAUNCH = {}
 G_KPC = 4.398600413517813e-09
 CENTER = np.array([8.0, 0.0, 0.0])
 HALF = 0.6
@@ -305,8 +307,13 @@ def main():
     nominal = ctx.sm_count * 128 * 2 * ctx.sm_clock_khz * 1e3 / 1e12
     ffma = ctx.probe_throughput(0)
     ffma2 = ctx.probe_throughput(1)
+    # DRAM bytes per launch of the dominant kernel, from the committed ncu capture of this same command
+    # (profiles/r01_ncu_summary.md: dram__bytes_read.sum + dram__bytes_write.sum); not re-measured here
+    traffic = NCU_DRAM_BYTES_PER_LAUNCH.get((args.workload, args.grid, args.n_src_rank))
     roofline = {"bound": "fp32", "achieved": achieved, "peak": nominal, "unit": "TFLOP/s", "frac": achieved / nominal,
-                "traffic": None, "kernel": "direct_sum_kernel", "kernel_ms": k_ms, "kernel_share_of_step": k_ms / ms_per_step,
+                "traffic": traffic, "kernel": "direct_sum_tp_kernel (target-paired, mass-folded tiles; K1 fast set)",
+                "kernel_ms": k_ms, "kernel_share_of_step": k_ms / ms_per_step,
+                "bound_note": "FP32 FMA-pipe bound (north_star: no tensor cores; HBM traffic negligible)",
                 "peak_kind": "nominal FP32: %d SM x 128 lanes x 2 flop x %.3f GHz (MEASURED_PEAKS.json has no FP32 entry)" % (
                     ctx.sm_count, ctx.sm_clock_khz / 1e6),
                 "peak_measured_ffma": ffma, "peak_measured_ffma2": ffma2, "frac_of_measured": achieved / max(ffma, ffma2),
@@ -324,7 +331,7 @@ def main():
     line = {
         "metric": "pairwise_grav_interactions_per_sec", "value": value, "unit": "G/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak" if args.workload == "c2" else "strong",
-        "vs_baseline": None, "dtype": "f32 pair arithmetic, f64 accumulation", "data": "synthetic",
+        "vs_baseline": None, "dtype": "f32", "dtype_note": "f32 pair arithmetic, f64 per-target accumulation", "data": "synthetic",
         "config": workload_config(args, world),
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "G/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

@@ -13,13 +13,19 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CSRC = os.path.join(ROOT, "oc_nbody_b200", "csrc")
 LIBDIR = os.path.join(ROOT, "oc_nbody_b200", "lib")
 LIB = os.path.join(LIBDIR, "liboc_nbody_b200.so")
-SOURCES = ["api.cu", "direct_sum.cu", "self_gravity.cu", "grid_interp.cu"]
+# (object name, source, extra flags); the translation units compile concurrently
+SOURCES = [
+    ("api", "api.cu", []),
+    ("direct_sum", "direct_sum.cu", []),
+    ("self_gravity", "self_gravity.cu", []),
+    ("grid_interp", "grid_interp.cu", []),
+]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC,-O2,-Wall",
-    "--shared",
 ]
+OBJDIR = os.path.join(ROOT, "build", "obj")
 
 
 def _nvcc():
@@ -39,17 +45,27 @@ def _stale(target, deps):
 def build_library(force=False, verbose=False):
     """Compile every CUDA source for sm_100a into LIB. Returns the path."""
     os.makedirs(LIBDIR, exist_ok=True)
-    srcs = [os.path.join(CSRC, s) for s in SOURCES]
-    deps = srcs + [os.path.join(CSRC, "ocg_internal.cuh"), os.path.join(ROOT, "include", "ocg.h")]
-    if not force and not _stale(LIB, deps):
-        return LIB
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + srcs
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if res.returncode != 0:
-        sys.stderr.write(res.stdout + res.stderr)
-        raise RuntimeError("nvcc failed building %s" % LIB)
-    if verbose:
-        sys.stderr.write(res.stderr)
+    os.makedirs(OBJDIR, exist_ok=True)
+    headers = [os.path.join(CSRC, h) for h in ("ocg_internal.cuh", "direct_kernel.cuh")] + [os.path.join(ROOT, "include", "ocg.h")]
+    objs, procs = [], []
+    for name, src, extra in SOURCES:
+        obj = os.path.join(OBJDIR, name + ".o")
+        objs.append(obj)
+        if force or _stale(obj, [os.path.join(CSRC, src)] + headers):
+            cmd = [_nvcc()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, os.path.join(CSRC, src)]
+            procs.append((obj, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)))
+    for obj, pr in procs:  # the translation units compile concurrently
+        out, err = pr.communicate()
+        if pr.returncode != 0:
+            sys.stderr.write(out + err)
+            raise RuntimeError("nvcc failed building %s" % obj)
+        if verbose:
+            sys.stderr.write(err)
+    if procs or force or _stale(LIB, objs):
+        res = subprocess.run([_nvcc(), "--shared", "-o", LIB] + objs, capture_output=True, text=True)
+        if res.returncode != 0:
+            sys.stderr.write(res.stdout + res.stderr)
+            raise RuntimeError("nvcc failed linking %s" % LIB)
     return LIB
 
 

@@ -498,6 +498,34 @@ __global__ void __launch_bounds__(256, 2) probe_contend_kernel(float* out, int i
   if (s == 0x123456789ull || t == 123.456f) out[0] = (float)s + t;
 }
 
+// Register-file operand bandwidth of FFMA2: MODE 0 = three distinct register pairs per instruction (a[k]*b[k]+d[k]),
+// 1 = two distinct pairs + one shared by consecutive instructions (operand reuse cache), 2 = two distinct pairs.
+template <int MODE>
+__global__ void __launch_bounds__(256, 2) probe_rf_kernel(float* out, int iters) {
+  typedef unsigned long long u64;
+  u64 a[8], b[8], d[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    asm("mov.b64 %0, {%1, %2};" : "=l"(a[k]) : "f"(1.0f + threadIdx.x * 1e-9f * (k + 1)), "f"(1.0f - k * 1e-9f));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(b[k]) : "f"(1e-9f * (k + 1) * threadIdx.x), "f"(2e-9f * k));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(d[k]) : "f"(threadIdx.x * 1e-6f + k), "f"(0.5f + k));
+  }
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        if (MODE == 0) asm volatile("fma.rn.ftz.f32x2 %0, %1, %2, %0;" : "+l"(d[k]) : "l"(a[k]), "l"(b[k]));
+        else if (MODE == 1) asm volatile("fma.rn.ftz.f32x2 %0, %1, %2, %0;" : "+l"(d[k]) : "l"(a[k]), "l"(b[0]));
+        else asm volatile("fma.rn.ftz.f32x2 %0, %1, %1, %0;" : "+l"(d[k]) : "l"(a[k]));
+      }
+  }
+  u64 s = 0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) s ^= d[k] ^ a[k] ^ b[k];
+  if (s == 0x123456789ull) out[0] = (float)s;
+}
+
 extern "C" double ocg_probe_throughput(ocg_ctx* ctx, int which) {
   if (!ctx) return -1.0;
   OcgDeviceGuard g(ctx->device);
@@ -520,6 +548,9 @@ extern "C" double ocg_probe_throughput(ocg_ctx* ctx, int which) {
     else if (which == 6) probe_packed_kernel<3><<<grid, block>>>(d_out, iters);
     else if (which == 7) probe_mix_kernel<2><<<ctx->sm_count * 2, block>>>(d_out, iters / 4);
     else if (which == 8) probe_mix_kernel<1><<<ctx->sm_count * 2, block>>>(d_out, iters / 4);
+    else if (which == 20) probe_rf_kernel<0><<<ctx->sm_count * 2, block>>>(d_out, iters);
+    else if (which == 21) probe_rf_kernel<1><<<ctx->sm_count * 2, block>>>(d_out, iters);
+    else if (which == 22) probe_rf_kernel<2><<<ctx->sm_count * 2, block>>>(d_out, iters);
     else if (which == 10) probe_contend_kernel<0><<<ctx->sm_count * 2, block>>>(d_out, iters);
     else if (which == 11) probe_contend_kernel<1><<<ctx->sm_count * 2, block>>>(d_out, iters);
     else if (which == 12) probe_contend_kernel<2><<<ctx->sm_count * 2, block>>>(d_out, iters);
@@ -539,6 +570,7 @@ extern "C" double ocg_probe_throughput(ocg_ctx* ctx, int which) {
     if (which == 0) rate = ops * 2.0 / (ms * 1e-3) / 1e12;        // TFLOP/s
     else if (which == 1 || which == 6) rate = ops * 4.0 / (ms * 1e-3) / 1e12;  // TFLOP/s (2 FMAs per lane-instr)
     else if (which == 2) rate = ops / (ms * 1e-3) / 1e9;                       // G rsqrt/s
+    else if (which >= 20) rate = (double)ctx->sm_count * 2 * block * (double)iters * 64.0 * 4.0 / (ms * 1e-3) / 1e12;
     else if (which >= 10) {
       // FFMA2 TFLOP/s only (48 FFMA2 per iteration, 4 flop per lane-instruction)
       rate = (double)ctx->sm_count * 2 * block * (double)iters * 48.0 * 4.0 / (ms * 1e-3) / 1e12;

@@ -355,8 +355,17 @@ __global__ void __launch_bounds__(OCG_CONSUMER_THREADS + (DED ? 32 : 0), MINB) d
 //   NP      : target pairs per thread (targets per thread = 2*NP; CTA tile = 512*NP targets)
 //   SMEMACC : FP64 accumulators live in shared memory (touched once per tile) instead of registers
 // DBG (timing experiments only, results are wrong): 1 = MUFU.RSQ replaced by an ALU-pipe bit trick,
-// 2 = source registers loaded once per tile instead of per group, 3 = both.
-template <int NP, bool POT, int UNR, int DBG>
+// 2 = source registers loaded once per tile instead of per group, 4 = no MUFU at all, 8 = accumulate FFMA2 with
+// two distinct register pairs instead of three, 16 = mass-folded loop with FADD2 differences (bits combine).
+// MF ("mass-folded", K1 only, !POT): the tile holds w*x | w*y | w*z | w | w^2*e2 with w = (m/M0)^-1/2, so that
+//   d'  = w*xs - w*xt = fma(-xt, w, xs')          3 FFMA2   (instead of 3 FADD2)
+//   r2' = w^2 (r^2 + e2),  r6' = r2'^3            3 FFMA2 + 2 FMUL2
+//   y3  = rsqrt(r6') = w^-3 (r^2+e2)^-3/2         MUFU.RSQ
+//   a  += d' * y3 = (m/M0) d (r^2+e2)^-3/2        3 FFMA2   -- the m*y3 multiply is gone:
+// 11 FMA-pipe operations per interaction instead of 12 (ceiling 20/22 = 91% of FP32 peak instead of 83%).
+// The price is the rounding of xs' = fl(w*xs): relative error 2^-24 |xs|/|d| in d', bounded because every
+// source closer to the target box than the precision radius is in the FP64 NEAR set (direct_sum.cu).
+template <int NP, bool POT, int UNR, int DBG, int MF = 0>
 __device__ __forceinline__ void tile_tpair(const float* __restrict__ stage, const u64 (&ntx)[NP], const u64 (&nty)[NP],
                                            const u64 (&ntz)[NP], u64 (&ax)[NP], u64 (&ay)[NP], u64 (&az)[NP],
                                            u64 (&ap)[NP]) {
@@ -381,12 +390,16 @@ __device__ __forceinline__ void tile_tpair(const float* __restrict__ stage, cons
     for (int q = 0; q < 4; ++q) {
       // duplicated source scalars: ptxas folds them into broadcast (.F32) operands
       const u64 xb = f2_pack(xs[q], xs[q]), yb = f2_pack(ys[q], ys[q]), zb = f2_pack(zs[q], zs[q]);
-      const u64 mb = f2_pack(ms[q], ms[q]), eb = f2_pack(es[q], es[q]);
+      // MF == 2: the w array of the tile is stored with adjacent sources swapped, so that w comes from a register
+      // of the opposite bank parity to w*x, w*y, w*z (LDS.128 puts source q of every component in R(4k+q))
+      const float mq = MF == 2 ? ms[q ^ 1] : ms[q];
+      const u64 mb = f2_pack(mq, mq), eb = f2_pack(es[q], es[q]);
 #pragma unroll
       for (int p = 0; p < NP; ++p) {
-        const u64 dx = f2_add(ntx[p], xb);
-        const u64 dy = f2_add(nty[p], yb);
-        const u64 dz = f2_add(ntz[p], zb);
+        const bool dfma = MF && !(DBG & 16);
+        const u64 dx = dfma ? f2_fma(ntx[p], mb, xb) : f2_add(ntx[p], xb);
+        const u64 dy = dfma ? f2_fma(nty[p], mb, yb) : f2_add(nty[p], yb);
+        const u64 dz = dfma ? f2_fma(ntz[p], mb, zb) : f2_add(ntz[p], zb);
         u64 r2 = f2_fma(dx, dx, eb);
         r2 = f2_fma(dy, dy, r2);
         r2 = f2_fma(dz, dz, r2);
@@ -394,24 +407,32 @@ __device__ __forceinline__ void tile_tpair(const float* __restrict__ stage, cons
         float r6a, r6b;
         f2_unpack(r6, r6a, r6b);
         u64 y3;
-        if (DBG & 1) {
+        if (DBG & 4) {
+          y3 = r6;
+        } else if (DBG & 1) {
           y3 = f2_pack(__int_as_float(0x5f3759df - (__float_as_int(r6a) >> 1)),
                        __int_as_float(0x5f3759df - (__float_as_int(r6b) >> 1)));
         } else {
           y3 = f2_pack(rsqrt_approx(r6a), rsqrt_approx(r6b));
         }
-        const u64 sc = f2_mul(y3, mb);
+        const u64 sc = MF ? y3 : f2_mul(y3, mb);
         if (POT) ap[p] = f2_fma(sc, r2, ap[p]);
-        ax[p] = f2_fma(dx, sc, ax[p]);
-        ay[p] = f2_fma(dy, sc, ay[p]);
-        az[p] = f2_fma(dz, sc, az[p]);
+        if (DBG & 8) {  // two distinct register pairs per instruction instead of three
+          ax[p] = f2_fma(dx, ax[p], ax[p]);
+          ay[p] = f2_fma(dy, ay[p], ay[p]);
+          az[p] = f2_fma(sc, az[p], az[p]);
+        } else {
+          ax[p] = f2_fma(dx, sc, ax[p]);
+          ay[p] = f2_fma(dy, sc, ay[p]);
+          az[p] = f2_fma(dz, sc, az[p]);
+        }
       }
     }
   }
 }
 
 //   NW      : consumer warps per CTA (CTA = 32*NW threads; CTA tile = 64*NW*NP targets)
-template <int NP, bool POT, bool SMEMACC, int MINB, int UNR, int NW = OCG_CONSUMER_WARPS, int DBG = 0>
+template <int NP, bool POT, bool SMEMACC, int MINB, int UNR, int NW = OCG_CONSUMER_WARPS, int DBG = 0, int MF = 0>
 __global__ void __launch_bounds__(32 * NW, MINB) direct_sum_tp_kernel(const DirectParams p) {
   constexpr int NTHR = 32 * NW;
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -484,7 +505,7 @@ __global__ void __launch_bounds__(32 * NW, MINB) direct_sum_tp_kernel(const Dire
       u64 ax[NP], ay[NP], az[NP], ap[NP];
 #pragma unroll
       for (int pp = 0; pp < NP; ++pp) ax[pp] = ay[pp] = az[pp] = ap[pp] = 0ull;
-      tile_tpair<NP, POT, UNR, DBG>(stage_base + s * OCG_TILE_FLOATS, ntx, nty, ntz, ax, ay, az, ap);
+      tile_tpair<NP, POT, UNR, DBG, MF>(stage_base + s * OCG_TILE_FLOATS, ntx, nty, ntz, ax, ay, az, ap);
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty_bar[s]);
       // fold this tile's FP32 sums into the FP64 accumulators (lane lo -> target 2p, hi -> target 2p+1)

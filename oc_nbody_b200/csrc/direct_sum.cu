@@ -36,6 +36,7 @@
 // target box mapped into (0.5, 1].  misc scratch layout (32 ints):
 //   [0..5]  target bbox as ordered ints: min xyz, max xyz (unscaled)
 //   [8] n_fast  [9] n_near  [10] n_fast_tiles  [11] scale (float bits)  [12] D^2 scaled (float bits)
+//   [13] M0 (float bits): power of two >= the largest source mass (mass-folded tiles, see tile_tpair MF)
 //   [16..31] histogram: hist[b] = #sources with scaled box distance < 0.5 * 2^-b
 #define MISC_BBOX 0
 #define MISC_NFAST 8
@@ -43,11 +44,13 @@
 #define MISC_NFAST_TILES 10
 #define MISC_SCALE 11
 #define MISC_D2 12
+#define MISC_M0 13
 #define MISC_HIST 16
 #define MISC_NBINS 12
 #define MISC_INTS 32
 
 #define R2_MIN_SCALED 1e-12f  /* r^6 >= 1e-36 stays a normal FP32 number */
+#define R2_MAX_FOLDED 1e12f   /* mass-folded r'^6 <= 1e36 stays finite */
 
 __device__ __forceinline__ int float_to_ordered(float f) {
   int i = __float_as_int(f);
@@ -113,6 +116,17 @@ __device__ __forceinline__ float box_dist2_scaled(float x, float y, float z, con
   return dx * dx + dy * dy + dz * dz;
 }
 
+// scaled squared distance from a source to the farthest corner of the target box
+__device__ __forceinline__ float box_far2_scaled(float x, float y, float z, const int* misc, float sc) {
+  float bx0 = ordered_to_float(misc[MISC_BBOX + 0]), by0 = ordered_to_float(misc[MISC_BBOX + 1]);
+  float bz0 = ordered_to_float(misc[MISC_BBOX + 2]), bx1 = ordered_to_float(misc[MISC_BBOX + 3]);
+  float by1 = ordered_to_float(misc[MISC_BBOX + 4]), bz1 = ordered_to_float(misc[MISC_BBOX + 5]);
+  float dx = fmaxf(fabsf(x - bx0), fabsf(x - bx1)) * sc;
+  float dy = fmaxf(fabsf(y - by0), fabsf(y - by1)) * sc;
+  float dz = fmaxf(fabsf(z - bz0), fabsf(z - bz1)) * sc;
+  return dx * dx + dy * dy + dz * dz;
+}
+
 // (a)-type criterion only: must this source be handled pair by pair?
 __device__ __forceinline__ bool source_must_be_near(float d2, float soft_scaled, int kernel) {
   const float e2 = soft_scaled * soft_scaled;
@@ -120,18 +134,34 @@ __device__ __forceinline__ bool source_must_be_near(float d2, float soft_scaled,
   return !(e2 > R2_MIN_SCALED || d2 > R2_MIN_SCALED);
 }
 
+// mass-folded tiles only: w^2 = M0/m >= 1 multiplies every r^2 the kernel forms; the source must have a
+// positive mass and its folded r'^6 must stay finite for the farthest target (the near side is covered by
+// source_must_be_near because w^2 >= 1).
+__device__ __forceinline__ bool source_unfoldable(float x, float y, float z, float m, float soft_scaled, int kernel,
+                                                  const int* misc, float sc) {
+  if (!(m > 0.f)) return true;
+  const float w2 = __int_as_float(misc[MISC_M0]) / m;
+  const float e2 = kernel == OCG_KERNEL_PLUMMER ? soft_scaled * soft_scaled : 0.f;
+  return !(w2 * (box_far2_scaled(x, y, z, misc, sc) + e2) < R2_MAX_FOLDED);
+}
+
 #define CLS_BLOCK 1024
 
 // distance histogram of the sources that are not already NEAR by criterion (a)
+// Also reduces the largest finite positive source mass into misc[MISC_M0] (positive floats order as ints).
 __global__ void __launch_bounds__(CLS_BLOCK) classify_hist_kernel(
     const float4* __restrict__ src, const float* __restrict__ soft, long long n, int kernel, int* misc) {
   __shared__ int h[MISC_NBINS];
+  __shared__ int mmax;
   if (threadIdx.x < MISC_NBINS) h[threadIdx.x] = 0;
+  if (threadIdx.x == 0) mmax = 0;
   __syncthreads();
   const float sc = __int_as_float(misc[MISC_SCALE]);
   long long i = blockIdx.x * (long long)CLS_BLOCK + threadIdx.x;
+  int mbits = 0;
   if (i < n) {
     float4 S = src[i];
+    if (S.w > 0.f && isfinite(S.w)) mbits = __float_as_int(S.w);
     float d2 = box_dist2_scaled(S.x, S.y, S.z, misc, sc);
     if (!source_must_be_near(d2, (soft ? soft[i] : 0.f) * sc, kernel)) {
       // largest b with d < 0.5 * 2^-b  <=>  d2 < 0.25 * 4^-b
@@ -139,36 +169,49 @@ __global__ void __launch_bounds__(CLS_BLOCK) classify_hist_kernel(
       for (int b = 0; b < MISC_NBINS && d2 < lim; ++b, lim *= 0.25f) atomicAdd(&h[b], 1);
     }
   }
+  for (int o = 16; o > 0; o >>= 1) mbits = max(mbits, __shfl_xor_sync(0xffffffffu, mbits, o));
+  if ((threadIdx.x & 31) == 0 && mbits) atomicMax(&mmax, mbits);
   __syncthreads();
   if (threadIdx.x < MISC_NBINS && h[threadIdx.x]) atomicAdd(&misc[MISC_HIST + threadIdx.x], h[threadIdx.x]);
+  if (threadIdx.x == 0 && mmax) atomicMax(&misc[MISC_M0], mmax);
 }
 
-__global__ void choose_radius_kernel(int* misc, int cap) {
+// precise == 0: no precision radius (criterion (a) only).  Rounds M0 up to a power of two.
+__global__ void choose_radius_kernel(int* misc, int cap, int precise) {
   float d2 = 0.f, lim = 0.25f;
-  for (int b = 0; b < MISC_NBINS; ++b, lim *= 0.25f)
+  for (int b = 0; precise && b < MISC_NBINS; ++b, lim *= 0.25f)
     if (misc[MISC_HIST + b] <= cap) {
       d2 = lim;
       break;
     }
   misc[MISC_D2] = __float_as_int(d2);
+  float m0 = __int_as_float(misc[MISC_M0]);
+  if (!(m0 > 0.f)) m0 = 1.f;
+  int e;
+  const float f = frexpf(m0, &e);  // m0 = f * 2^e, f in [0.5, 1)
+  m0 = ldexpf(1.0f, f > 0.5f ? e : e - 1);
+  if (!(m0 > 0.f) || !isfinite(m0)) m0 = 1.f;
+  misc[MISC_M0] = __float_as_int(m0);
 }
 
-__device__ __forceinline__ bool source_is_fast(float x, float y, float z, float soft, int kernel, const int* misc) {
+__device__ __forceinline__ bool source_is_fast(float x, float y, float z, float m, float soft, int kernel,
+                                               const int* misc, int mf) {
   const float sc = __int_as_float(misc[MISC_SCALE]);
   const float d2 = box_dist2_scaled(x, y, z, misc, sc);
   if (source_must_be_near(d2, soft * sc, kernel)) return false;
+  if (mf && source_unfoldable(x, y, z, m, soft * sc, kernel, misc, sc)) return false;
   return !(d2 < __int_as_float(misc[MISC_D2]));
 }
 
 __global__ void __launch_bounds__(CLS_BLOCK) classify_count_kernel(
     const float4* __restrict__ src, const float* __restrict__ soft, long long n, int kernel,
-    const int* __restrict__ misc, int* __restrict__ counts) {
+    const int* __restrict__ misc, int* __restrict__ counts, int mf) {
   __shared__ int wsum[CLS_BLOCK / 32];
   long long i = blockIdx.x * (long long)CLS_BLOCK + threadIdx.x;
   bool fast = false;
   if (i < n) {
     float4 S = src[i];
-    fast = source_is_fast(S.x, S.y, S.z, soft ? soft[i] : 0.f, kernel, misc);
+    fast = source_is_fast(S.x, S.y, S.z, S.w, soft ? soft[i] : 0.f, kernel, misc, mf);
   }
   unsigned b = __ballot_sync(0xffffffffu, fast);
   if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = __popc(b);
@@ -225,7 +268,7 @@ __global__ void __launch_bounds__(1024) classify_scan_kernel(int* counts, int nb
 __global__ void __launch_bounds__(CLS_BLOCK) classify_scatter_kernel(
     const float4* __restrict__ src, const float* __restrict__ soft, long long n, int kernel,
     const int* __restrict__ misc, const int* __restrict__ fast_off, float* __restrict__ tiles,
-    float4* __restrict__ near_xyzm, float* __restrict__ near_soft) {
+    float4* __restrict__ near_xyzm, float* __restrict__ near_soft, int mf) {
   __shared__ int wbase[CLS_BLOCK / 32];
   long long i = blockIdx.x * (long long)CLS_BLOCK + threadIdx.x;
   bool valid = i < n, fast = false;
@@ -234,7 +277,7 @@ __global__ void __launch_bounds__(CLS_BLOCK) classify_scatter_kernel(
   if (valid) {
     S = src[i];
     h = soft ? soft[i] : 0.f;
-    fast = source_is_fast(S.x, S.y, S.z, h, kernel, misc);
+    fast = source_is_fast(S.x, S.y, S.z, S.w, h, kernel, misc, mf);
   }
   unsigned b = __ballot_sync(0xffffffffu, fast);
   int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -263,11 +306,21 @@ __global__ void __launch_bounds__(CLS_BLOCK) classify_scatter_kernel(
     // Plummer sources whose scaled e2 is negligible are far enough (d2 > R2_MIN) to drop it too
     float hs = h * sc;
     float e2 = kernel == OCG_KERNEL_PLUMMER ? hs * hs : 0.f;
-    T[j] = S.x * sc;
-    T[OCG_TS + j] = S.y * sc;
-    T[2 * OCG_TS + j] = S.z * sc;
-    T[3 * OCG_TS + j] = S.w;
-    T[4 * OCG_TS + j] = e2;
+    if (mf) {
+      // mass-folded record: w = (m/M0)^-1/2 (M0 a power of two: m/M0 is exact), coordinates and e2 carry it
+      const float w = (float)rsqrt((double)(S.w / __int_as_float(misc[MISC_M0])));
+      T[j] = (S.x * sc) * w;
+      T[OCG_TS + j] = (S.y * sc) * w;
+      T[2 * OCG_TS + j] = (S.z * sc) * w;
+      T[3 * OCG_TS + (mf == 2 ? (j ^ 1) : j)] = w;
+      T[4 * OCG_TS + j] = (e2 * w) * w;
+    } else {
+      T[j] = S.x * sc;
+      T[OCG_TS + j] = S.y * sc;
+      T[2 * OCG_TS + j] = S.z * sc;
+      T[3 * OCG_TS + j] = S.w;
+      T[4 * OCG_TS + j] = e2;
+    }
   } else {
     long long pos = (block_start - foff) + (threadIdx.x - rank_fast);
     near_xyzm[pos] = S;
@@ -275,8 +328,9 @@ __global__ void __launch_bounds__(CLS_BLOCK) classify_scatter_kernel(
   }
 }
 
-// Pad the tail of the last fast tile with zero-mass sources (contribute exactly 0).
-__global__ void pad_tiles_kernel(float* tiles, const int* misc) {
+// Pad the tail of the last fast tile with zero-mass sources (contribute exactly 0; in the mass-folded
+// layout the same record reads w = 0, w*x = 0, w^2*e2 = 1: d' = 0, y3 = 1, d'*y3 = 0).
+__global__ void pad_tiles_kernel(float* tiles, const int* misc, int mf) {
   int nf = misc[MISC_NFAST];
   int nt = misc[MISC_NFAST_TILES];
   long long end = (long long)nt * OCG_TS;
@@ -285,7 +339,7 @@ __global__ void pad_tiles_kernel(float* tiles, const int* misc) {
     int j = (int)(pos - tile * OCG_TS);
     float* T = tiles + tile * (long long)OCG_TILE_FLOATS;
     T[j] = 0.f, T[OCG_TS + j] = 0.f, T[2 * OCG_TS + j] = 0.f;
-    T[3 * OCG_TS + j] = 0.f;
+    T[3 * OCG_TS + (mf == 2 ? (j ^ 1) : j)] = 0.f;  // pair-swizzled w array: the pad owns slot j^1, not j
     T[4 * OCG_TS + j] = 1.f;
   }
 }
@@ -295,10 +349,11 @@ __global__ void pad_tiles_kernel(float* tiles, const int* misc) {
 // (partials are in scaled units: acc' = acc / s^2, phi' = phi / s.)
 __global__ void finish_kernel(const double* __restrict__ partial, long long stride, int n_slots,
                               int nc_partial, double G, const int* __restrict__ misc, long long n_tgt,
-                              double* __restrict__ acc, double* __restrict__ pot, int accumulate) {
+                              double* __restrict__ acc, double* __restrict__ pot, int accumulate, int mf) {
   long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (t >= n_tgt) return;
   const double sc = (double)__int_as_float(misc[MISC_SCALE]);
+  if (mf) G *= (double)__int_as_float(misc[MISC_M0]);  // mass-folded partials are in units of M0
   for (int c = 0; c < nc_partial; ++c) {
     double s = 0.0;
     for (int k = 0; k < n_slots; ++k) s += partial[((long long)k * nc_partial + c) * stride + t];
@@ -395,6 +450,7 @@ struct DirectVariant {
   direct_fn fn[2][2];
   int smem_acc_comps;  // > 0: FP64 accumulators in shared memory, this many doubles per thread and component
   int nwarps;          // consumer warps per CTA (0 = OCG_CONSUMER_WARPS)
+  int mf;              // consumes mass-folded tiles (K1 without potential only); 2 = w array pair-swizzled
 };
 static inline int variant_threads(const DirectVariant& v) { return 32 * (v.nwarps ? v.nwarps : OCG_CONSUMER_WARPS); }
 #define OCG_FULL(TPT, PACKED, DED, MINB, UNR)                                                            \
@@ -421,6 +477,14 @@ static inline int variant_threads(const DirectVariant& v) { return 32 * (v.nwarp
   {                                                                                                      \
     {direct_sum_tp_kernel<NP, false, SMEMACC, MINB, UNR, NW>, nullptr},                                  \
     { direct_sum_tp_kernel<NP, true, SMEMACC, MINB, UNR, NW>, nullptr }                                  \
+  }
+#define OCG_TPMF(NP, SMEMACC, MINB, UNR, NW)                                                             \
+  {                                                                                                      \
+    {direct_sum_tp_kernel<NP, false, SMEMACC, MINB, UNR, NW, 0, 1>, nullptr}, { nullptr, nullptr }       \
+  }
+#define OCG_TPMFX(NP, SMEMACC, MINB, UNR, NW, DBG, MF)                                                   \
+  {                                                                                                      \
+    {direct_sum_tp_kernel<NP, false, SMEMACC, MINB, UNR, NW, DBG, MF>, nullptr}, { nullptr, nullptr }    \
   }
 #define OCG_TPD(NP, SMEMACC, MINB, UNR, NW, DBG)                                                         \
   {                                                                                                      \
@@ -467,17 +531,50 @@ static const DirectVariant g_variants[] = {
     /* 37 */ {"DBG np4 12w: no MUFU (timing only)", 8, 1, false, OCG_TPD(4, true, 1, 1, 12, 1), 8, 12},
     /* 38 */ {"DBG np4 12w: no LDS (timing only)", 8, 1, false, OCG_TPD(4, true, 1, 1, 12, 2), 8, 12},
     /* 39 */ {"DBG np4 12w: no MUFU, no LDS (timing only)", 8, 1, false, OCG_TPD(4, true, 1, 1, 12, 3), 8, 12},
+    /* 40 */ {"tpair-mf np4 smemacc 12w x minb1", 8, 1, false, OCG_TPMF(4, true, 1, 1, 12), 8, 12, 1},
+    /* 41 */ {"tpair-mf np4 smemacc 4w x minb3", 8, 3, false, OCG_TPMF(4, true, 3, 1, 4), 8, 4, 1},
+    /* 42 */ {"tpair-mf np2 smemacc 8w x minb2", 4, 2, false, OCG_TPMF(2, true, 2, 1, 8), 4, 8, 1},
+    /* 43 */ {"tpair-mf np1 regacc 8w x minb2 unr2", 2, 2, false,
+              {{direct_sum_tp_kernel<1, false, false, 2, 2, OCG_CONSUMER_WARPS, 0, 1>, nullptr}, {nullptr, nullptr}}, 0, 0, 1},
+    /* 44 */ {"tpair-mf np3 smemacc 12w x minb1", 6, 1, false, OCG_TPMF(3, true, 1, 1, 12), 6, 12, 1},
+    /* 45 */ {"tpair-mf np4 smemacc 12w x minb1 unr2", 8, 1, false, OCG_TPMF(4, true, 1, 2, 12), 8, 12, 1},
+    /* 46 */ {"tpair-mf np4 12w, w pair-swizzled", 8, 1, false, OCG_TPMFX(4, true, 1, 1, 12, 0, 2), 8, 12, 2},
+    /* 47 */ {"tpair-mf np2 8w x minb2, w pair-swizzled", 4, 2, false, OCG_TPMFX(2, true, 2, 1, 8, 0, 2), 4, 8, 2},
+    /* 48 */ {"DBG mf np4 12w: no MUFU", 8, 1, false, OCG_TPMFX(4, true, 1, 1, 12, 4, 1), 8, 12, 1},
+    /* 49 */ {"DBG mf np4 12w: 2-pair accumulate", 8, 1, false, OCG_TPMFX(4, true, 1, 1, 12, 8, 1), 8, 12, 1},
+    /* 50 */ {"DBG mf np4 12w: FADD2 differences", 8, 1, false, OCG_TPMFX(4, true, 1, 1, 12, 16, 1), 8, 12, 1},
+    /* 51 */ {"DBG mf np4 12w: no MUFU + 2-pair accumulate", 8, 1, false, OCG_TPMFX(4, true, 1, 1, 12, 12, 1), 8, 12, 1},
+    /* 52 */ {"DBG mf np4 12w: no MUFU + 2-pair + FADD2", 8, 1, false, OCG_TPMFX(4, true, 1, 1, 12, 28, 1), 8, 12, 1},
+    /* 53 */ {"DBG mf np4 12w swizzled: no MUFU", 8, 1, false, OCG_TPMFX(4, true, 1, 1, 12, 4, 2), 8, 12, 2},
+    /* 54 */ {"DBG mf np4 12w swizzled: no MUFU + 2-pair", 8, 1, false, OCG_TPMFX(4, true, 1, 1, 12, 12, 2), 8, 12, 2},
+    /* 55 */ {"DBG plain np4 12w: no MUFU", 8, 1, false, OCG_TPD(4, true, 1, 1, 12, 4), 8, 12},
+    /* 56 */ {"DBG plain np4 12w: 2-pair accumulate", 8, 1, false, OCG_TPD(4, true, 1, 1, 12, 8), 8, 12},
+    /* 57 */ {"DBG plain np4 12w: no MUFU + 2-pair", 8, 1, false, OCG_TPD(4, true, 1, 1, 12, 12), 8, 12},
+    /* 58 */ {"tpair-mf np6 8w x minb1, swizzled", 12, 1, false, OCG_TPMFX(6, true, 1, 1, 8, 0, 2), 12, 8, 2},
+    /* 59 */ {"tpair-mf np8 8w x minb1, swizzled", 16, 1, false, OCG_TPMFX(8, true, 1, 1, 8, 0, 2), 16, 8, 2},
+    /* 60 */ {"tpair-mf np5 12w x minb1, swizzled", 10, 1, false, OCG_TPMFX(5, true, 1, 1, 12, 0, 2), 10, 12, 2},
+    /* 61 */ {"tpair-mf np6 12w x minb1, swizzled", 12, 1, false, OCG_TPMFX(6, true, 1, 1, 12, 0, 2), 12, 12, 2},
+    /* 62 */ {"tpair-mf np4 12w x minb1 unr2, swizzled", 8, 1, false, OCG_TPMFX(4, true, 1, 2, 12, 0, 2), 8, 12, 2},
+    /* 63 */ {"tpair-mf np4 4w x minb3, swizzled", 8, 3, false, OCG_TPMFX(4, true, 3, 1, 4, 0, 2), 8, 4, 2},
+    /* 64 */ {"tpair-mf np3 12w x minb1, swizzled", 6, 1, false, OCG_TPMFX(3, true, 1, 1, 12, 0, 2), 6, 12, 2},
+    /* 65 */ {"tpair-mf np4 16w x minb1, swizzled", 8, 1, false, OCG_TPMFX(4, true, 1, 1, 16, 0, 2), 8, 16, 2},
 };
-#define OCG_N_CORRECT_VARIANTS 37 /* variants >= this are timing experiments with wrong results */
+/* variants 37..39 and 48.. are timing experiments with wrong results */
 static const int g_n_variants = (int)(sizeof(g_variants) / sizeof(g_variants[0]));
 // Production choices (tools/probe.py sweep on B200, profiles/r01_variant_sweep.json):
 #define OCG_VARIANT_BIG 31        /* >= 64k targets: target-paired, 8 targets/thread, 12 warps, 71% of FP32 peak */
+#define OCG_VARIANT_BIG_MF 58     /* the same with mass-folded, w-swizzled tiles (11 FMA-pipe ops per interaction; K1, no potential) */
 #define OCG_VARIANT_MID 27        /* >= 16k targets: target-paired, 2 targets/thread                              */
 #define OCG_VARIANT_MID_GUARD 4   /* source-paired 2 targets/thread (carries the eps2 == 0 guarded form)          */
 #define OCG_VARIANT_SMALL 1       /* few targets: 1 target/thread spreads them over more CTAs (has guard form)    */
 
 static int g_force_variant = -1;  // -1 = heuristic
 static int g_precise_near = 1;    // 0 = no precision radius (criterion (a) only)
+static int g_mass_fold = 1;       // 0 = never pick the mass-folded variant by heuristic
+extern "C" int ocg_debug_set_mass_fold(int on) {
+  g_mass_fold = on;
+  return 0;
+}
 extern "C" int ocg_debug_set_variant(int id) {
   if (id >= g_n_variants) return OCG_ERR_INVALID;
   g_force_variant = id;
@@ -491,11 +588,13 @@ extern "C" int ocg_debug_set_precise_near(int on) {
 
 // n_tgt: targets in the call (or shard); seg_len: typical length of one independent target run (= n_tgt for the
 // field build, the cluster size for batched self-gravity) — a tile never spans two runs.
-int ocg_pick_variant(ocg_ctx* ctx, int64_t n_tgt, int64_t seg_len, bool guard) {
+int ocg_pick_variant(ocg_ctx* ctx, int64_t n_tgt, int64_t seg_len, bool guard, bool allow_mf) {
   (void)ctx;
   if (g_force_variant >= 0) {
-    // a forced variant without the guarded form falls back to the guarded production kernels
-    if (!guard || g_variants[g_force_variant].fn[0][1]) return g_force_variant;
+    // a forced variant without the guarded form falls back to the guarded production kernels; so does a
+    // mass-folded one when the caller lays out plain tiles (K4)
+    if ((!guard || g_variants[g_force_variant].fn[0][1]) && (allow_mf || !g_variants[g_force_variant].mf))
+      return g_force_variant;
   }
   auto waste_ok = [&](int v) {
     const long long ct = (long long)variant_threads(g_variants[v]) * g_variants[v].tpt;
@@ -556,7 +655,10 @@ int ocg_direct_sum_impl(ocg_ctx* ctx, const float* src_xyzm, const float* src_so
     return OCG_OK;
   }
 
-  const int variant = ocg_pick_variant(ctx, n_tgt, n_tgt, /*guard=*/false);
+  int variant = ocg_pick_variant(ctx, n_tgt, n_tgt, /*guard=*/false, /*allow_mf=*/true);
+  if (g_variants[variant].mf && want_pot) variant = OCG_VARIANT_BIG;  // the potential has no mass-folded form
+  else if (variant == OCG_VARIANT_BIG && !want_pot && g_mass_fold && g_force_variant < 0) variant = OCG_VARIANT_BIG_MF;
+  const int mf = g_variants[variant].mf;
   const int tpt = ocg_variant_tpt(variant);
   const int CT = ocg_variant_threads(variant) * tpt;
   const long long n_ttiles = (n_tgt + CT - 1) / CT;
@@ -599,23 +701,23 @@ int ocg_direct_sum_impl(ocg_ctx* ctx, const float* src_xyzm, const float* src_so
   }
   scale_kernel<<<1, 1, 0, st>>>(misc, 1.0f);
   OCG_CHECK_LAUNCH(ctx, "scale_kernel");
-  if (g_precise_near) {
+  if (g_precise_near || mf) {
     classify_hist_kernel<<<(int)n_cls_blocks, CLS_BLOCK, 0, st>>>(src4, src_soft, n_src, kernel, misc);
     OCG_CHECK_LAUNCH(ctx, "classify_hist_kernel");
     // cap the FP64 set at ~0.2% of the sources (>= 4096): its pair cost is ~5x the FP32 one
     long long cap = n_src / 512;
     if (cap < 4096) cap = 4096;
-    choose_radius_kernel<<<1, 1, 0, st>>>(misc, (int)cap);
+    choose_radius_kernel<<<1, 1, 0, st>>>(misc, (int)cap, g_precise_near);
     OCG_CHECK_LAUNCH(ctx, "choose_radius_kernel");
   }
-  classify_count_kernel<<<(int)n_cls_blocks, CLS_BLOCK, 0, st>>>(src4, src_soft, n_src, kernel, misc, counts);
+  classify_count_kernel<<<(int)n_cls_blocks, CLS_BLOCK, 0, st>>>(src4, src_soft, n_src, kernel, misc, counts, mf);
   OCG_CHECK_LAUNCH(ctx, "classify_count_kernel");
   classify_scan_kernel<<<1, 1024, 0, st>>>(counts, (int)n_cls_blocks, n_src, misc);
   OCG_CHECK_LAUNCH(ctx, "classify_scan_kernel");
   classify_scatter_kernel<<<(int)n_cls_blocks, CLS_BLOCK, 0, st>>>(src4, src_soft, n_src, kernel, misc, counts,
-                                                                 tiles, near_xyzm, near_soft);
+                                                                 tiles, near_xyzm, near_soft, mf);
   OCG_CHECK_LAUNCH(ctx, "classify_scatter_kernel");
-  pad_tiles_kernel<<<1, OCG_TS, 0, st>>>(tiles, misc);
+  pad_tiles_kernel<<<1, OCG_TS, 0, st>>>(tiles, misc, mf);
   OCG_CHECK_LAUNCH(ctx, "pad_tiles_kernel");
 
   DirectParams p;
@@ -635,7 +737,7 @@ int ocg_direct_sum_impl(ocg_ctx* ctx, const float* src_xyzm, const float* src_so
 
   {
     long long nb = (n_tgt + 255) / 256;
-    finish_kernel<<<(int)nb, 256, 0, st>>>(partial, n_tgt, (int)n_chunks, NC, G, misc, n_tgt, acc, pot, accumulate);
+    finish_kernel<<<(int)nb, 256, 0, st>>>(partial, n_tgt, (int)n_chunks, NC, G, misc, n_tgt, acc, pot, accumulate, mf);
     OCG_CHECK_LAUNCH(ctx, "finish_kernel");
     long long nbn = (n_tgt + NEAR_BLOCK - 1) / NEAR_BLOCK;
     near_sum_kernel<<<(int)nbn, NEAR_BLOCK, 0, st>>>(near_xyzm, near_soft, misc, tgt4, n_tgt, kernel, G, acc, pot);

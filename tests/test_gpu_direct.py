@@ -108,24 +108,84 @@ def test_field_direct_edge_cases(ctx):
         assert rel_err_scalar(pot, pref) <= TOL
 
 
-N_VARIANTS = 37
+# ids 37..39 and 48..57 are timing experiments with wrong results; 40..47 consume mass-folded tiles (no potential form)
+PLAIN_VARIANTS = list(range(37))
+MASS_FOLDED_VARIANTS = list(range(40, 48)) + list(range(58, 66))
 
 
-@pytest.mark.parametrize("variant", list(range(N_VARIANTS)))
+@pytest.mark.parametrize("variant", PLAIN_VARIANTS + MASS_FOLDED_VARIANTS)
 def test_field_direct_variants(ctx, variant):
     """Every compiled tuning variant of the streaming kernel (targets/thread, packed vs scalar FP32,
-    dedicated vs in-line TMA producer, occupancy bound, unroll)."""
+    dedicated vs in-line TMA producer, occupancy bound, unroll, plain vs mass-folded tiles)."""
     rng = np.random.default_rng(21)
     src, soft = random_sources(rng, 11000, box=2.0)
     tgt = grid_targets(11)
+    want_pot = variant in PLAIN_VARIANTS
     ref, pref = oracle.field_direct(src, soft, tgt, oracle.KERNEL_PLUMMER, G, want_pot=True)
-    assert ctx.lib.ocg_debug_set_variant(variant) >= N_VARIANTS  # ids beyond N_VARIANTS are timing experiments
+    assert ctx.lib.ocg_debug_set_variant(variant) > max(MASS_FOLDED_VARIANTS)
     try:
-        acc, pot = run_k1(ctx, src, soft, tgt, oracle.KERNEL_PLUMMER, want_pot=True)
+        acc, pot = run_k1(ctx, src, soft, tgt, oracle.KERNEL_PLUMMER, want_pot=want_pot)
     finally:
         ctx.lib.ocg_debug_set_variant(-1)
     assert rel_err(acc, ref) <= TOL
+    if want_pot:
+        assert rel_err_scalar(pot, pref) <= TOL
+
+
+@pytest.mark.parametrize("kernel", [oracle.KERNEL_PLUMMER, oracle.KERNEL_SPLINE])
+def test_field_direct_mass_folded_edge_masses(ctx, kernel):
+    """Mass-folded tiles (w = (m/M0)^-1/2 folded into the coordinates): masses spanning 12 decades, zero and
+    negative masses (FP64 near set), sources far enough that w^2 r^2 would overflow (also near set), sources
+    inside the target box."""
+    rng = np.random.default_rng(77)
+    src, soft = random_sources(rng, 9000, box=1.5)
+    src[:, 3] = np.exp(rng.uniform(np.log(1e-4), np.log(1e8), src.shape[0])).astype(np.float32)
+    src[::97, 3] = 0.0
+    src[5::211, 3] *= -1.0
+    src[7::301, :3] *= 3.0e4          # tiny masses at huge distances: folded r^6 leaves the FP32 range
+    src[7::301, 3] = 1e-3
+    tgt = grid_targets(7)
+    ref = oracle.field_direct(src, soft, tgt, kernel, G)
+    for variant in (40, 43, 46, 58):
+        ctx.lib.ocg_debug_set_variant(variant)
+        try:
+            acc, _ = run_k1(ctx, src, soft, tgt, kernel)
+        finally:
+            ctx.lib.ocg_debug_set_variant(-1)
+        assert np.all(np.isfinite(acc))
+        assert rel_err(acc, ref) <= TOL
+
+
+@pytest.mark.parametrize("variant", [46, 58])
+@pytest.mark.parametrize("n_src", [511, 513, 1000, 1025, 1537])
+def test_field_direct_swizzled_tiles_ragged_tail(ctx, variant, n_src):
+    """The w array of a mass-folded tile is stored with adjacent sources swapped; odd and even source counts must
+    leave the last real source's w intact when the tail of the tile is padded."""
+    rng = np.random.default_rng(n_src)
+    src, soft = random_sources(rng, n_src, box=2.0)
+    src[:, :3] += np.float32(3.0)  # every source outside the precision radius: all of them in the FP32 tiles
+    tgt = grid_targets(5)
+    ref = oracle.field_direct(src, soft, tgt, oracle.KERNEL_PLUMMER, G)
+    ctx.lib.ocg_debug_set_variant(variant)
+    try:
+        acc, _ = run_k1(ctx, src, soft, tgt, oracle.KERNEL_PLUMMER)
+    finally:
+        ctx.lib.ocg_debug_set_variant(-1)
+    assert rel_err(acc, ref) <= TOL
+
+
+def test_field_direct_production_big_is_mass_folded(ctx):
+    """>= 64k targets without potential takes the mass-folded kernel; with potential the plain one; both agree
+    with the oracle and with each other to the parity tolerance."""
+    rng = np.random.default_rng(5)
+    src, soft = random_sources(rng, 2100, box=2.0)
+    tgt = grid_targets(41)
+    ref, pref = oracle.field_direct(src, soft, tgt, oracle.KERNEL_PLUMMER, G, want_pot=True)
+    a_mf, _ = run_k1(ctx, src, soft, tgt, oracle.KERNEL_PLUMMER, want_pot=False)
+    a_pl, pot = run_k1(ctx, src, soft, tgt, oracle.KERNEL_PLUMMER, want_pot=True)
+    assert rel_err(a_mf, ref) <= TOL and rel_err(a_pl, ref) <= TOL
     assert rel_err_scalar(pot, pref) <= TOL
+    assert not np.array_equal(a_mf, a_pl)  # two different kernels really ran
 
 
 def test_frame_subtract_and_host_form(ctx):

@@ -36,9 +36,12 @@ def main():
     ctx.set_kernel_timing(True)
     res = []
     nvar = ctx.lib.ocg_debug_set_variant(-1)
+    only = [int(x) for x in os.environ.get("OCG_PROBE_VARIANTS", "").split(",") if x]
     for kernel, want_pot in ((0, False), (0, True), (1, False)):
         for v in range(nvar):
             if (want_pot or kernel == 1) and v > 1:
+                continue
+            if only and v not in only:
                 continue
             ctx.lib.ocg_debug_set_variant(v)
             best = 1e30

@@ -6,4 +6,6 @@ names = ["FFMA (TFLOP/s)", "FFMA2 (TFLOP/s)", "MUFU.RSQ (G/s)", "FADD2 (TFLOP/s,
 out = {n: ctx.probe_throughput(i) for i, n in enumerate(names)}
 for i, n in ((10, "FFMA2 alone (2 CTA x 256)"), (11, "FFMA2 + 5 LDS.128 per 48"), (12, "FFMA2 + 10 LDS.128 per 48"), (13, "FFMA2 + 8 MUFU per 48"), (14, "FFMA2 + 10 LDS.128 + 8 MUFU per 48")):
     out[n] = ctx.probe_throughput(i)
+for i, n in ((20, "FFMA2 three distinct register pairs"), (21, "FFMA2 two distinct pairs + one reused"), (22, "FFMA2 two distinct pairs")):
+    out[n] = ctx.probe_throughput(i)
 print(json.dumps(out, indent=1))
