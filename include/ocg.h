@@ -149,6 +149,30 @@ int ocg_grid_interp_multi(ocg_ctx* ctx, const ocg_grid_desc* grid, const float* 
                           const int32_t* star_cluster_dev, int64_t n_star, double* acc_out_dev,
                           double* pot_out_dev, int32_t* cell_out_dev, void* stream);
 
+/* Two-level form: the reference's nested fine grid (grid.add_fine_grid, grid_cartesian.py:34-53,71-91; its default
+ * configuration, test_options:93-100).  A star inside the closed fine box [node2[0]+o, node2[n2-1]+o]^3 is
+ * interpolated on the fine lattice, any other star on the coarse one (whose points inside the fine box, dropped by
+ * grid_cartesian.py:71-81, are filled in from the fine lattice when the records are laid out).  `fine` shares
+ * n_cluster and origin_dev with `coarse`; fine == NULL (and rec_fine_dev == NULL) is the single-level call.
+ * rec_*_dev: HOST arrays of n_rec device pointers; weights: HOST array [n_rec].
+ * tensor_out_dev: fp64 [9][n_star] or NULL — tensor[3*i + j][s] = d a_j / d x_i of the interpolant at star s, the
+ *   T[i][j] of get_tidal_tensor_at_point (gizmo_interface.py:719-756), in acceleration units per length unit.
+ * level_out_dev: int32 [n_star] or NULL — 0 coarse, 1 fine.                                              */
+int ocg_grid_interp_nested(ocg_ctx* ctx, const ocg_grid_desc* coarse, const ocg_grid_desc* fine,
+                           const float* const* rec_coarse_dev, const float* const* rec_fine_dev,
+                           const double* weights, int32_t n_rec, const double* star_x_dev,
+                           const double* star_y_dev, const double* star_z_dev,
+                           const int32_t* star_cluster_dev, int64_t n_star, double* acc_out_dev,
+                           double* pot_out_dev, double* tensor_out_dev, int32_t* level_out_dev,
+                           int32_t* cell_out_dev, void* stream);
+
+/* K2 pack with a scatter: rec[index[i]] = float4(acc[0][i], acc[1][i], acc[2][i], pot[i]) for i < n.
+ * Lays rows of the reference's point list (kept coarse points | fine lattice | origin row,
+ * grid_cartesian.py:71-91) out as full-lattice node records.  acc_dev fp64 [3][n]; pot_dev [n] or NULL;
+ * index_dev int64 [n].                                                                                    */
+int ocg_pack_planes_indexed(ocg_ctx* ctx, const double* acc_dev, const double* pot_dev, int64_t n,
+                            const int64_t* index_dev, float* rec_dev, void* stream);
+
 /* ---- K4: cluster self-gravity (ph4 force loop behind oc_code.py:218-229) ---------------------
  * Plummer direct sum inside each segment (cluster) of a batch.
  * pos_dev fp64 [3][n] component-major, mass_dev fp64 [n]; seg_offsets_host int64 [n_seg+1]

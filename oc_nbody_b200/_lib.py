@@ -20,7 +20,7 @@ ABI_SYMBOLS = [
     "ocg_version", "ocg_create", "ocg_destroy", "ocg_last_error", "ocg_device_info", "ocg_launch_count",
     "ocg_last_direct_kernel_ms", "ocg_set_kernel_timing", "ocg_recentre_f64", "ocg_cast_f64_f32",
     "ocg_field_direct", "ocg_frame_subtract", "ocg_field_build_host", "ocg_pack_planes", "ocg_grid_time_blend",
-    "ocg_grid_interp", "ocg_grid_interp_multi", "ocg_self_gravity", "ocg_kick", "ocg_drift", "ocg_axpy", "ocg_probe_throughput",
+    "ocg_grid_interp", "ocg_grid_interp_multi", "ocg_grid_interp_nested", "ocg_pack_planes_indexed", "ocg_self_gravity", "ocg_kick", "ocg_drift", "ocg_axpy", "ocg_probe_throughput",
 ]
 
 
@@ -67,6 +67,9 @@ def load_library():
     L.ocg_grid_interp.argtypes = [vp, ctypes.POINTER(_GridDesc), vp, vp, dbl, vp, vp, vp, vp, i64, vp, vp, vp, vp]
     L.ocg_grid_interp_multi.argtypes = [vp, ctypes.POINTER(_GridDesc), vp, ctypes.POINTER(dbl), i32, vp, vp, vp, vp, i64, vp, vp,
                                         vp, vp]
+    L.ocg_grid_interp_nested.argtypes = [vp, ctypes.POINTER(_GridDesc), ctypes.POINTER(_GridDesc), vp, vp, ctypes.POINTER(dbl),
+                                         i32, vp, vp, vp, vp, i64, vp, vp, vp, vp, vp, vp]
+    L.ocg_pack_planes_indexed.argtypes = [vp, vp, vp, i64, vp, vp, vp]
     L.ocg_self_gravity.argtypes = [vp, vp, vp, i64, vp, i32, dbl, dbl, i64, i64, vp, vp, vp]
     L.ocg_kick.argtypes = [vp, vp, vp, i64, dbl, vp]
     L.ocg_drift.argtypes = [vp, vp, vp, i64, dbl, dbl, vp]
@@ -204,6 +207,41 @@ class Context:
         self._ck(self.lib.ocg_grid_interp_multi(self.h, ctypes.byref(d), ptrs, w, len(recs), _dptr(sx), _dptr(sy), _dptr(sz),
                                                 _dptr(star_cluster), sx.shape[0], _dptr(acc_out), _dptr(pot_out), None,
                                                 self._stream()), "ocg_grid_interp_multi")
+
+    @staticmethod
+    def _grid_desc(n, nodes, origin):
+        d = _GridDesc()
+        for k in range(3):
+            d.n[k] = int(n[k])
+            d.node_dev[k] = nodes[k].data_ptr()
+        d.n_cluster = int(origin.shape[0])
+        d.origin_dev = origin.data_ptr()
+        return d
+
+    def grid_interp_nested(self, n, nodes, origin, recs, weights, sx, sy, sz, star_cluster, acc_out, pot_out=None,
+                           fine_n=None, fine_nodes=None, recs_fine=None, tensor_out=None, level_out=None, cell_out=None):
+        """K3 on the reference's two-level grid (fine_* None: single level) with optional tidal tensor [9, n_star],
+        level and cell outputs."""
+        dc = self._grid_desc(n, nodes, origin)
+        ptrs = (ctypes.c_void_p * len(recs))(*[_dptr(r).value for r in recs])
+        w = (ctypes.c_double * len(recs))(*[float(x) for x in weights])
+        if fine_n is not None:
+            df = self._grid_desc(fine_n, fine_nodes, origin)
+            if recs_fine is None or len(recs_fine) != len(recs):
+                raise OcgError("grid_interp_nested: need as many fine as coarse record planes")
+            fptrs = (ctypes.c_void_p * len(recs))(*[_dptr(r).value for r in recs_fine])
+            dfp = ctypes.byref(df)
+        else:
+            fptrs, dfp = None, None
+        self._ck(self.lib.ocg_grid_interp_nested(self.h, ctypes.byref(dc), dfp, ptrs, fptrs, w, len(recs), _dptr(sx), _dptr(sy),
+                                                 _dptr(sz), _dptr(star_cluster), sx.shape[0], _dptr(acc_out), _dptr(pot_out),
+                                                 _dptr(tensor_out), _dptr(level_out), _dptr(cell_out), self._stream()),
+                 "ocg_grid_interp_nested")
+
+    def pack_planes_indexed(self, acc, pot, index, rec):
+        """rec[index[i]] = float4(acc[:, i], pot[i]) (K2 pack with a scatter)."""
+        self._ck(self.lib.ocg_pack_planes_indexed(self.h, _dptr(acc), _dptr(pot), acc.shape[1], _dptr(index), _dptr(rec),
+                                                  self._stream()), "ocg_pack_planes_indexed")
 
     def self_gravity(self, pos, mass, eps2, G, acc, pot=None, seg_offsets=None, tgt_begin=0, tgt_end=None):
         n = pos.shape[1]

@@ -75,6 +75,10 @@ struct InterpParams {
   const float4* rec[4];  // 1..4 record planes blended in time (2: linear bracket, 4: cubic B-spline coefficients)
   float w[4];            // their FP32 weights (the time blend is FP32 arithmetic)
   int n_rec;
+  // nested fine lattice (grid_cartesian.py:34-53,71-91) sharing origin and weights; n2[0] == 0: single level
+  int n2[3];
+  const double* node2[3];
+  const float4* rec2[4];
   const double* sx;
   const double* sy;
   const double* sz;
@@ -82,7 +86,9 @@ struct InterpParams {
   long long n_star;
   double* acc;
   double* pot;
+  double* tensor;  // [9][n_star]: tensor[3*i + j] = d a_j / d x_i (gizmo_interface.py:719-756), or NULL
   int* cell;
+  int* level;      // [n_star]: 0 coarse, 1 fine, or NULL
 };
 
 // Cell along one axis: i = searchsorted(node + o, x, side='right') - 1, clamped to [0, n-2].
@@ -107,97 +113,137 @@ __device__ __forceinline__ float lerp_rn_f(float a, float wa, float b, float wb)
   return __fadd_rn(__fmul_rn(a, wa), __fmul_rn(b, wb));
 }
 
-// One thread per star.  Arithmetic contract (identical in oracle/ocg_oracle.c: oracle_grid_interp):
+// One thread per star.  Arithmetic contract (identical in oracle/ocg_oracle.c: grid_interp_core):
+//   level     : (nested only) fine iff node2[0] + o <= x <= node2[n2-1] + o on all three axes        FP64 compares
 //   cell      : FP64 comparisons against node[i] + origin (bit-exact searchsorted)
 //   weight    : t = (x - (node[i] + origin)) * inv[i],  inv[i] = 1 / (node[i+1] - node[i])      FP64
 //   time blend: v = a*(1-w) + b*w on the FP32 records, every op rounded to FP32               FP32
 //   trilinear : z, then y, then x lerps of the 8 corner values, every op rounded to FP64        FP64
+//   tensor    : derivative of that trilinear form: differences of the z / y / x stage values times inv[i]
 // SMEM_NODES: node and inverse-spacing tables staged in shared memory (else read from global).
-template <bool SMEM_NODES, int MINB>
+template <bool SMEM_NODES, int MINB, bool NESTED, bool TENSOR>
 __global__ void __launch_bounds__(256, MINB) grid_interp_kernel(const InterpParams p) {
   extern __shared__ double s_tab[];
-  const double* nd[3];
-  const double* iv[3];
+  const double* nd[2][3];
+  const double* iv[2][3];
   if (SMEM_NODES) {
     int off = 0;
-    for (int d = 0; d < 3; ++d) {
-      double* sn = s_tab + off;
-      double* si = sn + p.n[d];
-      for (int i = threadIdx.x; i < p.n[d]; i += blockDim.x) {
-        sn[i] = p.node[d][i];
-        si[i] = i + 1 < p.n[d] ? __ddiv_rn(1.0, __dsub_rn(p.node[d][i + 1], p.node[d][i])) : 0.0;
+    for (int l = 0; l < (NESTED ? 2 : 1); ++l)
+      for (int d = 0; d < 3; ++d) {
+        const int n = l ? p.n2[d] : p.n[d];
+        const double* src = l ? p.node2[d] : p.node[d];
+        double* sn = s_tab + off;
+        double* si = sn + n;
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+          sn[i] = src[i];
+          si[i] = i + 1 < n ? __ddiv_rn(1.0, __dsub_rn(src[i + 1], src[i])) : 0.0;
+        }
+        nd[l][d] = sn, iv[l][d] = si;
+        off += 2 * n;
       }
-      nd[d] = sn, iv[d] = si;
-      off += 2 * p.n[d];
-    }
     __syncthreads();
   } else {
-    nd[0] = p.node[0], nd[1] = p.node[1], nd[2] = p.node[2];
-    iv[0] = iv[1] = iv[2] = nullptr;
+    for (int d = 0; d < 3; ++d) {
+      nd[0][d] = p.node[d], nd[1][d] = NESTED ? p.node2[d] : p.node[d];
+      iv[0][d] = iv[1][d] = nullptr;
+    }
   }
   // grid-stride over stars: the tables above are staged once per resident block, not once per 256 stars
   for (long long s = blockIdx.x * (long long)blockDim.x + threadIdx.x; s < p.n_star;
        s += (long long)gridDim.x * blockDim.x) {
-  const int cl = p.scl ? p.scl[s] : 0;
-  const double* org = p.origin + 3 * (long long)cl;
-  const double pos[3] = {p.sx[s], p.sy[s], p.sz[s]};
-  int c3[3];
-  double t[3], u[3];
+    const int cl = p.scl ? p.scl[s] : 0;
+    const double* org = p.origin + 3 * (long long)cl;
+    const double pos[3] = {p.sx[s], p.sy[s], p.sz[s]};
+    int lv = 0;
+    if (NESTED) {
+      lv = 1;
 #pragma unroll
-  for (int d = 0; d < 3; ++d) {
-    const double o = org[d];
-    const int i = find_cell(nd[d], p.n[d], o, pos[d]);
-    const double inv = SMEM_NODES ? iv[d][i] : __ddiv_rn(1.0, __dsub_rn(nd[d][i + 1], nd[d][i]));
-    t[d] = __dmul_rn(__dsub_rn(pos[d], __dadd_rn(nd[d][i], o)), inv);
-    u[d] = __dsub_rn(1.0, t[d]);
-    c3[d] = i;
-  }
-
-  const long long nyz = (long long)p.n[1] * p.n[2];
-  const long long n_node = (long long)p.n[0] * nyz + 1;  // + appended origin row
-  const long long base = (long long)cl * n_node + ((long long)c3[0] * p.n[1] + c3[1]) * p.n[2] + c3[2];
-  // corner order: (di,dj,dk) = 000,001,010,011,100,101,110,111
-  // time blend in FP32, left to right: v = ((r0*w0 + r1*w1) + r2*w2) + r3*w3 ; a single plane is taken as is
-  float4 v[8];
-#pragma unroll
-  for (int c = 0; c < 8; ++c) {
-    const long long off = base + (long long)(c >> 2) * nyz + (long long)((c >> 1) & 1) * p.n[2] + (c & 1);
-    float4 a = __ldg(p.rec[0] + off);
-    if (p.n_rec > 1) {
-      const float4 b = __ldg(p.rec[1] + off);
-      a = make_float4(lerp_rn_f(a.x, p.w[0], b.x, p.w[1]), lerp_rn_f(a.y, p.w[0], b.y, p.w[1]),
-                      lerp_rn_f(a.z, p.w[0], b.z, p.w[1]), lerp_rn_f(a.w, p.w[0], b.w, p.w[1]));
-      for (int r = 2; r < p.n_rec; ++r) {
-        const float4 e = __ldg(p.rec[r] + off);
-        const float wr = p.w[r];
-        a = make_float4(__fadd_rn(a.x, __fmul_rn(e.x, wr)), __fadd_rn(a.y, __fmul_rn(e.y, wr)),
-                        __fadd_rn(a.z, __fmul_rn(e.z, wr)), __fadd_rn(a.w, __fmul_rn(e.w, wr)));
+      for (int d = 0; d < 3; ++d) {
+        const double lo = __dadd_rn(nd[1][d][0], org[d]), hi = __dadd_rn(nd[1][d][p.n2[d] - 1], org[d]);
+        if (!(pos[d] >= lo && pos[d] <= hi)) lv = 0;
       }
     }
-    v[c] = a;
-  }
-  const int ncomp = p.pot ? 4 : 3;
+    int nn[3];
+    const float4* rec[4];
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    if (q >= ncomp) break;
-    double w[8];
+    for (int d = 0; d < 3; ++d) nn[d] = (NESTED && lv) ? p.n2[d] : p.n[d];
 #pragma unroll
-    for (int c = 0; c < 8; ++c) w[c] = (double)(q == 0 ? v[c].x : (q == 1 ? v[c].y : (q == 2 ? v[c].z : v[c].w)));
-    const double c00 = lerp_rn(w[0], u[2], w[1], t[2]);
-    const double c01 = lerp_rn(w[2], u[2], w[3], t[2]);
-    const double c10 = lerp_rn(w[4], u[2], w[5], t[2]);
-    const double c11 = lerp_rn(w[6], u[2], w[7], t[2]);
-    const double c0 = lerp_rn(c00, u[1], c01, t[1]);
-    const double c1 = lerp_rn(c10, u[1], c11, t[1]);
-    const double r = lerp_rn(c0, u[0], c1, t[0]);
-    if (q < 3) p.acc[(long long)q * p.n_star + s] = r;
-    else p.pot[s] = r;
-  }
-  if (p.cell) {
-    p.cell[s] = c3[0];
-    p.cell[p.n_star + s] = c3[1];
-    p.cell[2 * p.n_star + s] = c3[2];
-  }
+    for (int r = 0; r < 4; ++r) rec[r] = (NESTED && lv) ? p.rec2[r] : p.rec[r];
+    int c3[3];
+    double t[3], u[3], inv3[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      const double* ndd = (NESTED && lv) ? nd[1][d] : nd[0][d];
+      const double o = org[d];
+      const int i = find_cell(ndd, nn[d], o, pos[d]);
+      const double inv = SMEM_NODES ? ((NESTED && lv) ? iv[1][d][i] : iv[0][d][i])
+                                    : __ddiv_rn(1.0, __dsub_rn(ndd[i + 1], ndd[i]));
+      t[d] = __dmul_rn(__dsub_rn(pos[d], __dadd_rn(ndd[i], o)), inv);
+      u[d] = __dsub_rn(1.0, t[d]);
+      if (TENSOR) inv3[d] = inv;
+      c3[d] = i;
+    }
+
+    const long long nyz = (long long)nn[1] * nn[2];
+    const long long n_node = (long long)nn[0] * nyz + 1;  // + appended origin row
+    const long long base = (long long)cl * n_node + ((long long)c3[0] * nn[1] + c3[1]) * nn[2] + c3[2];
+    // corner order: (di,dj,dk) = 000,001,010,011,100,101,110,111
+    // time blend in FP32, left to right: v = ((r0*w0 + r1*w1) + r2*w2) + r3*w3 ; a single plane is taken as is
+    float4 v[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const long long off = base + (long long)(c >> 2) * nyz + (long long)((c >> 1) & 1) * nn[2] + (c & 1);
+      float4 a = __ldg(rec[0] + off);
+      if (p.n_rec > 1) {
+        const float4 b = __ldg(rec[1] + off);
+        a = make_float4(lerp_rn_f(a.x, p.w[0], b.x, p.w[1]), lerp_rn_f(a.y, p.w[0], b.y, p.w[1]),
+                        lerp_rn_f(a.z, p.w[0], b.z, p.w[1]), lerp_rn_f(a.w, p.w[0], b.w, p.w[1]));
+#pragma unroll
+        for (int r = 2; r < 4; ++r) {
+          if (r >= p.n_rec) break;
+          const float4 e = __ldg(rec[r] + off);
+          const float wr = p.w[r];
+          a = make_float4(__fadd_rn(a.x, __fmul_rn(e.x, wr)), __fadd_rn(a.y, __fmul_rn(e.y, wr)),
+                          __fadd_rn(a.z, __fmul_rn(e.z, wr)), __fadd_rn(a.w, __fmul_rn(e.w, wr)));
+        }
+      }
+      v[c] = a;
+    }
+    const int ncomp = p.pot ? 4 : 3;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      if (q >= ncomp) break;
+      double w[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) w[c] = (double)(q == 0 ? v[c].x : (q == 1 ? v[c].y : (q == 2 ? v[c].z : v[c].w)));
+      const double c00 = lerp_rn(w[0], u[2], w[1], t[2]);
+      const double c01 = lerp_rn(w[2], u[2], w[3], t[2]);
+      const double c10 = lerp_rn(w[4], u[2], w[5], t[2]);
+      const double c11 = lerp_rn(w[6], u[2], w[7], t[2]);
+      const double c0 = lerp_rn(c00, u[1], c01, t[1]);
+      const double c1 = lerp_rn(c10, u[1], c11, t[1]);
+      const double r = lerp_rn(c0, u[0], c1, t[0]);
+      if (q < 3) p.acc[(long long)q * p.n_star + s] = r;
+      else p.pot[s] = r;
+      if (TENSOR && q < 3) {
+        // d/dx: difference of the two x-face values; d/dy: y-edge differences blended in x; d/dz: z-edge
+        // differences blended in y then x; each times the inverse cell size of its axis
+        const double gx = __dmul_rn(__dsub_rn(c1, c0), inv3[0]);
+        const double gy = __dmul_rn(lerp_rn(__dsub_rn(c01, c00), u[0], __dsub_rn(c11, c10), t[0]), inv3[1]);
+        const double z0 = lerp_rn(__dsub_rn(w[1], w[0]), u[1], __dsub_rn(w[3], w[2]), t[1]);
+        const double z1 = lerp_rn(__dsub_rn(w[5], w[4]), u[1], __dsub_rn(w[7], w[6]), t[1]);
+        const double gz = __dmul_rn(lerp_rn(z0, u[0], z1, t[0]), inv3[2]);
+        p.tensor[(long long)(0 + q) * p.n_star + s] = gx;  // T[x][q] = d a_q / dx
+        p.tensor[(long long)(3 + q) * p.n_star + s] = gy;
+        p.tensor[(long long)(6 + q) * p.n_star + s] = gz;
+      }
+    }
+    if (p.cell) {
+      p.cell[s] = c3[0];
+      p.cell[p.n_star + s] = c3[1];
+      p.cell[2 * p.n_star + s] = c3[2];
+    }
+    if (p.level) p.level[s] = lv;
   }
 }
 
@@ -210,7 +256,9 @@ extern "C" int ocg_debug_set_interp_variant(int v) {
 
 static int interp_launch(ocg_ctx* ctx, const ocg_grid_desc* grid, const float* const* rec, const float* w, int n_rec,
                          const double* sx, const double* sy, const double* sz, const int32_t* scl, int64_t n_star,
-                         double* acc, double* pot, int32_t* cell, void* stream, const char* who) {
+                         double* acc, double* pot, int32_t* cell, void* stream, const char* who,
+                         const ocg_grid_desc* fine = nullptr, const float* const* rec_fine = nullptr,
+                         double* tensor = nullptr, int32_t* level = nullptr) {
   if (!grid) return ocg_fail(ctx, OCG_ERR_INVALID, "%s: grid is NULL", who);
   if (n_star < 0) return ocg_fail(ctx, OCG_ERR_INVALID, "%s: negative n_star", who);
   if (n_star == 0) return OCG_OK;
@@ -220,30 +268,50 @@ static int interp_launch(ocg_ctx* ctx, const ocg_grid_desc* grid, const float* c
   if (grid->n_cluster < 1 || !grid->origin_dev || !sx || !sy || !sz || !acc)
     return ocg_fail(ctx, OCG_ERR_INVALID, "%s: NULL argument", who);
   if (n_rec < 1 || n_rec > 4) return ocg_fail(ctx, OCG_ERR_INVALID, "%s: n_rec = %d outside [1,4]", who, n_rec);
+  if (fine) {
+    for (int d = 0; d < 3; ++d)
+      if (fine->n[d] < 2 || !fine->node_dev[d])
+        return ocg_fail(ctx, OCG_ERR_INVALID, "%s: fine axis %d needs >= 2 nodes (got %d)", who, d, fine->n[d]);
+    if (!rec_fine) return ocg_fail(ctx, OCG_ERR_INVALID, "%s: fine lattice without record planes", who);
+    if (fine->n_cluster != grid->n_cluster)
+      return ocg_fail(ctx, OCG_ERR_INVALID, "%s: coarse and fine lattices must hold the same clusters", who);
+  }
   OcgDeviceGuard g(ctx->device);
   InterpParams p;
-  for (int d = 0; d < 3; ++d) p.n[d] = grid->n[d], p.node[d] = grid->node_dev[d];
+  for (int d = 0; d < 3; ++d) {
+    p.n[d] = grid->n[d], p.node[d] = grid->node_dev[d];
+    p.n2[d] = fine ? fine->n[d] : 0, p.node2[d] = fine ? fine->node_dev[d] : nullptr;
+  }
   p.n_cluster = grid->n_cluster;
   p.origin = grid->origin_dev;
   for (int r = 0; r < 4; ++r) {
     p.rec[r] = r < n_rec ? reinterpret_cast<const float4*>(rec[r]) : nullptr;
+    p.rec2[r] = (fine && r < n_rec) ? reinterpret_cast<const float4*>(rec_fine[r]) : nullptr;
     p.w[r] = r < n_rec ? w[r] : 0.f;
-    if (r < n_rec && !rec[r]) return ocg_fail(ctx, OCG_ERR_INVALID, "%s: record plane %d is NULL", who, r);
+    if (r < n_rec && (!rec[r] || (fine && !rec_fine[r])))
+      return ocg_fail(ctx, OCG_ERR_INVALID, "%s: record plane %d is NULL", who, r);
   }
   p.n_rec = n_rec;
   p.sx = sx, p.sy = sy, p.sz = sz;
   p.scl = scl;
   p.n_star = n_star;
-  p.acc = acc, p.pot = pot, p.cell = cell;
+  p.acc = acc, p.pot = pot, p.cell = cell, p.tensor = tensor, p.level = level;
   long long nn = (long long)grid->n[0] + grid->n[1] + grid->n[2];
+  if (fine) nn += (long long)fine->n[0] + fine->n[1] + fine->n[2];
   // persistent launch: as many blocks as are resident at once (a multiple of the SM count), grid-stride inside
   const bool in_smem = nn <= 2048;
   const size_t smem = in_smem ? (size_t)nn * 2 * sizeof(double) : 0;
   typedef void (*interp_fn)(const InterpParams);
-  static const interp_fn fns[3][2] = {{grid_interp_kernel<false, 2>, grid_interp_kernel<true, 2>},
-                                      {grid_interp_kernel<false, 3>, grid_interp_kernel<true, 3>},
-                                      {grid_interp_kernel<false, 4>, grid_interp_kernel<true, 4>}};
-  interp_fn fn = fns[g_interp_variant][in_smem ? 1 : 0];
+  static const interp_fn fns[3][2] = {
+      {grid_interp_kernel<false, 2, false, false>, grid_interp_kernel<true, 2, false, false>},
+      {grid_interp_kernel<false, 3, false, false>, grid_interp_kernel<true, 3, false, false>},
+      {grid_interp_kernel<false, 4, false, false>, grid_interp_kernel<true, 4, false, false>}};
+  // [nested][tensor][in_smem]: the two-level and tensor forms (any combination) use <= 128-register builds
+  static const interp_fn fns_x[2][2][2] = {
+      {{nullptr, nullptr}, {grid_interp_kernel<false, 2, false, true>, grid_interp_kernel<true, 2, false, true>}},
+      {{grid_interp_kernel<false, 3, true, false>, grid_interp_kernel<true, 3, true, false>},
+       {grid_interp_kernel<false, 2, true, true>, grid_interp_kernel<true, 2, true, true>}}};
+  interp_fn fn = (fine || tensor) ? fns_x[fine ? 1 : 0][tensor ? 1 : 0][in_smem ? 1 : 0] : fns[g_interp_variant][in_smem ? 1 : 0];
   int occ = 0;
   OCG_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, 256, smem));
   if (occ < 1) occ = 1;
@@ -283,4 +351,45 @@ extern "C" int ocg_grid_interp_multi(ocg_ctx* ctx, const ocg_grid_desc* grid, co
   for (int r = 0; r < n_rec; ++r) w[r] = (float)weights[r];
   return interp_launch(ctx, grid, rec_dev, w, n_rec, star_x_dev, star_y_dev, star_z_dev, star_cluster_dev, n_star,
                        acc_out_dev, pot_out_dev, cell_out_dev, stream, "ocg_grid_interp_multi");
+}
+
+// Two-level form (the reference's nested fine grid, grid_cartesian.py:34-53,71-91) + optional tidal tensor
+// (gizmo_interface.py:719-756) + optional level/cell outputs.  fine == NULL: single level.
+extern "C" int ocg_grid_interp_nested(ocg_ctx* ctx, const ocg_grid_desc* coarse, const ocg_grid_desc* fine,
+                                      const float* const* rec_coarse_dev, const float* const* rec_fine_dev,
+                                      const double* weights, int32_t n_rec, const double* star_x_dev,
+                                      const double* star_y_dev, const double* star_z_dev,
+                                      const int32_t* star_cluster_dev, int64_t n_star, double* acc_out_dev,
+                                      double* pot_out_dev, double* tensor_out_dev, int32_t* level_out_dev,
+                                      int32_t* cell_out_dev, void* stream) {
+  if (!ctx) return OCG_ERR_INVALID;
+  if (!rec_coarse_dev || !weights || n_rec < 1 || n_rec > 4)
+    return ocg_fail(ctx, OCG_ERR_INVALID, "ocg_grid_interp_nested: need 1..4 record planes and weights");
+  float w[4];
+  for (int r = 0; r < n_rec; ++r) w[r] = (float)weights[r];
+  return interp_launch(ctx, coarse, rec_coarse_dev, w, n_rec, star_x_dev, star_y_dev, star_z_dev, star_cluster_dev,
+                       n_star, acc_out_dev, pot_out_dev, cell_out_dev, stream, "ocg_grid_interp_nested", fine,
+                       rec_fine_dev, tensor_out_dev, level_out_dev);
+}
+
+// rec[index[i]] = float4(acc[0][i], acc[1][i], acc[2][i], pot[i]) — K2 pack with a scatter: lays the rows of the
+// reference's point list (kept coarse points | fine lattice | origin) out as full-lattice node records.
+__global__ void pack_planes_indexed_kernel(const double* __restrict__ acc, const double* __restrict__ pot,
+                                           const long long* __restrict__ index, long long n, float4* __restrict__ rec) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  rec[index[i]] = make_float4((float)acc[i], (float)acc[n + i], (float)acc[2 * n + i], pot ? (float)pot[i] : 0.f);
+}
+
+extern "C" int ocg_pack_planes_indexed(ocg_ctx* ctx, const double* acc_dev, const double* pot_dev, int64_t n,
+                                       const int64_t* index_dev, float* rec_dev, void* stream) {
+  if (!ctx) return OCG_ERR_INVALID;
+  if (n < 0 || (n > 0 && (!acc_dev || !rec_dev || !index_dev)))
+    return ocg_fail(ctx, OCG_ERR_INVALID, "ocg_pack_planes_indexed: bad arguments");
+  if (n == 0) return OCG_OK;
+  OcgDeviceGuard g(ctx->device);
+  pack_planes_indexed_kernel<<<nblocks(n, 256), 256, 0, (cudaStream_t)stream>>>(
+      acc_dev, pot_dev, reinterpret_cast<const long long*>(index_dev), n, reinterpret_cast<float4*>(rec_dev));
+  OCG_CHECK_LAUNCH(ctx, "pack_planes_indexed_kernel");
+  return OCG_OK;
 }

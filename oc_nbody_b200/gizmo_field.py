@@ -33,6 +33,7 @@ _DEFAULTS = dict(
     grid_x_size_in_kpc=0.6, grid_y_size_in_kpc=0.6, grid_z_size_in_kpc=0.6, grid_resolution=0.6 / 16,
     star_softening_in_pc=11.2, dark_softening_in_pc=112.0, star_char_mass=None, dark_char_mass=None,
     softening_kernel="spline", plummer_eps_over_h=1.0 / 2.8, theta=0.5, fine_grid=False, with_potential=True,
+    grid_fine_x_size_in_kpc=None, grid_fine_y_size_in_kpc=None, grid_fine_z_size_in_kpc=None, grid_fine_resolution=None,
     # "linear" (BASELINE.json north_star) or "cubic" (the reference's own splrep/splev, gizmo_interface.py:587-620)
     time_interpolation="linear",
 )
@@ -63,7 +64,10 @@ class gizmo_field(object):
         if self.softening_kernel not in _lib.KERNELS:
             raise ValueError("softening_kernel must be one of %r" % (sorted(_lib.KERNELS),))
         if self.fine_grid:
-            raise NotImplementedError("nested fine grid is a SURVEY §8(f) 'next' row")
+            missing = [k for k in ("grid_fine_x_size_in_kpc", "grid_fine_y_size_in_kpc", "grid_fine_z_size_in_kpc",
+                                   "grid_fine_resolution") if getattr(self, k, None) is None]
+            if missing:
+                raise ValueError("fine_grid needs %s (options.py:108-118)" % ", ".join(missing))
         if self.time_interpolation not in ("linear", "cubic"):
             raise ValueError("time_interpolation must be 'linear' or 'cubic'")
         self.G = G_KPC_KMS_MYR  # kpc^2 km/s /Myr /Msun, the unit of gizmo_interface.py:70
@@ -132,9 +136,17 @@ class gizmo_field(object):
             return acc[0], acc[1], acc[2], pot
         return acc[0], acc[1], acc[2]
 
+    def _make_grid_(self):
+        """grid(...) [+ add_fine_grid(...)] exactly as gizmo_interface.py:412-419."""
+        g = grid(self.grid_x_size_in_kpc, self.grid_y_size_in_kpc, self.grid_z_size_in_kpc, self.grid_resolution)
+        if self.fine_grid:
+            g.add_fine_grid(self.grid_fine_x_size_in_kpc, self.grid_fine_y_size_in_kpc, self.grid_fine_z_size_in_kpc,
+                            self.grid_fine_resolution)
+        return g
+
     def _init_grid_(self):
         """Per-snapshot grid loop (gizmo_interface.py:393-510, minus the pickle caches)."""
-        self.grid = grid(self.grid_x_size_in_kpc, self.grid_y_size_in_kpc, self.grid_z_size_in_kpc, self.grid_resolution)
+        self.grid = self._make_grid_()
         ax, ay, az, ph = [], [], [], []
         for i, snap in enumerate(self.snapshots):
             self.grid.gen_evolved_grid(self.chosen_snapshot_positions[i])
@@ -152,7 +164,7 @@ class gizmo_field(object):
     def set_snapshot_fields(self, acc_x, acc_y, acc_z, pot=None):
         """Install pre-computed fields ([Nsnap, Ngrid+1] each, e.g. loaded from the reference's caches)."""
         if not hasattr(self, "grid"):
-            self.grid = grid(self.grid_x_size_in_kpc, self.grid_y_size_in_kpc, self.grid_z_size_in_kpc, self.grid_resolution)
+            self.grid = self._make_grid_()
         self.grid.snapshot_acceleration_x = np.asarray(acc_x, np.float64)
         self.grid.snapshot_acceleration_y = np.asarray(acc_y, np.float64)
         self.grid.snapshot_acceleration_z = np.asarray(acc_z, np.float64)
@@ -160,35 +172,75 @@ class gizmo_field(object):
         self.with_potential = pot is not None
         self._upload_planes_()
 
-    def _upload_planes_(self):
-        """FP64 [Nsnap, Ngrid+1] x3 -> float4 node records per snapshot in HBM (K2 pack)."""
+    def _layout_planes_(self, planes):
+        """FP64 [P, 4, Npoints] (ax, ay, az, phi per point of grid.init_grid) -> float4 node records in HBM.
+
+        Single lattice: one record array [P, Npoints, 4] in point order (= lattice order + origin row).
+        Nested grid (grid_cartesian.py:34-53,71-91): two arrays, ``coarse`` [P, ncoarse+1, 4] on the FULL coarse
+        lattice and ``fine`` [P, nfine+1, 4].  Kept coarse points are scattered to their lattice slots; the coarse
+        points the reference dropped (strictly inside the fine box) are filled by interpolating the fine lattice at
+        their positions (K3 itself), so that coarse cells straddling the fine box have all eight corners."""
         import torch
         dev = torch.device("cuda", self.ctx.device)
         g = self.grid
-        nsnap, nnode = g.snapshot_acceleration_x.shape
-        if nnode != len(g):
-            raise ValueError("field arrays have %d nodes, grid has %d" % (nnode, len(g)))
-        rec = torch.empty((nsnap, nnode, 4), dtype=torch.float32, device=dev)
-        for i in range(nsnap):
-            acc = torch.from_numpy(np.stack([g.snapshot_acceleration_x[i], g.snapshot_acceleration_y[i],
-                                             g.snapshot_acceleration_z[i]])).to(dev)
-            pot = None if g.snapshot_potential is None else torch.from_numpy(np.ascontiguousarray(g.snapshot_potential[i])).to(dev)
-            self.ctx.pack_planes(acc, pot, rec[i])
-        self._dev = dict(rec=rec, nodes=[torch.from_numpy(np.ascontiguousarray(a)).to(dev) for a in g.nodes],
+        P, _, npts = planes.shape
+        if npts != len(g):
+            raise ValueError("field arrays have %d points, grid has %d" % (npts, len(g)))
+
+        def up(a):
+            return torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+
+        if not g.has_fine_grid:
+            rec = torch.empty((P, npts, 4), dtype=torch.float32, device=dev)
+            for i in range(P):
+                self.ctx.pack_planes(up(planes[i, :3]), up(planes[i, 3]), rec[i])
+            return dict(coarse=rec, fine=None)
+        nc, nf, f0 = g.n_lattice, int(np.prod(g.fine_shape)), g.fine_row0
+        coarse = torch.zeros((P, nc + 1, 4), dtype=torch.float32, device=dev)
+        fine = torch.empty((P, nf + 1, 4), dtype=torch.float32, device=dev)
+        keep_idx = up(np.concatenate([g.coarse_keep_index, [nc]]).astype(np.int64))  # + the origin row
+        hole_idx = up(g.coarse_hole_index)
+        hole_pts = g.coarse_hole_points()
+        hx, hy, hz = (up(hole_pts[:, d]) for d in range(3))
+        fnodes = [up(a) for a in g.fine_nodes]
+        zero_origin = torch.zeros((1, 3), dtype=torch.float64, device=dev)
+        n_hole = hole_pts.shape[0]
+        h_acc = torch.empty((3, n_hole), dtype=torch.float64, device=dev)
+        h_pot = torch.empty(n_hole, dtype=torch.float64, device=dev)
+        for i in range(P):
+            self.ctx.pack_planes(up(planes[i, :3, f0:]), up(planes[i, 3, f0:]), fine[i])
+            rows = np.concatenate([planes[i, :, :f0], planes[i, :, -1:]], axis=1)
+            self.ctx.pack_planes_indexed(up(rows[:3]), up(rows[3]), keep_idx, coarse[i])
+            if n_hole:
+                self.ctx.grid_interp(g.fine_shape, fnodes, zero_origin, fine[i], None, 0.0, hx, hy, hz, None, h_acc, h_pot)
+                self.ctx.pack_planes_indexed(h_acc, h_pot, hole_idx, coarse[i])
+        return dict(coarse=coarse, fine=fine)
+
+    def _planes_(self):
+        g = self.grid
+        stacks = [g.snapshot_acceleration_x, g.snapshot_acceleration_y, g.snapshot_acceleration_z]
+        stacks.append(g.snapshot_potential if g.snapshot_potential is not None else np.zeros_like(stacks[0]))
+        return np.stack([np.asarray(a, np.float64) for a in stacks], axis=1)  # [Nsnap, 4, Npoints]
+
+    def _upload_planes_(self):
+        """FP64 [Nsnap, Npoints] x3 (+ potential) -> float4 node records per snapshot in HBM (K2 pack)."""
+        import torch
+        dev = torch.device("cuda", self.ctx.device)
+        g = self.grid
+        planes = self._planes_()
+        lay = self._layout_planes_(planes)
+        self._dev = dict(rec=lay["coarse"], rec_fine=lay["fine"],
+                         nodes=[torch.from_numpy(np.ascontiguousarray(a)).to(dev) for a in g.nodes],
+                         fine_nodes=[torch.from_numpy(np.ascontiguousarray(a)).to(dev) for a in g.fine_nodes] if g.has_fine_grid else None,
                          origin=torch.zeros((1, 3), dtype=torch.float64, device=dev), device=dev)
         if self.time_interpolation == "cubic":
             # one vectorised spline fit over all grid points (= splrep per point, gizmo_interface.py:591-597);
             # the coefficient planes replace the snapshot planes as what K3 gathers from
             from . import time_spline
-            stacks = [g.snapshot_acceleration_x, g.snapshot_acceleration_y, g.snapshot_acceleration_z]
-            stacks.append(g.snapshot_potential if g.snapshot_potential is not None else np.zeros_like(stacks[0]))
-            self._knots, coef = time_spline.fit(self.time_in_Myr, np.stack(stacks, axis=1))  # [Nsnap, 4, n_node]
+            self._knots, coef = time_spline.fit(self.time_in_Myr, planes)  # [Nsnap, 4, Npoints]
             self._coef = coef
-            crec = torch.empty((coef.shape[0], nnode, 4), dtype=torch.float32, device=dev)
-            for i in range(coef.shape[0]):
-                self.ctx.pack_planes(torch.from_numpy(np.ascontiguousarray(coef[i, :3])).to(dev),
-                                     torch.from_numpy(np.ascontiguousarray(coef[i, 3])).to(dev), crec[i])
-            self._dev["coef_rec"] = crec
+            clay = self._layout_planes_(coef)
+            self._dev["coef_rec"], self._dev["coef_rec_fine"] = clay["coarse"], clay["fine"]
         self._set_origin_(self._origin)
 
     # ---------------------------------------------------------------------- per-step state ----
@@ -233,6 +285,12 @@ class gizmo_field(object):
             f, w = self._spline_first, self._spline_w
             v = np.tensordot(w, self._coef[f:f + 4], axes=1)  # FP64 on the host: [4, n_node]
             self._blend_cache = (v[:3], v[3])
+        if self._blend_cache is None and self.grid.has_fine_grid:
+            # records are in lattice order for the two-level grid; blend the FP64 point-list stacks on the host
+            a, b, w = self._bracket
+            pl = self._planes_()
+            v = (1.0 - w) * pl[a] + w * pl[b]
+            self._blend_cache = (v[:3], v[3])
         if self._blend_cache is None:
             import torch
             a, b, w = self._bracket
@@ -253,21 +311,45 @@ class gizmo_field(object):
         return self._blend_()[1]
 
     # ---------------------------------------------------------------------------- the kick ----
-    def _interp_device_(self, sx, sy, sz, want_pot):
-        """K3 on device tensors (FP64 kpc). Returns acc [3,n] (, pot [n]) device tensors."""
+    def _time_planes_(self):
+        """(coarse planes, fine planes or None, weights) of the current model time."""
+        d = self._dev
+        if self.time_interpolation == "cubic":
+            f = self._spline_first
+            fine = None if d["coef_rec_fine"] is None else [d["coef_rec_fine"][f + j] for j in range(4)]
+            return [d["coef_rec"][f + j] for j in range(4)], fine, list(self._spline_w)
+        a, b, w = self._bracket
+        if b == a:
+            return [d["rec"][a]], None if d["rec_fine"] is None else [d["rec_fine"][a]], [1.0]
+        # FP32 weights exactly as ocg_grid_interp forms them: wb = fl32(w), wa = fl32(1 - wb)
+        wb = np.float32(w)
+        wa = np.float32(np.float32(1.0) - wb)
+        fine = None if d["rec_fine"] is None else [d["rec_fine"][a], d["rec_fine"][b]]
+        return [d["rec"][a], d["rec"][b]], fine, [float(wa), float(wb)]
+
+    def _interp_device_(self, sx, sy, sz, want_pot, want_tensor=False):
+        """K3 on device tensors (FP64 kpc). Returns acc [3,n], pot [n] or None (, tensor [9,n]) device tensors."""
         import torch
         d = self._dev
         n = sx.shape[0]
         acc = torch.empty((3, n), dtype=torch.float64, device=d["device"])
         pot = torch.empty(n, dtype=torch.float64, device=d["device"]) if want_pot else None
+        g = self.grid
+        if g.has_fine_grid or want_tensor:
+            recs, recs_fine, w = self._time_planes_()
+            tensor = torch.empty((9, n), dtype=torch.float64, device=d["device"]) if want_tensor else None
+            self.ctx.grid_interp_nested(g.shape, d["nodes"], d["origin"], recs, w, sx, sy, sz, None, acc, pot,
+                                        fine_n=g.fine_shape, fine_nodes=d["fine_nodes"], recs_fine=recs_fine,
+                                        tensor_out=tensor)
+            return (acc, pot, tensor) if want_tensor else (acc, pot)
         if self.time_interpolation == "cubic":
             f = self._spline_first
-            self.ctx.grid_interp_multi(self.grid.shape, d["nodes"], d["origin"], [d["coef_rec"][f + j] for j in range(4)],
+            self.ctx.grid_interp_multi(g.shape, d["nodes"], d["origin"], [d["coef_rec"][f + j] for j in range(4)],
                                        self._spline_w, sx, sy, sz, None, acc, pot)
             return acc, pot
         a, b, w = self._bracket
         rec = d["rec"]
-        self.ctx.grid_interp(self.grid.shape, d["nodes"], d["origin"], rec[a], rec[b] if b != a else None, w, sx, sy, sz,
+        self.ctx.grid_interp(g.shape, d["nodes"], d["origin"], rec[a], rec[b] if b != a else None, w, sx, sy, sz,
                              None, acc, pot)
         return acc, pot
 
@@ -303,9 +385,22 @@ class gizmo_field(object):
         u = units.kms ** 2
         return (float(pot[0]) | u) if scalar else (pot | u)
 
+    def get_tidal_tensor_at_point(self, eps, xlist, ylist, zlist):
+        """Tidal tensor T[i][j] = d a_j / d x_i in km/s/Myr/kpc (gizmo_interface.py:719-756): the analytic gradient
+        of the trilinear interpolant in place of nine RBF derivative evaluations per star.  Scalar form returns a
+        3x3 quantity, 1-D form an [n, 3, 3] one."""
+        import torch
+        x, y, z = (to_value(v, units.kpc) for v in (xlist, ylist, zlist))
+        scalar = not hasattr(x, "__iter__") and np.ndim(x) == 0
+        xs = [torch.from_numpy(np.atleast_1d(np.asarray(v, np.float64)).copy()).to(self._dev["device"]) for v in (x, y, z)]
+        _, _, tensor = self._interp_device_(xs[0], xs[1], xs[2], False, want_tensor=True)
+        T = tensor.cpu().numpy().T.reshape(-1, 3, 3)
+        u = units.kms / units.Myr / units.kpc
+        return (T[0] | u) if scalar else (T | u)
+
     def kick_device(self, pos_kpc, vel_kms, dt_myr):
         """Fused BRIDGE half-kick on device state (FP64 [3,n] tensors): v += dt * a_tidal(x). No host copies."""
-        acc, _ = self._interp_device_(pos_kpc[0], pos_kpc[1], pos_kpc[2], False)
+        acc = self._interp_device_(pos_kpc[0], pos_kpc[1], pos_kpc[2], False)[0]
         self.ctx.kick(vel_kms, acc, dt_myr)
 
     def stop(self):

@@ -212,6 +212,56 @@ def grid_interp_multi(nodes, origin, recs, weights, sx, sy, sz, star_cluster=Non
     return (acc, pot) if want_pot else acc
 
 
+def grid_interp_nested(nodes, fine_nodes, origin, recs, recs_fine, weights, sx, sy, sz, star_cluster=None,
+                       want_pot=False, want_tensor=False, want_level=False, want_cell=False):
+    """Two-level evaluation (the reference's nested fine grid, grid_cartesian.py:34-53,71-91): stars inside the
+    closed fine box use the fine lattice, the others the coarse one; optional tidal tensor T[3*i+j] = d a_j/d x_i
+    (gizmo_interface.py:719-756). fine_nodes None: single level. Returns a dict."""
+    xg, yg, zg = (_c(a, np.float64) for a in nodes)
+    nn = np.array([len(xg), len(yg), len(zg)], np.int32)
+    origin = _c(origin, np.float64).reshape(-1, 3)
+    recs = [_c(r, np.float32) for r in recs]
+    ptrs = (ctypes.c_void_p * len(recs))(*[r.ctypes.data for r in recs])
+    if fine_nodes is not None:
+        fx, fy, fz = (_c(a, np.float64) for a in fine_nodes)
+        nn2 = np.array([len(fx), len(fy), len(fz)], np.int32)
+        recs2 = [_c(r, np.float32) for r in recs_fine]
+        ptrs2 = (ctypes.c_void_p * len(recs2))(*[r.ctypes.data for r in recs2])
+    else:
+        fx = fy = fz = nn2 = ptrs2 = None
+    w = _c(weights, np.float64)
+    sx, sy, sz = (_c(a, np.float64) for a in (sx, sy, sz))
+    scl = _c(star_cluster, np.int32)
+    n = sx.shape[0]
+    out = dict(acc=np.empty((3, n), np.float64), pot=np.empty(n, np.float64) if want_pot else None,
+               tensor=np.empty((9, n), np.float64) if want_tensor else None,
+               level=np.empty(n, np.int32) if want_level else None, cell=np.empty((3, n), np.int32) if want_cell else None)
+    lib().oracle_grid_interp_nested(_p(nn), _p(xg), _p(yg), _p(zg), _p(nn2), _p(fx), _p(fy), _p(fz), _p(origin), ptrs, ptrs2,
+                                    _p(w), ctypes.c_int32(len(recs)), _p(sx), _p(sy), _p(sz), _p(scl), ctypes.c_int64(n),
+                                    _p(out["acc"]), _p(out["pot"]), _p(out["tensor"]), _p(out["level"]), _p(out["cell"]))
+    return out
+
+
+def layout_nested(planes, n_coarse, keep_index, hole_index, hole_points, fine_nodes, fine_row0):
+    """Point-list planes [P, 4, Npoints] of a nested grid (kept coarse | fine | origin, grid_cartesian.py:71-91) ->
+    (coarse records [P, n_coarse+1, 4], fine records [P, n_fine+1, 4]) FP32, the dropped coarse points filled by
+    trilinear interpolation of the fine lattice at their positions (same rule as gizmo_field._layout_planes_)."""
+    planes = np.asarray(planes, np.float64)
+    P = planes.shape[0]
+    nf = planes.shape[2] - 1 - fine_row0
+    coarse = np.zeros((P, n_coarse + 1, 4), np.float32)
+    fine = np.empty((P, nf + 1, 4), np.float32)
+    for i in range(P):
+        fine[i] = pack_planes(planes[i, :3, fine_row0:], planes[i, 3, fine_row0:])
+        coarse[i, keep_index] = pack_planes(planes[i, :3, :fine_row0], planes[i, 3, :fine_row0])
+        coarse[i, n_coarse] = pack_planes(planes[i, :3, -1:], planes[i, 3, -1:])[0]
+        if len(hole_index):
+            acc, pot = grid_interp(fine_nodes, np.zeros(3), fine[i], None, 0.0, hole_points[:, 0], hole_points[:, 1],
+                                   hole_points[:, 2], want_pot=True)
+            coarse[i, hole_index] = pack_planes(acc, pot)
+    return coarse, fine
+
+
 def kick(vel, acc, dt):
     vel = np.array(vel, np.float64, order="C", copy=True)
     acc = _c(acc, np.float64)

@@ -216,37 +216,57 @@ static inline float lerp2f(float a, float wa, float b, float wb) {
 /* get_gravity_at_point (gizmo_interface.py:677-717) as trilinear-in-space interpolation of a time blend of
  * 1..4 record planes.  rec[r]: [n_cluster][nx*ny*nz+1][4] FP32 node records (ax,ay,az,phi); w[r] FP32 weights.
  * Arithmetic contract (same as the CUDA kernel):
+ *   level  : (nested, grid_cartesian.py:34-53,71-91) fine iff node2[0]+o <= x <= node2[n2-1]+o on all axes
  *   cell   : searchsorted on node + origin (FP64)
  *   weight : t = (x - (node[i] + origin)) * inv[i], inv[i] = 1/(node[i+1] - node[i])            FP64
  *   time   : v = ((r0*w0 + r1*w1) + r2*w2) + r3*w3 on the FP32 records, each op rounded to FP32
- *   space  : z, y, x lerps of the 8 corner values, each op rounded to FP64 */
-static void grid_interp_core(const int32_t* nn, const double* nodex, const double* nodey, const double* nodez,
-                             const double* origin, const float* const* rec, const float* w, int n_rec,
-                             const double* sx, const double* sy, const double* sz, const int32_t* scl, int64_t n_star,
-                             double* acc, double* pot, int32_t* cell) {
-  const int nx = nn[0], ny = nn[1], nz = nn[2];
-  const int64_t nyz = (int64_t)ny * nz, n_node = (int64_t)nx * nyz + 1;
+ *   space  : z, y, x lerps of the 8 corner values, each op rounded to FP64
+ *   tensor : T[3*i + j] = d a_j / d x_i of that trilinear form (gizmo_interface.py:719-756 T[i][j]) */
+typedef struct {
+  const int32_t* nn;
+  const double* node[3];
+  const float* const* rec;
+} lattice_t;
+
+static void grid_interp_core2(const lattice_t* coarse, const lattice_t* fine, const double* origin, const float* w,
+                              int n_rec, const double* sx, const double* sy, const double* sz, const int32_t* scl,
+                              int64_t n_star, double* acc, double* pot, double* tensor, int32_t* level, int32_t* cell) {
 #pragma omp parallel for schedule(static)
   for (int64_t s = 0; s < n_star; ++s) {
     const int cl = scl ? scl[s] : 0;
     const double* o = origin + 3 * (int64_t)cl;
-    const int i = find_cell(nodex, nx, o[0], sx[s]);
-    const int j = find_cell(nodey, ny, o[1], sy[s]);
-    const int k = find_cell(nodez, nz, o[2], sz[s]);
-    const double tx = (sx[s] - (nodex[i] + o[0])) * (1.0 / (nodex[i + 1] - nodex[i]));
-    const double ty = (sy[s] - (nodey[j] + o[1])) * (1.0 / (nodey[j + 1] - nodey[j]));
-    const double tz = (sz[s] - (nodez[k] + o[2])) * (1.0 / (nodez[k + 1] - nodez[k]));
-    const double ux = 1.0 - tx, uy = 1.0 - ty, uz = 1.0 - tz;
-    const int64_t base = (int64_t)cl * n_node + ((int64_t)i * ny + j) * nz + k;
+    const double pos[3] = {sx[s], sy[s], sz[s]};
+    int lv = 0;
+    if (fine) {
+      lv = 1;
+      for (int d = 0; d < 3; ++d) {
+        const double lo = fine->node[d][0] + o[d], hi = fine->node[d][fine->nn[d] - 1] + o[d];
+        if (!(pos[d] >= lo && pos[d] <= hi)) lv = 0;
+      }
+    }
+    const lattice_t* L = lv ? fine : coarse;
+    const int nx = L->nn[0], ny = L->nn[1], nz = L->nn[2];
+    const int64_t nyz = (int64_t)ny * nz, n_node = (int64_t)nx * nyz + 1;
+    int c3[3];
+    double t[3], u[3], inv[3];
+    for (int d = 0; d < 3; ++d) {
+      const double* nd = L->node[d];
+      const int i = find_cell(nd, L->nn[d], o[d], pos[d]);
+      inv[d] = 1.0 / (nd[i + 1] - nd[i]);
+      t[d] = (pos[d] - (nd[i] + o[d])) * inv[d];
+      u[d] = 1.0 - t[d];
+      c3[d] = i;
+    }
+    const int64_t base = (int64_t)cl * n_node + ((int64_t)c3[0] * ny + c3[1]) * nz + c3[2];
     double v[8][4];
     for (int c = 0; c < 8; ++c) {
       const int64_t off = base + (int64_t)(c >> 2) * nyz + (int64_t)((c >> 1) & 1) * nz + (c & 1);
       for (int q = 0; q < 4; ++q) {
-        float a = rec[0][4 * off + q];
+        float a = L->rec[0][4 * off + q];
         if (n_rec > 1) {
-          a = lerp2f(a, w[0], rec[1][4 * off + q], w[1]);
+          a = lerp2f(a, w[0], L->rec[1][4 * off + q], w[1]);
           for (int r = 2; r < n_rec; ++r) {
-            volatile float pr = rec[r][4 * off + q] * w[r];
+            volatile float pr = L->rec[r][4 * off + q] * w[r];
             volatile float sm = a + pr;
             a = sm;
           }
@@ -256,15 +276,48 @@ static void grid_interp_core(const int32_t* nn, const double* nodex, const doubl
     }
     const int ncomp = pot ? 4 : 3;
     for (int q = 0; q < ncomp; ++q) {
-      const double c00 = lerp2(v[0][q], uz, v[1][q], tz), c01 = lerp2(v[2][q], uz, v[3][q], tz);
-      const double c10 = lerp2(v[4][q], uz, v[5][q], tz), c11 = lerp2(v[6][q], uz, v[7][q], tz);
-      const double c0 = lerp2(c00, uy, c01, ty), c1 = lerp2(c10, uy, c11, ty);
-      const double r = lerp2(c0, ux, c1, tx);
+      const double c00 = lerp2(v[0][q], u[2], v[1][q], t[2]), c01 = lerp2(v[2][q], u[2], v[3][q], t[2]);
+      const double c10 = lerp2(v[4][q], u[2], v[5][q], t[2]), c11 = lerp2(v[6][q], u[2], v[7][q], t[2]);
+      const double c0 = lerp2(c00, u[1], c01, t[1]), c1 = lerp2(c10, u[1], c11, t[1]);
+      const double r = lerp2(c0, u[0], c1, t[0]);
       if (q < 3) acc[(int64_t)q * n_star + s] = r;
       else pot[s] = r;
+      if (tensor && q < 3) {
+        const double gx = (c1 - c0) * inv[0];
+        const double gy = lerp2(c01 - c00, u[0], c11 - c10, t[0]) * inv[1];
+        const double z0 = lerp2(v[1][q] - v[0][q], u[1], v[3][q] - v[2][q], t[1]);
+        const double z1 = lerp2(v[5][q] - v[4][q], u[1], v[7][q] - v[6][q], t[1]);
+        const double gz = lerp2(z0, u[0], z1, t[0]) * inv[2];
+        tensor[(int64_t)(0 + q) * n_star + s] = gx;
+        tensor[(int64_t)(3 + q) * n_star + s] = gy;
+        tensor[(int64_t)(6 + q) * n_star + s] = gz;
+      }
     }
-    if (cell) cell[s] = i, cell[n_star + s] = j, cell[2 * n_star + s] = k;
+    if (cell) cell[s] = c3[0], cell[n_star + s] = c3[1], cell[2 * n_star + s] = c3[2];
+    if (level) level[s] = lv;
   }
+}
+
+static void grid_interp_core(const int32_t* nn, const double* nodex, const double* nodey, const double* nodez,
+                             const double* origin, const float* const* rec, const float* w, int n_rec,
+                             const double* sx, const double* sy, const double* sz, const int32_t* scl, int64_t n_star,
+                             double* acc, double* pot, int32_t* cell) {
+  lattice_t L = {nn, {nodex, nodey, nodez}, rec};
+  grid_interp_core2(&L, NULL, origin, w, n_rec, sx, sy, sz, scl, n_star, acc, pot, NULL, NULL, cell);
+}
+
+/* Two-level form + tidal tensor + level output (ocg_grid_interp_nested). nn2 == NULL: single level. */
+void oracle_grid_interp_nested(const int32_t* nn, const double* nodex, const double* nodey, const double* nodez,
+                               const int32_t* nn2, const double* node2x, const double* node2y, const double* node2z,
+                               const double* origin, const float* const* rec, const float* const* rec2,
+                               const double* weights, int32_t n_rec, const double* sx, const double* sy,
+                               const double* sz, const int32_t* scl, int64_t n_star, double* acc, double* pot,
+                               double* tensor, int32_t* level, int32_t* cell) {
+  float w[4] = {0, 0, 0, 0};
+  for (int r = 0; r < n_rec; ++r) w[r] = (float)weights[r];
+  lattice_t C = {nn, {nodex, nodey, nodez}, rec};
+  lattice_t F = {nn2, {node2x, node2y, node2z}, rec2};
+  grid_interp_core2(&C, nn2 ? &F : NULL, origin, w, n_rec, sx, sy, sz, scl, n_star, acc, pot, tensor, level, cell);
 }
 
 /* Linear-in-time form (north_star): planes a, b and the weight wb of b; wa = fl32(1 - fl32(wb)). */

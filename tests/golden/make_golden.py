@@ -38,6 +38,25 @@ def main():
     out["n_cases"] = np.array(len(cases))
     np.savez_compressed(os.path.join(HERE, "grid_reference.npz"), **out)
 
+    # nested fine grid (grid.add_fine_grid, grid_cartesian.py:34-53,71-91): coarse args, fine args
+    nested = [((0.6, 0.6, 0.6, 0.05), (0.1, 0.1, 0.1, 0.01)), ((0.6, 0.3, 0.45, 0.03), (0.2, 0.1, 0.12, 0.013)),
+              ((0.6, 0.6, 0.6, 0.02), (0.02, 0.02, 0.02, 0.0021)), ((0.6, 0.6, 0.6, 0.6 / 16), (0.25, 0.25, 0.25, 0.25 / 9))]
+    out = {}
+    for k, (cargs, fargs) in enumerate(nested):
+        g = ref.grid(*cargs)
+        g.add_fine_grid(*fargs)
+        g.gen_evolved_grid(np.array([8.0, -0.25, 0.125]))
+        out["case%d_coarse_args" % k] = np.array(cargs)
+        out["case%d_fine_args" % k] = np.array(fargs)
+        out["case%d_n" % k] = np.array([g.x_n, g.y_n, g.z_n])  # overwritten with the fine counts by the reference
+        out["case%d_x_fine_grid" % k] = g.x_fine_grid
+        out["case%d_y_fine_grid" % k] = g.y_fine_grid
+        out["case%d_z_fine_grid" % k] = g.z_fine_grid
+        out["case%d_init_grid" % k] = g.init_grid
+        out["case%d_evolved_grid" % k] = g.evolved_grid
+    out["n_cases"] = np.array(len(nested))
+    np.savez_compressed(os.path.join(HERE, "grid_nested_reference.npz"), **out)
+
     # the reference's time interpolation mechanism, as-is: splrep per grid point, splev at t
     rng = np.random.default_rng(1776)
     times = np.array([0.0, 22.0, 45.5, 68.0, 91.2, 113.9])

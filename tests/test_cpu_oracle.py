@@ -47,8 +47,111 @@ def test_grid_rejects_degenerate():
     from oc_nbody_b200.grid_cartesian import grid
     with pytest.raises(ValueError):
         grid(0.6, 0.6, 0.6, 0.5)  # int(L/res) = 1 node: nothing to interpolate between
-    with pytest.raises(NotImplementedError):
-        grid(0.6, 0.6, 0.6, 0.1).add_fine_grid(0.1, 0.1, 0.1, 0.01)
+    with pytest.raises(ValueError):
+        grid(0.6, 0.6, 0.6, 0.1).add_fine_grid(0.1, 0.1, 0.1, 0.09)  # one fine node
+    with pytest.raises(ValueError):
+        grid(0.6, 0.6, 0.6, 0.1).add_fine_grid(0.7, 0.1, 0.1, 0.01)  # fine box sticks out of the coarse one
+
+
+# ------------------------------------------------------------------ nested fine grid: pinned by the reference ----
+@pytest.mark.parametrize("k", range(4))
+def test_nested_grid_layout_matches_reference_golden(k):
+    """grid.add_fine_grid: point list bit-equal to the REAL grid_cartesian.py:34-53,71-91 (kept coarse | fine | origin),
+    and the lattice bookkeeping the CUDA kernel relies on is consistent with it."""
+    from oc_nbody_b200.grid_cartesian import grid
+    z = np.load(os.path.join(GOLD, "grid_nested_reference.npz"))
+    assert k < int(z["n_cases"])
+    g = grid(*z["case%d_coarse_args" % k])
+    g.add_fine_grid(*z["case%d_fine_args" % k])
+    g.gen_evolved_grid(np.array([8.0, -0.25, 0.125]))
+    assert np.array_equal(g.init_grid, z["case%d_init_grid" % k])
+    assert np.array_equal(g.evolved_grid, z["case%d_evolved_grid" % k])
+    assert (g.x_n, g.y_n, g.z_n) == tuple(z["case%d_n" % k]) == g.fine_shape  # the reference's overwrite quirk
+    for mine, key in zip(g.fine_nodes, ("x", "y", "z")):
+        assert np.array_equal(mine, z["case%d_%s_fine_grid" % (k, key)])
+    assert np.all(g.init_grid[g.origin_row] == 0.0) and g.origin_row == len(g) - 1
+    # bookkeeping: kept rows are the full coarse lattice minus the hole, in lattice order; fine rows follow
+    full = g._lattice_points_(g.x_grid, g.y_grid, g.z_grid)
+    assert np.array_equal(full[g.coarse_keep_index], g.init_grid[:g.fine_row0])
+    assert len(g.coarse_keep_index) + len(g.coarse_hole_index) == g.n_lattice
+    fine = g._lattice_points_(*g.fine_nodes)
+    assert np.array_equal(fine, g.init_grid[g.fine_row0:-1])
+    hole = g.coarse_hole_points()
+    half = np.array([g.fine_x_size_in_kpc, g.fine_y_size_in_kpc, g.fine_z_size_in_kpc])
+    assert np.all(np.abs(hole) < half) and not np.any(np.all(np.abs(g.init_grid[:g.fine_row0]) < half, axis=1))
+
+
+def _nested_affine_setup(rng):
+    from oc_nbody_b200.grid_cartesian import grid
+    g = grid(0.6, 0.45, 0.3, 0.05)
+    g.add_fine_grid(0.2, 0.1, 0.12, 0.013)
+    A = rng.normal(0, 1, (4, 3))
+    b = rng.normal(0, 1, 4)
+    planes = (A @ g.init_grid.T + b[:, None])[None]  # [1, 4, Npoints]: an affine field sampled on the point list
+    coarse, fine = oracle.layout_nested(planes, g.n_lattice, g.coarse_keep_index, g.coarse_hole_index, g.coarse_hole_points(),
+                                        g.fine_nodes, g.fine_row0)
+    return g, A, b, coarse, fine
+
+
+def test_nested_interp_affine_field_level_rule_and_tensor():
+    """Two-level trilinear interpolation reproduces an affine field on both levels and across the hole (dropped
+    coarse points are filled from the fine lattice); the level rule is the closed fine box; the tensor of an affine
+    field is its constant gradient, T[i][j] = d a_j / d x_i (gizmo_interface.py:719-756)."""
+    rng = np.random.default_rng(11)
+    g, A, b, coarse, fine = _nested_affine_setup(rng)
+    origin = np.array([8.0, -0.25, 0.125])
+    n = 4000
+    half_c = np.array([0.6, 0.45, 0.3])
+    half_f = np.array([0.2, 0.1, 0.12])
+    p = rng.uniform(-1, 1, (n, 3)) * half_c
+    p[: n // 2] = rng.uniform(-1.3, 1.3, (n // 2, 3)) * half_f  # around / inside the fine box
+    p[0] = half_f            # corner of the fine box: inside (closed)
+    p[1] = -half_f
+    p[2] = half_f * [1.0, 1.0, np.nextafter(1.0, 2.0)]  # just outside along z
+    x = p + origin
+    out = oracle.grid_interp_nested(g.nodes, g.fine_nodes, origin, [coarse[0]], [fine[0]], [1.0], x[:, 0], x[:, 1], x[:, 2],
+                                    want_pot=True, want_tensor=True, want_level=True)
+    # the level rule is applied to evolved coordinates: fine iff node_f[0]+o <= x <= node_f[-1]+o on every axis
+    lo = np.array([a[0] for a in g.fine_nodes]) + origin
+    hi = np.array([a[-1] for a in g.fine_nodes]) + origin
+    want_level = np.all((x >= lo) & (x <= hi), axis=1).astype(np.int32)
+    assert np.array_equal(out["level"], want_level)
+    assert want_level[0] == 1 and want_level[1] == 1 and want_level[2] == 0 and 100 < want_level.sum() < n - 100
+    want = A @ p.T + b[:, None]
+    scale = np.abs(want).max()
+    assert np.max(np.abs(out["acc"] - want[:3])) <= 3e-6 * scale     # FP32 records
+    assert np.max(np.abs(out["pot"] - want[3])) <= 3e-6 * scale
+    T = out["tensor"].reshape(3, 3, n)                              # T[i][j]
+    cell_f = 2 * half_f.min() / 20
+    assert np.max(np.abs(T - A[:3].T[:, :, None])) <= 2e-6 * scale / cell_f * 10
+
+
+def test_nested_interp_single_level_equals_plain_and_tensor_matches_finite_differences():
+    rng = np.random.default_rng(12)
+    nodes = [np.linspace(-0.6, 0.6, 9), np.linspace(-0.45, 0.45, 7), np.linspace(-0.3, 0.3, 5)]
+    n_node = 9 * 7 * 5 + 1
+    recs = [oracle.pack_planes(rng.normal(0, 1, (3, n_node)), rng.normal(0, 1, n_node)) for _ in range(2)]
+    origin = np.array([1.0, 2.0, 3.0])
+    n = 500
+    x = rng.uniform(-0.95, 0.95, (n, 3)) * [0.6, 0.45, 0.3] + origin
+    ref = oracle.grid_interp(nodes, origin, recs[0], recs[1], 0.3, x[:, 0], x[:, 1], x[:, 2])
+    wb = np.float32(0.3)
+    w = [float(np.float32(np.float32(1.0) - wb)), float(wb)]
+    out = oracle.grid_interp_nested(nodes, None, origin, recs, None, w, x[:, 0], x[:, 1], x[:, 2], want_tensor=True,
+                                    want_cell=True)
+    assert np.array_equal(out["acc"], ref)
+    # central differences inside the cell (the interpolant is multilinear there)
+    h = 1e-6
+    T = out["tensor"].reshape(3, 3, n)
+    for i in range(3):
+        dx = np.zeros(3)
+        dx[i] = h
+        ap = oracle.grid_interp_nested(nodes, None, origin, recs, None, w, *(x + dx).T, want_cell=True)
+        am = oracle.grid_interp_nested(nodes, None, origin, recs, None, w, *(x - dx).T, want_cell=True)
+        same = np.all(ap["cell"] == am["cell"], axis=0)
+        fd = (ap["acc"] - am["acc"]) / (2 * h)
+        assert same.sum() > n * 0.9
+        assert np.max(np.abs(fd[:, same] - T[i][:, same])) < 1e-6 * np.abs(T).max()
 
 
 # ------------------------------------------------------------------ softening kernels ----

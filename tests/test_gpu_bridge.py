@@ -135,3 +135,65 @@ def test_bridge_steps_match_oracle(small_world, ctx):
         assert rel_err(gv, v) <= TOL
     com = cl.bound_center_of_mass()
     assert np.linalg.norm(com - center) < 2e-3
+
+
+# ------------------------------------------------------------------ the reference's default: nested fine grid ----
+@pytest.mark.parametrize("time_interpolation", ["linear", "cubic"])
+def test_field_code_with_fine_grid(ctx, time_interpolation):
+    """options with grid_fine_* (test_options:93-100 in miniature): field build on the reference's point list
+    (kept coarse | fine | origin), two-level kick, potential and tidal tensor, against the oracle pipeline."""
+    from oc_nbody_b200.gizmo_field import gizmo_field
+    from oc_nbody_b200.synthetic import advance_snapshot, make_snapshot
+    from oc_nbody_b200.units import units
+    from oc_nbody_b200 import time_spline
+    nsnap = 2 if time_interpolation == "linear" else 4
+    snaps = [make_snapshot(15000, seed=1776)]
+    for _ in range(nsnap - 1):
+        snaps.append(advance_snapshot(snaps[-1], 23.0))
+    center = np.array([8.0, 0.0, 0.0])
+    opts = dict(grid_x_size_in_kpc=0.06, grid_y_size_in_kpc=0.06, grid_z_size_in_kpc=0.06, grid_resolution=0.06 / 7,
+                fine_grid=True, grid_fine_x_size_in_kpc=0.02, grid_fine_y_size_in_kpc=0.02, grid_fine_z_size_in_kpc=0.02,
+                grid_fine_resolution=0.02 / 6, softening_kernel="spline", time_interpolation=time_interpolation)
+    field = gizmo_field(opts, snaps, chosen_positions=np.tile(center, (nsnap, 1)), ctx=ctx)
+    g = field.grid
+    assert g.has_fine_grid and g.snapshot_acceleration_x.shape == (nsnap, len(g))
+    assert len(g) == g.n_lattice - len(g.coarse_hole_index) + int(np.prod(g.fine_shape)) + 1 and len(g.coarse_hole_index) > 0
+    # field build on the nested point list vs the oracle
+    raw, sub, pot = oracle_field(field, snaps[0], center)
+    got = np.stack([g.snapshot_acceleration_x[0], g.snapshot_acceleration_y[0], g.snapshot_acceleration_z[0]])
+    assert np.all(got[:, g.origin_row] == 0.0)
+    assert rel_err(got + raw[:, g.origin_row:g.origin_row + 1], raw) <= TOL
+    # the kick: oracle layout (hole filled from the fine lattice) + two-level interpolation, bit for bit
+    planes = field._planes_()
+    t = 9.2 if time_interpolation == "linear" else 30.0
+    field.evolve_grid(center)
+    field.evolve_model(t | units.Myr)
+    if time_interpolation == "cubic":
+        knots, coef = time_spline.fit(field.time_in_Myr, planes)
+        first, w = time_spline.basis(knots, t)
+        use, weights = coef[first:first + 4], list(w)
+    else:
+        wb = np.float32(0.4)
+        use, weights = planes, [float(np.float32(np.float32(1.0) - wb)), float(wb)]
+    coarse, fine = oracle.layout_nested(use, g.n_lattice, g.coarse_keep_index, g.coarse_hole_index, g.coarse_hole_points(),
+                                        g.fine_nodes, g.fine_row0)
+    rng = np.random.default_rng(8)
+    p = rng.uniform(-0.06, 0.06, (600, 3))
+    p[:300] = rng.uniform(-0.025, 0.025, (300, 3))
+    x = p + center
+    ref = oracle.grid_interp_nested(g.nodes, g.fine_nodes, center, list(coarse), list(fine), weights, x[:, 0], x[:, 1], x[:, 2],
+                                    want_pot=True, want_tensor=True, want_level=True)
+    assert 100 < ref["level"].sum() < 500
+    ax, ay, az = field.get_gravity_at_point(0 | units.kpc, x[:, 0] | units.kpc, x[:, 1] | units.kpc, x[:, 2] | units.kpc)
+    got = np.stack([c.value_in(units.kms / units.Myr) for c in (ax, ay, az)])
+    assert np.array_equal(got, ref["acc"])
+    phi = field.get_potential_at_point(0 | units.kpc, x[:, 0] | units.kpc, x[:, 1] | units.kpc, x[:, 2] | units.kpc)
+    assert np.allclose(phi.value_in(units.kms ** 2), ref["pot"] / 1.022712165045695e-3, rtol=1e-14)
+    T = field.get_tidal_tensor_at_point(0 | units.kpc, x[:, 0] | units.kpc, x[:, 1] | units.kpc, x[:, 2] | units.kpc)
+    Tv = T.value_in(units.kms / units.Myr / units.kpc)
+    assert Tv.shape == (600, 3, 3)
+    assert np.array_equal(Tv, ref["tensor"].T.reshape(-1, 3, 3))
+    T0 = field.get_tidal_tensor_at_point(0 | units.kpc, x[0, 0] | units.kpc, x[0, 1] | units.kpc, x[0, 2] | units.kpc)
+    assert np.array_equal(T0.value_in(units.kms / units.Myr / units.kpc), Tv[0])
+    # physics: the tidal tensor of a smooth field is nearly symmetric and nearly trace-free away from sources
+    assert field.evolved_acceleration.shape == (3, len(g))

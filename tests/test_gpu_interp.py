@@ -164,3 +164,88 @@ def test_grid_interp_multi_bit_exact_and_cubic_field_code(ctx):
         want = oracle.grid_interp(nodes, origin, rec, None, 0.0, p[:200, 0], p[:200, 1], p[:200, 2])
         assert np.max(np.abs(got - want)) <= 2e-6 * np.max(np.abs(want))   # FP32 coefficient planes
         assert np.allclose(f.evolved_acceleration, ev[:3], rtol=1e-10, atol=1e-14)
+
+
+# ------------------------------------------------------------------ nested fine grid + tidal tensor ----
+def _nested_case(rng, n_planes):
+    from oc_nbody_b200.grid_cartesian import grid
+    g = grid(0.6, 0.45, 0.3, 0.05)
+    g.add_fine_grid(0.2, 0.1, 0.12, 0.013)
+    planes = rng.normal(0, 1e-2, (n_planes, 4, len(g)))
+    coarse, fine = oracle.layout_nested(planes, g.n_lattice, g.coarse_keep_index, g.coarse_hole_index, g.coarse_hole_points(),
+                                        g.fine_nodes, g.fine_row0)
+    return g, planes, coarse, fine
+
+
+def _nested_stars(rng, g, origin, n):
+    half_c = np.array([0.6, 0.45, 0.3])
+    half_f = np.array([0.2, 0.1, 0.12])
+    p = rng.uniform(-1.1, 1.1, (n, 3)) * half_c
+    p[: n // 2] = rng.uniform(-1.3, 1.3, (n // 2, 3)) * half_f
+    x = p + origin
+    k = n // 10
+    for d in range(3):  # exactly on the faces of the fine box and on fine / coarse nodes (evolved values)
+        x[:k, d] = g.fine_nodes[d][rng.integers(0, len(g.fine_nodes[d]), k)] + origin[d]
+        x[k:2 * k, d] = g.nodes[d][rng.integers(0, len(g.nodes[d]), k)] + origin[d]
+    x[2 * k:2 * k + 50, 0] = g.fine_nodes[0][-1] + origin[0]
+    x[2 * k + 50:2 * k + 100, 2] = np.nextafter(g.fine_nodes[2][0] + origin[2], -np.inf)
+    return x
+
+
+@pytest.mark.parametrize("n_planes,weights", [(1, [1.0]), (2, [0.625, 0.375]), (4, [0.1, 0.55, 0.4, -0.05])])
+def test_grid_interp_nested_bit_exact(ctx, n_planes, weights):
+    """Two-level K3 (grid_cartesian.py:34-53,71-91) + tensor + level + cell vs the oracle, bit for bit."""
+    import torch
+    rng = np.random.default_rng(40 + n_planes)
+    g, _, coarse, fine = _nested_case(rng, n_planes)
+    origin = np.array([8.0, -0.25, 0.125])
+    n = 30000
+    x = _nested_stars(rng, g, origin, n)
+    ref = oracle.grid_interp_nested(g.nodes, g.fine_nodes, origin, list(coarse), list(fine), weights, x[:, 0], x[:, 1], x[:, 2],
+                                    want_pot=True, want_tensor=True, want_level=True, want_cell=True)
+    assert 0.2 * n < ref["level"].sum() < 0.8 * n
+    acc = torch.empty((3, n), dtype=torch.float64, device="cuda")
+    pot = torch.empty(n, dtype=torch.float64, device="cuda")
+    ten = torch.empty((9, n), dtype=torch.float64, device="cuda")
+    lev = torch.empty(n, dtype=torch.int32, device="cuda")
+    cell = torch.empty((3, n), dtype=torch.int32, device="cuda")
+    d_c, d_f = dev(coarse), dev(fine)
+    ctx.grid_interp_nested(g.shape, [dev(a) for a in g.nodes], dev(origin[None]), list(d_c), weights, dev(x[:, 0].copy()),
+                           dev(x[:, 1].copy()), dev(x[:, 2].copy()), None, acc, pot, fine_n=g.fine_shape,
+                           fine_nodes=[dev(a) for a in g.fine_nodes], recs_fine=list(d_f), tensor_out=ten, level_out=lev,
+                           cell_out=cell)
+    torch.cuda.synchronize()
+    assert np.array_equal(lev.cpu().numpy(), ref["level"])
+    assert np.array_equal(cell.cpu().numpy(), ref["cell"])
+    assert np.array_equal(acc.cpu().numpy(), ref["acc"])
+    assert np.array_equal(pot.cpu().numpy(), ref["pot"])
+    assert np.array_equal(ten.cpu().numpy(), ref["tensor"])
+    # without the optional outputs the same accelerations come back (different kernel instantiation)
+    acc2 = torch.empty_like(acc)
+    ctx.grid_interp_nested(g.shape, [dev(a) for a in g.nodes], dev(origin[None]), list(d_c), weights, dev(x[:, 0].copy()),
+                           dev(x[:, 1].copy()), dev(x[:, 2].copy()), None, acc2, None, fine_n=g.fine_shape,
+                           fine_nodes=[dev(a) for a in g.fine_nodes], recs_fine=list(d_f))
+    torch.cuda.synchronize()
+    assert np.array_equal(acc2.cpu().numpy(), ref["acc"])
+
+
+def test_grid_interp_tensor_single_level_batched(ctx):
+    """Tensor output on a batch of single-level grids (no fine lattice) vs the oracle."""
+    import torch
+    rng = np.random.default_rng(77)
+    shape, ncl = (9, 7, 5), 4
+    nodes = [np.linspace(-L, L, n) for L, n in zip((0.6, 0.45, 0.3), shape)]
+    origin = rng.normal(0, 3.0, (ncl, 3))
+    _, _, rec = make_planes(rng, nodes, ncl)
+    n = 6000
+    p, scl = star_cloud(rng, nodes, origin, n)
+    w = [0.25, 0.75]
+    ref = oracle.grid_interp_nested(nodes, None, origin, [rec[0], rec[1]], None, w, p[:, 0], p[:, 1], p[:, 2], scl,
+                                    want_tensor=True)
+    acc = torch.empty((3, n), dtype=torch.float64, device="cuda")
+    ten = torch.empty((9, n), dtype=torch.float64, device="cuda")
+    ctx.grid_interp_nested(shape, [dev(a) for a in nodes], dev(origin), [dev(rec[0]), dev(rec[1])], w, dev(p[:, 0].copy()),
+                           dev(p[:, 1].copy()), dev(p[:, 2].copy()), dev(scl), acc, tensor_out=ten)
+    torch.cuda.synchronize()
+    assert np.array_equal(acc.cpu().numpy(), ref["acc"])
+    assert np.array_equal(ten.cpu().numpy(), ref["tensor"])
