@@ -110,8 +110,12 @@ def test_evolve_model_brackets_and_follows_the_grid():
     assert f._bracket[:2] == (0, 1) and np.isclose(f._bracket[2], 0.5)
     with pytest.raises(ValueError):
         _field(dict(softening_kernel="cubic"))
-    with pytest.raises(NotImplementedError):
-        _field(dict(fine_grid=True))
+    with pytest.raises(ValueError):
+        _field(dict(fine_grid=True))  # options.py:113-118: fine_grid comes with its four grid_fine_* values
+    f = _field(dict(fine_grid=True, grid_fine_x_size_in_kpc=0.1, grid_fine_y_size_in_kpc=0.1, grid_fine_z_size_in_kpc=0.1,
+                    grid_fine_resolution=0.02))
+    g = f._make_grid_()
+    assert g.has_fine_grid and g.fine_shape == (5, 5, 5) and g.origin_row == len(g) - 1
 
 
 def test_bridge_orders_kicks_and_drifts_like_amuse():
