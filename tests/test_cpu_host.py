@@ -112,7 +112,7 @@ def test_evolve_model_brackets_and_follows_the_grid():
         _field(dict(softening_kernel="cubic"))
     with pytest.raises(ValueError):
         _field(dict(fine_grid=True))  # options.py:113-118: fine_grid comes with its four grid_fine_* values
-    f = _field(dict(fine_grid=True, grid_fine_x_size_in_kpc=0.1, grid_fine_y_size_in_kpc=0.1, grid_fine_z_size_in_kpc=0.1,
+    f, _ = _field(dict(fine_grid=True, grid_fine_x_size_in_kpc=0.1, grid_fine_y_size_in_kpc=0.1, grid_fine_z_size_in_kpc=0.1,
                     grid_fine_resolution=0.02))
     g = f._make_grid_()
     assert g.has_fine_grid and g.fine_shape == (5, 5, 5) and g.origin_row == len(g) - 1
