@@ -197,6 +197,27 @@ int ocg_drift(ocg_ctx* ctx, double* pos_dev, const double* vel_dev, int64_t n, d
 /* acc_sum = a + scale_b * b  (combine self-gravity with the tidal kick in other units) */
 int ocg_axpy(ocg_ctx* ctx, double* y_dev, const double* x_dev, double a, int64_t n, void* stream);
 
+/* ---- per-step cluster bookkeeping of the driver loop, on the device ----------------------------
+ * Bound subset + its centre of mass (oc_nbody.py:60-61: particles.bound_subset().center_of_mass(), fed to
+ * evolve_grid at oc_nbody.py:64).  A star is bound iff 0.5*|v - v_com|^2 + pot_to_v2*pot < 0, v_com the velocity of
+ * the cluster's centre of mass; when no star is bound every star counts.  One result row per segment (cluster):
+ *   out_dev[seg][0..2] centre of mass of the bound stars, [3] their mass, [4] their number, [5..7] v_com.
+ * pos_dev/vel_dev fp64 [3][n], mass_dev/pot_dev fp64 [n] (pot from ocg_self_gravity); seg_offsets_dev: DEVICE
+ * int64 [n_seg+1] or NULL for one segment [0,n); bound_mask_dev: uint8 [n] or NULL.                            */
+int ocg_bound_com(ocg_ctx* ctx, const double* pos_dev, const double* vel_dev, const double* mass_dev,
+                  const double* pot_dev, int64_t n, const int64_t* seg_offsets_dev, int32_t n_seg,
+                  double pot_to_v2, double* out_dev, uint8_t* bound_mask_dev, void* stream);
+/* Ejection cut of clean_ejections (oc_code.py:231-246): keep[i] = 0 iff |len_scale*(x_i - median(x))| > cut,
+ * the median taken per axis exactly as numpy.median does (mean of the two middle order statistics).
+ * median_out_dev: fp64 [3] or NULL.                                                                           */
+int ocg_eject_mask(ocg_ctx* ctx, const double* pos_dev, int64_t n, double len_scale, double cut,
+                   uint8_t* keep_mask_dev, double* median_out_dev, void* stream);
+/* Stable compaction (particles.remove_particles, oc_code.py:241-242): out[r][j] = in[r][i_j] for the j-th kept
+ * index i_j; in_dev fp64 [rows][n], out_dev fp64 with row stride out_stride (NULL: count only);
+ * n_keep_dev: DEVICE int64 receiving the number kept (nullable).                                              */
+int ocg_compact_rows(ocg_ctx* ctx, const double* in_dev, int32_t rows, int64_t n, const uint8_t* keep_mask_dev,
+                     double* out_dev, int64_t out_stride, int64_t* n_keep_dev, void* stream);
+
 /* ---- probes (roofline denominators measured live by bench.py) ------------------------------- */
 /* Runs an FFMA-only kernel (packed=0: FFMA, packed=1: FFMA2) over the whole GPU and returns
  * achieved TFLOP/s (2 flop per lane-FMA). which: 0 FFMA, 1 FFMA2, 2 MUFU.RSQ (G ops/s).     */

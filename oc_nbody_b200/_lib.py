@@ -20,7 +20,7 @@ ABI_SYMBOLS = [
     "ocg_version", "ocg_create", "ocg_destroy", "ocg_last_error", "ocg_device_info", "ocg_launch_count",
     "ocg_last_direct_kernel_ms", "ocg_set_kernel_timing", "ocg_recentre_f64", "ocg_cast_f64_f32",
     "ocg_field_direct", "ocg_frame_subtract", "ocg_field_build_host", "ocg_pack_planes", "ocg_grid_time_blend",
-    "ocg_grid_interp", "ocg_grid_interp_multi", "ocg_grid_interp_nested", "ocg_pack_planes_indexed", "ocg_self_gravity", "ocg_kick", "ocg_drift", "ocg_axpy", "ocg_probe_throughput",
+    "ocg_grid_interp", "ocg_grid_interp_multi", "ocg_grid_interp_nested", "ocg_pack_planes_indexed", "ocg_self_gravity", "ocg_bound_com", "ocg_eject_mask", "ocg_compact_rows", "ocg_kick", "ocg_drift", "ocg_axpy", "ocg_probe_throughput",
 ]
 
 
@@ -71,6 +71,9 @@ def load_library():
                                          i32, vp, vp, vp, vp, i64, vp, vp, vp, vp, vp, vp]
     L.ocg_pack_planes_indexed.argtypes = [vp, vp, vp, i64, vp, vp, vp]
     L.ocg_self_gravity.argtypes = [vp, vp, vp, i64, vp, i32, dbl, dbl, i64, i64, vp, vp, vp]
+    L.ocg_bound_com.argtypes = [vp, vp, vp, vp, vp, i64, vp, i32, dbl, vp, vp, vp]
+    L.ocg_eject_mask.argtypes = [vp, vp, i64, dbl, dbl, vp, vp, vp]
+    L.ocg_compact_rows.argtypes = [vp, vp, i32, i64, vp, vp, i64, vp, vp]
     L.ocg_kick.argtypes = [vp, vp, vp, i64, dbl, vp]
     L.ocg_drift.argtypes = [vp, vp, vp, i64, dbl, dbl, vp]
     L.ocg_axpy.argtypes = [vp, vp, vp, dbl, i64, vp]
@@ -254,6 +257,23 @@ class Context:
         self._ck(self.lib.ocg_self_gravity(self.h, _dptr(pos), _dptr(mass), n, _hptr(seg), n_seg, float(eps2), float(G),
                                            int(tgt_begin), int(tgt_end), _dptr(acc), _dptr(pot), self._stream()),
                  "ocg_self_gravity")
+
+    def bound_com(self, pos, vel, mass, pot, pot_to_v2, out, seg_offsets=None, bound_mask=None):
+        """out [n_seg, 8] fp64 device: bound-subset COM (3), bound mass, bound count, COM velocity (3)."""
+        n_seg = 1 if seg_offsets is None else seg_offsets.shape[0] - 1
+        self._ck(self.lib.ocg_bound_com(self.h, _dptr(pos), _dptr(vel), _dptr(mass), _dptr(pot), pos.shape[1], _dptr(seg_offsets),
+                                        n_seg, float(pot_to_v2), _dptr(out), _dptr(bound_mask), self._stream()), "ocg_bound_com")
+
+    def eject_mask(self, pos, len_scale, cut, keep_mask, median_out=None):
+        self._ck(self.lib.ocg_eject_mask(self.h, _dptr(pos), pos.shape[1], float(len_scale), float(cut), _dptr(keep_mask),
+                                         _dptr(median_out), self._stream()), "ocg_eject_mask")
+
+    def compact_rows(self, rows_in, keep_mask, rows_out, n_keep):
+        """rows_in [R, n] fp64 -> rows_out [R, n_out] (or None: count only); n_keep: int64 device scalar."""
+        R, n = rows_in.shape
+        self._ck(self.lib.ocg_compact_rows(self.h, _dptr(rows_in), R, n, _dptr(keep_mask), _dptr(rows_out),
+                                           0 if rows_out is None else rows_out.shape[1], _dptr(n_keep), self._stream()),
+                 "ocg_compact_rows")
 
     def kick(self, vel, acc, dt):
         self._ck(self.lib.ocg_kick(self.h, _dptr(vel), _dptr(acc), vel.shape[1], float(dt), self._stream()), "ocg_kick")

@@ -19,6 +19,7 @@ SOURCES = [
     ("direct_sum", "direct_sum.cu", []),
     ("self_gravity", "self_gravity.cu", []),
     ("grid_interp", "grid_interp.cu", []),
+    ("cluster_ops", "cluster_ops.cu", []),
 ]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -118,10 +118,30 @@ class cluster_code(object):
 
     def remove_particles(self, idx):
         """Drop particles by index (system.particles.remove_particles, oc_code.py:241-242)."""
-        keep = np.ones(self.n, bool)
-        keep[np.asarray(idx, np.int64)] = False
-        p = self.particles
-        self._set_state_(p._m[keep], p._x[:, keep], p._v[:, keep], p.key[keep])
+        import torch
+        keep = torch.ones(self.n, dtype=torch.uint8, device=self._dev)
+        keep[torch.as_tensor(np.asarray(idx, np.int64), device=self._dev)] = 0
+        self._compact_(keep)
+
+    def _compact_(self, keep):
+        """Stable on-device compaction of mass / pos / vel by a byte mask (ocg_compact_rows); returns the removed indices."""
+        import torch
+        rows = torch.cat([self.mass[None], self.pos, self.vel], dim=0).contiguous()  # [7, n]
+        n_keep = torch.zeros(1, dtype=torch.int64, device=self._dev)
+        self.ctx.compact_rows(rows, keep, None, n_keep)
+        nk = int(n_keep.item())
+        removed = torch.nonzero(keep == 0).flatten().cpu().numpy()
+        if nk == self.n:
+            return removed
+        out = torch.empty((7, nk), dtype=torch.float64, device=self._dev)
+        self.ctx.compact_rows(rows, keep, out, n_keep)
+        self.n = nk
+        self.mass, self.pos, self.vel = out[0].contiguous(), out[1:4].contiguous(), out[4:7].contiguous()
+        self.acc = torch.empty((3, nk), dtype=torch.float64, device=self._dev)
+        self.pot = torch.empty(nk, dtype=torch.float64, device=self._dev)
+        self.key = self.key[np.setdiff1d(np.arange(len(self.key)), removed)]
+        self._acc_valid = False
+        return removed
 
     # ---- gravity ----
     def compute_self_gravity(self, want_pot=False):
@@ -156,29 +176,28 @@ class cluster_code(object):
 
     # ---- driver helpers ----
     def clean_ejections(self, system=None):
-        """Remove stars farther than `eject_cut` pc from the median position (oc_code.py:231-246)."""
+        """Remove stars farther than `eject_cut` pc from the median position (oc_code.py:231-246): median select,
+        distance test and compaction all on the device."""
+        import torch
         if self.eject_cut is None:
             return None
-        x_pc = self.pos.cpu().numpy().T * 1000.0
-        dist = np.linalg.norm(x_pc - np.median(x_pc, axis=0), axis=1)
-        keys = np.where(dist > float(self.eject_cut))[0]
-        if len(keys):
-            self.remove_particles(keys)
-        return keys
+        keep = torch.empty(self.n, dtype=torch.uint8, device=self._dev)
+        self.ctx.eject_mask(self.pos, 1000.0, float(self.eject_cut), keep)
+        return self._compact_(keep)
 
-    def bound_center_of_mass(self):
-        """Centre of mass (kpc) of the bound subset: E_i = v_i^2/2 + phi_i < 0 in the cluster's COM frame
-        (oc_nbody.py:60-61: particles.bound_subset().center_of_mass())."""
+    def bound_center_of_mass(self, return_mask=False):
+        """Centre of mass (kpc) of the bound subset: E_i = |v_i - v_com|^2/2 + phi_i < 0
+        (oc_nbody.py:60-61: particles.bound_subset().center_of_mass()).  K4 with the potential, then one reduction
+        kernel; only the 8-double result row comes back to the host."""
+        import torch
         self.compute_self_gravity(want_pot=True)
-        m = self.mass.cpu().numpy()
-        x = self.pos.cpu().numpy()
-        v = self.vel.cpu().numpy()
-        phi = self.pot.cpu().numpy() / KMS_TO_KPC_PER_MYR  # kpc km/s /Myr -> (km/s)^2
-        vc = v - (v * m).sum(axis=1, keepdims=True) / m.sum()
-        bound = 0.5 * (vc * vc).sum(axis=0) + phi < 0.0
-        if not bound.any():
-            bound[:] = True
-        return (x[:, bound] * m[bound]).sum(axis=1) / m[bound].sum()
+        out = torch.empty((1, 8), dtype=torch.float64, device=self._dev)
+        mask = torch.empty(self.n, dtype=torch.uint8, device=self._dev) if return_mask else None
+        # pot is in kpc km/s /Myr; 1/KMS_TO_KPC_PER_MYR turns it into (km/s)^2
+        self.ctx.bound_com(self.pos, self.vel, self.mass, self.pot, 1.0 / KMS_TO_KPC_PER_MYR, out, None, mask)
+        res = out.cpu().numpy()[0]
+        self.n_bound, self.bound_mass = int(res[4]), float(res[3])
+        return (res[:3], mask.cpu().numpy().astype(bool)) if return_mask else res[:3]
 
     def stop(self):
         pass

@@ -262,6 +262,28 @@ def layout_nested(planes, n_coarse, keep_index, hole_index, hole_points, fine_no
     return coarse, fine
 
 
+def bound_com(pos, vel, mass, pot_v2):
+    """Bound subset and its centre of mass (oc_nbody.py:60-61, particles.bound_subset().center_of_mass()):
+    E_i = |v_i - v_com|^2 / 2 + phi_i < 0 with v_com the velocity of the cluster's centre of mass; everything
+    counts when nothing is bound.  pos, vel [3, n]; pot_v2 [n] in velocity^2 units. Returns (com[3], mask[n], v_com[3])."""
+    pos, vel, mass, pot_v2 = (np.asarray(a, np.float64) for a in (pos, vel, mass, pot_v2))
+    vcom = (vel * mass).sum(axis=1) / mass.sum()
+    dv = vel - vcom[:, None]
+    bound = 0.5 * (dv * dv).sum(axis=0) + pot_v2 < 0.0
+    if not bound.any():
+        bound[:] = True
+    return (pos[:, bound] * mass[bound]).sum(axis=1) / mass[bound].sum(), bound, vcom
+
+
+def eject_keep(pos, len_scale, cut):
+    """clean_ejections (oc_code.py:231-246): stars farther than `cut` from the per-axis median position are
+    removed. pos [3, n]. Returns (keep[n] bool, median[3])."""
+    pos = np.asarray(pos, np.float64)
+    med = np.median(pos, axis=1)
+    d = (pos - med[:, None]) * len_scale
+    return ~(np.sqrt((d * d).sum(axis=0)) > cut), med
+
+
 def kick(vel, acc, dt):
     vel = np.array(vel, np.float64, order="C", copy=True)
     acc = _c(acc, np.float64)

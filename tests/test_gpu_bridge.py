@@ -197,3 +197,82 @@ def test_field_code_with_fine_grid(ctx, time_interpolation):
     assert np.array_equal(T0.value_in(units.kms / units.Myr / units.kpc), Tv[0])
     # physics: the tidal tensor of a smooth field is nearly symmetric and nearly trace-free away from sources
     assert field.evolved_acceleration.shape == (3, len(g))
+
+
+# ------------------------------------------------------------------ per-step cluster bookkeeping on the device ----
+@pytest.mark.parametrize("n", [1000, 1025, 4096])
+def test_bound_com_eject_and_compaction_match_oracle(ctx, n):
+    """ocg_bound_com / ocg_eject_mask / ocg_compact_rows vs the numpy restatement of oc_nbody.py:60-61 and
+    oc_code.py:231-246: masks and medians bit for bit, centre of mass to FP64 summation-order accuracy."""
+    import torch
+    from util import dev
+    rng = np.random.default_rng(n)
+    pos = rng.normal(0, 1e-3, (3, n)) + np.array([[8.0], [0.1], [-0.2]])
+    vel = rng.normal(0, 0.5, (3, n)) + np.array([[10.0], [200.0], [5.0]])
+    vel[:, ::7] += rng.normal(0, 30.0, (3, len(range(0, n, 7))))      # unbound escapers
+    pos[:, 3::50] += rng.normal(0, 0.2, (3, len(range(3, n, 50))))     # far-flung stars for the ejection cut
+    mass = rng.uniform(0.3, 3.0, n)
+    pot_v2 = -rng.uniform(0.5, 20.0, n)
+    d_pos, d_vel, d_mass, d_pot = dev(pos), dev(vel), dev(mass), dev(pot_v2)
+    out = torch.empty((1, 8), dtype=torch.float64, device="cuda")
+    mask = torch.empty(n, dtype=torch.uint8, device="cuda")
+    ctx.bound_com(d_pos, d_vel, d_mass, d_pot, 1.0, out, None, mask)
+    torch.cuda.synchronize()
+    com, bound, vcom = oracle.bound_com(pos, vel, mass, pot_v2)
+    res = out.cpu().numpy()[0]
+    assert 0 < bound.sum() < n
+    assert np.array_equal(mask.cpu().numpy().astype(bool), bound)
+    assert res[4] == bound.sum() and np.isclose(res[3], mass[bound].sum(), rtol=1e-13)
+    assert np.allclose(res[:3], com, rtol=1e-13, atol=0) and np.allclose(res[5:], vcom, rtol=1e-13, atol=0)
+    # nothing bound -> every star counts
+    ctx.bound_com(d_pos, d_vel, d_mass, dev(np.full(n, 1e9)), 1.0, out, None, mask)
+    torch.cuda.synchronize()
+    assert int(out[0, 4].item()) == n and bool(mask.all())
+    assert np.allclose(out.cpu().numpy()[0, :3], (pos * mass).sum(axis=1) / mass.sum(), rtol=1e-13)
+    # a batch of clusters (segments), one result row each
+    seg = np.array([0, n // 3, n // 3 + 1, n], np.int64)
+    out3 = torch.empty((3, 8), dtype=torch.float64, device="cuda")
+    ctx.bound_com(d_pos, d_vel, d_mass, d_pot, 1.0, out3, dev(seg), None)
+    torch.cuda.synchronize()
+    for k in range(3):
+        a, b = seg[k], seg[k + 1]
+        c, bd, _ = oracle.bound_com(pos[:, a:b], vel[:, a:b], mass[a:b], pot_v2[a:b])
+        assert np.allclose(out3.cpu().numpy()[k, :3], c, rtol=1e-13) and out3[k, 4].item() == bd.sum()
+
+    # ejection cut: exact medians (odd and even n), keep mask, stable compaction
+    keep = torch.empty(n, dtype=torch.uint8, device="cuda")
+    med = torch.empty(3, dtype=torch.float64, device="cuda")
+    ctx.eject_mask(d_pos, 1000.0, 20.0, keep, med)
+    torch.cuda.synchronize()
+    want_keep, want_med = oracle.eject_keep(pos, 1000.0, 20.0)
+    assert np.array_equal(med.cpu().numpy(), want_med)
+    assert np.array_equal(keep.cpu().numpy().astype(bool), want_keep) and 0 < want_keep.sum() < n
+    rows = np.concatenate([mass[None], pos, vel])
+    nk = torch.zeros(1, dtype=torch.int64, device="cuda")
+    outr = torch.full((7, int(want_keep.sum())), np.nan, dtype=torch.float64, device="cuda")
+    ctx.compact_rows(dev(rows), keep, outr, nk)
+    torch.cuda.synchronize()
+    assert int(nk.item()) == want_keep.sum()
+    assert np.array_equal(outr.cpu().numpy(), rows[:, want_keep])
+
+
+def test_cluster_code_clean_ejections_and_bound_com(ctx):
+    from oc_nbody_b200.cluster import KMS_TO_KPC_PER_MYR, cluster_code
+    from oc_nbody_b200.synthetic import make_plummer_cluster
+    pos_pc, vel, mass = make_plummer_cluster(2000)
+    center = np.array([8.0, 0.0, 0.0])
+    pos = pos_pc * 1e-3 + center[:, None]
+    pos[:, 5] += 0.5          # 500 pc away: ejected
+    vel[:, 11] += 300.0       # unbound but still inside the cut
+    cl = cluster_code(mass, pos, vel, softening_pc=0.01, eject_cut=100.0, ctx=ctx)
+    removed = cl.clean_ejections()
+    want_keep, _ = oracle.eject_keep(pos, 1000.0, 100.0)
+    assert list(removed) == list(np.where(~want_keep)[0]) and 5 in removed and cl.n == want_keep.sum()
+    p = cl.particles
+    assert np.array_equal(p.position.value_in(p.position.unit).T, pos[:, want_keep]) and np.array_equal(p.key, np.where(want_keep)[0])
+    com, mask = cl.bound_center_of_mass(return_mask=True)
+    x, v, m = pos[:, want_keep], vel[:, want_keep], mass[want_keep]
+    _, phi = oracle.self_gravity(x, m, (0.01e-3) ** 2, cl.G, want_pot=True)
+    want_com, want_mask, _ = oracle.bound_com(x, v, m, phi / KMS_TO_KPC_PER_MYR)
+    assert np.array_equal(mask, want_mask) and not want_mask[list(np.where(want_keep)[0]).index(11)]
+    assert np.allclose(com - center, want_com - center, rtol=1e-6, atol=1e-12)
