@@ -201,3 +201,53 @@ class cluster_code(object):
 
     def stop(self):
         pass
+
+
+class sharded_cluster_code(cluster_code):
+    """The cluster code with its stars block-sharded over the ranks of a torch.distributed group (one process per
+    GPU): every rank owns stars [a, b) = shard_range(n_total, rank, world) — positions, velocities,
+    masses of that block only.  Each self-gravity evaluation all-gathers the positions over NCCL (1.5 MB at
+    N = 65 536) and runs K4 for the rank's target range; kicks, drifts and the tidal K3 gather are local.
+
+    mass / pos / vel passed in are the FULL arrays (identical on every rank); the constructor keeps the block."""
+
+    def __init__(self, mass, pos, vel, softening_pc=0.01, substeps=1, eject_cut=None, ctx=None, group=None):
+        import torch.distributed as dist
+        from .distributed import shard_range
+        self.group = group
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        mass = np.asarray(to_value(mass, units.MSun), np.float64)
+        self.n_total = mass.shape[0]
+        self.a, self.b = shard_range(self.n_total, self.rank, self.world)
+        pos = np.asarray(to_value(pos, units.kpc), np.float64)
+        vel = np.asarray(to_value(vel, units.kms), np.float64)
+        super().__init__(mass[self.a:self.b], pos[:, self.a:self.b], vel[:, self.a:self.b], softening_pc=softening_pc,
+                         substeps=substeps, eject_cut=eject_cut, ctx=ctx)
+        import torch
+        self.mass_all = torch.from_numpy(np.ascontiguousarray(mass)).to(self._dev)
+        self._acc_all = torch.empty((3, self.n_total), dtype=torch.float64, device=self._dev)
+        self._pot_all = torch.empty(self.n_total, dtype=torch.float64, device=self._dev)
+        self.key = np.arange(self.a, self.b)
+
+    def compute_self_gravity(self, want_pot=False):
+        from .distributed import allgather_particles
+        pos_all = allgather_particles(self.pos, self.n_total, self.group).contiguous()
+        self.ctx.self_gravity(pos_all, self.mass_all, self.parameters._eps2_kpc2, self.G, self._acc_all,
+                              self._pot_all if want_pot else None, tgt_begin=self.a, tgt_end=self.b)
+        self.acc.copy_(self._acc_all[:, self.a:self.b])
+        if want_pot:
+            self.pot.copy_(self._pot_all[self.a:self.b])
+        self._acc_valid = True
+        return self.acc
+
+    def gather_state(self):
+        """(pos [3, n_total], vel [3, n_total]) on every rank (for output / verification)."""
+        from .distributed import allgather_particles
+        return (allgather_particles(self.pos, self.n_total, self.group), allgather_particles(self.vel, self.n_total, self.group))
+
+    def clean_ejections(self, system=None):
+        raise NotImplementedError("ejections change the block partition; gather, clean on one rank, and re-shard")
+
+    def bound_center_of_mass(self, return_mask=False):
+        raise NotImplementedError("use gather_state() and a single-rank cluster_code for the bound-subset reduction")

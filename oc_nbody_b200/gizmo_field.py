@@ -36,6 +36,9 @@ _DEFAULTS = dict(
     grid_fine_x_size_in_kpc=None, grid_fine_y_size_in_kpc=None, grid_fine_z_size_in_kpc=None, grid_fine_resolution=None,
     # "linear" (BASELINE.json north_star) or "cubic" (the reference's own splrep/splev, gizmo_interface.py:587-620)
     time_interpolation="linear",
+    # per-snapshot field caches in the reference's own file names and format (gizmo_interface.py:373-391,454-459,
+    # 470-495): None = no caching.  The remaining keys only enter the cache file name.
+    cache_directory=None, sim_name="synthetic", grid_seed=1776, Rmax=50.0, startnum=None, endnum=None, num_prior=0,
 )
 
 
@@ -144,13 +147,83 @@ class gizmo_field(object):
                             self.grid_fine_resolution)
         return g
 
+    # ---- the reference's per-snapshot field caches (gizmo_interface.py:373-391,454-459,470-495) ----
+    def _grid_cache_name_(self, snapshot_index=None):
+        """Same file name, character for character, as gizmo_interface.py:373-391."""
+        if snapshot_index is not None:
+            cache_name = 'grid_snapshot' + str(snapshot_index) + '_'
+        else:
+            cache_name = 'grid_'
+        cache_name += self.sim_name
+        cache_name += '_ssid' + str(self.chosen_id)
+        cache_name += '_gridseed' + str(self.grid_seed) + '_Rmax' + str(self.Rmax)
+        cache_name += '_theta' + str(self.theta) + '_grid_x_size' + str(self.grid_x_size_in_kpc)
+        cache_name += '_grid_y_size' + str(self.grid_y_size_in_kpc)
+        cache_name += '_grid_z_size' + str(self.grid_z_size_in_kpc)
+        if self.fine_grid:
+            cache_name += '_fine_grid_x_size' + str(self.grid_fine_x_size_in_kpc)
+            cache_name += '_fine_grid_y_size' + str(self.grid_fine_y_size_in_kpc)
+            cache_name += '_fine_grid_z_size' + str(self.grid_fine_z_size_in_kpc)
+            cache_name += '_fine_grid_resolution' + str(self.grid_fine_resolution)
+        cache_name += '_start' + str(self.startnum)
+        cache_name += '_end' + str(self.endnum) + '_numprior' + str(self.num_prior)
+        return cache_name, str(self.cache_directory) + '/' + cache_name
+
+    def _snapshot_cache_files_(self, snapshot_index):
+        """x, y, z files as the reference derives them (gizmo_interface.py:441-446: 'snapshot' -> 'snapshot_x' ...)
+        + our potential file.  The reference runs str.replace over the whole PATH, so a cache directory whose name
+        contains 'snapshot' would be rewritten too; here only the file name is touched."""
+        name, _ = self._grid_cache_name_(snapshot_index)
+        return tuple(str(self.cache_directory) + '/' + name.replace('snapshot', 'snapshot_' + c) for c in ('x', 'y', 'z', 'pot'))
+
+    def _load_snapshot_cache_(self, snapshot_index, n_points, want_pot):
+        """Pickled FP64 [Ngrid+1] arrays the reference (or this code) wrote; None on any miss or shape mismatch."""
+        import pickle
+        if self.cache_directory is None:
+            return None
+        files = self._snapshot_cache_files_(snapshot_index)
+        try:
+            out = []
+            for f in files[:4 if want_pot else 3]:
+                with open(f, 'rb') as fh:
+                    a = np.asarray(pickle.load(fh), np.float64)
+                if a.shape != (n_points,):
+                    return None
+                out.append(a)
+            return tuple(out)
+        except (OSError, pickle.UnpicklingError, EOFError, ValueError):
+            return None
+
+    def _dump_snapshot_cache_(self, snapshot_index, arrays):
+        """pickle protocol 4 of each array into its own file (gizmo_interface.py:454-459,490-495)."""
+        import os
+        import pickle
+        if self.cache_directory is None:
+            return
+        os.makedirs(str(self.cache_directory), exist_ok=True)
+        for f, a in zip(self._snapshot_cache_files_(snapshot_index), arrays):
+            with open(f, 'wb') as fh:
+                pickle.dump(np.asarray(a, np.float64), fh, protocol=4)
+
     def _init_grid_(self):
-        """Per-snapshot grid loop (gizmo_interface.py:393-510, minus the pickle caches)."""
+        """Per-snapshot grid loop (gizmo_interface.py:393-510): load the snapshot's cached field or build it on the
+        GPU and write the cache in the reference's format.  (The reference's whole-``grid`` pickle, :395-398/:510, is
+        a pickle of ITS class and is not produced; the per-snapshot arrays are the expensive part.)"""
         self.grid = self._make_grid_()
+        if self.startnum is None:
+            self.startnum = self.snapshots[0].snapshot["index"]
+        if self.endnum is None:
+            self.endnum = self.snapshots[-1].snapshot["index"]
         ax, ay, az, ph = [], [], [], []
+        self.cache_hits = 0
         for i, snap in enumerate(self.snapshots):
             self.grid.gen_evolved_grid(self.chosen_snapshot_positions[i])
-            res = self._populate_grid_acceleration_(snap, self.grid, want_pot=self.with_potential)
+            res = self._load_snapshot_cache_(snap.snapshot["index"], len(self.grid), self.with_potential)
+            if res is not None:
+                self.cache_hits += 1
+            else:
+                res = self._populate_grid_acceleration_(snap, self.grid, want_pot=self.with_potential)
+                self._dump_snapshot_cache_(snap.snapshot["index"], res)
             ax.append(res[0]), ay.append(res[1]), az.append(res[2])
             if self.with_potential:
                 ph.append(res[3])

@@ -165,3 +165,40 @@ def test_shard_bounds():
     assert list(b) == [0, 3, 6, 8, 10]
     assert shard_range(10_000_000, 7, 8) == (8750000, 10000000)
     assert list(shard_bounds(3, 5)) == [0, 1, 2, 3, 3, 3]
+
+
+def test_snapshot_cache_names_and_format_follow_the_reference(tmp_path):
+    """gizmo_interface.py:373-391 (name), :441-446 ('snapshot' -> 'snapshot_x/_y/_z'), :454-459 (pickle protocol 4 of one
+    FP64 array per file): files written the reference's way are found and read; ours are readable the reference's way."""
+    import pickle
+    opts = dict(cache_directory=str(tmp_path), sim_name="m12i_res7100", grid_seed=1776, Rmax=50.0, theta=0.5, startnum=577,
+                endnum=585, num_prior=3, grid_x_size_in_kpc=0.6, grid_y_size_in_kpc=0.6, grid_z_size_in_kpc=0.6)
+    f, _ = _field(opts)
+    name, path = f._grid_cache_name_()
+    assert name == ("grid_m12i_res7100_ssid7_gridseed1776_Rmax50.0_theta0.5_grid_x_size0.6_grid_y_size0.6_grid_z_size0.6"
+                    "_start577_end585_numprior3") and path == str(tmp_path) + "/" + name
+    sname, _ = f._grid_cache_name_(580)
+    assert sname.startswith("grid_snapshot580_m12i_res7100_ssid7_")
+    files = f._snapshot_cache_files_(580)
+    assert [os.path.basename(x)[:len("grid_snapshot_x580")] for x in files[:3]] == ["grid_snapshot_x580", "grid_snapshot_y580",
+                                                                                     "grid_snapshot_z580"]
+    ff, _ = _field(dict(opts, fine_grid=True, grid_fine_x_size_in_kpc=0.02, grid_fine_y_size_in_kpc=0.02,
+                        grid_fine_z_size_in_kpc=0.02, grid_fine_resolution=0.0005))
+    assert "_fine_grid_x_size0.02_fine_grid_y_size0.02_fine_grid_z_size0.02_fine_grid_resolution0.0005_start577" in \
+        ff._grid_cache_name_()[0]
+    # a cache written the reference's way (three pickles, protocol 4) is a hit; wrong length or missing file is a miss
+    rng = np.random.default_rng(0)
+    arrs = [rng.normal(size=4097) for _ in range(3)]
+    for path, a in zip(files[:3], arrs):
+        pickle.dump(a, open(path, "wb"), protocol=4)
+    got = f._load_snapshot_cache_(580, 4097, want_pot=False)
+    assert got is not None and all(np.array_equal(g, a) for g, a in zip(got, arrs))
+    assert f._load_snapshot_cache_(580, 4096, want_pot=False) is None
+    assert f._load_snapshot_cache_(580, 4097, want_pot=True) is None      # no potential file: recompute
+    assert f._load_snapshot_cache_(581, 4097, want_pot=False) is None
+    # and what we write is what the reference reads back with pickle.load
+    f._dump_snapshot_cache_(581, arrs + [arrs[0] * 2])
+    for path, a in zip(f._snapshot_cache_files_(581), arrs + [arrs[0] * 2]):
+        assert np.array_equal(pickle.load(open(path, "rb")), a)
+    f.cache_directory = None
+    assert f._load_snapshot_cache_(580, 4097, want_pot=False) is None

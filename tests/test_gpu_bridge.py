@@ -276,3 +276,39 @@ def test_cluster_code_clean_ejections_and_bound_com(ctx):
     want_com, want_mask, _ = oracle.bound_com(x, v, m, phi / KMS_TO_KPC_PER_MYR)
     assert np.array_equal(mask, want_mask) and not want_mask[list(np.where(want_keep)[0]).index(11)]
     assert np.allclose(com - center, want_com - center, rtol=1e-6, atol=1e-12)
+
+
+def test_field_code_snapshot_caches_round_trip(ctx, tmp_path):
+    """Second construction with the same options is served from the reference-format caches, bit for bit."""
+    from oc_nbody_b200.gizmo_field import gizmo_field
+    from oc_nbody_b200.synthetic import advance_snapshot, make_snapshot
+    snaps = [make_snapshot(5000, seed=3)]
+    snaps.append(advance_snapshot(snaps[0], 23.0))
+    opts = dict(grid_x_size_in_kpc=0.06, grid_y_size_in_kpc=0.06, grid_z_size_in_kpc=0.06, grid_resolution=0.06 / 5,
+                cache_directory=str(tmp_path / "cache"))
+    a = gizmo_field(opts, snaps, ctx=ctx)
+    assert a.cache_hits == 0 and len(list((tmp_path / "cache").iterdir())) == 8
+    b = gizmo_field(opts, snaps, ctx=ctx)
+    assert b.cache_hits == 2
+    for k in ("snapshot_acceleration_x", "snapshot_acceleration_y", "snapshot_acceleration_z", "snapshot_potential"):
+        assert np.array_equal(getattr(a.grid, k), getattr(b.grid, k))
+    c = gizmo_field(dict(opts, with_potential=False), snaps, ctx=ctx)
+    assert c.cache_hits == 2 and c.grid.snapshot_potential is None
+
+
+def test_two_gpu_sharded_bridge_matches_single_gpu():
+    """K4 target-sharded over 2 GPUs with an NCCL all-gather of the positions per evaluation (tools/bridge_multi.py)."""
+    import json
+    import os
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29517", os.path.join(root, "tools", "bridge_multi.py"), "--n", "8192", "--steps", "2"]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+    line = json.loads([ln for ln in res.stdout.splitlines() if ln.startswith("{")][-1])
+    assert line["match"] and line["n_gpus"] == 2
