@@ -307,7 +307,7 @@ def test_two_gpu_sharded_bridge_matches_single_gpu():
         pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
-           "--master-port", "29517", os.path.join(root, "tools", "bridge_multi.py"), "--n", "8192", "--steps", "2"]
+           "--master-port", "29517", os.path.join(root, "tools", "bridge_multi.py"), "--stars", "8192", "--steps", "2"]
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
     line = json.loads([ln for ln in res.stdout.splitlines() if ln.startswith("{")][-1])

@@ -3,7 +3,7 @@
 computed on every rank, then times the step.
 
   python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
-      tools/bridge_multi.py [--n 65536] [--steps 5]            (N = 1 works too)
+      tools/bridge_multi.py [--stars 65536] [--steps 5]            (N = 1 works too)
 Prints one JSON line on rank 0."""
 import argparse
 import json
@@ -20,7 +20,7 @@ sys.path.insert(0, ROOT)
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--n", type=int, default=65536)
+    ap.add_argument("--stars", type=int, default=65536)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--grid", type=int, default=16)
     args = ap.parse_args()
@@ -43,7 +43,7 @@ def main():
     opts = dict(grid_x_size_in_kpc=0.05, grid_y_size_in_kpc=0.05, grid_z_size_in_kpc=0.05, grid_resolution=0.05 / args.grid,
                 with_potential=False)
     field = gizmo_field(opts, snaps, chosen_positions=np.tile(center, (2, 1)), ctx=ctx)   # replicated on every rank
-    pos_pc, vel, mass = make_plummer_cluster(args.n)
+    pos_pc, vel, mass = make_plummer_cluster(args.stars)
     pos = pos_pc * 1e-3 + center[:, None]
     dt = 0.1
 
@@ -79,7 +79,7 @@ def main():
     dv = float(np.max(np.abs(v_sh - v_1)) / np.max(np.abs(v_1)))
     ok = dx < 1e-10 and dv < 1e-10
     if rank == 0:
-        print(json.dumps({"n_gpus": world, "n_stars": args.n, "steps": args.steps, "ms_per_bridge_step_sharded": ms_sharded,
+        print(json.dumps({"n_gpus": world, "n_stars": args.stars, "steps": args.steps, "ms_per_bridge_step_sharded": ms_sharded,
                           "ms_per_bridge_step_single_gpu": ms_single, "max_rel_dx": dx, "max_rel_dv": dv, "match": ok}))
     if world > 1:
         dist.destroy_process_group()
