@@ -34,7 +34,11 @@ sys.path.insert(0, ROOT)
 
 FLOP_PER_INTERACTION = 20.0  # GPU-Gems-3 ch.31 convention, acc only
 # (workload, grid, sources per GPU) -> DRAM bytes moved by one launch of the streaming kernel (ncu, profiles/)
-NCU_DRAM_BYTES_PER_LAUNCH = {}
+NCU_DRAM_BYTES_PER_LAUNCH = {
+    # profiles/r01_ncu_dram_bench_full.csv: 249 632 768 B read (tiles + targets; the 200 MB of tiles are re-read from L2)
+    # + 667 437 824 B written (FP64 chunk partials) = 0.1 % of HBM bandwidth over the 919 ms launch
+    ("c2", 64, 10000000): 249632768 + 667437824,
+}
 G_KPC = 4.398600413517813e-09
 CENTER = np.array([8.0, 0.0, 0.0])
 HALF = 0.6

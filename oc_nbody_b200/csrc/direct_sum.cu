@@ -588,8 +588,7 @@ extern "C" int ocg_debug_set_precise_near(int on) {
 
 // n_tgt: targets in the call (or shard); seg_len: typical length of one independent target run (= n_tgt for the
 // field build, the cluster size for batched self-gravity) — a tile never spans two runs.
-int ocg_pick_variant(ocg_ctx* ctx, int64_t n_tgt, int64_t seg_len, bool guard, bool allow_mf) {
-  (void)ctx;
+int ocg_pick_variant(ocg_ctx* ctx, int64_t n_tgt, int64_t seg_len, bool guard, bool allow_mf, int64_t src_tiles) {
   if (g_force_variant >= 0) {
     // a forced variant without the guarded form falls back to the guarded production kernels; so does a
     // mass-folded one when the caller lays out plain tiles (K4)
@@ -601,9 +600,16 @@ int ocg_pick_variant(ocg_ctx* ctx, int64_t n_tgt, int64_t seg_len, bool guard, b
     const long long padded = (seg_len + ct - 1) / ct * ct;
     return padded * 8 <= seg_len * 9;  // <= 12.5% of the tile slots idle
   };
+  // few targets are fine for the wide-tile kernels when there are enough source tiles to cut into work items
+  // (>= 4 tile-granular items per resident CTA); this also keeps the result of a target shard bit-identical to
+  // the unsharded call (all target-paired kernels accumulate a target's sources in the same order)
+  auto enough = [&](int v) {
+    const long long ct = (long long)variant_threads(g_variants[v]) * g_variants[v].tpt;
+    return (n_tgt + ct - 1) / ct * src_tiles >= 4ll * ctx->sm_count * g_variants[v].minb;
+  };
   if (guard) return (n_tgt >= 16384 && waste_ok(OCG_VARIANT_MID_GUARD)) ? OCG_VARIANT_MID_GUARD : OCG_VARIANT_SMALL;
-  if (n_tgt >= 65536 && waste_ok(OCG_VARIANT_BIG)) return OCG_VARIANT_BIG;
-  if (n_tgt >= 16384 && waste_ok(OCG_VARIANT_MID)) return OCG_VARIANT_MID;
+  if ((n_tgt >= 65536 || enough(OCG_VARIANT_BIG)) && waste_ok(OCG_VARIANT_BIG)) return OCG_VARIANT_BIG;
+  if ((n_tgt >= 16384 || enough(OCG_VARIANT_MID)) && waste_ok(OCG_VARIANT_MID)) return OCG_VARIANT_MID;
   return OCG_VARIANT_SMALL;
 }
 int ocg_variant_tpt(int v) { return g_variants[v].tpt; }
@@ -655,7 +661,7 @@ int ocg_direct_sum_impl(ocg_ctx* ctx, const float* src_xyzm, const float* src_so
     return OCG_OK;
   }
 
-  int variant = ocg_pick_variant(ctx, n_tgt, n_tgt, /*guard=*/false, /*allow_mf=*/true);
+  int variant = ocg_pick_variant(ctx, n_tgt, n_tgt, /*guard=*/false, /*allow_mf=*/true, (n_src + OCG_TS - 1) / OCG_TS);
   if (g_variants[variant].mf && want_pot) variant = OCG_VARIANT_BIG;  // the potential has no mass-folded form
   else if (variant == OCG_VARIANT_BIG && !want_pot && g_mass_fold && g_force_variant < 0) variant = OCG_VARIANT_BIG_MF;
   const int mf = g_variants[variant].mf;

@@ -120,7 +120,8 @@ extern "C" int ocg_self_gravity(ocg_ctx* ctx, const double* pos_dev, const doubl
   const int64_t n_shard = tgt_end - tgt_begin;
   // the tile shape follows the typical cluster size, not the batch size: a 4096-star cluster would fill only
   // 1 1/3 of the 3072-target tiles of the big-grid kernel
-  const int variant = ocg_pick_variant(ctx, n_shard, (n + n_seg - 1) / n_seg, guard);
+  const int64_t seg_typ = (n + n_seg - 1) / n_seg;
+  const int variant = ocg_pick_variant(ctx, n_shard, seg_typ, guard, /*allow_mf=*/false, (seg_typ + OCG_TS - 1) / OCG_TS);
   const int tpt = ocg_variant_tpt(variant);
   const int CT = ocg_variant_threads(variant) * tpt;
 
@@ -142,10 +143,20 @@ extern "C" int ocg_self_gravity(ocg_ctx* ctx, const double* pos_dev, const doubl
   }
   seg_tile[n_seg] = total_tiles;
   const long long slots = ocg_variant_slots(ctx, variant);
-  long long n_chunks = n_tt_total > 0 ? (16 * slots + n_tt_total - 1) / n_tt_total : 1;
-  if (n_chunks > max_tiles) n_chunks = max_tiles;
-  if (n_chunks > 256) n_chunks = 256;
-  if (n_chunks < 1) n_chunks = 1;
+  // Source chunking: an item streams `tpc` tiles of its segment; items are strided statically over the resident
+  // CTAs, so the makespan is rounds * tpc tile-times (+ ~1/16 tile of start-up per item).  Pick the tiles-per-chunk
+  // that minimises it for the largest segment (every chunk non-empty there), keeping <= 256 partial-sum slots.
+  long long n_chunks = 1;
+  if (n_tt_total > 0) {
+    double best = 1e300;
+    for (long long tpc = 1; tpc <= max_tiles; ++tpc) {
+      const long long ch = (max_tiles + tpc - 1) / tpc;
+      if (ch > 256) continue;
+      const long long rounds = (n_tt_total * ch + slots - 1) / slots;
+      const double cost = (double)rounds * ((double)tpc + 0.0625);
+      if (cost < best) best = cost, n_chunks = ch;
+    }
+  }
   const long long n_items = n_tt_total * n_chunks;
   if (n_items > 0x7fffffffll) {
     free(seg_tile);

@@ -70,6 +70,13 @@ def main():
         return float(ms.item())
 
     sh = sharded_cluster_code(mass, pos, vel, softening_pc=0.01, ctx=ctx)
+    # stage checks: the all-gather reproduces the full arrays; the first sharded force equals the unsharded one
+    g_pos, g_vel = (t.cpu().numpy() for t in sh.gather_state())
+    gather_ok = bool(np.array_equal(g_pos, pos) and np.array_equal(g_vel, vel))
+    ref_code = cluster_code(mass, pos, vel, softening_pc=0.01, ctx=ctx)
+    a_full = ref_code.compute_self_gravity().cpu().numpy()
+    a_loc = sh.compute_self_gravity().cpu().numpy()
+    force_err = float(np.max(np.abs(a_loc - a_full[:, sh.a:sh.b])) / np.max(np.abs(a_full)))
     ms_sharded = run(sh, args.steps)
     x_sh, v_sh = (t.cpu().numpy() for t in sh.gather_state())
     single = cluster_code(mass, pos, vel, softening_pc=0.01, ctx=ctx)
@@ -77,10 +84,12 @@ def main():
     x_1, v_1 = single.pos.cpu().numpy(), single.vel.cpu().numpy()
     dx = float(np.max(np.abs(x_sh - x_1)) / np.max(np.abs(x_1 - center[:, None])))
     dv = float(np.max(np.abs(v_sh - v_1)) / np.max(np.abs(v_1)))
-    ok = dx < 1e-10 and dv < 1e-10
+    ok = dx < 1e-10 and dv < 1e-10 and gather_ok and force_err < 1e-12
+    print("rank %d: gather_ok %s force_err %.3e dx %.3e dv %.3e" % (rank, gather_ok, force_err, dx, dv), file=sys.stderr)
     if rank == 0:
         print(json.dumps({"n_gpus": world, "n_stars": args.stars, "steps": args.steps, "ms_per_bridge_step_sharded": ms_sharded,
-                          "ms_per_bridge_step_single_gpu": ms_single, "max_rel_dx": dx, "max_rel_dv": dv, "match": ok}))
+                          "ms_per_bridge_step_single_gpu": ms_single, "max_rel_dx": dx, "max_rel_dv": dv, "match": ok,
+                          "allgather_exact_rank0": gather_ok, "first_force_rel_err_rank0": force_err}))
     if world > 1:
         dist.destroy_process_group()
     if not ok:
