@@ -166,6 +166,20 @@ int ocg_grid_interp_nested(ocg_ctx* ctx, const ocg_grid_desc* coarse, const ocg_
                            double* pot_out_dev, double* tensor_out_dev, int32_t* level_out_dev,
                            int32_t* cell_out_dev, void* stream);
 
+/* Graph-replayable K3.  A captured CUDA graph freezes kernel parameters, but the time-blend weights change every
+ * step; these two calls move them to constant memory: ocg_set_interp_weight_slots() writes `n_slots` weight
+ * quadruples (HOST fp64 [n_slots][4], rounded to fp32) into slots first_slot.. (4 slots exist) in stream order —
+ * call it before each replay — and ocg_grid_interp_slot() is ocg_grid_interp_nested() (without tensor/level/cell
+ * outputs) reading its weights from slot `w_slot`.  Used by bridge.Bridge to replay a whole K(dt/2) D(dt) K(dt/2)
+ * step (oc_nbody.py:56) as one graph launch.                                                                  */
+int ocg_set_interp_weight_slots(ocg_ctx* ctx, const double* weights_host, int32_t first_slot, int32_t n_slots,
+                                void* stream);
+int ocg_grid_interp_slot(ocg_ctx* ctx, const ocg_grid_desc* coarse, const ocg_grid_desc* fine,
+                         const float* const* rec_coarse_dev, const float* const* rec_fine_dev, int32_t w_slot,
+                         int32_t n_rec, const double* star_x_dev, const double* star_y_dev,
+                         const double* star_z_dev, const int32_t* star_cluster_dev, int64_t n_star,
+                         double* acc_out_dev, double* pot_out_dev, void* stream);
+
 /* K2 pack with a scatter: rec[index[i]] = float4(acc[0][i], acc[1][i], acc[2][i], pot[i]) for i < n.
  * Lays rows of the reference's point list (kept coarse points | fine lattice | origin row,
  * grid_cartesian.py:71-91) out as full-lattice node records.  acc_dev fp64 [3][n]; pot_dev [n] or NULL;

@@ -20,7 +20,7 @@ ABI_SYMBOLS = [
     "ocg_version", "ocg_create", "ocg_destroy", "ocg_last_error", "ocg_device_info", "ocg_launch_count",
     "ocg_last_direct_kernel_ms", "ocg_set_kernel_timing", "ocg_recentre_f64", "ocg_cast_f64_f32",
     "ocg_field_direct", "ocg_frame_subtract", "ocg_field_build_host", "ocg_pack_planes", "ocg_grid_time_blend",
-    "ocg_grid_interp", "ocg_grid_interp_multi", "ocg_grid_interp_nested", "ocg_pack_planes_indexed", "ocg_self_gravity", "ocg_bound_com", "ocg_eject_mask", "ocg_compact_rows", "ocg_kick", "ocg_drift", "ocg_axpy", "ocg_probe_throughput",
+    "ocg_grid_interp", "ocg_grid_interp_multi", "ocg_grid_interp_nested", "ocg_pack_planes_indexed", "ocg_set_interp_weight_slots", "ocg_grid_interp_slot", "ocg_self_gravity", "ocg_bound_com", "ocg_eject_mask", "ocg_compact_rows", "ocg_kick", "ocg_drift", "ocg_axpy", "ocg_probe_throughput",
 ]
 
 
@@ -70,6 +70,9 @@ def load_library():
     L.ocg_grid_interp_nested.argtypes = [vp, ctypes.POINTER(_GridDesc), ctypes.POINTER(_GridDesc), vp, vp, ctypes.POINTER(dbl),
                                          i32, vp, vp, vp, vp, i64, vp, vp, vp, vp, vp, vp]
     L.ocg_pack_planes_indexed.argtypes = [vp, vp, vp, i64, vp, vp, vp]
+    L.ocg_set_interp_weight_slots.argtypes = [vp, ctypes.POINTER(dbl), i32, i32, vp]
+    L.ocg_grid_interp_slot.argtypes = [vp, ctypes.POINTER(_GridDesc), ctypes.POINTER(_GridDesc), vp, vp, i32, i32, vp, vp, vp, vp,
+                                       i64, vp, vp, vp]
     L.ocg_self_gravity.argtypes = [vp, vp, vp, i64, vp, i32, dbl, dbl, i64, i64, vp, vp, vp]
     L.ocg_bound_com.argtypes = [vp, vp, vp, vp, vp, i64, vp, i32, dbl, vp, vp, vp]
     L.ocg_eject_mask.argtypes = [vp, vp, i64, dbl, dbl, vp, vp, vp]
@@ -240,6 +243,31 @@ class Context:
                                                  _dptr(sz), _dptr(star_cluster), sx.shape[0], _dptr(acc_out), _dptr(pot_out),
                                                  _dptr(tensor_out), _dptr(level_out), _dptr(cell_out), self._stream()),
                  "ocg_grid_interp_nested")
+
+    def set_interp_weight_slots(self, weights, first_slot=0):
+        """weights: sequence of up-to-4-element weight lists, written to constant-memory slots first_slot.. (stream-ordered)."""
+        flat = []
+        for w in weights:
+            w = [float(x) for x in w]
+            flat.extend(w + [0.0] * (4 - len(w)))
+        arr = (ctypes.c_double * len(flat))(*flat)
+        self._ck(self.lib.ocg_set_interp_weight_slots(self.h, arr, int(first_slot), len(weights), self._stream()),
+                 "ocg_set_interp_weight_slots")
+
+    def grid_interp_slot(self, n, nodes, origin, recs, w_slot, sx, sy, sz, star_cluster, acc_out, pot_out=None, fine_n=None,
+                         fine_nodes=None, recs_fine=None):
+        """K3 with the time-blend weights taken from constant-memory slot `w_slot` (graph-replayable)."""
+        dc = self._grid_desc(n, nodes, origin)
+        ptrs = (ctypes.c_void_p * len(recs))(*[_dptr(r).value for r in recs])
+        if fine_n is not None:
+            df = self._grid_desc(fine_n, fine_nodes, origin)
+            fptrs = (ctypes.c_void_p * len(recs))(*[_dptr(r).value for r in recs_fine])
+            dfp = ctypes.byref(df)
+        else:
+            fptrs, dfp = None, None
+        self._ck(self.lib.ocg_grid_interp_slot(self.h, ctypes.byref(dc), dfp, ptrs, fptrs, int(w_slot), len(recs), _dptr(sx),
+                                               _dptr(sy), _dptr(sz), _dptr(star_cluster), sx.shape[0], _dptr(acc_out),
+                                               _dptr(pot_out), self._stream()), "ocg_grid_interp_slot")
 
     def pack_planes_indexed(self, acc, pot, index, rec):
         """rec[index[i]] = float4(acc[:, i], pot[i]) (K2 pack with a scatter)."""

@@ -10,18 +10,31 @@ oc_nbody.py runs unchanged against the B200 codes, and so the oracle has the sam
 When both the kicked system and its partner are this package's GPU codes the kick stays on the device
 (``partner.kick_device``): K3 gather + K5 update, no host copies.  Any other partner is kicked through the
 public ``get_gravity_at_point(eps, x, y, z)``.
+
+``use_cuda_graph=True``: for that device-resident pair the whole step (K3, K5, K4 with its pack and finish kernels,
+K5 ... — 10 launches) is captured once into a CUDA graph and replayed with ONE launch per step.  What changes from
+step to step — the time-blend weights of the two half-kicks — lives in constant memory and is refreshed before each
+replay (ocg_set_interp_weight_slots); the grid origin is a device buffer.  The graph is re-captured when the
+bracketing snapshots, the particle count or the timestep change.  Results equal the eager path's to FP64 rounding
+(the eager drift integrates over (t + dt) - model_time, which can differ from dt in the last bit).
 """
 from .units import to_value, units
 
 
 class Bridge(object):
-    def __init__(self, timestep=None, use_threading=False, verbose=False):
+    def __init__(self, timestep=None, use_threading=False, verbose=False, use_cuda_graph=False):
         if use_threading:
             raise NotImplementedError("the reference runs the bridge single-threaded (oc_nbody.py:49)")
         self.timestep = None if timestep is None else float(to_value(timestep, units.Myr))
         self.systems = []
         self.partners = {}
         self.time = 0.0
+        self.use_cuda_graph = bool(use_cuda_graph)
+        self._graph = None
+        self._graph_key = None
+        self._seen_key = None
+        self.graph_replays = 0
+        self.graph_captures = 0
 
     def add_system(self, system, partners=()):
         self.systems.append(system)
@@ -48,13 +61,63 @@ class Bridge(object):
         for s in self.systems:
             s.evolve_model(tend | units.Myr)
 
+    # ---- one-launch step for the device-resident cluster + field pair ----
+    def _device_pair_(self):
+        """(cluster, field) when the bridge holds exactly this package's cluster code kicked by its field code."""
+        if len(self.systems) != 2:
+            return None
+        for cl, fld in (self.systems, self.systems[::-1]):
+            if (self.partners[id(cl)] == (fld,) and self.partners[id(fld)] == () and hasattr(fld, "kick_device")
+                    and hasattr(fld, "_time_planes_") and type(cl).__name__ == "cluster_code" and hasattr(cl, "_evolve_device_")):
+                return cl, fld
+        return None
+
+    def _graph_step_(self, cl, fld, dt):
+        """K(dt/2) D(dt) K(dt/2) as one CUDA-graph launch.  The first step with a new configuration runs eagerly (it
+        also sizes every scratch buffer), the second captures, later ones replay."""
+        import torch
+        t0 = self.time
+        if abs(getattr(fld, "time", t0) - t0) > 1e-9 * max(1.0, abs(t0)) or not cl._acc_valid:
+            return False
+        rec0, fine0, w0 = fld._time_planes_()
+        fld.evolve_model((t0 + dt) | units.Myr)          # host only: bracket + weights of the second half-kick
+        rec1, fine1, w1 = fld._time_planes_()
+        key = (tuple(r.data_ptr() for r in rec0), tuple(r.data_ptr() for r in rec1), cl.n, cl.pos.data_ptr(), cl.substeps,
+               dt, cl.parameters._eps2_kpc2, fld._dev["origin"].data_ptr())
+
+        def body():
+            fld.kick_device(cl.pos, cl.vel, 0.5 * dt, planes=(rec0, fine0), w_slot=0)
+            cl._evolve_device_(dt)
+            fld.kick_device(cl.pos, cl.vel, 0.5 * dt, planes=(rec1, fine1), w_slot=1)
+
+        cl.ctx.set_interp_weight_slots([w0, w1])
+        if key == self._graph_key:
+            self._graph.replay()
+            self.graph_replays += 1
+        elif key == self._seen_key:
+            torch.cuda.synchronize()
+            self._graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self._graph):
+                body()
+            self._graph_key = key
+            self.graph_captures += 1
+            self._graph.replay()
+            self.graph_replays += 1
+        else:
+            self._seen_key = key
+            body()
+        cl.model_time = t0 + dt
+        return True
+
     def evolve_model(self, tend, timestep=None):
         tend = float(to_value(tend, units.Myr))
         dt = self.timestep if timestep is None else float(to_value(timestep, units.Myr))
         if dt is None:
             dt = tend - self.time
+        pair = self._device_pair_() if self.use_cuda_graph else None
         while self.time < tend - 0.5 * dt:
-            self.kick_systems(0.5 * dt)
-            self.drift_systems(self.time + dt)
-            self.kick_systems(0.5 * dt)
+            if pair is None or not self._graph_step_(pair[0], pair[1], dt):
+                self.kick_systems(0.5 * dt)
+                self.drift_systems(self.time + dt)
+                self.kick_systems(0.5 * dt)
             self.time += dt

@@ -151,6 +151,16 @@ class cluster_code(object):
         self._acc_valid = True
         return self.acc
 
+    def _evolve_device_(self, span):
+        """The device work of evolve_model: `substeps` kick-drift-kick leapfrog steps over `span` Myr.  No host
+        bookkeeping, no allocation, no synchronisation once the scratch buffers exist — capturable in a CUDA graph."""
+        h = span / self.substeps
+        for _ in range(self.substeps):
+            self.ctx.kick(self.vel, self.acc, 0.5 * h)
+            self.ctx.drift(self.pos, self.vel, h, KMS_TO_KPC_PER_MYR)
+            self.compute_self_gravity()
+            self.ctx.kick(self.vel, self.acc, 0.5 * h)
+
     def evolve_model(self, t_end, timestep=None):
         """Kick-drift-kick leapfrog under self-gravity from model_time to t_end (the BRIDGE drift,
         oc_nbody.py:56 -> cluster_code.evolve_model)."""
@@ -158,14 +168,9 @@ class cluster_code(object):
         span = t_end - self.model_time
         if span <= 0.0:
             return
-        h = span / self.substeps
         if not self._acc_valid:
             self.compute_self_gravity()
-        for _ in range(self.substeps):
-            self.ctx.kick(self.vel, self.acc, 0.5 * h)
-            self.ctx.drift(self.pos, self.vel, h, KMS_TO_KPC_PER_MYR)
-            self.compute_self_gravity()
-            self.ctx.kick(self.vel, self.acc, 0.5 * h)
+        self._evolve_device_(span)
         self.model_time = t_end
 
     def kick_velocities(self, ax, ay, az, dt_myr):

@@ -416,7 +416,8 @@ __device__ __forceinline__ void tile_tpair(const float* __restrict__ stage, cons
           y3 = f2_pack(rsqrt_approx(r6a), rsqrt_approx(r6b));
         }
         const u64 sc = MF ? y3 : f2_mul(y3, mb);
-        if (POT) ap[p] = f2_fma(sc, r2, ap[p]);
+        if (POT) ap[p] = f2_fma(sc, r2, ap[p]);  // plain tiles only (a mass-folded potential needs 2 more ops + 1/w:
+                                                 // measured slower than the plain form, profiles/r01_variant_sweep2.json)
         if (DBG & 8) {  // two distinct register pairs per instruction instead of three
           ax[p] = f2_fma(dx, ax[p], ax[p]);
           ay[p] = f2_fma(dy, ay[p], ay[p]);

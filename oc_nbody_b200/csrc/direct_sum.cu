@@ -486,6 +486,7 @@ static inline int variant_threads(const DirectVariant& v) { return 32 * (v.nwarp
   {                                                                                                      \
     {direct_sum_tp_kernel<NP, false, SMEMACC, MINB, UNR, NW, DBG, MF>, nullptr}, { nullptr, nullptr }    \
   }
+
 #define OCG_TPD(NP, SMEMACC, MINB, UNR, NW, DBG)                                                         \
   {                                                                                                      \
     {direct_sum_tp_kernel<NP, false, SMEMACC, MINB, UNR, NW, DBG>, nullptr}, { nullptr, nullptr }        \

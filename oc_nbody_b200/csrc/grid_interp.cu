@@ -67,6 +67,12 @@ extern "C" int ocg_grid_time_blend(ocg_ctx* ctx, const float* rec_a_dev, const f
 }
 
 // ------------------------------------------------------------------------------------ K3 ----
+// Time-blend weights that a captured CUDA graph can pick up: kernel parameters are frozen at capture, constant memory is
+// not.  ocg_set_interp_weight_slots() refreshes the slots (stream-ordered) before each replay; a K3 launch with
+// w_slot >= 0 reads its weights from there instead of from its parameter block.
+#define OCG_W_SLOTS 4
+__constant__ float c_interp_w[OCG_W_SLOTS][4];
+
 struct InterpParams {
   int n[3];
   int n_cluster;
@@ -74,6 +80,7 @@ struct InterpParams {
   const double* origin;
   const float4* rec[4];  // 1..4 record planes blended in time (2: linear bracket, 4: cubic B-spline coefficients)
   float w[4];            // their FP32 weights (the time blend is FP32 arithmetic)
+  int w_slot;            // >= 0: take the weights from c_interp_w[w_slot] (graph replay), else from w[]
   int n_rec;
   // nested fine lattice (grid_cartesian.py:34-53,71-91) sharing origin and weights; n2[0] == 0: single level
   int n2[3];
@@ -148,6 +155,9 @@ __global__ void __launch_bounds__(256, MINB) grid_interp_kernel(const InterpPara
       iv[0][d] = iv[1][d] = nullptr;
     }
   }
+  float wt[4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) wt[r] = p.w_slot >= 0 ? c_interp_w[p.w_slot][r] : p.w[r];
   // grid-stride over stars: the tables above are staged once per resident block, not once per 256 stars
   for (long long s = blockIdx.x * (long long)blockDim.x + threadIdx.x; s < p.n_star;
        s += (long long)gridDim.x * blockDim.x) {
@@ -196,13 +206,13 @@ __global__ void __launch_bounds__(256, MINB) grid_interp_kernel(const InterpPara
       float4 a = __ldg(rec[0] + off);
       if (p.n_rec > 1) {
         const float4 b = __ldg(rec[1] + off);
-        a = make_float4(lerp_rn_f(a.x, p.w[0], b.x, p.w[1]), lerp_rn_f(a.y, p.w[0], b.y, p.w[1]),
-                        lerp_rn_f(a.z, p.w[0], b.z, p.w[1]), lerp_rn_f(a.w, p.w[0], b.w, p.w[1]));
+        a = make_float4(lerp_rn_f(a.x, wt[0], b.x, wt[1]), lerp_rn_f(a.y, wt[0], b.y, wt[1]),
+                        lerp_rn_f(a.z, wt[0], b.z, wt[1]), lerp_rn_f(a.w, wt[0], b.w, wt[1]));
 #pragma unroll
         for (int r = 2; r < 4; ++r) {
           if (r >= p.n_rec) break;
           const float4 e = __ldg(rec[r] + off);
-          const float wr = p.w[r];
+          const float wr = wt[r];
           a = make_float4(__fadd_rn(a.x, __fmul_rn(e.x, wr)), __fadd_rn(a.y, __fmul_rn(e.y, wr)),
                           __fadd_rn(a.z, __fmul_rn(e.z, wr)), __fadd_rn(a.w, __fmul_rn(e.w, wr)));
         }
@@ -258,7 +268,7 @@ static int interp_launch(ocg_ctx* ctx, const ocg_grid_desc* grid, const float* c
                          const double* sx, const double* sy, const double* sz, const int32_t* scl, int64_t n_star,
                          double* acc, double* pot, int32_t* cell, void* stream, const char* who,
                          const ocg_grid_desc* fine = nullptr, const float* const* rec_fine = nullptr,
-                         double* tensor = nullptr, int32_t* level = nullptr) {
+                         double* tensor = nullptr, int32_t* level = nullptr, int w_slot = -1) {
   if (!grid) return ocg_fail(ctx, OCG_ERR_INVALID, "%s: grid is NULL", who);
   if (n_star < 0) return ocg_fail(ctx, OCG_ERR_INVALID, "%s: negative n_star", who);
   if (n_star == 0) return OCG_OK;
@@ -292,6 +302,7 @@ static int interp_launch(ocg_ctx* ctx, const ocg_grid_desc* grid, const float* c
       return ocg_fail(ctx, OCG_ERR_INVALID, "%s: record plane %d is NULL", who, r);
   }
   p.n_rec = n_rec;
+  p.w_slot = w_slot;
   p.sx = sx, p.sy = sy, p.sz = sz;
   p.scl = scl;
   p.n_star = n_star;
@@ -392,4 +403,35 @@ extern "C" int ocg_pack_planes_indexed(ocg_ctx* ctx, const double* acc_dev, cons
       acc_dev, pot_dev, reinterpret_cast<const long long*>(index_dev), n, reinterpret_cast<float4*>(rec_dev));
   OCG_CHECK_LAUNCH(ctx, "pack_planes_indexed_kernel");
   return OCG_OK;
+}
+
+// ---- graph-replayable form ------------------------------------------------------------------------------------
+extern "C" int ocg_set_interp_weight_slots(ocg_ctx* ctx, const double* weights_host, int32_t first_slot, int32_t n_slots,
+                                           void* stream) {
+  if (!ctx) return OCG_ERR_INVALID;
+  if (!weights_host || first_slot < 0 || n_slots < 1 || first_slot + n_slots > OCG_W_SLOTS)
+    return ocg_fail(ctx, OCG_ERR_INVALID, "ocg_set_interp_weight_slots: slots [%d, %d) outside [0, %d)", first_slot,
+                    first_slot + n_slots, OCG_W_SLOTS);
+  OcgDeviceGuard g(ctx->device);
+  float w[OCG_W_SLOTS][4];
+  for (int k = 0; k < n_slots; ++k)
+    for (int r = 0; r < 4; ++r) w[k][r] = (float)weights_host[4 * k + r];
+  // pageable source: the runtime stages it before returning, so `w` may live on this stack frame
+  OCG_CUDA(ctx, cudaMemcpyToSymbolAsync(c_interp_w, w, sizeof(float) * 4 * n_slots, sizeof(float) * 4 * first_slot,
+                                        cudaMemcpyHostToDevice, (cudaStream_t)stream));
+  return OCG_OK;
+}
+
+extern "C" int ocg_grid_interp_slot(ocg_ctx* ctx, const ocg_grid_desc* coarse, const ocg_grid_desc* fine,
+                                    const float* const* rec_coarse_dev, const float* const* rec_fine_dev, int32_t w_slot,
+                                    int32_t n_rec, const double* star_x_dev, const double* star_y_dev,
+                                    const double* star_z_dev, const int32_t* star_cluster_dev, int64_t n_star,
+                                    double* acc_out_dev, double* pot_out_dev, void* stream) {
+  if (!ctx) return OCG_ERR_INVALID;
+  if (!rec_coarse_dev || n_rec < 1 || n_rec > 4 || w_slot < 0 || w_slot >= OCG_W_SLOTS)
+    return ocg_fail(ctx, OCG_ERR_INVALID, "ocg_grid_interp_slot: need 1..4 record planes and a weight slot in [0, %d)", OCG_W_SLOTS);
+  const float w[4] = {0.f, 0.f, 0.f, 0.f};
+  return interp_launch(ctx, coarse, rec_coarse_dev, w, n_rec, star_x_dev, star_y_dev, star_z_dev, star_cluster_dev, n_star,
+                       acc_out_dev, pot_out_dev, nullptr, stream, "ocg_grid_interp_slot", fine, rec_fine_dev, nullptr, nullptr,
+                       w_slot);
 }

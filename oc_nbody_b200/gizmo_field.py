@@ -471,9 +471,18 @@ class gizmo_field(object):
         u = units.kms / units.Myr / units.kpc
         return (T[0] | u) if scalar else (T | u)
 
-    def kick_device(self, pos_kpc, vel_kms, dt_myr):
-        """Fused BRIDGE half-kick on device state (FP64 [3,n] tensors): v += dt * a_tidal(x). No host copies."""
-        acc = self._interp_device_(pos_kpc[0], pos_kpc[1], pos_kpc[2], False)[0]
+    def kick_device(self, pos_kpc, vel_kms, dt_myr, planes=None, w_slot=None):
+        """Fused BRIDGE half-kick on device state (FP64 [3,n] tensors): v += dt * a_tidal(x). No host copies.
+        With `planes` = (coarse planes, fine planes or None) and `w_slot` the time-blend weights are read from the
+        constant-memory slot (ocg_set_interp_weight_slots) — the form a captured CUDA graph replays."""
+        if w_slot is None:
+            acc = self._interp_device_(pos_kpc[0], pos_kpc[1], pos_kpc[2], False)[0]
+        else:
+            import torch
+            d, g = self._dev, self.grid
+            acc = torch.empty((3, pos_kpc.shape[1]), dtype=torch.float64, device=d["device"])
+            self.ctx.grid_interp_slot(g.shape, d["nodes"], d["origin"], planes[0], w_slot, pos_kpc[0], pos_kpc[1], pos_kpc[2],
+                                      None, acc, None, fine_n=g.fine_shape, fine_nodes=d["fine_nodes"], recs_fine=planes[1])
         self.ctx.kick(vel_kms, acc, dt_myr)
 
     def stop(self):

@@ -312,3 +312,38 @@ def test_two_gpu_sharded_bridge_matches_single_gpu():
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
     line = json.loads([ln for ln in res.stdout.splitlines() if ln.startswith("{")][-1])
     assert line["match"] and line["n_gpus"] == 2
+
+
+def test_bridge_cuda_graph_step_is_bit_identical(small_world, ctx):
+    """use_cuda_graph=True: eager first steps, then captured, replayed afterwards — the eager bridge's trajectory to
+    FP64 rounding, including after the grid is re-centred (evolve_grid only rewrites a device buffer the graph reads)."""
+    from oc_nbody_b200.bridge import Bridge
+    from oc_nbody_b200.cluster import cluster_code
+    from oc_nbody_b200.synthetic import make_plummer_cluster
+    from oc_nbody_b200.units import units
+    field, _, _ = small_world
+    pos_pc, vel, mass = make_plummer_cluster(1500)
+    center = np.array([8.0, 0.0, 0.0])
+    pos = pos_pc * 1e-3 + center[:, None]
+    dt, nstep = 0.1, 7
+    out = []
+    for use_graph in (False, True):
+        field.evolve_grid(center)
+        field.evolve_model(0.0 | units.Myr)
+        cl = cluster_code(mass, pos, vel, softening_pc=0.01, substeps=2, ctx=ctx)
+        system = Bridge(timestep=dt | units.Myr, use_threading=False, use_cuda_graph=use_graph)
+        system.add_system(cl, (field,))
+        system.add_system(field)
+        for i in range(nstep + 1):
+            system.evolve_model(i * dt | units.Myr, timestep=dt | units.Myr)
+            if i == 4:
+                field.evolve_grid(center + np.array([1e-4, -2e-4, 5e-5]))
+        out.append((cl.pos.cpu().numpy(), cl.vel.cpu().numpy(), cl.model_time, field.time, system.graph_replays,
+                    system.graph_captures))
+    (x0, v0, t0, ft0, r0, c0), (x1, v1, t1, ft1, r1, c1) = out
+    # step 1 is eager (no force yet), step 2 eager with the slot kernels (sizes the scratch), step 3 captures, 3.. replay
+    assert r0 == 0 and c0 == 0 and c1 == 1 and r1 == nstep - 2, (r0, c0, r1, c1)
+    # the eager drift integrates over span = (t + dt) - model_time, which differs from dt in the last bit at some
+    # steps; the graph bakes dt itself into the captured kernels.  Everything else is the same arithmetic.
+    assert np.max(np.abs(x0 - x1)) <= 1e-14 * 8.0 and np.max(np.abs(v0 - v1)) <= 1e-13 * np.max(np.abs(v0))
+    assert abs(t0 - t1) < 1e-12 and ft0 == ft1 and abs(t1 - nstep * dt) < 1e-12

@@ -186,6 +186,12 @@ def test_field_direct_production_big_is_mass_folded(ctx):
     assert rel_err(a_mf, ref) <= TOL and rel_err(a_pl, ref) <= TOL
     assert rel_err_scalar(pot, pref) <= TOL
     assert not np.array_equal(a_mf, a_pl)  # two different kernels really ran
+    ctx.lib.ocg_debug_set_mass_fold(0)
+    try:
+        a_off, _ = run_k1(ctx, src, soft, tgt, oracle.KERNEL_PLUMMER, want_pot=False)
+    finally:
+        ctx.lib.ocg_debug_set_mass_fold(1)
+    assert np.array_equal(a_off, a_pl)     # mass folding off: the plain-tile kernel, potential or not
 
 
 def test_frame_subtract_and_host_form(ctx):

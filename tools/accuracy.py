@@ -36,12 +36,11 @@ def main():
         ref, pref = oracle.field_direct(s32, soft, t32, kernel, G_KPC, want_pot=True)
         t_or = time.time() - t0
         d_soft = torch.from_numpy(soft).cuda()
-        # variant -1 = heuristic (few targets: 1 target/thread kernel); 31 = production plain target-paired kernel
-        # (>= 64k targets, with potential); 40 = production mass-folded kernel (>= 64k targets, no potential)
-        for variant, precise in ((-1, 1), (-1, 0), (31, 1), (40, 1), (40, 0)):
+        # 31 = plain target-paired kernel (K4's; K1 when the potential is wanted); 58 = production mass-folded kernel
+        for variant, precise in ((31, 1), (31, 0), (58, 1), (58, 0)):
             ctx.lib.ocg_debug_set_variant(variant)
             ctx.lib.ocg_debug_set_precise_near(precise)
-            want_pot = variant != 40
+            want_pot = variant not in (46, 58)
             acc = torch.empty((3, tgt.shape[0]), dtype=torch.float64, device="cuda")
             pot = torch.empty(tgt.shape[0], dtype=torch.float64, device="cuda") if want_pot else None
             ctx.field_direct(d_src, d_soft, d_tgt, kernel, G_KPC, acc, pot)

@@ -132,19 +132,24 @@ def main():
     fake.evolve_grid(center)
     for name, nst in (("bridge_step_c1_1k_stars", 1024), ("bridge_step_c3_65k_stars", 65536)):
         pos_pc, vel, mass = make_plummer_cluster(nst)
-        cl = cluster_code(mass, pos_pc * 1e-3 + center[:, None], vel, softening_pc=0.01, ctx=ctx)
-        system = Bridge(timestep=0.1 | units.Myr, use_threading=False)
-        system.add_system(cl, (fake,))
-        system.add_system(fake)
-        state = {"t": 0.0}
+        for graph in (False, True):
+            cl = cluster_code(mass, pos_pc * 1e-3 + center[:, None], vel, softening_pc=0.01, ctx=ctx)
+            fake.evolve_model(0.0 | units.Myr)
+            system = Bridge(timestep=0.1 | units.Myr, use_threading=False, use_cuda_graph=graph)
+            system.add_system(cl, (fake,))
+            system.add_system(fake)
+            state = {"t": 0.0}
 
-        def step():
-            state["t"] += 0.1
-            system.evolve_model(state["t"] | units.Myr, timestep=0.1 | units.Myr)
-        l0 = ctx.launch_count()
-        med, best = timeit(step, iters=20, warm=3)
-        out[name] = dict(ms_median=med, ms_best=best, kernel_launches_per_step=(ctx.launch_count() - l0) / 23.0,
-                         note="K(dt/2) D(dt) K(dt/2), device-resident, no host copies; self-gravity evaluated once per step")
+            def step():
+                state["t"] += 0.1
+                system.evolve_model(state["t"] | units.Myr, timestep=0.1 | units.Myr)
+            l0 = ctx.launch_count()
+            med, best = timeit(step, iters=20, warm=4)
+            out[name + ("_cuda_graph" if graph else "")] = dict(
+                ms_median=med, ms_best=best, kernel_launches_per_step=(ctx.launch_count() - l0) / 24.0,
+                graph_replays=system.graph_replays,
+                note="K(dt/2) D(dt) K(dt/2), device-resident, no host copies; self-gravity evaluated once per step" +
+                     ("; whole step replayed as one CUDA graph launch (library launch counter only sees the eager steps)" if graph else ""))
     os.makedirs("gpurun_out", exist_ok=True)
     with open("gpurun_out/bench_extra.json", "w") as f:
         json.dump(out, f, indent=1)

@@ -39,7 +39,7 @@ def main():
     only = [int(x) for x in os.environ.get("OCG_PROBE_VARIANTS", "").split(",") if x]
     for kernel, want_pot in ((0, False), (0, True), (1, False)):
         for v in range(nvar):
-            if (want_pot or kernel == 1) and v > 1:
+            if (want_pot or kernel == 1) and v not in (0, 1, 31) and not (kernel == 1 and v in (46, 58)):
                 continue
             if only and v not in only:
                 continue
