@@ -180,6 +180,49 @@ def workload_config(args, n_gpus):
             "l2_policy": "inputs larger than L2 (%.0f MB of sources per GPU vs 126 MB L2)" % (args.n_src_rank * 20 / 1e6)}
 
 
+def bridge_step_times(ctx):
+    """BRIDGE step time (the second half of BASELINE.json's metric): K(dt/2) D(dt) K(dt/2) of a Plummer cluster kicked by
+    a 16^3 grid field interpolated in space and time, device resident, eager launches and one-launch CUDA-graph replay.
+    configs[0] shape (1 024 stars) and configs[2] shape (65 536 stars)."""
+    import torch
+    from oc_nbody_b200.bridge import Bridge
+    from oc_nbody_b200.cluster import cluster_code
+    from oc_nbody_b200.gizmo_field import gizmo_field
+    from oc_nbody_b200.synthetic import make_plummer_cluster
+    from oc_nbody_b200.units import units
+
+    class _Snap(object):
+        snapshot = {"index": 0, "time": 0.0}
+    nn = 16
+    fld = gizmo_field(dict(grid_x_size_in_kpc=0.05, grid_y_size_in_kpc=0.05, grid_z_size_in_kpc=0.05, grid_resolution=0.05 / nn),
+                      [_Snap(), _Snap()], time_in_Myr=[0.0, 23.0], build=False, ctx=ctx)
+    rng = np.random.default_rng(7)
+    tid = rng.normal(0, 1e-3, (2, 3, nn ** 3 + 1))
+    fld.set_snapshot_fields(tid[:, 0], tid[:, 1], tid[:, 2])
+    fld.evolve_grid(CENTER)
+    out = {"unit": "ms", "dt_myr": 0.1, "grid": "16^3, 2 snapshots, linear in time"}
+    for nst in (1024, 65536):
+        pos_pc, vel, mass = make_plummer_cluster(nst)
+        for graph in (False, True):
+            cl = cluster_code(mass, pos_pc * 1e-3 + CENTER[:, None], vel, softening_pc=0.01, ctx=ctx)
+            fld.evolve_model(0.0 | units.Myr)
+            system = Bridge(timestep=0.1 | units.Myr, use_threading=False, use_cuda_graph=graph)
+            system.add_system(cl, (fld,))
+            system.add_system(fld)
+            t, ts = 0.0, []
+            for i in range(24):
+                t += 0.1
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                system.evolve_model(t | units.Myr, timestep=0.1 | units.Myr)
+                e1.record()
+                torch.cuda.synchronize()
+                if i >= 4:
+                    ts.append(e0.elapsed_time(e1))
+            out["%d_stars_%s" % (nst, "cuda_graph" if graph else "eager")] = float(np.median(ts))
+    return out
+
+
 # ------------------------------------------------------------------------------------ main ----
 def main():
     ap = argparse.ArgumentParser()
@@ -328,6 +371,7 @@ def main():
         if world > 1:
             dist.destroy_process_group()
         return
+    bridge = bridge_step_times(ctx) if world == 1 else None
     cpu = None
     if not args.no_cpu_baseline:
         r, desc, threads = cpu_sample_rate(g.evolved_grid, pos[:400000], mass[:400000], eps[:400000], 12.0)
@@ -345,6 +389,7 @@ def main():
         "roofline": roofline,
         "cpu_baseline": cpu,
         "pct_fp32_peak": 100.0 * achieved / nominal,
+        "bridge_step": bridge,
         "origin_row_abs_max": result_check,
     }
     print(json.dumps(line))

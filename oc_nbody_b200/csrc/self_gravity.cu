@@ -68,6 +68,59 @@ __global__ void finish_self_kernel(const double* __restrict__ partial, long long
   }
 }
 
+// ------------------------------------------------------------------------ small clusters ----
+// One launch for a cluster of a few thousand stars (the reference's own configuration is N = 1 024, test_options:57),
+// where the streaming kernel above is latency-bound (pack + TMA ring start-up + finish = 3 launches for ~1e6 pairs).
+// A CTA stages ALL sources once in shared memory (recentred on the first particle in FP64, rounded to FP32 — the same
+// inputs the streaming path and the oracle use), each of its 8 warps owns one target, the 32 lanes split the sources,
+// FP32 pair arithmetic (guarded rsqrt(r^2)^3 form: valid for any eps2 >= 0), four independent FP32 partial sums per
+// lane, FP64 from the warp-shuffle reduction on.  The potential excludes the self term by index.
+#define SG_SMALL_WARPS 8
+#define SG_SMALL_MAX_N 4096
+__global__ void __launch_bounds__(32 * SG_SMALL_WARPS) self_gravity_small_kernel(
+    const double* __restrict__ pos, const double* __restrict__ mass, long long n, float e2, double G,
+    long long tgt_begin, long long tgt_end, double* __restrict__ acc, double* __restrict__ pot) {
+  extern __shared__ float4 s_src[];
+  const double cx = pos[0], cy = pos[n], cz = pos[2 * n];
+  for (long long i = threadIdx.x; i < n; i += blockDim.x)
+    s_src[i] = make_float4((float)(pos[i] - cx), (float)(pos[n + i] - cy), (float)(pos[2 * n + i] - cz), (float)mass[i]);
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long t = tgt_begin + (long long)blockIdx.x * SG_SMALL_WARPS + warp;
+  if (t >= tgt_end) return;
+  const float4 T = s_src[t];
+  float ax[4] = {0.f, 0.f, 0.f, 0.f}, ay[4] = {0.f, 0.f, 0.f, 0.f}, az[4] = {0.f, 0.f, 0.f, 0.f}, ap[4] = {0.f, 0.f, 0.f, 0.f};
+  for (long long j0 = lane; j0 < n; j0 += 128) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const long long j = j0 + 32 * u;
+      if (j < n) {
+        const float4 S = s_src[j];
+        const float dx = S.x - T.x, dy = S.y - T.y, dz = S.z - T.z;
+        const float r2 = fmaf(dz, dz, fmaf(dy, dy, fmaf(dx, dx, e2)));
+        float ri;
+        asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(ri) : "f"(r2));
+        if (!(r2 > 0.f)) ri = 0.f;
+        const float mri = S.w * ri;
+        const float sc = mri * (ri * ri);
+        ax[u] = fmaf(dx, sc, ax[u]), ay[u] = fmaf(dy, sc, ay[u]), az[u] = fmaf(dz, sc, az[u]);
+        if (j != t) ap[u] += mri;
+      }
+    }
+  }
+  double v[4] = {((double)ax[0] + (double)ax[1]) + ((double)ax[2] + (double)ax[3]),
+                 ((double)ay[0] + (double)ay[1]) + ((double)ay[2] + (double)ay[3]),
+                 ((double)az[0] + (double)az[1]) + ((double)az[2] + (double)az[3]),
+                 ((double)ap[0] + (double)ap[1]) + ((double)ap[2] + (double)ap[3])};
+#pragma unroll
+  for (int c = 0; c < 4; ++c)
+    for (int o = 16; o > 0; o >>= 1) v[c] += __shfl_xor_sync(0xffffffffu, v[c], o);
+  if (lane == 0) {
+    acc[t] = G * v[0], acc[n + t] = G * v[1], acc[2 * n + t] = G * v[2];
+    if (pot) pot[t] = -G * v[3];
+  }
+}
+
 static unsigned long long fnv1a(const void* data, size_t bytes, unsigned long long h) {
   const unsigned char* p = (const unsigned char*)data;
   for (size_t i = 0; i < bytes; ++i) {
@@ -75,6 +128,12 @@ static unsigned long long fnv1a(const void* data, size_t bytes, unsigned long lo
     h *= 1099511628211ull;
   }
   return h;
+}
+
+static int g_small_path = 1;  // 0: always take the streaming kernel (tests compare the two)
+extern "C" int ocg_debug_set_small_cluster_path(int on) {
+  g_small_path = on;
+  return 0;
 }
 
 extern "C" int ocg_self_gravity(ocg_ctx* ctx, const double* pos_dev, const double* mass_dev, int64_t n,
@@ -106,6 +165,18 @@ extern "C" int ocg_self_gravity(ocg_ctx* ctx, const double* pos_dev, const doubl
   const bool want_pot = pot_dev != nullptr;
   const int NC = want_pot ? 4 : 3;
   const float e2f = (float)eps2;
+  if (g_small_path && n_seg == 1 && n <= SG_SMALL_MAX_N) {
+    // a single small cluster: one fused launch (see self_gravity_small_kernel)
+    const size_t smem = sizeof(float4) * (size_t)n;
+    OCG_CUDA(ctx, cudaFuncSetAttribute((const void*)self_gravity_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)(sizeof(float4) * SG_SMALL_MAX_N)));
+    const long long nb = (tgt_end - tgt_begin + SG_SMALL_WARPS - 1) / SG_SMALL_WARPS;
+    self_gravity_small_kernel<<<(int)nb, 32 * SG_SMALL_WARPS, smem, st>>>(pos_dev, mass_dev, n, e2f, G, tgt_begin, tgt_end,
+                                                                         acc_dev, pot_dev);
+    OCG_CHECK_LAUNCH(ctx, "self_gravity_small_kernel");
+    ctx->ev_valid = 0;
+    return OCG_OK;
+  }
   const bool guard = !(e2f > 0.f);
   // power-of-two length scale that puts eps at ~2^-8, so that r^6 >= eps^6 ~ 3.5e-15 stays far from the
   // FP32 underflow threshold and separations up to ~1e8 eps stay below overflow (the guarded eps2 == 0

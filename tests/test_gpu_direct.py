@@ -307,3 +307,39 @@ def test_self_gravity_large_cluster_target_shards(ctx, n, world):
         # enough source tiles per shard for the target-paired kernels: the sharded result is bit-identical to the
         # unsharded one (same per-target accumulation order), so an N-GPU BRIDGE run reproduces the 1-GPU trajectory
         assert np.array_equal(acc.cpu().numpy(), full.cpu().numpy())
+
+
+@pytest.mark.parametrize("n,eps_pc", [(1024, 0.01), (4096, 0.01), (333, 0.0), (2, 0.01), (1, 0.01)])
+def test_self_gravity_small_cluster_path(ctx, n, eps_pc):
+    """The fused one-launch kernel for a single small cluster (N <= 4096; the reference runs N = 1024, test_options:57)
+    against the oracle and against the streaming kernel it stands in for, full range and a target shard."""
+    import torch
+    from oc_nbody_b200.synthetic import make_plummer_cluster
+    pos_pc, _, mass = make_plummer_cluster(max(n, 2), seed=n)
+    pos = (pos_pc * 1e-3 + np.array([[8.0], [0.01], [-0.02]]))[:, :n]
+    mass = mass[:n]
+    eps2 = (eps_pc * 1e-3) ** 2
+    d_pos, d_m = dev(np.ascontiguousarray(pos)), dev(np.ascontiguousarray(mass))
+    res = {}
+    for small in (1, 0):
+        ctx.lib.ocg_debug_set_small_cluster_path(small)
+        try:
+            acc = torch.zeros((3, n), dtype=torch.float64, device="cuda")
+            pot = torch.zeros(n, dtype=torch.float64, device="cuda")
+            ctx.self_gravity(d_pos, d_m, eps2, G, acc, pot)
+            sh = torch.full((3, n), np.nan, dtype=torch.float64, device="cuda")
+            ctx.self_gravity(d_pos, d_m, eps2, G, sh, None, tgt_begin=n // 3, tgt_end=n - n // 4)
+        finally:
+            ctx.lib.ocg_debug_set_small_cluster_path(1)
+        torch.cuda.synchronize()
+        res[small] = (acc.cpu().numpy(), pot.cpu().numpy(), sh.cpu().numpy())
+    ref, pref = oracle.self_gravity(pos, mass, eps2, G, want_pot=True)
+    for small in (1, 0):
+        a, p, sh = res[small]
+        if n > 1:
+            assert rel_err(a, ref) <= TOL
+            assert rel_err_scalar(p, pref) <= TOL
+        else:
+            assert np.all(a == 0.0) and np.all(p == 0.0)
+        lo, hi = n // 3, n - n // 4
+        assert np.array_equal(sh[:, lo:hi], a[:, lo:hi]) and np.all(np.isnan(sh[:, :lo])) and np.all(np.isnan(sh[:, hi:]))
