@@ -139,7 +139,8 @@ __device__ __forceinline__ bool source_must_be_near(float d2, float soft_scaled,
 // source_must_be_near because w^2 >= 1).
 __device__ __forceinline__ bool source_unfoldable(float x, float y, float z, float m, float soft_scaled, int kernel,
                                                   const int* misc, float sc) {
-  if (!(m > 0.f)) return true;
+  if (m == 0.f) return false;  // massless: stored as a null record (w = 0), contributes exactly 0
+  if (!(m > 0.f)) return true; // negative or NaN mass: FP64 pair path
   const float w2 = __int_as_float(misc[MISC_M0]) / m;
   const float e2 = kernel == OCG_KERNEL_PLUMMER ? soft_scaled * soft_scaled : 0.f;
   return !(w2 * (box_far2_scaled(x, y, z, misc, sc) + e2) < R2_MAX_FOLDED);
@@ -308,12 +309,13 @@ __global__ void __launch_bounds__(CLS_BLOCK) classify_scatter_kernel(
     float e2 = kernel == OCG_KERNEL_PLUMMER ? hs * hs : 0.f;
     if (mf) {
       // mass-folded record: w = (m/M0)^-1/2 (M0 a power of two: m/M0 is exact), coordinates and e2 carry it
-      const float w = (float)rsqrt((double)(S.w / __int_as_float(misc[MISC_M0])));
-      T[j] = (S.x * sc) * w;
-      T[OCG_TS + j] = (S.y * sc) * w;
-      T[2 * OCG_TS + j] = (S.z * sc) * w;
+      const bool massless = S.w == 0.f;  // null record, same as the tile padding: d' = 0, y3 = 1, d'*y3 = 0
+      const float w = massless ? 0.f : (float)rsqrt((double)(S.w / __int_as_float(misc[MISC_M0])));
+      T[j] = massless ? 0.f : (S.x * sc) * w;
+      T[OCG_TS + j] = massless ? 0.f : (S.y * sc) * w;
+      T[2 * OCG_TS + j] = massless ? 0.f : (S.z * sc) * w;
       T[3 * OCG_TS + (mf == 2 ? (j ^ 1) : j)] = w;
-      T[4 * OCG_TS + j] = (e2 * w) * w;
+      T[4 * OCG_TS + j] = massless ? 1.f : (e2 * w) * w;
     } else {
       T[j] = S.x * sc;
       T[OCG_TS + j] = S.y * sc;
