@@ -139,6 +139,28 @@ def cpu_sample_rate(tgt_pos, src_pos, src_mass, src_eps, seconds):
     return n_s * tp.shape[0] / dt, desc, oracle.num_threads()
 
 
+def reference_time_interp_cost(n_points=16 ** 3 + 1, n_snap=9):
+    """The reference's OWN per-step time interpolation, run as-is with scipy (gizmo_interface.py:587-620): one
+    splrep per grid point and component at start-up, one splev per grid point and component on every evolve_model.
+    configs[0] size (16^3+1 points, 9 snapshots as test_options:20-22), single process (the reference spreads the
+    same calls over multiprocessing.Pool(ncpu))."""
+    from scipy import interpolate
+    rng = np.random.default_rng(1776)
+    times = 23.0 * np.arange(n_snap)
+    series = rng.normal(0.0, 1e-2, (3, n_snap, n_points))
+    t0 = time.perf_counter()
+    tck = [[interpolate.splrep(times, series[c][:, i]) for i in range(n_points)] for c in range(3)]
+    setup = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    for c in range(3):
+        for i in range(n_points):
+            float(interpolate.splev(57.3, tck[c][i]))
+    step = time.perf_counter() - t0
+    return {"n_grid_points": n_points, "n_snapshots": n_snap, "splrep_setup_s": setup, "splev_per_evolve_model_s": step,
+            "calls_per_step": 3 * n_points,
+            "note": "reference mechanism run with scipy as-is, 1 process; here evolve_model is O(1) and the blend is fused into K3"}
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU path = the oracle port (the reference itself cannot be imported:
     SURVEY §0.3), all host threads, each step a bounded sample of the N=1 workload."""
@@ -165,6 +187,7 @@ def run_reference(args):
         "cpu_baseline": {"value": val, "unit": "G/s", "cores": threads, "kind": "port", "sample": desc},
         "e2e": {"value": val, "unit": "G/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
+        "reference_time_interp": reference_time_interp_cost(),
         "note": "ms_per_step extrapolates the sampled rate to the full step (a direct sum's rate is size independent)",
     }
     print(json.dumps(line))
