@@ -125,7 +125,8 @@ def cpu_sample_rate(tgt_pos, src_pos, src_mass, src_eps, seconds):
     import oracle
     e2 = src_eps * src_eps
     n_s = src_pos.shape[0]
-    cal_t = np.ascontiguousarray(tgt_pos[:: max(1, tgt_pos.shape[0] // 512)][:512])
+    cal_t = np.ascontiguousarray(tgt_pos[:: max(1, tgt_pos.shape[0] // 2048)][:2048])
+    oracle.field_direct_fast(src_pos[:20000], src_mass[:20000], e2[:20000], cal_t[:64], G_KPC)  # spin the threads up
     t0 = time.perf_counter()
     oracle.field_direct_fast(src_pos, src_mass, e2, cal_t, G_KPC)
     rate0 = n_s * cal_t.shape[0] / max(time.perf_counter() - t0, 1e-4)
@@ -168,7 +169,7 @@ def run_reference(args):
     if rank != 0:
         return
     g = make_targets(args.grid)
-    n_sample_src = min(args.n_src, 400000)
+    n_sample_src = min(args.n_src, 1000000)
     pos, mass, eps = make_sources(n_sample_src, seed=1776)
     rates, desc, threads = [], "", 1
     per_step = max(2.0, min(20.0, 120.0 / max(1, args.steps + args.warmup)))
@@ -397,7 +398,7 @@ def main():
     bridge = bridge_step_times(ctx) if world == 1 else None
     cpu = None
     if not args.no_cpu_baseline:
-        r, desc, threads = cpu_sample_rate(g.evolved_grid, pos[:400000], mass[:400000], eps[:400000], 12.0)
+        r, desc, threads = cpu_sample_rate(g.evolved_grid, pos[:1000000], mass[:1000000], eps[:1000000], 15.0)
         cpu = {"value": r / 1e9, "unit": "G/s", "cores": threads, "kind": "port", "sample": desc}
     line = {
         "metric": "pairwise_grav_interactions_per_sec", "value": value, "unit": "G/s", "n_gpus": world, "steps": args.steps,

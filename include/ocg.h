@@ -97,7 +97,9 @@ int ocg_frame_subtract(ocg_ctx* ctx, double* acc_dev, int64_t n_tgt, int64_t cen
  * src_pos_host [n_src][3], src_mass_host [n_src], src_soft_host [n_src] (NULL = 0),
  * tgt_pos_host [n_tgt][3] (= grid.evolved_grid), center[3] (= grid.ss_evolved_position),
  * center_row: row of tgt that sits at `center` (the appended origin, grid_cartesian.py:66-67)
- * or -1 for no subtraction. acc_host [3][n_tgt]; pot_host [n_tgt] or NULL.                     */
+ * or -1 for no subtraction. acc_host [3][n_tgt]; pot_host [n_tgt] or NULL.
+ * The sources are streamed through HBM in chunks of 2^26 particles, so n_src is not limited by device
+ * memory or by the 2^31 particles-per-call limit of ocg_field_direct.                              */
 int ocg_field_build_host(ocg_ctx* ctx, const double* src_pos_host, const double* src_mass_host,
                          const double* src_soft_host, int64_t n_src, const double* tgt_pos_host,
                          int64_t n_tgt, const double center[3], int64_t center_row, int kernel,

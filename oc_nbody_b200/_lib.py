@@ -88,6 +88,7 @@ def load_library():
     L.ocg_debug_set_precise_near.argtypes = [ctypes.c_int]
     L.ocg_debug_set_mass_fold.argtypes = [ctypes.c_int]
     L.ocg_debug_set_small_cluster_path.argtypes = [ctypes.c_int]
+    L.ocg_debug_set_host_chunk.argtypes = [ctypes.c_int64]
     _lib = L
     return L
 

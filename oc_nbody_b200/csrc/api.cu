@@ -217,6 +217,14 @@ extern "C" int ocg_frame_subtract(ocg_ctx* ctx, double* acc_dev, int64_t n_tgt, 
 }
 
 // --------------------------------------------------------------- K1 host form (e2e path) ----
+// Sources are streamed through HBM in chunks of this many particles (accumulate = 1 after the first): bounded device
+// memory (~100 B per staged particle) for snapshots of any size, and no 2^31 limit on n_src.
+static int64_t g_host_chunk = 1ll << 26;
+extern "C" int ocg_debug_set_host_chunk(int64_t n) {
+  g_host_chunk = n > 0 ? n : (1ll << 26);
+  return 0;
+}
+
 extern "C" int ocg_field_build_host(ocg_ctx* ctx, const double* src_pos_host, const double* src_mass_host,
                                     const double* src_soft_host, int64_t n_src, const double* tgt_pos_host,
                                     int64_t n_tgt, const double center[3], int64_t center_row, int kernel,
@@ -235,28 +243,33 @@ extern "C" int ocg_field_build_host(ocg_ctx* ctx, const double* src_pos_host, co
   float *d_src, *d_sft = nullptr, *d_tgt;
   int rc;
   const int NCO = pot_host ? 4 : 3;
-  if ((rc = ocg_scratch(ctx, OCG_SCR_F64A, sizeof(double) * 3 * (size_t)(n_src > n_tgt ? n_src : n_tgt), (void**)&d_pos))) return rc;
-  if ((rc = ocg_scratch(ctx, OCG_SCR_F64B, sizeof(double) * (size_t)(n_src > 0 ? n_src : 1), (void**)&d_mass))) return rc;
-  if ((rc = ocg_scratch(ctx, OCG_SCR_SRC, sizeof(float) * 4 * (size_t)(n_src > 0 ? n_src : 1), (void**)&d_src))) return rc;
+  const int64_t chunk = n_src < g_host_chunk ? n_src : g_host_chunk;  // particles staged at a time
+  if ((rc = ocg_scratch(ctx, OCG_SCR_F64A, sizeof(double) * 3 * (size_t)(chunk > n_tgt ? chunk : n_tgt), (void**)&d_pos))) return rc;
+  if ((rc = ocg_scratch(ctx, OCG_SCR_F64B, sizeof(double) * (size_t)(chunk > 0 ? chunk : 1), (void**)&d_mass))) return rc;
+  if ((rc = ocg_scratch(ctx, OCG_SCR_SRC, sizeof(float) * 4 * (size_t)(chunk > 0 ? chunk : 1), (void**)&d_src))) return rc;
   if ((rc = ocg_scratch(ctx, OCG_SCR_TGT, sizeof(float) * 4 * (size_t)n_tgt, (void**)&d_tgt))) return rc;
   if ((rc = ocg_scratch(ctx, OCG_SCR_OUT, sizeof(double) * NCO * (size_t)n_tgt, (void**)&d_out))) return rc;
-  if (n_src > 0) {
-    OCG_CUDA(ctx, cudaMemcpyAsync(d_pos, src_pos_host, sizeof(double) * 3 * n_src, cudaMemcpyHostToDevice, st));
-    OCG_CUDA(ctx, cudaMemcpyAsync(d_mass, src_mass_host, sizeof(double) * n_src, cudaMemcpyHostToDevice, st));
-    if ((rc = ocg_recentre_f64(ctx, d_pos, d_mass, n_src, center, d_src, st))) return rc;
-    if (src_soft_host) {
-      if ((rc = ocg_scratch(ctx, OCG_SCR_F64C, sizeof(double) * (size_t)n_src, (void**)&d_soft))) return rc;
-      if ((rc = ocg_scratch(ctx, OCG_SCR_SOFT, sizeof(float) * (size_t)n_src, (void**)&d_sft))) return rc;
-      OCG_CUDA(ctx, cudaMemcpyAsync(d_soft, src_soft_host, sizeof(double) * n_src, cudaMemcpyHostToDevice, st));
-      if ((rc = ocg_cast_f64_f32(ctx, d_soft, n_src, d_sft, st))) return rc;
-    }
+  if (n_src > 0 && src_soft_host) {
+    if ((rc = ocg_scratch(ctx, OCG_SCR_F64C, sizeof(double) * (size_t)chunk, (void**)&d_soft))) return rc;
+    if ((rc = ocg_scratch(ctx, OCG_SCR_SOFT, sizeof(float) * (size_t)chunk, (void**)&d_sft))) return rc;
   }
-  // targets reuse the FP64 staging buffer after the source recentre kernel has consumed it (same stream)
+  // targets first (they go through the FP64 staging buffer the source chunks reuse afterwards; same stream)
   d_tpos = d_pos;
   OCG_CUDA(ctx, cudaMemcpyAsync(d_tpos, tgt_pos_host, sizeof(double) * 3 * n_tgt, cudaMemcpyHostToDevice, st));
   if ((rc = ocg_recentre_f64(ctx, d_tpos, nullptr, n_tgt, center, d_tgt, st))) return rc;
   double* d_pot = pot_host ? d_out + 3 * n_tgt : nullptr;
-  if ((rc = ocg_direct_sum_impl(ctx, d_src, d_sft, n_src, d_tgt, n_tgt, kernel, G, d_out, d_pot, 0, st))) return rc;
+  if (n_src == 0 && (rc = ocg_direct_sum_impl(ctx, d_src, d_sft, 0, d_tgt, n_tgt, kernel, G, d_out, d_pot, 0, st))) return rc;
+  for (int64_t off = 0; off < n_src; off += chunk) {
+    const int64_t nc = n_src - off < chunk ? n_src - off : chunk;
+    OCG_CUDA(ctx, cudaMemcpyAsync(d_pos, src_pos_host + 3 * off, sizeof(double) * 3 * nc, cudaMemcpyHostToDevice, st));
+    OCG_CUDA(ctx, cudaMemcpyAsync(d_mass, src_mass_host + off, sizeof(double) * nc, cudaMemcpyHostToDevice, st));
+    if ((rc = ocg_recentre_f64(ctx, d_pos, d_mass, nc, center, d_src, st))) return rc;
+    if (src_soft_host) {
+      OCG_CUDA(ctx, cudaMemcpyAsync(d_soft, src_soft_host + off, sizeof(double) * nc, cudaMemcpyHostToDevice, st));
+      if ((rc = ocg_cast_f64_f32(ctx, d_soft, nc, d_sft, st))) return rc;
+    }
+    if ((rc = ocg_direct_sum_impl(ctx, d_src, d_sft, nc, d_tgt, n_tgt, kernel, G, d_out, d_pot, off > 0 ? 1 : 0, st))) return rc;
+  }
   if (center_row >= 0 && (rc = ocg_frame_subtract(ctx, d_out, n_tgt, center_row, st))) return rc;
   OCG_CUDA(ctx, cudaMemcpyAsync(acc_host, d_out, sizeof(double) * 3 * n_tgt, cudaMemcpyDeviceToHost, st));
   if (pot_host) OCG_CUDA(ctx, cudaMemcpyAsync(pot_host, d_pot, sizeof(double) * n_tgt, cudaMemcpyDeviceToHost, st));

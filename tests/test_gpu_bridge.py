@@ -347,3 +347,36 @@ def test_bridge_cuda_graph_step_is_bit_identical(small_world, ctx):
     # steps; the graph bakes dt itself into the captured kernels.  Everything else is the same arithmetic.
     assert np.max(np.abs(x0 - x1)) <= 1e-14 * 8.0 and np.max(np.abs(v0 - v1)) <= 1e-13 * np.max(np.abs(v0))
     assert abs(t0 - t1) < 1e-12 and ft0 == ft1 and abs(t1 - nstep * dt) < 1e-12
+
+
+def test_pykdgrav_compat_call_sites(ctx):
+    """The reference's own three calls (gizmo_interface.py:561,564,566) through the drop-in module:
+    tree = ConstructKDTree(r, m, soft); GetAccelParallel(grid, tree, G, theta); GetAccelParallel([centre], ...)."""
+    from oc_nbody_b200.grid_cartesian import grid
+    from oc_nbody_b200.pykdgrav_compat import ConstructKDTree, GetAccelParallel, GetPotentialParallel
+    from oc_nbody_b200.synthetic import make_snapshot
+    snap = make_snapshot(30000, seed=11)
+    r = np.concatenate([snap[s]["position"] for s in ("star", "dark", "gas")])
+    m = np.concatenate([snap[s]["mass"] for s in ("star", "dark", "gas")])
+    soft = np.concatenate([np.full(len(snap["star"]["mass"]), 11.2e-3), np.full(len(snap["dark"]["mass"]), 112e-3),
+                           2.8e-3 * snap["gas"]["smooth.length"]])
+    g = grid(0.05, 0.05, 0.05, 0.05 / 6)
+    center = np.array([8.0, 0.0, 0.0])
+    g.gen_evolved_grid(center)
+    G_ref, theta = 4.398600413517813e-09, 0.5
+    tree = ConstructKDTree(np.float64(r), np.float64(m), np.float64(soft), ctx=ctx)
+    accel = GetAccelParallel(g.evolved_grid, tree, G_ref, theta)
+    accel_center = GetAccelParallel(np.array([g.ss_evolved_position]), tree, G_ref, theta)
+    assert accel.shape == (len(g), 3) and accel_center.shape == (1, 3)
+    s32 = oracle.recentre(r, m, center)
+    ref, pref = oracle.field_direct(s32, soft.astype(np.float32), oracle.recentre(g.evolved_grid, None, center),
+                                    oracle.KERNEL_SPLINE, G_ref, want_pot=True)
+    assert rel_err(accel.T, ref) <= TOL
+    assert rel_err(accel_center.T, ref[:, -1:]) <= TOL
+    # the frame subtraction as the reference writes it (gizmo_interface.py:569-571) leaves the tidal field
+    tidal = accel - accel_center[0]
+    want = oracle.frame_subtract(ref, g.origin_row)
+    scale = np.sqrt((ref * ref).sum(axis=0)).max()
+    assert np.max(np.abs(tidal.T - want)) <= 2e-6 * scale
+    pot = GetPotentialParallel(g.evolved_grid, tree, G_ref, theta)
+    assert np.max(np.abs(pot - pref) / np.abs(pref)) <= TOL

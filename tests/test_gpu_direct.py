@@ -220,6 +220,16 @@ def test_frame_subtract_and_host_form(ctx):
     ctx.frame_subtract(d, row)
     torch.cuda.synchronize()
     assert np.array_equal(d.cpu().numpy(), ref)
+    # the host form streams the sources through HBM in chunks (2^26 by default): force 4 ragged chunks
+    ctx.lib.ocg_debug_set_host_chunk(1777)
+    try:
+        acc_c, pot_c = ctx.field_build_host(pos, mass, soft, tgt, center, row, oracle.KERNEL_SPLINE, G, want_pot=True)
+    finally:
+        ctx.lib.ocg_debug_set_host_chunk(0)
+    assert np.all(acc_c[:, row] == 0.0)
+    assert rel_err(acc_c + raw[:, row:row + 1], raw) <= TOL
+    _, pref = oracle.field_direct(s32, soft.astype(np.float32), t32, oracle.KERNEL_SPLINE, G, want_pot=True)
+    assert rel_err_scalar(pot_c, pref) <= TOL
 
 
 @pytest.mark.parametrize("n,eps_pc", [(1024, 0.01), (777, 0.0), (4100, 0.05), (20000, 0.01), (17000, 0.0), (66000, 0.01)])

@@ -111,3 +111,48 @@ def test_config3_interp_full_batch_bit_exact(ctx):
                     dev(p[:, 1].copy()), dev(p[:, 2].copy()), dev(scl), acc, pot)
     torch.cuda.synchronize()
     assert np.array_equal(acc.cpu().numpy(), ref) and np.array_equal(pot.cpu().numpy(), refpot)
+
+
+def test_reference_default_grid_test_options(ctx):
+    """The grid of the reference's own example run (test_options:93-100: 0.6 kpc box at 0.005 -> 120^3 coarse nodes,
+    0.02 kpc fine box at 0.0005 -> 40^3 fine nodes; ~1.79 M field points): field build on the reference's point list,
+    two-level kick against the oracle's layout + interpolation, bit for bit."""
+    from oc_nbody_b200.gizmo_field import gizmo_field
+    from oc_nbody_b200.synthetic import advance_snapshot, make_snapshot
+    from oc_nbody_b200.units import units
+    snaps = [make_snapshot(100000, seed=1776)]
+    snaps.append(advance_snapshot(snaps[0], 23.0))
+    center = np.array([8.0, 0.0, 0.0])
+    opts = dict(grid_x_size_in_kpc=0.6, grid_y_size_in_kpc=0.6, grid_z_size_in_kpc=0.6, grid_resolution=0.005, fine_grid=True,
+                grid_fine_x_size_in_kpc=0.02, grid_fine_y_size_in_kpc=0.02, grid_fine_z_size_in_kpc=0.02,
+                grid_fine_resolution=0.0005, with_potential=False)
+    field = gizmo_field(opts, snaps, chosen_positions=np.tile(center, (2, 1)), ctx=ctx)
+    g = field.grid
+    assert g.coarse_shape == (120, 120, 120) and g.fine_shape == (40, 40, 40)
+    assert len(g) == 120 ** 3 - len(g.coarse_hole_index) + 40 ** 3 + 1 and len(g.coarse_hole_index) == 64
+    assert g.snapshot_acceleration_x.shape == (2, len(g)) and np.all(np.isfinite(g.snapshot_acceleration_x))
+    assert g.snapshot_acceleration_x[0, g.origin_row] == 0.0
+    # spot rows of the field against the oracle (raw field: frame term added back)
+    r, m, soft = field._source_arrays_(snaps[0])
+    rows = np.array([0, 12345, g.fine_row0 - 1, g.fine_row0, g.fine_row0 + 31999, len(g) - 2, len(g) - 1])
+    s32 = oracle.recentre(r, m, center)
+    t32 = oracle.recentre(g.init_grid[rows] + center, None, center)
+    raw = oracle.field_direct(s32, soft.astype(np.float32), t32, oracle.KERNEL_SPLINE, field.G)
+    got = np.stack([g.snapshot_acceleration_x[0][rows], g.snapshot_acceleration_y[0][rows], g.snapshot_acceleration_z[0][rows]])
+    assert rel_err(got + raw[:, -1:], raw) <= TOL
+    # the kick
+    field.evolve_grid(center)
+    field.evolve_model(9.2 | units.Myr)
+    wb = np.float32(0.4)
+    coarse, fine = oracle.layout_nested(field._planes_(), g.n_lattice, g.coarse_keep_index, g.coarse_hole_index,
+                                        g.coarse_hole_points(), g.fine_nodes, g.fine_row0)
+    rng = np.random.default_rng(5)
+    p = np.concatenate([rng.normal(0, 0.004, (3000, 3)), rng.uniform(-0.03, 0.03, (2000, 3)), rng.uniform(-0.6, 0.6, (1000, 3))])
+    x = p + center
+    ref = oracle.grid_interp_nested(g.nodes, g.fine_nodes, center, list(coarse), list(fine),
+                                    [float(np.float32(np.float32(1.0) - wb)), float(wb)], x[:, 0], x[:, 1], x[:, 2],
+                                    want_level=True)
+    assert 2500 < ref["level"].sum() < 5500
+    ax, ay, az = field.get_gravity_at_point(0 | units.kpc, x[:, 0] | units.kpc, x[:, 1] | units.kpc, x[:, 2] | units.kpc)
+    got = np.stack([c.value_in(units.kms / units.Myr) for c in (ax, ay, az)])
+    assert np.array_equal(got, ref["acc"])
