@@ -591,7 +591,8 @@ extern "C" int ocg_debug_set_precise_near(int on) {
 
 // n_tgt: targets in the call (or shard); seg_len: typical length of one independent target run (= n_tgt for the
 // field build, the cluster size for batched self-gravity) — a tile never spans two runs.
-int ocg_pick_variant(ocg_ctx* ctx, int64_t n_tgt, int64_t seg_len, bool guard, bool allow_mf, int64_t src_tiles) {
+int ocg_pick_variant(ocg_ctx* ctx, int64_t n_tgt, int64_t seg_len, bool guard, bool allow_mf, int64_t src_tiles,
+                     bool fine_tiles) {
   if (g_force_variant >= 0) {
     // a forced variant without the guarded form falls back to the guarded production kernels; so does a
     // mass-folded one when the caller lays out plain tiles (K4)
@@ -611,7 +612,10 @@ int ocg_pick_variant(ocg_ctx* ctx, int64_t n_tgt, int64_t seg_len, bool guard, b
     return (n_tgt + ct - 1) / ct * src_tiles >= 4ll * ctx->sm_count * g_variants[v].minb;
   };
   if (guard) return (n_tgt >= 16384 && waste_ok(OCG_VARIANT_MID_GUARD)) ? OCG_VARIANT_MID_GUARD : OCG_VARIANT_SMALL;
-  if ((n_tgt >= 65536 || enough(OCG_VARIANT_BIG)) && waste_ok(OCG_VARIANT_BIG)) return OCG_VARIANT_BIG;
+  // fine_tiles (K4): a cluster has few target tiles, so the 512-target kernel balances better over the SMs than the
+  // 3072-target one although its inner loop is ~1 point slower (tools/probe_k4.py: 65.0 vs 63.0 % at N = 65 536,
+  // 64.8 vs 57.4 % at 16 x 16 384)
+  if (!fine_tiles && (n_tgt >= 65536 || enough(OCG_VARIANT_BIG)) && waste_ok(OCG_VARIANT_BIG)) return OCG_VARIANT_BIG;
   if ((n_tgt >= 16384 || enough(OCG_VARIANT_MID)) && waste_ok(OCG_VARIANT_MID)) return OCG_VARIANT_MID;
   return OCG_VARIANT_SMALL;
 }

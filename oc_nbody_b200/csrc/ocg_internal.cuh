@@ -107,7 +107,7 @@ struct DirectParams {
 
 // ---- entry points implemented in other translation units ------------------------------------
 int ocg_pick_variant(ocg_ctx* ctx, int64_t n_tgt, int64_t seg_len, bool guard, bool allow_mf = false,
-                     int64_t src_tiles = 0);
+                     int64_t src_tiles = 0, bool fine_tiles = false);
 int ocg_variant_tpt(int variant);
 int ocg_variant_threads(int variant);
 int ocg_variant_slots(ocg_ctx* ctx, int variant);

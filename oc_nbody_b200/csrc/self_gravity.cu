@@ -192,7 +192,8 @@ extern "C" int ocg_self_gravity(ocg_ctx* ctx, const double* pos_dev, const doubl
   // the tile shape follows the typical cluster size, not the batch size: a 4096-star cluster would fill only
   // 1 1/3 of the 3072-target tiles of the big-grid kernel
   const int64_t seg_typ = (n + n_seg - 1) / n_seg;
-  const int variant = ocg_pick_variant(ctx, n_shard, seg_typ, guard, /*allow_mf=*/false, (seg_typ + OCG_TS - 1) / OCG_TS);
+  const int variant = ocg_pick_variant(ctx, n_shard, seg_typ, guard, /*allow_mf=*/false, (seg_typ + OCG_TS - 1) / OCG_TS,
+                                       /*fine_tiles=*/true);
   const int tpt = ocg_variant_tpt(variant);
   const int CT = ocg_variant_threads(variant) * tpt;
 
