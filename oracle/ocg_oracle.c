@@ -7,12 +7,15 @@
  * PARITY UNPINNED BY THE REFERENCE: gusbeane/oc_nbody ships no tests, golden vectors or fixtures
  * (SURVEY.md §4, §8c), cannot be imported (analysis.py:573 SyntaxError; amuse/pykdgrav/rbf absent)
  * and the arithmetic of its field build lives in un-vendored, un-pinned pykdgrav.  What IS pinned:
- *   - the grid layout, against the real grid_cartesian.py imported in the build container
- *     (tests/golden/grid_*.npz, made by tests/golden/make_golden.py);
+ *   - the grid layout, single lattice and nested fine grid, against the real grid_cartesian.py imported
+ *     in the build container (tests/golden/grid_reference.npz, grid_nested_reference.npz, made by
+ *     tests/golden/make_golden.py);
+ *   - the reference's time interpolation (scipy splrep/splev per grid point, runnable as-is):
+ *     tests/golden/time_spline_reference.npz;
  *   - the spline kernel, restated from pykdgrav's published ForceKernel/PotentialKernel
  *     (M. Grudic, pykdgrav/pytreegrav kernel.py; cubic spline of Springel et al. 2001 with
  *     support radius h), checked for continuity/Newtonian limits and against scipy quadrature of
- *     the spline density in tests/test_oracle.py;
+ *     the spline density in tests/test_cpu_oracle.py;
  *   - analytic known answers (two-body, shell theorem, homogeneous sphere, affine fields).
  *
  * Every function is the FP64 restatement of one step of the reference with the north_star's

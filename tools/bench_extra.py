@@ -109,6 +109,31 @@ def main():
         out[name] = dict(ms_median=med, ms_best=best, interactions=inter, ginter_s=inter / med / 1e6,
                          pct_fp32_peak=100 * 20 * inter / med / 1e9 / nominal, note="pack + kernel + finish per call")
 
+    # ---- configs[3] as a whole: one BRIDGE step of 256 clusters x 4096 stars, each kicked by its own 32^3 grid ----
+    from oc_nbody_b200.cluster import KMS_TO_KPC_PER_MYR
+    pos_pc, vel1, mass1 = make_plummer_cluster(nstar)
+    bpos = torch.from_numpy(np.ascontiguousarray(np.concatenate([pos_pc * 1e-3 + origin[k][:, None] for k in range(ncl)], axis=1))).to(dev)
+    bvel = torch.from_numpy(np.ascontiguousarray(np.tile(vel1, (1, ncl)))).to(dev)
+    bm = torch.from_numpy(np.tile(mass1, ncl)).to(dev)
+    bseg = np.arange(ncl + 1, dtype=np.int64) * nstar
+    a_t = torch.empty((3, ncl * nstar), dtype=torch.float64, device=dev)
+    a_s = torch.empty((3, ncl * nstar), dtype=torch.float64, device=dev)
+    ctx.self_gravity(bpos, bm, (0.01e-3) ** 2, G_KPC_KMS_MYR, a_s, None, seg_offsets=bseg)
+
+    def batch_step(dt=0.1):
+        ctx.grid_interp((n, n, n), nodes, d_or, rec[0], rec[1], 0.37, bpos[0], bpos[1], bpos[2], d_scl, a_t, None)
+        ctx.kick(bvel, a_t, 0.5 * dt)
+        ctx.kick(bvel, a_s, 0.5 * dt)
+        ctx.drift(bpos, bvel, dt, KMS_TO_KPC_PER_MYR)
+        ctx.self_gravity(bpos, bm, (0.01e-3) ** 2, G_KPC_KMS_MYR, a_s, None, seg_offsets=bseg)
+        ctx.kick(bvel, a_s, 0.5 * dt)
+        ctx.grid_interp((n, n, n), nodes, d_or, rec[0], rec[1], 0.38, bpos[0], bpos[1], bpos[2], d_scl, a_t, None)
+        ctx.kick(bvel, a_t, 0.5 * dt)
+    med, best = timeit(batch_step, iters=10, warm=2)
+    out["bridge_step_c4_256_clusters_x_4096_stars"] = dict(
+        ms_median=med, ms_best=best, stars=ncl * nstar,
+        note="K3 batched (per-cluster 32^3 grids, 2 snapshots) + K5 + K4 batched (256 segments) + K5 + K3 + K5, device resident")
+
     # ---- BRIDGE step ----
     from oc_nbody_b200.bridge import Bridge
     from oc_nbody_b200.cluster import cluster_code
