@@ -380,3 +380,27 @@ def test_pykdgrav_compat_call_sites(ctx):
     assert np.max(np.abs(tidal.T - want)) <= 2e-6 * scale
     pot = GetPotentialParallel(g.evolved_grid, tree, G_ref, theta)
     assert np.max(np.abs(pot - pref) / np.abs(pref)) <= TOL
+
+
+def test_driver_loop_follows_the_cluster(small_world, ctx):
+    """oc_nbody.py:15-70 restated over the GPU codes (driver.evolve_cluster_in_galaxy): the grid origin follows the
+    bound centre of mass, ejected stars leave the system, frames carry the reference's keys, energy stays put."""
+    from oc_nbody_b200.driver import evolve_cluster_in_galaxy
+    from oc_nbody_b200.synthetic import make_plummer_cluster
+    field, _, _ = small_world
+    pos_pc, vel, mass = make_plummer_cluster(800)
+    center = np.array([8.0, 0.0, 0.0])
+    pos = pos_pc * 1e-3 + center[:, None]
+    vel = vel + np.array([[0.0], [20.0], [0.0]])       # the cluster moves through the grid: 20 km/s ~ 0.02 kpc/Myr
+    pos[:, 17] += 0.3                                   # one star far outside the ejection cut
+    field.evolve_grid(center)
+    field.evolve_model(0.0)
+    cl, rec = evolve_cluster_in_galaxy(field, mass, pos, vel, timestep=0.05, tend=0.5, softening_pc=0.01, eject_cut=100.0,
+                                       ctx=ctx)
+    assert len(rec.frames) == 10 and cl.n == 799 and 17 not in cl.key
+    f = rec.frames[-1]
+    assert set(f) == {"time", "position", "velocity", "mass", "com", "chosen_position", "chosen_velocity"}
+    assert f["position"].shape == (799, 3) and abs(f["time"] - 0.45) < 1e-12
+    # the grid origin is the last bound centre of mass, which moved with the cluster: 0.45 Myr x 20 km/s ~ 9 pc in y
+    assert np.allclose(field._origin, f["com"]) and 0.007 < f["com"][1] - rec.frames[0]["com"][1] < 0.011
+    assert abs(f["com"][0] - 8.0) < 2e-3
