@@ -202,6 +202,35 @@ int ocg_self_gravity(ocg_ctx* ctx, const double* pos_dev, const double* mass_dev
                      int64_t tgt_begin, int64_t tgt_end, double* acc_dev, double* pot_dev,
                      void* stream);
 
+/* ---- K6: Hermite force loop + 4th-order Hermite predictor / corrector ------
+ * The arithmetic of the ph4 worker itself (4th-order Hermite, oc_code.py:218-229; options.py:248-253):
+ *   acc[c][i]  = G sum_j m_j d_c / r^3                                  d = x_j - x_i, r^2 = |d|^2 + eps2
+ *   jerk[c][i] = G vel_to_len sum_j m_j [ w_c / r^3 - 3 (d.w) d_c / r^5 ]   w = v_j - v_i
+ * vel_dev fp64 [3][n] in the caller's velocity unit; vel_to_len converts it to length/time of the
+ * acceleration's time unit (kpc, km/s, Myr: 1.0227e-3), so jerk is in acceleration units per time.
+ * Positions AND velocities of each segment are recentred on its first particle before rounding to fp32.
+ * Other arguments as ocg_self_gravity; jerk_dev fp64 [3][n]; pot_dev nullable.  ph4's block time steps
+ * are not reproduced: all stars share one step (see ocg_hermite_correct for the step criterion).      */
+int ocg_self_gravity_hermite(ocg_ctx* ctx, const double* pos_dev, const double* vel_dev,
+                             const double* mass_dev, int64_t n, const int64_t* seg_offsets_host,
+                             int32_t n_seg, double eps2, double G, double vel_to_len, int64_t tgt_begin,
+                             int64_t tgt_end, double* acc_dev, double* jerk_dev, double* pot_dev,
+                             void* stream);
+/* Predictor: pos_pred = pos + ((vel*dt + acc*(dt^2/2)) + jerk*(dt^3/6)) * vel_to_len,
+ *            vel_pred = vel + (acc*dt + jerk*(dt^2/2)); fp64 [3][n], every op rounded separately.     */
+int ocg_hermite_predict(ocg_ctx* ctx, const double* pos_dev, const double* vel_dev, const double* acc_dev,
+                        const double* jerk_dev, int64_t n, double dt, double vel_to_len,
+                        double* pos_pred_dev, double* vel_pred_dev, void* stream);
+/* Corrector (Makino & Aarseth 1992) from the force at the predicted state (acc1, jerk1):
+ *   a2 = (-6 (a0 - a1) - dt (4 j0 + 2 j1)) / dt^2      a3 = (12 (a0 - a1) + 6 dt (j0 + j1)) / dt^3
+ *   vel = vel_pred + a2 dt^3/6 + a3 dt^4/24            pos = pos_pred + (a2 dt^4/24 + a3 dt^5/120) vel_to_len
+ * then acc0 <- acc1, jerk0 <- jerk1.  dt_min_dev (DEVICE fp64 scalar, nullable) receives the minimum over the
+ * stars of the Aarseth step sqrt(eta (|a1||a2'| + |j1|^2) / (|j1||a3| + |a2'|^2)), a2' = a2 + dt a3.          */
+int ocg_hermite_correct(ocg_ctx* ctx, double* pos_dev, double* vel_dev, double* acc0_dev, double* jerk0_dev,
+                        const double* pos_pred_dev, const double* vel_pred_dev, const double* acc1_dev,
+                        const double* jerk1_dev, int64_t n, double dt, double vel_to_len, double eta,
+                        double* dt_min_dev, void* stream);
+
 /* ---- K5: BRIDGE kick / drift (amuse.couple.bridge kick + leapfrog drift, oc_nbody.py:56) ----
  * vel[c][i] += dt * acc[c][i]   ;   pos[c][i] += dt * vel[c][i] * vel_to_len
  * All fp64 [3][n] component-major; mul and add rounded separately (no FMA) so that a numpy

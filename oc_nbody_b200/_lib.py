@@ -20,7 +20,7 @@ ABI_SYMBOLS = [
     "ocg_version", "ocg_create", "ocg_destroy", "ocg_last_error", "ocg_device_info", "ocg_launch_count",
     "ocg_last_direct_kernel_ms", "ocg_set_kernel_timing", "ocg_recentre_f64", "ocg_cast_f64_f32",
     "ocg_field_direct", "ocg_frame_subtract", "ocg_field_build_host", "ocg_pack_planes", "ocg_grid_time_blend",
-    "ocg_grid_interp", "ocg_grid_interp_multi", "ocg_grid_interp_nested", "ocg_pack_planes_indexed", "ocg_set_interp_weight_slots", "ocg_grid_interp_slot", "ocg_self_gravity", "ocg_bound_com", "ocg_eject_mask", "ocg_compact_rows", "ocg_kick", "ocg_drift", "ocg_axpy", "ocg_probe_throughput",
+    "ocg_grid_interp", "ocg_grid_interp_multi", "ocg_grid_interp_nested", "ocg_pack_planes_indexed", "ocg_set_interp_weight_slots", "ocg_grid_interp_slot", "ocg_self_gravity", "ocg_self_gravity_hermite", "ocg_hermite_predict", "ocg_hermite_correct", "ocg_bound_com", "ocg_eject_mask", "ocg_compact_rows", "ocg_kick", "ocg_drift", "ocg_axpy", "ocg_probe_throughput",
 ]
 
 
@@ -74,6 +74,13 @@ def load_library():
     L.ocg_grid_interp_slot.argtypes = [vp, ctypes.POINTER(_GridDesc), ctypes.POINTER(_GridDesc), vp, vp, i32, i32, vp, vp, vp, vp,
                                        i64, vp, vp, vp]
     L.ocg_self_gravity.argtypes = [vp, vp, vp, i64, vp, i32, dbl, dbl, i64, i64, vp, vp, vp]
+    L.ocg_self_gravity_hermite.argtypes = [vp, vp, vp, vp, i64, vp, i32, dbl, dbl, dbl, i64, i64, vp, vp, vp, vp]
+    L.ocg_hermite_predict.argtypes = [vp, vp, vp, vp, vp, i64, dbl, dbl, vp, vp, vp]
+    L.ocg_hermite_correct.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, dbl, dbl, dbl, vp, vp]
+    L.ocg_debug_set_hermite_variant.argtypes = [ctypes.c_int]
+    L.ocg_debug_hermite_variant_name.restype = ctypes.c_char_p
+    L.ocg_debug_hermite_variant_name.argtypes = [ctypes.c_int]
+    L.ocg_debug_set_hermite_small_path.argtypes = [ctypes.c_int]
     L.ocg_bound_com.argtypes = [vp, vp, vp, vp, vp, i64, vp, i32, dbl, vp, vp, vp]
     L.ocg_eject_mask.argtypes = [vp, vp, i64, dbl, dbl, vp, vp, vp]
     L.ocg_compact_rows.argtypes = [vp, vp, i32, i64, vp, vp, i64, vp, vp]
@@ -287,6 +294,32 @@ class Context:
         self._ck(self.lib.ocg_self_gravity(self.h, _dptr(pos), _dptr(mass), n, _hptr(seg), n_seg, float(eps2), float(G),
                                            int(tgt_begin), int(tgt_end), _dptr(acc), _dptr(pot), self._stream()),
                  "ocg_self_gravity")
+
+    def self_gravity_hermite(self, pos, vel, mass, eps2, G, vel_to_len, acc, jerk, pot=None, seg_offsets=None,
+                             tgt_begin=0, tgt_end=None):
+        """K6: acceleration and jerk (and optionally the potential) of the cluster's self-gravity."""
+        n = pos.shape[1]
+        if seg_offsets is None:
+            seg, n_seg = None, 1
+        else:
+            seg = np.ascontiguousarray(seg_offsets, dtype=np.int64)
+            n_seg = len(seg) - 1
+        tgt_end = n if tgt_end is None else tgt_end
+        self._ck(self.lib.ocg_self_gravity_hermite(self.h, _dptr(pos), _dptr(vel), _dptr(mass), n, _hptr(seg), n_seg,
+                                                   float(eps2), float(G), float(vel_to_len), int(tgt_begin), int(tgt_end),
+                                                   _dptr(acc), _dptr(jerk), _dptr(pot), self._stream()),
+                 "ocg_self_gravity_hermite")
+
+    def hermite_predict(self, pos, vel, acc, jerk, dt, vel_to_len, pos_pred, vel_pred):
+        self._ck(self.lib.ocg_hermite_predict(self.h, _dptr(pos), _dptr(vel), _dptr(acc), _dptr(jerk), pos.shape[1], float(dt),
+                                              float(vel_to_len), _dptr(pos_pred), _dptr(vel_pred), self._stream()),
+                 "ocg_hermite_predict")
+
+    def hermite_correct(self, pos, vel, acc0, jerk0, pos_pred, vel_pred, acc1, jerk1, dt, vel_to_len, eta, dt_min=None):
+        self._ck(self.lib.ocg_hermite_correct(self.h, _dptr(pos), _dptr(vel), _dptr(acc0), _dptr(jerk0), _dptr(pos_pred),
+                                              _dptr(vel_pred), _dptr(acc1), _dptr(jerk1), pos.shape[1], float(dt),
+                                              float(vel_to_len), float(eta), _dptr(dt_min), self._stream()),
+                 "ocg_hermite_correct")
 
     def bound_com(self, pos, vel, mass, pot, pot_to_v2, out, seg_offsets=None, bound_mask=None):
         """out [n_seg, 8] fp64 device: bound-subset COM (3), bound mass, bound count, COM velocity (3)."""

@@ -18,6 +18,7 @@ SOURCES = [
     ("api", "api.cu", []),
     ("direct_sum", "direct_sum.cu", []),
     ("self_gravity", "self_gravity.cu", []),
+    ("hermite", "hermite.cu", []),
     ("grid_interp", "grid_interp.cu", []),
     ("cluster_ops", "cluster_ops.cu", []),
 ]

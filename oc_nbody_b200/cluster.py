@@ -3,7 +3,9 @@ oc_code.py:218-229, behind the same gravity-code duck type the driver uses (oc_n
 ``.particles``, ``.parameters.epsilon_squared``, ``.evolve_model(t)``, ``.stop()``.
 
 Algorithm (BASELINE.json north_star): Plummer-softened direct-sum self-gravity (K4) + kick-drift-kick
-leapfrog (K5) in place of ph4's 4th-order Hermite with block time steps.  State lives in HBM as FP64
+leapfrog (K5) in place of ph4's 4th-order Hermite with block time steps.  ``integrator="hermite"`` selects ph4's
+own scheme instead: acceleration + jerk direct sum (K6), 4th-order Hermite predictor /
+corrector with one shared step, Aarseth step criterion evaluated on the device.  State lives in HBM as FP64
 component-major arrays in the field code's unit system (kpc, km/s, Myr, Msun) so that the BRIDGE kick (K3)
 consumes the positions without conversion or host copies.
 
@@ -78,8 +80,13 @@ class cluster_code(object):
     oc_code.py:225; ``substeps`` leapfrog steps per evolve_model call (ph4 chooses its own block steps;
     here the BRIDGE timestep is subdivided evenly)."""
 
-    def __init__(self, mass, pos, vel, softening_pc=0.01, substeps=1, eject_cut=None, ctx=None):
+    def __init__(self, mass, pos, vel, softening_pc=0.01, substeps=1, eject_cut=None, ctx=None, integrator="leapfrog",
+                 eta=0.14):
         import torch
+        if integrator not in ("leapfrog", "hermite"):
+            raise ValueError("integrator must be 'leapfrog' or 'hermite', not %r" % (integrator,))
+        self.integrator = integrator
+        self.eta = float(eta)  # Aarseth accuracy parameter (ph4's timestep_parameter, default 0.14)
         self.ctx = ctx or _lib.default_context()
         self._dev = torch.device("cuda", self.ctx.device)
         self.parameters = _Parameters()
@@ -111,6 +118,16 @@ class cluster_code(object):
         self.pot = torch.empty(n, dtype=torch.float64, device=self._dev)
         self.key = np.arange(n) if key is None else np.asarray(key)
         self._acc_valid = False
+        self._alloc_hermite_()
+
+    def _alloc_hermite_(self):
+        import torch
+        if self.integrator != "hermite":
+            return
+        n = self.n
+        mk = lambda: torch.empty((3, n), dtype=torch.float64, device=self._dev)
+        self.jerk, self.acc1, self.jerk1, self.pos_p, self.vel_p = mk(), mk(), mk(), mk(), mk()
+        self.dt_min = torch.full((1,), float("inf"), dtype=torch.float64, device=self._dev)
 
     @property
     def particles(self):
@@ -141,6 +158,7 @@ class cluster_code(object):
         self.pot = torch.empty(nk, dtype=torch.float64, device=self._dev)
         self.key = self.key[np.setdiff1d(np.arange(len(self.key)), removed)]
         self._acc_valid = False
+        self._alloc_hermite_()
         return removed
 
     # ---- gravity ----
@@ -151,9 +169,35 @@ class cluster_code(object):
         self._acc_valid = True
         return self.acc
 
+    def _force_hermite_(self, pos, vel, acc, jerk):
+        """K6 at the state (pos, vel) -> acc (km/s/Myr), jerk (km/s/Myr^2)."""
+        self.ctx.self_gravity_hermite(pos, vel, self.mass, self.parameters._eps2_kpc2, self.G, KMS_TO_KPC_PER_MYR, acc, jerk)
+
+    def _evolve_hermite_(self, span):
+        """`substeps` shared 4th-order Hermite steps over `span` Myr (ph4's scheme without its block steps): force at the
+        current state (the BRIDGE kick has just changed the velocities, so the jerk is always re-evaluated), then
+        predict -> K6 at the predicted state -> correct.  Leaves the Aarseth step of the last step in self.dt_min."""
+        h = span / self.substeps
+        self._force_hermite_(self.pos, self.vel, self.acc, self.jerk)
+        for _ in range(self.substeps):
+            self.ctx.hermite_predict(self.pos, self.vel, self.acc, self.jerk, h, KMS_TO_KPC_PER_MYR, self.pos_p, self.vel_p)
+            self._force_hermite_(self.pos_p, self.vel_p, self.acc1, self.jerk1)
+            self.ctx.hermite_correct(self.pos, self.vel, self.acc, self.jerk, self.pos_p, self.vel_p, self.acc1, self.jerk1,
+                                     h, KMS_TO_KPC_PER_MYR, self.eta, self.dt_min)
+        self._acc_valid = True
+
+    def suggested_substeps(self, span):
+        """Sub-steps (a power of two) that bring span / substeps under the Aarseth step of the last Hermite step."""
+        dt = float(self.dt_min.item())
+        if not (dt > 0.0) or not np.isfinite(dt):
+            return self.substeps
+        return int(2 ** max(0, int(np.ceil(np.log2(span / dt)))))
+
     def _evolve_device_(self, span):
-        """The device work of evolve_model: `substeps` kick-drift-kick leapfrog steps over `span` Myr.  No host
+        """The device work of evolve_model: `substeps` kick-drift-kick leapfrog (or Hermite) steps over `span` Myr.  No host
         bookkeeping, no allocation, no synchronisation once the scratch buffers exist — capturable in a CUDA graph."""
+        if self.integrator == "hermite":
+            return self._evolve_hermite_(span)
         h = span / self.substeps
         for _ in range(self.substeps):
             self.ctx.kick(self.vel, self.acc, 0.5 * h)
@@ -168,7 +212,7 @@ class cluster_code(object):
         span = t_end - self.model_time
         if span <= 0.0:
             return
-        if not self._acc_valid:
+        if not self._acc_valid and self.integrator != "hermite":
             self.compute_self_gravity()
         self._evolve_device_(span)
         self.model_time = t_end
@@ -216,7 +260,8 @@ class sharded_cluster_code(cluster_code):
 
     mass / pos / vel passed in are the FULL arrays (identical on every rank); the constructor keeps the block."""
 
-    def __init__(self, mass, pos, vel, softening_pc=0.01, substeps=1, eject_cut=None, ctx=None, group=None):
+    def __init__(self, mass, pos, vel, softening_pc=0.01, substeps=1, eject_cut=None, ctx=None, group=None,
+                 integrator="leapfrog", eta=0.14):
         import torch.distributed as dist
         from .distributed import shard_range
         self.group = group
@@ -228,12 +273,30 @@ class sharded_cluster_code(cluster_code):
         pos = np.asarray(to_value(pos, units.kpc), np.float64)
         vel = np.asarray(to_value(vel, units.kms), np.float64)
         super().__init__(mass[self.a:self.b], pos[:, self.a:self.b], vel[:, self.a:self.b], softening_pc=softening_pc,
-                         substeps=substeps, eject_cut=eject_cut, ctx=ctx)
+                         substeps=substeps, eject_cut=eject_cut, ctx=ctx, integrator=integrator, eta=eta)
         import torch
         self.mass_all = torch.from_numpy(np.ascontiguousarray(mass)).to(self._dev)
         self._acc_all = torch.empty((3, self.n_total), dtype=torch.float64, device=self._dev)
         self._pot_all = torch.empty(self.n_total, dtype=torch.float64, device=self._dev)
+        if integrator == "hermite":
+            self._jerk_all = torch.empty((3, self.n_total), dtype=torch.float64, device=self._dev)
         self.key = np.arange(self.a, self.b)
+
+    def _force_hermite_(self, pos, vel, acc, jerk):
+        """K6 for the rank's target block: positions AND velocities are all-gathered (the jerk needs both)."""
+        from .distributed import allgather_particles
+        pos_all = allgather_particles(pos, self.n_total, self.group).contiguous()
+        vel_all = allgather_particles(vel, self.n_total, self.group).contiguous()
+        self.ctx.self_gravity_hermite(pos_all, vel_all, self.mass_all, self.parameters._eps2_kpc2, self.G, KMS_TO_KPC_PER_MYR,
+                                      self._acc_all, self._jerk_all, tgt_begin=self.a, tgt_end=self.b)
+        acc.copy_(self._acc_all[:, self.a:self.b])
+        jerk.copy_(self._jerk_all[:, self.a:self.b])
+
+    def _evolve_hermite_(self, span):
+        import torch.distributed as dist
+        super()._evolve_hermite_(span)
+        if dist.is_initialized() and self.world > 1:
+            dist.all_reduce(self.dt_min, op=dist.ReduceOp.MIN, group=self.group)
 
     def compute_self_gravity(self, want_pot=False):
         from .distributed import allgather_particles

@@ -1,0 +1,591 @@
+// K6: the Hermite force loop — acceleration AND jerk of the cluster's self-gravity — plus the predictor and
+// corrector of the 4th-order Hermite scheme (Makino & Aarseth 1992) with the Aarseth time-step criterion.
+//
+// This is the arithmetic of the AMUSE ph4 worker the reference instantiates at oc_code.py:218-229 (4th-order
+// Hermite, Plummer softening epsilon_squared, oc_code.py:225) — SURVEY §8f rank 5.  ph4's block (individual)
+// time steps are not reproduced: every star takes the same step (the BRIDGE step divided into `substeps`), the
+// Aarseth criterion is evaluated on the device and its minimum handed back so the host can choose `substeps`.
+//
+//   a_i = G sum_j m_j d / r^3                       d = x_j - x_i,  r^2 = |d|^2 + eps^2
+//   j_i = G sum_j m_j [ w / r^3 - 3 (d.w) d / r^5 ] w = v_j - v_i
+//
+// Same structure as K4 (direct_kernel.cuh): TMA-staged source tiles in a shared-memory ring, target-paired
+// packed FP32 (the two lanes of an FFMA2 are two targets, the source is the broadcast operand), FP32 partial
+// sums over one 512-source tile, FP64 per-target accumulators in shared memory, chunk partials summed in index
+// order by the finish kernel (run-to-run deterministic).  26 FMA-pipe operations + 1 MUFU per interaction.
+#include "direct_kernel.cuh"
+
+#include <math.h>
+
+#define HM_TS 512
+#define HM_NARR 7 /* x | y | z | m | vx | vy | vz */
+#define HM_TILE_FLOATS (HM_NARR * HM_TS)
+#define HM_TILE_BYTES (HM_TILE_FLOATS * 4)
+#define HM_NSTAGE 3
+
+struct HermiteParams {
+  const float* tiles;     // [tile][7][HM_TS]: scaled positions, mass, unscaled velocities
+  const float4* tgt_pos;  // [n] recentred (x, y, z, m), unscaled
+  const float4* tgt_vel;  // [n] recentred (vx, vy, vz, 0)
+  double* partial;        // [slot][NC][out_stride]
+  long long out_stride;
+  const OcgWorkItem* items;
+  int n_items;
+  float e2s;    // eps^2 in scaled units
+  float scale;  // power-of-two length scale
+};
+
+// FP64 particles -> source tiles and float4 targets; each segment recentred on its first particle (position AND
+// velocity) in FP64 before rounding to FP32.
+__global__ void pack_hermite_kernel(const double* __restrict__ pos, const double* __restrict__ vel,
+                                    const double* __restrict__ mass, long long n,
+                                    const long long* __restrict__ seg_off, const long long* __restrict__ seg_tile,
+                                    int n_seg, float scale, float* __restrict__ tiles, float4* __restrict__ tgt_pos,
+                                    float4* __restrict__ tgt_vel) {
+  const long long total_tiles = seg_tile[n_seg];
+  const long long slot = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (slot >= total_tiles * HM_TS) return;
+  const long long tile = slot / HM_TS;
+  const int j = (int)(slot - tile * HM_TS);
+  int lo = 0, hi = n_seg;
+  while (hi - lo > 1) {
+    int mid = (lo + hi) >> 1;
+    if (seg_tile[mid] <= tile) lo = mid;
+    else hi = mid;
+  }
+  const long long first = seg_off[lo];
+  const long long idx = first + (tile - seg_tile[lo]) * HM_TS + j;
+  float* T = tiles + tile * (long long)HM_TILE_FLOATS;
+  float v[HM_NARR] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (idx < seg_off[lo + 1]) {
+    const float x = (float)(pos[idx] - pos[first]), y = (float)(pos[n + idx] - pos[n + first]),
+                z = (float)(pos[2 * n + idx] - pos[2 * n + first]);
+    const float vx = (float)(vel[idx] - vel[first]), vy = (float)(vel[n + idx] - vel[n + first]),
+                vz = (float)(vel[2 * n + idx] - vel[2 * n + first]);
+    const float m = (float)mass[idx];
+    v[0] = x * scale, v[1] = y * scale, v[2] = z * scale, v[3] = m, v[4] = vx, v[5] = vy, v[6] = vz;
+    tgt_pos[idx] = make_float4(x, y, z, m);
+    tgt_vel[idx] = make_float4(vx, vy, vz, 0.f);
+  }
+#pragma unroll
+  for (int a = 0; a < HM_NARR; ++a) T[a * HM_TS + j] = v[a];
+}
+
+// One source tile against NP target pairs.  Per interaction (one lane of each packed instruction):
+//   d  = xs - xt, w = vs - vt                6 FADD
+//   r2 = d.d + e2                            3 FFMA
+//   rv = d.w                                 1 FMUL + 2 FFMA
+//   ri = rsqrt(r2)                           MUFU
+//   q  = ri*ri, mri = m*ri, mr3 = mri*q      3 FMUL      (phi += mri: +1 FADD)
+//   al = (rv*q)*(-3)                         2 FMUL
+//   t  = al*d + w                            3 FFMA
+//   j += mr3*t, a += mr3*d                   6 FFMA
+// = 26 FMA-pipe operations (41 flop counting an FMA as two).
+template <int NP, bool POT, bool GUARD, int UNR>
+__device__ __forceinline__ void hermite_tile(const float* __restrict__ stage, const u64 (&ntx)[NP], const u64 (&nty)[NP],
+                                             const u64 (&ntz)[NP], const u64 (&ntu)[NP], const u64 (&ntv)[NP],
+                                             const u64 (&ntw)[NP], const u64 eb, u64 (&ax)[NP], u64 (&ay)[NP],
+                                             u64 (&az)[NP], u64 (&jx)[NP], u64 (&jy)[NP], u64 (&jz)[NP], u64 (&ap)[NP]) {
+  const float4* sx = reinterpret_cast<const float4*>(stage);
+  const float4* sy = sx + HM_TS / 4;
+  const float4* sz = sy + HM_TS / 4;
+  const float4* sm = sz + HM_TS / 4;
+  const float4* su = sm + HM_TS / 4;
+  const float4* sv = su + HM_TS / 4;
+  const float4* sw = sv + HM_TS / 4;
+  const u64 c3 = f2_pack(-3.0f, -3.0f);
+#pragma unroll UNR
+  for (int j = 0; j < HM_TS / 4; ++j) {
+    const float4 X = sx[j], Y = sy[j], Z = sz[j], M = sm[j], U = su[j], V = sv[j], W = sw[j];
+    const float xs[4] = {X.x, X.y, X.z, X.w}, ys[4] = {Y.x, Y.y, Y.z, Y.w}, zs[4] = {Z.x, Z.y, Z.z, Z.w};
+    const float ms[4] = {M.x, M.y, M.z, M.w};
+    const float us[4] = {U.x, U.y, U.z, U.w}, vs[4] = {V.x, V.y, V.z, V.w}, ws[4] = {W.x, W.y, W.z, W.w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      // duplicated source scalars: ptxas folds them into broadcast (.F32) operands
+      const u64 xb = f2_pack(xs[q], xs[q]), yb = f2_pack(ys[q], ys[q]), zb = f2_pack(zs[q], zs[q]);
+      const u64 ub = f2_pack(us[q], us[q]), vb = f2_pack(vs[q], vs[q]), wb = f2_pack(ws[q], ws[q]);
+      const u64 mb = f2_pack(ms[q], ms[q]);
+#pragma unroll
+      for (int p = 0; p < NP; ++p) {
+        const u64 dx = f2_add(ntx[p], xb), dy = f2_add(nty[p], yb), dz = f2_add(ntz[p], zb);
+        const u64 du = f2_add(ntu[p], ub), dv = f2_add(ntv[p], vb), dw = f2_add(ntw[p], wb);
+        u64 r2 = f2_fma(dx, dx, eb);
+        r2 = f2_fma(dy, dy, r2);
+        r2 = f2_fma(dz, dz, r2);
+        u64 rv = f2_mul(dx, du);
+        rv = f2_fma(dy, dv, rv);
+        rv = f2_fma(dz, dw, rv);
+        float r2a, r2b;
+        f2_unpack(r2, r2a, r2b);
+        float ria = rsqrt_approx(r2a), rib = rsqrt_approx(r2b);
+        if (GUARD) {  // eps2 == 0: coincident pairs (the self pair among them) contribute nothing
+          ria = r2a > 0.f ? ria : 0.f;
+          rib = r2b > 0.f ? rib : 0.f;
+        }
+        const u64 ri = f2_pack(ria, rib);
+        const u64 qq = f2_mul(ri, ri);
+        const u64 mri = f2_mul(mb, ri);
+        const u64 mr3 = f2_mul(mri, qq);
+        if (POT) ap[p] = f2_add(ap[p], mri);
+        const u64 al = f2_mul(f2_mul(rv, qq), c3);
+        const u64 tx = f2_fma(al, dx, du), ty = f2_fma(al, dy, dv), tz = f2_fma(al, dz, dw);
+        jx[p] = f2_fma(mr3, tx, jx[p]);
+        jy[p] = f2_fma(mr3, ty, jy[p]);
+        jz[p] = f2_fma(mr3, tz, jz[p]);
+        ax[p] = f2_fma(mr3, dx, ax[p]);
+        ay[p] = f2_fma(mr3, dy, ay[p]);
+        az[p] = f2_fma(mr3, dz, az[p]);
+      }
+    }
+  }
+}
+
+//   NP : target pairs per thread (targets per thread = 2*NP); NW : warps per CTA; CTA tile = 64*NW*NP targets
+template <int NP, bool POT, bool GUARD, int NW, int UNR>
+__global__ void __launch_bounds__(32 * NW, 1) hermite_tp_kernel(const HermiteParams p) {
+  constexpr int NTHR = 32 * NW;
+  constexpr int NC = POT ? 7 : 6;
+  constexpr int T = 2 * NP;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float* stage_base = reinterpret_cast<float*>(smem_raw);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_raw + HM_NSTAGE * HM_TILE_BYTES);
+  uint64_t* empty_bar = full_bar + HM_NSTAGE;
+  double* sacc = reinterpret_cast<double*>(smem_raw + HM_NSTAGE * HM_TILE_BYTES + 128);  // [NC][T][NTHR]
+  const int tid = threadIdx.x;
+  const int lane = tid & 31;
+
+  if (tid == 0) {
+    for (int s = 0; s < HM_NSTAGE; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], NW);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  uint32_t it = 0;  // running tile counter: stage = it % NSTAGE, phase = (it / NSTAGE) & 1
+  auto issue_tile = [&](uint32_t n, const float* src) {
+    const uint32_t s = n % HM_NSTAGE, ph = (n / HM_NSTAGE) & 1u;
+    mbar_wait(&empty_bar[s], ph ^ 1u);
+    mbar_expect_tx(&full_bar[s], HM_TILE_BYTES);
+    tma_bulk_g2s(stage_base + s * HM_TILE_FLOATS, src, HM_TILE_BYTES, &full_bar[s]);
+  };
+
+  const float scale = p.scale;
+  const u64 eb = f2_pack(p.e2s, p.e2s);
+  for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+    const OcgWorkItem w = p.items[item];
+    const long long tgt_begin = w.tgt_begin, slot = w.out_slot;
+    const int tgt_count = w.tgt_count, tile_count = w.tile_count;
+    const float* src = p.tiles + w.tile_begin * (long long)HM_TILE_FLOATS;
+    if (tid == 0) {
+      const int pre = tile_count < HM_NSTAGE - 1 ? tile_count : HM_NSTAGE - 1;
+      for (int k = 0; k < pre; ++k) issue_tile(it + k, src + (long long)k * HM_TILE_FLOATS);
+    }
+
+    u64 ntx[NP], nty[NP], ntz[NP], ntu[NP], ntv[NP], ntw[NP];
+#pragma unroll
+    for (int pp = 0; pp < NP; ++pp) {
+      float c[2][6];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int local = (2 * pp + h) * NTHR + tid;
+        const long long gi = tgt_begin + (local < tgt_count ? local : tgt_count - 1);
+        const float4 P = __ldg(&p.tgt_pos[gi]);
+        const float4 V = __ldg(&p.tgt_vel[gi]);
+        c[h][0] = -P.x * scale, c[h][1] = -P.y * scale, c[h][2] = -P.z * scale;  // power of two: exact
+        c[h][3] = -V.x, c[h][4] = -V.y, c[h][5] = -V.z;
+      }
+      ntx[pp] = f2_pack(c[0][0], c[1][0]), nty[pp] = f2_pack(c[0][1], c[1][1]), ntz[pp] = f2_pack(c[0][2], c[1][2]);
+      ntu[pp] = f2_pack(c[0][3], c[1][3]), ntv[pp] = f2_pack(c[0][4], c[1][4]), ntw[pp] = f2_pack(c[0][5], c[1][5]);
+    }
+#pragma unroll
+    for (int i = 0; i < NC * T; ++i) sacc[i * NTHR + tid] = 0.0;
+
+    for (int k = 0; k < tile_count; ++k, ++it) {
+      if (tid == 0 && k + HM_NSTAGE - 1 < tile_count)
+        issue_tile(it + HM_NSTAGE - 1, src + (long long)(k + HM_NSTAGE - 1) * HM_TILE_FLOATS);
+      const uint32_t s = it % HM_NSTAGE, ph = (it / HM_NSTAGE) & 1u;
+      mbar_wait(&full_bar[s], ph);
+      u64 ax[NP], ay[NP], az[NP], jx[NP], jy[NP], jz[NP], ap[NP];
+#pragma unroll
+      for (int pp = 0; pp < NP; ++pp) ax[pp] = ay[pp] = az[pp] = jx[pp] = jy[pp] = jz[pp] = ap[pp] = 0ull;
+      hermite_tile<NP, POT, GUARD, UNR>(stage_base + s * HM_TILE_FLOATS, ntx, nty, ntz, ntu, ntv, ntw, eb, ax, ay, az,
+                                        jx, jy, jz, ap);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty_bar[s]);
+      // fold this tile's FP32 sums into the FP64 accumulators (lane lo -> target 2p, hi -> target 2p+1)
+#pragma unroll
+      for (int pp = 0; pp < NP; ++pp) {
+        float v[7][2];
+        f2_unpack(ax[pp], v[0][0], v[0][1]);
+        f2_unpack(ay[pp], v[1][0], v[1][1]);
+        f2_unpack(az[pp], v[2][0], v[2][1]);
+        f2_unpack(jx[pp], v[3][0], v[3][1]);
+        f2_unpack(jy[pp], v[4][0], v[4][1]);
+        f2_unpack(jz[pp], v[5][0], v[5][1]);
+        f2_unpack(ap[pp], v[6][0], v[6][1]);
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+          for (int c = 0; c < NC; ++c) sacc[(c * T + 2 * pp + h) * NTHR + tid] += (double)v[c][h];
+      }
+    }
+
+#pragma unroll
+    for (int t = 0; t < T; ++t) {
+      const int local = t * NTHR + tid;
+      if (local < tgt_count) {
+        const long long gi = tgt_begin + local;
+#pragma unroll
+        for (int c = 0; c < NC; ++c) p.partial[(slot * NC + c) * p.out_stride + gi] = sacc[(c * T + t) * NTHR + tid];
+      }
+    }
+  }
+}
+
+// acc = G s^2 sum, jerk = G s^3 vel_to_len sum (positions scaled by s, velocities not), pot = -G s sum with the
+// self term (m/eps, included by the kernel because targets == sources) removed with the kernel's own FP32 expression.
+__global__ void finish_hermite_kernel(const double* __restrict__ partial, long long stride, int n_slots, int nc, double G,
+                                      double vel_to_len, long long t0, long long t1, const float4* __restrict__ tgt_pos,
+                                      float e2s, float scale, double* __restrict__ acc, double* __restrict__ jerk,
+                                      double* __restrict__ pot) {
+  long long t = t0 + blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (t >= t1) return;
+  const double sc = (double)scale;
+  for (int c = 0; c < nc; ++c) {
+    double s = 0.0;
+    for (int k = 0; k < n_slots; ++k) s += partial[((long long)k * nc + c) * stride + t];
+    if (c < 3) acc[(long long)c * stride + t] = s * (G * sc * sc);
+    else if (c < 6) jerk[(long long)(c - 3) * stride + t] = s * (G * sc * sc * sc * vel_to_len);
+    else {
+      if (e2s > 0.f) s -= (double)(tgt_pos[t].w * rsqrt_approx(e2s));
+      pot[t] = -s * (G * sc);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------ small clusters ----
+// One launch for one cluster of <= 4096 stars (the reference's own run is N = 1 024, test_options:57): every CTA
+// stages all sources in shared memory, a warp owns one target, its 32 lanes split the sources, FP32 pair arithmetic
+// with two independent partial sums per lane, FP64 from the warp-shuffle reduction on.
+#define HM_SMALL_WARPS 8
+#define HM_SMALL_MAX_N 4096
+__global__ void __launch_bounds__(32 * HM_SMALL_WARPS) hermite_small_kernel(
+    const double* __restrict__ pos, const double* __restrict__ vel, const double* __restrict__ mass, long long n,
+    float e2s, float scale, double G, double vel_to_len, long long tgt_begin, long long tgt_end,
+    double* __restrict__ acc, double* __restrict__ jerk, double* __restrict__ pot) {
+  extern __shared__ float4 s_all[];
+  float4* s_pos = s_all;
+  float4* s_vel = s_all + n;
+  for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+    s_pos[i] = make_float4((float)(pos[i] - pos[0]) * scale, (float)(pos[n + i] - pos[n]) * scale,
+                           (float)(pos[2 * n + i] - pos[2 * n]) * scale, (float)mass[i]);
+    s_vel[i] = make_float4((float)(vel[i] - vel[0]), (float)(vel[n + i] - vel[n]), (float)(vel[2 * n + i] - vel[2 * n]), 0.f);
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long t = tgt_begin + (long long)blockIdx.x * HM_SMALL_WARPS + warp;
+  if (t >= tgt_end) return;
+  const float4 P = s_pos[t], V = s_vel[t];
+  float a[2][7];
+#pragma unroll
+  for (int u = 0; u < 2; ++u)
+#pragma unroll
+    for (int c = 0; c < 7; ++c) a[u][c] = 0.f;
+  for (long long j0 = lane; j0 < n; j0 += 64) {
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const long long j = j0 + 32 * u;
+      if (j < n) {
+        const float4 S = s_pos[j], W = s_vel[j];
+        const float dx = S.x - P.x, dy = S.y - P.y, dz = S.z - P.z;
+        const float du = W.x - V.x, dv = W.y - V.y, dw = W.z - V.z;
+        const float r2 = fmaf(dz, dz, fmaf(dy, dy, fmaf(dx, dx, e2s)));
+        const float rv = fmaf(dz, dw, fmaf(dy, dv, dx * du));
+        float ri = rsqrt_approx(r2);
+        if (!(r2 > 0.f)) ri = 0.f;
+        const float qq = ri * ri, mri = S.w * ri, mr3 = mri * qq;
+        const float al = (rv * qq) * -3.0f;
+        a[u][0] = fmaf(mr3, dx, a[u][0]), a[u][1] = fmaf(mr3, dy, a[u][1]), a[u][2] = fmaf(mr3, dz, a[u][2]);
+        a[u][3] = fmaf(mr3, fmaf(al, dx, du), a[u][3]);
+        a[u][4] = fmaf(mr3, fmaf(al, dy, dv), a[u][4]);
+        a[u][5] = fmaf(mr3, fmaf(al, dz, dw), a[u][5]);
+        if (j != t) a[u][6] += mri;
+      }
+    }
+  }
+  double v[7];
+#pragma unroll
+  for (int c = 0; c < 7; ++c) {
+    v[c] = (double)a[0][c] + (double)a[1][c];
+    for (int o = 16; o > 0; o >>= 1) v[c] += __shfl_xor_sync(0xffffffffu, v[c], o);
+  }
+  if (lane == 0) {
+    const double sc = (double)scale;
+    const double ka = G * sc * sc, kj = G * sc * sc * sc * vel_to_len;
+    acc[t] = ka * v[0], acc[n + t] = ka * v[1], acc[2 * n + t] = ka * v[2];
+    jerk[t] = kj * v[3], jerk[n + t] = kj * v[4], jerk[2 * n + t] = kj * v[5];
+    if (pot) pot[t] = -(G * sc) * v[6];
+  }
+}
+
+// ------------------------------------------------------------------------------ launcher ----
+typedef void (*hermite_fn)(const HermiteParams);
+struct HermiteVariant {
+  const char* name;
+  int np, nw;
+  hermite_fn fn[2][2];  // [pot][guard]
+};
+#define HM_V(NP, NW, UNR)                                                                                   \
+  {                                                                                                         \
+    {hermite_tp_kernel<NP, false, false, NW, UNR>, hermite_tp_kernel<NP, false, true, NW, UNR>}, {          \
+      hermite_tp_kernel<NP, true, false, NW, UNR>, hermite_tp_kernel<NP, true, true, NW, UNR>               \
+    }                                                                                                       \
+  }
+static const HermiteVariant g_hm_variants[] = {
+    {"np4 8w (2048-target tiles)", 4, 8, HM_V(4, 8, 1)},
+    {"np3 8w (1536-target tiles)", 3, 8, HM_V(3, 8, 1)},
+    {"np2 8w (1024-target tiles)", 2, 8, HM_V(2, 8, 1)},
+    {"np2 12w (1536-target tiles)", 2, 12, HM_V(2, 12, 1)},
+    {"np3 12w (2304-target tiles)", 3, 12, HM_V(3, 12, 1)},
+    {"np4 8w unroll 2", 4, 8, HM_V(4, 8, 2)},
+};
+#define HM_N_VARIANTS ((int)(sizeof(g_hm_variants) / sizeof(g_hm_variants[0])))
+static int g_hm_force_variant = -1;
+static int g_hm_small_path = 1;
+extern "C" int ocg_debug_set_hermite_variant(int v) {
+  g_hm_force_variant = v < HM_N_VARIANTS ? v : -1;
+  return HM_N_VARIANTS;
+}
+extern "C" const char* ocg_debug_hermite_variant_name(int v) {
+  return v >= 0 && v < HM_N_VARIANTS ? g_hm_variants[v].name : "";
+}
+extern "C" int ocg_debug_set_hermite_small_path(int on) {
+  g_hm_small_path = on;
+  return 0;
+}
+
+static float hermite_scale(float e2f) {
+  // power-of-two length scale that puts eps at ~2^-8 (as K4 does): 1/r^3 <= 2^24 for softened pairs, and
+  // separations up to ~1e8 eps stay far from FP32 range limits; eps2 == 0 keeps scale 1 (guarded form)
+  if (!(e2f > 0.f)) return 1.0f;
+  int e;
+  frexpf(sqrtf(e2f), &e);
+  float scale = ldexpf(1.0f, -8 - e);
+  if (!(scale > 0.f) || !isfinite(scale) || !(e2f * scale * scale > 0.f)) scale = 1.0f;
+  return scale;
+}
+
+extern "C" int ocg_self_gravity_hermite(ocg_ctx* ctx, const double* pos_dev, const double* vel_dev, const double* mass_dev,
+                                        int64_t n, const int64_t* seg_offsets_host, int32_t n_seg, double eps2, double G,
+                                        double vel_to_len, int64_t tgt_begin, int64_t tgt_end, double* acc_dev,
+                                        double* jerk_dev, double* pot_dev, void* stream) {
+  if (!ctx) return OCG_ERR_INVALID;
+  if (n < 0 || n_seg < 1) return ocg_fail(ctx, OCG_ERR_INVALID, "ocg_self_gravity_hermite: n < 0 or n_seg < 1");
+  if (n == 0) return OCG_OK;
+  if (!pos_dev || !vel_dev || !mass_dev || !acc_dev || !jerk_dev)
+    return ocg_fail(ctx, OCG_ERR_INVALID, "ocg_self_gravity_hermite: NULL argument");
+  if (!(eps2 >= 0.0)) return ocg_fail(ctx, OCG_ERR_INVALID, "ocg_self_gravity_hermite: eps2 = %g must be >= 0", eps2);
+  if (tgt_begin < 0 || tgt_end > n || tgt_begin > tgt_end)
+    return ocg_fail(ctx, OCG_ERR_INVALID, "ocg_self_gravity_hermite: target range [%lld,%lld) outside [0,%lld)",
+                    (long long)tgt_begin, (long long)tgt_end, (long long)n);
+  int64_t one_seg[2] = {0, n};
+  if (!seg_offsets_host) {
+    if (n_seg != 1)
+      return ocg_fail(ctx, OCG_ERR_INVALID, "ocg_self_gravity_hermite: seg_offsets is NULL but n_seg = %d", n_seg);
+    seg_offsets_host = one_seg;
+  }
+  if (seg_offsets_host[0] != 0 || seg_offsets_host[n_seg] != n)
+    return ocg_fail(ctx, OCG_ERR_INVALID, "ocg_self_gravity_hermite: seg_offsets must run from 0 to n");
+  for (int s = 0; s < n_seg; ++s)
+    if (seg_offsets_host[s + 1] < seg_offsets_host[s])
+      return ocg_fail(ctx, OCG_ERR_INVALID, "ocg_self_gravity_hermite: seg_offsets not monotone at %d", s);
+  if (tgt_begin == tgt_end) return OCG_OK;
+
+  OcgDeviceGuard g(ctx->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool want_pot = pot_dev != nullptr;
+  const int NC = want_pot ? 7 : 6;
+  const float e2f = (float)eps2;
+  const bool guard = !(e2f > 0.f);
+  const float scale = hermite_scale(e2f);
+  const float e2s = guard ? 0.f : e2f * scale * scale;
+
+  if (g_hm_small_path && n_seg == 1 && n <= HM_SMALL_MAX_N) {
+    const size_t smem = 2 * sizeof(float4) * (size_t)n;
+    OCG_CUDA(ctx, cudaFuncSetAttribute((const void*)hermite_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)(2 * sizeof(float4) * HM_SMALL_MAX_N)));
+    const long long nb = (tgt_end - tgt_begin + HM_SMALL_WARPS - 1) / HM_SMALL_WARPS;
+    hermite_small_kernel<<<(int)nb, 32 * HM_SMALL_WARPS, smem, st>>>(pos_dev, vel_dev, mass_dev, n, e2s, scale, G, vel_to_len,
+                                                                    tgt_begin, tgt_end, acc_dev, jerk_dev, pot_dev);
+    OCG_CHECK_LAUNCH(ctx, "hermite_small_kernel");
+    ctx->ev_valid = 0;
+    return OCG_OK;
+  }
+
+  // tile shape by the typical cluster size: the largest CTA tile that still gives every SM work
+  const int64_t seg_typ = (n + n_seg - 1) / n_seg;
+  int variant = g_hm_force_variant;
+  if (variant < 0) {
+    // among the 2048/1536/1024-target tiles, the one that pads the typical cluster least (ties: the larger)
+    double best = 1e300;
+    for (int c = 0; c < 3; ++c) {
+      const long long ct = 64ll * g_hm_variants[c].nw * g_hm_variants[c].np;
+      const double waste = (double)(((seg_typ + ct - 1) / ct) * ct) / (double)seg_typ;
+      if (waste < best - 1e-9) best = waste, variant = c;
+    }
+  }
+  const HermiteVariant& v = g_hm_variants[variant];
+  const int NTHR = 32 * v.nw, CT = 2 * v.np * NTHR;
+
+  OcgClusterPlan plan;
+  int rc;
+  if ((rc = ocg_plan_cluster_items(ctx, n, seg_offsets_host, n_seg, tgt_begin, tgt_end, CT, HM_TS, ctx->sm_count, st, &plan)))
+    return rc;
+  float* tiles;
+  float4* tgt;
+  double* partial;
+  rc = ocg_scratch(ctx, OCG_SCR_TILES, (size_t)plan.total_tiles * HM_TILE_BYTES, (void**)&tiles);
+  if (!rc) rc = ocg_scratch(ctx, OCG_SCR_TGT, 2 * sizeof(float4) * (size_t)n, (void**)&tgt);
+  if (!rc) rc = ocg_scratch(ctx, OCG_SCR_PARTIAL, sizeof(double) * (size_t)plan.n_chunks * NC * (size_t)n, (void**)&partial);
+  if (rc) return rc;
+  {
+    const long long nslots = plan.total_tiles * HM_TS;
+    pack_hermite_kernel<<<(int)((nslots + 255) / 256), 256, 0, st>>>(pos_dev, vel_dev, mass_dev, n, plan.d_seg_off,
+                                                                    plan.d_seg_tile, n_seg, scale, tiles, tgt, tgt + n);
+    OCG_CHECK_LAUNCH(ctx, "pack_hermite_kernel");
+  }
+  HermiteParams p;
+  p.tiles = tiles, p.tgt_pos = tgt, p.tgt_vel = tgt + n, p.partial = partial, p.out_stride = n;
+  p.items = plan.d_items, p.n_items = (int)plan.n_items, p.e2s = e2s, p.scale = scale;
+  hermite_fn fn = v.fn[want_pot][guard];
+  const size_t smem = HM_NSTAGE * HM_TILE_BYTES + 128 + (size_t)NC * 2 * v.np * NTHR * sizeof(double);
+  OCG_CUDA(ctx, cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int grid = ctx->sm_count < p.n_items ? ctx->sm_count : p.n_items;
+  if (grid < 1) grid = 1;
+  if (ctx->timing) OCG_CUDA(ctx, cudaEventRecord(ctx->ev0, st));
+  fn<<<grid, NTHR, smem, st>>>(p);
+  OCG_CHECK_LAUNCH(ctx, "hermite_tp_kernel");
+  if (ctx->timing) {
+    OCG_CUDA(ctx, cudaEventRecord(ctx->ev1, st));
+    ctx->ev_valid = 1;
+  }
+  const int64_t n_shard = tgt_end - tgt_begin;
+  finish_hermite_kernel<<<(int)((n_shard + 255) / 256), 256, 0, st>>>(partial, n, (int)plan.n_chunks, NC, G, vel_to_len,
+                                                                     tgt_begin, tgt_end, tgt, e2s, scale, acc_dev, jerk_dev,
+                                                                     pot_dev);
+  OCG_CHECK_LAUNCH(ctx, "finish_hermite_kernel");
+  return OCG_OK;
+}
+
+// ------------------------------------------------------------------ predictor / corrector ----
+// FP64, every multiply and add rounded separately in a fixed order, so that the numpy restatement in the oracle
+// reproduces the bits (as K5 does).
+//   xp = x + ((v*dt + a*(dt^2/2)) + j*(dt^3/6)) * vel_to_len        vp = v + (a*dt + j*(dt^2/2))
+__global__ void hermite_predict_kernel(const double* __restrict__ pos, const double* __restrict__ vel,
+                                       const double* __restrict__ acc, const double* __restrict__ jerk, long long n3,
+                                       double c1, double c2, double c3, double vel_to_len, double* __restrict__ pos_p,
+                                       double* __restrict__ vel_p) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= n3) return;
+  const double v = vel[i], a = acc[i], j = jerk[i];
+  const double dx = __dadd_rn(__dadd_rn(__dmul_rn(v, c1), __dmul_rn(a, c2)), __dmul_rn(j, c3));
+  pos_p[i] = __dadd_rn(pos[i], __dmul_rn(dx, vel_to_len));
+  vel_p[i] = __dadd_rn(v, __dadd_rn(__dmul_rn(a, c1), __dmul_rn(j, c2)));
+}
+
+struct HermiteCoef {
+  double k6, k4, k2, i2;     // a2 = ((a0-a1)*(-6) - (j0*4 + j1*2)*dt) * (1/dt^2)
+  double k12, k6dt, i3;      // a3 = ((a0-a1)*12 + (j0+j1)*(6 dt)) * (1/dt^3)
+  double dt, d3, d4, d5;     // dt, dt^3/6, dt^4/24, dt^5/120
+  double vel_to_len, eta;
+};
+
+// Corrector + Aarseth step.  One thread per star (the step criterion needs vector norms):
+//   v1 = vp + a2*(dt^3/6) + a3*(dt^4/24)          x1 = xp + (a2*(dt^4/24) + a3*(dt^5/120)) * vel_to_len
+//   dt_i = sqrt(eta (|a1||a2'| + |j1|^2) / (|j1||a3| + |a2'|^2)),  a2' = a2 + dt a3
+// and acc0 <- acc1, jerk0 <- jerk1 (the end-of-step force is the start-of-step force of the next step).
+__global__ void hermite_correct_kernel(double* __restrict__ pos, double* __restrict__ vel, double* __restrict__ acc0,
+                                       double* __restrict__ jerk0, const double* __restrict__ pos_p,
+                                       const double* __restrict__ vel_p, const double* __restrict__ acc1,
+                                       const double* __restrict__ jerk1, long long n, HermiteCoef k,
+                                       unsigned long long* __restrict__ dt_min_bits) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  double dti = __longlong_as_double(0x7ff0000000000000ll);
+  if (i < n) {
+    double s_a = 0.0, s_j = 0.0, s_2 = 0.0, s_3 = 0.0;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const long long q = c * n + i;
+      const double a0 = acc0[q], j0 = jerk0[q], a1 = acc1[q], j1 = jerk1[q];
+      const double da = __dadd_rn(a0, -a1);
+      const double a2 = __dmul_rn(__dadd_rn(__dmul_rn(da, k.k6), -__dmul_rn(__dadd_rn(__dmul_rn(j0, k.k4), __dmul_rn(j1, k.k2)), k.dt)), k.i2);
+      const double a3 = __dmul_rn(__dadd_rn(__dmul_rn(da, k.k12), __dmul_rn(__dadd_rn(j0, j1), k.k6dt)), k.i3);
+      vel[q] = __dadd_rn(__dadd_rn(vel_p[q], __dmul_rn(a2, k.d3)), __dmul_rn(a3, k.d4));
+      pos[q] = __dadd_rn(pos_p[q], __dmul_rn(__dadd_rn(__dmul_rn(a2, k.d4), __dmul_rn(a3, k.d5)), k.vel_to_len));
+      acc0[q] = a1, jerk0[q] = j1;
+      const double a2e = a2 + k.dt * a3;
+      s_a += a1 * a1, s_j += j1 * j1, s_2 += a2e * a2e, s_3 += a3 * a3;
+    }
+    const double num = sqrt(s_a * s_2) + s_j, den = sqrt(s_j * s_3) + s_2;
+    if (den > 0.0 && num > 0.0) dti = sqrt(k.eta * num / den);
+  }
+  if (dt_min_bits) {
+    // positive doubles order like their bit patterns
+    unsigned long long b = (unsigned long long)__double_as_longlong(dti);
+    for (int o = 16; o > 0; o >>= 1) {
+      const unsigned long long other = __shfl_xor_sync(0xffffffffu, b, o);
+      b = other < b ? other : b;
+    }
+    if ((threadIdx.x & 31) == 0) atomicMin(dt_min_bits, b);
+  }
+}
+
+__global__ void set_u64_kernel(unsigned long long* p, unsigned long long v) { *p = v; }
+
+extern "C" int ocg_hermite_predict(ocg_ctx* ctx, const double* pos_dev, const double* vel_dev, const double* acc_dev,
+                                   const double* jerk_dev, int64_t n, double dt, double vel_to_len, double* pos_pred_dev,
+                                   double* vel_pred_dev, void* stream) {
+  if (!ctx) return OCG_ERR_INVALID;
+  if (n < 0 || (n > 0 && (!pos_dev || !vel_dev || !acc_dev || !jerk_dev || !pos_pred_dev || !vel_pred_dev)))
+    return ocg_fail(ctx, OCG_ERR_INVALID, "ocg_hermite_predict: bad arguments");
+  if (n == 0) return OCG_OK;
+  OcgDeviceGuard g(ctx->device);
+  const double c2 = dt * dt * 0.5, c3 = dt * dt * dt / 6.0;
+  hermite_predict_kernel<<<(int)((3 * n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(pos_dev, vel_dev, acc_dev, jerk_dev, 3 * n,
+                                                                                      dt, c2, c3, vel_to_len, pos_pred_dev,
+                                                                                      vel_pred_dev);
+  OCG_CHECK_LAUNCH(ctx, "hermite_predict_kernel");
+  return OCG_OK;
+}
+
+extern "C" int ocg_hermite_correct(ocg_ctx* ctx, double* pos_dev, double* vel_dev, double* acc0_dev, double* jerk0_dev,
+                                   const double* pos_pred_dev, const double* vel_pred_dev, const double* acc1_dev,
+                                   const double* jerk1_dev, int64_t n, double dt, double vel_to_len, double eta,
+                                   double* dt_min_dev, void* stream) {
+  if (!ctx) return OCG_ERR_INVALID;
+  if (n < 0 || (n > 0 && (!pos_dev || !vel_dev || !acc0_dev || !jerk0_dev || !pos_pred_dev || !vel_pred_dev || !acc1_dev ||
+                          !jerk1_dev)))
+    return ocg_fail(ctx, OCG_ERR_INVALID, "ocg_hermite_correct: bad arguments");
+  if (!(dt != 0.0)) return ocg_fail(ctx, OCG_ERR_INVALID, "ocg_hermite_correct: dt must be non-zero");
+  if (n == 0) return OCG_OK;
+  OcgDeviceGuard g(ctx->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  HermiteCoef k;
+  const double dt2 = dt * dt, dt3 = dt * dt * dt;
+  k.k6 = -6.0, k.k4 = 4.0, k.k2 = 2.0, k.i2 = 1.0 / dt2;
+  k.k12 = 12.0, k.k6dt = 6.0 * dt, k.i3 = 1.0 / dt3;
+  k.dt = dt, k.d3 = dt3 / 6.0, k.d4 = dt2 * dt2 / 24.0, k.d5 = dt2 * dt3 / 120.0;
+  k.vel_to_len = vel_to_len, k.eta = eta;
+  if (dt_min_dev) {
+    set_u64_kernel<<<1, 1, 0, st>>>((unsigned long long*)dt_min_dev, 0x7ff0000000000000ull);
+    OCG_CHECK_LAUNCH(ctx, "set_u64_kernel");
+  }
+  hermite_correct_kernel<<<(int)((n + 255) / 256), 256, 0, st>>>(pos_dev, vel_dev, acc0_dev, jerk0_dev, pos_pred_dev,
+                                                                vel_pred_dev, acc1_dev, jerk1_dev, n, k,
+                                                                (unsigned long long*)dt_min_dev);
+  OCG_CHECK_LAUNCH(ctx, "hermite_correct_kernel");
+  return OCG_OK;
+}

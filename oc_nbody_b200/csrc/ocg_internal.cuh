@@ -105,6 +105,18 @@ struct DirectParams {
   float scale_val;           // host-chosen scale when scale_ptr is NULL (K4)
 };
 
+// ---- work plan of the cluster kernels (self_gravity.cu; shared by K4 and the Hermite force loop) ----
+struct OcgClusterPlan {
+  long long total_tiles;  // source tiles over all segments
+  long long n_chunks;     // source chunks per target tile = partial-sum slots
+  long long n_items;
+  const OcgWorkItem* d_items;   // device
+  const long long* d_seg_tile;  // device [n_seg+1]: first source tile of each segment
+  const long long* d_seg_off;   // device [n_seg+1]: first particle of each segment
+};
+int ocg_plan_cluster_items(ocg_ctx* ctx, int64_t n, const int64_t* seg_offsets_host, int32_t n_seg, int64_t tgt_begin,
+                           int64_t tgt_end, int ct, int ts, long long slots, cudaStream_t st, OcgClusterPlan* out);
+
 // ---- entry points implemented in other translation units ------------------------------------
 int ocg_pick_variant(ocg_ctx* ctx, int64_t n_tgt, int64_t seg_len, bool guard, bool allow_mf = false,
                      int64_t src_tiles = 0, bool fine_tiles = false);

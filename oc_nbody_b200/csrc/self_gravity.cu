@@ -130,6 +130,115 @@ static unsigned long long fnv1a(const void* data, size_t bytes, unsigned long lo
   return h;
 }
 
+// Host-side plan shared by K4 and the Hermite force loop (hermite.cu): source-tile offsets per segment, the
+// number of source chunks, and the (target tile x source chunk) item list, uploaded to the device (skipped when
+// the same plan is already there).  `ct` targets per CTA tile, `ts` sources per source tile, `slots` resident CTAs.
+int ocg_plan_cluster_items(ocg_ctx* ctx, int64_t n, const int64_t* seg_offsets_host, int32_t n_seg, int64_t tgt_begin,
+                           int64_t tgt_end, int ct, int ts, long long slots, cudaStream_t st, OcgClusterPlan* out) {
+  const int CT = ct;
+  long long* seg_tile = (long long*)malloc(sizeof(long long) * (2 * (size_t)n_seg + 2));
+  if (!seg_tile) return ocg_fail(ctx, OCG_ERR_NOMEM, "malloc failed");
+  long long* seg_off_ll = seg_tile + n_seg + 1;
+  long long total_tiles = 0, n_tt_total = 0, max_tiles = 1;
+  for (int s = 0; s <= n_seg; ++s) seg_off_ll[s] = seg_offsets_host[s];
+  for (int s = 0; s < n_seg; ++s) {
+    seg_tile[s] = total_tiles;
+    long long len = seg_off_ll[s + 1] - seg_off_ll[s];
+    long long nt = (len + ts - 1) / ts;
+    total_tiles += nt;
+    if (nt > max_tiles) max_tiles = nt;
+    long long a = seg_off_ll[s] > tgt_begin ? seg_off_ll[s] : tgt_begin;
+    long long b = seg_off_ll[s + 1] < tgt_end ? seg_off_ll[s + 1] : tgt_end;
+    if (b > a) n_tt_total += (b - a + CT - 1) / CT;
+  }
+  seg_tile[n_seg] = total_tiles;
+  // Source chunking: an item streams `tpc` tiles of its segment; items are strided statically over the resident
+  // CTAs, so the makespan is rounds * tpc tile-times (+ ~1/16 tile of start-up per item).  Pick the tiles-per-chunk
+  // that minimises it for the largest segment (every chunk non-empty there), keeping <= 256 partial-sum slots.
+  long long n_chunks = 1;
+  if (n_tt_total > 0) {
+    double best = 1e300;
+    for (long long tpc = 1; tpc <= max_tiles; ++tpc) {
+      const long long ch = (max_tiles + tpc - 1) / tpc;
+      if (ch > 256) continue;
+      const long long rounds = (n_tt_total * ch + slots - 1) / slots;
+      const double cost = (double)rounds * ((double)tpc + 0.0625);
+      if (cost < best) best = cost, n_chunks = ch;
+    }
+  }
+  const long long n_items = n_tt_total * n_chunks;
+  if (n_items > 0x7fffffffll) {
+    free(seg_tile);
+    return ocg_fail(ctx, OCG_ERR_INVALID, "too many work items");
+  }
+  if ((size_t)n_items > ctx->items_host_cap) {
+    free(ctx->items_host);
+    ctx->items_host = (OcgWorkItem*)malloc(sizeof(OcgWorkItem) * (size_t)n_items);
+    ctx->items_host_cap = ctx->items_host ? (size_t)n_items : 0;
+    ctx->items_uploaded = 0;
+    if (!ctx->items_host) {
+      free(seg_tile);
+      return ocg_fail(ctx, OCG_ERR_NOMEM, "malloc of %lld work items failed", n_items);
+    }
+  }
+  // chunk-major order: CTAs resident together stream the same source tiles (L2 reuse)
+  long long w = 0;
+  for (long long c = 0; c < n_chunks; ++c) {
+    for (int s = 0; s < n_seg; ++s) {
+      long long a = seg_off_ll[s] > tgt_begin ? seg_off_ll[s] : tgt_begin;
+      long long b = seg_off_ll[s + 1] < tgt_end ? seg_off_ll[s + 1] : tgt_end;
+      if (b <= a) continue;
+      long long nt = seg_tile[s + 1] - seg_tile[s];
+      long long tpc = (nt + n_chunks - 1) / n_chunks;
+      long long tb = c * tpc, te = tb + tpc < nt ? tb + tpc : nt;
+      for (long long t0 = a; t0 < b; t0 += CT) {
+        OcgWorkItem& it = ctx->items_host[w++];
+        it.tgt_begin = t0;
+        it.tgt_count = (int)(b - t0 < CT ? b - t0 : CT);
+        it.tile_begin = seg_tile[s] + (tb < nt ? tb : nt);
+        it.tile_count = (int)(te > tb ? te - tb : 0);
+        it.out_slot = c;
+      }
+    }
+  }
+  unsigned long long h = fnv1a(ctx->items_host, sizeof(OcgWorkItem) * (size_t)n_items, 1469598103934665603ull);
+  h = fnv1a(seg_tile, sizeof(long long) * (2 * (size_t)n_seg + 2), h);
+
+  int rc = 0;
+  OcgWorkItem* d_items;
+  long long* d_seg;
+  const size_t seg_bytes = sizeof(long long) * (2 * (size_t)n_seg + 2);
+  const size_t items_bytes = sizeof(OcgWorkItem) * (size_t)n_items;
+  void* items_raw = nullptr;
+  const size_t before = ctx->scratch_bytes[OCG_SCR_ITEMS];
+  if (!rc) rc = ocg_scratch(ctx, OCG_SCR_ITEMS, items_bytes + seg_bytes + 64, &items_raw);
+  if (rc) {
+    free(seg_tile);
+    return rc;
+  }
+  d_items = (OcgWorkItem*)items_raw;
+  d_seg = (long long*)((char*)items_raw + ((items_bytes + 63) / 64) * 64);
+  const bool reuse = before == ctx->scratch_bytes[OCG_SCR_ITEMS] && ctx->items_uploaded == (size_t)n_items &&
+                     ctx->items_hash == h;
+  if (!reuse) {
+    // synchronous small copies: the plan changes only when the segment layout or shard changes
+    cudaError_t e = cudaMemcpyAsync(d_items, ctx->items_host, items_bytes, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_seg, seg_tile, seg_bytes, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);  // seg_tile is freed below
+    if (e != cudaSuccess) {
+      free(seg_tile);
+      return ocg_fail(ctx, OCG_ERR_CUDA, "upload of the work plan failed: %s", cudaGetErrorString(e));
+    }
+    ctx->items_uploaded = (size_t)n_items;
+    ctx->items_hash = h;
+  }
+  free(seg_tile);
+  out->total_tiles = total_tiles, out->n_chunks = n_chunks, out->n_items = n_items;
+  out->d_items = d_items, out->d_seg_tile = d_seg, out->d_seg_off = d_seg + n_seg + 1;
+  return OCG_OK;
+}
+
+
 static int g_small_path = 1;  // 0: always take the streaming kernel (tests compare the two)
 extern "C" int ocg_debug_set_small_cluster_path(int on) {
   g_small_path = on;
@@ -197,113 +306,22 @@ extern "C" int ocg_self_gravity(ocg_ctx* ctx, const double* pos_dev, const doubl
   const int tpt = ocg_variant_tpt(variant);
   const int CT = ocg_variant_threads(variant) * tpt;
 
-  // ---- host-side plan: tile offsets per segment, chunk count, item list ----
-  long long* seg_tile = (long long*)malloc(sizeof(long long) * (2 * (size_t)n_seg + 2));
-  if (!seg_tile) return ocg_fail(ctx, OCG_ERR_NOMEM, "malloc failed");
-  long long* seg_off_ll = seg_tile + n_seg + 1;
-  long long total_tiles = 0, n_tt_total = 0, max_tiles = 1;
-  for (int s = 0; s <= n_seg; ++s) seg_off_ll[s] = seg_offsets_host[s];
-  for (int s = 0; s < n_seg; ++s) {
-    seg_tile[s] = total_tiles;
-    long long len = seg_off_ll[s + 1] - seg_off_ll[s];
-    long long nt = (len + OCG_TS - 1) / OCG_TS;
-    total_tiles += nt;
-    if (nt > max_tiles) max_tiles = nt;
-    long long a = seg_off_ll[s] > tgt_begin ? seg_off_ll[s] : tgt_begin;
-    long long b = seg_off_ll[s + 1] < tgt_end ? seg_off_ll[s + 1] : tgt_end;
-    if (b > a) n_tt_total += (b - a + CT - 1) / CT;
-  }
-  seg_tile[n_seg] = total_tiles;
-  const long long slots = ocg_variant_slots(ctx, variant);
-  // Source chunking: an item streams `tpc` tiles of its segment; items are strided statically over the resident
-  // CTAs, so the makespan is rounds * tpc tile-times (+ ~1/16 tile of start-up per item).  Pick the tiles-per-chunk
-  // that minimises it for the largest segment (every chunk non-empty there), keeping <= 256 partial-sum slots.
-  long long n_chunks = 1;
-  if (n_tt_total > 0) {
-    double best = 1e300;
-    for (long long tpc = 1; tpc <= max_tiles; ++tpc) {
-      const long long ch = (max_tiles + tpc - 1) / tpc;
-      if (ch > 256) continue;
-      const long long rounds = (n_tt_total * ch + slots - 1) / slots;
-      const double cost = (double)rounds * ((double)tpc + 0.0625);
-      if (cost < best) best = cost, n_chunks = ch;
-    }
-  }
-  const long long n_items = n_tt_total * n_chunks;
-  if (n_items > 0x7fffffffll) {
-    free(seg_tile);
-    return ocg_fail(ctx, OCG_ERR_INVALID, "ocg_self_gravity: too many work items");
-  }
-  if ((size_t)n_items > ctx->items_host_cap) {
-    free(ctx->items_host);
-    ctx->items_host = (OcgWorkItem*)malloc(sizeof(OcgWorkItem) * (size_t)n_items);
-    ctx->items_host_cap = ctx->items_host ? (size_t)n_items : 0;
-    ctx->items_uploaded = 0;
-    if (!ctx->items_host) {
-      free(seg_tile);
-      return ocg_fail(ctx, OCG_ERR_NOMEM, "malloc of %lld work items failed", n_items);
-    }
-  }
-  // chunk-major order: CTAs resident together stream the same source tiles (L2 reuse)
-  long long w = 0;
-  for (long long c = 0; c < n_chunks; ++c) {
-    for (int s = 0; s < n_seg; ++s) {
-      long long a = seg_off_ll[s] > tgt_begin ? seg_off_ll[s] : tgt_begin;
-      long long b = seg_off_ll[s + 1] < tgt_end ? seg_off_ll[s + 1] : tgt_end;
-      if (b <= a) continue;
-      long long nt = seg_tile[s + 1] - seg_tile[s];
-      long long tpc = (nt + n_chunks - 1) / n_chunks;
-      long long tb = c * tpc, te = tb + tpc < nt ? tb + tpc : nt;
-      for (long long t0 = a; t0 < b; t0 += CT) {
-        OcgWorkItem& it = ctx->items_host[w++];
-        it.tgt_begin = t0;
-        it.tgt_count = (int)(b - t0 < CT ? b - t0 : CT);
-        it.tile_begin = seg_tile[s] + (tb < nt ? tb : nt);
-        it.tile_count = (int)(te > tb ? te - tb : 0);
-        it.out_slot = c;
-      }
-    }
-  }
-  unsigned long long h = fnv1a(ctx->items_host, sizeof(OcgWorkItem) * (size_t)n_items, 1469598103934665603ull);
-  h = fnv1a(seg_tile, sizeof(long long) * (2 * (size_t)n_seg + 2), h);
-
+  OcgClusterPlan plan;
   int rc;
+  if ((rc = ocg_plan_cluster_items(ctx, n, seg_offsets_host, n_seg, tgt_begin, tgt_end, CT, OCG_TS,
+                                   ocg_variant_slots(ctx, variant), st, &plan)))
+    return rc;
+  const long long total_tiles = plan.total_tiles, n_chunks = plan.n_chunks, n_items = plan.n_items;
+  const OcgWorkItem* d_items = plan.d_items;
+  const long long* d_seg_tile = plan.d_seg_tile;
+  const long long* d_seg_off = plan.d_seg_off;
   float* tiles;
   float4* tgt;
   double* partial;
-  OcgWorkItem* d_items;
-  long long* d_seg;
-  const size_t seg_bytes = sizeof(long long) * (2 * (size_t)n_seg + 2);
-  const size_t items_bytes = sizeof(OcgWorkItem) * (size_t)n_items;
   rc = ocg_scratch(ctx, OCG_SCR_TILES, (size_t)total_tiles * OCG_TILE_BYTES, (void**)&tiles);
   if (!rc) rc = ocg_scratch(ctx, OCG_SCR_TGT, sizeof(float4) * (size_t)n, (void**)&tgt);
   if (!rc) rc = ocg_scratch(ctx, OCG_SCR_PARTIAL, sizeof(double) * (size_t)n_chunks * NC * (size_t)n, (void**)&partial);
-  void* items_raw = nullptr;
-  const size_t before = ctx->scratch_bytes[OCG_SCR_ITEMS];
-  if (!rc) rc = ocg_scratch(ctx, OCG_SCR_ITEMS, items_bytes + seg_bytes + 64, &items_raw);
-  if (rc) {
-    free(seg_tile);
-    return rc;
-  }
-  d_items = (OcgWorkItem*)items_raw;
-  d_seg = (long long*)((char*)items_raw + ((items_bytes + 63) / 64) * 64);
-  const bool reuse = before == ctx->scratch_bytes[OCG_SCR_ITEMS] && ctx->items_uploaded == (size_t)n_items &&
-                     ctx->items_hash == h;
-  if (!reuse) {
-    // synchronous small copies: the plan changes only when the segment layout or shard changes
-    cudaError_t e = cudaMemcpyAsync(d_items, ctx->items_host, items_bytes, cudaMemcpyHostToDevice, st);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(d_seg, seg_tile, seg_bytes, cudaMemcpyHostToDevice, st);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(st);  // seg_tile is freed below
-    if (e != cudaSuccess) {
-      free(seg_tile);
-      return ocg_fail(ctx, OCG_ERR_CUDA, "upload of the work plan failed: %s", cudaGetErrorString(e));
-    }
-    ctx->items_uploaded = (size_t)n_items;
-    ctx->items_hash = h;
-  }
-  free(seg_tile);
-  const long long* d_seg_tile = d_seg;
-  const long long* d_seg_off = d_seg + n_seg + 1;
+  if (rc) return rc;
 
   {
     long long nslots = total_tiles * OCG_TS;

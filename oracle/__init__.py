@@ -148,6 +148,65 @@ def self_gravity(pos, mass, eps2, G, seg_offsets=None, t0=0, t1=None, want_pot=F
     return (acc, pot) if want_pot else acc
 
 
+def self_gravity_hermite(pos, vel, mass, eps2, G, vel_to_len=1.0, seg_offsets=None, t0=0, t1=None, want_pot=False):
+    """Acceleration and jerk (and potential) of Plummer self-gravity per segment: the ph4 force loop itself
+    (4th-order Hermite, oc_code.py:218-229). pos, vel [3,n] fp64. Returns (acc, jerk[, pot])."""
+    pos, vel = _c(pos, np.float64), _c(vel, np.float64)
+    n = pos.shape[1]
+    mass = _c(mass, np.float64)
+    seg = np.array([0, n], np.int64) if seg_offsets is None else _c(seg_offsets, np.int64)
+    t1 = n if t1 is None else t1
+    acc, jerk = np.zeros((3, n), np.float64), np.zeros((3, n), np.float64)
+    pot = np.zeros(n, np.float64) if want_pot else None
+    lib().oracle_self_gravity_hermite(_p(pos), _p(vel), _p(mass), ctypes.c_int64(n), _p(seg), ctypes.c_int32(len(seg) - 1),
+                                      ctypes.c_double(eps2), ctypes.c_double(G), ctypes.c_double(vel_to_len),
+                                      ctypes.c_int64(t0), ctypes.c_int64(t1), _p(acc), _p(jerk), _p(pot))
+    return (acc, jerk, pot) if want_pot else (acc, jerk)
+
+
+def hermite_predict(pos, vel, acc, jerk, dt, vel_to_len=1.0):
+    """Predictor of the 4th-order Hermite scheme (Makino & Aarseth 1992), every product and sum rounded
+    separately in the order the CUDA kernel uses (bit-exact contract)."""
+    dt = float(dt)
+    c2, c3 = dt * dt * 0.5, dt * dt * dt / 6.0
+    dx = (vel * dt + acc * c2) + jerk * c3
+    return pos + dx * vel_to_len, vel + (acc * dt + jerk * c2)
+
+
+def hermite_correct(pos_p, vel_p, acc0, jerk0, acc1, jerk1, dt, vel_to_len=1.0, eta=0.14):
+    """Corrector + Aarseth step: returns (pos, vel, dt_min).  Same operation order as the CUDA kernel for pos / vel
+    (bit-exact); dt_min = min_i sqrt(eta (|a1||a2'| + |j1|^2) / (|j1||a3| + |a2'|^2)), a2' = a2 + dt a3."""
+    dt = float(dt)
+    dt2, dt3 = dt * dt, dt * dt * dt
+    i2, i3 = 1.0 / dt2, 1.0 / dt3
+    d3, d4, d5 = dt3 / 6.0, dt2 * dt2 / 24.0, dt2 * dt3 / 120.0
+    da = acc0 - acc1
+    a2 = (da * -6.0 - (jerk0 * 4.0 + jerk1 * 2.0) * dt) * i2
+    a3 = (da * 12.0 + (jerk0 + jerk1) * (6.0 * dt)) * i3
+    vel = (vel_p + a2 * d3) + a3 * d4
+    pos = pos_p + (a2 * d4 + a3 * d5) * vel_to_len
+    a2e = a2 + dt * a3
+    s_a, s_j, s_2, s_3 = ((v * v).sum(axis=0) for v in (acc1, jerk1, a2e, a3))
+    num, den = np.sqrt(s_a * s_2) + s_j, np.sqrt(s_j * s_3) + s_2
+    ok = (den > 0) & (num > 0)
+    dti = np.where(ok, np.sqrt(eta * num / np.where(ok, den, 1.0)), np.inf)
+    return pos, vel, float(dti.min()) if dti.size else float("inf")
+
+
+def hermite_evolve(pos, vel, mass, eps2, G, span, substeps, vel_to_len=1.0, eta=0.14):
+    """`substeps` shared Hermite steps over `span` (what cluster_code(integrator="hermite").evolve_model does):
+    force at the current state, then predict - evaluate - correct per step. Returns (pos, vel, dt_min)."""
+    h = span / substeps
+    acc, jerk = self_gravity_hermite(pos, vel, mass, eps2, G, vel_to_len)
+    dt_min = float("inf")
+    for _ in range(substeps):
+        xp, vp = hermite_predict(pos, vel, acc, jerk, h, vel_to_len)
+        a1, j1 = self_gravity_hermite(xp, vp, mass, eps2, G, vel_to_len)
+        pos, vel, dt_min = hermite_correct(xp, vp, acc, jerk, a1, j1, h, vel_to_len, eta)
+        acc, jerk = a1, j1
+    return pos, vel, dt_min
+
+
 def pack_planes(acc, pot=None):
     acc = _c(acc, np.float64)
     n = acc.shape[1]

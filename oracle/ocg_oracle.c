@@ -16,7 +16,10 @@
  *     (M. Grudic, pykdgrav/pytreegrav kernel.py; cubic spline of Springel et al. 2001 with
  *     support radius h), checked for continuity/Newtonian limits and against scipy quadrature of
  *     the spline density in tests/test_cpu_oracle.py;
- *   - analytic known answers (two-body, shell theorem, homogeneous sphere, affine fields).
+ *   - analytic known answers (two-body, shell theorem, homogeneous sphere, affine fields);
+ *   - the Hermite force loop and step (ph4 is absent: the scheme is restated from Makino & Aarseth 1992):
+ *     jerk against a finite difference of the acceleration along the flow, 4th-order convergence and energy
+ *     conservation on a Kepler orbit.
  *
  * Every function is the FP64 restatement of one step of the reference with the north_star's
  * algorithm substitutions (direct sum for the theta=0.5 tree, trilinear for RBF, linear-in-time
@@ -185,6 +188,53 @@ void oracle_self_gravity(const double* pos, const double* mass, int64_t n, const
         }
       }
       acc[i] = G * ax, acc[n + i] = G * ay, acc[2 * n + i] = G * az;
+      if (pot) pot[i] = G * ph;
+    }
+  }
+  free(r);
+}
+
+/* Hermite force loop: acceleration AND jerk (and potential) of the cluster's self-gravity — the arithmetic of
+ * the ph4 worker itself (4th-order Hermite; oc_code.py:218-229, eps2 = oc_code.py:225).  Positions and
+ * velocities of each segment recentred on its first particle, rounded to FP32 exactly as the GPU path does;
+ * pair terms and sums in FP64:  jerk = G vel_to_len sum m [ w/r^3 - 3 (d.w) d / r^5 ],  r^2 = |d|^2 + eps2. */
+void oracle_self_gravity_hermite(const double* pos, const double* vel, const double* mass, int64_t n, const int64_t* seg_off,
+                                 int32_t n_seg, double eps2, double G, double vel_to_len, int64_t t0, int64_t t1, double* acc,
+                                 double* jerk, double* pot) {
+  float* r = (float*)malloc(sizeof(float) * 7 * (size_t)n);
+  for (int s = 0; s < n_seg; ++s) {
+    const int64_t a = seg_off[s], b = seg_off[s + 1];
+    for (int64_t i = a; i < b; ++i) {
+      for (int c = 0; c < 3; ++c) {
+        r[7 * i + c] = (float)(pos[c * n + i] - pos[c * n + a]);
+        r[7 * i + 4 + c] = (float)(vel[c * n + i] - vel[c * n + a]);
+      }
+      r[7 * i + 3] = (float)mass[i];
+    }
+  }
+  const double e2 = (double)(float)eps2;
+  for (int s = 0; s < n_seg; ++s) {
+    const int64_t a = seg_off[s], b = seg_off[s + 1];
+    const int64_t lo = a > t0 ? a : t0, hi = b < t1 ? b : t1;
+#pragma omp parallel for schedule(static)
+    for (int64_t i = lo; i < hi; ++i) {
+      double A[3] = {0, 0, 0}, J[3] = {0, 0, 0}, ph = 0;
+      const float* ti = r + 7 * i;
+      for (int64_t j = a; j < b; ++j) {
+        if (j == i) continue;
+        const float* sj = r + 7 * j;
+        const double d[3] = {(double)sj[0] - ti[0], (double)sj[1] - ti[1], (double)sj[2] - ti[2]};
+        const double w[3] = {(double)sj[4] - ti[4], (double)sj[5] - ti[5], (double)sj[6] - ti[6]};
+        const double r2 = d[0] * d[0] + d[1] * d[1] + d[2] * d[2] + e2;
+        if (r2 > 0.0) {
+          const double ri = 1.0 / sqrt(r2), m = sj[3];
+          const double f = m * ri * ri * ri;
+          const double al = -3.0 * (d[0] * w[0] + d[1] * w[1] + d[2] * w[2]) * ri * ri;
+          for (int c = 0; c < 3; ++c) A[c] += f * d[c], J[c] += f * (w[c] + al * d[c]);
+          ph -= m * ri;
+        }
+      }
+      for (int c = 0; c < 3; ++c) acc[c * n + i] = G * A[c], jerk[c * n + i] = G * vel_to_len * J[c];
       if (pot) pot[i] = G * ph;
     }
   }

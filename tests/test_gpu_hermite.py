@@ -1,0 +1,221 @@
+"""K6 on the GPU: the Hermite force loop (acceleration + jerk) and the 4th-order Hermite predictor / corrector —
+ph4's own arithmetic (oc_code.py:218-229) — against the CPU oracle, through the C ABI."""
+import numpy as np
+import pytest
+
+import oracle
+from util import TOL, dev, rel_err, rel_err_scalar
+
+pytestmark = pytest.mark.gpu
+
+G = 4.3986004e-09      # kpc^2 km/s /Myr /Msun (gizmo_interface.py:70)
+VTL = 1.022712165045695e-3  # kpc per Myr at 1 km/s
+EPS2 = (0.01e-3) ** 2  # (0.01 pc)^2 in kpc^2 (test_options:63, oc_code.py:225)
+
+
+def cluster(n, seed=1777, center=(8.0, 0.0, 0.0), vsys=(0.0, 220.0, 0.0), kroupa=False):
+    from oc_nbody_b200.synthetic import make_plummer_cluster
+    pos_pc, vel, mass = make_plummer_cluster(n, seed=seed)
+    if kroupa:
+        mass = np.exp(np.random.default_rng(seed).uniform(np.log(0.1), np.log(20.0), n))
+    return pos_pc * 1e-3 + np.asarray(center)[:, None], vel + np.asarray(vsys)[:, None], mass
+
+
+def gpu_force(ctx, pos, vel, mass, eps2=EPS2, seg=None, t0=0, t1=None, want_pot=True):
+    import torch
+    n = pos.shape[1]
+    acc = torch.full((3, n), np.nan, dtype=torch.float64, device="cuda")
+    jerk = torch.full((3, n), np.nan, dtype=torch.float64, device="cuda")
+    pot = torch.full((n,), np.nan, dtype=torch.float64, device="cuda") if want_pot else None
+    ctx.self_gravity_hermite(dev(pos), dev(vel), dev(mass), eps2, G, VTL, acc, jerk, pot, seg_offsets=seg, tgt_begin=t0,
+                             tgt_end=t1)
+    torch.cuda.synchronize()
+    return acc.cpu().numpy(), jerk.cpu().numpy(), (pot.cpu().numpy() if want_pot else None)
+
+
+def check(got, ref, sl=slice(None)):
+    a, j, p = got
+    ra, rj, rp = ref
+    assert rel_err(a[:, sl], ra[:, sl]) <= TOL
+    assert rel_err(j[:, sl], rj[:, sl]) <= TOL
+    if p is not None:
+        assert rel_err_scalar(p[sl], rp[sl]) <= TOL
+
+
+@pytest.mark.parametrize("n", [2, 33, 1024, 4096])
+def test_small_cluster_path_matches_oracle(ctx, n):
+    pos, vel, mass = cluster(n, kroupa=(n == 1024))
+    ref = oracle.self_gravity_hermite(pos, vel, mass, EPS2, G, VTL, want_pot=True)
+    check(gpu_force(ctx, pos, vel, mass), ref)
+
+
+@pytest.mark.parametrize("n", [700, 5000, 12289])
+def test_streaming_path_matches_oracle_and_small_path(ctx, n):
+    pos, vel, mass = cluster(n, seed=3)
+    ref = oracle.self_gravity_hermite(pos, vel, mass, EPS2, G, VTL, want_pot=True)
+    ctx.lib.ocg_debug_set_hermite_small_path(0)
+    try:
+        got = gpu_force(ctx, pos, vel, mass)
+        again = gpu_force(ctx, pos, vel, mass)
+    finally:
+        ctx.lib.ocg_debug_set_hermite_small_path(1)
+    check(got, ref)
+    for x, y in zip(got, again):
+        assert np.array_equal(x, y)  # run-to-run deterministic
+    if n <= 4096:
+        small = gpu_force(ctx, pos, vel, mass)
+        assert rel_err(got[0], small[0]) <= 2e-6 and rel_err(got[1], small[1]) <= 2e-6
+
+
+def test_every_kernel_variant_matches_oracle(ctx):
+    pos, vel, mass = cluster(5000, seed=8)
+    ref = oracle.self_gravity_hermite(pos, vel, mass, EPS2, G, VTL, want_pot=True)
+    nv = ctx.lib.ocg_debug_set_hermite_variant(-1)
+    assert nv >= 3
+    try:
+        for v in range(nv):
+            ctx.lib.ocg_debug_set_hermite_variant(v)
+            check(gpu_force(ctx, pos, vel, mass), ref)
+            check(gpu_force(ctx, pos, vel, mass, want_pot=False), ref)
+    finally:
+        ctx.lib.ocg_debug_set_hermite_variant(-1)
+
+
+def test_batch_of_ragged_clusters_and_target_shards(ctx):
+    lens = [4096, 0, 1, 777, 2048, 5000, 513]
+    seg = np.concatenate([[0], np.cumsum(lens)])
+    parts = [cluster(l, seed=20 + i, center=(8.0 * np.cos(i), 8.0 * np.sin(i), 0.1 * i)) for i, l in enumerate(lens) if l]
+    pos, vel, mass = (np.concatenate([p[k] for p in parts], axis=-1) for k in range(3))
+    ref = oracle.self_gravity_hermite(pos, vel, mass, EPS2, G, VTL, seg_offsets=seg, want_pot=True)
+    got = gpu_force(ctx, pos, vel, mass, seg=seg)
+    check(got, ref)
+    # the lone star feels nothing
+    i1 = seg[2]
+    assert np.all(got[0][:, i1] == 0) and np.all(got[1][:, i1] == 0) and got[2][i1] == 0
+    # a rank's target shard: written for [t0, t1) only, same values
+    n = pos.shape[1]
+    t0, t1 = 3000, 9001
+    sh = gpu_force(ctx, pos, vel, mass, seg=seg, t0=t0, t1=t1)
+    for x, y in zip(sh, got):
+        assert np.array_equal(x[..., t0:t1], y[..., t0:t1])
+        assert np.all(np.isnan(x[..., :t0])) and np.all(np.isnan(x[..., t1:]))
+    assert n > t1
+
+
+def test_unsoftened_form_skips_coincident_pairs(ctx):
+    pos, vel, mass = cluster(3000, seed=4)
+    pos[:, 17] = pos[:, 5]       # a coincident pair: contributes nothing when eps2 == 0
+    pos[:, 2999] = pos[:, 0]     # ... including one with the recentring origin (where tile padding sits)
+    ref = oracle.self_gravity_hermite(pos, vel, mass, 0.0, G, VTL, want_pot=True)
+    for small in (1, 0):
+        ctx.lib.ocg_debug_set_hermite_small_path(small)
+        try:
+            got = gpu_force(ctx, pos, vel, mass, eps2=0.0)
+        finally:
+            ctx.lib.ocg_debug_set_hermite_small_path(1)
+        assert all(np.all(np.isfinite(x)) for x in got)
+        check(got, ref)
+
+
+def test_argument_errors(ctx):
+    import torch
+    from oc_nbody_b200._lib import OcgError
+    pos, vel, mass = cluster(64)
+    a = torch.empty((3, 64), dtype=torch.float64, device="cuda")
+    with pytest.raises(OcgError):
+        ctx.self_gravity_hermite(dev(pos), dev(vel), dev(mass), -1.0, G, VTL, a, a.clone())
+    with pytest.raises(OcgError):
+        ctx.self_gravity_hermite(dev(pos), dev(vel), dev(mass), EPS2, G, VTL, a, a.clone(), tgt_begin=10, tgt_end=65)
+    with pytest.raises(OcgError):
+        ctx.self_gravity_hermite(dev(pos), dev(vel), dev(mass), EPS2, G, VTL, a, a.clone(), seg_offsets=[0, 40, 30, 64])
+    with pytest.raises(OcgError):
+        ctx.hermite_correct(dev(pos), dev(vel), a, a, dev(pos), dev(vel), a, a, 0.0, VTL, 0.14)
+
+
+def test_predictor_and_corrector_are_bit_exact(ctx):
+    import torch
+    rng = np.random.default_rng(12)
+    n = 3001
+    pos, vel, mass = cluster(n, seed=6)
+    a0, j0 = oracle.self_gravity_hermite(pos, vel, mass, EPS2, G, VTL)
+    dt = 0.0123
+    xp_ref, vp_ref = oracle.hermite_predict(pos, vel, a0, j0, dt, VTL)
+    xp, vp = torch.empty((3, n), dtype=torch.float64, device="cuda"), torch.empty((3, n), dtype=torch.float64, device="cuda")
+    ctx.hermite_predict(dev(pos), dev(vel), dev(a0), dev(j0), dt, VTL, xp, vp)
+    assert np.array_equal(xp.cpu().numpy(), xp_ref) and np.array_equal(vp.cpu().numpy(), vp_ref)
+    a1, j1 = oracle.self_gravity_hermite(xp_ref, vp_ref, mass, EPS2, G, VTL)
+    x_ref, v_ref, dtm_ref = oracle.hermite_correct(xp_ref, vp_ref, a0, j0, a1, j1, dt, VTL, 0.14)
+    x, v, da0, dj0 = dev(pos), dev(vel), dev(a0), dev(j0)
+    dtm = torch.zeros(1, dtype=torch.float64, device="cuda")
+    ctx.hermite_correct(x, v, da0, dj0, xp, vp, dev(a1), dev(j1), dt, VTL, 0.14, dtm)
+    assert np.array_equal(x.cpu().numpy(), x_ref) and np.array_equal(v.cpu().numpy(), v_ref)
+    assert np.array_equal(da0.cpu().numpy(), a1) and np.array_equal(dj0.cpu().numpy(), j1)
+    assert abs(dtm.item() - dtm_ref) <= 1e-12 * dtm_ref
+    del rng
+
+
+@pytest.mark.parametrize("n,substeps", [(1024, 4), (6000, 2)])
+def test_cluster_code_hermite_evolve_matches_oracle(ctx, n, substeps):
+    from oc_nbody_b200.cluster import cluster_code
+    from oc_nbody_b200.units import units
+    pos, vel, mass = cluster(n, seed=31)
+    cl = cluster_code(mass, pos, vel, softening_pc=0.01, substeps=substeps, ctx=ctx, integrator="hermite")
+    span = 0.05
+    cl.evolve_model(span | units.Myr)
+    x_ref, v_ref, dtm_ref = oracle.hermite_evolve(pos, vel, mass, EPS2, G, span, substeps, VTL, 0.14)
+    x, v = cl.pos.cpu().numpy(), cl.vel.cpu().numpy()
+    # displacements over the span agree to the force tolerance
+    assert rel_err(x - pos, x_ref - pos) <= TOL
+    assert rel_err(v - vel, v_ref - vel) <= TOL
+    assert abs(cl.dt_min.item() - dtm_ref) <= 1e-3 * dtm_ref
+    assert cl.suggested_substeps(span) >= 1
+    # Hermite and leapfrog integrate the same dynamics
+    lf = cluster_code(mass, pos, vel, softening_pc=0.01, substeps=64 * substeps, ctx=ctx)
+    lf.evolve_model(span | units.Myr)
+    scale = np.abs(x_ref - pos).max()
+    assert np.max(np.abs(lf.pos.cpu().numpy() - x)) <= 2e-2 * scale
+
+
+def test_bridge_with_hermite_cluster_eager_equals_cuda_graph(ctx):
+    from oc_nbody_b200.bridge import Bridge
+    from oc_nbody_b200.cluster import cluster_code
+    from oc_nbody_b200.gizmo_field import gizmo_field
+    from oc_nbody_b200.synthetic import advance_snapshot, make_snapshot
+    from oc_nbody_b200.units import units
+    center = np.array([8.0, 0.0, 0.0])
+    snaps = [make_snapshot(20000, seed=1776)]
+    snaps.append(advance_snapshot(snaps[0], 23.0))
+    opts = dict(grid_x_size_in_kpc=0.05, grid_y_size_in_kpc=0.05, grid_z_size_in_kpc=0.05, grid_resolution=0.05 / 8)
+    field = gizmo_field(opts, snaps, chosen_positions=np.tile(center, (2, 1)), ctx=ctx)
+    pos, vel, mass = cluster(1024, seed=2)
+    out = []
+    for graph in (False, True):
+        field.evolve_grid(center)
+        field.evolve_model(0.0 | units.Myr)
+        cl = cluster_code(mass, pos, vel, softening_pc=0.01, substeps=2, ctx=ctx, integrator="hermite")
+        system = Bridge(timestep=0.1 | units.Myr, use_threading=False, use_cuda_graph=graph)
+        system.add_system(cl, (field,))
+        system.add_system(field)
+        system.evolve_model(0.5 | units.Myr, timestep=0.1 | units.Myr)
+        out.append((cl.pos.cpu().numpy(), cl.vel.cpu().numpy()))
+        if graph:
+            assert system.graph_replays >= 3
+    assert np.max(np.abs(out[0][0] - out[1][0])) <= 1e-13 * 8.0
+    assert np.max(np.abs(out[0][1] - out[1][1])) <= 1e-12 * 220.0
+
+
+def test_fullsize_65536_third_law_and_rows(ctx):
+    """configs[2] size: N = 65 536.  Newton's third law for the acceleration AND the jerk (sum m a = sum m j = 0 up to
+    rounding), and 150 rows against the oracle over all sources."""
+    n = 65536
+    pos, vel, mass = cluster(n, seed=1777, kroupa=True)
+    a, j, p = gpu_force(ctx, pos, vel, mass)
+    for f in (a, j):
+        net = (mass * f).sum(axis=1)
+        assert np.max(np.abs(net)) <= 1e-6 * (mass * np.sqrt((f * f).sum(axis=0))).sum()
+    rows = np.unique(np.random.default_rng(1).integers(0, n, 150))
+    ref = [oracle.self_gravity_hermite(pos, vel, mass, EPS2, G, VTL, t0=int(t), t1=int(t) + 1, want_pot=True) for t in rows]
+    ea = max(rel_err(a[:, t:t + 1], r[0][:, t:t + 1]) for t, r in zip(rows, ref))
+    ej = max(rel_err(j[:, t:t + 1], r[1][:, t:t + 1]) for t, r in zip(rows, ref))
+    ep = max(rel_err_scalar(p[t:t + 1], r[2][t:t + 1]) for t, r in zip(rows, ref))
+    assert ea <= TOL and ej <= TOL and ep <= TOL
