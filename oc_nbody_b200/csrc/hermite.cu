@@ -425,18 +425,10 @@ extern "C" int ocg_self_gravity_hermite(ocg_ctx* ctx, const double* pos_dev, con
     return OCG_OK;
   }
 
-  // tile shape by the typical cluster size: the largest CTA tile that still gives every SM work
-  const int64_t seg_typ = (n + n_seg - 1) / n_seg;
   int variant = g_hm_force_variant;
-  if (variant < 0) {
-    // among the 2048/1536/1024-target tiles, the one that pads the typical cluster least (ties: the larger)
-    double best = 1e300;
-    for (int c = 0; c < 3; ++c) {
-      const long long ct = 64ll * g_hm_variants[c].nw * g_hm_variants[c].np;
-      const double waste = (double)(((seg_typ + ct - 1) / ct) * ct) / (double)seg_typ;
-      if (waste < best - 1e-9) best = waste, variant = c;
-    }
-  }
+  // measured on B200 (tools/bench_hermite.py, profiles/r01_bench_hermite.json): the 1024-target tile (4 targets per
+  // thread, 212 registers, no spills) is the fastest shape at N = 65 536 and on batches of 4096-star clusters
+  if (variant < 0) variant = 2;
   const HermiteVariant& v = g_hm_variants[variant];
   const int NTHR = 32 * v.nw, CT = 2 * v.np * NTHR;
 

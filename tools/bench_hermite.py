@@ -34,6 +34,16 @@ def main():
     ang = np.linspace(0, 2 * np.pi, ncl, endpoint=False)
     origin = np.stack([8 * np.cos(ang), 8 * np.sin(ang), np.zeros(ncl)], 1)
     nv = ctx.lib.ocg_debug_set_hermite_variant(-1)
+    if "--profile" in sys.argv:
+        # the launch an ncu capture targets: production variant, N = 65 536, no potential, 6 calls
+        pos_pc, vel1, mass = make_plummer_cluster(65536)
+        d_pos, d_vel, d_m = (torch.from_numpy(np.ascontiguousarray(x)).to(dev) for x in (pos_pc * 1e-3 + origin[0][:, None], vel1, mass))
+        a = torch.empty((3, 65536), dtype=torch.float64, device=dev)
+        j = torch.empty((3, 65536), dtype=torch.float64, device=dev)
+        for _ in range(6):
+            ctx.self_gravity_hermite(d_pos, d_vel, d_m, eps2, G_KPC_KMS_MYR, KMS_TO_KPC_PER_MYR, a, j, None)
+        torch.cuda.synchronize()
+        return
     for name, nseg, npc in (("k6_hermite_n65536", 1, 65536), ("k6_hermite_256x4096", 256, 4096), ("k6_hermite_n1024_small", 1, 1024),
                             ("k6_hermite_n4096_small", 1, 4096)):
         pos_pc, vel1, mass = make_plummer_cluster(npc)
