@@ -182,6 +182,27 @@ int ocg_grid_interp_slot(ocg_ctx* ctx, const ocg_grid_desc* coarse, const ocg_gr
                          const double* star_z_dev, const int32_t* star_cluster_dev, int64_t n_star,
                          double* acc_out_dev, double* pot_out_dev, void* stream);
 
+/* get_gravity_at_point / get_tidal_tensor_at_point with the reference's OWN spatial interpolation
+ * (gizmo_interface.py:651-756; options nclose / basis / order, options.py:43-45): per star the
+ * `nclose` nearest points of the evolved grid (cKDTree.query over lattice + appended origin row) and the
+ * polyharmonic-spline RBF interpolant with polynomial terms of degree <= `order`
+ * (rbf.interpolate.RBFInterpolant(..., basis=phs<phs>, order=order)), evaluated at the star.
+ * field_dev: fp64 [n_comp][n_cluster][n_node] — the time-evaluated grid arrays the reference interpolates
+ *   (grid.evolved_acceleration_x/y/z, evolved_potential), n_comp in 1..4; out_dev fp64 [n_comp][n_star].
+ * nclose + C(order+3,3) <= 206 (the reference's 150 + 56); phs in {1,3,5,7}; include_origin: the appended origin row
+ *   (grid_cartesian.py:66-67) takes part in the neighbour search (0 when it duplicates a lattice node).
+ * tensor_out_dev: fp64 [3][n_comp][n_star] or NULL — d out_c / d x_i (T[i][j] of gizmo_interface.py:719-756 for c = j).
+ * status_out_dev: int32 [n_star] or NULL — 0 ok; bit 0 neighbour window truncated (star far outside the grid),
+ *   bit 1 refinement not converged (ill-conditioned stencil, e.g. clipped by the grid edge), bit 2 zero pivot.
+ * neighbors_out_dev: int64 [nclose][n_star] or NULL — point-list indices of the neighbours, nearest first, ties by
+ *   index.  Single-level grid only.                                                                              */
+int ocg_grid_interp_rbf(ocg_ctx* ctx, const ocg_grid_desc* grid, const double* field_dev, int32_t n_comp,
+                        int32_t nclose, int32_t order, int32_t phs, int32_t include_origin,
+                        const double* star_x_dev, const double* star_y_dev, const double* star_z_dev,
+                        const int32_t* star_cluster_dev, int64_t n_star, double* out_dev,
+                        double* tensor_out_dev, int32_t* status_out_dev, int64_t* neighbors_out_dev,
+                        void* stream);
+
 /* K2 pack with a scatter: rec[index[i]] = float4(acc[0][i], acc[1][i], acc[2][i], pot[i]) for i < n.
  * Lays rows of the reference's point list (kept coarse points | fine lattice | origin row,
  * grid_cartesian.py:71-91) out as full-lattice node records.  acc_dev fp64 [3][n]; pot_dev [n] or NULL;

@@ -20,7 +20,7 @@ ABI_SYMBOLS = [
     "ocg_version", "ocg_create", "ocg_destroy", "ocg_last_error", "ocg_device_info", "ocg_launch_count",
     "ocg_last_direct_kernel_ms", "ocg_set_kernel_timing", "ocg_recentre_f64", "ocg_cast_f64_f32",
     "ocg_field_direct", "ocg_frame_subtract", "ocg_field_build_host", "ocg_pack_planes", "ocg_grid_time_blend",
-    "ocg_grid_interp", "ocg_grid_interp_multi", "ocg_grid_interp_nested", "ocg_pack_planes_indexed", "ocg_set_interp_weight_slots", "ocg_grid_interp_slot", "ocg_self_gravity", "ocg_self_gravity_hermite", "ocg_hermite_predict", "ocg_hermite_correct", "ocg_bound_com", "ocg_eject_mask", "ocg_compact_rows", "ocg_kick", "ocg_drift", "ocg_axpy", "ocg_probe_throughput",
+    "ocg_grid_interp", "ocg_grid_interp_multi", "ocg_grid_interp_nested", "ocg_pack_planes_indexed", "ocg_set_interp_weight_slots", "ocg_grid_interp_slot", "ocg_grid_interp_rbf", "ocg_self_gravity", "ocg_self_gravity_hermite", "ocg_hermite_predict", "ocg_hermite_correct", "ocg_bound_com", "ocg_eject_mask", "ocg_compact_rows", "ocg_kick", "ocg_drift", "ocg_axpy", "ocg_probe_throughput",
 ]
 
 
@@ -74,6 +74,7 @@ def load_library():
     L.ocg_grid_interp_slot.argtypes = [vp, ctypes.POINTER(_GridDesc), ctypes.POINTER(_GridDesc), vp, vp, i32, i32, vp, vp, vp, vp,
                                        i64, vp, vp, vp]
     L.ocg_self_gravity.argtypes = [vp, vp, vp, i64, vp, i32, dbl, dbl, i64, i64, vp, vp, vp]
+    L.ocg_grid_interp_rbf.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, vp, i64, vp, vp, vp, vp, vp]
     L.ocg_self_gravity_hermite.argtypes = [vp, vp, vp, vp, i64, vp, i32, dbl, dbl, dbl, i64, i64, vp, vp, vp, vp]
     L.ocg_hermite_predict.argtypes = [vp, vp, vp, vp, vp, i64, dbl, dbl, vp, vp, vp]
     L.ocg_hermite_correct.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, dbl, dbl, dbl, vp, vp]
@@ -252,6 +253,16 @@ class Context:
                                                  _dptr(sz), _dptr(star_cluster), sx.shape[0], _dptr(acc_out), _dptr(pot_out),
                                                  _dptr(tensor_out), _dptr(level_out), _dptr(cell_out), self._stream()),
                  "ocg_grid_interp_nested")
+
+    def grid_interp_rbf(self, n, nodes, origin, field, sx, sy, sz, star_cluster, out, nclose=150, order=5, phs=3,
+                        include_origin=True, tensor_out=None, status_out=None, neighbors_out=None):
+        """K7: the reference's own spatial interpolation (kNN + polyharmonic-spline RBF, gizmo_interface.py:651-717).
+        field fp64 [n_comp, n_cluster * n_node] (or [n_comp, n_node]); out [n_comp, n_star]."""
+        dc = self._grid_desc(n, nodes, origin)
+        self._ck(self.lib.ocg_grid_interp_rbf(self.h, ctypes.byref(dc), _dptr(field), int(field.shape[0]), int(nclose), int(order),
+                                              int(phs), 1 if include_origin else 0, _dptr(sx), _dptr(sy), _dptr(sz),
+                                              _dptr(star_cluster), sx.shape[0], _dptr(out), _dptr(tensor_out), _dptr(status_out),
+                                              _dptr(neighbors_out), self._stream()), "ocg_grid_interp_rbf")
 
     def set_interp_weight_slots(self, weights, first_slot=0):
         """weights: sequence of up-to-4-element weight lists, written to constant-memory slots first_slot.. (stream-ordered)."""

@@ -68,7 +68,8 @@ class Bridge(object):
             return None
         for cl, fld in (self.systems, self.systems[::-1]):
             if (self.partners[id(cl)] == (fld,) and self.partners[id(fld)] == () and hasattr(fld, "kick_device")
-                    and hasattr(fld, "_time_planes_") and type(cl).__name__ == "cluster_code" and hasattr(cl, "_evolve_device_")):
+                    and hasattr(fld, "_time_planes_") and getattr(fld, "space_interpolation", "trilinear") == "trilinear"
+                    and type(cl).__name__ == "cluster_code" and hasattr(cl, "_evolve_device_")):
                 return cl, fld
         return None
 

@@ -20,6 +20,7 @@ SOURCES = [
     ("self_gravity", "self_gravity.cu", []),
     ("hermite", "hermite.cu", []),
     ("grid_interp", "grid_interp.cu", []),
+    ("rbf_interp", "rbf_interp.cu", []),
     ("cluster_ops", "cluster_ops.cu", []),
 ]
 NVCC_FLAGS = [

@@ -36,6 +36,8 @@ _DEFAULTS = dict(
     grid_fine_x_size_in_kpc=None, grid_fine_y_size_in_kpc=None, grid_fine_z_size_in_kpc=None, grid_fine_resolution=None,
     # "linear" (BASELINE.json north_star) or "cubic" (the reference's own splrep/splev, gizmo_interface.py:587-620)
     time_interpolation="linear",
+    space_interpolation="trilinear",  # "rbf": the reference's own kNN + RBF-PHS interpolant (options nclose/basis/order)
+    nclose=150, basis="phs3", order=5,  # options.py:43-45
     # per-snapshot field caches in the reference's own file names and format (gizmo_interface.py:373-391,454-459,
     # 470-495): None = no caching.  The remaining keys only enter the cache file name.
     cache_directory=None, sim_name="synthetic", grid_seed=1776, Rmax=50.0, startnum=None, endnum=None, num_prior=0,
@@ -73,6 +75,16 @@ class gizmo_field(object):
                 raise ValueError("fine_grid needs %s (options.py:108-118)" % ", ".join(missing))
         if self.time_interpolation not in ("linear", "cubic"):
             raise ValueError("time_interpolation must be 'linear' or 'cubic'")
+        if self.space_interpolation not in ("trilinear", "rbf"):
+            raise ValueError("space_interpolation must be 'trilinear' or 'rbf'")
+        if self.space_interpolation == "rbf":
+            if self.fine_grid:
+                raise NotImplementedError("space_interpolation='rbf' supports the single-level grid only")
+            basis = getattr(self.basis, "__name__", None) or str(self.basis)  # a name or an rbf.basis object (options.py:178-246)
+            if basis not in ("phs1", "phs3", "phs5", "phs7"):
+                raise NotImplementedError("space_interpolation='rbf' implements the odd polyharmonic splines phs1/3/5/7, not %r" % (basis,))
+            self._rbf_phs = int(basis[3:])
+            self.nclose, self.order = int(self.nclose), int(self.order)
         self.G = G_KPC_KMS_MYR  # kpc^2 km/s /Myr /Msun, the unit of gizmo_interface.py:70
         self._ctx = ctx  # created lazily: host-side logic (source assembly, time bracketing) needs no GPU
         self.snapshots = list(snapshots)
@@ -400,9 +412,40 @@ class gizmo_field(object):
         fine = None if d["rec_fine"] is None else [d["rec_fine"][a], d["rec_fine"][b]]
         return [d["rec"][a], d["rec"][b]], fine, [float(wa), float(wb)]
 
+    def _rbf_field_(self):
+        """FP64 [4, n_node] device copy of the time-evaluated grid arrays (grid.evolved_acceleration_x/y/z and the
+        potential, gizmo_interface.py:618-620) that the RBF interpolant reads; refreshed when the model time changes."""
+        import torch
+        if getattr(self, "_rbf_cache", None) is None or self._rbf_cache[0] is not self._blend_():
+            b = self._blend_()
+            f = np.concatenate([b[0], b[1][None]], axis=0)
+            self._rbf_cache = (b, torch.from_numpy(np.ascontiguousarray(f)).to(self._dev["device"]))
+        return self._rbf_cache[1]
+
+    def _interp_rbf_(self, sx, sy, sz, want_pot, want_tensor):
+        """K7: kNN(nclose) + RBF-PHS on the device; the last status vector is kept in self.rbf_status."""
+        import torch
+        d, g = self._dev, self.grid
+        n = sx.shape[0]
+        f = self._rbf_field_()
+        out = torch.empty((4, n), dtype=torch.float64, device=d["device"])
+        tensor = torch.empty((3, 4, n), dtype=torch.float64, device=d["device"]) if want_tensor else None
+        self.rbf_status = torch.empty(n, dtype=torch.int32, device=d["device"])
+        dup = all(len(a) % 2 == 1 and a[len(a) // 2] == 0.0 for a in g.nodes)  # the origin row duplicates a lattice node
+        self.ctx.grid_interp_rbf(g.shape, d["nodes"], d["origin"], f, sx, sy, sz, None, out, nclose=self.nclose,
+                                 order=self.order, phs=self._rbf_phs, include_origin=not dup, tensor_out=tensor,
+                                 status_out=self.rbf_status)
+        acc, pot = out[:3], (out[3] if want_pot else None)
+        if want_tensor:
+            # [3 (d/dx_i), 3 (a_j), n] -> [9, n] with row 3*i + j, as K3's tensor output
+            return acc, pot, tensor[:, :3, :].reshape(9, n)
+        return acc, pot
+
     def _interp_device_(self, sx, sy, sz, want_pot, want_tensor=False):
         """K3 on device tensors (FP64 kpc). Returns acc [3,n], pot [n] or None (, tensor [9,n]) device tensors."""
         import torch
+        if self.space_interpolation == "rbf":
+            return self._interp_rbf_(sx, sy, sz, want_pot, want_tensor)
         d = self._dev
         n = sx.shape[0]
         acc = torch.empty((3, n), dtype=torch.float64, device=d["device"])
@@ -475,7 +518,7 @@ class gizmo_field(object):
         """Fused BRIDGE half-kick on device state (FP64 [3,n] tensors): v += dt * a_tidal(x). No host copies.
         With `planes` = (coarse planes, fine planes or None) and `w_slot` the time-blend weights are read from the
         constant-memory slot (ocg_set_interp_weight_slots) — the form a captured CUDA graph replays."""
-        if w_slot is None:
+        if w_slot is None or self.space_interpolation == "rbf":
             acc = self._interp_device_(pos_kpc[0], pos_kpc[1], pos_kpc[2], False)[0]
         else:
             import torch

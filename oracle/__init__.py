@@ -301,6 +301,64 @@ def grid_interp_nested(nodes, fine_nodes, origin, recs, recs_fine, weights, sx, 
     return out
 
 
+def rbf_monomial_powers(order):
+    """Exponents of the monomials of total degree <= order in 3-D (56 for the reference's order 5)."""
+    return [(a, b, d - a - b) for d in range(order + 1) for a in range(d, -1, -1) for b in range(d - a, -1, -1)]
+
+
+def rbf_interp(nodes, origin, fields, sx, sy, sz, nclose=150, order=5, phs=3, include_origin=True, want_tensor=False,
+               want_neighbors=False):
+    """get_gravity_at_point as the reference evaluates it (gizmo_interface.py:651-717): per star the `nclose` nearest
+    points of the evolved grid (lattice nodes in C order + the appended origin row; cKDTree.query) and
+    rbf.interpolate.RBFInterpolant(points, values, basis=phs<phs>, order=order) evaluated at the star.  The `rbf`
+    package is absent here; scipy.interpolate.RBFInterpolator (same author, kernel='cubic', degree=order) is the
+    same interpolant and pins this function in tests/test_cpu_rbf.py.
+
+    Brute-force neighbour search, ordered by (distance^2, point index); the saddle-point system [[K, P], [P', 0]] in
+    coordinates shifted to the star and scaled by the grid spacing (the interpolant is invariant under both), solved
+    with LAPACK in FP64.  fields [n_comp, n_node]; returns dict(out [n_comp, n], tensor [3, n_comp, n], neighbors)."""
+    xg, yg, zg = (np.asarray(a, np.float64) for a in nodes)
+    o = np.asarray(origin, np.float64).reshape(3)
+    gx, gy, gz = np.meshgrid(xg + o[0], yg + o[1], zg + o[2], indexing="ij")
+    pts = np.stack([gx.ravel(), gy.ravel(), gz.ravel()], axis=1)
+    pts = np.concatenate([pts, o[None]]) if include_origin else pts
+    fields = np.asarray(fields, np.float64)
+    h = max(xg[1] - xg[0], yg[1] - yg[0], zg[1] - zg[0])
+    pw = np.array(rbf_monomial_powers(order))
+    nm = len(pw)
+    sx, sy, sz = (np.atleast_1d(np.asarray(a, np.float64)) for a in (sx, sy, sz))
+    n = sx.shape[0]
+    out = np.empty((fields.shape[0], n))
+    tensor = np.empty((3, fields.shape[0], n)) if want_tensor else None
+    nbrs = np.empty((nclose, n), np.int64)
+    for s in range(n):
+        p = np.array([sx[s], sy[s], sz[s]])
+        d = pts - p
+        d2 = (d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1]) + d[:, 2] * d[:, 2]
+        ids = np.lexsort((np.arange(len(d2)), d2))[:nclose]
+        nbrs[:, s] = ids
+        y = (pts[ids] - p) / h
+        r = np.sqrt(((y[:, None, :] - y[None, :, :]) ** 2).sum(axis=-1))
+        P = np.prod(y[:, None, :] ** pw[None, :, :], axis=-1)
+        A = np.block([[r ** phs, P], [P.T, np.zeros((nm, nm))]])
+        rhs = np.concatenate([fields[:, ids].T, np.zeros((nm, fields.shape[0]))])
+        sol = np.linalg.solve(A, rhs)            # [nclose + nm, n_comp]: weights, then polynomial coefficients
+        r0 = np.sqrt((y * y).sum(axis=1))
+        out[:, s] = (r0 ** phs) @ sol[:nclose] + sol[nclose]    # every monomial but the constant vanishes at the star
+        if want_tensor:
+            for a in range(3):
+                # d/dx_a at the star: -phs |y|^(phs-2) y_a for the radial part, the coefficient of x_a for the polynomial
+                g = -phs * np.where(r0 > 0, r0 ** (phs - 2), 0.0) * y[:, a]
+                lin = [k for k in range(nm) if pw[k].sum() == 1 and pw[k][a] == 1]
+                tensor[a, :, s] = (g @ sol[:nclose] + (sol[nclose + lin[0]] if lin else 0.0)) / h
+    res = dict(out=out)
+    if want_tensor:
+        res["tensor"] = tensor
+    if want_neighbors:
+        res["neighbors"] = nbrs
+    return res
+
+
 def layout_nested(planes, n_coarse, keep_index, hole_index, hole_points, fine_nodes, fine_row0):
     """Point-list planes [P, 4, Npoints] of a nested grid (kept coarse | fine | origin, grid_cartesian.py:71-91) ->
     (coarse records [P, n_coarse+1, 4], fine records [P, n_fine+1, 4]) FP32, the dropped coarse points filled by

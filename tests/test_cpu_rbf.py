@@ -1,0 +1,71 @@
+"""Pins the oracle's restatement of the reference's own spatial interpolation (gizmo_interface.py:651-717:
+cKDTree.query(nclose) + rbf.interpolate.RBFInterpolant(basis=phs3, order=5)).  The `rbf` package (T. Hines) is not in
+this image; scipy.interpolate.RBFInterpolator — the same author's port of it into scipy — with kernel='cubic' (r^3)
+and degree=5 is the same interpolant, and cKDTree is the reference's own neighbour search."""
+import numpy as np
+import pytest
+
+import oracle
+
+
+def lattice(n=12, half=0.06, origin=(8.0, 0.1, -0.2)):
+    ax = np.linspace(-half, half, n)
+    o = np.asarray(origin)
+    g = np.stack(np.meshgrid(ax + o[0], ax + o[1], ax + o[2], indexing="ij"), -1).reshape(-1, 3)
+    return (ax, ax, ax), o, np.concatenate([g, o[None]])
+
+
+def smooth_fields(pts):
+    x, y, z = (pts - pts[-1]).T * 20.0
+    return np.stack([np.sin(x) + y * z, np.cos(y) * x, x * x - z + 0.3 * y ** 3, np.exp(0.5 * x) - y])
+
+
+def test_rbf_oracle_matches_scipy_rbfinterpolator_and_ckdtree():
+    from scipy.interpolate import RBFInterpolator
+    from scipy.spatial import cKDTree
+    nodes, o, pts = lattice()
+    f = smooth_fields(pts)
+    rng = np.random.default_rng(4)
+    p = o + rng.uniform(-0.012, 0.012, (12, 3))
+    res = oracle.rbf_interp(nodes, o, f, p[:, 0], p[:, 1], p[:, 2], want_neighbors=True)
+    # the reference's neighbour search (gizmo_interface.py:654,664)
+    _, ids = cKDTree(pts).query(p, 150)
+    assert np.array_equal(np.sort(ids, axis=1), np.sort(res["neighbors"].T, axis=1))
+    for c in range(4):
+        ref = RBFInterpolator(pts, f[c], neighbors=150, kernel="cubic", degree=5)(p)
+        assert np.allclose(res["out"][c], ref, rtol=1e-9, atol=1e-11)
+    # other odd polyharmonic splines of options.py:178-246 and a lower order
+    res5 = oracle.rbf_interp(nodes, o, f[:1], p[:3, 0], p[:3, 1], p[:3, 2], nclose=80, order=3, phs=5)
+    ref5 = RBFInterpolator(pts, f[0], neighbors=80, kernel="quintic", degree=3)(p[:3])
+    # scipy's quintic kernel is -r^5: the interpolant is the same, only the sign of the weights differs
+    assert np.allclose(res5["out"][0], ref5, rtol=1e-8, atol=1e-10)
+
+
+def test_rbf_reproduces_polynomials_up_to_its_order_and_their_gradients():
+    nodes, o, pts = lattice()
+    x, y, z = (pts - o).T * 10.0
+    f = np.stack([1.0 + x - 2 * y + 0.5 * z, x * y * z - y ** 2, x ** 5 - 3 * x * y ** 3 * z + z ** 4, x ** 2 * z ** 3])
+    p = o + np.array([[0.003, -0.004, 0.0012], [0.011, 0.002, -0.007]])
+    res = oracle.rbf_interp(nodes, o, f, p[:, 0], p[:, 1], p[:, 2], want_tensor=True)
+    X, Y, Z = (p - o).T * 10.0
+    exact = np.stack([1.0 + X - 2 * Y + 0.5 * Z, X * Y * Z - Y ** 2, X ** 5 - 3 * X * Y ** 3 * Z + Z ** 4, X ** 2 * Z ** 3])
+    assert np.allclose(res["out"], exact, rtol=0, atol=1e-9)
+    gx = 10.0 * np.stack([np.ones_like(X), Y * Z, 5 * X ** 4 - 3 * Y ** 3 * Z, 2 * X * Z ** 3])
+    gz = 10.0 * np.stack([0.5 * np.ones_like(X), X * Y, -3 * X * Y ** 3 + 4 * Z ** 3, 3 * X ** 2 * Z ** 2])
+    assert np.allclose(res["tensor"][0], gx, rtol=0, atol=1e-6)
+    assert np.allclose(res["tensor"][2], gz, rtol=0, atol=1e-6)
+
+
+def test_rbf_neighbour_order_and_ties():
+    nodes, o, pts = lattice(n=8, half=0.035)
+    f = smooth_fields(pts)[:1]
+    # a star exactly on the grid origin: the origin row is its nearest neighbour (distance 0), then shells of equidistant
+    # lattice nodes, ordered by point index inside a shell
+    res = oracle.rbf_interp(nodes, o, f, [o[0]], [o[1]], [o[2]], nclose=100, want_neighbors=True)
+    nb = res["neighbors"][:, 0]
+    assert nb[0] == len(pts) - 1
+    d = np.linalg.norm(pts[nb] - o, axis=1)
+    assert np.all(np.diff(d) >= -1e-15)
+    shell = nb[1:9]
+    assert np.all(np.diff(shell) > 0) and np.allclose(d[1:9], d[1])
+    assert res["out"][0, 0] == pytest.approx(f[0, -1], abs=1e-12)  # interpolation: exact at a data point
