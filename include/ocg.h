@@ -193,7 +193,8 @@ int ocg_grid_interp_slot(ocg_ctx* ctx, const ocg_grid_desc* coarse, const ocg_gr
  *   (grid_cartesian.py:66-67) takes part in the neighbour search (0 when it duplicates a lattice node).
  * tensor_out_dev: fp64 [3][n_comp][n_star] or NULL — d out_c / d x_i (T[i][j] of gizmo_interface.py:719-756 for c = j).
  * status_out_dev: int32 [n_star] or NULL — 0 ok; bit 0 neighbour window truncated (star far outside the grid),
- *   bit 1 refinement not converged (ill-conditioned stencil, e.g. clipped by the grid edge), bit 2 zero pivot.
+ *   bit 1 refinement not converged (ill-conditioned stencil, e.g. clipped by the grid edge), bit 2 zero pivot;
+ *   bits 8-15: refinement iterations used (status & 0xff == 0 means a good result).
  * neighbors_out_dev: int64 [nclose][n_star] or NULL — point-list indices of the neighbours, nearest first, ties by
  *   index.  Single-level grid only.                                                                              */
 int ocg_grid_interp_rbf(ocg_ctx* ctx, const ocg_grid_desc* grid, const double* field_dev, int32_t n_comp,

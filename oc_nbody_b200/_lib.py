@@ -78,6 +78,7 @@ def load_library():
     L.ocg_self_gravity_hermite.argtypes = [vp, vp, vp, vp, i64, vp, i32, dbl, dbl, dbl, i64, i64, vp, vp, vp, vp]
     L.ocg_hermite_predict.argtypes = [vp, vp, vp, vp, vp, i64, dbl, dbl, vp, vp, vp]
     L.ocg_hermite_correct.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, dbl, dbl, dbl, vp, vp]
+    L.ocg_debug_rbf_phase_cycles.argtypes = [ctypes.POINTER(ctypes.c_double)]
     L.ocg_debug_set_hermite_variant.argtypes = [ctypes.c_int]
     L.ocg_debug_hermite_variant_name.restype = ctypes.c_char_p
     L.ocg_debug_hermite_variant_name.argtypes = [ctypes.c_int]

@@ -25,9 +25,10 @@
 #define RBF_NMONO_MAX 56
 #define RBF_NRHS_MAX 4
 #define RBF_THREADS 256
-#define RBF_SLOTS 7    /* ceil(RBF_NMAX / 32): rows per lane in the register-resident triangular solves */
 #define RBF_MAXIT 12
 #define RBF_CAND_MAX 4097 /* 16^3 lattice nodes + the origin row */
+#define RBF_NPHASE 6
+#define RBF_LDA 207 /* column stride of the factor matrix: odd, so rows and columns are both bank-conflict free */
 
 struct RbfParams {
   int n[3];
@@ -36,7 +37,7 @@ struct RbfParams {
   const double* origin;   // [n_cluster][3]
   const double* field;    // [n_comp][n_cluster][n_node]
   long long comp_stride;  // n_cluster * n_node
-  int n_comp, nclose, nmono, phs, include_origin, want_tensor;
+  int n_comp, nclose, nmono, order, phs, include_origin, want_tensor;
   const double *sx, *sy, *sz;
   const int* scl;
   long long n_star;
@@ -46,6 +47,9 @@ struct RbfParams {
   long long* nb_out;  // [nclose][n_star] neighbour point indices (nullable)
   unsigned char pw[RBF_NMONO_MAX][3];
 };
+
+// cycles spent per phase by thread 0 of every CTA (select, assemble, factorise, residual, solve, output); debug only
+__device__ unsigned long long g_rbf_cycles[RBF_NPHASE];
 
 __device__ __forceinline__ int rbf_find_cell(const double* __restrict__ node, int n, double o, double x) {
   // searchsorted(node + o, x, side='right') - 1 clamped to [0, n-2] (the rule of K3)
@@ -68,54 +72,60 @@ __device__ __forceinline__ double rbf_phi(double r2, int phs) {
   return v;
 }
 
-__device__ __forceinline__ double rbf_mono(const double* __restrict__ Y, int ld, int m, const unsigned char* pw) {
-  double v = 1.0;
-  const double x = Y[m], y = Y[ld + m], z = Y[2 * ld + m];
-  for (int a = 0; a < pw[0]; ++a) v *= x;
-  for (int a = 0; a < pw[1]; ++a) v *= y;
-  for (int a = 0; a < pw[2]; ++a) v *= z;
-  return v;
+// Entries of the saddle-point matrix in FP64.  Y [3][ncl] scaled coordinates, PT [3][order+1][ncl] their powers.
+__device__ __forceinline__ double rbf_k(int i, int j, int ncl, const double* __restrict__ Y, int phs) {
+  const double dx = Y[i] - Y[j], dy = Y[ncl + i] - Y[ncl + j], dz = Y[2 * ncl + i] - Y[2 * ncl + j];
+  return rbf_phi(dx * dx + dy * dy + dz * dz, phs);
 }
-
-// entry (i, j) of the saddle-point matrix in FP64
-__device__ __forceinline__ double rbf_entry(int i, int j, int ncl, const double* __restrict__ Y, const RbfParams& p) {
-  if (i < ncl && j < ncl) {
-    const double dx = Y[i] - Y[j], dy = Y[RBF_NMAX + i] - Y[RBF_NMAX + j], dz = Y[2 * RBF_NMAX + i] - Y[2 * RBF_NMAX + j];
-    return rbf_phi(dx * dx + dy * dy + dz * dz, p.phs);
-  }
-  if (i < ncl) return rbf_mono(Y, RBF_NMAX, i, p.pw[j - ncl]);
-  if (j < ncl) return rbf_mono(Y, RBF_NMAX, j, p.pw[i - ncl]);
-  return 0.0;
+__device__ __forceinline__ double rbf_p(int m, int k, int ncl, int np1, const double* __restrict__ PT, const RbfParams& p) {
+  const unsigned char* pw = p.pw[k];
+  return PT[(0 * np1 + pw[0]) * ncl + m] * PT[(1 * np1 + pw[1]) * ncl + m] * PT[(2 * np1 + pw[2]) * ncl + m];
 }
 
 __global__ void __launch_bounds__(RBF_THREADS, 1) rbf_interp_kernel(const RbfParams p) {
   extern __shared__ __align__(16) unsigned char smem[];
-  const int ncl = p.nclose, N = p.nclose + p.nmono;
-  float* A = reinterpret_cast<float*>(smem);                 // [N][N] column-major; aliased by the candidate distances
+  const int ncl = p.nclose, N = p.nclose + p.nmono, np1 = p.order + 1;
+  float* A = reinterpret_cast<float*>(smem);                 // [N][RBF_LDA] column-major; aliased by the candidate distances
   double* cand = reinterpret_cast<double*>(smem);            // [<= RBF_CAND_MAX]
-  unsigned char* q = smem + sizeof(float) * RBF_NMAX * RBF_NMAX;
-  double* Y = reinterpret_cast<double*>(q);                  // [3][RBF_NMAX] scaled coordinates relative to the star
-  q += sizeof(double) * 3 * RBF_NMAX;
-  double* B = reinterpret_cast<double*>(q);                  // [RBF_NRHS_MAX][RBF_NMAX] right-hand sides
-  q += sizeof(double) * RBF_NRHS_MAX * RBF_NMAX;
+  size_t a_bytes = sizeof(float) * (size_t)RBF_LDA * N;
+  if (a_bytes < sizeof(double) * RBF_CAND_MAX) a_bytes = sizeof(double) * RBF_CAND_MAX;
+  unsigned char* q = smem + ((a_bytes + 15) / 16) * 16;
+  double* Y = reinterpret_cast<double*>(q);                  // [3][ncl] scaled coordinates relative to the star
+  q += sizeof(double) * 3 * ncl;
+  double* PT = reinterpret_cast<double*>(q);                 // [3][order+1][ncl] powers of the coordinates
+  q += sizeof(double) * 3 * np1 * ncl;
+  double* B = reinterpret_cast<double*>(q);                  // [RBF_NRHS_MAX][N] right-hand sides
+  q += sizeof(double) * RBF_NRHS_MAX * N;
   double* U = reinterpret_cast<double*>(q);                  // solutions
-  q += sizeof(double) * RBF_NRHS_MAX * RBF_NMAX;
+  q += sizeof(double) * RBF_NRHS_MAX * N;
   double* R = reinterpret_cast<double*>(q);                  // residuals
-  q += sizeof(double) * RBF_NRHS_MAX * RBF_NMAX;
-  float* RP = reinterpret_cast<float*>(q);                   // reciprocal pivots
-  q += sizeof(float) * RBF_NMAX;
-  int* nbc = reinterpret_cast<int*>(q);                      // candidate ordinal of the m-th neighbour
-  q += sizeof(int) * RBF_NMAX;
-  int* perm = reinterpret_cast<int*>(q);                     // row permutation of the factorisation
-  q += sizeof(int) * RBF_NMAX;
+  q += sizeof(double) * RBF_NRHS_MAX * N;
   long long* nb = reinterpret_cast<long long*>(q);           // point index of the m-th neighbour (within its cluster)
-  q += sizeof(long long) * RBF_NMAX;
-  __shared__ int s_lo[3], s_cnt[3], s_cell[3], s_piv, s_flag, s_conv[RBF_NRHS_MAX], s_C;
-  __shared__ double s_p[3], s_o[3], s_h, s_r2max;
+  q += sizeof(long long) * ncl;
+  float* ZF = reinterpret_cast<float*>(q);                   // corrections (FP32 solves)
+  q += sizeof(float) * RBF_NRHS_MAX * N;
+  float* ZS = reinterpret_cast<float*>(q);                   // ... of the current block, scaled by the reciprocal pivots
+  q += sizeof(float) * RBF_NRHS_MAX * N;
+  float* RP = reinterpret_cast<float*>(q);                   // reciprocal pivots
+  q += sizeof(float) * N;
+  int* nbc = reinterpret_cast<int*>(q);                      // candidate ordinal of the m-th neighbour
+  q += sizeof(int) * ncl;
+  int* perm = reinterpret_cast<int*>(q);                     // row permutation of the factorisation
+  __shared__ int s_lo[3], s_cnt[3], s_cell[3], s_flag, s_conv[RBF_NRHS_MAX], s_C, s_wbi[RBF_THREADS / 32];
+  __shared__ float s_wbest[RBF_THREADS / 32];
+  __shared__ double s_p[3], s_o[3], s_h, s_r2max, s_zprev[RBF_NRHS_MAX];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nrhs = p.want_tensor ? 4 : 1;
   const long long n_node = (long long)p.n[0] * p.n[1] * p.n[2] + 1;
+  long long t_phase = clock64();
+  auto phase_done = [&](int which) {
+    if (tid == 0) {
+      const long long t = clock64();
+      atomicAdd(&g_rbf_cycles[which], (unsigned long long)(t - t_phase));
+      t_phase = t;
+    }
+  };
 
   for (long long s = blockIdx.x; s < p.n_star; s += gridDim.x) {
     const int cl = p.scl ? p.scl[s] : 0;
@@ -175,7 +185,7 @@ __global__ void __launch_bounds__(RBF_THREADS, 1) rbf_interp_kernel(const RbfPar
       }
       __syncthreads();
       // sufficient iff no excluded lattice node can be as close as the nclose-th neighbour
-      bool ok = true, grown = false;
+      bool ok = true;
       for (int d = 0; d < 3; ++d) {
         if (s_lo[d] > 0) {
           const double b = s_p[d] - (p.node[d][s_lo[d] - 1] + s_o[d]);
@@ -185,69 +195,90 @@ __global__ void __launch_bounds__(RBF_THREADS, 1) rbf_interp_kernel(const RbfPar
           const double b = (p.node[d][s_lo[d] + s_cnt[d]] + s_o[d]) - s_p[d];
           ok = ok && (b > 0.0 && b * b > s_r2max);
         }
-        grown = grown || s_cnt[d] < p.n[d];
       }
-      if (ok || !grown) break;
+      if (ok) break;
       if (W >= 16) {
         status |= 1;  // stencil truncated: the star is too far outside the grid for a 16-node window
         break;
       }
       __syncthreads();
     }
-    // coordinates of the neighbours, shifted to the star and scaled by the spacing
+    // coordinates of the neighbours, shifted to the star and scaled by the spacing, and their powers
     {
       const int cy = s_cnt[1], cz = s_cnt[2], Clat = s_cnt[0] * cy * cz;
       for (int m = tid; m < ncl; m += RBF_THREADS) {
         const int c = nbc[m];
-        double qx, qy, qz;
+        double qd[3];
         long long gi;
         if (c < Clat) {
           const int ix = s_lo[0] + c / (cy * cz), iy = s_lo[1] + (c / cz) % cy, iz = s_lo[2] + c % cz;
-          qx = __dadd_rn(p.node[0][ix], s_o[0]), qy = __dadd_rn(p.node[1][iy], s_o[1]), qz = __dadd_rn(p.node[2][iz], s_o[2]);
+          qd[0] = __dadd_rn(p.node[0][ix], s_o[0]), qd[1] = __dadd_rn(p.node[1][iy], s_o[1]), qd[2] = __dadd_rn(p.node[2][iz], s_o[2]);
           gi = ((long long)ix * p.n[1] + iy) * p.n[2] + iz;
         } else {
-          qx = s_o[0], qy = s_o[1], qz = s_o[2];
+          qd[0] = s_o[0], qd[1] = s_o[1], qd[2] = s_o[2];
           gi = n_node - 1;
         }
         nb[m] = gi;
         if (p.nb_out) p.nb_out[(long long)m * p.n_star + s] = gi;
-        Y[m] = __ddiv_rn(__dadd_rn(qx, -s_p[0]), s_h);
-        Y[RBF_NMAX + m] = __ddiv_rn(__dadd_rn(qy, -s_p[1]), s_h);
-        Y[2 * RBF_NMAX + m] = __ddiv_rn(__dadd_rn(qz, -s_p[2]), s_h);
+        for (int d = 0; d < 3; ++d) {
+          const double y = __ddiv_rn(__dadd_rn(qd[d], -s_p[d]), s_h);
+          Y[d * ncl + m] = y;
+          double v = 1.0;
+          for (int a = 0; a < np1; ++a) {
+            PT[(d * np1 + a) * ncl + m] = v;
+            v *= y;
+          }
+        }
       }
     }
     __syncthreads();  // the candidate distances (aliased by A) are dead from here on
+    phase_done(0);
 
     // ---- 2. assemble (FP64 -> FP32) and factorise ----------------------------------------------------------
-    for (int e = tid; e < N * N; e += RBF_THREADS) {
-      const int j = e / N, i = e - j * N;
-      A[e] = (float)rbf_entry(i, j, ncl, Y, p);
+    if (tid < ncl) {  // row of a data point: K | P
+#pragma unroll 4
+      for (int j = 0; j < ncl; ++j) A[j * RBF_LDA + tid] = (float)rbf_k(tid, j, ncl, Y, p.phs);
+#pragma unroll 4
+      for (int k = 0; k < p.nmono; ++k) A[(ncl + k) * RBF_LDA + tid] = (float)rbf_p(tid, k, ncl, np1, PT, p);
+    } else if (tid < N) {  // row of a monomial: P' | 0
+#pragma unroll 4
+      for (int j = 0; j < ncl; ++j) A[j * RBF_LDA + tid] = (float)rbf_p(j, tid - ncl, ncl, np1, PT, p);
+      for (int k = 0; k < p.nmono; ++k) A[(ncl + k) * RBF_LDA + tid] = 0.f;
     }
     for (int i = tid; i < N; i += RBF_THREADS) perm[i] = i;
     __syncthreads();
-    if (warp == 0) {  // pivot of column 0
+    phase_done(1);
+    {  // pivot candidates of column 0, one per warp
       float best = -1.f;
       int bi = 0;
-      for (int i = lane; i < N; i += 32) {
-        const float v = fabsf(A[i]);
-        if (v > best) best = v, bi = i;
-      }
+      if (tid < N) best = fabsf(A[tid]), bi = tid;
       for (int o = 16; o > 0; o >>= 1) {
         const float ov = __shfl_xor_sync(0xffffffffu, best, o);
         const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
         if (ov > best || (ov == best && oi < bi)) best = ov, bi = oi;
       }
-      if (lane == 0) s_piv = bi;
+      if (lane == 0) s_wbest[warp] = best, s_wbi[warp] = bi;
     }
     if (tid == 0) s_flag = 0;
+    // Right-looking LU with partial pivoting; thread `tid` owns row `tid`: its multiplier stays in a register, the row
+    // of U is a broadcast load, and column k+1's pivot candidates fall out of the update itself.
     for (int k = 0; k < N; ++k) {
-      __syncthreads();  // pivot row of column k known; trailing update of step k-1 complete
-      const int pv = s_piv;
+      __syncthreads();  // trailing update of step k-1 complete, per-warp pivot candidates of column k visible
+      int pv = k;
+      {
+        float best = -1.f;
+#pragma unroll
+        for (int w = 0; w < RBF_THREADS / 32; ++w) {
+          const float ov = s_wbest[w];
+          const int oi = s_wbi[w];
+          if (ov > best || (ov == best && oi < pv)) best = ov, pv = oi;
+        }
+      }
       if (pv != k) {
-        for (int j = tid; j < N; j += RBF_THREADS) {
-          const float t = A[j * N + k];
-          A[j * N + k] = A[j * N + pv];
-          A[j * N + pv] = t;
+        if (tid < N) {
+          const float t = A[tid * RBF_LDA + k];
+          A[tid * RBF_LDA + k] = A[tid * RBF_LDA + pv];
+          A[tid * RBF_LDA + pv] = t;
         }
         if (tid == 0) {
           const int t = perm[k];
@@ -256,50 +287,53 @@ __global__ void __launch_bounds__(RBF_THREADS, 1) rbf_interp_kernel(const RbfPar
         }
       }
       __syncthreads();
-      const float piv = A[k * N + k];
+      const float piv = A[k * RBF_LDA + k];
       float rp = 1.0f / piv;
       if (!(fabsf(piv) > 1e-30f)) rp = 0.f;
       if (tid == 0) {
         RP[k] = rp;
         if (rp == 0.f) s_flag = 1;
       }
-      // A_ij -= L_ik U_kj with L_ik = A[k][i] * rp (column k keeps the unscaled values), 4 columns per pass
-      const float* __restrict__ lk = A + k * N;
-      for (int j0 = k + 1 + 4 * warp; j0 < N; j0 += 4 * (RBF_THREADS / 32)) {
-        float u[4];
-#pragma unroll
-        for (int c = 0; c < 4; ++c) u[c] = (j0 + c < N) ? A[(j0 + c) * N + k] * rp : 0.f;
-        float best = -1.f;
-        int bi = k + 1;
-        for (int i = k + 1 + lane; i < N; i += 32) {
-          const float l = lk[i];
-#pragma unroll
-          for (int c = 0; c < 4; ++c)
-            if (j0 + c < N) {
-              const float v = fmaf(-l, u[c], A[(j0 + c) * N + i]);
-              A[(j0 + c) * N + i] = v;
-              if (c == 0 && j0 == k + 1 && fabsf(v) > best) best = fabsf(v), bi = i;
-            }
+      // A_ij -= L_ik U_kj, L_ik = A[k][i] * rp (column k keeps the unscaled values)
+      float best = -1.f;
+      int bi = k + 1;
+      if (tid > k && tid < N) {
+        const float l = A[k * RBF_LDA + tid] * rp;
+        float* __restrict__ row = A + tid;
+        const float* __restrict__ urow = A + k;
+        int j = k + 1;
+        {
+          const float v = fmaf(-l, urow[j * RBF_LDA], row[j * RBF_LDA]);
+          row[j * RBF_LDA] = v;
+          best = fabsf(v), bi = tid;
+          ++j;
         }
-        if (j0 == k + 1) {  // this warp has just finished column k+1: choose its pivot
-          for (int o = 16; o > 0; o >>= 1) {
-            const float ov = __shfl_xor_sync(0xffffffffu, best, o);
-            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-            if (ov > best || (ov == best && oi < bi)) best = ov, bi = oi;
-          }
-          if (lane == 0) s_piv = bi;
+        for (; j + 8 <= N; j += 8) {
+          float a[8], u[8];
+#pragma unroll
+          for (int c = 0; c < 8; ++c) a[c] = row[(j + c) * RBF_LDA], u[c] = urow[(j + c) * RBF_LDA];
+#pragma unroll
+          for (int c = 0; c < 8; ++c) row[(j + c) * RBF_LDA] = fmaf(-l, u[c], a[c]);
         }
+        for (; j < N; ++j) row[j * RBF_LDA] = fmaf(-l, urow[j * RBF_LDA], row[j * RBF_LDA]);
       }
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ov > best || (ov == best && oi < bi)) best = ov, bi = oi;
+      }
+      if (lane == 0) s_wbest[warp] = best, s_wbi[warp] = bi;
     }
     __syncthreads();
     if (s_flag) status |= 4;
+    phase_done(2);
 
     // ---- 3. right-hand sides and FP64 iterative refinement -------------------------------------------------
     for (int e = tid; e < nrhs * N; e += RBF_THREADS) {
       const int r = e / N, i = e - r * N;
       double v;
       if (i < ncl) {
-        const double x = Y[i], y = Y[RBF_NMAX + i], z = Y[2 * RBF_NMAX + i];
+        const double x = Y[i], y = Y[ncl + i], z = Y[2 * ncl + i];
         const double r2 = x * x + y * y + z * z;
         if (r == 0) v = rbf_phi(r2, p.phs);
         else {
@@ -314,109 +348,146 @@ __global__ void __launch_bounds__(RBF_THREADS, 1) rbf_interp_kernel(const RbfPar
         if (r == 0) v = (pw[0] + pw[1] + pw[2] == 0) ? 1.0 : 0.0;
         else v = (pw[r - 1] == 1 && pw[0] + pw[1] + pw[2] == 1) ? 1.0 : 0.0;
       }
-      B[r * RBF_NMAX + i] = v;
-      U[r * RBF_NMAX + i] = 0.0;
-      R[r * RBF_NMAX + i] = v;
+      B[r * N + i] = v;
+      U[r * N + i] = 0.0;
+      R[r * N + i] = v;
     }
-    if (tid < RBF_NRHS_MAX) s_conv[tid] = 0;
+    if (tid < RBF_NRHS_MAX) s_conv[tid] = 0, s_zprev[tid] = 0.0;
     __syncthreads();
-    double prev_z = 0.0;
+    int iters = 0;
     for (int it = 0; it < RBF_MAXIT; ++it) {
+      iters = it + 1;
       if (it > 0) {
         // R = B - A U in FP64, entries regenerated from the coordinates (row i per thread, all right-hand sides)
         if (tid < N) {
           double acc[RBF_NRHS_MAX];
 #pragma unroll
           for (int r = 0; r < RBF_NRHS_MAX; ++r) acc[r] = 0.0;
-          for (int j = 0; j < N; ++j) {
-            const double e = rbf_entry(tid, j, ncl, Y, p);
+          if (tid < ncl) {
+#pragma unroll 4
+            for (int j = 0; j < ncl; ++j) {
+              const double e = rbf_k(tid, j, ncl, Y, p.phs);
 #pragma unroll
-            for (int r = 0; r < RBF_NRHS_MAX; ++r)
-              if (r < nrhs) acc[r] += e * U[r * RBF_NMAX + j];
+              for (int r = 0; r < RBF_NRHS_MAX; ++r)
+                if (r < nrhs) acc[r] += e * U[r * N + j];
+            }
+#pragma unroll 4
+            for (int k = 0; k < p.nmono; ++k) {
+              const double e = rbf_p(tid, k, ncl, np1, PT, p);
+#pragma unroll
+              for (int r = 0; r < RBF_NRHS_MAX; ++r)
+                if (r < nrhs) acc[r] += e * U[r * N + ncl + k];
+            }
+          } else {
+#pragma unroll 4
+            for (int j = 0; j < ncl; ++j) {
+              const double e = rbf_p(j, tid - ncl, ncl, np1, PT, p);
+#pragma unroll
+              for (int r = 0; r < RBF_NRHS_MAX; ++r)
+                if (r < nrhs) acc[r] += e * U[r * N + j];
+            }
           }
 #pragma unroll
           for (int r = 0; r < RBF_NRHS_MAX; ++r)
-            if (r < nrhs) R[r * RBF_NMAX + tid] = B[r * RBF_NMAX + tid] - acc[r];
+            if (r < nrhs) R[r * N + tid] = B[r * N + tid] - acc[r];
+        }
+        __syncthreads();
+        phase_done(3);
+      }
+      // z = (LU)^-1 P R through the FP32 factors: 32-column blocks, the triangular diagonal block by one warp per
+      // right-hand side (values in registers, one shuffle per column), the rows outside the block by all threads
+      for (int e = tid; e < nrhs * N; e += RBF_THREADS) {
+        const int r = e / N, i = e - r * N;
+        ZF[e] = (float)R[r * N + perm[i]];
+      }
+      __syncthreads();
+      for (int k0 = 0; k0 < N; k0 += 32) {  // forward, unit lower: L_ik = A[k][i] * RP[k]
+        const int kw = N - k0 < 32 ? N - k0 : 32;
+        if (warp < nrhs) {
+          float z = lane < kw ? ZF[warp * N + k0 + lane] : 0.f;
+          float lc[32];  // this lane's row of the diagonal block, fetched before the dependent chain starts
+#pragma unroll
+          for (int c = 0; c < 32; ++c) lc[c] = (c < kw && lane > c && lane < kw) ? A[(k0 + c) * RBF_LDA + k0 + lane] * RP[k0 + c] : 0.f;
+#pragma unroll
+          for (int c = 0; c < 32; ++c) z = fmaf(-lc[c], __shfl_sync(0xffffffffu, z, c), z);
+          if (lane < kw) ZF[warp * N + k0 + lane] = z, ZS[warp * N + k0 + lane] = z * RP[k0 + lane];
+        }
+        __syncthreads();
+        const int m = N - k0 - kw;
+        for (int e = tid; e < nrhs * m; e += RBF_THREADS) {
+          const int r = e / m, i = k0 + kw + (e - r * m);
+          float acc = 0.f;
+          for (int c = 0; c < kw; ++c) acc = fmaf(A[(k0 + c) * RBF_LDA + i], ZS[r * N + k0 + c], acc);
+          ZF[r * N + i] -= acc;
         }
         __syncthreads();
       }
-      if (warp < nrhs && !s_conv[warp]) {
-        // z = (LU)^-1 P R for right-hand side `warp`; z lives in registers, rows i = slot*32 + lane
-        float z[RBF_SLOTS];
+      for (int k0 = ((N - 1) / 32) * 32; k0 >= 0; k0 -= 32) {  // backward, upper: U_kk = 1 / RP[k], U_ik = A[k][i]
+        const int kw = N - k0 < 32 ? N - k0 : 32;
+        if (warp < nrhs) {
+          float z = lane < kw ? ZF[warp * N + k0 + lane] : 0.f;
+          float uc[32];
+          const float rpl = lane < kw ? RP[k0 + lane] : 0.f;
 #pragma unroll
-        for (int t = 0; t < RBF_SLOTS; ++t) {
-          const int i = t * 32 + lane;
-          z[t] = i < N ? (float)R[warp * RBF_NMAX + perm[i]] : 0.f;
-        }
-        // forward: unit lower, column-oriented
+          for (int c = 0; c < 32; ++c) uc[c] = (c < kw && lane < c) ? A[(k0 + c) * RBF_LDA + k0 + lane] : 0.f;
 #pragma unroll
-        for (int kt = 0; kt < RBF_SLOTS; ++kt) {
-          for (int src = 0; src < 32; ++src) {
-            const int k = kt * 32 + src;
-            if (k >= N) break;
-            const float zk = __shfl_sync(0xffffffffu, z[kt], src) * RP[k];
-            const float* __restrict__ col = A + k * N;
-#pragma unroll
-            for (int t = 0; t < RBF_SLOTS; ++t) {
-              const int i = t * 32 + lane;
-              if (t >= kt && i > k && i < N) z[t] = fmaf(-col[i], zk, z[t]);
-            }
+          for (int c = 31; c >= 0; --c) {
+            if (lane == c) z *= rpl;  // z_c = z'_c / U_cc
+            z = fmaf(-uc[c], __shfl_sync(0xffffffffu, z, c), z);
           }
+          if (lane < kw) ZF[warp * N + k0 + lane] = z;
         }
-        // backward: upper, column-oriented
-#pragma unroll
-        for (int kt = RBF_SLOTS - 1; kt >= 0; --kt) {
-          for (int src = 31; src >= 0; --src) {
-            const int k = kt * 32 + src;
-            if (k >= N) continue;
-            const float zk = __shfl_sync(0xffffffffu, z[kt], src) * RP[k];
-            if (lane == src) z[kt] = zk;
-            const float* __restrict__ col = A + k * N;
-#pragma unroll
-            for (int t = 0; t < RBF_SLOTS; ++t) {
-              const int i = t * 32 + lane;
-              if (t <= kt && i < k) z[t] = fmaf(-col[i], zk, z[t]);
-            }
-          }
+        __syncthreads();
+        for (int e = tid; e < nrhs * k0; e += RBF_THREADS) {
+          const int r = e / k0, i = e - r * k0;
+          float acc = 0.f;
+          for (int c = 0; c < kw; ++c) acc = fmaf(A[(k0 + c) * RBF_LDA + i], ZF[r * N + k0 + c], acc);
+          ZF[r * N + i] -= acc;
         }
+        __syncthreads();
+      }
+      if (warp < nrhs) {
         double zmax = 0.0, umax = 0.0;
-#pragma unroll
-        for (int t = 0; t < RBF_SLOTS; ++t) {
-          const int i = t * 32 + lane;
-          if (i < N) {
-            const double u = U[warp * RBF_NMAX + i] + (double)z[t];
-            U[warp * RBF_NMAX + i] = u;
-            zmax = fmax(zmax, fabs((double)z[t]));
-            umax = fmax(umax, fabs(u));
-          }
+        for (int i = lane; i < N; i += 32) {
+          const double z = (double)ZF[warp * N + i];
+          const double u = U[warp * N + i] + z;
+          U[warp * N + i] = u;
+          zmax = fmax(zmax, fabs(z));
+          umax = fmax(umax, fabs(u));
+          if (!(z == z)) zmax = z;
         }
         for (int o = 16; o > 0; o >>= 1) {
-          zmax = fmax(zmax, __shfl_xor_sync(0xffffffffu, zmax, o));
-          umax = fmax(umax, __shfl_xor_sync(0xffffffffu, umax, o));
+          const double oz = __shfl_xor_sync(0xffffffffu, zmax, o), ou = __shfl_xor_sync(0xffffffffu, umax, o);
+          zmax = (oz > zmax || !(oz == oz)) ? oz : zmax;
+          umax = fmax(umax, ou);
         }
-        // converged when the correction is below 1e-10 of the solution (the next correction would be ~1e-3 of that);
-        // a correction that stopped shrinking ends the iteration too (accepted if already small)
-        int conv = 0;
-        if (!(zmax == zmax) || !(umax == umax)) conv = 2;
-        else if (zmax <= 1e-10 * umax) conv = 1;
-        else if (it > 0 && zmax > 0.5 * prev_z) conv = zmax <= 1e-7 * umax ? 1 : 2;
-        prev_z = zmax;
-        if (lane == 0 && conv) s_conv[warp] = conv;
+        // converged when the correction is below 1e-10 of the solution (the next one would be ~1e-3 of that); a
+        // correction that stopped shrinking ends the iteration too (accepted if already small)
+        if (lane == 0) {
+          int conv = 0;
+          if (!(zmax == zmax) || !(umax == umax)) conv = 2;
+          else if (zmax <= 1e-10 * umax) conv = 1;
+          else if (it > 0 && zmax > 0.5 * s_zprev[warp]) conv = zmax <= 1e-7 * umax ? 1 : 2;
+          s_zprev[warp] = zmax;
+          s_conv[warp] = conv;
+        }
       }
       __syncthreads();
+      phase_done(4);
       bool done = true;
       for (int r = 0; r < nrhs; ++r) done = done && s_conv[r] != 0;
       if (done) break;
     }
     for (int r = 0; r < nrhs; ++r)
       if (s_conv[r] != 1) status |= 2;  // refinement did not converge (ill-conditioned stencil, e.g. clipped by the grid edge)
+    status |= iters << 8;
 
     // ---- 4. out_c = sum_m u_m field_c[id_m] ------------------------------------------------------------------
     for (int pair = warp; pair < nrhs * p.n_comp; pair += RBF_THREADS / 32) {
       const int r = pair / p.n_comp, c = pair - r * p.n_comp;
       const double* __restrict__ f = p.field + (long long)c * p.comp_stride + (long long)cl * n_node;
       double acc = 0.0;
-      for (int m = lane; m < ncl; m += 32) acc += U[r * RBF_NMAX + m] * f[nb[m]];
+      for (int m = lane; m < ncl; m += 32) acc += U[r * N + m] * f[nb[m]];
       for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
       if (lane == 0) {
         if (r == 0) p.out[(long long)c * p.n_star + s] = acc;
@@ -425,7 +496,25 @@ __global__ void __launch_bounds__(RBF_THREADS, 1) rbf_interp_kernel(const RbfPar
     }
     if (tid == 0 && p.status) p.status[s] = status;
     __syncthreads();
+    phase_done(5);
   }
+}
+
+static size_t rbf_smem_bytes(int N, int ncl, int np1) {
+  size_t a = sizeof(float) * (size_t)RBF_LDA * N;
+  if (a < sizeof(double) * RBF_CAND_MAX) a = sizeof(double) * RBF_CAND_MAX;
+  a = ((a + 15) / 16) * 16;
+  return a + sizeof(double) * 3 * ncl + sizeof(double) * 3 * np1 * ncl + 3 * sizeof(double) * RBF_NRHS_MAX * N +
+         sizeof(long long) * ncl + 2 * sizeof(float) * RBF_NRHS_MAX * N + sizeof(float) * N + sizeof(int) * ncl + sizeof(int) * N;
+}
+
+// cycles per phase summed over CTAs since the last call (select, assemble, factorise, residual, solve, output)
+extern "C" int ocg_debug_rbf_phase_cycles(double* out6) {
+  unsigned long long h[RBF_NPHASE], z[RBF_NPHASE] = {0, 0, 0, 0, 0, 0};
+  if (cudaMemcpyFromSymbol(h, g_rbf_cycles, sizeof(h)) != cudaSuccess) return -1;
+  if (cudaMemcpyToSymbol(g_rbf_cycles, z, sizeof(z)) != cudaSuccess) return -1;
+  for (int i = 0; i < RBF_NPHASE; ++i) out6[i] = (double)h[i];
+  return 0;
 }
 
 extern "C" int ocg_grid_interp_rbf(ocg_ctx* ctx, const ocg_grid_desc* grid, const double* field_dev, int32_t n_comp,
@@ -463,13 +552,15 @@ extern "C" int ocg_grid_interp_rbf(ocg_ctx* ctx, const ocg_grid_desc* grid, cons
     return ocg_fail(ctx, OCG_ERR_INVALID, "ocg_grid_interp_rbf: the grid has fewer than nclose = %d points", nclose);
   p.n_cluster = grid->n_cluster < 1 ? 1 : grid->n_cluster;
   p.origin = grid->origin_dev, p.field = field_dev, p.comp_stride = (long long)p.n_cluster * (n_lat + 1);
-  p.n_comp = n_comp, p.nclose = nclose, p.nmono = nm, p.phs = phs, p.include_origin = include_origin ? 1 : 0;
+  p.n_comp = n_comp, p.nclose = nclose, p.nmono = nm, p.order = order, p.phs = phs, p.include_origin = include_origin ? 1 : 0;
   p.want_tensor = tensor_out_dev ? 1 : 0;
   p.sx = star_x_dev, p.sy = star_y_dev, p.sz = star_z_dev, p.scl = star_cluster_dev, p.n_star = n_star;
   p.out = out_dev, p.tensor = tensor_out_dev, p.status = status_out_dev, p.nb_out = (long long*)neighbors_out_dev;
   OcgDeviceGuard g(ctx->device);
-  size_t smem = sizeof(float) * RBF_NMAX * RBF_NMAX + sizeof(double) * 3 * RBF_NMAX + 3 * sizeof(double) * RBF_NRHS_MAX * RBF_NMAX +
-                sizeof(float) * RBF_NMAX + 2 * sizeof(int) * RBF_NMAX + sizeof(long long) * RBF_NMAX;
+  const size_t smem = rbf_smem_bytes(nclose + nm, nclose, order + 1);
+  if (smem > 227 * 1024)
+    return ocg_fail(ctx, OCG_ERR_INVALID, "ocg_grid_interp_rbf: nclose = %d, order = %d need %zu bytes of shared memory", nclose,
+                    order, smem);
   OCG_CUDA(ctx, cudaFuncSetAttribute((const void*)rbf_interp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int grid_dim = (int)(n_star < ctx->sm_count ? n_star : ctx->sm_count);
   rbf_interp_kernel<<<grid_dim, RBF_THREADS, smem, (cudaStream_t)stream>>>(p);

@@ -2,6 +2,7 @@
 ms per kick and stars/s at the reference's N = 1 024 and at N = 16 384, with and without the tidal tensor, next to the
 same evaluation by scipy (cKDTree + RBFInterpolator, the reference's CPU mechanism) on a bounded sample.
 python tools/bench_rbf.py -> gpurun_out/bench_rbf.json"""
+import ctypes
 import json
 import os
 import sys
@@ -48,9 +49,18 @@ def main():
             def k7():
                 ctx.grid_interp_rbf((n, n, n), nodes, d_o, d_f, sx, sy, sz, None, res, tensor_out=t, status_out=st)
             med, best = timeit(k7, iters=5, warm=2)
+            cyc = (ctypes.c_double * 6)()
+            ctx.lib.ocg_debug_rbf_phase_cycles(cyc)
+            k7()
+            torch.cuda.synchronize()
+            ctx.lib.ocg_debug_rbf_phase_cycles(cyc)
+            tot = sum(cyc) or 1.0
             out["k7_rbf_%d_stars_%s" % (ns, name)] = dict(ms_median=med, ms_best=best, stars_per_s=ns / med * 1e3,
                                                           us_per_star_per_sm=med * 1e3 * ctx.sm_count / ns,
-                                                          status_nonzero=int((st != 0).sum().item()),
+                                                          status_nonzero=int(((st & 0xff) != 0).sum().item()),
+                                                          refinement_iterations_mean=float((st >> 8).double().mean().item()),
+                                                          phase_share=dict(zip(("select", "assemble", "factorise", "residual", "solve", "output"),
+                                                                               [round(c / tot, 4) for c in cyc])),
                                                           fp32_lu_flop_per_star=2.0 / 3.0 * 206 ** 3)
     # the reference's CPU mechanism on a sample: per star, kNN + 3 RBF interpolants (gizmo_interface.py:661-675, 698-704)
     from scipy.interpolate import RBFInterpolator
