@@ -194,11 +194,16 @@ int ocg_grid_interp_slot(ocg_ctx* ctx, const ocg_grid_desc* coarse, const ocg_gr
  * tensor_out_dev: fp64 [3][n_comp][n_star] or NULL — d out_c / d x_i (T[i][j] of gizmo_interface.py:719-756 for c = j).
  * status_out_dev: int32 [n_star] or NULL — 0 ok; bit 0 neighbour window truncated (star far outside the grid),
  *   bit 1 refinement not converged (ill-conditioned stencil, e.g. clipped by the grid edge), bit 2 zero pivot;
- *   bits 8-15: refinement iterations used (status & 0xff == 0 means a good result).
+ *   bit 3 see `embedded`; bits 8-15: refinement iterations used (status & 0xff == 0 means a good result).
  * neighbors_out_dev: int64 [nclose][n_star] or NULL — point-list indices of the neighbours, nearest first, ties by
- *   index.  Single-level grid only.                                                                              */
+ *   index.
+ * embedded: 0 for the single-level grid.  1: `grid` is the FINE lattice of the reference's nested grid
+ *   (grid_cartesian.py:34-53,71-91; field_dev then holds the fine rows + origin row of the point list).  Every kept
+ *   coarse point lies on or outside the fine box, so the neighbour set is exact whenever the nclose-th neighbour is
+ *   closer than the box surface; a star for which it is not gets status bit 3 (mixed-level stencil: not evaluated
+ *   faithfully).                                                                                                 */
 int ocg_grid_interp_rbf(ocg_ctx* ctx, const ocg_grid_desc* grid, const double* field_dev, int32_t n_comp,
-                        int32_t nclose, int32_t order, int32_t phs, int32_t include_origin,
+                        int32_t nclose, int32_t order, int32_t phs, int32_t include_origin, int32_t embedded,
                         const double* star_x_dev, const double* star_y_dev, const double* star_z_dev,
                         const int32_t* star_cluster_dev, int64_t n_star, double* out_dev,
                         double* tensor_out_dev, int32_t* status_out_dev, int64_t* neighbors_out_dev,

@@ -74,7 +74,7 @@ def load_library():
     L.ocg_grid_interp_slot.argtypes = [vp, ctypes.POINTER(_GridDesc), ctypes.POINTER(_GridDesc), vp, vp, i32, i32, vp, vp, vp, vp,
                                        i64, vp, vp, vp]
     L.ocg_self_gravity.argtypes = [vp, vp, vp, i64, vp, i32, dbl, dbl, i64, i64, vp, vp, vp]
-    L.ocg_grid_interp_rbf.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, vp, i64, vp, vp, vp, vp, vp]
+    L.ocg_grid_interp_rbf.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp, i64, vp, vp, vp, vp, vp]
     L.ocg_self_gravity_hermite.argtypes = [vp, vp, vp, vp, i64, vp, i32, dbl, dbl, dbl, i64, i64, vp, vp, vp, vp]
     L.ocg_hermite_predict.argtypes = [vp, vp, vp, vp, vp, i64, dbl, dbl, vp, vp, vp]
     L.ocg_hermite_correct.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, dbl, dbl, dbl, vp, vp]
@@ -256,12 +256,12 @@ class Context:
                  "ocg_grid_interp_nested")
 
     def grid_interp_rbf(self, n, nodes, origin, field, sx, sy, sz, star_cluster, out, nclose=150, order=5, phs=3,
-                        include_origin=True, tensor_out=None, status_out=None, neighbors_out=None):
+                        include_origin=True, tensor_out=None, status_out=None, neighbors_out=None, embedded=False):
         """K7: the reference's own spatial interpolation (kNN + polyharmonic-spline RBF, gizmo_interface.py:651-717).
         field fp64 [n_comp, n_cluster * n_node] (or [n_comp, n_node]); out [n_comp, n_star]."""
         dc = self._grid_desc(n, nodes, origin)
         self._ck(self.lib.ocg_grid_interp_rbf(self.h, ctypes.byref(dc), _dptr(field), int(field.shape[0]), int(nclose), int(order),
-                                              int(phs), 1 if include_origin else 0, _dptr(sx), _dptr(sy), _dptr(sz),
+                                              int(phs), 1 if include_origin else 0, 1 if embedded else 0, _dptr(sx), _dptr(sy), _dptr(sz),
                                               _dptr(star_cluster), sx.shape[0], _dptr(out), _dptr(tensor_out), _dptr(status_out),
                                               _dptr(neighbors_out), self._stream()), "ocg_grid_interp_rbf")
 

@@ -37,7 +37,7 @@ struct RbfParams {
   const double* origin;   // [n_cluster][3]
   const double* field;    // [n_comp][n_cluster][n_node]
   long long comp_stride;  // n_cluster * n_node
-  int n_comp, nclose, nmono, order, phs, include_origin, want_tensor;
+  int n_comp, nclose, nmono, order, phs, include_origin, want_tensor, embedded;
   const double *sx, *sy, *sz;
   const int* scl;
   long long n_star;
@@ -202,6 +202,17 @@ __global__ void __launch_bounds__(RBF_THREADS, 1) rbf_interp_kernel(const RbfPar
         break;
       }
       __syncthreads();
+    }
+    if (p.embedded) {
+      // the lattice is the fine level of the reference's nested grid: every kept coarse point lies on or outside the
+      // fine box, so the neighbours are all fine points iff the nclose-th one is closer than the box surface
+      bool inside = true;
+      for (int d = 0; d < 3; ++d) {
+        const double b0 = s_p[d] - (p.node[d][0] + s_o[d]), b1 = (p.node[d][p.n[d] - 1] + s_o[d]) - s_p[d];
+        const double b = b0 < b1 ? b0 : b1;
+        inside = inside && (b > 0.0 && b * b > s_r2max);
+      }
+      if (!inside) status |= 8;
     }
     // coordinates of the neighbours, shifted to the star and scaled by the spacing, and their powers
     {
@@ -518,7 +529,7 @@ extern "C" int ocg_debug_rbf_phase_cycles(double* out6) {
 }
 
 extern "C" int ocg_grid_interp_rbf(ocg_ctx* ctx, const ocg_grid_desc* grid, const double* field_dev, int32_t n_comp,
-                                   int32_t nclose, int32_t order, int32_t phs, int32_t include_origin,
+                                   int32_t nclose, int32_t order, int32_t phs, int32_t include_origin, int32_t embedded,
                                    const double* star_x_dev, const double* star_y_dev, const double* star_z_dev,
                                    const int32_t* star_cluster_dev, int64_t n_star, double* out_dev, double* tensor_out_dev,
                                    int32_t* status_out_dev, int64_t* neighbors_out_dev, void* stream) {
@@ -554,6 +565,7 @@ extern "C" int ocg_grid_interp_rbf(ocg_ctx* ctx, const ocg_grid_desc* grid, cons
   p.origin = grid->origin_dev, p.field = field_dev, p.comp_stride = (long long)p.n_cluster * (n_lat + 1);
   p.n_comp = n_comp, p.nclose = nclose, p.nmono = nm, p.order = order, p.phs = phs, p.include_origin = include_origin ? 1 : 0;
   p.want_tensor = tensor_out_dev ? 1 : 0;
+  p.embedded = embedded ? 1 : 0;
   p.sx = star_x_dev, p.sy = star_y_dev, p.sz = star_z_dev, p.scl = star_cluster_dev, p.n_star = n_star;
   p.out = out_dev, p.tensor = tensor_out_dev, p.status = status_out_dev, p.nb_out = (long long*)neighbors_out_dev;
   OcgDeviceGuard g(ctx->device);

@@ -78,8 +78,6 @@ class gizmo_field(object):
         if self.space_interpolation not in ("trilinear", "rbf"):
             raise ValueError("space_interpolation must be 'trilinear' or 'rbf'")
         if self.space_interpolation == "rbf":
-            if self.fine_grid:
-                raise NotImplementedError("space_interpolation='rbf' supports the single-level grid only")
             basis = getattr(self.basis, "__name__", None) or str(self.basis)  # a name or an rbf.basis object (options.py:178-246)
             if basis not in ("phs1", "phs3", "phs5", "phs7"):
                 raise NotImplementedError("space_interpolation='rbf' implements the odd polyharmonic splines phs1/3/5/7, not %r" % (basis,))
@@ -414,16 +412,22 @@ class gizmo_field(object):
 
     def _rbf_field_(self):
         """FP64 [4, n_node] device copy of the time-evaluated grid arrays (grid.evolved_acceleration_x/y/z and the
-        potential, gizmo_interface.py:618-620) that the RBF interpolant reads; refreshed when the model time changes."""
+        potential, gizmo_interface.py:618-620) that the RBF interpolant reads; refreshed when the model time changes.
+        Nested grid: the fine rows + origin row of the point list (see _interp_rbf_)."""
         import torch
         if getattr(self, "_rbf_cache", None) is None or self._rbf_cache[0] is not self._blend_():
             b = self._blend_()
             f = np.concatenate([b[0], b[1][None]], axis=0)
+            if self.grid.has_fine_grid:
+                f = f[:, self.grid.fine_row0:]
             self._rbf_cache = (b, torch.from_numpy(np.ascontiguousarray(f)).to(self._dev["device"]))
         return self._rbf_cache[1]
 
     def _interp_rbf_(self, sx, sy, sz, want_pot, want_tensor):
-        """K7: kNN(nclose) + RBF-PHS on the device; the last status vector is kept in self.rbf_status."""
+        """K7: kNN(nclose) + RBF-PHS on the device; the last status vector is kept in self.rbf_status (status & 0xff
+        == 0: good).  On the nested grid the search runs over the fine lattice + origin row: exact for every star whose
+        nclose-th neighbour is closer than the surface of the fine box (all kept coarse points lie on or outside it);
+        other stars are flagged with status bit 3."""
         import torch
         d, g = self._dev, self.grid
         n = sx.shape[0]
@@ -431,10 +435,11 @@ class gizmo_field(object):
         out = torch.empty((4, n), dtype=torch.float64, device=d["device"])
         tensor = torch.empty((3, 4, n), dtype=torch.float64, device=d["device"]) if want_tensor else None
         self.rbf_status = torch.empty(n, dtype=torch.int32, device=d["device"])
-        dup = all(len(a) % 2 == 1 and a[len(a) // 2] == 0.0 for a in g.nodes)  # the origin row duplicates a lattice node
-        self.ctx.grid_interp_rbf(g.shape, d["nodes"], d["origin"], f, sx, sy, sz, None, out, nclose=self.nclose,
+        shape, nodes_h, nodes_d = (g.fine_shape, g.fine_nodes, d["fine_nodes"]) if g.has_fine_grid else (g.shape, g.nodes, d["nodes"])
+        dup = all(len(a) % 2 == 1 and a[len(a) // 2] == 0.0 for a in nodes_h)  # the origin row duplicates a lattice node
+        self.ctx.grid_interp_rbf(shape, nodes_d, d["origin"], f, sx, sy, sz, None, out, nclose=self.nclose,
                                  order=self.order, phs=self._rbf_phs, include_origin=not dup, tensor_out=tensor,
-                                 status_out=self.rbf_status)
+                                 status_out=self.rbf_status, embedded=g.has_fine_grid)
         acc, pot = out[:3], (out[3] if want_pot else None)
         if want_tensor:
             # [3 (d/dx_i), 3 (a_j), n] -> [9, n] with row 3*i + j, as K3's tensor output

@@ -306,24 +306,13 @@ def rbf_monomial_powers(order):
     return [(a, b, d - a - b) for d in range(order + 1) for a in range(d, -1, -1) for b in range(d - a, -1, -1)]
 
 
-def rbf_interp(nodes, origin, fields, sx, sy, sz, nclose=150, order=5, phs=3, include_origin=True, want_tensor=False,
-               want_neighbors=False):
-    """get_gravity_at_point as the reference evaluates it (gizmo_interface.py:651-717): per star the `nclose` nearest
-    points of the evolved grid (lattice nodes in C order + the appended origin row; cKDTree.query) and
-    rbf.interpolate.RBFInterpolant(points, values, basis=phs<phs>, order=order) evaluated at the star.  The `rbf`
-    package is absent here; scipy.interpolate.RBFInterpolator (same author, kernel='cubic', degree=order) is the
-    same interpolant and pins this function in tests/test_cpu_rbf.py.
-
-    Brute-force neighbour search, ordered by (distance^2, point index); the saddle-point system [[K, P], [P', 0]] in
-    coordinates shifted to the star and scaled by the grid spacing (the interpolant is invariant under both), solved
-    with LAPACK in FP64.  fields [n_comp, n_node]; returns dict(out [n_comp, n], tensor [3, n_comp, n], neighbors)."""
-    xg, yg, zg = (np.asarray(a, np.float64) for a in nodes)
-    o = np.asarray(origin, np.float64).reshape(3)
-    gx, gy, gz = np.meshgrid(xg + o[0], yg + o[1], zg + o[2], indexing="ij")
-    pts = np.stack([gx.ravel(), gy.ravel(), gz.ravel()], axis=1)
-    pts = np.concatenate([pts, o[None]]) if include_origin else pts
+def rbf_interp_points(pts, fields, sx, sy, sz, h, nclose=150, order=5, phs=3, want_tensor=False, want_neighbors=False):
+    """kNN(nclose) + RBF-PHS interpolation of `fields` [n_comp, n_pts] given on an arbitrary point list `pts` [n_pts, 3]
+    (what gizmo_interface.py:651-717 does on grid.evolved_grid, nested or not).  Brute-force neighbour search ordered by
+    (distance^2, point index); the saddle-point system [[K, P], [P', 0]] in coordinates shifted to the star and scaled
+    by `h` (the interpolant is invariant under both), solved with LAPACK in FP64."""
+    pts = np.asarray(pts, np.float64)
     fields = np.asarray(fields, np.float64)
-    h = max(xg[1] - xg[0], yg[1] - yg[0], zg[1] - zg[0])
     pw = np.array(rbf_monomial_powers(order))
     nm = len(pw)
     sx, sy, sz = (np.atleast_1d(np.asarray(a, np.float64)) for a in (sx, sy, sz))
@@ -357,6 +346,23 @@ def rbf_interp(nodes, origin, fields, sx, sy, sz, nclose=150, order=5, phs=3, in
     if want_neighbors:
         res["neighbors"] = nbrs
     return res
+
+
+def rbf_interp(nodes, origin, fields, sx, sy, sz, nclose=150, order=5, phs=3, include_origin=True, want_tensor=False,
+               want_neighbors=False):
+    """get_gravity_at_point as the reference evaluates it (gizmo_interface.py:651-717): per star the `nclose` nearest
+    points of the evolved grid (lattice nodes in C order + the appended origin row; cKDTree.query) and
+    rbf.interpolate.RBFInterpolant(points, values, basis=phs<phs>, order=order) evaluated at the star.  The `rbf`
+    package is absent here; scipy.interpolate.RBFInterpolator (same author, kernel='cubic', degree=order) is the
+    same interpolant and pins this function in tests/test_cpu_rbf.py.
+    fields [n_comp, n_node]; returns dict(out [n_comp, n], tensor [3, n_comp, n], neighbors)."""
+    xg, yg, zg = (np.asarray(a, np.float64) for a in nodes)
+    o = np.asarray(origin, np.float64).reshape(3)
+    gx, gy, gz = np.meshgrid(xg + o[0], yg + o[1], zg + o[2], indexing="ij")
+    pts = np.stack([gx.ravel(), gy.ravel(), gz.ravel()], axis=1)
+    pts = np.concatenate([pts, o[None]]) if include_origin else pts
+    h = max(xg[1] - xg[0], yg[1] - yg[0], zg[1] - zg[0])
+    return rbf_interp_points(pts, fields, sx, sy, sz, h, nclose, order, phs, want_tensor, want_neighbors)
 
 
 def layout_nested(planes, n_coarse, keep_index, hole_index, hole_points, fine_nodes, fine_row0):

@@ -219,3 +219,23 @@ def test_fullsize_65536_third_law_and_rows(ctx):
     ej = max(rel_err(j[:, t:t + 1], r[1][:, t:t + 1]) for t, r in zip(rows, ref))
     ep = max(rel_err_scalar(p[t:t + 1], r[2][t:t + 1]) for t, r in zip(rows, ref))
     assert ea <= TOL and ej <= TOL and ep <= TOL
+
+
+def test_two_gpu_sharded_hermite_matches_single_gpu():
+    """K6 target-sharded over 2 GPUs: positions and velocities NCCL-all-gathered per force evaluation, predictor /
+    corrector local, Aarseth step all-reduced (tools/bridge_multi.py --integrator hermite)."""
+    import json
+    import os
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29519", os.path.join(root, "tools", "bridge_multi.py"), "--stars", "8192", "--steps", "2",
+           "--integrator", "hermite"]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+    line = json.loads([ln for ln in res.stdout.splitlines() if ln.startswith("{")][-1])
+    assert line["match"] and line["n_gpus"] == 2 and line["integrator"] == "hermite"

@@ -196,3 +196,35 @@ def test_field_code_rbf_mode_matches_oracle_and_drives_the_bridge(ctx):
     system.evolve_model(0.2 | units.Myr, timestep=0.1 | units.Myr)
     assert system.graph_replays == 0 and np.all(np.isfinite(cl.pos.cpu().numpy()))
     assert np.all(field.rbf_status.cpu().numpy() & 0xff == 0)
+
+
+def test_field_code_rbf_on_the_nested_grid(ctx):
+    """The reference's default grid (coarse lattice with a fine lattice nested around the cluster, test_options:93-100):
+    the RBF search over the fine lattice + origin row equals the search over the reference's whole point list
+    (kept coarse + fine + origin) for stars inside the fine box; a star near its surface is flagged."""
+    from oc_nbody_b200.gizmo_field import gizmo_field
+    from oc_nbody_b200.synthetic import advance_snapshot, make_snapshot
+    from oc_nbody_b200.units import units
+    center = np.array([8.0, 0.0, 0.0])
+    snaps = [make_snapshot(8000, seed=1776)]
+    snaps.append(advance_snapshot(snaps[0], 23.0))
+    opts = dict(grid_x_size_in_kpc=0.06, grid_y_size_in_kpc=0.06, grid_z_size_in_kpc=0.06, grid_resolution=0.06 / 8, fine_grid=True,
+                grid_fine_x_size_in_kpc=0.012, grid_fine_y_size_in_kpc=0.012, grid_fine_z_size_in_kpc=0.012,
+                grid_fine_resolution=0.012 / 14, space_interpolation="rbf")
+    field = gizmo_field(opts, snaps, chosen_positions=np.tile(center, (2, 1)), ctx=ctx)
+    field.evolve_grid(center)
+    field.evolve_model(11.0 | units.Myr)
+    g = field.grid
+    assert g.has_fine_grid
+    rng = np.random.default_rng(8)
+    p = center + rng.uniform(-0.004, 0.004, (12, 3))
+    p[-1] = center + np.array([0.0115, 0.0, 0.0])  # half a fine cell from the surface of the fine box: mixed-level stencil
+    ax, ay, az = field.get_gravity_at_point(0 | units.kpc, p[:, 0] | units.kpc, p[:, 1] | units.kpc, p[:, 2] | units.kpc)
+    got = np.stack([c.value_in(units.kms / units.Myr) for c in (ax, ay, az)])
+    st = field.rbf_status.cpu().numpy() & 0xff
+    assert np.all(st[:-1] == 0) and st[-1] & 8
+    fld = np.concatenate([field.evolved_acceleration, field.evolved_potential[None]])
+    h = g.fine_nodes[0][1] - g.fine_nodes[0][0]
+    ref = oracle.rbf_interp_points(g.evolved_grid, fld, p[:-1, 0], p[:-1, 1], p[:-1, 2], h, want_neighbors=True)
+    assert np.all(ref["neighbors"] >= g.fine_row0)  # every neighbour is a fine point or the origin row
+    assert close(got[:, :-1], ref["out"][:3], 1e-9)

@@ -23,6 +23,8 @@ def main():
     ap.add_argument("--stars", type=int, default=65536)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--grid", type=int, default=16)
+    ap.add_argument("--integrator", default="leapfrog", choices=("leapfrog", "hermite"),
+                    help="hermite: K6 (acc + jerk) target-sharded, positions AND velocities all-gathered per evaluation")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -69,7 +71,7 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
-    sh = sharded_cluster_code(mass, pos, vel, softening_pc=0.01, ctx=ctx)
+    sh = sharded_cluster_code(mass, pos, vel, softening_pc=0.01, ctx=ctx, integrator=args.integrator)
     # stage checks: the all-gather reproduces the full arrays; the first sharded force equals the unsharded one
     g_pos, g_vel = (t.cpu().numpy() for t in sh.gather_state())
     gather_ok = bool(np.array_equal(g_pos, pos) and np.array_equal(g_vel, vel))
@@ -79,7 +81,7 @@ def main():
     force_err = float(np.max(np.abs(a_loc - a_full[:, sh.a:sh.b])) / np.max(np.abs(a_full)))
     ms_sharded = run(sh, args.steps)
     x_sh, v_sh = (t.cpu().numpy() for t in sh.gather_state())
-    single = cluster_code(mass, pos, vel, softening_pc=0.01, ctx=ctx)
+    single = cluster_code(mass, pos, vel, softening_pc=0.01, ctx=ctx, integrator=args.integrator)
     ms_single = run(single, args.steps)
     x_1, v_1 = single.pos.cpu().numpy(), single.vel.cpu().numpy()
     dx = float(np.max(np.abs(x_sh - x_1)) / np.max(np.abs(x_1 - center[:, None])))
@@ -87,7 +89,7 @@ def main():
     ok = dx < 1e-10 and dv < 1e-10 and gather_ok and force_err < 1e-12
     print("rank %d: gather_ok %s force_err %.3e dx %.3e dv %.3e" % (rank, gather_ok, force_err, dx, dv), file=sys.stderr)
     if rank == 0:
-        print(json.dumps({"n_gpus": world, "n_stars": args.stars, "steps": args.steps, "ms_per_bridge_step_sharded": ms_sharded,
+        print(json.dumps({"n_gpus": world, "n_stars": args.stars, "integrator": args.integrator, "steps": args.steps, "ms_per_bridge_step_sharded": ms_sharded,
                           "ms_per_bridge_step_single_gpu": ms_single, "max_rel_dx": dx, "max_rel_dv": dv, "match": ok,
                           "allgather_exact_rank0": gather_ok, "first_force_rel_err_rank0": force_err}))
     if world > 1:
