@@ -244,6 +244,32 @@ def bridge_step_times(ctx):
                 if i >= 4:
                     ts.append(e0.elapsed_time(e1))
             out["%d_stars_%s" % (nst, "cuda_graph" if graph else "eager")] = float(np.median(ts))
+    # the reference-algorithm modes: ph4's Hermite scheme as the drift (K6, two acc+jerk evaluations
+    # per step) and the kNN(150) + RBF-PHS interpolant as the kick (K7, two kicks per step)
+    rbf = gizmo_field(dict(grid_x_size_in_kpc=0.05, grid_y_size_in_kpc=0.05, grid_z_size_in_kpc=0.05, grid_resolution=0.05 / nn,
+                           space_interpolation="rbf"), [_Snap(), _Snap()], time_in_Myr=[0.0, 23.0], build=False, ctx=ctx)
+    rbf.set_snapshot_fields(tid[:, 0], tid[:, 1], tid[:, 2])
+    rbf.evolve_grid(CENTER)
+    for key, nst, field, kw, graph in (("1024_stars_hermite_cuda_graph", 1024, fld, dict(integrator="hermite"), True),
+                                       ("65536_stars_hermite_cuda_graph", 65536, fld, dict(integrator="hermite"), True),
+                                       ("1024_stars_rbf_kick_eager", 1024, rbf, {}, False)):
+        pos_pc, vel, mass = make_plummer_cluster(nst)
+        cl = cluster_code(mass, pos_pc * 1e-3 + CENTER[:, None], vel, softening_pc=0.01, ctx=ctx, **kw)
+        field.evolve_model(0.0 | units.Myr)
+        system = Bridge(timestep=0.1 | units.Myr, use_threading=False, use_cuda_graph=graph)
+        system.add_system(cl, (field,))
+        system.add_system(field)
+        t, ts = 0.0, []
+        for i in range(12):
+            t += 0.1
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            system.evolve_model(t | units.Myr, timestep=0.1 | units.Myr)
+            e1.record()
+            torch.cuda.synchronize()
+            if i >= 4:
+                ts.append(e0.elapsed_time(e1))
+        out[key] = float(np.median(ts))
     return out
 
 

@@ -77,6 +77,19 @@ def main():
         ctx.lib.ocg_debug_set_hermite_variant(-1)
         out[name] = dict(interactions=inter, note="pack + kernel + finish per call (small: one fused launch)", variants=res)
 
+    # ---- the same force loop on the host cores (the oracle's FP64 OpenMP restatement; bounded sample of N = 65 536) ----
+    if "--no-cpu-baseline" not in sys.argv:
+        import time
+        import oracle
+        pos_pc, vel1, mass = make_plummer_cluster(65536)
+        rows = 2048
+        t0 = time.perf_counter()
+        oracle.self_gravity_hermite(pos_pc * 1e-3 + origin[0][:, None], vel1, mass, eps2, G_KPC_KMS_MYR, KMS_TO_KPC_PER_MYR,
+                                    t0=0, t1=rows)
+        dt = time.perf_counter() - t0
+        out["cpu_baseline"] = dict(value=rows * 65536.0 / dt / 1e9, unit="G interactions/s", cores=oracle.num_threads(), kind="port",
+                                   sample="%d of the 65 536 targets x all sources, FP64 OpenMP acc + jerk (oracle/ocg_oracle.c), %.1f s" % (rows, dt))
+
     # ---- BRIDGE step with the Hermite cluster code ----
     from oc_nbody_b200.bridge import Bridge
     from oc_nbody_b200.cluster import cluster_code
