@@ -93,7 +93,8 @@ extern "C" int ocg_destroy(ocg_ctx* ctx) {
     if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
   cudaEventDestroy(ctx->ev0);
   cudaEventDestroy(ctx->ev1);
-  free(ctx->items_host);
+  free(ctx->plan[0].items_host);
+  free(ctx->plan[1].items_host);
   free(ctx);
   return OCG_OK;
 }

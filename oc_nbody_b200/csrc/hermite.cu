@@ -434,14 +434,16 @@ extern "C" int ocg_self_gravity_hermite(ocg_ctx* ctx, const double* pos_dev, con
 
   OcgClusterPlan plan;
   int rc;
-  if ((rc = ocg_plan_cluster_items(ctx, n, seg_offsets_host, n_seg, tgt_begin, tgt_end, CT, HM_TS, ctx->sm_count, st, &plan)))
+  if ((rc = ocg_plan_cluster_items(ctx, n, seg_offsets_host, n_seg, tgt_begin, tgt_end, CT, HM_TS, ctx->sm_count, st, &plan, /*which=*/1)))
     return rc;
   float* tiles;
   float4* tgt;
   double* partial;
-  rc = ocg_scratch(ctx, OCG_SCR_TILES, (size_t)plan.total_tiles * HM_TILE_BYTES, (void**)&tiles);
-  if (!rc) rc = ocg_scratch(ctx, OCG_SCR_TGT, 2 * sizeof(float4) * (size_t)n, (void**)&tgt);
-  if (!rc) rc = ocg_scratch(ctx, OCG_SCR_PARTIAL, sizeof(double) * (size_t)plan.n_chunks * NC * (size_t)n, (void**)&partial);
+  // own scratch slots: a CUDA graph that captured this call must survive K4 calls (bound_center_of_mass) that would
+  // otherwise grow - i.e. reallocate - a shared buffer
+  rc = ocg_scratch(ctx, OCG_SCR_TILES_HM, (size_t)plan.total_tiles * HM_TILE_BYTES, (void**)&tiles);
+  if (!rc) rc = ocg_scratch(ctx, OCG_SCR_TGT_HM, 2 * sizeof(float4) * (size_t)n, (void**)&tgt);
+  if (!rc) rc = ocg_scratch(ctx, OCG_SCR_PARTIAL_HM, sizeof(double) * (size_t)plan.n_chunks * 7 * (size_t)n, (void**)&partial);
   if (rc) return rc;
   {
     const long long nslots = plan.total_tiles * HM_TS;

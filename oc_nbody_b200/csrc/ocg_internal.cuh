@@ -31,7 +31,7 @@ struct OcgWorkItem {
 
 enum { OCG_SCR_TILES = 0, OCG_SCR_PARTIAL, OCG_SCR_NEAR, OCG_SCR_ITEMS, OCG_SCR_MISC, OCG_SCR_TGT,
        OCG_SCR_SRC, OCG_SCR_SOFT, OCG_SCR_F64A, OCG_SCR_F64B, OCG_SCR_F64C, OCG_SCR_OUT, OCG_SCR_COUNTS,
-       OCG_SCR_N };
+       OCG_SCR_ITEMS_HM, OCG_SCR_TILES_HM, OCG_SCR_TGT_HM, OCG_SCR_PARTIAL_HM, OCG_SCR_N };
 
 struct ocg_ctx {
   int device;
@@ -45,11 +45,14 @@ struct ocg_ctx {
   int timing;
   cudaEvent_t ev0, ev1;
   int ev_valid;
-  // cached host copy of the last uploaded item list (K4), to skip re-upload
-  OcgWorkItem* items_host;
-  size_t items_host_cap;
-  size_t items_uploaded;  // number of items currently in device list
-  unsigned long long items_hash;
+  // cached host copy of the last uploaded item list, to skip re-upload: [0] K4, [1] the Hermite force loop.  Each has
+  // its own device buffer (OCG_SCR_ITEMS / OCG_SCR_ITEMS_HM): a captured CUDA graph of one must not see the other's plan.
+  struct PlanCache {
+    OcgWorkItem* items_host;
+    size_t items_host_cap;
+    size_t items_uploaded;  // number of items currently in device list
+    unsigned long long items_hash;
+  } plan[2];
 };
 
 // ---- error helpers ------------------------------------------------------------------------------
@@ -115,7 +118,8 @@ struct OcgClusterPlan {
   const long long* d_seg_off;   // device [n_seg+1]: first particle of each segment
 };
 int ocg_plan_cluster_items(ocg_ctx* ctx, int64_t n, const int64_t* seg_offsets_host, int32_t n_seg, int64_t tgt_begin,
-                           int64_t tgt_end, int ct, int ts, long long slots, cudaStream_t st, OcgClusterPlan* out);
+                           int64_t tgt_end, int ct, int ts, long long slots, cudaStream_t st, OcgClusterPlan* out,
+                           int which = 0);
 
 // ---- entry points implemented in other translation units ------------------------------------
 int ocg_pick_variant(ocg_ctx* ctx, int64_t n_tgt, int64_t seg_len, bool guard, bool allow_mf = false,

@@ -134,8 +134,10 @@ static unsigned long long fnv1a(const void* data, size_t bytes, unsigned long lo
 // number of source chunks, and the (target tile x source chunk) item list, uploaded to the device (skipped when
 // the same plan is already there).  `ct` targets per CTA tile, `ts` sources per source tile, `slots` resident CTAs.
 int ocg_plan_cluster_items(ocg_ctx* ctx, int64_t n, const int64_t* seg_offsets_host, int32_t n_seg, int64_t tgt_begin,
-                           int64_t tgt_end, int ct, int ts, long long slots, cudaStream_t st, OcgClusterPlan* out) {
+                           int64_t tgt_end, int ct, int ts, long long slots, cudaStream_t st, OcgClusterPlan* out, int which) {
   const int CT = ct;
+  ocg_ctx::PlanCache& pc = ctx->plan[which ? 1 : 0];
+  const int scr = which ? OCG_SCR_ITEMS_HM : OCG_SCR_ITEMS;
   long long* seg_tile = (long long*)malloc(sizeof(long long) * (2 * (size_t)n_seg + 2));
   if (!seg_tile) return ocg_fail(ctx, OCG_ERR_NOMEM, "malloc failed");
   long long* seg_off_ll = seg_tile + n_seg + 1;
@@ -171,12 +173,12 @@ int ocg_plan_cluster_items(ocg_ctx* ctx, int64_t n, const int64_t* seg_offsets_h
     free(seg_tile);
     return ocg_fail(ctx, OCG_ERR_INVALID, "too many work items");
   }
-  if ((size_t)n_items > ctx->items_host_cap) {
-    free(ctx->items_host);
-    ctx->items_host = (OcgWorkItem*)malloc(sizeof(OcgWorkItem) * (size_t)n_items);
-    ctx->items_host_cap = ctx->items_host ? (size_t)n_items : 0;
-    ctx->items_uploaded = 0;
-    if (!ctx->items_host) {
+  if ((size_t)n_items > pc.items_host_cap) {
+    free(pc.items_host);
+    pc.items_host = (OcgWorkItem*)malloc(sizeof(OcgWorkItem) * (size_t)n_items);
+    pc.items_host_cap = pc.items_host ? (size_t)n_items : 0;
+    pc.items_uploaded = 0;
+    if (!pc.items_host) {
       free(seg_tile);
       return ocg_fail(ctx, OCG_ERR_NOMEM, "malloc of %lld work items failed", n_items);
     }
@@ -192,7 +194,7 @@ int ocg_plan_cluster_items(ocg_ctx* ctx, int64_t n, const int64_t* seg_offsets_h
       long long tpc = (nt + n_chunks - 1) / n_chunks;
       long long tb = c * tpc, te = tb + tpc < nt ? tb + tpc : nt;
       for (long long t0 = a; t0 < b; t0 += CT) {
-        OcgWorkItem& it = ctx->items_host[w++];
+        OcgWorkItem& it = pc.items_host[w++];
         it.tgt_begin = t0;
         it.tgt_count = (int)(b - t0 < CT ? b - t0 : CT);
         it.tile_begin = seg_tile[s] + (tb < nt ? tb : nt);
@@ -201,7 +203,7 @@ int ocg_plan_cluster_items(ocg_ctx* ctx, int64_t n, const int64_t* seg_offsets_h
       }
     }
   }
-  unsigned long long h = fnv1a(ctx->items_host, sizeof(OcgWorkItem) * (size_t)n_items, 1469598103934665603ull);
+  unsigned long long h = fnv1a(pc.items_host, sizeof(OcgWorkItem) * (size_t)n_items, 1469598103934665603ull);
   h = fnv1a(seg_tile, sizeof(long long) * (2 * (size_t)n_seg + 2), h);
 
   int rc = 0;
@@ -210,27 +212,27 @@ int ocg_plan_cluster_items(ocg_ctx* ctx, int64_t n, const int64_t* seg_offsets_h
   const size_t seg_bytes = sizeof(long long) * (2 * (size_t)n_seg + 2);
   const size_t items_bytes = sizeof(OcgWorkItem) * (size_t)n_items;
   void* items_raw = nullptr;
-  const size_t before = ctx->scratch_bytes[OCG_SCR_ITEMS];
-  if (!rc) rc = ocg_scratch(ctx, OCG_SCR_ITEMS, items_bytes + seg_bytes + 64, &items_raw);
+  const size_t before = ctx->scratch_bytes[scr];
+  if (!rc) rc = ocg_scratch(ctx, scr, items_bytes + seg_bytes + 64, &items_raw);
   if (rc) {
     free(seg_tile);
     return rc;
   }
   d_items = (OcgWorkItem*)items_raw;
   d_seg = (long long*)((char*)items_raw + ((items_bytes + 63) / 64) * 64);
-  const bool reuse = before == ctx->scratch_bytes[OCG_SCR_ITEMS] && ctx->items_uploaded == (size_t)n_items &&
-                     ctx->items_hash == h;
+  const bool reuse = before == ctx->scratch_bytes[scr] && pc.items_uploaded == (size_t)n_items &&
+                     pc.items_hash == h;
   if (!reuse) {
     // synchronous small copies: the plan changes only when the segment layout or shard changes
-    cudaError_t e = cudaMemcpyAsync(d_items, ctx->items_host, items_bytes, cudaMemcpyHostToDevice, st);
+    cudaError_t e = cudaMemcpyAsync(d_items, pc.items_host, items_bytes, cudaMemcpyHostToDevice, st);
     if (e == cudaSuccess) e = cudaMemcpyAsync(d_seg, seg_tile, seg_bytes, cudaMemcpyHostToDevice, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);  // seg_tile is freed below
     if (e != cudaSuccess) {
       free(seg_tile);
       return ocg_fail(ctx, OCG_ERR_CUDA, "upload of the work plan failed: %s", cudaGetErrorString(e));
     }
-    ctx->items_uploaded = (size_t)n_items;
-    ctx->items_hash = h;
+    pc.items_uploaded = (size_t)n_items;
+    pc.items_hash = h;
   }
   free(seg_tile);
   out->total_tiles = total_tiles, out->n_chunks = n_chunks, out->n_items = n_items;

@@ -46,12 +46,13 @@ class frame_recorder(object):
 
 
 def evolve_cluster_in_galaxy(galaxy_code, mass, pos_kpc, vel_kms, timestep, tend, softening_pc=0.01, eject_cut=None,
-                             substeps=1, use_cuda_graph=True, record_every=1, ctx=None):
+                             substeps=1, use_cuda_graph=True, record_every=1, ctx=None, integrator="leapfrog"):
     """oc_nbody.py:15-70 with the cluster given as arrays (the reference builds it from a King model + Kroupa IMF through
     AMUSE, oc_code.py:197-216) and ``galaxy_code`` an already built ``gizmo_field``.  timestep / tend in Myr
-    (options 'timestep', 'tend', oc_nbody.py:18-20).  Returns (cluster_code, frame_recorder)."""
+    (options 'timestep', 'tend', oc_nbody.py:18-20); integrator "hermite" drifts with ph4's own scheme (K6).
+    Returns (cluster_code, frame_recorder)."""
     cl = cluster_code(mass, pos_kpc, vel_kms, softening_pc=softening_pc, substeps=substeps, eject_cut=eject_cut,
-                      ctx=ctx or galaxy_code.ctx)
+                      ctx=ctx or galaxy_code.ctx, integrator=integrator)
     times = np.arange(0.0, float(tend), float(timestep))            # oc_nbody.py:20
     system = Bridge(timestep=timestep | units.Myr, use_threading=False, use_cuda_graph=use_cuda_graph)  # :49
     system.add_system(cl, (galaxy_code,))                           # :50  the cluster is kicked by the galaxy

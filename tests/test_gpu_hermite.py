@@ -239,3 +239,27 @@ def test_two_gpu_sharded_hermite_matches_single_gpu():
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
     line = json.loads([ln for ln in res.stdout.splitlines() if ln.startswith("{")][-1])
     assert line["match"] and line["n_gpus"] == 2 and line["integrator"] == "hermite"
+
+
+def test_driver_loop_with_hermite_graph_steps_and_k4_bookkeeping_between_them(ctx):
+    """The reference's driver loop (oc_nbody.py:49-66) above the small-cluster size: every step replays the captured
+    Hermite step (K6, streaming kernel with its own work plan and scratch) and then runs K4 with the potential for the
+    bound-subset centre of mass.  The two plans must not disturb each other: graph and eager runs agree."""
+    from oc_nbody_b200.driver import evolve_cluster_in_galaxy
+    from oc_nbody_b200.gizmo_field import gizmo_field
+    from oc_nbody_b200.synthetic import advance_snapshot, make_snapshot
+    center = np.array([8.0, 0.0, 0.0])
+    snaps = [make_snapshot(20000, seed=1776)]
+    snaps.append(advance_snapshot(snaps[0], 23.0))
+    opts = dict(grid_x_size_in_kpc=0.05, grid_y_size_in_kpc=0.05, grid_z_size_in_kpc=0.05, grid_resolution=0.05 / 8)
+    pos, vel, mass = cluster(5000, seed=12)
+    out = []
+    for graph in (False, True):
+        field = gizmo_field(opts, snaps, chosen_positions=np.tile(center, (2, 1)), ctx=ctx)
+        field.evolve_grid(center)
+        cl, rec = evolve_cluster_in_galaxy(field, mass, pos, vel, timestep=0.1, tend=0.65, softening_pc=0.01, substeps=1,
+                                           use_cuda_graph=graph, ctx=ctx, integrator="hermite")
+        out.append((cl.pos.cpu().numpy(), cl.vel.cpu().numpy(), len(rec.frames)))
+    assert out[0][2] == out[1][2] == 7
+    assert np.max(np.abs(out[0][0] - out[1][0])) <= 1e-12 * 8.0
+    assert np.max(np.abs(out[0][1] - out[1][1])) <= 1e-11 * 220.0
