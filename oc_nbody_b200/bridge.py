@@ -17,6 +17,8 @@ step to step — the time-blend weights of the two half-kicks — lives in const
 replay (ocg_set_interp_weight_slots); the grid origin is a device buffer.  The graph is re-captured when the
 bracketing snapshots, the particle count or the timestep change.  Results equal the eager path's to FP64 rounding
 (the eager drift integrates over (t + dt) - model_time, which can differ from dt in the last bit).
+The star-sharded cluster code is captured the same way, its NCCL all-gathers included (every rank takes the same
+eager / capture / replay decisions, so the collectives stay matched).
 """
 from .units import to_value, units
 
@@ -69,7 +71,7 @@ class Bridge(object):
         for cl, fld in (self.systems, self.systems[::-1]):
             if (self.partners[id(cl)] == (fld,) and self.partners[id(fld)] == () and hasattr(fld, "kick_device")
                     and hasattr(fld, "_time_planes_") and getattr(fld, "space_interpolation", "trilinear") == "trilinear"
-                    and type(cl).__name__ == "cluster_code" and hasattr(cl, "_evolve_device_")):
+                    and type(cl).__name__ in ("cluster_code", "sharded_cluster_code") and hasattr(cl, "_evolve_device_")):
                 return cl, fld
         return None
 

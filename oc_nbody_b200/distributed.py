@@ -74,12 +74,19 @@ def self_gravity_sharded(pos_local, gather_fn, acc_fn, n_total, group=None):
 
 
 def allgather_particles(pos_local, n_total, group=None):
-    """All-gather [3, n_local] blocks (possibly of unequal size) into [3, n_total] on every rank."""
+    """All-gather [3, n_local] blocks (possibly of unequal size) into [3, n_total] on every rank.
+    Equal blocks (n_total divisible by the world size): ONE NCCL all-gather into a [world, 3, n_local] buffer and one
+    strided copy — two launches, capturable in a CUDA graph.  Unequal blocks are padded to the widest."""
     import torch
     import torch.distributed as dist
     rank, world = _world(group)
     if world == 1:
         return pos_local
+    if n_total % world == 0 and pos_local.is_contiguous():
+        width = n_total // world
+        buf = torch.empty((world, 3, width), dtype=pos_local.dtype, device=pos_local.device)
+        dist.all_gather_into_tensor(buf, pos_local, group=group)
+        return buf.permute(1, 0, 2).reshape(3, n_total)   # one copy kernel: [3][world][width] is [3][n_total]
     bounds = shard_bounds(n_total, world)
     width = int(np.max(np.diff(bounds)))
     send = torch.zeros((width, 3), dtype=pos_local.dtype, device=pos_local.device)

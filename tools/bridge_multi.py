@@ -23,6 +23,7 @@ def main():
     ap.add_argument("--stars", type=int, default=65536)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--grid", type=int, default=16)
+    ap.add_argument("--graph", action="store_true", help="replay the sharded step (NCCL all-gathers included) as one CUDA graph")
     ap.add_argument("--integrator", default="leapfrog", choices=("leapfrog", "hermite"),
                     help="hermite: K6 (acc + jerk) target-sharded, positions AND velocities all-gathered per evaluation")
     args = ap.parse_args()
@@ -52,23 +53,28 @@ def main():
     def run(code, steps, timed=False):
         field.evolve_grid(center)
         field.evolve_model(0.0 | units.Myr)
-        system = Bridge(timestep=dt | units.Myr, use_threading=False)
+        system = Bridge(timestep=dt | units.Myr, use_threading=False, use_cuda_graph=args.graph)
         system.add_system(code, (field,))
         system.add_system(field)
         system.evolve_model(0.0 | units.Myr, timestep=dt | units.Myr)
         system.evolve_model(dt | units.Myr, timestep=dt | units.Myr)  # warm-up step (also validates)
+        if args.graph:  # two more: the step that sizes the scratch buffers and the one that captures
+            system.evolve_model(2 * dt | units.Myr, timestep=dt | units.Myr)
+            system.evolve_model(3 * dt | units.Myr, timestep=dt | units.Myr)
+        first = 4 if args.graph else 2
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
         e0.record()
-        for i in range(2, steps + 2):
+        for i in range(first, steps + first):
             system.evolve_model(i * dt | units.Myr, timestep=dt | units.Myr)
         e1.record()
         torch.cuda.synchronize()
         ms = torch.tensor([e0.elapsed_time(e1) / steps], dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        run.replays = system.graph_replays
         return float(ms.item())
 
     sh = sharded_cluster_code(mass, pos, vel, softening_pc=0.01, ctx=ctx, integrator=args.integrator)
@@ -89,7 +95,7 @@ def main():
     ok = dx < 1e-10 and dv < 1e-10 and gather_ok and force_err < 1e-12
     print("rank %d: gather_ok %s force_err %.3e dx %.3e dv %.3e" % (rank, gather_ok, force_err, dx, dv), file=sys.stderr)
     if rank == 0:
-        print(json.dumps({"n_gpus": world, "n_stars": args.stars, "integrator": args.integrator, "steps": args.steps, "ms_per_bridge_step_sharded": ms_sharded,
+        print(json.dumps({"n_gpus": world, "n_stars": args.stars, "integrator": args.integrator, "cuda_graph": bool(args.graph), "graph_replays_last_run": getattr(run, "replays", 0), "steps": args.steps, "ms_per_bridge_step_sharded": ms_sharded,
                           "ms_per_bridge_step_single_gpu": ms_single, "max_rel_dx": dx, "max_rel_dv": dv, "match": ok,
                           "allgather_exact_rank0": gather_ok, "first_force_rel_err_rank0": force_err}))
     if world > 1:
