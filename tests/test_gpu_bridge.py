@@ -296,8 +296,10 @@ def test_field_code_snapshot_caches_round_trip(ctx, tmp_path):
     assert c.cache_hits == 2 and c.grid.snapshot_potential is None
 
 
-def test_two_gpu_sharded_bridge_matches_single_gpu():
-    """K4 target-sharded over 2 GPUs with an NCCL all-gather of the positions per evaluation (tools/bridge_multi.py)."""
+@pytest.mark.parametrize("graph", [False, True])
+def test_two_gpu_sharded_bridge_matches_single_gpu(graph):
+    """K4 target-sharded over 2 GPUs with an NCCL all-gather of the positions per evaluation (tools/bridge_multi.py);
+    graph=True replays the whole sharded step, collectives included, as one CUDA graph per rank."""
     import json
     import os
     import subprocess
@@ -307,11 +309,13 @@ def test_two_gpu_sharded_bridge_matches_single_gpu():
         pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
-           "--master-port", "29517", os.path.join(root, "tools", "bridge_multi.py"), "--stars", "8192", "--steps", "2"]
+           "--master-port", "29518" if graph else "29517", os.path.join(root, "tools", "bridge_multi.py"), "--stars", "8192",
+           "--steps", "2"] + (["--graph"] if graph else [])
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
     line = json.loads([ln for ln in res.stdout.splitlines() if ln.startswith("{")][-1])
     assert line["match"] and line["n_gpus"] == 2
+    assert not graph or line["graph_replays_last_run"] >= 2
 
 
 def test_bridge_cuda_graph_step_is_bit_identical(small_world, ctx):
