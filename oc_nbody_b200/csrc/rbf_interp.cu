@@ -28,7 +28,9 @@
 #define RBF_MAXIT 12
 #define RBF_CAND_MAX 4097 /* 16^3 lattice nodes + the origin row */
 #define RBF_NPHASE 6
-#define RBF_LDA 207 /* column stride of the factor matrix: odd, so rows and columns are both bank-conflict free */
+#define RBF_LDA 212 /* column stride of the factor matrix: a multiple of 4 (16-byte aligned column segments for LDS.128), 4-way
+                        bank conflicts only on the O(N^2) row-wise accesses */
+#define RBF_NB 8    /* panel width of the blocked LU */
 
 struct RbfParams {
   int n[3];
@@ -111,8 +113,9 @@ __global__ void __launch_bounds__(RBF_THREADS, 1) rbf_interp_kernel(const RbfPar
   int* nbc = reinterpret_cast<int*>(q);                      // candidate ordinal of the m-th neighbour
   q += sizeof(int) * ncl;
   int* perm = reinterpret_cast<int*>(q);                     // row permutation of the factorisation
-  __shared__ int s_lo[3], s_cnt[3], s_cell[3], s_flag, s_conv[RBF_NRHS_MAX], s_C, s_wbi[RBF_THREADS / 32];
-  __shared__ float s_wbest[RBF_THREADS / 32];
+  __shared__ int s_lo[3], s_cnt[3], s_cell[3], s_flag, s_conv[RBF_NRHS_MAX], s_C, s_pv[RBF_NB];
+  __shared__ unsigned s_wkey[RBF_THREADS / 32];
+  __shared__ __align__(16) float s_prow[2][RBF_NB];
   __shared__ double s_p[3], s_o[3], s_h, s_r2max, s_zprev[RBF_NRHS_MAX];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -259,81 +262,137 @@ __global__ void __launch_bounds__(RBF_THREADS, 1) rbf_interp_kernel(const RbfPar
     for (int i = tid; i < N; i += RBF_THREADS) perm[i] = i;
     __syncthreads();
     phase_done(1);
-    {  // pivot candidates of column 0, one per warp
-      float best = -1.f;
-      int bi = 0;
-      if (tid < N) best = fabsf(A[tid]), bi = tid;
-      for (int o = 16; o > 0; o >>= 1) {
-        const float ov = __shfl_xor_sync(0xffffffffu, best, o);
-        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-        if (ov > best || (ov == best && oi < bi)) best = ov, bi = oi;
-      }
-      if (lane == 0) s_wbest[warp] = best, s_wbi[warp] = bi;
-    }
     if (tid == 0) s_flag = 0;
-    // Right-looking LU with partial pivoting; thread `tid` owns row `tid`: its multiplier stays in a register, the row
-    // of U is a broadcast load, and column k+1's pivot candidates fall out of the update itself.
-    for (int k = 0; k < N; ++k) {
-      __syncthreads();  // trailing update of step k-1 complete, per-warp pivot candidates of column k visible
-      int pv = k;
-      {
-        float best = -1.f;
+    // Blocked right-looking LU with partial pivoting, panels of RBF_NB columns.  Thread `tid` owns row `tid`.
+    //   panel   : the row's RBF_NB panel entries live in registers; per column one block-wide arg-max (warp shuffles +
+    //             one value per warp), the pivot row is published through shared memory (which also performs the row
+    //             exchange), the elimination inside the panel never touches shared memory;
+    //   swaps   : the panel's row exchanges are applied to the other columns by one thread per column;
+    //   U rows  : U[kb..kb+NB)[j] = L_panel^-1 A[kb..kb+NB)[j], one thread per column;
+    //   trailing: A[i][j] -= sum_c L[i][kb+c] U[kb+c][j]: the RBF_NB multipliers of a row stay in registers and the
+    //             U column segment is two broadcast LDS.128, so an element is read and written once per RBF_NB pivots
+    //             (4 shared-memory wavefronts per 32 elements per panel instead of 3 per pivot).
+    // Column k keeps the unscaled values A[k][i] below the diagonal; L_ik = A[k][i] * RP[k].
+    for (int kb = 0; kb < N; kb += RBF_NB) {
+      const int nb = N - kb < RBF_NB ? N - kb : RBF_NB;
+      const bool act = tid >= kb && tid < N;
+      float a[RBF_NB];
 #pragma unroll
-        for (int w = 0; w < RBF_THREADS / 32; ++w) {
-          const float ov = s_wbest[w];
-          const int oi = s_wbi[w];
-          if (ov > best || (ov == best && oi < pv)) best = ov, pv = oi;
+      for (int c = 0; c < RBF_NB; ++c) a[c] = (act && c < nb) ? A[(kb + c) * RBF_LDA + tid] : 0.f;
+#pragma unroll
+      for (int c = 0; c < RBF_NB; ++c) {
+        if (c < nb) {  // uniform
+          const int k = kb + c;
+          // pivot = arg-max |a[c]| over rows >= k, on the key (magnitude bits without their low byte | 255 - row): one
+          // REDUX per warp and eight keys per CTA instead of a shuffle tree (partial pivoting only needs a near-maximal
+          // pivot; ties go to the lowest row)
+          unsigned key = (act && tid >= k) ? ((__float_as_uint(fabsf(a[c])) & 0xffffff00u) | (255u - (unsigned)tid)) : 0u;
+          key = __reduce_max_sync(0xffffffffu, key);
+          if (lane == 0) s_wkey[warp] = key;
+          __syncthreads();
+#pragma unroll
+          for (int w = 0; w < RBF_THREADS / 32; ++w) key = max(key, s_wkey[w]);
+          const int pv = key ? 255 - (int)(key & 0xffu) : k;
+          // slot 0 <- the pivot row (it becomes row k), slot 1 <- the old row k (it moves to row pv)
+          if (tid == pv) {
+#pragma unroll
+            for (int c2 = 0; c2 < RBF_NB; ++c2) s_prow[0][c2] = a[c2];
+          } else if (tid == k) {
+#pragma unroll
+            for (int c2 = 0; c2 < RBF_NB; ++c2) s_prow[1][c2] = a[c2];
+          }
+          __syncthreads();
+          if (pv != k) {
+            if (tid == k) {
+#pragma unroll
+              for (int c2 = 0; c2 < RBF_NB; ++c2) a[c2] = s_prow[0][c2];
+            } else if (tid == pv) {
+#pragma unroll
+              for (int c2 = 0; c2 < RBF_NB; ++c2) a[c2] = s_prow[1][c2];
+            }
+          }
+          const float piv = s_prow[0][c];
+          float rp = 1.0f / piv;
+          if (!(fabsf(piv) > 1e-30f)) rp = 0.f;
+          if (tid == 0) {
+            RP[k] = rp;
+            if (rp == 0.f) s_flag = 1;
+            s_pv[c] = pv;
+            const int t = perm[k];
+            perm[k] = perm[pv];
+            perm[pv] = t;
+          }
+          if (act && tid > k) {
+            const float l = a[c] * rp;
+#pragma unroll
+            for (int c2 = 0; c2 < RBF_NB; ++c2)
+              if (c2 > c) a[c2] = fmaf(-l, s_prow[0][c2], a[c2]);
+          }
         }
       }
-      if (pv != k) {
-        if (tid < N) {
-          const float t = A[tid * RBF_LDA + k];
-          A[tid * RBF_LDA + k] = A[tid * RBF_LDA + pv];
-          A[tid * RBF_LDA + pv] = t;
+      if (act) {
+#pragma unroll
+        for (int c = 0; c < RBF_NB; ++c)
+          if (c < nb) A[(kb + c) * RBF_LDA + tid] = a[c];
+      }
+      __syncthreads();  // panel written back, RP / s_pv of the whole panel visible
+      if (tid < N && (tid < kb || tid >= kb + nb)) {
+        float* colp = A + tid * RBF_LDA;  // this thread's column: apply the panel's row exchanges in order
+        for (int c = 0; c < nb; ++c) {
+          const int k = kb + c, pv = s_pv[c];
+          if (pv != k) {
+            const float t = colp[k];
+            colp[k] = colp[pv];
+            colp[pv] = t;
+          }
         }
-        if (tid == 0) {
-          const int t = perm[k];
-          perm[k] = perm[pv];
-          perm[pv] = t;
+        if (tid >= kb + nb) {  // ... and turn rows kb..kb+nb of it into U: forward substitution with the panel's unit-lower block
+          float u[RBF_NB];
+#pragma unroll
+          for (int c = 0; c < RBF_NB; ++c) u[c] = c < nb ? colp[kb + c] : 0.f;
+#pragma unroll
+          for (int c = 1; c < RBF_NB; ++c)
+#pragma unroll
+            for (int c1 = 0; c1 < c; ++c1)
+              if (c < nb) u[c] = fmaf(-(A[(kb + c1) * RBF_LDA + kb + c] * RP[kb + c1]), u[c1], u[c]);
+#pragma unroll
+          for (int c = 0; c < RBF_NB; ++c)
+            if (c < nb) colp[kb + c] = u[c];
         }
       }
       __syncthreads();
-      const float piv = A[k * RBF_LDA + k];
-      float rp = 1.0f / piv;
-      if (!(fabsf(piv) > 1e-30f)) rp = 0.f;
-      if (tid == 0) {
-        RP[k] = rp;
-        if (rp == 0.f) s_flag = 1;
-      }
-      // A_ij -= L_ik U_kj, L_ik = A[k][i] * rp (column k keeps the unscaled values)
-      float best = -1.f;
-      int bi = k + 1;
-      if (tid > k && tid < N) {
-        const float l = A[k * RBF_LDA + tid] * rp;
-        float* __restrict__ row = A + tid;
-        const float* __restrict__ urow = A + k;
-        int j = k + 1;
-        {
-          const float v = fmaf(-l, urow[j * RBF_LDA], row[j * RBF_LDA]);
-          row[j * RBF_LDA] = v;
-          best = fabsf(v), bi = tid;
-          ++j;
-        }
-        for (; j + 8 <= N; j += 8) {
-          float a[8], u[8];
+      if (nb == RBF_NB && tid >= kb + RBF_NB && tid < N) {
+        float l[RBF_NB];
 #pragma unroll
-          for (int c = 0; c < 8; ++c) a[c] = row[(j + c) * RBF_LDA], u[c] = urow[(j + c) * RBF_LDA];
-#pragma unroll
-          for (int c = 0; c < 8; ++c) row[(j + c) * RBF_LDA] = fmaf(-l, u[c], a[c]);
+        for (int c = 0; c < RBF_NB; ++c) l[c] = A[(kb + c) * RBF_LDA + tid] * RP[kb + c];
+        int j = kb + RBF_NB;
+        for (; j + 2 <= N; j += 2) {
+          // (j * RBF_LDA + kb) * 4 bytes is a multiple of 16: RBF_LDA and kb are multiples of 4
+          const float4 u0 = *reinterpret_cast<const float4*>(A + j * RBF_LDA + kb);
+          const float4 u1 = *reinterpret_cast<const float4*>(A + j * RBF_LDA + kb + 4);
+          const float4 v0 = *reinterpret_cast<const float4*>(A + (j + 1) * RBF_LDA + kb);
+          const float4 v1 = *reinterpret_cast<const float4*>(A + (j + 1) * RBF_LDA + kb + 4);
+          float x = A[j * RBF_LDA + tid], y = A[(j + 1) * RBF_LDA + tid];
+          x = fmaf(-l[0], u0.x, x), y = fmaf(-l[0], v0.x, y);
+          x = fmaf(-l[1], u0.y, x), y = fmaf(-l[1], v0.y, y);
+          x = fmaf(-l[2], u0.z, x), y = fmaf(-l[2], v0.z, y);
+          x = fmaf(-l[3], u0.w, x), y = fmaf(-l[3], v0.w, y);
+          x = fmaf(-l[4], u1.x, x), y = fmaf(-l[4], v1.x, y);
+          x = fmaf(-l[5], u1.y, x), y = fmaf(-l[5], v1.y, y);
+          x = fmaf(-l[6], u1.z, x), y = fmaf(-l[6], v1.z, y);
+          x = fmaf(-l[7], u1.w, x), y = fmaf(-l[7], v1.w, y);
+          A[j * RBF_LDA + tid] = x, A[(j + 1) * RBF_LDA + tid] = y;
         }
-        for (; j < N; ++j) row[j * RBF_LDA] = fmaf(-l, urow[j * RBF_LDA], row[j * RBF_LDA]);
+        for (; j < N; ++j) {
+          const float4 u0 = *reinterpret_cast<const float4*>(A + j * RBF_LDA + kb);
+          const float4 u1 = *reinterpret_cast<const float4*>(A + j * RBF_LDA + kb + 4);
+          float x = A[j * RBF_LDA + tid];
+          x = fmaf(-l[0], u0.x, x), x = fmaf(-l[1], u0.y, x), x = fmaf(-l[2], u0.z, x), x = fmaf(-l[3], u0.w, x);
+          x = fmaf(-l[4], u1.x, x), x = fmaf(-l[5], u1.y, x), x = fmaf(-l[6], u1.z, x), x = fmaf(-l[7], u1.w, x);
+          A[j * RBF_LDA + tid] = x;
+        }
       }
-      for (int o = 16; o > 0; o >>= 1) {
-        const float ov = __shfl_xor_sync(0xffffffffu, best, o);
-        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-        if (ov > best || (ov == best && oi < bi)) best = ov, bi = oi;
-      }
-      if (lane == 0) s_wbest[warp] = best, s_wbi[warp] = bi;
+      __syncthreads();  // trailing update complete before the next panel is loaded
     }
     __syncthreads();
     if (s_flag) status |= 4;
