@@ -84,9 +84,9 @@ def allgather_particles(pos_local, n_total, group=None):
         return pos_local
     if n_total % world == 0 and pos_local.is_contiguous():
         width = n_total // world
-        buf = torch.empty((world, 3, width), dtype=pos_local.dtype, device=pos_local.device)
+        buf = torch.empty((world * 3, width), dtype=pos_local.dtype, device=pos_local.device)  # rank blocks concatenated
         dist.all_gather_into_tensor(buf, pos_local, group=group)
-        return buf.permute(1, 0, 2).reshape(3, n_total)   # one copy kernel: [3][world][width] is [3][n_total]
+        return buf.view(world, 3, width).permute(1, 0, 2).reshape(3, n_total)   # one copy kernel: [3][world][width] is [3][n_total]
     bounds = shard_bounds(n_total, world)
     width = int(np.max(np.diff(bounds)))
     send = torch.zeros((width, 3), dtype=pos_local.dtype, device=pos_local.device)

@@ -55,6 +55,12 @@ def _worker(rank, world, port, outdir):
 
     acc_local = self_gravity_sharded(torch.from_numpy(np.ascontiguousarray(pos[:, a:b])),
                                      lambda p: allgather_particles(p, n), acc_fn, n).numpy()
+    # equal blocks take the single-collective path (all_gather_into_tensor + one strided copy)
+    n2 = 256
+    vel = rng.normal(0, 1.0, (3, n2))
+    a2, b2 = shard_range(n2, rank, world)
+    gathered = allgather_particles(torch.from_numpy(np.ascontiguousarray(vel[:, a2:b2])), n2)
+    assert gathered.shape == (3, n2) and np.array_equal(gathered.numpy(), vel)
     np.savez(os.path.join(outdir, "rank%d.npz" % rank), field=field, acc_local=acc_local, a=a, b=b)
     dist.barrier()
     dist.destroy_process_group()

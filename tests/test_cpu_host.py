@@ -202,3 +202,27 @@ def test_snapshot_cache_names_and_format_follow_the_reference(tmp_path):
         assert np.array_equal(pickle.load(open(path, "rb")), a)
     f.cache_directory = None
     assert f._load_snapshot_cache_(580, 4097, want_pot=False) is None
+
+
+def test_reference_algorithm_options_are_validated_on_the_host():
+    """space_interpolation / basis / integrator (SURVEY §8f rank 5 modes) are checked before any GPU work."""
+    import pytest
+    from oc_nbody_b200.cluster import cluster_code
+    from oc_nbody_b200.gizmo_field import gizmo_field
+
+    class _Snap(object):
+        snapshot = {"index": 0, "time": 0.0}
+    base = dict(grid_x_size_in_kpc=0.05, grid_y_size_in_kpc=0.05, grid_z_size_in_kpc=0.05, grid_resolution=0.05 / 8)
+    f = gizmo_field(dict(base, space_interpolation="rbf", nclose="150", order="5", basis="phs3"), [_Snap()], build=False)
+    assert f.space_interpolation == "rbf" and f.nclose == 150 and f.order == 5 and f._rbf_phs == 3
+
+    class phs5(object):  # options.py:178-246 hands over rbf.basis objects; their name is what matters
+        pass
+    phs5.__name__ = "phs5"
+    assert gizmo_field(dict(base, space_interpolation="rbf", basis=phs5), [_Snap()], build=False)._rbf_phs == 5
+    with pytest.raises(ValueError):
+        gizmo_field(dict(base, space_interpolation="cubic"), [_Snap()], build=False)
+    with pytest.raises(NotImplementedError):
+        gizmo_field(dict(base, space_interpolation="rbf", basis="ga"), [_Snap()], build=False)
+    with pytest.raises(ValueError):
+        cluster_code(np.ones(4), np.zeros((3, 4)), np.zeros((3, 4)), integrator="rk4")
