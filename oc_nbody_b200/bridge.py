@@ -82,6 +82,8 @@ class Bridge(object):
         t0 = self.time
         if abs(getattr(fld, "time", t0) - t0) > 1e-9 * max(1.0, abs(t0)) or not cl._acc_valid:
             return False
+        if getattr(cl, "auto_substeps", False) and not cl._auto_started:
+            cl._first_substeps_(dt)
         rec0, fine0, w0 = fld._time_planes_()
         fld.evolve_model((t0 + dt) | units.Myr)          # host only: bracket + weights of the second half-kick
         rec1, fine1, w1 = fld._time_planes_()
@@ -110,6 +112,8 @@ class Bridge(object):
             self._seen_key = key
             body()
         cl.model_time = t0 + dt
+        if getattr(cl, "auto_substeps", False):
+            cl._update_substeps_(dt)   # a changed count changes the key: the next step runs eagerly, the one after re-captures
         return True
 
     def evolve_model(self, tend, timestep=None):

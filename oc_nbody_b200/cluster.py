@@ -78,7 +78,10 @@ class cluster_code(object):
 
     mass [n] Msun, pos [3,n] kpc, vel [3,n] km/s (floats or unit-carrying); ``softening_pc`` as in
     oc_code.py:225; ``substeps`` leapfrog steps per evolve_model call (ph4 chooses its own block steps;
-    here the BRIDGE timestep is subdivided evenly)."""
+    here the BRIDGE timestep is subdivided evenly).  With ``integrator="hermite"``, ``substeps="auto"`` lets the Aarseth
+    criterion choose: the count (a power of two, at most ``max_substeps``) follows the minimum step measured on the
+    device during the previous call, and eta * min |a| / |j| before the first one — ph4's accuracy control applied to
+    one shared step."""
 
     def __init__(self, mass, pos, vel, softening_pc=0.01, substeps=1, eject_cut=None, ctx=None, integrator="leapfrog",
                  eta=0.14):
@@ -91,7 +94,12 @@ class cluster_code(object):
         self._dev = torch.device("cuda", self.ctx.device)
         self.parameters = _Parameters()
         self.parameters.epsilon_squared = (softening_pc | units.parsec) ** 2
-        self.substeps = int(substeps)
+        self.auto_substeps = substeps == "auto"
+        if self.auto_substeps and integrator != "hermite":
+            raise ValueError("substeps='auto' needs integrator='hermite' (the step criterion uses the jerk)")
+        self.substeps = 1 if self.auto_substeps else int(substeps)
+        self.max_substeps = 1 << 14
+        self._auto_started = False
         self.eject_cut = eject_cut  # pc, oc_code.py:241
         self.G = G_KPC_KMS_MYR
         self.model_time = 0.0
@@ -186,6 +194,26 @@ class cluster_code(object):
                                      h, KMS_TO_KPC_PER_MYR, self.eta, self.dt_min)
         self._acc_valid = True
 
+    def _update_substeps_(self, span):
+        """substeps="auto": size the next call from the Aarseth minimum of the last step (one 8-byte read-back)."""
+        if self.auto_substeps:
+            self.substeps = min(self.max_substeps, self.suggested_substeps(span))
+
+    def _first_substeps_(self, span):
+        """substeps="auto", before any step exists: the start-up criterion dt = eta * min |a| / |j| (Aarseth 1985)."""
+        import torch
+        self._force_hermite_(self.pos, self.vel, self.acc, self.jerk)
+        a2, j2 = (self.acc * self.acc).sum(dim=0), (self.jerk * self.jerk).sum(dim=0)
+        ok = j2 > 0
+        dt = float((self.eta * torch.sqrt(a2[ok] / j2[ok])).min().item()) if bool(ok.any()) else span
+        if hasattr(self, "group") and getattr(self, "world", 1) > 1:
+            import torch.distributed as dist
+            t = torch.tensor([dt], dtype=torch.float64, device=self._dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MIN, group=self.group)
+            dt = float(t.item())
+        self.substeps = min(self.max_substeps, int(2 ** max(0, int(np.ceil(np.log2(span / dt))))) if dt > 0 else 1)
+        self._auto_started = True
+
     def suggested_substeps(self, span):
         """Sub-steps (a power of two) that bring span / substeps under the Aarseth step of the last Hermite step."""
         dt = float(self.dt_min.item())
@@ -214,7 +242,10 @@ class cluster_code(object):
             return
         if not self._acc_valid and self.integrator != "hermite":
             self.compute_self_gravity()
+        if self.auto_substeps and not self._auto_started:
+            self._first_substeps_(span)
         self._evolve_device_(span)
+        self._update_substeps_(span)
         self.model_time = t_end
 
     def kick_velocities(self, ax, ay, az, dt_myr):

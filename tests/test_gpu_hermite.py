@@ -263,3 +263,39 @@ def test_driver_loop_with_hermite_graph_steps_and_k4_bookkeeping_between_them(ct
     assert out[0][2] == out[1][2] == 7
     assert np.max(np.abs(out[0][0] - out[1][0])) <= 1e-12 * 8.0
     assert np.max(np.abs(out[0][1] - out[1][1])) <= 1e-11 * 220.0
+
+
+def test_hermite_auto_substeps_follow_the_aarseth_criterion(ctx):
+    """substeps="auto": the count is a power of two that brings the shared step under the Aarseth minimum measured on the
+    device; the result equals the fixed-count run with the same count and conserves energy far better than one step."""
+    from oc_nbody_b200.cluster import KMS_TO_KPC_PER_MYR, cluster_code
+    from oc_nbody_b200.units import units
+    import torch
+    pos, vel, mass = cluster(1024, seed=44)
+    span = 0.05
+
+    def energy(cl):
+        pot = torch.empty(cl.n, dtype=torch.float64, device="cuda")
+        ctx.self_gravity_hermite(cl.pos, cl.vel, cl.mass, EPS2, G, VTL, cl.acc1, cl.jerk1, pot)
+        v = cl.vel - (cl.vel * cl.mass).sum(dim=1, keepdim=True) / cl.mass.sum()
+        return float((0.5 * cl.mass * (v * v).sum(dim=0)).sum() + 0.5 * (cl.mass * pot).sum() / KMS_TO_KPC_PER_MYR)
+    auto = cluster_code(mass, pos, vel, softening_pc=0.01, substeps="auto", ctx=ctx, integrator="hermite")
+    e0 = energy(auto)
+    auto.evolve_model(span | units.Myr)
+    n1 = None
+    first = auto.substeps  # already the suggestion for the NEXT call
+    assert first >= 1 and first & (first - 1) == 0
+    # the count used for the first call came from eta * min |a|/|j|
+    a, j = oracle.self_gravity_hermite(pos, vel, mass, EPS2, G, VTL)
+    dt0 = 0.14 * np.sqrt(((a * a).sum(axis=0) / (j * j).sum(axis=0)).min())
+    n1 = int(2 ** max(0, int(np.ceil(np.log2(span / dt0)))))
+    fixed = cluster_code(mass, pos, vel, softening_pc=0.01, substeps=n1, ctx=ctx, integrator="hermite")
+    fixed.evolve_model(span | units.Myr)
+    assert np.array_equal(auto.pos.cpu().numpy(), fixed.pos.cpu().numpy())
+    assert span / first <= auto.dt_min.item() * (1 + 1e-12) or first == auto.max_substeps
+    one = cluster_code(mass, pos, vel, softening_pc=0.01, substeps=1, ctx=ctx, integrator="hermite")
+    one.evolve_model(span | units.Myr)
+    de_auto, de_one = abs(energy(auto) - e0), abs(energy(one) - e0)
+    assert de_auto <= 1e-5 * abs(e0) and (n1 == 1 or de_auto < de_one)
+    with pytest.raises(ValueError):
+        cluster_code(mass, pos, vel, substeps="auto", ctx=ctx)
