@@ -142,8 +142,8 @@ __device__ __forceinline__ void hermite_tile(const float* __restrict__ stage, co
 }
 
 //   NP : target pairs per thread (targets per thread = 2*NP); NW : warps per CTA; CTA tile = 64*NW*NP targets
-template <int NP, bool POT, bool GUARD, int NW, int UNR>
-__global__ void __launch_bounds__(32 * NW, 1) hermite_tp_kernel(const HermiteParams p) {
+template <int NP, bool POT, bool GUARD, int NW, int UNR, int MINB = 1>
+__global__ void __launch_bounds__(32 * NW, MINB) hermite_tp_kernel(const HermiteParams p) {
   constexpr int NTHR = 32 * NW;
   constexpr int NC = POT ? 7 : 6;
   constexpr int T = 2 * NP;
@@ -335,22 +335,26 @@ __global__ void __launch_bounds__(32 * HM_SMALL_WARPS) hermite_small_kernel(
 typedef void (*hermite_fn)(const HermiteParams);
 struct HermiteVariant {
   const char* name;
-  int np, nw;
+  int np, nw, minb;
   hermite_fn fn[2][2];  // [pot][guard]
 };
-#define HM_V(NP, NW, UNR)                                                                                   \
-  {                                                                                                         \
-    {hermite_tp_kernel<NP, false, false, NW, UNR>, hermite_tp_kernel<NP, false, true, NW, UNR>}, {          \
-      hermite_tp_kernel<NP, true, false, NW, UNR>, hermite_tp_kernel<NP, true, true, NW, UNR>               \
-    }                                                                                                       \
+#define HM_V(NP, NW, UNR, MINB)                                                                                          \
+  {                                                                                                                      \
+    {hermite_tp_kernel<NP, false, false, NW, UNR, MINB>, hermite_tp_kernel<NP, false, true, NW, UNR, MINB>}, {           \
+      hermite_tp_kernel<NP, true, false, NW, UNR, MINB>, hermite_tp_kernel<NP, true, true, NW, UNR, MINB>                \
+    }                                                                                                                    \
   }
 static const HermiteVariant g_hm_variants[] = {
-    {"np4 8w (2048-target tiles)", 4, 8, HM_V(4, 8, 1)},
-    {"np3 8w (1536-target tiles)", 3, 8, HM_V(3, 8, 1)},
-    {"np2 8w (1024-target tiles)", 2, 8, HM_V(2, 8, 1)},
-    {"np2 12w (1536-target tiles)", 2, 12, HM_V(2, 12, 1)},
-    {"np3 12w (2304-target tiles)", 3, 12, HM_V(3, 12, 1)},
-    {"np4 8w unroll 2", 4, 8, HM_V(4, 8, 2)},
+    {"np4 8w (2048-target tiles)", 4, 8, 1, HM_V(4, 8, 1, 1)},
+    {"np3 8w (1536-target tiles)", 3, 8, 1, HM_V(3, 8, 1, 1)},
+    {"np2 8w (1024-target tiles)", 2, 8, 1, HM_V(2, 8, 1, 1)},
+    {"np2 12w (1536-target tiles)", 2, 12, 1, HM_V(2, 12, 1, 1)},
+    {"np3 12w (2304-target tiles)", 3, 12, 1, HM_V(3, 12, 1, 1)},
+    {"np4 8w unroll 2", 4, 8, 1, HM_V(4, 8, 2, 1)},
+    {"np1 8w x 2 CTA/SM (512-target tiles)", 1, 8, 2, HM_V(1, 8, 1, 2)},
+    {"np1 8w x 2 CTA/SM unroll 2", 1, 8, 2, HM_V(1, 8, 2, 2)},
+    {"np2 8w unroll 2", 2, 8, 1, HM_V(2, 8, 2, 1)},
+    {"np1 4w x 3 CTA/SM (256-target tiles)", 1, 4, 3, HM_V(1, 4, 1, 3)},
 };
 #define HM_N_VARIANTS ((int)(sizeof(g_hm_variants) / sizeof(g_hm_variants[0])))
 static int g_hm_force_variant = -1;
@@ -426,15 +430,16 @@ extern "C" int ocg_self_gravity_hermite(ocg_ctx* ctx, const double* pos_dev, con
   }
 
   int variant = g_hm_force_variant;
-  // measured on B200 (tools/bench_hermite.py, profiles/r01_bench_hermite.json): the 1024-target tile (4 targets per
-  // thread, 212 registers, no spills) is the fastest shape at N = 65 536 and on batches of 4096-star clusters
-  if (variant < 0) variant = 2;
+  // measured on B200 (tools/bench_hermite.py, profiles/r01_bench_hermite.json): one target pair per thread, two
+  // 8-warp CTAs per SM (122 registers, 16 warps per SM), 4-source-group loop unrolled twice is the fastest shape at
+  // N = 65 536 (60.6 % of FP32 peak, kernel 62.2 %) and on batches of 4096-star clusters (59.9 %)
+  if (variant < 0) variant = 7;
   const HermiteVariant& v = g_hm_variants[variant];
   const int NTHR = 32 * v.nw, CT = 2 * v.np * NTHR;
 
   OcgClusterPlan plan;
   int rc;
-  if ((rc = ocg_plan_cluster_items(ctx, n, seg_offsets_host, n_seg, tgt_begin, tgt_end, CT, HM_TS, ctx->sm_count, st, &plan, /*which=*/1)))
+  if ((rc = ocg_plan_cluster_items(ctx, n, seg_offsets_host, n_seg, tgt_begin, tgt_end, CT, HM_TS, (long long)ctx->sm_count * v.minb, st, &plan, /*which=*/1)))
     return rc;
   float* tiles;
   float4* tgt;
@@ -457,7 +462,7 @@ extern "C" int ocg_self_gravity_hermite(ocg_ctx* ctx, const double* pos_dev, con
   hermite_fn fn = v.fn[want_pot][guard];
   const size_t smem = HM_NSTAGE * HM_TILE_BYTES + 128 + (size_t)NC * 2 * v.np * NTHR * sizeof(double);
   OCG_CUDA(ctx, cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int grid = ctx->sm_count < p.n_items ? ctx->sm_count : p.n_items;
+  int grid = ctx->sm_count * v.minb < p.n_items ? ctx->sm_count * v.minb : p.n_items;
   if (grid < 1) grid = 1;
   if (ctx->timing) OCG_CUDA(ctx, cudaEventRecord(ctx->ev0, st));
   fn<<<grid, NTHR, smem, st>>>(p);
