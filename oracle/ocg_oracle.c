@@ -17,6 +17,8 @@
  *     support radius h), checked for continuity/Newtonian limits and against scipy quadrature of
  *     the spline density in tests/test_cpu_oracle.py;
  *   - analytic known answers (two-body, shell theorem, homogeneous sphere, affine fields);
+ *   - the reference's kNN + RBF-PHS spatial interpolation (oracle/__init__.py: rbf_interp*): against scipy's cKDTree and
+ *     RBFInterpolator (the rbf author's port) live and through tests/golden/rbf_reference.npz;
  *   - the Hermite force loop and step (ph4 is absent: the scheme is restated from Makino & Aarseth 1992):
  *     jerk against a finite difference of the acceleration along the flow, 4th-order convergence and energy
  *     conservation on a Kepler orbit.

@@ -6,7 +6,9 @@ The GPU box has no /root/reference: tests only read the committed .npz files.
 What can be generated: only `grid_cartesian.py` is importable (numpy only).  Everything else on the hot path
 needs amuse / pykdgrav / rbf / gizmo_analysis, which are absent, and gizmo_interface.py cannot be imported at all
 (analysis.py:573 SyntaxError) — SURVEY.md §0.3.  The reference's time interpolation is scipy's splrep/splev
-(gizmo_interface.py:587-597,38-44), which IS runnable: a fixture of it pins the cubic-in-time "next" row.
+(gizmo_interface.py:587-597,38-44), which IS runnable: a fixture of it pins the cubic-in-time "next" row.  So is its
+neighbour search (scipy's cKDTree over the real grid class's point list); the RBF interpolant itself comes from scipy's
+RBFInterpolator, the `rbf` author's own port: rbf_reference.npz pins the reference-algorithm kick (K7).
 """
 import importlib.util
 import os
@@ -68,6 +70,41 @@ def main():
         vals[:, i] = [float(interpolate.splev(t, tck)) for t in t_eval]
     np.savez_compressed(os.path.join(HERE, "time_spline_reference.npz"), times=times, series=series, t_eval=t_eval,
                         values=vals)
+    # the reference's spatial interpolation (gizmo_interface.py:651-717) on the REAL grid class: cKDTree.query(150) over
+    # grid.evolved_grid — the reference's own neighbour search — and the RBF interpolant through the neighbours.  The `rbf`
+    # package is absent; scipy.interpolate.RBFInterpolator(kernel="cubic", degree=5) is the same author's port of
+    # rbf.interpolate.RBFInterpolant(phs3, order=5) into scipy and evaluates the same interpolant.
+    from scipy.interpolate import RBFInterpolator
+    from scipy.spatial import cKDTree
+    out = {}
+    rbf_cases = [((0.05, 0.05, 0.05, 0.05 / 16), None), ((0.06, 0.06, 0.06, 0.06 / 8), (0.012, 0.012, 0.012, 0.012 / 14))]
+    origin = np.array([8.0, -0.25, 0.125])
+    for k, (cargs, fargs) in enumerate(rbf_cases):
+        g = ref.grid(*cargs)
+        if fargs is not None:
+            g.add_fine_grid(*fargs)
+        g.gen_evolved_grid(origin)
+        pts = g.evolved_grid
+        x, y, z = ((pts - origin) * 40.0).T
+        fields = np.stack([np.sin(x) + y * z, np.cos(y) * x - 0.2 * z, x * x - z + 0.3 * y ** 3])   # ax, ay, az stand-ins
+        rng = np.random.default_rng(1776 + k)
+        half = 0.012 if fargs is None else 0.0035
+        stars = origin + rng.uniform(-half, half, (24, 3))
+        tree = cKDTree(pts)                                    # gizmo_interface.py:642
+        _, ids = tree.query(stars, 150)                        # :654,664
+        vals = np.empty((3, len(stars)))
+        for s in range(len(stars)):
+            for c in range(3):                                 # :666-674, 698-704
+                vals[c, s] = RBFInterpolator(pts[ids[s]], fields[c][ids[s]], kernel="cubic", degree=5)(stars[s][None])[0]
+        out["case%d_coarse_args" % k] = np.array(cargs)
+        out["case%d_fine_args" % k] = np.array(fargs if fargs is not None else [0.0, 0.0, 0.0, 0.0])
+        out["case%d_fields" % k] = fields
+        out["case%d_stars" % k] = stars
+        out["case%d_neighbors" % k] = np.sort(ids, axis=1)
+        out["case%d_values" % k] = vals
+    out["n_cases"] = np.array(len(rbf_cases))
+    out["origin"] = origin
+    np.savez_compressed(os.path.join(HERE, "rbf_reference.npz"), **out)
     print("wrote golden fixtures to", HERE)
 
 

@@ -69,3 +69,30 @@ def test_rbf_neighbour_order_and_ties():
     shell = nb[1:9]
     assert np.all(np.diff(shell) > 0) and np.allclose(d[1:9], d[1])
     assert res["out"][0, 0] == pytest.approx(f[0, -1], abs=1e-12)  # interpolation: exact at a data point
+
+
+def _golden_cases():
+    import os
+    from oc_nbody_b200.grid_cartesian import grid
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "rbf_reference.npz"))
+    origin = z["origin"]
+    for k in range(int(z["n_cases"])):
+        g = grid(*z["case%d_coarse_args" % k])
+        fargs = z["case%d_fine_args" % k]
+        if fargs[3] > 0:
+            g.add_fine_grid(*fargs)
+        g.gen_evolved_grid(origin)
+        yield g, origin, z["case%d_fields" % k], z["case%d_stars" % k], z["case%d_neighbors" % k], z["case%d_values" % k]
+
+
+def test_rbf_oracle_matches_the_golden_fixture():
+    """tests/golden/rbf_reference.npz (made by make_golden.py from the REAL grid class, cKDTree and scipy's RBFInterpolator):
+    single lattice and the nested grid."""
+    n = 0
+    for g, origin, fields, stars, nbr, vals in _golden_cases():
+        h = (g.fine_nodes if g.has_fine_grid else g.nodes)[0]
+        res = oracle.rbf_interp_points(g.evolved_grid, fields, stars[:, 0], stars[:, 1], stars[:, 2], h[1] - h[0], want_neighbors=True)
+        assert np.array_equal(np.sort(res["neighbors"].T, axis=1), nbr)
+        assert np.max(np.abs(res["out"] - vals) / np.abs(vals).max(axis=1, keepdims=True)) <= 1e-9
+        n += 1
+    assert n == 2

@@ -228,3 +228,25 @@ def test_field_code_rbf_on_the_nested_grid(ctx):
     ref = oracle.rbf_interp_points(g.evolved_grid, fld, p[:-1, 0], p[:-1, 1], p[:-1, 2], h, want_neighbors=True)
     assert np.all(ref["neighbors"] >= g.fine_row0)  # every neighbour is a fine point or the origin row
     assert close(got[:, :-1], ref["out"][:3], 1e-9)
+
+
+def test_rbf_matches_the_golden_fixture(ctx):
+    """K7 against tests/golden/rbf_reference.npz — cKDTree neighbours and scipy RBFInterpolator values on the point list of
+    the REAL grid class (single lattice, and the nested grid evaluated over its fine level)."""
+    import torch
+    from test_cpu_rbf import _golden_cases
+    for g, origin, fields, stars, nbr, vals in _golden_cases():
+        nested = g.has_fine_grid
+        nodes = g.fine_nodes if nested else g.nodes
+        shape = g.fine_shape if nested else g.shape
+        f = fields[:, g.fine_row0:] if nested else fields
+        n = stars.shape[0]
+        out = torch.empty((3, n), dtype=torch.float64, device="cuda")
+        st = torch.empty(n, dtype=torch.int32, device="cuda")
+        nb = torch.empty((150, n), dtype=torch.int64, device="cuda")
+        ctx.grid_interp_rbf(shape, [dev(a) for a in nodes], dev(origin[None]), dev(f), dev(stars[:, 0]), dev(stars[:, 1]),
+                            dev(stars[:, 2]), None, out, status_out=st, neighbors_out=nb, embedded=nested)
+        assert np.all(st.cpu().numpy() & 0xff == 0)
+        got_nb = np.sort(nb.cpu().numpy().T, axis=1) + (g.fine_row0 if nested else 0)   # indices into the reference's point list
+        assert np.array_equal(got_nb, nbr)
+        assert close(out.cpu().numpy(), vals, 1e-9)
