@@ -44,6 +44,21 @@ _DEFAULTS = dict(
 )
 
 
+def clean_Rmag(snap, Rmax):
+    """Drop every particle farther than ``Rmax`` kpc from the galactic centre, species by species, all per-particle
+    arrays alike — ``gizmo_interface._clean_Rmag_`` (gizmo_interface.py:297-304), applied by the reference right after
+    reading the snapshots (:254-255).  In place; returns the snapshot."""
+    for key in snap.keys():
+        part = snap[key]
+        keep = np.where(part.prop("host.distance.total") < Rmax)[0]
+        n = len(part.prop("host.distance.total"))
+        for name in list(part.keys()):
+            arr = part[name]
+            if hasattr(arr, "shape") and len(getattr(arr, "shape", ())) >= 1 and arr.shape[0] == n:
+                part[name] = arr[keep]
+    return snap
+
+
 class gizmo_field(object):
     """Time-varying tidal field on a Cartesian grid that rides with the cluster.
 

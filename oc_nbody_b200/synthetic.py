@@ -19,6 +19,9 @@ class _Species(dict):
             return self["position"]
         if name == "host.velocity.principal":
             return self["velocity"]
+        if name == "host.distance.total":
+            p = self["position"]
+            return np.sqrt((p * p).sum(axis=1))
         if name == "host.distance.principal.cylindrical":
             p = self["position"]
             return np.stack([np.hypot(p[:, 0], p[:, 1]), np.arctan2(p[:, 1], p[:, 0]), p[:, 2]], axis=1)

@@ -226,3 +226,20 @@ def test_reference_algorithm_options_are_validated_on_the_host():
         gizmo_field(dict(base, space_interpolation="rbf", basis="ga"), [_Snap()], build=False)
     with pytest.raises(ValueError):
         cluster_code(np.ones(4), np.zeros((3, 4)), np.zeros((3, 4)), integrator="rk4")
+
+
+def test_clean_Rmag_follows_the_reference_rule():
+    """gizmo_interface.py:297-304: keep rmag < Rmax (strict), every per-particle array of every species."""
+    from oc_nbody_b200.gizmo_field import clean_Rmag
+    from oc_nbody_b200.synthetic import make_snapshot
+    snap = make_snapshot(5000, seed=3)
+    before = {k: (snap[k]["position"].copy(), snap[k]["mass"].copy()) for k in ("star", "dark", "gas")}
+    n_gas_before = len(snap["gas"]["smooth.length"])
+    clean_Rmag(snap, 12.5)
+    for k in ("star", "dark", "gas"):
+        pos0, m0 = before[k]
+        keep = np.sqrt((pos0 * pos0).sum(axis=1)) < 12.5
+        assert np.array_equal(snap[k]["position"], pos0[keep]) and np.array_equal(snap[k]["mass"], m0[keep])
+        assert len(snap[k]["id"]) == keep.sum()
+    assert len(snap["gas"]["smooth.length"]) == len(snap["gas"]["mass"]) < n_gas_before
+    assert snap.snapshot["index"] == 577
