@@ -426,16 +426,27 @@ class gizmo_field(object):
         return [d["rec"][a], d["rec"][b]], fine, [float(wa), float(wb)]
 
     def _rbf_field_(self):
-        """FP64 [4, n_node] device copy of the time-evaluated grid arrays (grid.evolved_acceleration_x/y/z and the
+        """FP64 [4, n_node] device array of the time-evaluated grid fields (grid.evolved_acceleration_x/y/z and the
         potential, gizmo_interface.py:618-620) that the RBF interpolant reads; refreshed when the model time changes.
-        Nested grid: the fine rows + origin row of the point list (see _interp_rbf_)."""
+        Single lattice, linear in time: blended on the device (K2) with no host round trip.  Cubic in time or nested
+        grid: the host-side blend, uploaded (nested: the fine rows + origin row of the point list, see _interp_rbf_)."""
         import torch
-        if getattr(self, "_rbf_cache", None) is None or self._rbf_cache[0] is not self._blend_():
-            b = self._blend_()
-            f = np.concatenate([b[0], b[1][None]], axis=0)
-            if self.grid.has_fine_grid:
-                f = f[:, self.grid.fine_row0:]
-            self._rbf_cache = (b, torch.from_numpy(np.ascontiguousarray(f)).to(self._dev["device"]))
+        d, g = self._dev, self.grid
+        if self.time_interpolation == "linear" and not g.has_fine_grid:
+            a, b, w = self._bracket
+            key = (a, b, w, d["rec"].data_ptr())
+            if getattr(self, "_rbf_cache", None) is None or self._rbf_cache[0] != key:
+                n = d["rec"].shape[1]
+                f = torch.empty((4, n), dtype=torch.float64, device=d["device"])
+                self.ctx.grid_time_blend(d["rec"][a], d["rec"][b] if b != a else None, w, f[:3], f[3])
+                self._rbf_cache = (key, f)
+            return self._rbf_cache[1]
+        blend = self._blend_()
+        if getattr(self, "_rbf_cache", None) is None or self._rbf_cache[0] is not blend:
+            f = np.concatenate([blend[0], blend[1][None]], axis=0)
+            if g.has_fine_grid:
+                f = f[:, g.fine_row0:]
+            self._rbf_cache = (blend, torch.from_numpy(np.ascontiguousarray(f)).to(d["device"]))
         return self._rbf_cache[1]
 
     def _interp_rbf_(self, sx, sy, sz, want_pot, want_tensor):
