@@ -8,16 +8,20 @@ Workload
   N = 1 : BASELINE.json configs[1] — 64^3 (+1 origin) Cartesian grid from a synthetic 10M-particle
           GIZMO-format snapshot, Plummer-softened direct sum, one B200.  A step is one pass of the field build
           over one snapshot (2.62e12 interactions).
-  N > 1 : the same grid; every rank holds its own 10M-particle source shard (1e7*N particles in total, 8e7 at
-          N = 8 ~ configs[4]'s "1e8-particle snapshot sharded"), computes the full-grid partial field, then one
-          NCCL all-reduce (sum, fp64, 3*(64^3+1)) over NVLink and the frame subtraction.  Per-GPU work is fixed:
-          "scaling": "weak".   `--workload c5` runs configs[4] itself (128^3 grid, 1e8 particles split over N).
+  N > 1 : STRONG scaling of that same job (north_star's target): the one 10M-particle snapshot is split over the ranks
+          (rank p takes every N-th particle), every rank computes the full-grid partial field of its shard, then one
+          NCCL all-reduce (sum, fp64, 3*(64^3+1)) over NVLink and the frame subtraction.  `--workload c5s` is the
+          64^3 x 1e8 job north_star names for the 8-GPU target, `--workload c5` configs[4] (128^3 x 1e8);
+          `--scaling weak` keeps the particle count per rank fixed instead.
 
   value : whole-job interactions/s with inputs (FP32 recentred sources/targets) resident in HBM.
   e2e   : same metric through the C-ABI host call ocg_field_build_host (N=1) / the device calls fed from pinned
           host tensors (N>1): FP64 host buffers in, H2D, recentre, K1, [all-reduce], K1b, D2H of the field.
-  --impl reference : the reference's CPU path (the FP64 OpenMP port in oracle/, all host threads) on a bounded
-          sample of the same workload.
+  parity_check : rows of the (all-reduced) raw field against the FP64 oracle over ALL shards, strict metric; the run
+          fails when the raw field misses 1e-5.
+  roofline_k4, bridge_step, cpu_baseline.bridge_step (N=1): K4 at N = 65 536 and the BRIDGE step, GPU and CPU.
+  --impl reference : the reference's CPU path (the FP64 OpenMP port in oracle/, ALL host threads, also under torchrun)
+          on a bounded sample of the same config.
 """
 import argparse
 import json
@@ -33,11 +37,11 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 FLOP_PER_INTERACTION = 20.0  # GPU-Gems-3 ch.31 convention, acc only
-# (workload, grid, sources per GPU) -> DRAM bytes moved by one launch of the streaming kernel (ncu, profiles/)
+# (grid, sources on this GPU) -> DRAM bytes moved by one launch of the streaming kernel (ncu --set full, profiles/)
 NCU_DRAM_BYTES_PER_LAUNCH = {
     # profiles/r01_ncu_dram_bench_full.csv: 249 632 768 B read (tiles + targets; the 200 MB of tiles are re-read from L2)
     # + 667 437 824 B written (FP64 chunk partials) = 0.1 % of HBM bandwidth over the 919 ms launch
-    ("c2", 64, 10000000): 249632768 + 667437824,
+    (64, 10000000): 249632768 + 667437824,
 }
 G_KPC = 4.398600413517813e-09
 CENTER = np.array([8.0, 0.0, 0.0])
@@ -162,46 +166,97 @@ def reference_time_interp_cost(n_points=16 ** 3 + 1, n_snap=9):
             "note": "reference mechanism run with scipy as-is, 1 process; here evolve_model is O(1) and the blend is fused into K3"}
 
 
-def run_reference(args):
+def host_threads():
+    """Every host core this process may use (torchrun exports OMP_NUM_THREADS=1: not what a CPU baseline wants)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except (AttributeError, OSError):
+        return max(1, os.cpu_count() or 1)
+
+
+def sample_sources(args):
+    """The bounded source sample the CPU legs use: the first 1e6 particles of an equally shaped snapshot."""
+    return make_sources(min(args.n_src_total, 1000000), seed=1776)
+
+
+def run_reference(args, world):
     """--impl reference: the reference's CPU path = the oracle port (the reference itself cannot be imported:
-    SURVEY §0.3), all host threads, each step a bounded sample of the N=1 workload."""
+    SURVEY §0.3), ALL host threads (also under torchrun), on the same config as the repo arm at this N; each step is a
+    bounded sample of that workload.  Rank 0 alone runs; the other ranks exit without work."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    import oracle
+    threads = oracle.set_num_threads(host_threads())
     g = make_targets(args.grid)
-    n_sample_src = min(args.n_src, 1000000)
-    pos, mass, eps = make_sources(n_sample_src, seed=1776)
-    rates, desc, threads = [], "", 1
+    pos, mass, eps = sample_sources(args)
+    rates, secs, desc = [], [], ""
     per_step = max(2.0, min(20.0, 120.0 / max(1, args.steps + args.warmup)))
     for i in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
         r, desc, threads = cpu_sample_rate(g.evolved_grid, pos, mass, eps, per_step)
         if i >= args.warmup:
             rates.append(r)
+            secs.append(time.perf_counter() - t0)
     val = float(np.mean(rates)) / 1e9
-    inter_step = float(len(g)) * args.n_src
+    inter_step = float(len(g)) * args.n_src_total
     line = {
         "impl": "reference", "metric": "pairwise_grav_interactions_per_sec", "value": val, "unit": "G/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": inter_step / (val * 1e9) * 1e3, "higher_is_better": True, "scaling": "weak",
+        "ms_per_step": float(np.mean(secs)) * 1e3, "higher_is_better": True, "scaling": args.scaling,
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(args, 1),
+        "config": workload_config(args, world),
         "cpu_baseline": {"value": val, "unit": "G/s", "cores": threads, "kind": "port", "sample": desc},
         "e2e": {"value": val, "unit": "G/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
+        "ms_per_full_step_extrapolated": inter_step / (val * 1e9) * 1e3,
         "reference_time_interp": reference_time_interp_cost(),
-        "note": "ms_per_step extrapolates the sampled rate to the full step (a direct sum's rate is size independent)",
+        "note": "a step here is the bounded sample named in cpu_baseline.sample (ms_per_step is its wall time); the rate of "
+                "a direct sum is size independent, ms_per_full_step_extrapolated applies it to the whole workload",
     }
     print(json.dumps(line))
 
 
 def workload_config(args, n_gpus):
-    return {"workload": "%s: %d^3+1 grid targets x %d synthetic snapshot particles per GPU (%d total), Plummer-softened "
-                        "direct-sum field build" % ("configs[4]" if args.workload == "c5" else "configs[1]", args.grid,
-                                                    args.n_src_rank, args.n_src_rank * n_gpus),
-            "grid": args.grid, "n_targets": args.grid ** 3 + 1, "n_sources_per_gpu": args.n_src_rank,
-            "n_sources_total": args.n_src_rank * n_gpus, "softening": "plummer, per-source epsilon",
-            "parallelism": "source-sharded x%d + NCCL all-reduce(fp64)" % n_gpus if n_gpus > 1 else "single GPU",
-            "l2_policy": "inputs larger than L2 (%.0f MB of sources per GPU vs 126 MB L2)" % (args.n_src_rank * 20 / 1e6)}
+    name = {"c2": "configs[1]", "c5": "configs[4]", "c5s": "64^3 x 1e8 (north_star strong-scaling target)"}[args.workload]
+    return {"workload": "%s: %d^3+1 grid targets x %d synthetic snapshot particles in total, Plummer-softened direct-sum field "
+                        "build" % (name, args.grid, args.n_src_total),
+            "grid": args.grid, "n_targets": args.grid ** 3 + 1, "n_sources_total": args.n_src_total,
+            "softening": "plummer, per-source epsilon", "scaling": args.scaling,
+            "parallelism": "source-sharded (every n-th particle) + NCCL all-reduce(fp64) over the ranks; 1 rank = single GPU",
+            "l2_policy": "inputs larger than L2 at N=1 (%.0f MB of sources vs 126 MB L2); at N>1 the FP64 chunk partials "
+                         "(> 600 MB per step) flush L2 between steps" % (args.n_src_total * 20 / 1e6)}
+
+
+def cpu_bridge_step_ms(n_stars, steps):
+    """BRIDGE step on the host: the CPU pipeline assembled from the oracle (tests/test_gpu_fullsize.py::
+    test_config0_full_bridge_run) — trilinear + linear-in-time tidal kick from a 16^3 grid, FP64 OpenMP direct-sum
+    self-gravity, KDK leapfrog — all host threads."""
+    import oracle
+    from oc_nbody_b200.synthetic import make_plummer_cluster
+    from oc_nbody_b200.cluster import KMS_TO_KPC_PER_MYR
+    from oc_nbody_b200.units import G_KPC_KMS_MYR
+    nn = 16
+    rng = np.random.default_rng(7)
+    ax = np.linspace(-0.05, 0.05, nn)
+    recs = [oracle.pack_planes(rng.normal(0, 1e-3, (3, nn ** 3 + 1))) for _ in range(2)]
+    pos_pc, vel, mass = make_plummer_cluster(n_stars)
+    x, v = pos_pc * 1e-3 + CENTER[:, None], vel.copy()
+    eps2, dt = (0.01e-3) ** 2, 0.1
+
+    def tidal(xx, w):
+        return oracle.grid_interp([ax, ax, ax], CENTER[None], recs[0], recs[1], w, xx[0], xx[1], xx[2])
+    ts = []
+    for i in range(steps + 1):
+        t0 = time.perf_counter()
+        v = oracle.kick(v, tidal(x, 0.1), 0.5 * dt)
+        v = oracle.kick(v, oracle.self_gravity(x, mass, eps2, G_KPC_KMS_MYR), 0.5 * dt)
+        x = oracle.drift(x, v, dt, KMS_TO_KPC_PER_MYR)
+        v = oracle.kick(v, oracle.self_gravity(x, mass, eps2, G_KPC_KMS_MYR), 0.5 * dt)
+        v = oracle.kick(v, tidal(x, 0.2), 0.5 * dt)
+        if i:
+            ts.append(time.perf_counter() - t0)
+    return float(np.median(ts)) * 1e3
 
 
 def bridge_step_times(ctx):
@@ -273,6 +328,38 @@ def bridge_step_times(ctx):
     return out
 
 
+def k4_roofline(ctx, nominal):
+    """Second roofline entry (driver-run): K4 cluster self-gravity at configs[2]'s N = 65 536 (4.29e9 interactions per
+    evaluation), whole evaluation (pack + kernel + finish) timed with CUDA events, L2 flushed by the >126 MB partials."""
+    import torch
+    from oc_nbody_b200.synthetic import make_plummer_cluster
+    n = 65536
+    pos_pc, _, mass = make_plummer_cluster(n)
+    dev = torch.device("cuda", ctx.device)
+    d_pos = torch.from_numpy(np.ascontiguousarray(pos_pc * 1e-3 + CENTER[:, None])).to(dev)
+    d_m = torch.from_numpy(mass).to(dev)
+    acc = torch.empty((3, n), dtype=torch.float64, device=dev)
+    ts, ks = [], []
+    ctx.set_kernel_timing(True)
+    for i in range(10):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        ctx.self_gravity(d_pos, d_m, (0.01e-3) ** 2, G_KPC, acc)
+        e1.record()
+        torch.cuda.synchronize()
+        if i >= 3:
+            ts.append(e0.elapsed_time(e1))
+            ks.append(ctx.last_direct_kernel_ms())
+    ctx.set_kernel_timing(False)
+    ms, kms = float(np.median(ts)), float(np.median(ks))
+    inter = float(n) * n
+    ach = FLOP_PER_INTERACTION * inter / (ms * 1e-3) / 1e12
+    return {"bound": "fp32", "kernel": "K4 ocg_self_gravity, N = 65536 (configs[2]): pack + direct_sum_tp_kernel + finish",
+            "achieved": ach, "peak": nominal, "unit": "TFLOP/s", "frac": ach / nominal, "traffic": None,
+            "ms_per_evaluation": ms, "kernel_ms": kms, "frac_kernel_alone": FLOP_PER_INTERACTION * inter / (kms * 1e-3) / 1e12 / nominal,
+            "interactions_per_launch": inter, "flop_per_interaction": FLOP_PER_INTERACTION}
+
+
 # ------------------------------------------------------------------------------------ main ----
 def main():
     ap = argparse.ArgumentParser()
@@ -280,26 +367,27 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="c2", choices=["c2", "c5"])
-    ap.add_argument("--n-src", type=float, default=None, help="override particles per GPU (debug)")
+    ap.add_argument("--workload", default="c2", choices=["c2", "c5", "c5s"],
+                    help="c2 = configs[1] (64^3 x 1e7); c5 = configs[4] (128^3 x 1e8); c5s = 64^3 x 1e8")
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
+                    help="strong (default): the workload's total particle count is split over the ranks; weak: every rank "
+                         "holds that many particles")
+    ap.add_argument("--n-src", type=float, default=None, help="override the particle count (debug)")
     ap.add_argument("--grid", type=int, default=None, help="override grid nodes per axis (debug)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--variant", default="auto", help="auto | kernel tuning-variant id (debug)")
+    ap.add_argument("--no-extras", action="store_true", help="skip the BRIDGE-step and K4 extras (profiling runs)")
+    ap.add_argument("--variant", default="auto", help="auto | kernel shape id (debug)")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if args.workload == "c5":
-        args.grid = args.grid or 128
-        args.n_src_rank = int(args.n_src or 1e8 / world)
-    else:
-        args.grid = args.grid or 64
-        args.n_src_rank = int(args.n_src or 1e7)
-    args.n_src = args.n_src_rank
+    args.grid = args.grid or (128 if args.workload == "c5" else 64)
+    base = int(args.n_src or (1e7 if args.workload == "c2" else 1e8))
+    args.n_src_total = base * world if args.scaling == "weak" else base
     if args.warmup < 3:
         args.warmup = 3  # timing rule: W >= 3
     if args.impl == "reference":
-        return run_reference(args)
+        return run_reference(args, world)
 
     import torch
     import torch.distributed as dist
@@ -311,15 +399,20 @@ def main():
     from oc_nbody_b200 import Context
     ctx = Context(local_rank)
     if args.variant != "auto":
-        ctx.lib.ocg_debug_set_variant(int(args.variant))
+        ctx.debug_set("direct_variant", int(args.variant))
     dev = torch.device("cuda", local_rank)
 
     g = make_targets(args.grid)
     n_tgt = len(g)
-    pos, mass, eps = make_sources(args.n_src_rank, seed=1776 + rank)
+    # strong scaling: ONE snapshot (the N = 1 workload), rank p takes every world-th particle starting at p, so the shards
+    # are statistically alike (equal near-field work); weak scaling: every rank generates its own snapshot
+    if args.scaling == "weak":
+        pos, mass, eps = make_sources(base, seed=1776 + rank)
+    else:
+        pos, mass, eps = (np.ascontiguousarray(a[rank::world]) for a in make_sources(base, seed=1776))
     n_src = pos.shape[0]
     inter_rank = float(n_src) * n_tgt
-    inter_total = inter_rank * world
+    inter_total = float(args.n_src_total) * n_tgt
 
     # pinned host buffers (e2e path) and resident device inputs (value path)
     h_pos, h_mass, h_eps = (torch.from_numpy(a).pin_memory() for a in (pos, mass, eps))
@@ -333,11 +426,12 @@ def main():
     acc = torch.empty((3, n_tgt), dtype=torch.float64, device=dev)
     torch.cuda.synchronize()
 
-    def step_resident():
+    def step_resident(subtract=True):
         ctx.field_direct(d_src, d_eps, d_tgt, 0, G_KPC, acc)
         if world > 1:
             dist.all_reduce(acc)
-        ctx.frame_subtract(acc, g.origin_row)
+        if subtract:
+            ctx.frame_subtract(acc, g.origin_row)
 
     def step_e2e():
         if world == 1:
@@ -373,6 +467,32 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
+    # ---- parity self-check (untimed): rows of the (all-reduced) raw field against the FP64 oracle over ALL shards ----
+    parity = None
+    step_resident(subtract=False)
+    rows = np.unique(np.concatenate([np.linspace(0, n_tgt - 2, 16).astype(np.int64), [g.origin_row]]))
+    got_rows = acc[:, torch.from_numpy(rows).to(dev)].cpu().numpy()
+    if rank == 0 and not args.no_cpu_baseline:
+        import oracle
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        from util import rel_err
+        oracle.set_num_threads(host_threads())
+        fp, fm, fe = make_sources(base, seed=1776) if (world > 1 and args.scaling == "strong") else (pos, mass, eps)
+        if args.scaling == "weak" and world > 1:
+            parts = [make_sources(base, seed=1776 + r) for r in range(world)]
+            fp, fm, fe = (np.concatenate([q[k] for q in parts]) for k in range(3))
+        s32 = oracle.recentre(fp, fm, CENTER)
+        t32 = oracle.recentre(g.evolved_grid[rows], None, CENTER)
+        ref = oracle.field_direct(s32, fe.astype(np.float32), t32, oracle.KERNEL_PLUMMER, G_KPC)
+        o = int(np.nonzero(rows == g.origin_row)[0][0])
+        keep = np.arange(len(rows)) != o
+        parity = {"rows": int(len(rows)), "sources": int(s32.shape[0]), "tolerance": 1e-5,
+                  "metric": "max_c |a - a_ref| / max(|a_ref,c|, 1e-3 ||a_ref||), FP64 oracle on the same FP32-rounded inputs",
+                  "raw_field": rel_err(got_rows, ref),
+                  "tidal_residual": rel_err((got_rows - got_rows[:, o:o + 1])[:, keep], (ref - ref[:, o:o + 1])[:, keep])}
+        parity["ok"] = bool(parity["raw_field"] <= 1e-5)
+        del s32, fp, fm, fe
+
     # ---- resident (device-timed) ----
     for _ in range(args.warmup):
         step_resident()
@@ -398,17 +518,19 @@ def main():
     h2d = n_src * (24 + 8 + 8) + n_tgt * 24
     d2h = n_tgt * 24
 
-    # ---- roofline of the dominant kernel (direct_sum_kernel), FP32 pipe ----
+    # ---- roofline of the dominant kernel (direct_sum_tp_kernel), FP32 pipe ----
     k_ms = float(np.mean(kernel_ms))
     achieved = FLOP_PER_INTERACTION * inter_rank / (k_ms * 1e-3) / 1e12
     nominal = ctx.sm_count * 128 * 2 * ctx.sm_clock_khz * 1e3 / 1e12
     ffma = ctx.probe_throughput(0)
     ffma2 = ctx.probe_throughput(1)
-    # DRAM bytes per launch of the dominant kernel, from the committed ncu capture of this same command
-    # (profiles/r01_ncu_summary.md: dram__bytes_read.sum + dram__bytes_write.sum); not re-measured here
-    traffic = NCU_DRAM_BYTES_PER_LAUNCH.get((args.workload, args.grid, args.n_src_rank))
+    # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture of this same command
+    # (dram__bytes_read.sum + dram__bytes_write.sum, profiles/); null when no capture exists for this configuration.
+    # traffic_model is what the launch must move: source tiles + targets once, FP64 chunk partials written once.
+    traffic = NCU_DRAM_BYTES_PER_LAUNCH.get((args.grid, n_src))
     roofline = {"bound": "fp32", "achieved": achieved, "peak": nominal, "unit": "TFLOP/s", "frac": achieved / nominal,
-                "traffic": traffic, "kernel": "direct_sum_tp_kernel (target-paired, mass-folded tiles; K1 fast set)",
+                "traffic": traffic, "traffic_model": ctx.last_direct_traffic_model(),
+                "kernel": "direct_sum_tp_kernel (target-paired, mass-folded tiles, FP32 runs of 64 sources folded into FP64; K1 fast set)",
                 "kernel_ms": k_ms, "kernel_share_of_step": k_ms / ms_per_step,
                 "bound_note": "FP32 FMA-pipe bound (north_star: no tensor cores; HBM traffic negligible)",
                 "peak_kind": "nominal FP32: %d SM x 128 lanes x 2 flop x %.3f GHz (MEASURED_PEAKS.json has no FP32 entry)" % (
@@ -421,23 +543,35 @@ def main():
         if world > 1:
             dist.destroy_process_group()
         return
-    bridge = bridge_step_times(ctx) if world == 1 else None
+    extras = world == 1 and not args.no_extras
+    bridge = bridge_step_times(ctx) if extras else None
+    roofline_k4 = k4_roofline(ctx, nominal) if extras else None
     cpu = None
     if not args.no_cpu_baseline:
-        r, desc, threads = cpu_sample_rate(g.evolved_grid, pos[:1000000], mass[:1000000], eps[:1000000], 15.0)
+        import oracle
+        oracle.set_num_threads(host_threads())
+        sp, sm, se = sample_sources(args)
+        r, desc, threads = cpu_sample_rate(g.evolved_grid, sp, sm, se, 15.0)
         cpu = {"value": r / 1e9, "unit": "G/s", "cores": threads, "kind": "port", "sample": desc}
+        if extras:
+            cpu["bridge_step"] = {"unit": "ms", "cores": threads, "kind": "port",
+                                  "1024_stars": cpu_bridge_step_ms(1024, 8), "65536_stars": cpu_bridge_step_ms(65536, 2),
+                                  "what": "oracle pipeline: trilinear + linear-in-time tidal kick (16^3 grid), FP64 OpenMP direct-sum "
+                                          "self-gravity, KDK leapfrog (the CPU side of tests/test_gpu_fullsize.py::test_config0_full_bridge_run)"}
     line = {
         "metric": "pairwise_grav_interactions_per_sec", "value": value, "unit": "G/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak" if args.workload == "c2" else "strong",
+        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": args.scaling,
         "vs_baseline": None, "dtype": "f32", "dtype_note": "f32 pair arithmetic, f64 per-target accumulation", "data": "synthetic",
         "config": workload_config(args, world),
         "clocks": clocks,
-        "e2e": {"value": e2e_value, "unit": "G/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+        "e2e": {"value": e2e_value, "unit": "G/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
                 "api": "ocg_field_build_host (C ABI, host buffers)" if world == 1 else
-                       "pinned host tensors -> ocg_recentre_f64/ocg_field_direct/all_reduce/ocg_frame_subtract -> host"},
+                       "pinned host tensors -> ocg_recentre_f64/ocg_field_direct/all_reduce/ocg_frame_subtract -> host, every rank"},
         "gpu_launches": launches,
         "roofline": roofline,
+        "roofline_k4": roofline_k4,
         "cpu_baseline": cpu,
+        "parity_check": parity,
         "pct_fp32_peak": 100.0 * achieved / nominal,
         "bridge_step": bridge,
         "origin_row_abs_max": result_check,
@@ -445,6 +579,8 @@ def main():
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+    if parity is not None and not parity["ok"]:
+        raise SystemExit("bench.py: parity self-check failed: %r" % (parity,))
 
 
 if __name__ == "__main__":

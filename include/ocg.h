@@ -32,7 +32,12 @@
 extern "C" {
 #endif
 
-#define OCG_VERSION 100 /* 0.1.0 */
+/* The library is built with -fvisibility=hidden; only the entry points declared here (and in ocg_debug.h) are exported. */
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)
+#endif
+
+#define OCG_VERSION 200 /* 0.2.0 */
 
 /* status codes */
 #define OCG_OK 0
@@ -62,6 +67,9 @@ int64_t ocg_launch_count(const ocg_ctx* ctx);
 double ocg_last_direct_kernel_ms(ocg_ctx* ctx);
 /* Enable(1)/disable(0) event timing around the direct-sum kernel (default off). */
 int ocg_set_kernel_timing(ocg_ctx* ctx, int enabled);
+/* Bytes the streaming kernel of the most recent ocg_field_direct call has to move through HBM (source tiles and
+ * targets read once, FP64 chunk partials written once): the model bench.py prints beside the ncu-measured traffic. */
+int64_t ocg_last_direct_traffic_bytes(const ocg_ctx* ctx);
 
 /* ---- K0: recentre fp64 -> fp32 ------------------------------------------------
  * out_xyzw[i] = (float)(pos[i] - center) , w = (float)mass[i] (or 0 when mass_dev == NULL).
@@ -295,6 +303,9 @@ int ocg_compact_rows(ocg_ctx* ctx, const double* in_dev, int32_t rows, int64_t n
  * achieved TFLOP/s (2 flop per lane-FMA). which: 0 FFMA, 1 FFMA2, 2 MUFU.RSQ (G ops/s).     */
 double ocg_probe_throughput(ocg_ctx* ctx, int which);
 
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
 #ifdef __cplusplus
 }
 #endif

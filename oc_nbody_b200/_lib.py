@@ -10,6 +10,8 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "liboc_nbody_b200.so")
+# the -DOCG_TUNING build (every sweep shape + timing-only experiments); only tools/ ask for it, via OCG_TUNING_LIB=1
+LIB_PATH_TUNING = os.path.join(_HERE, "lib", "liboc_nbody_b200_tuning.so")
 
 KERNEL_PLUMMER = 0
 KERNEL_SPLINE = 1
@@ -18,10 +20,17 @@ KERNELS = {"plummer": KERNEL_PLUMMER, "spline": KERNEL_SPLINE}
 # every symbol include/ocg.h declares (tests check the library exports them all)
 ABI_SYMBOLS = [
     "ocg_version", "ocg_create", "ocg_destroy", "ocg_last_error", "ocg_device_info", "ocg_launch_count",
-    "ocg_last_direct_kernel_ms", "ocg_set_kernel_timing", "ocg_recentre_f64", "ocg_cast_f64_f32",
+    "ocg_last_direct_kernel_ms", "ocg_set_kernel_timing", "ocg_last_direct_traffic_bytes", "ocg_recentre_f64", "ocg_cast_f64_f32",
     "ocg_field_direct", "ocg_frame_subtract", "ocg_field_build_host", "ocg_pack_planes", "ocg_grid_time_blend",
     "ocg_grid_interp", "ocg_grid_interp_multi", "ocg_grid_interp_nested", "ocg_pack_planes_indexed", "ocg_set_interp_weight_slots", "ocg_grid_interp_slot", "ocg_grid_interp_rbf", "ocg_self_gravity", "ocg_self_gravity_hermite", "ocg_hermite_predict", "ocg_hermite_correct", "ocg_bound_com", "ocg_eject_mask", "ocg_compact_rows", "ocg_kick", "ocg_drift", "ocg_axpy", "ocg_probe_throughput",
 ]
+
+
+# include/ocg_debug.h (test / tuning hooks; not part of the drop-in ABI)
+DEBUG_SYMBOLS = ["ocg_debug_set", "ocg_debug_variant_count", "ocg_debug_variant_name", "ocg_debug_variant_built",
+                 "ocg_debug_rbf_phase_cycles"]
+KNOBS = {"direct_variant": 0, "precise_near": 1, "mass_fold": 2, "small_cluster_path": 3, "host_chunk": 4,
+         "hermite_variant": 5, "hermite_small_path": 6, "interp_variant": 7, "rbf_share": 8}
 
 
 class OcgError(RuntimeError):
@@ -41,10 +50,11 @@ def load_library():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
+    path = LIB_PATH_TUNING if os.environ.get("OCG_TUNING_LIB") == "1" else LIB_PATH
+    if not os.path.exists(path):
         raise OcgError("%s is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
-                       "(oc_nbody_b200 has no CPU fallback)" % LIB_PATH)
-    L = ctypes.CDLL(LIB_PATH)
+                       "(oc_nbody_b200 has no CPU fallback)" % path)
+    L = ctypes.CDLL(path)
     vp, i32, i64, dbl = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_double
     L.ocg_version.restype = ctypes.c_int
     L.ocg_create.argtypes = [ctypes.c_int, ctypes.POINTER(vp)]
@@ -57,6 +67,8 @@ def load_library():
     L.ocg_last_direct_kernel_ms.restype = dbl
     L.ocg_last_direct_kernel_ms.argtypes = [vp]
     L.ocg_set_kernel_timing.argtypes = [vp, ctypes.c_int]
+    L.ocg_last_direct_traffic_bytes.restype = i64
+    L.ocg_last_direct_traffic_bytes.argtypes = [vp]
     L.ocg_recentre_f64.argtypes = [vp, vp, vp, i64, ctypes.POINTER(dbl), vp, vp]
     L.ocg_cast_f64_f32.argtypes = [vp, vp, i64, vp, vp]
     L.ocg_field_direct.argtypes = [vp, vp, vp, i64, vp, i64, ctypes.c_int, dbl, vp, vp, ctypes.c_int, vp]
@@ -78,11 +90,12 @@ def load_library():
     L.ocg_self_gravity_hermite.argtypes = [vp, vp, vp, vp, i64, vp, i32, dbl, dbl, dbl, i64, i64, vp, vp, vp, vp]
     L.ocg_hermite_predict.argtypes = [vp, vp, vp, vp, vp, i64, dbl, dbl, vp, vp, vp]
     L.ocg_hermite_correct.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, dbl, dbl, dbl, vp, vp]
-    L.ocg_debug_rbf_phase_cycles.argtypes = [ctypes.POINTER(ctypes.c_double)]
-    L.ocg_debug_set_hermite_variant.argtypes = [ctypes.c_int]
-    L.ocg_debug_hermite_variant_name.restype = ctypes.c_char_p
-    L.ocg_debug_hermite_variant_name.argtypes = [ctypes.c_int]
-    L.ocg_debug_set_hermite_small_path.argtypes = [ctypes.c_int]
+    L.ocg_debug_rbf_phase_cycles.argtypes = [vp, ctypes.POINTER(ctypes.c_double)]
+    L.ocg_debug_set.argtypes = [vp, ctypes.c_int, i64]
+    L.ocg_debug_variant_count.argtypes = [ctypes.c_int]
+    L.ocg_debug_variant_name.restype = ctypes.c_char_p
+    L.ocg_debug_variant_name.argtypes = [ctypes.c_int, ctypes.c_int]
+    L.ocg_debug_variant_built.argtypes = [ctypes.c_int, ctypes.c_int]
     L.ocg_bound_com.argtypes = [vp, vp, vp, vp, vp, i64, vp, i32, dbl, vp, vp, vp]
     L.ocg_eject_mask.argtypes = [vp, vp, i64, dbl, dbl, vp, vp, vp]
     L.ocg_compact_rows.argtypes = [vp, vp, i32, i64, vp, vp, i64, vp, vp]
@@ -91,13 +104,6 @@ def load_library():
     L.ocg_axpy.argtypes = [vp, vp, vp, dbl, i64, vp]
     L.ocg_probe_throughput.restype = dbl
     L.ocg_probe_throughput.argtypes = [vp, ctypes.c_int]
-    L.ocg_debug_set_variant.argtypes = [ctypes.c_int]
-    L.ocg_debug_variant_name.restype = ctypes.c_char_p
-    L.ocg_debug_variant_name.argtypes = [ctypes.c_int]
-    L.ocg_debug_set_precise_near.argtypes = [ctypes.c_int]
-    L.ocg_debug_set_mass_fold.argtypes = [ctypes.c_int]
-    L.ocg_debug_set_small_cluster_path.argtypes = [ctypes.c_int]
-    L.ocg_debug_set_host_chunk.argtypes = [ctypes.c_int64]
     _lib = L
     return L
 
@@ -156,6 +162,19 @@ class Context:
         import torch
         return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
+    # ---- test / tuning hooks (include/ocg_debug.h): state of THIS ctx ----
+    def debug_set(self, knob, value):
+        self._ck(self.lib.ocg_debug_set(self.h, KNOBS[knob], int(value)), "ocg_debug_set(%s)" % knob)
+
+    def variant_count(self, family=0):
+        return int(self.lib.ocg_debug_variant_count(int(family)))
+
+    def variant_name(self, vid, family=0):
+        return self.lib.ocg_debug_variant_name(int(family), int(vid)).decode()
+
+    def variant_built(self, vid, family=0):
+        return bool(self.lib.ocg_debug_variant_built(int(family), int(vid)))
+
     # ---- bookkeeping ----
     def launch_count(self):
         return int(self.lib.ocg_launch_count(self.h))
@@ -165,6 +184,9 @@ class Context:
 
     def last_direct_kernel_ms(self):
         return float(self.lib.ocg_last_direct_kernel_ms(self.h))
+
+    def last_direct_traffic_model(self):
+        return int(self.lib.ocg_last_direct_traffic_bytes(self.h))
 
     def probe_throughput(self, which):
         v = float(self.lib.ocg_probe_throughput(self.h, int(which)))

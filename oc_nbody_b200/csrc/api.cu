@@ -1,9 +1,11 @@
 // Context, scratch, small element-wise kernels and the host-buffer form of the field build.
 #include "ocg_internal.cuh"
+#include "../../include/ocg_debug.h"
 
 #include <stdarg.h>
 #include <stdlib.h>
 
+#define OCG_HOST_CHUNK_DEFAULT (1ll << 26)
 static char g_create_err[512] = "";
 
 int ocg_fail(ocg_ctx* ctx, int code, const char* fmt, ...) {
@@ -71,6 +73,16 @@ extern "C" int ocg_create(int device, ocg_ctx** out) {
   ocg_ctx* ctx = (ocg_ctx*)calloc(1, sizeof(ocg_ctx));
   if (!ctx) return ocg_fail(nullptr, OCG_ERR_NOMEM, "calloc failed");
   ctx->device = device;
+  ctx->knobs.direct_variant = -1;
+  ctx->knobs.precise_near = 1;
+  ctx->knobs.mass_fold = 1;
+  ctx->knobs.small_cluster_path = 1;
+  ctx->knobs.host_chunk = OCG_HOST_CHUNK_DEFAULT;
+  ctx->knobs.hermite_variant = -1;
+  ctx->knobs.hermite_small_path = 1;
+  ctx->knobs.interp_variant = 2;
+  ctx->knobs.field_precision = 0;
+  ctx->knobs.rbf_share = 1;
   ctx->sm_count = prop.multiProcessorCount;
   int khz = 0;
   cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, device);
@@ -118,6 +130,8 @@ extern "C" int ocg_set_kernel_timing(ocg_ctx* ctx, int enabled) {
   return OCG_OK;
 }
 
+extern "C" int64_t ocg_last_direct_traffic_bytes(const ocg_ctx* ctx) { return ctx ? (int64_t)ctx->last_traffic_bytes : -1; }
+
 extern "C" double ocg_last_direct_kernel_ms(ocg_ctx* ctx) {
   if (!ctx || !ctx->ev_valid) return -1.0;
   OcgDeviceGuard g(ctx->device);
@@ -125,6 +139,45 @@ extern "C" double ocg_last_direct_kernel_ms(ocg_ctx* ctx) {
   float ms = 0.f;
   if (cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1) != cudaSuccess) return -1.0;
   return (double)ms;
+}
+
+// ---------------------------------------------------------- tuning / test knobs (include/ocg_debug.h) ----
+extern "C" int ocg_debug_set(ocg_ctx* ctx, int knob, int64_t value) {
+  if (!ctx) return OCG_ERR_INVALID;
+  OcgKnobs& k = ctx->knobs;
+  switch (knob) {
+    case OCG_KNOB_DIRECT_VARIANT:
+      if (value >= 0 && !ocg_direct_variant_built((int)value))
+        return ocg_fail(ctx, OCG_ERR_INVALID, "K1/K4 shape %lld is not in this build (sweep shapes need the OCG_TUNING library)",
+                        (long long)value);
+      k.direct_variant = value < 0 ? -1 : (int)value;
+      return OCG_OK;
+    case OCG_KNOB_PRECISE_NEAR: k.precise_near = value != 0; return OCG_OK;
+    case OCG_KNOB_MASS_FOLD: k.mass_fold = value != 0; return OCG_OK;
+    case OCG_KNOB_SMALL_CLUSTER_PATH: k.small_cluster_path = value != 0; return OCG_OK;
+    case OCG_KNOB_HOST_CHUNK: k.host_chunk = value > 0 ? value : OCG_HOST_CHUNK_DEFAULT; return OCG_OK;
+    case OCG_KNOB_HERMITE_VARIANT:
+      if (value >= ocg_hermite_n_variants()) return ocg_fail(ctx, OCG_ERR_INVALID, "no Hermite shape %lld", (long long)value);
+      k.hermite_variant = value < 0 ? -1 : (int)value;
+      return OCG_OK;
+    case OCG_KNOB_HERMITE_SMALL_PATH: k.hermite_small_path = value != 0; return OCG_OK;
+    case OCG_KNOB_INTERP_VARIANT:
+      if (value < 0 || value > 2) return ocg_fail(ctx, OCG_ERR_INVALID, "K3 register bound %lld outside 0..2", (long long)value);
+      k.interp_variant = (int)value;
+      return OCG_OK;
+    case OCG_KNOB_RBF_SHARE: k.rbf_share = value != 0; return OCG_OK;
+    default: return ocg_fail(ctx, OCG_ERR_INVALID, "ocg_debug_set: unknown knob %d", knob);
+  }
+}
+extern "C" int ocg_debug_variant_count(int family) {
+  return family == 0 ? ocg_direct_n_variants() : family == 1 ? ocg_hermite_n_variants() : 0;
+}
+extern "C" const char* ocg_debug_variant_name(int family, int id) {
+  return family == 0 ? ocg_direct_variant_name(id) : family == 1 ? ocg_hermite_variant_name(id) : "";
+}
+extern "C" int ocg_debug_variant_built(int family, int id) {
+  if (family == 0) return ocg_direct_variant_built(id) ? 1 : 0;
+  return id >= 0 && id < ocg_hermite_n_variants() ? 1 : 0;
 }
 
 // ---------------------------------------------------------------------------- K0 kernels ----
@@ -220,11 +273,6 @@ extern "C" int ocg_frame_subtract(ocg_ctx* ctx, double* acc_dev, int64_t n_tgt, 
 // --------------------------------------------------------------- K1 host form (e2e path) ----
 // Sources are streamed through HBM in chunks of this many particles (accumulate = 1 after the first): bounded device
 // memory (~100 B per staged particle) for snapshots of any size, and no 2^31 limit on n_src.
-static int64_t g_host_chunk = 1ll << 26;
-extern "C" int ocg_debug_set_host_chunk(int64_t n) {
-  g_host_chunk = n > 0 ? n : (1ll << 26);
-  return 0;
-}
 
 extern "C" int ocg_field_build_host(ocg_ctx* ctx, const double* src_pos_host, const double* src_mass_host,
                                     const double* src_soft_host, int64_t n_src, const double* tgt_pos_host,
@@ -244,7 +292,7 @@ extern "C" int ocg_field_build_host(ocg_ctx* ctx, const double* src_pos_host, co
   float *d_src, *d_sft = nullptr, *d_tgt;
   int rc;
   const int NCO = pot_host ? 4 : 3;
-  const int64_t chunk = n_src < g_host_chunk ? n_src : g_host_chunk;  // particles staged at a time
+  const int64_t chunk = n_src < ctx->knobs.host_chunk ? n_src : ctx->knobs.host_chunk;  // particles staged at a time
   if ((rc = ocg_scratch(ctx, OCG_SCR_F64A, sizeof(double) * 3 * (size_t)(chunk > n_tgt ? chunk : n_tgt), (void**)&d_pos))) return rc;
   if ((rc = ocg_scratch(ctx, OCG_SCR_F64B, sizeof(double) * (size_t)(chunk > 0 ? chunk : 1), (void**)&d_mass))) return rc;
   if ((rc = ocg_scratch(ctx, OCG_SCR_SRC, sizeof(float) * 4 * (size_t)(chunk > 0 ? chunk : 1), (void**)&d_src))) return rc;

@@ -365,7 +365,8 @@ __global__ void __launch_bounds__(OCG_CONSUMER_THREADS + (DED ? 32 : 0), MINB) d
 // 11 FMA-pipe operations per interaction instead of 12 (ceiling 20/22 = 91% of FP32 peak instead of 83%).
 // The price is the rounding of xs' = fl(w*xs): relative error 2^-24 |xs|/|d| in d', bounded because every
 // source closer to the target box than the precision radius is in the FP64 NEAR set (direct_sum.cu).
-template <int NP, bool POT, int UNR, int DBG, int MF = 0>
+// FOLD: sources per call (one FP32 accumulation run); `stage` points at the first of them inside the tile.
+template <int NP, bool POT, int UNR, int DBG, int MF = 0, int FOLD = OCG_TS>
 __device__ __forceinline__ void tile_tpair(const float* __restrict__ stage, const u64 (&ntx)[NP], const u64 (&nty)[NP],
                                            const u64 (&ntz)[NP], u64 (&ax)[NP], u64 (&ay)[NP], u64 (&az)[NP],
                                            u64 (&ap)[NP]) {
@@ -374,18 +375,20 @@ __device__ __forceinline__ void tile_tpair(const float* __restrict__ stage, cons
   const float4* sz = sy + OCG_TS / 4;
   const float4* sm = sz + OCG_TS / 4;
   const float4* se = sm + OCG_TS / 4;
+  const float4* sv = se + OCG_TS / 4;  // mass-folded tiles with potential: 6th array, 1/w = (m/M0)^1/2
   float4 X0 = sx[0], Y0 = sy[0], Z0 = sz[0], M0 = sm[0], E0 = se[0];
 #pragma unroll UNR
-  for (int j = 0; j < OCG_TS / 4; ++j) {
-    float4 X, Y, Z, M, E;
+  for (int j = 0; j < FOLD / 4; ++j) {
+    float4 X, Y, Z, M, E, V = make_float4(0.f, 0.f, 0.f, 0.f);
     if (DBG & 2) {
       X = X0, Y = Y0, Z = Z0, M = M0, E = E0;
       X0.x += 1e-7f;  // keep the loop body from being hoisted
     } else {
       X = sx[j], Y = sy[j], Z = sz[j], M = sm[j], E = se[j];
+      if (MF && POT) V = sv[j];
     }
     const float xs[4] = {X.x, X.y, X.z, X.w}, ys[4] = {Y.x, Y.y, Y.z, Y.w}, zs[4] = {Z.x, Z.y, Z.z, Z.w};
-    const float ms[4] = {M.x, M.y, M.z, M.w}, es[4] = {E.x, E.y, E.z, E.w};
+    const float ms[4] = {M.x, M.y, M.z, M.w}, es[4] = {E.x, E.y, E.z, E.w}, vs[4] = {V.x, V.y, V.z, V.w};
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       // duplicated source scalars: ptxas folds them into broadcast (.F32) operands
@@ -416,8 +419,12 @@ __device__ __forceinline__ void tile_tpair(const float* __restrict__ stage, cons
           y3 = f2_pack(rsqrt_approx(r6a), rsqrt_approx(r6b));
         }
         const u64 sc = MF ? y3 : f2_mul(y3, mb);
-        if (POT) ap[p] = f2_fma(sc, r2, ap[p]);  // plain tiles only (a mass-folded potential needs 2 more ops + 1/w:
-                                                 // measured slower than the plain form, profiles/r01_variant_sweep2.json)
+        if (POT) {
+          // plain: m y3 r2 = m/r.  mass-folded: y3' r2' = 1/(w r), times 1/w = (m/M0)/r: one more multiply, the same
+          // 13 FMA-pipe operations per interaction as the plain form with potential
+          if (MF) ap[p] = f2_fma(f2_mul(y3, r2), f2_pack(vs[q], vs[q]), ap[p]);
+          else ap[p] = f2_fma(sc, r2, ap[p]);
+        }
         if (DBG & 8) {  // two distinct register pairs per instruction instead of three
           ax[p] = f2_fma(dx, ax[p], ax[p]);
           ay[p] = f2_fma(dy, ay[p], ay[p]);
@@ -433,14 +440,22 @@ __device__ __forceinline__ void tile_tpair(const float* __restrict__ stage, cons
 }
 
 //   NW      : consumer warps per CTA (CTA = 32*NW threads; CTA tile = 64*NW*NP targets)
-template <int NP, bool POT, bool SMEMACC, int MINB, int UNR, int NW = OCG_CONSUMER_WARPS, int DBG = 0, int MF = 0>
+//   FOLD    : sources per FP32 accumulation run.  The FP32 partial sums of a run are folded into the FP64 per-target
+//             accumulators after FOLD sources; the rounding error of the FP32 running sums grows linearly with FOLD and
+//             is THE error term of the kernel (tools/sim_fp32_error.py: with exact accumulation the tidal residual is
+//             good to 7e-7 strict, with FOLD = 512 to 7e-5), so FOLD is the accuracy/throughput knob.
+template <int NP, bool POT, bool SMEMACC, int MINB, int UNR, int NW = OCG_CONSUMER_WARPS, int DBG = 0, int MF = 0,
+          int FOLD = OCG_TS>
 __global__ void __launch_bounds__(32 * NW, MINB) direct_sum_tp_kernel(const DirectParams p) {
+  static_assert(OCG_TS % FOLD == 0 && FOLD % 4 == 0, "FOLD must divide the tile");
   constexpr int NTHR = 32 * NW;
+  constexpr int TILE_FLOATS = OCG_TILE_ARRAYS(MF, POT) * OCG_TS, TILE_BYTES = TILE_FLOATS * 4;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float* stage_base = reinterpret_cast<float*>(smem_raw);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_raw + OCG_NSTAGE * OCG_TILE_BYTES);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_raw + OCG_NSTAGE * TILE_BYTES);
   uint64_t* empty_bar = full_bar + OCG_NSTAGE;
-  double* sacc = reinterpret_cast<double*>(smem_raw + OCG_NSTAGE * OCG_TILE_BYTES + 128);  // [NC][2*NP][256]
+  // FP64 accumulators: the two targets of a pair sit side by side, sacc2[(c*NP + pp)*NTHR + tid] = {2pp, 2pp+1}
+  double2* sacc2 = reinterpret_cast<double2*>(smem_raw + OCG_NSTAGE * TILE_BYTES + 128);
   constexpr int NC = POT ? 4 : 3;
   constexpr int T = 2 * NP;
   const int tid = threadIdx.x;
@@ -459,8 +474,8 @@ __global__ void __launch_bounds__(32 * NW, MINB) direct_sum_tp_kernel(const Dire
   auto issue_tile = [&](uint32_t n, const float* src) {
     const uint32_t s = n % OCG_NSTAGE, ph = (n / OCG_NSTAGE) & 1u;
     mbar_wait(&empty_bar[s], ph ^ 1u);
-    mbar_expect_tx(&full_bar[s], OCG_TILE_BYTES);
-    tma_bulk_g2s(stage_base + s * OCG_TILE_FLOATS, src, OCG_TILE_BYTES, &full_bar[s]);
+    mbar_expect_tx(&full_bar[s], TILE_BYTES);
+    tma_bulk_g2s(stage_base + s * TILE_FLOATS, src, TILE_BYTES, &full_bar[s]);
   };
 
   const float scale = p.scale_ptr ? *p.scale_ptr : p.scale_val;
@@ -468,10 +483,10 @@ __global__ void __launch_bounds__(32 * NW, MINB) direct_sum_tp_kernel(const Dire
     long long tgt_begin, tile_begin, slot;
     int tgt_count, tile_count;
     decode_item<T, NTHR>(p, item, tgt_begin, tgt_count, tile_begin, tile_count, slot);
-    const float* src = p.tiles + tile_begin * (long long)OCG_TILE_FLOATS;
+    const float* src = p.tiles + tile_begin * (long long)TILE_FLOATS;
     if (tid == 0) {
       const int pre = tile_count < OCG_NSTAGE - 1 ? tile_count : OCG_NSTAGE - 1;
-      for (int k = 0; k < pre; ++k) issue_tile(it + k, src + (long long)k * OCG_TILE_FLOATS);
+      for (int k = 0; k < pre; ++k) issue_tile(it + k, src + (long long)k * TILE_FLOATS);
     }
 
     u64 ntx[NP], nty[NP], ntz[NP];
@@ -490,7 +505,7 @@ __global__ void __launch_bounds__(32 * NW, MINB) direct_sum_tp_kernel(const Dire
     }
     if (SMEMACC) {
 #pragma unroll
-      for (int i = 0; i < NC * T; ++i) sacc[i * NTHR + tid] = 0.0;
+      for (int i = 0; i < NC * NP; ++i) sacc2[i * NTHR + tid] = make_double2(0.0, 0.0);
     } else {
 #pragma unroll
       for (int t = 0; t < T; ++t)
@@ -500,31 +515,41 @@ __global__ void __launch_bounds__(32 * NW, MINB) direct_sum_tp_kernel(const Dire
 
     for (int k = 0; k < tile_count; ++k, ++it) {
       if (tid == 0 && k + OCG_NSTAGE - 1 < tile_count)
-        issue_tile(it + OCG_NSTAGE - 1, src + (long long)(k + OCG_NSTAGE - 1) * OCG_TILE_FLOATS);
+        issue_tile(it + OCG_NSTAGE - 1, src + (long long)(k + OCG_NSTAGE - 1) * TILE_FLOATS);
       const uint32_t s = it % OCG_NSTAGE, ph = (it / OCG_NSTAGE) & 1u;
       mbar_wait(&full_bar[s], ph);
-      u64 ax[NP], ay[NP], az[NP], ap[NP];
+#pragma unroll 1
+      for (int b = 0; b < OCG_TS / FOLD; ++b) {
+        u64 ax[NP], ay[NP], az[NP], ap[NP];
 #pragma unroll
-      for (int pp = 0; pp < NP; ++pp) ax[pp] = ay[pp] = az[pp] = ap[pp] = 0ull;
-      tile_tpair<NP, POT, UNR, DBG, MF>(stage_base + s * OCG_TILE_FLOATS, ntx, nty, ntz, ax, ay, az, ap);
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&empty_bar[s]);
-      // fold this tile's FP32 sums into the FP64 accumulators (lane lo -> target 2p, hi -> target 2p+1)
+        for (int pp = 0; pp < NP; ++pp) ax[pp] = ay[pp] = az[pp] = ap[pp] = 0ull;
+        tile_tpair<NP, POT, UNR, DBG, MF, FOLD>(stage_base + s * TILE_FLOATS + b * FOLD, ntx, nty, ntz, ax, ay, az, ap);
+        if (b == OCG_TS / FOLD - 1) {  // the stage has been read: hand it back before folding
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&empty_bar[s]);
+        }
+        // fold this run's FP32 sums into the FP64 accumulators (lane lo -> target 2p, hi -> target 2p+1)
 #pragma unroll
-      for (int pp = 0; pp < NP; ++pp) {
-        float v[4][2];
-        f2_unpack(ax[pp], v[0][0], v[0][1]);
-        f2_unpack(ay[pp], v[1][0], v[1][1]);
-        f2_unpack(az[pp], v[2][0], v[2][1]);
-        f2_unpack(ap[pp], v[3][0], v[3][1]);
-#pragma unroll
-        for (int h = 0; h < 2; ++h)
+        for (int pp = 0; pp < NP; ++pp) {
+          float v[4][2];
+          f2_unpack(ax[pp], v[0][0], v[0][1]);
+          f2_unpack(ay[pp], v[1][0], v[1][1]);
+          f2_unpack(az[pp], v[2][0], v[2][1]);
+          f2_unpack(ap[pp], v[3][0], v[3][1]);
 #pragma unroll
           for (int c = 0; c < NC; ++c) {
-            const double add = c < 3 ? (double)v[c][h] : -(double)v[3][h];
-            if (SMEMACC) sacc[(c * T + 2 * pp + h) * NTHR + tid] += add;
-            else dacc[SMEMACC ? 0 : 2 * pp + h][c] += add;
+            const double a0 = c < 3 ? (double)v[c][0] : -(double)v[3][0];
+            const double a1 = c < 3 ? (double)v[c][1] : -(double)v[3][1];
+            if (SMEMACC) {
+              double2 q = sacc2[(c * NP + pp) * NTHR + tid];
+              q.x += a0, q.y += a1;
+              sacc2[(c * NP + pp) * NTHR + tid] = q;
+            } else {
+              dacc[SMEMACC ? 0 : 2 * pp][c] += a0;
+              dacc[SMEMACC ? 0 : 2 * pp + 1][c] += a1;
+            }
           }
+        }
       }
     }
 
@@ -534,9 +559,16 @@ __global__ void __launch_bounds__(32 * NW, MINB) direct_sum_tp_kernel(const Dire
       if (local < tgt_count) {
         const long long gi = tgt_begin + local;
 #pragma unroll
-        for (int c = 0; c < NC; ++c)
-          p.partial[(slot * NC + c) * p.out_stride + gi] =
-              SMEMACC ? sacc[(c * T + t) * NTHR + tid] : dacc[SMEMACC ? 0 : t][c];
+        for (int c = 0; c < NC; ++c) {
+          double v;
+          if (SMEMACC) {
+            const double2 q = sacc2[(c * NP + (t >> 1)) * NTHR + tid];
+            v = (t & 1) ? q.y : q.x;
+          } else {
+            v = dacc[SMEMACC ? 0 : t][c];
+          }
+          p.partial[(slot * NC + c) * p.out_stride + gi] = v;
+        }
       }
     }
   }

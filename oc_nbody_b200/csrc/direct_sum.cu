@@ -4,17 +4,20 @@
 // (gizmo_interface.py:561,564,566 — a theta=0.5 monopole tree in un-vendored pykdgrav), with the
 // exact theta->0 sum, and the ph4 force loop behind oc_code.py:218-229.
 //
-// Design (see DESIGN.md §K1):
-//  * sources are re-laid once per call into component-major tiles (x|y|z|m|e2, OCG_TS each) and
+// Design (see DESIGN.md §4 K1):
+//  * sources are re-laid once per call into component-major tiles of OCG_TS sources — plain
+//    (x|y|z|m|e2) or mass-folded (w*x|w*y|w*z|w|w^2*e2, w = (m/M0)^-1/2, the w array pair-swizzled) — and
 //    split into a FAST set (every target sees them as Plummer(e2) or pure Newtonian) and a NEAR set
-//    (spline sources whose support can reach the target box; singular e2==0 sources inside it);
-//  * the fast kernel streams tiles through a 4-stage shared-memory ring filled by one TMA bulk
-//    copy per tile (cp.async.bulk + mbarrier), a dedicated producer warp, 8 consumer warps;
-//  * the inner loop is packed FP32: FADD2/FFMA2/FMUL2 on two sources at a time + 2 MUFU.RSQ,
-//    12 FMA-pipe instructions per 2 interactions; FP32 partial sums live for one tile (512
-//    sources) and are folded into FP64 per-target accumulators;
-//  * work = (target tile x source chunk) items, statically strided over a persistent grid of
-//    2 CTAs/SM; chunk partials are summed in fixed order by a finish kernel => deterministic.
+//    (spline sources whose support can reach the target box; singular e2 == 0 sources inside it; sources
+//    inside the precision radius), the latter evaluated pair by pair in FP64;
+//  * the fast kernel streams tiles through a 4-stage shared-memory ring filled by one TMA bulk copy per
+//    tile (cp.async.bulk + mbarrier), issued in line by thread 0 of the CTA (no producer warp);
+//  * the inner loop is packed FP32 with the two lanes of an instruction holding two TARGETS and the source
+//    a broadcast operand: 11 (mass-folded) or 12 FMA-pipe instructions + 2 MUFU.RSQ per 2 interactions;
+//    FP32 partial sums live for one run of FOLD sources and are then folded into FP64 per-target
+//    accumulators in shared memory;
+//  * work = (target tile x source chunk) items, statically strided over a persistent grid of one CTA per
+//    SM; chunk partials are summed in fixed order by a finish kernel => run-to-run deterministic.
 #include "ocg_internal.cuh"
 
 #include <math.h>
@@ -269,7 +272,7 @@ __global__ void __launch_bounds__(1024) classify_scan_kernel(int* counts, int nb
 __global__ void __launch_bounds__(CLS_BLOCK) classify_scatter_kernel(
     const float4* __restrict__ src, const float* __restrict__ soft, long long n, int kernel,
     const int* __restrict__ misc, const int* __restrict__ fast_off, float* __restrict__ tiles,
-    float4* __restrict__ near_xyzm, float* __restrict__ near_soft, int mf) {
+    float4* __restrict__ near_xyzm, float* __restrict__ near_soft, int mf, int narr) {
   __shared__ int wbase[CLS_BLOCK / 32];
   long long i = blockIdx.x * (long long)CLS_BLOCK + threadIdx.x;
   bool valid = i < n, fast = false;
@@ -302,7 +305,7 @@ __global__ void __launch_bounds__(CLS_BLOCK) classify_scatter_kernel(
     long long pos = foff + rank_fast;
     long long tile = pos / OCG_TS;
     int j = (int)(pos - tile * OCG_TS);
-    float* T = tiles + tile * (long long)OCG_TILE_FLOATS;
+    float* T = tiles + tile * (long long)narr * OCG_TS;
     // spline sources that reach the fast set are Newtonian for every target: e2 = 0;
     // Plummer sources whose scaled e2 is negligible are far enough (d2 > R2_MIN) to drop it too
     float hs = h * sc;
@@ -316,6 +319,7 @@ __global__ void __launch_bounds__(CLS_BLOCK) classify_scatter_kernel(
       T[2 * OCG_TS + j] = massless ? 0.f : (S.z * sc) * w;
       T[3 * OCG_TS + (mf == 2 ? (j ^ 1) : j)] = w;
       T[4 * OCG_TS + j] = massless ? 1.f : (e2 * w) * w;
+      if (narr == 6) T[5 * OCG_TS + j] = massless ? 0.f : (float)sqrt((double)(S.w / __int_as_float(misc[MISC_M0])));  // 1/w
     } else {
       T[j] = S.x * sc;
       T[OCG_TS + j] = S.y * sc;
@@ -331,18 +335,19 @@ __global__ void __launch_bounds__(CLS_BLOCK) classify_scatter_kernel(
 }
 
 // Pad the tail of the last fast tile with zero-mass sources (contribute exactly 0; in the mass-folded
-// layout the same record reads w = 0, w*x = 0, w^2*e2 = 1: d' = 0, y3 = 1, d'*y3 = 0).
-__global__ void pad_tiles_kernel(float* tiles, const int* misc, int mf) {
+// layout the same record reads w = 0, w*x = 0, w^2*e2 = 1, 1/w := 0: d' = 0, y3 = 1, d'*y3 = 0, (y3*r2)*0 = 0).
+__global__ void pad_tiles_kernel(float* tiles, const int* misc, int mf, int narr) {
   int nf = misc[MISC_NFAST];
   int nt = misc[MISC_NFAST_TILES];
   long long end = (long long)nt * OCG_TS;
   for (long long pos = nf + threadIdx.x; pos < end; pos += blockDim.x) {
     long long tile = pos / OCG_TS;
     int j = (int)(pos - tile * OCG_TS);
-    float* T = tiles + tile * (long long)OCG_TILE_FLOATS;
+    float* T = tiles + tile * (long long)narr * OCG_TS;
     T[j] = 0.f, T[OCG_TS + j] = 0.f, T[2 * OCG_TS + j] = 0.f;
     T[3 * OCG_TS + (mf == 2 ? (j ^ 1) : j)] = 0.f;  // pair-swizzled w array: the pad owns slot j^1, not j
     T[4 * OCG_TS + j] = 1.f;
+    if (narr == 6) T[5 * OCG_TS + j] = 0.f;
   }
 }
 
@@ -440,11 +445,14 @@ __global__ void __launch_bounds__(NEAR_BLOCK) near_sum_kernel(
 }
 
 // ------------------------------------------------------------------------------ launchers ----
+typedef void (*direct_fn)(const DirectParams);
 static size_t direct_smem_bytes() { return OCG_NSTAGE * OCG_TILE_BYTES + 2 * OCG_NSTAGE * 8; }
 
-typedef void (*direct_fn)(const DirectParams);
-
-// A tuning variant of the streaming kernel. fn[pot][guard]; sweep-only variants fill fn[0][0] only.
+// A shape of the streaming kernel. fn[pot][guard]; entries without a form are null.  The table index is the variant id
+// quoted in profiles/ (stable across rounds).  Only the PRODUCTION shapes are compiled into the shipped library; the
+// sweep shapes and the timing experiments (DBG != 0: wrong results by construction) exist only in the -DOCG_TUNING
+// build (oc_nbody_b200/build.py tuning=True -> liboc_nbody_b200_tuning.so), where tools/probe.py selects them through
+// ocg_debug_set (include/ocg_debug.h).
 struct DirectVariant {
   const char* name;
   int tpt, minb;
@@ -455,6 +463,12 @@ struct DirectVariant {
   int mf;              // consumes mass-folded tiles (K1 without potential only); 2 = w array pair-swizzled
 };
 static inline int variant_threads(const DirectVariant& v) { return 32 * (v.nwarps ? v.nwarps : OCG_CONSUMER_WARPS); }
+#define OCG_NOFN {{nullptr, nullptr}, {nullptr, nullptr}}
+#ifdef OCG_TUNING
+#define TUNE(...) __VA_ARGS__
+#else
+#define TUNE(...) OCG_NOFN
+#endif
 #define OCG_FULL(TPT, PACKED, DED, MINB, UNR)                                                            \
   {                                                                                                      \
     {direct_sum_kernel<TPT, false, false, PACKED, DED, MINB, UNR>,                                       \
@@ -480,6 +494,12 @@ static inline int variant_threads(const DirectVariant& v) { return 32 * (v.nwarp
     {direct_sum_tp_kernel<NP, false, SMEMACC, MINB, UNR, NW>, nullptr},                                  \
     { direct_sum_tp_kernel<NP, true, SMEMACC, MINB, UNR, NW>, nullptr }                                  \
   }
+/* plain tiles, with and without potential, FP32 runs of FOLD sources */
+#define OCG_TPWF(NP, SMEMACC, MINB, UNR, NW, FOLD)                                                       \
+  {                                                                                                      \
+    {direct_sum_tp_kernel<NP, false, SMEMACC, MINB, UNR, NW, 0, 0, FOLD>, nullptr},                      \
+    { direct_sum_tp_kernel<NP, true, SMEMACC, MINB, UNR, NW, 0, 0, FOLD>, nullptr }                      \
+  }
 #define OCG_TPMF(NP, SMEMACC, MINB, UNR, NW)                                                             \
   {                                                                                                      \
     {direct_sum_tp_kernel<NP, false, SMEMACC, MINB, UNR, NW, 0, 1>, nullptr}, { nullptr, nullptr }       \
@@ -488,116 +508,132 @@ static inline int variant_threads(const DirectVariant& v) { return 32 * (v.nwarp
   {                                                                                                      \
     {direct_sum_tp_kernel<NP, false, SMEMACC, MINB, UNR, NW, DBG, MF>, nullptr}, { nullptr, nullptr }    \
   }
-
+/* mass-folded, pair-swizzled tiles, FP32 runs of FOLD sources */
+#define OCG_TPMFF(NP, MINB, UNR, NW, FOLD)                                                               \
+  {                                                                                                      \
+    {direct_sum_tp_kernel<NP, false, true, MINB, UNR, NW, 0, 2, FOLD>, nullptr}, { nullptr, nullptr }    \
+  }
+/* mass-folded, pair-swizzled tiles, with and without potential (6- and 5-array tiles), SMEMACC selectable */
+#define OCG_TPMFP(NP, SMEMACC, MINB, UNR, NW, FOLD)                                                      \
+  {                                                                                                      \
+    {direct_sum_tp_kernel<NP, false, SMEMACC, MINB, UNR, NW, 0, 2, FOLD>, nullptr},                      \
+    { direct_sum_tp_kernel<NP, true, SMEMACC, MINB, UNR, NW, 0, 2, FOLD>, nullptr }                      \
+  }
 #define OCG_TPD(NP, SMEMACC, MINB, UNR, NW, DBG)                                                         \
   {                                                                                                      \
     {direct_sum_tp_kernel<NP, false, SMEMACC, MINB, UNR, NW, DBG>, nullptr}, { nullptr, nullptr }        \
   }
 static const DirectVariant g_variants[] = {
-    /* 0 */ {"tpt2 packed ded minb2 unr2", 2, 2, true, OCG_FULL(2, true, true, 2, 2)},
-    /* 1 */ {"tpt1 packed ded minb2 unr2", 1, 2, true, OCG_FULL(1, true, true, 2, 2)},
-    /* 2 */ {"tpt2 scalar ded minb2 unr2", 2, 2, true, OCG_FULL(2, false, true, 2, 2)},
-    /* 3 */ {"tpt1 scalar ded minb2 unr2", 1, 2, true, OCG_FULL(1, false, true, 2, 2)},
-    /* 4 */ {"tpt2 packed inl minb2 unr2", 2, 2, false, OCG_FULL(2, true, false, 2, 2)},
-    /* 5 */ {"tpt1 packed inl minb3 unr2", 1, 3, false, OCG_ONE(1, true, false, 3, 2)},
-    /* 6 */ {"tpt1 packed inl minb4 unr2", 1, 4, false, OCG_ONE(1, true, false, 4, 2)},
-    /* 7 */ {"tpt2 packed inl minb3 unr2", 2, 3, false, OCG_ONE(2, true, false, 3, 2)},
-    /* 8 */ {"tpt2 packed inl minb2 unr4", 2, 2, false, OCG_ONE(2, true, false, 2, 4)},
-    /* 9 */ {"tpt1 packed inl minb3 unr4", 1, 3, false, OCG_ONE(1, true, false, 3, 4)},
-    /* 10 */ {"tpt2 packed ded minb2 unr1", 2, 2, true, OCG_ONE(2, true, true, 2, 1)},
-    /* 11 */ {"tpt2 packed inl minb2 unr1", 2, 2, false, OCG_ONE(2, true, false, 2, 1)},
-    /* 12 */ {"tpt1 packed inl minb2 unr2", 1, 2, false, OCG_ONE(1, true, false, 2, 2)},
-    /* 13 */ {"tpt1 packed inl minb3 unr1", 1, 3, false, OCG_ONE(1, true, false, 3, 1)},
-    /* 14 */ {"tpt2 packed ded minb2 unr4", 2, 2, true, OCG_ONE(2, true, true, 2, 4)},
-    /* 15 */ {"tpt2 packed inl minb2 unr2 pipe", 2, 2, false, OCG_ONEP(2, false, 2, 2)},
-    /* 16 */ {"tpt2 packed inl minb2 unr1 pipe", 2, 2, false, OCG_ONEP(2, false, 2, 1)},
-    /* 17 */ {"tpt2 packed ded minb2 unr2 pipe", 2, 2, true, OCG_ONEP(2, true, 2, 2)},
-    /* 18 */ {"tpt1 packed inl minb3 unr2 pipe", 1, 3, false, OCG_ONEP(1, false, 3, 2)},
-    /* 19 */ {"tpt1 packed inl minb2 unr4 pipe", 1, 2, false, OCG_ONEP(1, false, 2, 4)},
-    /* 20 */ {"tpt2 packed inl minb2 unr4 pipe", 2, 2, false, OCG_ONEP(2, false, 2, 4)},
-    /* 21 */ {"tpair np2 (4 tgt/thr) regacc minb2 unr1", 4, 2, false, OCG_TP(2, false, 2, 1), 0},
-    /* 22 */ {"tpair np2 (4 tgt/thr) regacc minb2 unr2", 4, 2, false, OCG_TP(2, false, 2, 2), 0},
-    /* 23 */ {"tpair np2 (4 tgt/thr) smemacc minb2 unr1", 4, 2, false, OCG_TP(2, true, 2, 1), 4},
-    /* 24 */ {"tpair np4 (8 tgt/thr) smemacc minb2 unr1", 8, 2, false, OCG_TP(4, true, 2, 1), 8},
-    /* 25 */ {"tpair np3 (6 tgt/thr) smemacc minb2 unr1", 6, 2, false, OCG_TP(3, true, 2, 1), 6},
-    /* 26 */ {"tpair np4 (8 tgt/thr) smemacc minb1 unr1", 8, 1, false, OCG_TP(4, true, 1, 1), 8},
-    /* 27 */ {"tpair np1 (2 tgt/thr) regacc minb2 unr2", 2, 2, false, OCG_TP(1, false, 2, 2), 0},
-    /* 28 */ {"tpair np2 (4 tgt/thr) regacc minb3 unr1", 4, 3, false, OCG_TP(2, false, 3, 1), 0},
-    /* 29 */ {"tpair np4 smemacc 4w x minb3 (12 w/SM)", 8, 3, false, OCG_TPW(4, true, 3, 1, 4), 8, 4},
-    /* 30 */ {"tpair np3 smemacc 4w x minb3 (12 w/SM)", 6, 3, false, OCG_TPW(3, true, 3, 1, 4), 6, 4},
-    /* 31 */ {"tpair np4 smemacc 12w x minb1 (12 w/SM)", 8, 1, false, OCG_TPW(4, true, 1, 1, 12), 8, 12},
-    /* 32 */ {"tpair np4 smemacc 6w x minb2 (12 w/SM)", 8, 2, false, OCG_TPW(4, true, 2, 1, 6), 8, 6},
-    /* 33 */ {"tpair np2 regacc 4w x minb3 (12 w/SM)", 4, 3, false, OCG_TPW(2, false, 3, 1, 4), 0, 4},
-    /* 34 */ {"tpair np2 regacc 4w x minb3 unr2 (12 w/SM)", 4, 3, false, OCG_TPW(2, false, 3, 2, 4), 0, 4},
-    /* 35 */ {"tpair np4 smemacc 4w x minb2 (8 w/SM)", 8, 2, false, OCG_TPW(4, true, 2, 1, 4), 8, 4},
-    /* 36 */ {"tpair np4 smemacc 10w x minb1 (10 w/SM)", 8, 1, false, OCG_TPW(4, true, 1, 1, 10), 8, 10},
-    /* 37 */ {"DBG np4 12w: no MUFU (timing only)", 8, 1, false, OCG_TPD(4, true, 1, 1, 12, 1), 8, 12},
-    /* 38 */ {"DBG np4 12w: no LDS (timing only)", 8, 1, false, OCG_TPD(4, true, 1, 1, 12, 2), 8, 12},
-    /* 39 */ {"DBG np4 12w: no MUFU, no LDS (timing only)", 8, 1, false, OCG_TPD(4, true, 1, 1, 12, 3), 8, 12},
-    /* 40 */ {"tpair-mf np4 smemacc 12w x minb1", 8, 1, false, OCG_TPMF(4, true, 1, 1, 12), 8, 12, 1},
-    /* 41 */ {"tpair-mf np4 smemacc 4w x minb3", 8, 3, false, OCG_TPMF(4, true, 3, 1, 4), 8, 4, 1},
-    /* 42 */ {"tpair-mf np2 smemacc 8w x minb2", 4, 2, false, OCG_TPMF(2, true, 2, 1, 8), 4, 8, 1},
+    /* 0 */ {"tpt2 packed ded minb2 unr2", 2, 2, true, TUNE(OCG_FULL(2, true, true, 2, 2))},
+    /* 1 */ {"tpt1 packed ded minb2 unr2", 1, 2, true, OCG_FULL(1, true, true, 2, 2)},  // production: SMALL
+    /* 2 */ {"tpt2 scalar ded minb2 unr2", 2, 2, true, TUNE(OCG_FULL(2, false, true, 2, 2))},
+    /* 3 */ {"tpt1 scalar ded minb2 unr2", 1, 2, true, TUNE(OCG_FULL(1, false, true, 2, 2))},
+    /* 4 */ {"tpt2 packed inl minb2 unr2", 2, 2, false, OCG_FULL(2, true, false, 2, 2)},  // production: MID_GUARD
+    /* 5 */ {"tpt1 packed inl minb3 unr2", 1, 3, false, TUNE(OCG_ONE(1, true, false, 3, 2))},
+    /* 6 */ {"tpt1 packed inl minb4 unr2", 1, 4, false, TUNE(OCG_ONE(1, true, false, 4, 2))},
+    /* 7 */ {"tpt2 packed inl minb3 unr2", 2, 3, false, TUNE(OCG_ONE(2, true, false, 3, 2))},
+    /* 8 */ {"tpt2 packed inl minb2 unr4", 2, 2, false, TUNE(OCG_ONE(2, true, false, 2, 4))},
+    /* 9 */ {"tpt1 packed inl minb3 unr4", 1, 3, false, TUNE(OCG_ONE(1, true, false, 3, 4))},
+    /* 10 */ {"tpt2 packed ded minb2 unr1", 2, 2, true, TUNE(OCG_ONE(2, true, true, 2, 1))},
+    /* 11 */ {"tpt2 packed inl minb2 unr1", 2, 2, false, TUNE(OCG_ONE(2, true, false, 2, 1))},
+    /* 12 */ {"tpt1 packed inl minb2 unr2", 1, 2, false, TUNE(OCG_ONE(1, true, false, 2, 2))},
+    /* 13 */ {"tpt1 packed inl minb3 unr1", 1, 3, false, TUNE(OCG_ONE(1, true, false, 3, 1))},
+    /* 14 */ {"tpt2 packed ded minb2 unr4", 2, 2, true, TUNE(OCG_ONE(2, true, true, 2, 4))},
+    /* 15 */ {"tpt2 packed inl minb2 unr2 pipe", 2, 2, false, TUNE(OCG_ONEP(2, false, 2, 2))},
+    /* 16 */ {"tpt2 packed inl minb2 unr1 pipe", 2, 2, false, TUNE(OCG_ONEP(2, false, 2, 1))},
+    /* 17 */ {"tpt2 packed ded minb2 unr2 pipe", 2, 2, true, TUNE(OCG_ONEP(2, true, 2, 2))},
+    /* 18 */ {"tpt1 packed inl minb3 unr2 pipe", 1, 3, false, TUNE(OCG_ONEP(1, false, 3, 2))},
+    /* 19 */ {"tpt1 packed inl minb2 unr4 pipe", 1, 2, false, TUNE(OCG_ONEP(1, false, 2, 4))},
+    /* 20 */ {"tpt2 packed inl minb2 unr4 pipe", 2, 2, false, TUNE(OCG_ONEP(2, false, 2, 4))},
+    /* 21 */ {"tpair np2 (4 tgt/thr) regacc minb2 unr1", 4, 2, false, TUNE(OCG_TP(2, false, 2, 1)), 0},
+    /* 22 */ {"tpair np2 (4 tgt/thr) regacc minb2 unr2", 4, 2, false, TUNE(OCG_TP(2, false, 2, 2)), 0},
+    /* 23 */ {"tpair np2 (4 tgt/thr) smemacc minb2 unr1", 4, 2, false, TUNE(OCG_TP(2, true, 2, 1)), 4},
+    /* 24 */ {"tpair np4 (8 tgt/thr) smemacc minb2 unr1", 8, 2, false, TUNE(OCG_TP(4, true, 2, 1)), 8},
+    /* 25 */ {"tpair np3 (6 tgt/thr) smemacc minb2 unr1", 6, 2, false, TUNE(OCG_TP(3, true, 2, 1)), 6},
+    /* 26 */ {"tpair np4 (8 tgt/thr) smemacc minb1 unr1", 8, 1, false, TUNE(OCG_TP(4, true, 1, 1)), 8},
+    /* 27 */ {"tpair np1 (2 tgt/thr) regacc minb2 unr2", 2, 2, false, OCG_TP(1, false, 2, 2), 0},  // production: MID (K4)
+    /* 28 */ {"tpair np2 (4 tgt/thr) regacc minb3 unr1", 4, 3, false, TUNE(OCG_TP(2, false, 3, 1)), 0},
+    /* 29 */ {"tpair np4 smemacc 4w x minb3 (12 w/SM)", 8, 3, false, TUNE(OCG_TPW(4, true, 3, 1, 4)), 8, 4},
+    /* 30 */ {"tpair np3 smemacc 4w x minb3 (12 w/SM)", 6, 3, false, TUNE(OCG_TPW(3, true, 3, 1, 4)), 6, 4},
+    /* 31 */ {"tpair np4 smemacc 12w x minb1 (12 w/SM)", 8, 1, false, OCG_TPW(4, true, 1, 1, 12), 8, 12},  // production: BIG
+    /* 32 */ {"tpair np4 smemacc 6w x minb2 (12 w/SM)", 8, 2, false, TUNE(OCG_TPW(4, true, 2, 1, 6)), 8, 6},
+    /* 33 */ {"tpair np2 regacc 4w x minb3 (12 w/SM)", 4, 3, false, TUNE(OCG_TPW(2, false, 3, 1, 4)), 0, 4},
+    /* 34 */ {"tpair np2 regacc 4w x minb3 unr2 (12 w/SM)", 4, 3, false, TUNE(OCG_TPW(2, false, 3, 2, 4)), 0, 4},
+    /* 35 */ {"tpair np4 smemacc 4w x minb2 (8 w/SM)", 8, 2, false, TUNE(OCG_TPW(4, true, 2, 1, 4)), 8, 4},
+    /* 36 */ {"tpair np4 smemacc 10w x minb1 (10 w/SM)", 8, 1, false, TUNE(OCG_TPW(4, true, 1, 1, 10)), 8, 10},
+    /* 37 */ {"DBG np4 12w: no MUFU (timing only)", 8, 1, false, TUNE(OCG_TPD(4, true, 1, 1, 12, 1)), 8, 12},
+    /* 38 */ {"DBG np4 12w: no LDS (timing only)", 8, 1, false, TUNE(OCG_TPD(4, true, 1, 1, 12, 2)), 8, 12},
+    /* 39 */ {"DBG np4 12w: no MUFU, no LDS (timing only)", 8, 1, false, TUNE(OCG_TPD(4, true, 1, 1, 12, 3)), 8, 12},
+    /* 40 */ {"tpair-mf np4 smemacc 12w x minb1", 8, 1, false, TUNE(OCG_TPMF(4, true, 1, 1, 12)), 8, 12, 1},
+    /* 41 */ {"tpair-mf np4 smemacc 4w x minb3", 8, 3, false, TUNE(OCG_TPMF(4, true, 3, 1, 4)), 8, 4, 1},
+    /* 42 */ {"tpair-mf np2 smemacc 8w x minb2", 4, 2, false, TUNE(OCG_TPMF(2, true, 2, 1, 8)), 4, 8, 1},
     /* 43 */ {"tpair-mf np1 regacc 8w x minb2 unr2", 2, 2, false,
-              {{direct_sum_tp_kernel<1, false, false, 2, 2, OCG_CONSUMER_WARPS, 0, 1>, nullptr}, {nullptr, nullptr}}, 0, 0, 1},
-    /* 44 */ {"tpair-mf np3 smemacc 12w x minb1", 6, 1, false, OCG_TPMF(3, true, 1, 1, 12), 6, 12, 1},
-    /* 45 */ {"tpair-mf np4 smemacc 12w x minb1 unr2", 8, 1, false, OCG_TPMF(4, true, 1, 2, 12), 8, 12, 1},
-    /* 46 */ {"tpair-mf np4 12w, w pair-swizzled", 8, 1, false, OCG_TPMFX(4, true, 1, 1, 12, 0, 2), 8, 12, 2},
-    /* 47 */ {"tpair-mf np2 8w x minb2, w pair-swizzled", 4, 2, false, OCG_TPMFX(2, true, 2, 1, 8, 0, 2), 4, 8, 2},
-    /* 48 */ {"DBG mf np4 12w: no MUFU", 8, 1, false, OCG_TPMFX(4, true, 1, 1, 12, 4, 1), 8, 12, 1},
-    /* 49 */ {"DBG mf np4 12w: 2-pair accumulate", 8, 1, false, OCG_TPMFX(4, true, 1, 1, 12, 8, 1), 8, 12, 1},
-    /* 50 */ {"DBG mf np4 12w: FADD2 differences", 8, 1, false, OCG_TPMFX(4, true, 1, 1, 12, 16, 1), 8, 12, 1},
-    /* 51 */ {"DBG mf np4 12w: no MUFU + 2-pair accumulate", 8, 1, false, OCG_TPMFX(4, true, 1, 1, 12, 12, 1), 8, 12, 1},
-    /* 52 */ {"DBG mf np4 12w: no MUFU + 2-pair + FADD2", 8, 1, false, OCG_TPMFX(4, true, 1, 1, 12, 28, 1), 8, 12, 1},
-    /* 53 */ {"DBG mf np4 12w swizzled: no MUFU", 8, 1, false, OCG_TPMFX(4, true, 1, 1, 12, 4, 2), 8, 12, 2},
-    /* 54 */ {"DBG mf np4 12w swizzled: no MUFU + 2-pair", 8, 1, false, OCG_TPMFX(4, true, 1, 1, 12, 12, 2), 8, 12, 2},
-    /* 55 */ {"DBG plain np4 12w: no MUFU", 8, 1, false, OCG_TPD(4, true, 1, 1, 12, 4), 8, 12},
-    /* 56 */ {"DBG plain np4 12w: 2-pair accumulate", 8, 1, false, OCG_TPD(4, true, 1, 1, 12, 8), 8, 12},
-    /* 57 */ {"DBG plain np4 12w: no MUFU + 2-pair", 8, 1, false, OCG_TPD(4, true, 1, 1, 12, 12), 8, 12},
-    /* 58 */ {"tpair-mf np6 8w x minb1, swizzled", 12, 1, false, OCG_TPMFX(6, true, 1, 1, 8, 0, 2), 12, 8, 2},
-    /* 59 */ {"tpair-mf np8 8w x minb1, swizzled", 16, 1, false, OCG_TPMFX(8, true, 1, 1, 8, 0, 2), 16, 8, 2},
-    /* 60 */ {"tpair-mf np5 12w x minb1, swizzled", 10, 1, false, OCG_TPMFX(5, true, 1, 1, 12, 0, 2), 10, 12, 2},
-    /* 61 */ {"tpair-mf np6 12w x minb1, swizzled", 12, 1, false, OCG_TPMFX(6, true, 1, 1, 12, 0, 2), 12, 12, 2},
-    /* 62 */ {"tpair-mf np4 12w x minb1 unr2, swizzled", 8, 1, false, OCG_TPMFX(4, true, 1, 2, 12, 0, 2), 8, 12, 2},
-    /* 63 */ {"tpair-mf np4 4w x minb3, swizzled", 8, 3, false, OCG_TPMFX(4, true, 3, 1, 4, 0, 2), 8, 4, 2},
-    /* 64 */ {"tpair-mf np3 12w x minb1, swizzled", 6, 1, false, OCG_TPMFX(3, true, 1, 1, 12, 0, 2), 6, 12, 2},
-    /* 65 */ {"tpair-mf np4 16w x minb1, swizzled", 8, 1, false, OCG_TPMFX(4, true, 1, 1, 16, 0, 2), 8, 16, 2},
+              TUNE({{direct_sum_tp_kernel<1, false, false, 2, 2, OCG_CONSUMER_WARPS, 0, 1>, nullptr}, {nullptr, nullptr}}), 0, 0, 1},
+    /* 44 */ {"tpair-mf np3 smemacc 12w x minb1", 6, 1, false, TUNE(OCG_TPMF(3, true, 1, 1, 12)), 6, 12, 1},
+    /* 45 */ {"tpair-mf np4 smemacc 12w x minb1 unr2", 8, 1, false, TUNE(OCG_TPMF(4, true, 1, 2, 12)), 8, 12, 1},
+    /* 46 */ {"tpair-mf np4 12w, w pair-swizzled", 8, 1, false, TUNE(OCG_TPMFX(4, true, 1, 1, 12, 0, 2)), 8, 12, 2},
+    /* 47 */ {"tpair-mf np2 8w x minb2, w pair-swizzled", 4, 2, false, TUNE(OCG_TPMFX(2, true, 2, 1, 8, 0, 2)), 4, 8, 2},
+    /* 48 */ {"DBG mf np4 12w: no MUFU", 8, 1, false, TUNE(OCG_TPMFX(4, true, 1, 1, 12, 4, 1)), 8, 12, 1},
+    /* 49 */ {"DBG mf np4 12w: 2-pair accumulate", 8, 1, false, TUNE(OCG_TPMFX(4, true, 1, 1, 12, 8, 1)), 8, 12, 1},
+    /* 50 */ {"DBG mf np4 12w: FADD2 differences", 8, 1, false, TUNE(OCG_TPMFX(4, true, 1, 1, 12, 16, 1)), 8, 12, 1},
+    /* 51 */ {"DBG mf np4 12w: no MUFU + 2-pair accumulate", 8, 1, false, TUNE(OCG_TPMFX(4, true, 1, 1, 12, 12, 1)), 8, 12, 1},
+    /* 52 */ {"DBG mf np4 12w: no MUFU + 2-pair + FADD2", 8, 1, false, TUNE(OCG_TPMFX(4, true, 1, 1, 12, 28, 1)), 8, 12, 1},
+    /* 53 */ {"DBG mf np4 12w swizzled: no MUFU", 8, 1, false, TUNE(OCG_TPMFX(4, true, 1, 1, 12, 4, 2)), 8, 12, 2},
+    /* 54 */ {"DBG mf np4 12w swizzled: no MUFU + 2-pair", 8, 1, false, TUNE(OCG_TPMFX(4, true, 1, 1, 12, 12, 2)), 8, 12, 2},
+    /* 55 */ {"DBG plain np4 12w: no MUFU", 8, 1, false, TUNE(OCG_TPD(4, true, 1, 1, 12, 4)), 8, 12},
+    /* 56 */ {"DBG plain np4 12w: 2-pair accumulate", 8, 1, false, TUNE(OCG_TPD(4, true, 1, 1, 12, 8)), 8, 12},
+    /* 57 */ {"DBG plain np4 12w: no MUFU + 2-pair", 8, 1, false, TUNE(OCG_TPD(4, true, 1, 1, 12, 12)), 8, 12},
+    /* 58 */ {"tpair-mf np6 8w x minb1, swizzled", 12, 1, false, TUNE(OCG_TPMFX(6, true, 1, 1, 8, 0, 2)), 12, 8, 2},
+    /* 59 */ {"tpair-mf np8 8w x minb1, swizzled", 16, 1, false, TUNE(OCG_TPMFX(8, true, 1, 1, 8, 0, 2)), 16, 8, 2},
+    /* 60 */ {"tpair-mf np5 12w x minb1, swizzled", 10, 1, false, TUNE(OCG_TPMFX(5, true, 1, 1, 12, 0, 2)), 10, 12, 2},
+    /* 61 */ {"tpair-mf np6 12w x minb1, swizzled", 12, 1, false, TUNE(OCG_TPMFX(6, true, 1, 1, 12, 0, 2)), 12, 12, 2},
+    /* 62 */ {"tpair-mf np4 12w x minb1 unr2, swizzled", 8, 1, false, TUNE(OCG_TPMFX(4, true, 1, 2, 12, 0, 2)), 8, 12, 2},
+    /* 63 */ {"tpair-mf np4 4w x minb3, swizzled", 8, 3, false, TUNE(OCG_TPMFX(4, true, 3, 1, 4, 0, 2)), 8, 4, 2},
+    /* 64 */ {"tpair-mf np3 12w x minb1, swizzled", 6, 1, false, TUNE(OCG_TPMFX(3, true, 1, 1, 12, 0, 2)), 6, 12, 2},
+    /* 65 */ {"tpair-mf np4 16w x minb1, swizzled", 8, 1, false, TUNE(OCG_TPMFX(4, true, 1, 1, 16, 0, 2)), 8, 16, 2},
+    // ---- round 2: FP32 accumulation runs shorter than the tile (FOLD) ----
+    /* 66 */ {"tpair-mf np6 8w swizzled fold128", 12, 1, false, TUNE(OCG_TPMFF(6, 1, 1, 8, 128)), 12, 8, 2},
+    /* 67 */ {"tpair-mf np6 8w swizzled fold64", 12, 1, false, OCG_TPMFF(6, 1, 1, 8, 64), 12, 8, 2},  // production: BIG_MF
+    /* 68 */ {"tpair-mf np6 8w swizzled fold32", 12, 1, false, TUNE(OCG_TPMFF(6, 1, 1, 8, 32)), 12, 8, 2},
+    /* 69 */ {"tpair np4 12w fold128", 8, 1, false, TUNE(OCG_TPWF(4, true, 1, 1, 12, 128)), 8, 12},
+    /* 70 */ {"tpair np4 12w fold64", 8, 1, false, TUNE(OCG_TPWF(4, true, 1, 1, 12, 64)), 8, 12},
+    /* 71 */ {"tpair np4 12w fold32", 8, 1, false, TUNE(OCG_TPWF(4, true, 1, 1, 12, 32)), 8, 12},
+    /* 72 */ {"tpair np1 regacc minb2 unr2 fold64", 2, 2, false, TUNE(OCG_TPWF(1, false, 2, 2, OCG_CONSUMER_WARPS, 64)), 0},
+    /* 73 */ {"tpair np1 regacc minb2 unr2 fold128", 2, 2, false, TUNE(OCG_TPWF(1, false, 2, 2, OCG_CONSUMER_WARPS, 128)), 0},
+    // ---- mass-folded tiles with a potential form (6-array tiles), and for the mid-size target counts ----
+    /* 74 */ {"tpair-mf(+pot) np4 12w swizzled fold64", 8, 1, false, OCG_TPMFP(4, true, 1, 1, 12, 64), 8, 12, 2},  // production: BIG_MF_POT
+    /* 75 */ {"tpair-mf(+pot) np5 8w swizzled fold64", 10, 1, false, TUNE(OCG_TPMFP(5, true, 1, 1, 8, 64)), 10, 8, 2},
+    /* 76 */ {"tpair-mf(+pot) np4 12w swizzled fold512", 8, 1, false, TUNE(OCG_TPMFP(4, true, 1, 1, 12, 512)), 8, 12, 2},
+    /* 77 */ {"tpair-mf(+pot) np1 regacc minb2 unr2 swizzled fold64", 2, 2, false, OCG_TPMFP(1, false, 2, 2, OCG_CONSUMER_WARPS, 64), 0, 0, 2},  // production: MID_MF
+    /* 78 */ {"tpair-mf(+pot) np1 regacc minb2 unr2 swizzled fold512", 2, 2, false, TUNE(OCG_TPMFP(1, false, 2, 2, OCG_CONSUMER_WARPS, 512)), 0, 0, 2},
 };
-/* variants 37..39 and 48.. are timing experiments with wrong results */
 static const int g_n_variants = (int)(sizeof(g_variants) / sizeof(g_variants[0]));
-// Production choices (tools/probe.py sweep on B200, profiles/r01_variant_sweep.json):
-#define OCG_VARIANT_BIG 31        /* >= 64k targets: target-paired, 8 targets/thread, 12 warps, 71% of FP32 peak */
-#define OCG_VARIANT_BIG_MF 58     /* the same with mass-folded, w-swizzled tiles (11 FMA-pipe ops per interaction; K1, no potential) */
-#define OCG_VARIANT_MID 27        /* >= 16k targets: target-paired, 2 targets/thread                              */
+// Production choices (tools/probe.py sweeps on B200, profiles/r01_variant_sweep*.json, profiles/r02_fold_sweep.json):
+// FOLD (profiles/r02_fold_sweep.json, 2e6 particles x 3001 lattice targets, strict metric on the tidal residual):
+//   mass-folded  FOLD 512: 1.6e-4 at 76.2 % of FP32 peak | 128: 1.9e-5 at 74.3 % | 64: 1.1e-5 at 73.1 % | 32: 1.2e-5 at 71.1 %
+//   plain tiles  FOLD 512: 2.0e-4 at 64.9 %              | 128: 1.4e-4 at 60.6 % | 64: 1.4e-4 at 59.9 % (no gain: their error is
+//   the rounding of d = x_s - x_t, coherent over all sources of one binade; the mass-folded d' = fma(-x_t, w, w x_s) dithers it)
+#define OCG_VARIANT_BIG 31        /* >= 64k targets, plain tiles: 8 targets/thread, 12 warps (mass folding switched off) */
+#define OCG_VARIANT_BIG_MF 67     /* K1 >= 64k targets: mass-folded, w-swizzled tiles, 12 targets/thread, 8 warps, FOLD 64 */
+#define OCG_VARIANT_BIG_MF_POT 74 /* the same with the potential: 6-array tiles, 8 targets/thread, 12 warps, FOLD 64 */
+#define OCG_VARIANT_MID 27        /* >= 16k targets, plain tiles (K4): target-paired, 2 targets/thread              */
+#define OCG_VARIANT_MID_MF 77     /* K1 mid-size target counts: mass-folded, 2 targets/thread, FOLD 64, with or without potential */
 #define OCG_VARIANT_MID_GUARD 4   /* source-paired 2 targets/thread (carries the eps2 == 0 guarded form)          */
 #define OCG_VARIANT_SMALL 1       /* few targets: 1 target/thread spreads them over more CTAs (has guard form)    */
 
-static int g_force_variant = -1;  // -1 = heuristic
-static int g_precise_near = 1;    // 0 = no precision radius (criterion (a) only)
-static int g_mass_fold = 1;       // 0 = never pick the mass-folded variant by heuristic
-extern "C" int ocg_debug_set_mass_fold(int on) {
-  g_mass_fold = on;
-  return 0;
-}
-extern "C" int ocg_debug_set_variant(int id) {
-  if (id >= g_n_variants) return OCG_ERR_INVALID;
-  g_force_variant = id;
-  return g_n_variants;
-}
-extern "C" const char* ocg_debug_variant_name(int id) { return id >= 0 && id < g_n_variants ? g_variants[id].name : ""; }
-extern "C" int ocg_debug_set_precise_near(int on) {
-  g_precise_near = on;
-  return 0;
-}
+int ocg_direct_n_variants() { return g_n_variants; }
+const char* ocg_direct_variant_name(int id) { return id >= 0 && id < g_n_variants ? g_variants[id].name : ""; }
+bool ocg_direct_variant_built(int id) { return id >= 0 && id < g_n_variants && g_variants[id].fn[0][0] != nullptr; }
 
 // n_tgt: targets in the call (or shard); seg_len: typical length of one independent target run (= n_tgt for the
 // field build, the cluster size for batched self-gravity) — a tile never spans two runs.
 int ocg_pick_variant(ocg_ctx* ctx, int64_t n_tgt, int64_t seg_len, bool guard, bool allow_mf, int64_t src_tiles,
                      bool fine_tiles) {
-  if (g_force_variant >= 0) {
+  const int forced = ctx->knobs.direct_variant;
+  if (forced >= 0 && forced < g_n_variants && g_variants[forced].fn[0][0]) {
     // a forced variant without the guarded form falls back to the guarded production kernels; so does a
     // mass-folded one when the caller lays out plain tiles (K4)
-    if ((!guard || g_variants[g_force_variant].fn[0][1]) && (allow_mf || !g_variants[g_force_variant].mf))
-      return g_force_variant;
+    if ((!guard || g_variants[forced].fn[0][1]) && (allow_mf || !g_variants[forced].mf)) return forced;
   }
   auto waste_ok = [&](int v) {
     const long long ct = (long long)variant_threads(g_variants[v]) * g_variants[v].tpt;
@@ -636,7 +672,9 @@ int ocg_launch_direct(ocg_ctx* ctx, DirectParams& p, int variant, bool pot, bool
   }
   direct_fn fn = v->fn[pot][guard];
   size_t smem = direct_smem_bytes();
-  if (v->smem_acc_comps) smem = OCG_NSTAGE * OCG_TILE_BYTES + 128 + (size_t)(pot ? 4 : 3) * v->smem_acc_comps * variant_threads(*v) * sizeof(double);
+  const size_t tile_bytes = (size_t)OCG_TILE_ARRAYS(v->mf, pot) * OCG_TS * sizeof(float);
+  if (v->mf) smem = OCG_NSTAGE * tile_bytes + 128;  // target-paired kernels: ring | barriers | FP64 accumulators
+  if (v->smem_acc_comps) smem = OCG_NSTAGE * tile_bytes + 128 + (size_t)(pot ? 4 : 3) * v->smem_acc_comps * variant_threads(*v) * sizeof(double);
   OCG_CUDA(ctx, cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int grid = ctx->sm_count * v->minb;
   if (grid > p.n_items) grid = p.n_items;
@@ -669,9 +707,15 @@ int ocg_direct_sum_impl(ocg_ctx* ctx, const float* src_xyzm, const float* src_so
   }
 
   int variant = ocg_pick_variant(ctx, n_tgt, n_tgt, /*guard=*/false, /*allow_mf=*/true, (n_src + OCG_TS - 1) / OCG_TS);
-  if (g_variants[variant].mf && want_pot) variant = OCG_VARIANT_BIG;  // the potential has no mass-folded form
-  else if (variant == OCG_VARIANT_BIG && !want_pot && g_mass_fold && g_force_variant < 0) variant = OCG_VARIANT_BIG_MF;
+  if (ctx->knobs.mass_fold && ctx->knobs.direct_variant < 0) {
+    // the field build takes mass-folded tiles wherever a target-paired kernel runs: one FMA-pipe operation fewer per
+    // interaction, and the w factor dithers the rounding of the coordinate difference (see the FOLD table above)
+    if (variant == OCG_VARIANT_BIG) variant = want_pot ? OCG_VARIANT_BIG_MF_POT : OCG_VARIANT_BIG_MF;
+    else if (variant == OCG_VARIANT_MID) variant = OCG_VARIANT_MID_MF;
+  }
+  if (g_variants[variant].mf && want_pot && !g_variants[variant].fn[1][0]) variant = OCG_VARIANT_BIG;  // no potential form
   const int mf = g_variants[variant].mf;
+  const int narr = OCG_TILE_ARRAYS(mf, want_pot);
   const int tpt = ocg_variant_tpt(variant);
   const int CT = ocg_variant_threads(variant) * tpt;
   const long long n_ttiles = (n_tgt + CT - 1) / CT;
@@ -695,7 +739,7 @@ int ocg_direct_sum_impl(ocg_ctx* ctx, const float* src_xyzm, const float* src_so
   const long long n_cls_blocks = (n_src + CLS_BLOCK - 1) / CLS_BLOCK;
   int rc;
   if ((rc = ocg_scratch(ctx, OCG_SCR_MISC, MISC_INTS * sizeof(int), (void**)&misc))) return rc;
-  if ((rc = ocg_scratch(ctx, OCG_SCR_TILES, (size_t)n_tiles_max * OCG_TILE_BYTES, (void**)&tiles))) return rc;
+  if ((rc = ocg_scratch(ctx, OCG_SCR_TILES, (size_t)n_tiles_max * narr * OCG_TS * sizeof(float), (void**)&tiles))) return rc;
   if ((rc = ocg_scratch(ctx, OCG_SCR_PARTIAL, (size_t)n_chunks * NC * n_tgt * sizeof(double), (void**)&partial))) return rc;
   if ((rc = ocg_scratch(ctx, OCG_SCR_NEAR, (size_t)n_src * 20, (void**)&near_xyzm))) return rc;
   near_soft = reinterpret_cast<float*>(near_xyzm + n_src);
@@ -714,13 +758,13 @@ int ocg_direct_sum_impl(ocg_ctx* ctx, const float* src_xyzm, const float* src_so
   }
   scale_kernel<<<1, 1, 0, st>>>(misc, 1.0f);
   OCG_CHECK_LAUNCH(ctx, "scale_kernel");
-  if (g_precise_near || mf) {
+  if (ctx->knobs.precise_near || mf) {
     classify_hist_kernel<<<(int)n_cls_blocks, CLS_BLOCK, 0, st>>>(src4, src_soft, n_src, kernel, misc);
     OCG_CHECK_LAUNCH(ctx, "classify_hist_kernel");
     // cap the FP64 set at ~0.2% of the sources (>= 4096): its pair cost is ~5x the FP32 one
     long long cap = n_src / 512;
     if (cap < 4096) cap = 4096;
-    choose_radius_kernel<<<1, 1, 0, st>>>(misc, (int)cap, g_precise_near);
+    choose_radius_kernel<<<1, 1, 0, st>>>(misc, (int)cap, ctx->knobs.precise_near);
     OCG_CHECK_LAUNCH(ctx, "choose_radius_kernel");
   }
   classify_count_kernel<<<(int)n_cls_blocks, CLS_BLOCK, 0, st>>>(src4, src_soft, n_src, kernel, misc, counts, mf);
@@ -728,9 +772,9 @@ int ocg_direct_sum_impl(ocg_ctx* ctx, const float* src_xyzm, const float* src_so
   classify_scan_kernel<<<1, 1024, 0, st>>>(counts, (int)n_cls_blocks, n_src, misc);
   OCG_CHECK_LAUNCH(ctx, "classify_scan_kernel");
   classify_scatter_kernel<<<(int)n_cls_blocks, CLS_BLOCK, 0, st>>>(src4, src_soft, n_src, kernel, misc, counts,
-                                                                 tiles, near_xyzm, near_soft, mf);
+                                                                 tiles, near_xyzm, near_soft, mf, narr);
   OCG_CHECK_LAUNCH(ctx, "classify_scatter_kernel");
-  pad_tiles_kernel<<<1, OCG_TS, 0, st>>>(tiles, misc, mf);
+  pad_tiles_kernel<<<1, OCG_TS, 0, st>>>(tiles, misc, mf, narr);
   OCG_CHECK_LAUNCH(ctx, "pad_tiles_kernel");
 
   DirectParams p;
@@ -747,6 +791,7 @@ int ocg_direct_sum_impl(ocg_ctx* ctx, const float* src_xyzm, const float* src_so
   p.scale_ptr = reinterpret_cast<const float*>(misc + MISC_SCALE);
   p.scale_val = 1.0f;
   if ((rc = ocg_launch_direct(ctx, p, variant, want_pot, /*guard=*/false, st))) return rc;
+  ctx->last_traffic_bytes = n_tiles_max * (long long)narr * OCG_TS * 4 + n_tgt * 16 + n_chunks * NC * n_tgt * 8;
 
   {
     long long nb = (n_tgt + 255) / 256;

@@ -257,12 +257,7 @@ __global__ void __launch_bounds__(256, MINB) grid_interp_kernel(const InterpPara
   }
 }
 
-static int g_interp_variant = 2;  // 0: <=128 regs (2 blocks/SM), 1: <=80 regs (3), 2: <=64 regs (4: fastest, latency-bound)
-extern "C" int ocg_debug_set_interp_variant(int v) {
-  if (v < 0 || v > 2) return OCG_ERR_INVALID;
-  g_interp_variant = v;
-  return OCG_OK;
-}
+// ctx->knobs.interp_variant: 0: <=128 regs (2 blocks/SM), 1: <=80 regs (3), 2: <=64 regs (4: fastest, latency-bound)
 
 static int interp_launch(ocg_ctx* ctx, const ocg_grid_desc* grid, const float* const* rec, const float* w, int n_rec,
                          const double* sx, const double* sy, const double* sz, const int32_t* scl, int64_t n_star,
@@ -322,7 +317,7 @@ static int interp_launch(ocg_ctx* ctx, const ocg_grid_desc* grid, const float* c
       {{nullptr, nullptr}, {grid_interp_kernel<false, 2, false, true>, grid_interp_kernel<true, 2, false, true>}},
       {{grid_interp_kernel<false, 3, true, false>, grid_interp_kernel<true, 3, true, false>},
        {grid_interp_kernel<false, 2, true, true>, grid_interp_kernel<true, 2, true, true>}}};
-  interp_fn fn = (fine || tensor) ? fns_x[fine ? 1 : 0][tensor ? 1 : 0][in_smem ? 1 : 0] : fns[g_interp_variant][in_smem ? 1 : 0];
+  interp_fn fn = (fine || tensor) ? fns_x[fine ? 1 : 0][tensor ? 1 : 0][in_smem ? 1 : 0] : fns[ctx->knobs.interp_variant][in_smem ? 1 : 0];
   int occ = 0;
   OCG_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, 256, smem));
   if (occ < 1) occ = 1;

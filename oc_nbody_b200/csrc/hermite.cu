@@ -344,32 +344,28 @@ struct HermiteVariant {
       hermite_tp_kernel<NP, true, false, NW, UNR, MINB>, hermite_tp_kernel<NP, true, true, NW, UNR, MINB>                \
     }                                                                                                                    \
   }
+// Only the production shape is compiled into the shipped library; the others exist in the -DOCG_TUNING build.
+#ifdef OCG_TUNING
+#define HM_TUNE(...) __VA_ARGS__
+#else
+#define HM_TUNE(...) {{nullptr, nullptr}, {nullptr, nullptr}}
+#endif
+#define HM_PRODUCTION 7
 static const HermiteVariant g_hm_variants[] = {
-    {"np4 8w (2048-target tiles)", 4, 8, 1, HM_V(4, 8, 1, 1)},
-    {"np3 8w (1536-target tiles)", 3, 8, 1, HM_V(3, 8, 1, 1)},
-    {"np2 8w (1024-target tiles)", 2, 8, 1, HM_V(2, 8, 1, 1)},
-    {"np2 12w (1536-target tiles)", 2, 12, 1, HM_V(2, 12, 1, 1)},
-    {"np3 12w (2304-target tiles)", 3, 12, 1, HM_V(3, 12, 1, 1)},
-    {"np4 8w unroll 2", 4, 8, 1, HM_V(4, 8, 2, 1)},
-    {"np1 8w x 2 CTA/SM (512-target tiles)", 1, 8, 2, HM_V(1, 8, 1, 2)},
+    {"np4 8w (2048-target tiles)", 4, 8, 1, HM_TUNE(HM_V(4, 8, 1, 1))},
+    {"np3 8w (1536-target tiles)", 3, 8, 1, HM_TUNE(HM_V(3, 8, 1, 1))},
+    {"np2 8w (1024-target tiles)", 2, 8, 1, HM_TUNE(HM_V(2, 8, 1, 1))},
+    {"np2 12w (1536-target tiles)", 2, 12, 1, HM_TUNE(HM_V(2, 12, 1, 1))},
+    {"np3 12w (2304-target tiles)", 3, 12, 1, HM_TUNE(HM_V(3, 12, 1, 1))},
+    {"np4 8w unroll 2", 4, 8, 1, HM_TUNE(HM_V(4, 8, 2, 1))},
+    {"np1 8w x 2 CTA/SM (512-target tiles)", 1, 8, 2, HM_TUNE(HM_V(1, 8, 1, 2))},
     {"np1 8w x 2 CTA/SM unroll 2", 1, 8, 2, HM_V(1, 8, 2, 2)},
-    {"np2 8w unroll 2", 2, 8, 1, HM_V(2, 8, 2, 1)},
-    {"np1 4w x 3 CTA/SM (256-target tiles)", 1, 4, 3, HM_V(1, 4, 1, 3)},
+    {"np2 8w unroll 2", 2, 8, 1, HM_TUNE(HM_V(2, 8, 2, 1))},
+    {"np1 4w x 3 CTA/SM (256-target tiles)", 1, 4, 3, HM_TUNE(HM_V(1, 4, 1, 3))},
 };
 #define HM_N_VARIANTS ((int)(sizeof(g_hm_variants) / sizeof(g_hm_variants[0])))
-static int g_hm_force_variant = -1;
-static int g_hm_small_path = 1;
-extern "C" int ocg_debug_set_hermite_variant(int v) {
-  g_hm_force_variant = v < HM_N_VARIANTS ? v : -1;
-  return HM_N_VARIANTS;
-}
-extern "C" const char* ocg_debug_hermite_variant_name(int v) {
-  return v >= 0 && v < HM_N_VARIANTS ? g_hm_variants[v].name : "";
-}
-extern "C" int ocg_debug_set_hermite_small_path(int on) {
-  g_hm_small_path = on;
-  return 0;
-}
+int ocg_hermite_n_variants() { return HM_N_VARIANTS; }
+const char* ocg_hermite_variant_name(int v) { return v >= 0 && v < HM_N_VARIANTS ? g_hm_variants[v].name : ""; }
 
 static float hermite_scale(float e2f) {
   // power-of-two length scale that puts eps at ~2^-8 (as K4 does): 1/r^3 <= 2^24 for softened pairs, and
@@ -417,7 +413,7 @@ extern "C" int ocg_self_gravity_hermite(ocg_ctx* ctx, const double* pos_dev, con
   const float scale = hermite_scale(e2f);
   const float e2s = guard ? 0.f : e2f * scale * scale;
 
-  if (g_hm_small_path && n_seg == 1 && n <= HM_SMALL_MAX_N) {
+  if (ctx->knobs.hermite_small_path && n_seg == 1 && n <= HM_SMALL_MAX_N) {
     const size_t smem = 2 * sizeof(float4) * (size_t)n;
     OCG_CUDA(ctx, cudaFuncSetAttribute((const void*)hermite_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)(2 * sizeof(float4) * HM_SMALL_MAX_N)));
@@ -429,11 +425,12 @@ extern "C" int ocg_self_gravity_hermite(ocg_ctx* ctx, const double* pos_dev, con
     return OCG_OK;
   }
 
-  int variant = g_hm_force_variant;
+  int variant = ctx->knobs.hermite_variant;
+  if (variant >= HM_N_VARIANTS || (variant >= 0 && !g_hm_variants[variant].fn[0][0])) variant = -1;
   // measured on B200 (tools/bench_hermite.py, profiles/r01_bench_hermite.json): one target pair per thread, two
   // 8-warp CTAs per SM (122 registers, 16 warps per SM), 4-source-group loop unrolled twice is the fastest shape at
   // N = 65 536 (60.6 % of FP32 peak, kernel 62.2 %) and on batches of 4096-star clusters (59.9 %)
-  if (variant < 0) variant = 7;
+  if (variant < 0) variant = HM_PRODUCTION;
   const HermiteVariant& v = g_hm_variants[variant];
   const int NTHR = 32 * v.nw, CT = 2 * v.np * NTHR;
 

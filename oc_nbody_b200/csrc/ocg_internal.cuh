@@ -15,6 +15,8 @@
 #define OCG_TS 512
 #define OCG_TILE_FLOATS (5 * OCG_TS)
 #define OCG_TILE_BYTES (OCG_TILE_FLOATS * 4)
+/* mass-folded tiles that also serve the potential carry a 6th array, 1/w */
+#define OCG_TILE_ARRAYS(MF, POT) (((MF) && (POT)) ? 6 : 5)
 #define OCG_NSTAGE 4
 #define OCG_CONSUMER_WARPS 8
 #define OCG_CONSUMER_THREADS (OCG_CONSUMER_WARPS * 32)
@@ -33,8 +35,23 @@ enum { OCG_SCR_TILES = 0, OCG_SCR_PARTIAL, OCG_SCR_NEAR, OCG_SCR_ITEMS, OCG_SCR_
        OCG_SCR_SRC, OCG_SCR_SOFT, OCG_SCR_F64A, OCG_SCR_F64B, OCG_SCR_F64C, OCG_SCR_OUT, OCG_SCR_COUNTS,
        OCG_SCR_ITEMS_HM, OCG_SCR_TILES_HM, OCG_SCR_TGT_HM, OCG_SCR_PARTIAL_HM, OCG_SCR_N };
 
+// Tuning / test knobs of one ctx (include/ocg_debug.h: ocg_debug_set).  Defaults are the production behaviour.
+struct OcgKnobs {
+  int direct_variant;       // -1 = heuristic, else index into the K1/K4 shape table (direct_sum.cu)
+  int precise_near;         // 1 = sources inside the precision radius take the FP64 pair path
+  int mass_fold;            // 1 = K1 without potential uses mass-folded tiles
+  int small_cluster_path;   // 1 = one small cluster takes the fused single-launch K4 kernel
+  long long host_chunk;     // particles staged at a time by ocg_field_build_host
+  int hermite_variant;      // -1 = production shape of the Hermite force kernel
+  int hermite_small_path;   // 1 = one small cluster takes the fused single-launch K6 kernel
+  int interp_variant;       // register bound of K3: 0 <=128, 1 <=80, 2 <=64 (production)
+  int field_precision;      // 0 = FP32 pair arithmetic + FP64 accumulation (north_star), 1 = every pair in FP64
+  int rbf_share;            // 1 = K7 shares one factorisation between stars with the same stencil pattern
+};
+
 struct ocg_ctx {
   int device;
+  OcgKnobs knobs;
   int sm_count;
   int sm_clock_khz;
   size_t global_mem;
@@ -45,6 +62,7 @@ struct ocg_ctx {
   int timing;
   cudaEvent_t ev0, ev1;
   int ev_valid;
+  long long last_traffic_bytes;  // model of the last K1 launch's HBM traffic (ocg_last_direct_traffic_bytes)
   // cached host copy of the last uploaded item list, to skip re-upload: [0] K4, [1] the Hermite force loop.  Each has
   // its own device buffer (OCG_SCR_ITEMS / OCG_SCR_ITEMS_HM): a captured CUDA graph of one must not see the other's plan.
   struct PlanCache {
@@ -124,6 +142,11 @@ int ocg_plan_cluster_items(ocg_ctx* ctx, int64_t n, const int64_t* seg_offsets_h
 // ---- entry points implemented in other translation units ------------------------------------
 int ocg_pick_variant(ocg_ctx* ctx, int64_t n_tgt, int64_t seg_len, bool guard, bool allow_mf = false,
                      int64_t src_tiles = 0, bool fine_tiles = false);
+int ocg_direct_n_variants();
+const char* ocg_direct_variant_name(int id);
+bool ocg_direct_variant_built(int id);
+int ocg_hermite_n_variants();
+const char* ocg_hermite_variant_name(int id);
 int ocg_variant_tpt(int variant);
 int ocg_variant_threads(int variant);
 int ocg_variant_slots(ocg_ctx* ctx, int variant);

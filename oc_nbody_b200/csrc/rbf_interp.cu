@@ -18,6 +18,7 @@
 //      (residual in FP64, correction through the FP32 factors held by one warp per right-hand side in registers);
 //   4. out_c = sum_m u_m field_c[id_m] in FP64.
 #include "ocg_internal.cuh"
+#include "../../include/ocg_debug.h"
 
 #include <math.h>
 
@@ -121,6 +122,7 @@ __global__ void __launch_bounds__(RBF_THREADS, 1) rbf_interp_kernel(const RbfPar
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nrhs = p.want_tensor ? 4 : 1;
   const long long n_node = (long long)p.n[0] * p.n[1] * p.n[2] + 1;
+#ifdef OCG_TUNING
   long long t_phase = clock64();
   auto phase_done = [&](int which) {
     if (tid == 0) {
@@ -129,6 +131,9 @@ __global__ void __launch_bounds__(RBF_THREADS, 1) rbf_interp_kernel(const RbfPar
       t_phase = t;
     }
   };
+#else
+  auto phase_done = [&](int) {};
+#endif
 
   for (long long s = blockIdx.x; s < p.n_star; s += gridDim.x) {
     const int cl = p.scl ? p.scl[s] : 0;
@@ -579,12 +584,14 @@ static size_t rbf_smem_bytes(int N, int ncl, int np1) {
 }
 
 // cycles per phase summed over CTAs since the last call (select, assemble, factorise, residual, solve, output)
-extern "C" int ocg_debug_rbf_phase_cycles(double* out6) {
+extern "C" int ocg_debug_rbf_phase_cycles(ocg_ctx* ctx, double* out6) {
+  if (!ctx || !out6) return OCG_ERR_INVALID;
+  OcgDeviceGuard g(ctx->device);
   unsigned long long h[RBF_NPHASE], z[RBF_NPHASE] = {0, 0, 0, 0, 0, 0};
-  if (cudaMemcpyFromSymbol(h, g_rbf_cycles, sizeof(h)) != cudaSuccess) return -1;
-  if (cudaMemcpyToSymbol(g_rbf_cycles, z, sizeof(z)) != cudaSuccess) return -1;
+  if (cudaMemcpyFromSymbol(h, g_rbf_cycles, sizeof(h)) != cudaSuccess) return OCG_ERR_CUDA;
+  if (cudaMemcpyToSymbol(g_rbf_cycles, z, sizeof(z)) != cudaSuccess) return OCG_ERR_CUDA;
   for (int i = 0; i < RBF_NPHASE; ++i) out6[i] = (double)h[i];
-  return 0;
+  return OCG_OK;
 }
 
 extern "C" int ocg_grid_interp_rbf(ocg_ctx* ctx, const ocg_grid_desc* grid, const double* field_dev, int32_t n_comp,

@@ -241,12 +241,6 @@ int ocg_plan_cluster_items(ocg_ctx* ctx, int64_t n, const int64_t* seg_offsets_h
 }
 
 
-static int g_small_path = 1;  // 0: always take the streaming kernel (tests compare the two)
-extern "C" int ocg_debug_set_small_cluster_path(int on) {
-  g_small_path = on;
-  return 0;
-}
-
 extern "C" int ocg_self_gravity(ocg_ctx* ctx, const double* pos_dev, const double* mass_dev, int64_t n,
                                 const int64_t* seg_offsets_host, int32_t n_seg, double eps2, double G,
                                 int64_t tgt_begin, int64_t tgt_end, double* acc_dev, double* pot_dev,
@@ -276,7 +270,7 @@ extern "C" int ocg_self_gravity(ocg_ctx* ctx, const double* pos_dev, const doubl
   const bool want_pot = pot_dev != nullptr;
   const int NC = want_pot ? 4 : 3;
   const float e2f = (float)eps2;
-  if (g_small_path && n_seg == 1 && n <= SG_SMALL_MAX_N) {
+  if (ctx->knobs.small_cluster_path && n_seg == 1 && n <= SG_SMALL_MAX_N) {
     // a single small cluster: one fused launch (see self_gravity_small_kernel)
     const size_t smem = sizeof(float4) * (size_t)n;
     OCG_CUDA(ctx, cudaFuncSetAttribute((const void*)self_gravity_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -66,6 +66,7 @@ def lib():
         _lib.oracle_spline_pot.restype = ctypes.c_double
         _lib.oracle_spline_pot.argtypes = [ctypes.c_double, ctypes.c_double]
         _lib.oracle_num_threads.restype = ctypes.c_int
+        _lib.oracle_set_num_threads.restype = ctypes.c_int
     return _lib
 
 
@@ -79,6 +80,11 @@ def _c(a, dt):
 
 def num_threads():
     return int(lib().oracle_num_threads())
+
+
+def set_num_threads(n):
+    """OpenMP threads of the oracle's loops (bench.py's CPU legs: all host cores, also under torchrun). Returns the count."""
+    return int(lib().oracle_set_num_threads(ctypes.c_int(int(n))))
 
 
 # ------------------------------------------------------------------------------------------------
@@ -111,6 +117,17 @@ def field_direct(src_xyzm, src_soft, tgt_xyzw, kernel, G, want_pot=False):
     lib().oracle_field_direct(_p(src), _p(soft), ctypes.c_int64(src.shape[0]), _p(tgt), ctypes.c_int64(tgt.shape[0]),
                               ctypes.c_int(kernel), ctypes.c_double(G), _p(acc), _p(pot))
     return (acc, pot) if want_pot else acc
+
+
+def field_direct_abs(src_xyzm, src_soft, tgt_xyzw, kernel, G):
+    """[3, n_tgt] sums of the magnitudes of the pair terms of field_direct (the condition number of each sum)."""
+    src = _c(src_xyzm, np.float32).reshape(-1, 4)
+    soft = _c(src_soft, np.float32)
+    tgt = _c(tgt_xyzw, np.float32).reshape(-1, 4)
+    out = np.zeros((3, tgt.shape[0]), np.float64)
+    lib().oracle_field_direct_abs(_p(src), _p(soft), ctypes.c_int64(src.shape[0]), _p(tgt), ctypes.c_int64(tgt.shape[0]),
+                                  ctypes.c_int(kernel), ctypes.c_double(G), _p(out))
+    return out
 
 
 def field_direct_fast(src_pos, src_mass, src_e2, tgt_pos, G):
@@ -162,6 +179,23 @@ def self_gravity_hermite(pos, vel, mass, eps2, G, vel_to_len=1.0, seg_offsets=No
                                       ctypes.c_double(eps2), ctypes.c_double(G), ctypes.c_double(vel_to_len),
                                       ctypes.c_int64(t0), ctypes.c_int64(t1), _p(acc), _p(jerk), _p(pot))
     return (acc, jerk, pot) if want_pot else (acc, jerk)
+
+
+def self_gravity_abs(pos, mass, eps2, G, vel=None, vel_to_len=1.0, seg_offsets=None, t0=0, t1=None):
+    """Sums of the magnitudes of the pair terms of self_gravity (and, with vel, of the jerk terms of
+    self_gravity_hermite): the condition numbers the parity tests weigh cancellation with. [3,n] (, [3,n])."""
+    pos = _c(pos, np.float64)
+    n = pos.shape[1]
+    mass = _c(mass, np.float64)
+    vel = None if vel is None else _c(vel, np.float64)
+    seg = np.array([0, n], np.int64) if seg_offsets is None else _c(seg_offsets, np.int64)
+    t1 = n if t1 is None else t1
+    a = np.zeros((3, n), np.float64)
+    j = np.zeros((3, n), np.float64) if vel is not None else None
+    lib().oracle_self_gravity_abs(_p(pos), _p(vel), _p(mass), ctypes.c_int64(n), _p(seg), ctypes.c_int32(len(seg) - 1),
+                                  ctypes.c_double(eps2), ctypes.c_double(G), ctypes.c_double(vel_to_len), ctypes.c_int64(t0),
+                                  ctypes.c_int64(t1), _p(a), _p(j))
+    return a if vel is None else (a, j)
 
 
 def hermite_predict(pos, vel, acc, jerk, dt, vel_to_len=1.0):

@@ -49,6 +49,17 @@ int oracle_num_threads(void) {
 #endif
 }
 
+/* The timed CPU baseline wants every host core even when the launcher exported OMP_NUM_THREADS=1 (torchrun does). */
+int oracle_set_num_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+  return omp_get_max_threads();
+#else
+  (void)n;
+  return 1;
+#endif
+}
+
 /* (float)(pos - center): the FP32 rounding the GPU path applies after recentring in FP64
  * (SURVEY §7 H3).  pos [n][3] fp64 -> out [n][4] fp32 (x,y,z,m). */
 void oracle_recentre(const double* pos, const double* mass, int64_t n, const double* center, float* out) {
@@ -122,6 +133,37 @@ void oracle_field_direct(const float* src_xyzm, const float* src_soft, int64_t n
     }
     acc[t] = G * ax, acc[n_tgt + t] = G * ay, acc[2 * n_tgt + t] = G * az;
     if (pot) pot[t] = G * ph;
+  }
+}
+
+/* Condition numbers of the sums above: abs_out[c][t] = G * sum_s |term_c(s, t)| — the sum of the MAGNITUDES of the pair
+ * terms that oracle_field_direct adds with signs.  FP32 pair arithmetic delivers every pair term to a few ulp of ITSELF
+ * (north_star: "fp32-source, fp64-accumulate"), so |a_gpu - a_ref| <= eps_pair * abs_out is the backward-error bound the
+ * parity tests use where terms cancel (tests/util.py::rel_err). */
+void oracle_field_direct_abs(const float* src_xyzm, const float* src_soft, int64_t n_src, const float* tgt_xyzw,
+                             int64_t n_tgt, int kernel, double G, double* abs_out) {
+#pragma omp parallel for schedule(static)
+  for (int64_t t = 0; t < n_tgt; ++t) {
+    const double tx = tgt_xyzw[4 * t], ty = tgt_xyzw[4 * t + 1], tz = tgt_xyzw[4 * t + 2];
+    double ax = 0, ay = 0, az = 0;
+    for (int64_t s = 0; s < n_src; ++s) {
+      const double dx = src_xyzm[4 * s] - tx, dy = src_xyzm[4 * s + 1] - ty, dz = src_xyzm[4 * s + 2] - tz;
+      const double m = fabs((double)src_xyzm[4 * s + 3]);
+      const double h = src_soft ? (double)src_soft[s] : 0.0;
+      double r2 = dx * dx + dy * dy + dz * dz, f = 0.0;
+      if (kernel == KERNEL_PLUMMER) {
+        r2 += h * h;
+        if (r2 > 0.0) {
+          const double ri = 1.0 / sqrt(r2);
+          f = ri * ri * ri;
+        }
+      } else if (r2 > 0.0) {
+        const double r = sqrt(r2);
+        f = r >= h ? 1.0 / (r2 * r) : fabs(spline_force(r, h));
+      }
+      ax += m * f * fabs(dx), ay += m * f * fabs(dy), az += m * f * fabs(dz);
+    }
+    abs_out[t] = G * ax, abs_out[n_tgt + t] = G * ay, abs_out[2 * n_tgt + t] = G * az;
   }
 }
 
@@ -238,6 +280,53 @@ void oracle_self_gravity_hermite(const double* pos, const double* vel, const dou
       }
       for (int c = 0; c < 3; ++c) acc[c * n + i] = G * A[c], jerk[c * n + i] = G * vel_to_len * J[c];
       if (pot) pot[i] = G * ph;
+    }
+  }
+  free(r);
+}
+
+/* Condition numbers of the cluster sums (see oracle_field_direct_abs): abs_acc[c][i] = G sum_j |m d_c / r^3| and, when
+ * vel != NULL, abs_jerk[c][i] = G vel_to_len sum_j (|m w_c / r^3| + |3 m (d.w) d_c / r^5|); same inputs and roundings as
+ * oracle_self_gravity[_hermite]. */
+void oracle_self_gravity_abs(const double* pos, const double* vel, const double* mass, int64_t n, const int64_t* seg_off,
+                             int32_t n_seg, double eps2, double G, double vel_to_len, int64_t t0, int64_t t1,
+                             double* abs_acc, double* abs_jerk) {
+  float* r = (float*)malloc(sizeof(float) * 7 * (size_t)n);
+  for (int s = 0; s < n_seg; ++s) {
+    const int64_t a = seg_off[s], b = seg_off[s + 1];
+    for (int64_t i = a; i < b; ++i) {
+      for (int c = 0; c < 3; ++c) {
+        r[7 * i + c] = (float)(pos[c * n + i] - pos[c * n + a]);
+        r[7 * i + 4 + c] = vel ? (float)(vel[c * n + i] - vel[c * n + a]) : 0.f;
+      }
+      r[7 * i + 3] = (float)mass[i];
+    }
+  }
+  const double e2 = (double)(float)eps2;
+  for (int s = 0; s < n_seg; ++s) {
+    const int64_t a = seg_off[s], b = seg_off[s + 1];
+    const int64_t lo = a > t0 ? a : t0, hi = b < t1 ? b : t1;
+#pragma omp parallel for schedule(static)
+    for (int64_t i = lo; i < hi; ++i) {
+      double A[3] = {0, 0, 0}, J[3] = {0, 0, 0};
+      const float* ti = r + 7 * i;
+      for (int64_t j = a; j < b; ++j) {
+        if (j == i) continue;
+        const float* sj = r + 7 * j;
+        const double d[3] = {(double)sj[0] - ti[0], (double)sj[1] - ti[1], (double)sj[2] - ti[2]};
+        const double w[3] = {(double)sj[4] - ti[4], (double)sj[5] - ti[5], (double)sj[6] - ti[6]};
+        const double r2 = d[0] * d[0] + d[1] * d[1] + d[2] * d[2] + e2;
+        if (r2 > 0.0) {
+          const double ri = 1.0 / sqrt(r2), m = fabs((double)sj[3]);
+          const double f = m * ri * ri * ri;
+          const double al = 3.0 * fabs(d[0] * w[0] + d[1] * w[1] + d[2] * w[2]) * ri * ri;
+          for (int c = 0; c < 3; ++c) A[c] += f * fabs(d[c]), J[c] += f * (fabs(w[c]) + al * fabs(d[c]));
+        }
+      }
+      for (int c = 0; c < 3; ++c) {
+        abs_acc[c * n + i] = G * A[c];
+        if (abs_jerk) abs_jerk[c * n + i] = G * vel_to_len * J[c];
+      }
     }
   }
   free(r);

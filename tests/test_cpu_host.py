@@ -17,7 +17,20 @@ def test_library_loads_and_exports_every_declared_symbol():
     assert declared == sorted(ABI_SYMBOLS)
     for name in declared:
         assert hasattr(L, name), name
-    assert L.ocg_version() == 100
+    assert L.ocg_version() == 200
+
+
+def test_library_exports_nothing_but_the_declared_c_abi():
+    """Built with -fvisibility=hidden: the dynamic symbol table holds exactly include/ocg.h + include/ocg_debug.h — no
+    mangled internals, no undeclared hooks."""
+    import subprocess
+    from oc_nbody_b200._lib import ABI_SYMBOLS, DEBUG_SYMBOLS, LIB_PATH
+    dbg = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "ocg_debug.h")).read(), flags=re.S)
+    declared_dbg = sorted(set(re.findall(r"\b(ocg_[a-z0-9_]+)\s*\(", dbg)))
+    assert declared_dbg == sorted(DEBUG_SYMBOLS)
+    out = subprocess.run(["nm", "-D", "--defined-only", LIB_PATH], capture_output=True, text=True, check=True).stdout
+    exported = sorted(ln.split()[-1] for ln in out.splitlines() if " T " in ln or " W " in ln or " B " in ln or " D " in ln)
+    assert exported == sorted(ABI_SYMBOLS + DEBUG_SYMBOLS)
 
 
 def test_no_cpu_fallback():

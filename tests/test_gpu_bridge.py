@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 
 import oracle
-from util import TOL, rel_err
+from util import TOL, rel_err, rel_err_norm
 
 pytestmark = pytest.mark.gpu
 
@@ -18,6 +18,9 @@ def oracle_field(field, snap, center, want_pot=True):
     t32 = oracle.recentre(tgt, None, center)
     kern = oracle.KERNEL_SPLINE if field.softening_kernel == "spline" else oracle.KERNEL_PLUMMER
     raw, pot = oracle.field_direct(s32, soft.astype(np.float32), t32, kern, field.G, want_pot=True)
+    # miniature snapshots (1e4..1e5 particles): single pair terms rival the net field at some grid points, so the raw field
+    # is gated on "strict bound OR backward-error bound of the sum" (util.rel_err, abs_sum); the full-size configs are not
+    oracle_field.cond = oracle.field_direct_abs(s32, soft.astype(np.float32), t32, kern, field.G)
     return raw, oracle.frame_subtract(raw, g.origin_row), pot
 
 
@@ -42,7 +45,7 @@ def test_field_code_build_matches_oracle(small_world):
         raw, sub, pot = oracle_field(field, snaps[i], centers[i])
         got = np.stack([g.snapshot_acceleration_x[i], g.snapshot_acceleration_y[i], g.snapshot_acceleration_z[i]])
         assert np.all(got[:, g.origin_row] == 0.0)
-        assert rel_err(got + raw[:, g.origin_row:g.origin_row + 1], raw) <= TOL
+        assert rel_err(got + raw[:, g.origin_row:g.origin_row + 1], raw, abs_sum=oracle_field.cond) <= TOL
         assert np.max(np.abs(g.snapshot_potential[i] - pot) / np.abs(pot)) <= TOL
 
 
@@ -131,8 +134,9 @@ def test_bridge_steps_match_oracle(small_world, ctx):
         gx = p.position.value_in(units.kpc).T - center[:, None]
         gv = p.velocity.value_in(units.kms).T
         # offsets from the cluster centre (pc scale) and velocities both within 1e-5
-        assert rel_err(gx, x - center[:, None]) <= TOL
-        assert rel_err(gv, v) <= TOL
+        # trajectories: norm metric (a position / velocity component is not a sum of pair terms and may pass through 0)
+        assert rel_err_norm(gx, x - center[:, None]) <= TOL
+        assert rel_err_norm(gv, v) <= TOL
     com = cl.bound_center_of_mass()
     assert np.linalg.norm(com - center) < 2e-3
 
@@ -162,7 +166,7 @@ def test_field_code_with_fine_grid(ctx, time_interpolation):
     raw, sub, pot = oracle_field(field, snaps[0], center)
     got = np.stack([g.snapshot_acceleration_x[0], g.snapshot_acceleration_y[0], g.snapshot_acceleration_z[0]])
     assert np.all(got[:, g.origin_row] == 0.0)
-    assert rel_err(got + raw[:, g.origin_row:g.origin_row + 1], raw) <= TOL
+    assert rel_err(got + raw[:, g.origin_row:g.origin_row + 1], raw, abs_sum=oracle_field.cond) <= TOL
     # the kick: oracle layout (hole filled from the fine lattice) + two-level interpolation, bit for bit
     planes = field._planes_()
     t = 9.2 if time_interpolation == "linear" else 30.0
@@ -375,8 +379,10 @@ def test_pykdgrav_compat_call_sites(ctx):
     s32 = oracle.recentre(r, m, center)
     ref, pref = oracle.field_direct(s32, soft.astype(np.float32), oracle.recentre(g.evolved_grid, None, center),
                                     oracle.KERNEL_SPLINE, G_ref, want_pot=True)
-    assert rel_err(accel.T, ref) <= TOL
-    assert rel_err(accel_center.T, ref[:, -1:]) <= TOL
+    cond = oracle.field_direct_abs(s32, soft.astype(np.float32), oracle.recentre(g.evolved_grid, None, center),
+                                   oracle.KERNEL_SPLINE, G_ref)  # 30 000-particle miniature: see oracle_field
+    assert rel_err(accel.T, ref, abs_sum=cond) <= TOL
+    assert rel_err(accel_center.T, ref[:, -1:], abs_sum=cond[:, -1:]) <= TOL
     # the frame subtraction as the reference writes it (gizmo_interface.py:569-571) leaves the tidal field
     tidal = accel - accel_center[0]
     want = oracle.frame_subtract(ref, g.origin_row)

@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 
 import oracle
-from util import TOL, dev, rel_err
+from util import TOL, dev, rel_err, rel_err_norm
 
 pytestmark = pytest.mark.gpu
 G = 4.398600413517813e-09
@@ -39,7 +39,15 @@ def test_config1_rows_match_oracle_on_a_target_subset(config1):
                                      [(32 * 64 + 32) * 64 + 32, (31 * 64 + 31) * 64 + 31]]))
     ref = oracle.field_direct(c["s32"], c["soft"], c["t32"][rows], oracle.KERNEL_PLUMMER, G)
     got = c["acc"][:, dev(rows)].cpu().numpy()
+    # the raw field, strict metric (floor 1e-3 ||a||)
     assert rel_err(got, ref) <= TOL
+    # ... and the quantity the reference actually returns and the kick consumes: the field minus the field at the grid
+    # centre (gizmo_interface.py:569-573), ~1e-2 of the raw field, same strict metric
+    o = int(np.nonzero(rows == n - 1)[0][0])
+    keep = np.arange(len(rows)) != o
+    res_got, res_ref = (got - got[:, o:o + 1])[:, keep], (ref - ref[:, o:o + 1])[:, keep]
+    print("configs[1] tidal residual, strict metric:", rel_err(res_got, res_ref))
+    assert rel_err(res_got, res_ref) <= TOL
 
 
 def test_config1_additivity_determinism_and_frame_row(ctx, config1):
@@ -87,7 +95,8 @@ def test_config2_self_gravity_momentum_and_rows(ctx):
     first = int(np.random.default_rng(3).integers(0, n - 200))
     for lo, hi in ((first, first + 1), (n - 200, n)):   # oracle target ranges: one random row, the last 200
         ref, pref = oracle.self_gravity(pos, mass, eps2, G, t0=lo, t1=hi, want_pot=True)
-        assert rel_err(a[:, lo:hi], ref[:, lo:hi]) <= TOL
+        cond = oracle.self_gravity_abs(pos, mass, eps2, G, t0=lo, t1=hi)  # cluster: close pairs, see util.rel_err
+        assert rel_err(a[:, lo:hi], ref[:, lo:hi], abs_sum=cond[:, lo:hi]) <= TOL
         assert np.max(np.abs(ph[lo:hi] - pref[lo:hi]) / np.abs(pref[lo:hi])) <= TOL
     # potential energy is symmetric: sum m_i phi_i = 2 W, and every phi < 0
     assert np.all(ph < 0.0)
@@ -186,7 +195,11 @@ def test_config0_full_bridge_run(ctx):
         raw, pot = oracle.field_direct(s32, soft.astype(np.float32), t32, oracle.KERNEL_SPLINE, field.G, want_pot=True)
         got = np.stack([g.snapshot_acceleration_x[i], g.snapshot_acceleration_y[i], g.snapshot_acceleration_z[i]])
         assert np.all(got[:, g.origin_row] == 0.0)
-        assert rel_err(got + raw[:, g.origin_row:g.origin_row + 1], raw) <= TOL
+        assert rel_err(got + raw[:, g.origin_row:g.origin_row + 1], raw) <= TOL          # raw field, strict metric
+        sub = oracle.frame_subtract(raw, g.origin_row)
+        keep = np.arange(len(g)) != g.origin_row
+        print("configs[0] tidal residual, strict metric:", rel_err(got[:, keep], sub[:, keep]))
+        assert rel_err(got[:, keep], sub[:, keep]) <= TOL                               # what the reference returns
         assert np.max(np.abs(g.snapshot_potential[i] - pot) / np.abs(pot)) <= TOL
         recs.append(oracle.pack_planes(got, g.snapshot_potential[i]))
     # 5 BRIDGE steps: K(dt/2) D(dt) K(dt/2), the cluster drifting under its own gravity
@@ -216,5 +229,6 @@ def test_config0_full_bridge_run(ctx):
             system.evolve_model(i * dt | units.Myr, timestep=dt | units.Myr)
         gx = cl.pos.cpu().numpy() - center[:, None]
         gv = cl.vel.cpu().numpy()
-        assert rel_err(gx, x - center[:, None]) <= TOL
-        assert rel_err(gv, v) <= TOL
+        # trajectories: norm metric (a position / velocity component is not a sum of pair terms and may pass through 0)
+        assert rel_err_norm(gx, x - center[:, None]) <= TOL
+        assert rel_err_norm(gv, v) <= TOL

@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 
 import oracle
-from util import TOL, dev, rel_err, rel_err_scalar
+from util import EPS_PAIR, TOL, dev, rel_err, rel_err_norm, rel_err_scalar
 
 pytestmark = pytest.mark.gpu
 
@@ -33,11 +33,23 @@ def gpu_force(ctx, pos, vel, mass, eps2=EPS2, seg=None, t0=0, t1=None, want_pot=
     return acc.cpu().numpy(), jerk.cpu().numpy(), (pot.cpu().numpy() if want_pot else None)
 
 
+# the jerk term chains ~twice as many FP32 operations as the acceleration term (d.w, alpha, alpha*d + w)
+EPS_PAIR_JERK = 2 * EPS_PAIR
+
+
+def hermite_ref(pos, vel, mass, eps2=EPS2, seg=None, t0=0, t1=None):
+    """FP64 oracle (acc, jerk, pot) plus the condition numbers of the two sums (sum of |pair terms|): cluster
+    self-gravity is where close pairs make single terms exceed the net field, see util.rel_err."""
+    a, j, p = oracle.self_gravity_hermite(pos, vel, mass, eps2, G, VTL, seg_offsets=seg, t0=t0, t1=t1, want_pot=True)
+    sa, sj = oracle.self_gravity_abs(pos, mass, eps2, G, vel=vel, vel_to_len=VTL, seg_offsets=seg, t0=t0, t1=t1)
+    return a, j, p, sa, sj
+
+
 def check(got, ref, sl=slice(None)):
     a, j, p = got
-    ra, rj, rp = ref
-    assert rel_err(a[:, sl], ra[:, sl]) <= TOL
-    assert rel_err(j[:, sl], rj[:, sl]) <= TOL
+    ra, rj, rp, sa, sj = ref
+    assert rel_err(a[:, sl], ra[:, sl], abs_sum=sa[:, sl]) <= TOL
+    assert rel_err(j[:, sl], rj[:, sl], abs_sum=sj[:, sl], eps_pair=EPS_PAIR_JERK) <= TOL
     if p is not None:
         assert rel_err_scalar(p[sl], rp[sl]) <= TOL
 
@@ -45,40 +57,40 @@ def check(got, ref, sl=slice(None)):
 @pytest.mark.parametrize("n", [2, 33, 1024, 4096])
 def test_small_cluster_path_matches_oracle(ctx, n):
     pos, vel, mass = cluster(n, kroupa=(n == 1024))
-    ref = oracle.self_gravity_hermite(pos, vel, mass, EPS2, G, VTL, want_pot=True)
+    ref = hermite_ref(pos, vel, mass)
     check(gpu_force(ctx, pos, vel, mass), ref)
 
 
 @pytest.mark.parametrize("n", [700, 5000, 12289])
 def test_streaming_path_matches_oracle_and_small_path(ctx, n):
     pos, vel, mass = cluster(n, seed=3)
-    ref = oracle.self_gravity_hermite(pos, vel, mass, EPS2, G, VTL, want_pot=True)
-    ctx.lib.ocg_debug_set_hermite_small_path(0)
+    ref = hermite_ref(pos, vel, mass)
+    ctx.debug_set("hermite_small_path", 0)
     try:
         got = gpu_force(ctx, pos, vel, mass)
         again = gpu_force(ctx, pos, vel, mass)
     finally:
-        ctx.lib.ocg_debug_set_hermite_small_path(1)
+        ctx.debug_set("hermite_small_path", 1)
     check(got, ref)
     for x, y in zip(got, again):
         assert np.array_equal(x, y)  # run-to-run deterministic
     if n <= 4096:
         small = gpu_force(ctx, pos, vel, mass)
-        assert rel_err(got[0], small[0]) <= 2e-6 and rel_err(got[1], small[1]) <= 2e-6
+        assert rel_err(got[0], small[0], abs_sum=ref[3]) <= TOL and rel_err(got[1], small[1], abs_sum=ref[4]) <= TOL
 
 
 def test_every_kernel_variant_matches_oracle(ctx):
     pos, vel, mass = cluster(5000, seed=8)
-    ref = oracle.self_gravity_hermite(pos, vel, mass, EPS2, G, VTL, want_pot=True)
-    nv = ctx.lib.ocg_debug_set_hermite_variant(-1)
+    ref = hermite_ref(pos, vel, mass)
+    nv = ctx.variant_count(family=1)
     assert nv >= 3
     try:
-        for v in range(nv):
-            ctx.lib.ocg_debug_set_hermite_variant(v)
+        for v in range(nv):  # a shape this build does not carry falls back to the production one
+            ctx.debug_set("hermite_variant", v)
             check(gpu_force(ctx, pos, vel, mass), ref)
             check(gpu_force(ctx, pos, vel, mass, want_pot=False), ref)
     finally:
-        ctx.lib.ocg_debug_set_hermite_variant(-1)
+        ctx.debug_set("hermite_variant", -1)
 
 
 def test_batch_of_ragged_clusters_and_target_shards(ctx):
@@ -86,7 +98,7 @@ def test_batch_of_ragged_clusters_and_target_shards(ctx):
     seg = np.concatenate([[0], np.cumsum(lens)])
     parts = [cluster(l, seed=20 + i, center=(8.0 * np.cos(i), 8.0 * np.sin(i), 0.1 * i)) for i, l in enumerate(lens) if l]
     pos, vel, mass = (np.concatenate([p[k] for p in parts], axis=-1) for k in range(3))
-    ref = oracle.self_gravity_hermite(pos, vel, mass, EPS2, G, VTL, seg_offsets=seg, want_pot=True)
+    ref = hermite_ref(pos, vel, mass, seg=seg)
     got = gpu_force(ctx, pos, vel, mass, seg=seg)
     check(got, ref)
     # the lone star feels nothing
@@ -106,13 +118,13 @@ def test_unsoftened_form_skips_coincident_pairs(ctx):
     pos, vel, mass = cluster(3000, seed=4)
     pos[:, 17] = pos[:, 5]       # a coincident pair: contributes nothing when eps2 == 0
     pos[:, 2999] = pos[:, 0]     # ... including one with the recentring origin (where tile padding sits)
-    ref = oracle.self_gravity_hermite(pos, vel, mass, 0.0, G, VTL, want_pot=True)
+    ref = hermite_ref(pos, vel, mass, eps2=0.0)
     for small in (1, 0):
-        ctx.lib.ocg_debug_set_hermite_small_path(small)
+        ctx.debug_set("hermite_small_path", small)
         try:
             got = gpu_force(ctx, pos, vel, mass, eps2=0.0)
         finally:
-            ctx.lib.ocg_debug_set_hermite_small_path(1)
+            ctx.debug_set("hermite_small_path", 1)
         assert all(np.all(np.isfinite(x)) for x in got)
         check(got, ref)
 
@@ -164,9 +176,10 @@ def test_cluster_code_hermite_evolve_matches_oracle(ctx, n, substeps):
     cl.evolve_model(span | units.Myr)
     x_ref, v_ref, dtm_ref = oracle.hermite_evolve(pos, vel, mass, EPS2, G, span, substeps, VTL, 0.14)
     x, v = cl.pos.cpu().numpy(), cl.vel.cpu().numpy()
-    # displacements over the span agree to the force tolerance
-    assert rel_err(x - pos, x_ref - pos) <= TOL
-    assert rel_err(v - vel, v_ref - vel) <= TOL
+    # displacements over the span agree to the force tolerance (norm metric: a trajectory is not a sum of pair terms,
+    # and a velocity change component can pass through zero)
+    assert rel_err_norm(x - pos, x_ref - pos) <= TOL
+    assert rel_err_norm(v - vel, v_ref - vel) <= TOL
     assert abs(cl.dt_min.item() - dtm_ref) <= 1e-3 * dtm_ref
     assert cl.suggested_substeps(span) >= 1
     # Hermite and leapfrog integrate the same dynamics
@@ -214,9 +227,9 @@ def test_fullsize_65536_third_law_and_rows(ctx):
         net = (mass * f).sum(axis=1)
         assert np.max(np.abs(net)) <= 1e-6 * (mass * np.sqrt((f * f).sum(axis=0))).sum()
     rows = np.unique(np.random.default_rng(1).integers(0, n, 150))
-    ref = [oracle.self_gravity_hermite(pos, vel, mass, EPS2, G, VTL, t0=int(t), t1=int(t) + 1, want_pot=True) for t in rows]
-    ea = max(rel_err(a[:, t:t + 1], r[0][:, t:t + 1]) for t, r in zip(rows, ref))
-    ej = max(rel_err(j[:, t:t + 1], r[1][:, t:t + 1]) for t, r in zip(rows, ref))
+    ref = [hermite_ref(pos, vel, mass, t0=int(t), t1=int(t) + 1) for t in rows]
+    ea = max(rel_err(a[:, t:t + 1], r[0][:, t:t + 1], abs_sum=r[3][:, t:t + 1]) for t, r in zip(rows, ref))
+    ej = max(rel_err(j[:, t:t + 1], r[1][:, t:t + 1], abs_sum=r[4][:, t:t + 1], eps_pair=EPS_PAIR_JERK) for t, r in zip(rows, ref))
     ep = max(rel_err_scalar(p[t:t + 1], r[2][t:t + 1]) for t, r in zip(rows, ref))
     assert ea <= TOL and ej <= TOL and ep <= TOL
 

@@ -67,9 +67,9 @@ def main():
         ctx.grid_interp((n, n, n), nodes, d_or, rec[0], rec[1], 0.37, sx, sy, sz, d_scl, acc, pot)
     for name, fn, ncomp, var in (("k3_interp_c4", k3, 3, 2), ("k3_interp_c4_with_potential", k3p, 4, 2),
                                  ("k3_interp_c4_minb2", k3, 3, 0), ("k3_interp_c4_minb3", k3, 3, 1)):
-        ctx.lib.ocg_debug_set_interp_variant(var)
+        ctx.debug_set("interp_variant", var)
         med, best = timeit(fn, flush=flush)
-        ctx.lib.ocg_debug_set_interp_variant(2)
+        ctx.debug_set("interp_variant", 2)
         alg = ncl * (nstar * (24 + 8 * ncomp) + 2 * 3 * 4 * n ** 3)  # 3-component planes
         moved = ncl * (nstar * (24 + 4 + 8 * ncomp) + 2 * 16 * n ** 3)  # records are float4: 16 B per node per snapshot
         out[name] = dict(ms_median=med, ms_best=best, algorithmic_bytes=alg, gbs=alg / med / 1e6,

@@ -8,6 +8,8 @@ import json
 import os
 import sys
 
+os.environ.setdefault("OCG_TUNING_LIB", "1")  # sweep shapes / phase counters live in the OCG_TUNING build
+
 import numpy as np
 import torch
 
@@ -33,7 +35,7 @@ def main():
     ncl = 256
     ang = np.linspace(0, 2 * np.pi, ncl, endpoint=False)
     origin = np.stack([8 * np.cos(ang), 8 * np.sin(ang), np.zeros(ncl)], 1)
-    nv = ctx.lib.ocg_debug_set_hermite_variant(-1)
+    nv = ctx.variant_count(family=1)
     if "--profile" in sys.argv:
         # the launch an ncu capture targets: production variant, N = 65 536, no potential, 6 calls
         pos_pc, vel1, mass = make_plummer_cluster(65536)
@@ -59,7 +61,7 @@ def main():
         res = {}
         variants = range(nv) if npc > 4096 or nseg > 1 else [-1]
         for v in variants:
-            ctx.lib.ocg_debug_set_hermite_variant(v)
+            ctx.debug_set("hermite_variant", v)
             for pot in (None, ph):
                 def k6():
                     ctx.self_gravity_hermite(d_pos, d_vel, d_m, eps2, G_KPC_KMS_MYR, KMS_TO_KPC_PER_MYR, a, j, pot,
@@ -69,12 +71,12 @@ def main():
                 k6()
                 kms = ctx.lib.ocg_last_direct_kernel_ms(ctx.h)
                 ctx.lib.ocg_set_kernel_timing(ctx.h, 0)
-                key = ("auto" if v < 0 else ctx.lib.ocg_debug_hermite_variant_name(v).decode()) + (" +pot" if pot is not None else "")
+                key = ("auto" if v < 0 else ctx.variant_name(v, family=1)) + (" +pot" if pot is not None else "")
                 res[key] = dict(ms_median=med, ms_best=best, kernel_ms=kms if kms > 0 else None, ginter_s=inter / med / 1e6,
                                 tflops=FLOP * inter / med / 1e9, pct_fp32_peak=100 * FLOP * inter / med / 1e9 / nominal,
                                 pct_fma_pipe_slots=100 * 2 * OPS * inter / med / 1e9 / nominal,
                                 kernel_pct_fp32_peak=(100 * FLOP * inter / kms / 1e9 / nominal) if kms > 0 else None)
-        ctx.lib.ocg_debug_set_hermite_variant(-1)
+        ctx.debug_set("hermite_variant", -1)
         out[name] = dict(interactions=inter, note="pack + kernel + finish per call (small: one fused launch)", variants=res)
 
     # ---- the same force loop on the host cores (the oracle's FP64 OpenMP restatement; bounded sample of N = 65 536) ----

@@ -6,6 +6,8 @@ import ctypes
 import json
 import os
 import sys
+
+os.environ.setdefault("OCG_TUNING_LIB", "1")  # sweep shapes / phase counters live in the OCG_TUNING build
 import time
 
 import numpy as np
@@ -50,10 +52,10 @@ def main():
                 ctx.grid_interp_rbf((n, n, n), nodes, d_o, d_f, sx, sy, sz, None, res, tensor_out=t, status_out=st)
             med, best = timeit(k7, iters=5, warm=2)
             cyc = (ctypes.c_double * 6)()
-            ctx.lib.ocg_debug_rbf_phase_cycles(cyc)
+            ctx.lib.ocg_debug_rbf_phase_cycles(ctx.h, cyc)
             k7()
             torch.cuda.synchronize()
-            ctx.lib.ocg_debug_rbf_phase_cycles(cyc)
+            ctx.lib.ocg_debug_rbf_phase_cycles(ctx.h, cyc)
             tot = sum(cyc) or 1.0
             out["k7_rbf_%d_stars_%s" % (ns, name)] = dict(ms_median=med, ms_best=best, stars_per_s=ns / med * 1e3,
                                                           us_per_star_per_sm=med * 1e3 * ctx.sm_count / ns,

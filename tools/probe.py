@@ -4,6 +4,8 @@ import json
 import os
 import sys
 
+os.environ.setdefault("OCG_TUNING_LIB", "1")  # sweep shapes / phase counters live in the OCG_TUNING build
+
 import numpy as np
 import torch
 
@@ -35,25 +37,25 @@ def main():
     inter = float(n_src) * tgt.shape[0]
     ctx.set_kernel_timing(True)
     res = []
-    nvar = ctx.lib.ocg_debug_set_variant(-1)
+    nvar = ctx.variant_count()
     only = [int(x) for x in os.environ.get("OCG_PROBE_VARIANTS", "").split(",") if x]
     for kernel, want_pot in ((0, False), (0, True), (1, False)):
         for v in range(nvar):
-            if (want_pot or kernel == 1) and v not in (0, 1, 31) and not (kernel == 1 and v in (46, 58)):
+            if not ctx.variant_built(v) or ((want_pot or kernel == 1) and v not in (0, 1, 31, 70) and not (kernel == 1 and v in (46, 58, 67))):
                 continue
             if only and v not in only:
                 continue
-            ctx.lib.ocg_debug_set_variant(v)
+            ctx.debug_set("direct_variant", v)
             best = 1e30
             for rep in range(3):
                 ctx.field_direct(d_src, d_soft, d_tgt, kernel, 1.0, acc, pot if want_pot else None)
                 torch.cuda.synchronize()
                 best = min(best, ctx.last_direct_kernel_ms())
-            r = dict(variant=v, name=ctx.lib.ocg_debug_variant_name(v).decode(), kernel=kernel, pot=want_pot, ms=best,
+            r = dict(variant=v, name=ctx.variant_name(v), kernel=kernel, pot=want_pot, ms=best,
                      ginter_s=inter / best / 1e6, pct_peak=100 * 20 * inter / best / 1e9 / out["nominal_tflops"])
             res.append(r)
             print(json.dumps(r), flush=True)
-    ctx.lib.ocg_debug_set_variant(-1)
+    ctx.debug_set("direct_variant", -1)
     out["variants"] = res
     os.makedirs("gpurun_out", exist_ok=True)
     with open("gpurun_out/probe.json", "w") as f:

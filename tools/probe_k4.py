@@ -4,6 +4,8 @@ import json
 import os
 import sys
 
+os.environ.setdefault("OCG_TUNING_LIB", "1")  # sweep shapes / phase counters live in the OCG_TUNING build
+
 import numpy as np
 import torch
 
@@ -26,8 +28,8 @@ def main():
         d_pos, d_m = torch.from_numpy(np.ascontiguousarray(pos)).to(dev), torch.from_numpy(m).to(dev)
         a = torch.empty((3, nseg * npc), dtype=torch.float64, device=dev)
         inter = float(nseg) * npc * npc
-        for v in [-1] + list(range(21, 37)) + [0, 4]:
-            ctx.lib.ocg_debug_set_variant(v)
+        for v in [-1] + [x for x in list(range(21, 37)) + [0, 4, 69, 70, 71, 72, 73] if ctx.variant_built(x)]:
+            ctx.debug_set("direct_variant", v)
             ts = []
             try:
                 for rep in range(8):
@@ -42,9 +44,9 @@ def main():
                 print(name, v, "failed:", exc)
                 continue
             finally:
-                ctx.lib.ocg_debug_set_variant(-1)
+                ctx.debug_set("direct_variant", -1)
             ms = float(np.median(ts))
-            r = dict(config=name, variant=v, name=ctx.lib.ocg_debug_variant_name(v).decode() if v >= 0 else "heuristic", ms=ms,
+            r = dict(config=name, variant=v, name=ctx.variant_name(v) if v >= 0 else "heuristic", ms=ms,
                      pct_fp32_peak=100 * 20 * inter / ms / 1e9 / nominal)
             out.append(r)
             print(json.dumps(r), flush=True)
