@@ -62,6 +62,12 @@ const char* ocg_last_error(const ocg_ctx* ctx);
 int ocg_device_info(ocg_ctx* ctx, int* sm_count, int* sm_clock_khz, int64_t* global_mem_bytes);
 /* Counts kernels this library launched on this ctx since creation (bench.py "gpu_launches"). */
 int64_t ocg_launch_count(const ocg_ctx* ctx);
+/* CUDA-graph safety.  A captured graph of calls on this ctx freezes the addresses of the ctx's scratch buffers and
+ * relies on the work plan (K4 / K6 item list) resident in them.  The value returned here changes whenever either does
+ * (a later call needed a larger buffer; another particle set uploaded its plan): a caller that replays a captured
+ * graph compares it with the value taken right after capture and re-captures on a mismatch (bridge.Bridge does).
+ * The simplest way never to see a mismatch is one ctx per captured step: a ctx is only scratch + settings.        */
+int64_t ocg_capture_epoch(const ocg_ctx* ctx);
 /* Milliseconds (cudaEvent, on `stream`) spent inside the dominant kernel of the most recent
  * ocg_field_direct / ocg_self_gravity call; the call synchronises `stream`. <0 on error. */
 double ocg_last_direct_kernel_ms(ocg_ctx* ctx);
@@ -236,6 +242,38 @@ int ocg_self_gravity(ocg_ctx* ctx, const double* pos_dev, const double* mass_dev
                      const int64_t* seg_offsets_host, int32_t n_seg, double eps2, double G,
                      int64_t tgt_begin, int64_t tgt_end, double* acc_dev, double* pot_dev,
                      void* stream);
+
+/* ---- multi-GPU: one process per GPU on one NVLink / NVSwitch node ----------------
+ * The reference has no multi-GPU path (its only parallel construct is a multiprocessing.Pool, gizmo_interface.py:600-605).
+ * Partition (BASELINE.json north_star): K1 source-sharded — every rank computes the full-grid partial field of its share
+ * of the snapshot, then an all-reduce; K4 star-sharded — every rank owns a block of stars and needs all positions at
+ * every self-gravity evaluation.  The exchange runs over peer memory: each rank owns a WINDOW of device memory that every
+ * other rank maps (CUDA IPC), and the kernels load / store the peers' windows directly, synchronising through flags in
+ * them.  Set-up, once per process:
+ *   1. ocg_comm_create  allocates this rank's window and fills an opaque OCG_COMM_HANDLE_BYTES handle;
+ *   2. the caller all-gathers the handles by any means it has (MPI_Allgather, torch.distributed, a shared file);
+ *   3. ocg_comm_connect maps the peers' windows (handles in rank order).
+ * Every rank must then issue the same sequence of ocg_comm_* / *_sharded calls.  window_bytes: at least
+ * 48 * ceil(n_stars / nranks) for ocg_self_gravity_sharded; the all-reduce works through whatever size it is given
+ * (16 bytes per element for a single pass).  nranks <= 16.                                                        */
+#define OCG_COMM_HANDLE_BYTES 128
+int ocg_comm_create(ocg_ctx* ctx, int32_t rank, int32_t nranks, int64_t window_bytes, void* handle_out);
+int ocg_comm_connect(ocg_ctx* ctx, const void* all_handles /* [nranks][OCG_COMM_HANDLE_BYTES] */);
+int ocg_comm_destroy(ocg_ctx* ctx); /* also done by ocg_destroy */
+int ocg_comm_info(const ocg_ctx* ctx, int32_t* rank, int32_t* nranks, int64_t* window_bytes);
+/* Synchronises `stream` and reports whether an exchange kernel gave up waiting for a peer (~2 s poll limit). */
+int ocg_comm_status(ocg_ctx* ctx, void* stream);
+/* buf[i] <- sum over the ranks of their buf[i], in place, fp64, summed in rank order: deterministic and bit-identical on
+ * every rank (the all-reduce of the K1 partial fields, 3*(Ngrid+1) elements).  One kernel per window-full. */
+int ocg_comm_allreduce_f64(ocg_ctx* ctx, double* buf_dev, int64_t n, void* stream);
+/* K4 for this rank's block of ONE cluster of n stars, block = [rank*n/nranks ...) with sizes differing by at most one
+ * (the first n % nranks ranks hold one more).  pos_local_dev fp64 [3][n_local] (this rank's stars only), mass_all_dev fp64
+ * [n] (replicated); acc_local_dev fp64 [3][n_local], pot_local_dev [n_local] or NULL.  Two launches: one kernel publishes
+ * the block, waits for the peers', reads all blocks over NVLink and writes the FP32 source tiles (recentred on star 0,
+ * exactly the single-GPU inputs, so the sharded trajectory equals the single-GPU one); then the force kernel for the
+ * rank's target rows.  eps2 > 0.                                                                                    */
+int ocg_self_gravity_sharded(ocg_ctx* ctx, const double* pos_local_dev, const double* mass_all_dev, int64_t n, double eps2,
+                             double G, double* acc_local_dev, double* pot_local_dev, void* stream);
 
 /* ---- K6: Hermite force loop + 4th-order Hermite predictor / corrector ------
  * The arithmetic of the ph4 worker itself (4th-order Hermite, oc_code.py:218-229; options.py:248-253):

@@ -19,10 +19,10 @@ KERNELS = {"plummer": KERNEL_PLUMMER, "spline": KERNEL_SPLINE}
 
 # every symbol include/ocg.h declares (tests check the library exports them all)
 ABI_SYMBOLS = [
-    "ocg_version", "ocg_create", "ocg_destroy", "ocg_last_error", "ocg_device_info", "ocg_launch_count",
+    "ocg_version", "ocg_create", "ocg_destroy", "ocg_last_error", "ocg_device_info", "ocg_launch_count", "ocg_capture_epoch",
     "ocg_last_direct_kernel_ms", "ocg_set_kernel_timing", "ocg_last_direct_traffic_bytes", "ocg_recentre_f64", "ocg_cast_f64_f32",
     "ocg_field_direct", "ocg_frame_subtract", "ocg_field_build_host", "ocg_pack_planes", "ocg_grid_time_blend",
-    "ocg_grid_interp", "ocg_grid_interp_multi", "ocg_grid_interp_nested", "ocg_pack_planes_indexed", "ocg_set_interp_weight_slots", "ocg_grid_interp_slot", "ocg_grid_interp_rbf", "ocg_self_gravity", "ocg_self_gravity_hermite", "ocg_hermite_predict", "ocg_hermite_correct", "ocg_bound_com", "ocg_eject_mask", "ocg_compact_rows", "ocg_kick", "ocg_drift", "ocg_axpy", "ocg_probe_throughput",
+    "ocg_grid_interp", "ocg_grid_interp_multi", "ocg_grid_interp_nested", "ocg_pack_planes_indexed", "ocg_set_interp_weight_slots", "ocg_grid_interp_slot", "ocg_grid_interp_rbf", "ocg_self_gravity", "ocg_self_gravity_hermite", "ocg_hermite_predict", "ocg_hermite_correct", "ocg_bound_com", "ocg_eject_mask", "ocg_compact_rows", "ocg_kick", "ocg_drift", "ocg_axpy", "ocg_probe_throughput", "ocg_comm_create", "ocg_comm_connect", "ocg_comm_destroy", "ocg_comm_info", "ocg_comm_status", "ocg_comm_allreduce_f64", "ocg_self_gravity_sharded",
 ]
 
 
@@ -30,7 +30,7 @@ ABI_SYMBOLS = [
 DEBUG_SYMBOLS = ["ocg_debug_set", "ocg_debug_variant_count", "ocg_debug_variant_name", "ocg_debug_variant_built",
                  "ocg_debug_rbf_phase_cycles"]
 KNOBS = {"direct_variant": 0, "precise_near": 1, "mass_fold": 2, "small_cluster_path": 3, "host_chunk": 4,
-         "hermite_variant": 5, "hermite_small_path": 6, "interp_variant": 7, "rbf_share": 8}
+         "hermite_variant": 5, "hermite_small_path": 6, "interp_variant": 7, "rbf_share": 8, "near_cap": 9}
 
 
 class OcgError(RuntimeError):
@@ -64,6 +64,8 @@ def load_library():
     L.ocg_device_info.argtypes = [vp, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int), ctypes.POINTER(i64)]
     L.ocg_launch_count.restype = i64
     L.ocg_launch_count.argtypes = [vp]
+    L.ocg_capture_epoch.restype = i64
+    L.ocg_capture_epoch.argtypes = [vp]
     L.ocg_last_direct_kernel_ms.restype = dbl
     L.ocg_last_direct_kernel_ms.argtypes = [vp]
     L.ocg_set_kernel_timing.argtypes = [vp, ctypes.c_int]
@@ -102,6 +104,13 @@ def load_library():
     L.ocg_kick.argtypes = [vp, vp, vp, i64, dbl, vp]
     L.ocg_drift.argtypes = [vp, vp, vp, i64, dbl, dbl, vp]
     L.ocg_axpy.argtypes = [vp, vp, vp, dbl, i64, vp]
+    L.ocg_comm_create.argtypes = [vp, i32, i32, i64, vp]
+    L.ocg_comm_connect.argtypes = [vp, vp]
+    L.ocg_comm_destroy.argtypes = [vp]
+    L.ocg_comm_info.argtypes = [vp, ctypes.POINTER(i32), ctypes.POINTER(i32), ctypes.POINTER(i64)]
+    L.ocg_comm_status.argtypes = [vp, vp]
+    L.ocg_comm_allreduce_f64.argtypes = [vp, vp, i64, vp]
+    L.ocg_self_gravity_sharded.argtypes = [vp, vp, vp, i64, dbl, dbl, vp, vp, vp]
     L.ocg_probe_throughput.restype = dbl
     L.ocg_probe_throughput.argtypes = [vp, ctypes.c_int]
     _lib = L
@@ -178,6 +187,10 @@ class Context:
     # ---- bookkeeping ----
     def launch_count(self):
         return int(self.lib.ocg_launch_count(self.h))
+
+    def capture_epoch(self):
+        """Changes whenever something a captured CUDA graph of this ctx's calls froze has changed (include/ocg.h)."""
+        return int(self.lib.ocg_capture_epoch(self.h))
 
     def set_kernel_timing(self, on):
         self._ck(self.lib.ocg_set_kernel_timing(self.h, 1 if on else 0), "ocg_set_kernel_timing")
@@ -382,6 +395,39 @@ class Context:
     def axpy(self, y, x, a):
         self._ck(self.lib.ocg_axpy(self.h, _dptr(y), _dptr(x), float(a), y.numel(), self._stream()), "ocg_axpy")
 
+    # ---- multi-GPU exchange over peer memory (include/ocg.h: ocg_comm_*) ----
+    COMM_HANDLE_BYTES = 128
+
+    def comm_create(self, rank, nranks, window_bytes):
+        """Allocate this rank's exchange window; returns the opaque handle (bytes) every other rank needs."""
+        buf = ctypes.create_string_buffer(self.COMM_HANDLE_BYTES)
+        self._ck(self.lib.ocg_comm_create(self.h, int(rank), int(nranks), int(window_bytes), buf), "ocg_comm_create")
+        self.comm_rank, self.comm_nranks = int(rank), int(nranks)
+        return buf.raw
+
+    def comm_connect(self, handles):
+        """handles: the nranks handle blobs in rank order (all-gathered by the caller)."""
+        blob = b"".join(handles)
+        self._ck(self.lib.ocg_comm_connect(self.h, ctypes.c_char_p(blob)), "ocg_comm_connect")
+        self.comm_connected = True
+
+    def comm_destroy(self):
+        self._ck(self.lib.ocg_comm_destroy(self.h), "ocg_comm_destroy")
+        self.comm_connected = False
+
+    def comm_status(self):
+        self._ck(self.lib.ocg_comm_status(self.h, self._stream()), "ocg_comm_status")
+
+    def comm_allreduce_f64(self, buf):
+        """In-place fp64 sum over the ranks, rank order (bit-identical on all ranks)."""
+        self._ck(self.lib.ocg_comm_allreduce_f64(self.h, _dptr(buf), buf.numel(), self._stream()), "ocg_comm_allreduce_f64")
+
+    def self_gravity_sharded(self, pos_local, mass_all, eps2, G, acc_local, pot_local=None):
+        """K4 for this rank's block of stars, the position gather fused into the tile pack (peer memory over NVLink)."""
+        self._ck(self.lib.ocg_self_gravity_sharded(self.h, _dptr(pos_local), _dptr(mass_all), mass_all.shape[0], float(eps2),
+                                                   float(G), _dptr(acc_local), _dptr(pot_local), self._stream()),
+                 "ocg_self_gravity_sharded")
+
     # ---- host-buffer call (numpy in, numpy out; H2D/D2H inside) ----
     def field_build_host(self, src_pos, src_mass, src_soft, tgt_pos, center, center_row, kernel, G, want_pot=False):
         """_populate_grid_acceleration_ (gizmo_interface.py:512-573) in one call. Returns acc [3,n_tgt] (, pot)."""
@@ -398,6 +444,12 @@ class Context:
                                                _vec3(center), int(center_row), int(kernel), float(G), _hptr(acc),
                                                _hptr(pot)), "ocg_field_build_host")
         return (acc, pot) if want_pot else acc
+
+
+def private_context(device=None):
+    """A ctx of its own for one code object (scratch + settings only): what a captured CUDA graph wants, so that no
+    other caller can move or overwrite the buffers the graph froze."""
+    return Context(int(os.environ.get("LOCAL_RANK", "0")) if device is None else device)
 
 
 _default_ctx = {}

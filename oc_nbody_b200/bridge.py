@@ -15,7 +15,8 @@ public ``get_gravity_at_point(eps, x, y, z)``.
 K5 ... — 10 launches) is captured once into a CUDA graph and replayed with ONE launch per step.  What changes from
 step to step — the time-blend weights of the two half-kicks — lives in constant memory and is refreshed before each
 replay (ocg_set_interp_weight_slots); the grid origin is a device buffer.  The graph is re-captured when the
-bracketing snapshots, the particle count or the timestep change.  Results equal the eager path's to FP64 rounding
+bracketing snapshots, the particle count, the timestep or the capture epoch of a context (scratch reallocated, another
+work plan uploaded: include/ocg.h ocg_capture_epoch) change.  Results equal the eager path's to FP64 rounding
 (the eager drift integrates over (t + dt) - model_time, which can differ from dt in the last bit).
 The star-sharded cluster code is captured the same way, its NCCL all-gathers included (every rank takes the same
 eager / capture / replay decisions, so the collectives stay matched).
@@ -87,8 +88,11 @@ class Bridge(object):
         rec0, fine0, w0 = fld._time_planes_()
         fld.evolve_model((t0 + dt) | units.Myr)          # host only: bracket + weights of the second half-kick
         rec1, fine1, w1 = fld._time_planes_()
+        # what a captured graph froze: record planes, particle buffers, step parameters — and, through the capture epochs,
+        # the scratch addresses and resident work plans of the two contexts (another call on a shared ctx may have grown a
+        # buffer or uploaded another cluster's plan since: then this step runs eagerly and the next one re-captures)
         key = (tuple(r.data_ptr() for r in rec0), tuple(r.data_ptr() for r in rec1), cl.n, cl.pos.data_ptr(), cl.substeps,
-               dt, cl.parameters._eps2_kpc2, fld._dev["origin"].data_ptr())
+               dt, cl.parameters._eps2_kpc2, fld._dev["origin"].data_ptr(), cl.ctx.capture_epoch(), fld.ctx.capture_epoch())
 
         def body():
             fld.kick_device(cl.pos, cl.vel, 0.5 * dt, planes=(rec0, fine0), w_slot=0)
@@ -100,6 +104,11 @@ class Bridge(object):
             self._graph.replay()
             self.graph_replays += 1
         elif key == self._seen_key:
+            # capture.  On a ctx shared with another particle set the resident work plan may be the other one's, and a
+            # plan upload is not capturable: re-evaluate the current force eagerly first (same inputs, same values), which
+            # leaves this cluster's plan resident, and take the key with the epoch that results
+            cl._prepare_capture_()
+            key = key[:-2] + (cl.ctx.capture_epoch(), fld.ctx.capture_epoch())
             torch.cuda.synchronize()
             self._graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self._graph):

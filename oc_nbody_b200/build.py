@@ -25,6 +25,7 @@ SOURCES = [
     ("grid_interp", "grid_interp.cu", []),
     ("rbf_interp", "rbf_interp.cu", []),
     ("cluster_ops", "cluster_ops.cu", []),
+    ("comm", "comm.cu", []),
 ]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -90,7 +90,9 @@ class cluster_code(object):
             raise ValueError("integrator must be 'leapfrog' or 'hermite', not %r" % (integrator,))
         self.integrator = integrator
         self.eta = float(eta)  # Aarseth accuracy parameter (ph4's timestep_parameter, default 0.14)
-        self.ctx = ctx or _lib.default_context()
+        # a ctx of its own unless the caller shares one: a ctx is only scratch + settings, and a BRIDGE step captured as a
+        # CUDA graph freezes the scratch addresses and the resident work plan (ocg_capture_epoch, include/ocg.h)
+        self.ctx = ctx or _lib.private_context()
         self._dev = torch.device("cuda", self.ctx.device)
         self.parameters = _Parameters()
         self.parameters.epsilon_squared = (softening_pc | units.parsec) ** 2
@@ -279,6 +281,15 @@ class cluster_code(object):
         self.n_bound, self.bound_mass = int(res[4]), float(res[3])
         return (res[:3], mask.cpu().numpy().astype(bool)) if return_mask else res[:3]
 
+    def _prepare_capture_(self):
+        """Called by Bridge right before it captures a step as a CUDA graph: recompute the current force eagerly (same
+        positions, so the same values) so that everything the force call uploads on demand — the work plan — is resident
+        and the capture itself contains kernel launches only."""
+        if self.integrator == "hermite":
+            self._force_hermite_(self.pos, self.vel, self.acc, self.jerk)
+        else:
+            self.compute_self_gravity()
+
     def stop(self):
         pass
 
@@ -292,9 +303,15 @@ class sharded_cluster_code(cluster_code):
     mass / pos / vel passed in are the FULL arrays (identical on every rank); the constructor keeps the block."""
 
     def __init__(self, mass, pos, vel, softening_pc=0.01, substeps=1, eject_cut=None, ctx=None, group=None,
-                 integrator="leapfrog", eta=0.14):
+                 integrator="leapfrog", eta=0.14, exchange="peer"):
+        """exchange="peer": the position gather of the leapfrog force runs over peer memory, fused into the tile pack
+        (ocg_self_gravity_sharded: 2 launches per evaluation); "nccl": torch.distributed all-gather + copy + K4 with a
+        target range (also what the Hermite force, which needs velocities too, uses)."""
         import torch.distributed as dist
         from .distributed import shard_range
+        if exchange not in ("peer", "nccl"):
+            raise ValueError("exchange must be 'peer' or 'nccl', not %r" % (exchange,))
+        self.exchange = exchange
         self.group = group
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
@@ -312,6 +329,11 @@ class sharded_cluster_code(cluster_code):
         if integrator == "hermite":
             self._jerk_all = torch.empty((3, self.n_total), dtype=torch.float64, device=self._dev)
         self.key = np.arange(self.a, self.b)
+        self._peer = False
+        if exchange == "peer" and integrator == "leapfrog" and self.parameters._eps2_kpc2 > 0.0 and self.n_total // self.world >= 2048:
+            from .distributed import connect_comm
+            connect_comm(self.ctx, group, window_bytes=max(1 << 20, 64 * (self.n_total // self.world + 1)))
+            self._peer = True
 
     def _force_hermite_(self, pos, vel, acc, jerk):
         """K6 for the rank's target block: positions AND velocities are all-gathered (the jerk needs both)."""
@@ -331,6 +353,12 @@ class sharded_cluster_code(cluster_code):
 
     def compute_self_gravity(self, want_pot=False):
         from .distributed import allgather_particles
+        if self._peer:
+            # one kernel publishes this block, reads the peers' over NVLink and packs the FP32 tiles; one force kernel
+            self.ctx.self_gravity_sharded(self.pos, self.mass_all, self.parameters._eps2_kpc2, self.G, self.acc,
+                                          self.pot if want_pot else None)
+            self._acc_valid = True
+            return self.acc
         pos_all = allgather_particles(self.pos, self.n_total, self.group).contiguous()
         self.ctx.self_gravity(pos_all, self.mass_all, self.parameters._eps2_kpc2, self.G, self._acc_all,
                               self._pot_all if want_pot else None, tgt_begin=self.a, tgt_end=self.b)

@@ -18,7 +18,7 @@ int ocg_fail(ocg_ctx* ctx, int code, const char* fmt, ...) {
   return code;
 }
 
-int ocg_scratch(ocg_ctx* ctx, int which, size_t bytes, void** out) {
+int ocg_scratch(ocg_ctx* ctx, int which, size_t bytes, void** out, bool zero_on_alloc) {
   if (bytes == 0) bytes = 256;
   if (ctx->scratch_bytes[which] < bytes) {
     if (ctx->scratch[which]) {
@@ -42,8 +42,14 @@ int ocg_scratch(ocg_ctx* ctx, int which, size_t bytes, void** out) {
       return ocg_fail(ctx, OCG_ERR_NOMEM, "cudaMalloc of %zu bytes for scratch %d failed: %s", bytes,
                       which, cudaGetErrorString(e));
     }
+    if (zero_on_alloc && cudaMemset(p, 0, want) != cudaSuccess) {  // synchronous: ordered before any later launch
+      cudaGetLastError();
+      cudaFree(p);
+      return ocg_fail(ctx, OCG_ERR_CUDA, "cudaMemset of scratch %d failed", which);
+    }
     ctx->scratch[which] = p;
     ctx->scratch_bytes[which] = want;
+    ctx->scratch_generation++;
   }
   *out = ctx->scratch[which];
   return OCG_OK;
@@ -83,6 +89,7 @@ extern "C" int ocg_create(int device, ocg_ctx** out) {
   ctx->knobs.interp_variant = 2;
   ctx->knobs.field_precision = 0;
   ctx->knobs.rbf_share = 1;
+  ctx->knobs.near_cap = 0;
   ctx->sm_count = prop.multiProcessorCount;
   int khz = 0;
   cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, device);
@@ -100,6 +107,7 @@ extern "C" int ocg_create(int device, ocg_ctx** out) {
 extern "C" int ocg_destroy(ocg_ctx* ctx) {
   if (!ctx) return OCG_OK;
   OcgDeviceGuard g(ctx->device);
+  ocg_comm_destroy(ctx);
   cudaDeviceSynchronize();
   for (int i = 0; i < OCG_SCR_N; ++i)
     if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
@@ -122,6 +130,17 @@ extern "C" int ocg_device_info(ocg_ctx* ctx, int* sm_count, int* sm_clock_khz, i
 }
 
 extern "C" int64_t ocg_launch_count(const ocg_ctx* ctx) { return ctx ? ctx->launches : -1; }
+
+// Everything a captured CUDA graph of this ctx's calls froze into its kernel nodes: the scratch addresses (generation)
+// and the work plans resident in the two item buffers (K4, K6).
+extern "C" int64_t ocg_capture_epoch(const ocg_ctx* ctx) {
+  if (!ctx) return -1;
+  unsigned long long h = 1469598103934665603ull;
+  const unsigned long long parts[5] = {ctx->scratch_generation, ctx->plan[0].items_hash, (unsigned long long)ctx->plan[0].items_uploaded,
+                                       ctx->plan[1].items_hash, (unsigned long long)ctx->plan[1].items_uploaded};
+  for (int i = 0; i < 5; ++i) h = (h ^ parts[i]) * 1099511628211ull;
+  return (int64_t)(h >> 1);
+}
 
 extern "C" int ocg_set_kernel_timing(ocg_ctx* ctx, int enabled) {
   if (!ctx) return OCG_ERR_INVALID;
@@ -166,6 +185,7 @@ extern "C" int ocg_debug_set(ocg_ctx* ctx, int knob, int64_t value) {
       k.interp_variant = (int)value;
       return OCG_OK;
     case OCG_KNOB_RBF_SHARE: k.rbf_share = value != 0; return OCG_OK;
+    case OCG_KNOB_NEAR_CAP: k.near_cap = value > 0 ? value : 0; return OCG_OK;
     default: return ocg_fail(ctx, OCG_ERR_INVALID, "ocg_debug_set: unknown knob %d", knob);
   }
 }

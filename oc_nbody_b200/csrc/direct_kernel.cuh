@@ -2,6 +2,7 @@
 // Included by direct_sum.cu only.
 #pragma once
 #include "ocg_internal.cuh"
+#include "streamk.cuh"
 
 typedef unsigned long long u64;
 
@@ -479,11 +480,38 @@ __global__ void __launch_bounds__(32 * NW, MINB) direct_sum_tp_kernel(const Dire
   };
 
   const float scale = p.scale_ptr ? *p.scale_ptr : p.scale_val;
-  for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-    long long tgt_begin, tile_begin, slot;
+  __shared__ int s_last;
+  __shared__ long long s_sk[3];  // units of the launch, participating CTAs, end of this CTA's unit range: read back in
+                                 // the segment epilogue instead of being held in registers across the tile loop
+  // ---- stream-K: this CTA's share of the (target tile x source tile) units, see streamk.cuh ----
+  long long u;
+  {
+    const long long U = sk_units(p.sk);
+    const long long G_ = sk_ctas(U, gridDim.x);  // CTAs that take part: every one of them gets at least one unit
+    if (U == 0) {  // nothing to stream (K1 with an empty fast set): the field of no sources is zero
+      if (!p.accumulate)
+        for (long long i = blockIdx.x * (long long)NTHR + tid; i < p.out_n; i += (long long)gridDim.x * NTHR) {
+          p.out_acc[i] = 0.0, p.out_acc[p.out_n + i] = 0.0, p.out_acc[2 * p.out_n + i] = 0.0;
+          if (POT) p.out_pot[i] = 0.0;
+        }
+      return;
+    }
+    u = blockIdx.x < G_ ? sk_first_unit(blockIdx.x, U, G_) : 0;
+    if (tid == 0) s_sk[0] = U, s_sk[1] = G_, s_sk[2] = blockIdx.x < G_ ? sk_first_unit(blockIdx.x + 1, U, G_) : 0;
+    __syncthreads();
+  }
+  for (int row = u < s_sk[2] ? sk_find_row(p.sk, u) : 0; u < s_sk[2]; ++row) {
     int tgt_count, tile_count;
-    decode_item<T, NTHR>(p, item, tgt_begin, tgt_count, tile_begin, tile_count, slot);
-    const float* src = p.tiles + tile_begin * (long long)TILE_FLOATS;
+    long long tgt_begin;
+    const float* src;
+    {
+      const long long rs = sk_row_start(p.sk, row), re = sk_row_start(p.sk, row + 1), u_end = s_sk[2];
+      long long tile_begin;
+      tile_count = (int)((re < u_end ? re : u_end) - u);
+      sk_row(p.sk, row, tgt_begin, tgt_count, tile_begin);
+      src = p.tiles + (tile_begin + (u - rs)) * (long long)TILE_FLOATS;
+      u += tile_count;
+    }
     if (tid == 0) {
       const int pre = tile_count < OCG_NSTAGE - 1 ? tile_count : OCG_NSTAGE - 1;
       for (int k = 0; k < pre; ++k) issue_tile(it + k, src + (long long)k * TILE_FLOATS);
@@ -553,21 +581,68 @@ __global__ void __launch_bounds__(32 * NW, MINB) direct_sum_tp_kernel(const Dire
       }
     }
 
+    // ---- segment epilogue: who shares this row, and the final scaling (recomputed here, not carried over the loop) ----
+    const long long U = s_sk[0], G_ = s_sk[1];
+    const long long rs = sk_row_start(p.sk, row), re = sk_row_start(p.sk, row + 1);
+    const int first_cta = sk_cta_of(rs, U, G_);
+    const int n_sharers = sk_cta_of(re - 1, U, G_) - first_cta + 1;
+    const long long slot = (long long)blockIdx.x - first_cta;
+    {
+      long long unused_tile;
+      sk_row(p.sk, row, tgt_begin, tgt_count, unused_tile);  // re-read: not live across the tile loop
+    }
+    // final scaling of the sums: G s^2 (potential: G s), times M0 when the tiles are mass-folded
+    const double gm = p.G * (p.m0_ptr ? (double)*p.m0_ptr : 1.0), fa = gm * (double)scale * (double)scale, fp = gm * (double)scale;
+    auto write_out = [&](long long gi, int c, double sum) {
+      if (c < 3) {
+        double* dst = p.out_acc + (long long)c * p.out_n + gi;
+        const double v = sum * fa;
+        *dst = p.accumulate ? *dst + v : v;
+      } else {
+        if (p.self_e2s > 0.f)  // K4: targets are sources; take the self term -m/eps out with the kernel's own FP32 expression
+          sum += (double)((__ldg(&p.tgt[gi]).w * rsqrt_approx((p.self_e2s * p.self_e2s) * p.self_e2s)) * p.self_e2s);
+        const double v = sum * fp;
+        p.out_pot[gi] = p.accumulate ? p.out_pot[gi] + v : v;
+      }
+    };
+    auto own = [&](int t, int c) -> double {
+      if (SMEMACC) {
+        const double2 q = sacc2[(c * NP + (t >> 1)) * NTHR + tid];
+        return (t & 1) ? q.y : q.x;
+      }
+      return dacc[SMEMACC ? 0 : t][c];
+    };
+    if (n_sharers == 1) {
+      // the whole row was streamed here: scale and write the field
 #pragma unroll
-    for (int t = 0; t < T; ++t) {
-      const int local = t * NTHR + tid;
-      if (local < tgt_count) {
-        const long long gi = tgt_begin + local;
+      for (int t = 0; t < T; ++t) {
+        const int local = t * NTHR + tid;
+        if (local < tgt_count)
 #pragma unroll
-        for (int c = 0; c < NC; ++c) {
-          double v;
-          if (SMEMACC) {
-            const double2 q = sacc2[(c * NP + (t >> 1)) * NTHR + tid];
-            v = (t & 1) ? q.y : q.x;
-          } else {
-            v = dacc[SMEMACC ? 0 : t][c];
+          for (int c = 0; c < NC; ++c) write_out(tgt_begin + local, c, own(t, c));
+      }
+    } else {
+#pragma unroll
+      for (int t = 0; t < T; ++t) {
+        const int local = t * NTHR + tid;
+        if (local < tgt_count)
+#pragma unroll
+          for (int c = 0; c < NC; ++c) p.partial[(slot * NC + c) * p.out_stride + tgt_begin + local] = own(t, c);
+      }
+      if (sk_last_of_row(p.sk, row, n_sharers, &s_last)) {
+        // last of the row's CTAs: add the slots in slot order (deterministic whatever the arrival order)
+#pragma unroll
+        for (int t = 0; t < T; ++t) {
+          const int local = t * NTHR + tid;
+          if (local < tgt_count) {
+            const long long gi = tgt_begin + local;
+#pragma unroll
+            for (int c = 0; c < NC; ++c) {
+              double sum = 0.0;
+              for (int k = 0; k < n_sharers; ++k) sum += __ldcg(&p.partial[((long long)k * NC + c) * p.out_stride + gi]);
+              write_out(gi, c, sum);
+            }
           }
-          p.partial[(slot * NC + c) * p.out_stride + gi] = v;
         }
       }
     }

@@ -32,7 +32,7 @@
 // target box, or a source whose r^6 could leave the FP32 range for some target — or (b) accuracy
 // profits from it — it lies within the "precision radius" D of the target box, where single pair terms
 // are large compared with the net field and FP32 rounding of them would dominate the error budget.
-// D is the largest of 0.5, 0.25, ... x (box extent) for which the NEAR set stays below a small cap
+// D is the largest of 0.5, 0.35, 0.25, ... x (box extent) for which the NEAR set stays below a small cap
 // (so the FP64 work is <~1% of the total); it is chosen on the device from a distance histogram.
 //
 // All distances here are in SCALED units: lengths x scale, scale = 2^k with the largest extent of the
@@ -40,7 +40,7 @@
 //   [0..5]  target bbox as ordered ints: min xyz, max xyz (unscaled)
 //   [8] n_fast  [9] n_near  [10] n_fast_tiles  [11] scale (float bits)  [12] D^2 scaled (float bits)
 //   [13] M0 (float bits): power of two >= the largest source mass (mass-folded tiles, see tile_tpair MF)
-//   [16..31] histogram: hist[b] = #sources with scaled box distance < 0.5 * 2^-b
+//   [16..31] histogram: hist[b] = #sources with scaled box distance < 0.5 * 2^(-b/2)
 #define MISC_BBOX 0
 #define MISC_NFAST 8
 #define MISC_NNEAR 9
@@ -49,7 +49,7 @@
 #define MISC_D2 12
 #define MISC_M0 13
 #define MISC_HIST 16
-#define MISC_NBINS 12
+#define MISC_NBINS 16
 #define MISC_INTS 32
 
 #define R2_MIN_SCALED 1e-12f  /* r^6 >= 1e-36 stays a normal FP32 number */
@@ -168,9 +168,9 @@ __global__ void __launch_bounds__(CLS_BLOCK) classify_hist_kernel(
     if (S.w > 0.f && isfinite(S.w)) mbits = __float_as_int(S.w);
     float d2 = box_dist2_scaled(S.x, S.y, S.z, misc, sc);
     if (!source_must_be_near(d2, (soft ? soft[i] : 0.f) * sc, kernel)) {
-      // largest b with d < 0.5 * 2^-b  <=>  d2 < 0.25 * 4^-b
+      // every b with d < 0.5 * 2^(-b/2)  <=>  d2 < 0.25 * 2^-b
       float lim = 0.25f;
-      for (int b = 0; b < MISC_NBINS && d2 < lim; ++b, lim *= 0.25f) atomicAdd(&h[b], 1);
+      for (int b = 0; b < MISC_NBINS && d2 < lim; ++b, lim *= 0.5f) atomicAdd(&h[b], 1);
     }
   }
   for (int o = 16; o > 0; o >>= 1) mbits = max(mbits, __shfl_xor_sync(0xffffffffu, mbits, o));
@@ -183,7 +183,7 @@ __global__ void __launch_bounds__(CLS_BLOCK) classify_hist_kernel(
 // precise == 0: no precision radius (criterion (a) only).  Rounds M0 up to a power of two.
 __global__ void choose_radius_kernel(int* misc, int cap, int precise) {
   float d2 = 0.f, lim = 0.25f;
-  for (int b = 0; precise && b < MISC_NBINS; ++b, lim *= 0.25f)
+  for (int b = 0; precise && b < MISC_NBINS; ++b, lim *= 0.5f)
     if (misc[MISC_HIST + b] <= cap) {
       d2 = lim;
       break;
@@ -463,6 +463,8 @@ struct DirectVariant {
   int mf;              // consumes mass-folded tiles (K1 without potential only); 2 = w array pair-swizzled
 };
 static inline int variant_threads(const DirectVariant& v) { return 32 * (v.nwarps ? v.nwarps : OCG_CONSUMER_WARPS); }
+// target-paired shapes (direct_sum_tp_kernel: stream-K rows, fused finish) vs source-paired ones (direct_sum_kernel: items)
+static inline bool variant_is_tp(const DirectVariant& v) { return !strncmp(v.name, "tpair", 5) || !strncmp(v.name, "DBG", 3); }
 #define OCG_NOFN {{nullptr, nullptr}, {nullptr, nullptr}}
 #ifdef OCG_TUNING
 #define TUNE(...) __VA_ARGS__
@@ -604,8 +606,9 @@ static const DirectVariant g_variants[] = {
     /* 74 */ {"tpair-mf(+pot) np4 12w swizzled fold64", 8, 1, false, OCG_TPMFP(4, true, 1, 1, 12, 64), 8, 12, 2},  // production: BIG_MF_POT
     /* 75 */ {"tpair-mf(+pot) np5 8w swizzled fold64", 10, 1, false, TUNE(OCG_TPMFP(5, true, 1, 1, 8, 64)), 10, 8, 2},
     /* 76 */ {"tpair-mf(+pot) np4 12w swizzled fold512", 8, 1, false, TUNE(OCG_TPMFP(4, true, 1, 1, 12, 512)), 8, 12, 2},
-    /* 77 */ {"tpair-mf(+pot) np1 regacc minb2 unr2 swizzled fold64", 2, 2, false, OCG_TPMFP(1, false, 2, 2, OCG_CONSUMER_WARPS, 64), 0, 0, 2},  // production: MID_MF
+    /* 77 */ {"tpair-mf(+pot) np1 regacc minb2 unr2 swizzled fold32", 2, 2, false, OCG_TPMFP(1, false, 2, 2, OCG_CONSUMER_WARPS, 32), 0, 0, 2},  // production: MID_MF
     /* 78 */ {"tpair-mf(+pot) np1 regacc minb2 unr2 swizzled fold512", 2, 2, false, TUNE(OCG_TPMFP(1, false, 2, 2, OCG_CONSUMER_WARPS, 512)), 0, 0, 2},
+    /* 79 */ {"tpair-mf(+pot) np1 regacc minb2 unr2 swizzled fold64", 2, 2, false, TUNE(OCG_TPMFP(1, false, 2, 2, OCG_CONSUMER_WARPS, 64)), 0, 0, 2},
 };
 static const int g_n_variants = (int)(sizeof(g_variants) / sizeof(g_variants[0]));
 // Production choices (tools/probe.py sweeps on B200, profiles/r01_variant_sweep*.json, profiles/r02_fold_sweep.json):
@@ -617,7 +620,8 @@ static const int g_n_variants = (int)(sizeof(g_variants) / sizeof(g_variants[0])
 #define OCG_VARIANT_BIG_MF 67     /* K1 >= 64k targets: mass-folded, w-swizzled tiles, 12 targets/thread, 8 warps, FOLD 64 */
 #define OCG_VARIANT_BIG_MF_POT 74 /* the same with the potential: 6-array tiles, 8 targets/thread, 12 warps, FOLD 64 */
 #define OCG_VARIANT_MID 27        /* >= 16k targets, plain tiles (K4): target-paired, 2 targets/thread              */
-#define OCG_VARIANT_MID_MF 77     /* K1 mid-size target counts: mass-folded, 2 targets/thread, FOLD 64, with or without potential */
+#define OCG_VARIANT_MID_MF 77     /* K1 mid-size target counts: mass-folded, 2 targets/thread, register FP64 accumulators (a fold costs
+                                     12 instructions): FOLD 32, with or without potential */
 #define OCG_VARIANT_MID_GUARD 4   /* source-paired 2 targets/thread (carries the eps2 == 0 guarded form)          */
 #define OCG_VARIANT_SMALL 1       /* few targets: 1 target/thread spreads them over more CTAs (has guard form)    */
 
@@ -655,6 +659,8 @@ int ocg_pick_variant(ocg_ctx* ctx, int64_t n_tgt, int64_t seg_len, bool guard, b
   if ((n_tgt >= 16384 || enough(OCG_VARIANT_MID)) && waste_ok(OCG_VARIANT_MID)) return OCG_VARIANT_MID;
   return OCG_VARIANT_SMALL;
 }
+bool ocg_variant_is_tp(int v) { return variant_is_tp(g_variants[v]); }
+int ocg_variant_cluster_tp() { return OCG_VARIANT_MID; }
 int ocg_variant_tpt(int v) { return g_variants[v].tpt; }
 int ocg_variant_threads(int v) { return variant_threads(g_variants[v]); }
 int ocg_variant_slots(ocg_ctx* ctx, int v) { return ctx->sm_count * g_variants[v].minb; }
@@ -677,7 +683,7 @@ int ocg_launch_direct(ocg_ctx* ctx, DirectParams& p, int variant, bool pot, bool
   if (v->smem_acc_comps) smem = OCG_NSTAGE * tile_bytes + 128 + (size_t)(pot ? 4 : 3) * v->smem_acc_comps * variant_threads(*v) * sizeof(double);
   OCG_CUDA(ctx, cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int grid = ctx->sm_count * v->minb;
-  if (grid > p.n_items) grid = p.n_items;
+  if (!variant_is_tp(*v) && grid > p.n_items) grid = p.n_items;  // stream-K kernels always fill the machine
   if (grid < 1) grid = 1;
   if (ctx->timing) OCG_CUDA(ctx, cudaEventRecord(ctx->ev0, st));
   fn<<<grid, variant_threads(*v) + (v->ded ? 32 : 0), smem, st>>>(p);
@@ -720,15 +726,24 @@ int ocg_direct_sum_impl(ocg_ctx* ctx, const float* src_xyzm, const float* src_so
   const int CT = ocg_variant_threads(variant) * tpt;
   const long long n_ttiles = (n_tgt + CT - 1) / CT;
   const long long n_tiles_max = (n_src + OCG_TS - 1) / OCG_TS;
-  // chunking: aim for >= 64 equal-cost items per resident CTA slot (static striding; tail loss < 1%)
   const long long slots = ocg_variant_slots(ctx, variant);
-  long long n_chunks = (64 * slots + n_ttiles - 1) / n_ttiles;
-  if (n_chunks > n_tiles_max) n_chunks = n_tiles_max;
-  if (n_chunks > 1024) n_chunks = 1024;
-  if (n_chunks < 1) n_chunks = 1;
-  const long long tiles_per_chunk = (n_tiles_max + n_chunks - 1) / n_chunks;
-  n_chunks = (n_tiles_max + tiles_per_chunk - 1) / tiles_per_chunk;
-  if (n_ttiles * n_chunks > 0x7fffffffll) return ocg_fail(ctx, OCG_ERR_INVALID, "too many work items");
+  const bool tp = variant_is_tp(g_variants[variant]);
+  long long n_chunks, tiles_per_chunk = 0;
+  if (tp) {
+    // stream-K (streamk.cuh): a row of targets is shared by at most ceil(CTAs / rows) + 1 consecutive CTAs
+    n_chunks = (slots + n_ttiles - 1) / n_ttiles + 1;
+    if (n_chunks > slots) n_chunks = slots;
+    if (n_ttiles > 0x7fffffffll) return ocg_fail(ctx, OCG_ERR_INVALID, "too many target tiles");
+  } else {
+    // (target tile x source chunk) items dealt round robin: aim for >= 64 equal-cost items per resident CTA slot
+    n_chunks = (64 * slots + n_ttiles - 1) / n_ttiles;
+    if (n_chunks > n_tiles_max) n_chunks = n_tiles_max;
+    if (n_chunks > 1024) n_chunks = 1024;
+    if (n_chunks < 1) n_chunks = 1;
+    tiles_per_chunk = (n_tiles_max + n_chunks - 1) / n_chunks;
+    n_chunks = (n_tiles_max + tiles_per_chunk - 1) / tiles_per_chunk;
+    if (n_ttiles * n_chunks > 0x7fffffffll) return ocg_fail(ctx, OCG_ERR_INVALID, "too many work items");
+  }
 
   int* misc;
   float* tiles;
@@ -744,6 +759,9 @@ int ocg_direct_sum_impl(ocg_ctx* ctx, const float* src_xyzm, const float* src_so
   if ((rc = ocg_scratch(ctx, OCG_SCR_NEAR, (size_t)n_src * 20, (void**)&near_xyzm))) return rc;
   near_soft = reinterpret_cast<float*>(near_xyzm + n_src);
   if ((rc = ocg_scratch(ctx, OCG_SCR_COUNTS, (size_t)n_cls_blocks * sizeof(int), (void**)&counts))) return rc;
+  unsigned int* tickets = nullptr;
+  if (tp && (rc = ocg_scratch(ctx, OCG_SCR_TICKETS, (size_t)n_ttiles * sizeof(unsigned int), (void**)&tickets, /*zero_on_alloc=*/true)))
+    return rc;
 
   const float4* src4 = reinterpret_cast<const float4*>(src_xyzm);
   const float4* tgt4 = reinterpret_cast<const float4*>(tgt_xyzw);
@@ -761,9 +779,11 @@ int ocg_direct_sum_impl(ocg_ctx* ctx, const float* src_xyzm, const float* src_so
   if (ctx->knobs.precise_near || mf) {
     classify_hist_kernel<<<(int)n_cls_blocks, CLS_BLOCK, 0, st>>>(src4, src_soft, n_src, kernel, misc);
     OCG_CHECK_LAUNCH(ctx, "classify_hist_kernel");
-    // cap the FP64 set at ~0.2% of the sources (>= 4096): its pair cost is ~5x the FP32 one
-    long long cap = n_src / 512;
-    if (cap < 4096) cap = 4096;
+    // cap the FP64 set at ~0.2% of the sources: its pair cost is ~4x the FP32 one, so the near pass stays ~1% of the call.
+    // Small snapshots (few, heavy particles: the reference's test_options scale) get a floor of 16384: their single pair
+    // terms are a larger share of the field, and the whole call is milliseconds anyway.
+    long long cap = ctx->knobs.near_cap > 0 ? ctx->knobs.near_cap : n_src / 512;
+    if (ctx->knobs.near_cap <= 0 && cap < 16384) cap = 16384;
     choose_radius_kernel<<<1, 1, 0, st>>>(misc, (int)cap, ctx->knobs.precise_near);
     OCG_CHECK_LAUNCH(ctx, "choose_radius_kernel");
   }
@@ -790,13 +810,26 @@ int ocg_direct_sum_impl(ocg_ctx* ctx, const float* src_xyzm, const float* src_so
   p.n_fast_tiles = misc + MISC_NFAST_TILES;
   p.scale_ptr = reinterpret_cast<const float*>(misc + MISC_SCALE);
   p.scale_val = 1.0f;
+  p.sk.rows = nullptr, p.sk.row_prefix = nullptr;
+  p.sk.n_rows = (int)n_ttiles, p.sk.n_slots = (int)n_chunks;
+  p.sk.n_tgt = n_tgt, p.sk.ct = CT;
+  p.sk.nst_uniform = misc + MISC_NFAST_TILES;
+  p.sk.tickets = tickets;
+  p.out_acc = acc, p.out_pot = pot, p.out_n = n_tgt;
+  p.G = G, p.accumulate = accumulate, p.self_e2s = -1.f;
+  p.m0_ptr = mf ? reinterpret_cast<const float*>(misc + MISC_M0) : nullptr;
   if ((rc = ocg_launch_direct(ctx, p, variant, want_pot, /*guard=*/false, st))) return rc;
-  ctx->last_traffic_bytes = n_tiles_max * (long long)narr * OCG_TS * 4 + n_tgt * 16 + n_chunks * NC * n_tgt * 8;
+  // what the launch has to move through HBM: tiles and targets once, the FP64 field once, and for the rows shared by
+  // several CTAs one partial slot per extra sharer (at most one extra sharer per CTA boundary)
+  ctx->last_traffic_bytes = n_tiles_max * (long long)narr * OCG_TS * 4 + n_tgt * 16 + (long long)NC * n_tgt * 8 +
+                            (tp ? 2 * (slots < n_ttiles ? slots : n_ttiles) : n_chunks * n_tgt / CT) * (long long)NC * CT * 8;
 
   {
     long long nb = (n_tgt + 255) / 256;
-    finish_kernel<<<(int)nb, 256, 0, st>>>(partial, n_tgt, (int)n_chunks, NC, G, misc, n_tgt, acc, pot, accumulate, mf);
-    OCG_CHECK_LAUNCH(ctx, "finish_kernel");
+    if (!tp) {
+      finish_kernel<<<(int)nb, 256, 0, st>>>(partial, n_tgt, (int)n_chunks, NC, G, misc, n_tgt, acc, pot, accumulate, mf);
+      OCG_CHECK_LAUNCH(ctx, "finish_kernel");
+    }
     long long nbn = (n_tgt + NEAR_BLOCK - 1) / NEAR_BLOCK;
     near_sum_kernel<<<(int)nbn, NEAR_BLOCK, 0, st>>>(near_xyzm, near_soft, misc, tgt4, n_tgt, kernel, G, acc, pot);
     OCG_CHECK_LAUNCH(ctx, "near_sum_kernel");

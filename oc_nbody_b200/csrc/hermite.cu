@@ -11,8 +11,9 @@
 //
 // Same structure as K4 (direct_kernel.cuh): TMA-staged source tiles in a shared-memory ring, target-paired
 // packed FP32 (the two lanes of an FFMA2 are two targets, the source is the broadcast operand), FP32 partial
-// sums over one 512-source tile, FP64 per-target accumulators in shared memory, chunk partials summed in index
-// order by the finish kernel (run-to-run deterministic).  26 FMA-pipe operations + 1 MUFU per interaction.
+// sums over one 512-source tile, FP64 per-target accumulators in shared memory; the work is cut stream-K fashion
+// (streamk.cuh) and the last CTA of a target row adds the row's partial slots in slot order and writes the result
+// (run-to-run deterministic, no finish kernel).  26 FMA-pipe operations + 1 MUFU per interaction.
 #include "direct_kernel.cuh"
 
 #include <math.h>
@@ -29,8 +30,11 @@ struct HermiteParams {
   const float4* tgt_vel;  // [n] recentred (vx, vy, vz, 0)
   double* partial;        // [slot][NC][out_stride]
   long long out_stride;
-  const OcgWorkItem* items;
-  int n_items;
+  StreamKParams sk;       // rows = target tiles of the shard x the source tiles of their segment (streamk.cuh)
+  double* out_acc;        // final outputs [3][out_stride], [3][out_stride], [out_stride], written by a row's last CTA
+  double* out_jerk;
+  double* out_pot;
+  double G, vel_to_len;
   float e2s;    // eps^2 in scaled units
   float scale;  // power-of-two length scale
 };
@@ -174,11 +178,30 @@ __global__ void __launch_bounds__(32 * NW, MINB) hermite_tp_kernel(const Hermite
 
   const float scale = p.scale;
   const u64 eb = f2_pack(p.e2s, p.e2s);
-  for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-    const OcgWorkItem w = p.items[item];
-    const long long tgt_begin = w.tgt_begin, slot = w.out_slot;
-    const int tgt_count = w.tgt_count, tile_count = w.tile_count;
-    const float* src = p.tiles + w.tile_begin * (long long)HM_TILE_FLOATS;
+  __shared__ int s_last;
+  __shared__ long long s_sk[3];  // units of the launch, participating CTAs, end of this CTA's unit range: read back in
+                                 // the segment epilogue instead of being held in registers across the tile loop
+  // ---- stream-K: this CTA's share of the (target tile x source tile) units, see streamk.cuh ----
+  long long u;
+  {
+    const long long U = sk_units(p.sk);
+    const long long G_ = sk_ctas(U, gridDim.x);  // CTAs that take part: every one of them gets at least one unit
+    u = blockIdx.x < G_ ? sk_first_unit(blockIdx.x, U, G_) : 0;
+    if (tid == 0) s_sk[0] = U, s_sk[1] = G_, s_sk[2] = blockIdx.x < G_ ? sk_first_unit(blockIdx.x + 1, U, G_) : 0;
+    __syncthreads();
+  }
+  for (int row = u < s_sk[2] ? sk_find_row(p.sk, u) : 0; u < s_sk[2]; ++row) {
+    int tgt_count, tile_count;
+    long long tgt_begin;
+    const float* src;
+    {
+      const long long rs = sk_row_start(p.sk, row), re = sk_row_start(p.sk, row + 1), u_end = s_sk[2];
+      long long tile_begin;
+      tile_count = (int)((re < u_end ? re : u_end) - u);
+      sk_row(p.sk, row, tgt_begin, tgt_count, tile_begin);
+      src = p.tiles + (tile_begin + (u - rs)) * (long long)HM_TILE_FLOATS;
+      u += tile_count;
+    }
     if (tid == 0) {
       const int pre = tile_count < HM_NSTAGE - 1 ? tile_count : HM_NSTAGE - 1;
       for (int k = 0; k < pre; ++k) issue_tile(it + k, src + (long long)k * HM_TILE_FLOATS);
@@ -233,35 +256,60 @@ __global__ void __launch_bounds__(32 * NW, MINB) hermite_tp_kernel(const Hermite
       }
     }
 
-#pragma unroll
-    for (int t = 0; t < T; ++t) {
-      const int local = t * NTHR + tid;
-      if (local < tgt_count) {
-        const long long gi = tgt_begin + local;
-#pragma unroll
-        for (int c = 0; c < NC; ++c) p.partial[(slot * NC + c) * p.out_stride + gi] = sacc[(c * T + t) * NTHR + tid];
-      }
+    // ---- segment epilogue: who shares this row, and the final scaling (recomputed here, not carried over the loop) ----
+    const long long U = s_sk[0], G_ = s_sk[1];
+    const long long rs = sk_row_start(p.sk, row), re = sk_row_start(p.sk, row + 1);
+    const int first_cta = sk_cta_of(rs, U, G_);
+    const int n_sharers = sk_cta_of(re - 1, U, G_) - first_cta + 1;
+    const long long slot = (long long)blockIdx.x - first_cta;
+    {
+      long long unused_tile;
+      sk_row(p.sk, row, tgt_begin, tgt_count, unused_tile);  // re-read: not live across the tile loop
     }
-  }
-}
-
-// acc = G s^2 sum, jerk = G s^3 vel_to_len sum (positions scaled by s, velocities not), pot = -G s sum with the
-// self term (m/eps, included by the kernel because targets == sources) removed with the kernel's own FP32 expression.
-__global__ void finish_hermite_kernel(const double* __restrict__ partial, long long stride, int n_slots, int nc, double G,
-                                      double vel_to_len, long long t0, long long t1, const float4* __restrict__ tgt_pos,
-                                      float e2s, float scale, double* __restrict__ acc, double* __restrict__ jerk,
-                                      double* __restrict__ pot) {
-  long long t = t0 + blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (t >= t1) return;
-  const double sc = (double)scale;
-  for (int c = 0; c < nc; ++c) {
-    double s = 0.0;
-    for (int k = 0; k < n_slots; ++k) s += partial[((long long)k * nc + c) * stride + t];
-    if (c < 3) acc[(long long)c * stride + t] = s * (G * sc * sc);
-    else if (c < 6) jerk[(long long)(c - 3) * stride + t] = s * (G * sc * sc * sc * vel_to_len);
-    else {
-      if (e2s > 0.f) s -= (double)(tgt_pos[t].w * rsqrt_approx(e2s));
-      pot[t] = -s * (G * sc);
+    // acc = G s^2 sum, jerk = G s^3 vel_to_len sum (positions scaled by s, velocities not), pot = -G s sum with the self
+    // term (m/eps, included because targets == sources) removed with the kernel's own FP32 expression
+    const double sc = (double)scale, fa = p.G * sc * sc, fj = fa * sc * p.vel_to_len, fp = p.G * sc;
+    auto write_out = [&](long long gi, int c, double sum) {
+      if (c < 3) p.out_acc[(long long)c * p.out_stride + gi] = sum * fa;
+      else if (c < 6) p.out_jerk[(long long)(c - 3) * p.out_stride + gi] = sum * fj;
+      else {
+        if (p.e2s > 0.f) sum -= (double)(__ldg(&p.tgt_pos[gi]).w * rsqrt_approx(p.e2s));
+        p.out_pot[gi] = -sum * fp;
+      }
+    };
+    if (n_sharers == 1) {
+      // the whole row was streamed here: scale and write acceleration, jerk and potential
+#pragma unroll
+      for (int t = 0; t < T; ++t) {
+        const int local = t * NTHR + tid;
+        if (local < tgt_count)
+#pragma unroll
+          for (int c = 0; c < NC; ++c) write_out(tgt_begin + local, c, sacc[(c * T + t) * NTHR + tid]);
+      }
+    } else {
+#pragma unroll
+      for (int t = 0; t < T; ++t) {
+        const int local = t * NTHR + tid;
+        if (local < tgt_count)
+#pragma unroll
+          for (int c = 0; c < NC; ++c) p.partial[(slot * NC + c) * p.out_stride + tgt_begin + local] = sacc[(c * T + t) * NTHR + tid];
+      }
+      if (sk_last_of_row(p.sk, row, n_sharers, &s_last)) {
+        // last of the row's CTAs: add the slots in slot order (deterministic whatever the arrival order)
+#pragma unroll
+        for (int t = 0; t < T; ++t) {
+          const int local = t * NTHR + tid;
+          if (local < tgt_count) {
+            const long long gi = tgt_begin + local;
+#pragma unroll
+            for (int c = 0; c < NC; ++c) {
+              double sum = 0.0;
+              for (int k = 0; k < n_sharers; ++k) sum += __ldcg(&p.partial[((long long)k * NC + c) * p.out_stride + gi]);
+              write_out(gi, c, sum);
+            }
+          }
+        }
+      }
     }
   }
 }
@@ -434,18 +482,21 @@ extern "C" int ocg_self_gravity_hermite(ocg_ctx* ctx, const double* pos_dev, con
   const HermiteVariant& v = g_hm_variants[variant];
   const int NTHR = 32 * v.nw, CT = 2 * v.np * NTHR;
 
-  OcgClusterPlan plan;
+  const long long grid_ctas = (long long)ctx->sm_count * v.minb;
+  OcgClusterRows plan;
   int rc;
-  if ((rc = ocg_plan_cluster_items(ctx, n, seg_offsets_host, n_seg, tgt_begin, tgt_end, CT, HM_TS, (long long)ctx->sm_count * v.minb, st, &plan, /*which=*/1)))
+  if ((rc = ocg_plan_cluster_rows(ctx, n, seg_offsets_host, n_seg, tgt_begin, tgt_end, CT, HM_TS, grid_ctas, st, &plan, /*which=*/1)))
     return rc;
   float* tiles;
   float4* tgt;
   double* partial;
+  unsigned int* tickets;
   // own scratch slots: a CUDA graph that captured this call must survive K4 calls (bound_center_of_mass) that would
-  // otherwise grow - i.e. reallocate - a shared buffer
+  // otherwise grow - i.e. reallocate - a shared buffer; the partials are always sized for the 7-component form
   rc = ocg_scratch(ctx, OCG_SCR_TILES_HM, (size_t)plan.total_tiles * HM_TILE_BYTES, (void**)&tiles);
   if (!rc) rc = ocg_scratch(ctx, OCG_SCR_TGT_HM, 2 * sizeof(float4) * (size_t)n, (void**)&tgt);
-  if (!rc) rc = ocg_scratch(ctx, OCG_SCR_PARTIAL_HM, sizeof(double) * (size_t)plan.n_chunks * 7 * (size_t)n, (void**)&partial);
+  if (!rc) rc = ocg_scratch(ctx, OCG_SCR_PARTIAL_HM, sizeof(double) * (size_t)plan.n_slots * 7 * (size_t)n, (void**)&partial);
+  if (!rc) rc = ocg_scratch(ctx, OCG_SCR_TICKETS_HM, sizeof(unsigned int) * (size_t)(plan.n_rows > 0 ? plan.n_rows : 1), (void**)&tickets, true);
   if (rc) return rc;
   {
     const long long nslots = plan.total_tiles * HM_TS;
@@ -453,26 +504,23 @@ extern "C" int ocg_self_gravity_hermite(ocg_ctx* ctx, const double* pos_dev, con
                                                                     plan.d_seg_tile, n_seg, scale, tiles, tgt, tgt + n);
     OCG_CHECK_LAUNCH(ctx, "pack_hermite_kernel");
   }
+  if (plan.n_rows == 0) return OCG_OK;
   HermiteParams p;
   p.tiles = tiles, p.tgt_pos = tgt, p.tgt_vel = tgt + n, p.partial = partial, p.out_stride = n;
-  p.items = plan.d_items, p.n_items = (int)plan.n_items, p.e2s = e2s, p.scale = scale;
+  p.sk.rows = plan.d_rows, p.sk.row_prefix = plan.d_prefix, p.sk.n_rows = plan.n_rows, p.sk.n_slots = plan.n_slots;
+  p.sk.n_tgt = n, p.sk.ct = CT, p.sk.nst_uniform = nullptr, p.sk.tickets = tickets;
+  p.out_acc = acc_dev, p.out_jerk = jerk_dev, p.out_pot = pot_dev, p.G = G, p.vel_to_len = vel_to_len;
+  p.e2s = e2s, p.scale = scale;
   hermite_fn fn = v.fn[want_pot][guard];
   const size_t smem = HM_NSTAGE * HM_TILE_BYTES + 128 + (size_t)NC * 2 * v.np * NTHR * sizeof(double);
   OCG_CUDA(ctx, cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int grid = ctx->sm_count * v.minb < p.n_items ? ctx->sm_count * v.minb : p.n_items;
-  if (grid < 1) grid = 1;
   if (ctx->timing) OCG_CUDA(ctx, cudaEventRecord(ctx->ev0, st));
-  fn<<<grid, NTHR, smem, st>>>(p);
+  fn<<<(int)grid_ctas, NTHR, smem, st>>>(p);
   OCG_CHECK_LAUNCH(ctx, "hermite_tp_kernel");
   if (ctx->timing) {
     OCG_CUDA(ctx, cudaEventRecord(ctx->ev1, st));
     ctx->ev_valid = 1;
   }
-  const int64_t n_shard = tgt_end - tgt_begin;
-  finish_hermite_kernel<<<(int)((n_shard + 255) / 256), 256, 0, st>>>(partial, n, (int)plan.n_chunks, NC, G, vel_to_len,
-                                                                     tgt_begin, tgt_end, tgt, e2s, scale, acc_dev, jerk_dev,
-                                                                     pot_dev);
-  OCG_CHECK_LAUNCH(ctx, "finish_hermite_kernel");
   return OCG_OK;
 }
 

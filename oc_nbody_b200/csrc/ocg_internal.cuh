@@ -33,7 +33,8 @@ struct OcgWorkItem {
 
 enum { OCG_SCR_TILES = 0, OCG_SCR_PARTIAL, OCG_SCR_NEAR, OCG_SCR_ITEMS, OCG_SCR_MISC, OCG_SCR_TGT,
        OCG_SCR_SRC, OCG_SCR_SOFT, OCG_SCR_F64A, OCG_SCR_F64B, OCG_SCR_F64C, OCG_SCR_OUT, OCG_SCR_COUNTS,
-       OCG_SCR_ITEMS_HM, OCG_SCR_TILES_HM, OCG_SCR_TGT_HM, OCG_SCR_PARTIAL_HM, OCG_SCR_N };
+       OCG_SCR_ITEMS_HM, OCG_SCR_TILES_HM, OCG_SCR_TGT_HM, OCG_SCR_PARTIAL_HM, OCG_SCR_TICKETS, OCG_SCR_TICKETS_HM,
+       OCG_SCR_N };
 
 // Tuning / test knobs of one ctx (include/ocg_debug.h: ocg_debug_set).  Defaults are the production behaviour.
 struct OcgKnobs {
@@ -47,10 +48,14 @@ struct OcgKnobs {
   int interp_variant;       // register bound of K3: 0 <=128, 1 <=80, 2 <=64 (production)
   int field_precision;      // 0 = FP32 pair arithmetic + FP64 accumulation (north_star), 1 = every pair in FP64
   int rbf_share;            // 1 = K7 shares one factorisation between stars with the same stencil pattern
+  long long near_cap;       // > 0: size limit of K1's FP64 precision-radius set (0 = max(16384, n_src / 512))
 };
+
+struct ocg_comm;  // comm.cu: the rank's exchange window and the mapped windows of its peers
 
 struct ocg_ctx {
   int device;
+  ocg_comm* comm;
   OcgKnobs knobs;
   int sm_count;
   int sm_clock_khz;
@@ -58,6 +63,7 @@ struct ocg_ctx {
   char err[1024];
   void* scratch[OCG_SCR_N];
   size_t scratch_bytes[OCG_SCR_N];
+  unsigned long long scratch_generation;  // bumped whenever a scratch buffer is (re)allocated: its address changed
   long long launches;
   int timing;
   cudaEvent_t ev0, ev1;
@@ -94,7 +100,7 @@ int ocg_fail(ocg_ctx* ctx, int code, const char* fmt, ...);
   } while (0)
 
 // Grow-only scratch buffer tied to the ctx.
-int ocg_scratch(ocg_ctx* ctx, int which, size_t bytes, void** out);
+int ocg_scratch(ocg_ctx* ctx, int which, size_t bytes, void** out, bool zero_on_alloc = false);
 
 struct OcgDeviceGuard {
   int prev;
@@ -108,6 +114,25 @@ struct OcgDeviceGuard {
   ~OcgDeviceGuard() {
     if (changed) cudaSetDevice(prev);
   }
+};
+
+// ---- stream-K work decomposition of the target-paired kernels (streamk.cuh) ----------------------
+struct OcgRow {
+  long long tgt_begin;   // first target of the row (global index)
+  long long tile_begin;  // first source tile of the run this row streams
+  int tgt_count;         // targets in the row (<= CTA tile)
+  int pad;
+};
+
+struct StreamKParams {
+  const OcgRow* rows;           // list mode (K4/K6); NULL = uniform mode (K1)
+  const long long* row_prefix;  // list mode: [n_rows + 1] prefix sums of the rows' source-tile counts
+  int n_rows;
+  int n_slots;                  // slots per row in the partial buffer (>= the most CTAs any row is shared by)
+  long long n_tgt;              // uniform mode: row r = targets [r*ct, min((r+1)*ct, n_tgt))
+  int ct;
+  const int* nst_uniform;       // uniform mode: device count of source tiles every row streams
+  unsigned int* tickets;        // [n_rows]; zero on entry, zero again on exit
 };
 
 // ---- parameter block of the direct-sum kernels (direct_sum.cu) -------------------------------
@@ -124,6 +149,15 @@ struct DirectParams {
   const int* n_fast_tiles;   // device: number of fast tiles actually present
   const float* scale_ptr;    // device: power-of-two length scale applied to targets (K1), or NULL
   float scale_val;           // host-chosen scale when scale_ptr is NULL (K4)
+  // target-paired kernels (direct_sum_tp_kernel): stream-K rows and the fused finish
+  StreamKParams sk;
+  double* out_acc;           // final field [3][out_n] (and [out_n] potential), written by the row's last CTA:
+  double* out_pot;           //   out = G * s^2 * sum (potential G * s), times M0 for mass-folded tiles
+  long long out_n;
+  double G;
+  int accumulate;            // add to the outputs instead of overwriting (K1 source chunks)
+  float self_e2s;            // K4: scaled eps^2 whose self term -m/eps is removed from the potential; < 0: none
+  const float* m0_ptr;       // mass-folded tiles: device M0 (partials are in units of M0); NULL otherwise
 };
 
 // ---- work plan of the cluster kernels (self_gravity.cu; shared by K4 and the Hermite force loop) ----
@@ -138,6 +172,18 @@ struct OcgClusterPlan {
 int ocg_plan_cluster_items(ocg_ctx* ctx, int64_t n, const int64_t* seg_offsets_host, int32_t n_seg, int64_t tgt_begin,
                            int64_t tgt_end, int ct, int ts, long long slots, cudaStream_t st, OcgClusterPlan* out,
                            int which = 0);
+// Stream-K form of the plan (streamk.cuh): one row per target tile of the shard, against the source tiles of its segment.
+struct OcgClusterRows {
+  long long total_tiles;        // source tiles over all segments
+  int n_rows;
+  int n_slots;                  // most CTAs any row is shared by, for a grid of `grid` CTAs
+  const OcgRow* d_rows;         // device [n_rows]
+  const long long* d_prefix;    // device [n_rows + 1]
+  const long long* d_seg_tile;  // device [n_seg + 1]
+  const long long* d_seg_off;   // device [n_seg + 1]
+};
+int ocg_plan_cluster_rows(ocg_ctx* ctx, int64_t n, const int64_t* seg_offsets_host, int32_t n_seg, int64_t tgt_begin,
+                          int64_t tgt_end, int ct, int ts, long long grid, cudaStream_t st, OcgClusterRows* out, int which = 0);
 
 // ---- entry points implemented in other translation units ------------------------------------
 int ocg_pick_variant(ocg_ctx* ctx, int64_t n_tgt, int64_t seg_len, bool guard, bool allow_mf = false,
@@ -147,6 +193,8 @@ const char* ocg_direct_variant_name(int id);
 bool ocg_direct_variant_built(int id);
 int ocg_hermite_n_variants();
 const char* ocg_hermite_variant_name(int id);
+bool ocg_variant_is_tp(int variant);
+int ocg_variant_cluster_tp();  // the target-paired shape K4 uses for clusters (512-target rows)
 int ocg_variant_tpt(int variant);
 int ocg_variant_threads(int variant);
 int ocg_variant_slots(ocg_ctx* ctx, int variant);

@@ -241,6 +241,82 @@ int ocg_plan_cluster_items(ocg_ctx* ctx, int64_t n, const int64_t* seg_offsets_h
 }
 
 
+// Stream-K plan (streamk.cuh) shared by K4 and the Hermite force loop: rows = target tiles of the shard, each against the
+// source tiles of its own segment; uploaded once and kept while the segment layout / shard / tile shape stay the same.
+// The cache slot and device buffer are those of the item plan (`which`: 0 K4, 1 K6), so the capture epoch covers it.
+int ocg_plan_cluster_rows(ocg_ctx* ctx, int64_t n, const int64_t* seg_offsets_host, int32_t n_seg, int64_t tgt_begin,
+                          int64_t tgt_end, int ct, int ts, long long grid, cudaStream_t st, OcgClusterRows* out, int which) {
+  ocg_ctx::PlanCache& pc = ctx->plan[which ? 1 : 0];
+  const int scr = which ? OCG_SCR_ITEMS_HM : OCG_SCR_ITEMS;
+  long long n_rows = 0, total_tiles = 0;
+  for (int s = 0; s < n_seg; ++s) {
+    const long long a = seg_offsets_host[s] > tgt_begin ? seg_offsets_host[s] : tgt_begin;
+    const long long b = seg_offsets_host[s + 1] < tgt_end ? seg_offsets_host[s + 1] : tgt_end;
+    if (b > a) n_rows += (b - a + ct - 1) / ct;
+    total_tiles += (seg_offsets_host[s + 1] - seg_offsets_host[s] + ts - 1) / ts;
+  }
+  if (n_rows > 0x7fffffffll) return ocg_fail(ctx, OCG_ERR_INVALID, "too many target tiles");
+  // one host block: rows | prefix | seg_tile | seg_off   (OcgRow is 24 bytes: keeps every part 8-byte aligned)
+  const size_t rows_bytes = sizeof(OcgRow) * (size_t)n_rows, pre_bytes = sizeof(long long) * ((size_t)n_rows + 1);
+  const size_t seg_bytes = sizeof(long long) * (2 * (size_t)n_seg + 2), bytes = rows_bytes + pre_bytes + seg_bytes;
+  const size_t cap_items = (bytes + sizeof(OcgWorkItem) - 1) / sizeof(OcgWorkItem);
+  if (cap_items > pc.items_host_cap) {
+    free(pc.items_host);
+    pc.items_host = (OcgWorkItem*)malloc(sizeof(OcgWorkItem) * cap_items);
+    pc.items_host_cap = pc.items_host ? cap_items : 0;
+    pc.items_uploaded = 0;
+    if (!pc.items_host) return ocg_fail(ctx, OCG_ERR_NOMEM, "malloc of the work plan failed");
+  }
+  char* base = (char*)pc.items_host;
+  OcgRow* rows = (OcgRow*)base;
+  long long* prefix = (long long*)(base + rows_bytes);
+  long long* seg_tile = (long long*)(base + rows_bytes + pre_bytes);
+  long long* seg_off = seg_tile + n_seg + 1;
+  long long tile0 = 0, r = 0, units = 0;
+  for (int s = 0; s < n_seg; ++s) {
+    const long long len = seg_offsets_host[s + 1] - seg_offsets_host[s], nt = (len + ts - 1) / ts;
+    seg_tile[s] = tile0, seg_off[s] = seg_offsets_host[s];
+    const long long a = seg_offsets_host[s] > tgt_begin ? seg_offsets_host[s] : tgt_begin;
+    const long long b = seg_offsets_host[s + 1] < tgt_end ? seg_offsets_host[s + 1] : tgt_end;
+    for (long long t0 = a; t0 < b; t0 += ct, ++r) {
+      rows[r].tgt_begin = t0, rows[r].tile_begin = tile0;
+      rows[r].tgt_count = (int)(b - t0 < ct ? b - t0 : ct), rows[r].pad = 0;
+      prefix[r] = units;
+      units += nt;
+    }
+    tile0 += nt;
+  }
+  prefix[n_rows] = units;
+  seg_tile[n_seg] = tile0, seg_off[n_seg] = seg_offsets_host[n_seg];
+  // the most CTAs a row is shared by, with exactly the kernel's arithmetic (streamk.cuh: sk_cta_of)
+  long long n_slots = 1;
+  if (units < grid) grid = units;  // sk_ctas
+  for (long long i = 0; i < n_rows && units > 0; ++i) {
+    const long long c0 = ((prefix[i] + 1) * grid + units - 1) / units - 1, c1 = (prefix[i + 1] * grid + units - 1) / units - 1;
+    if (c1 - c0 + 1 > n_slots) n_slots = c1 - c0 + 1;
+  }
+  unsigned long long h = fnv1a(base, bytes, 1469598103934665603ull ^ (unsigned long long)grid);
+  void* raw = nullptr;
+  const size_t before = ctx->scratch_bytes[scr];
+  int rc = ocg_scratch(ctx, scr, bytes + 64, &raw);
+  if (rc) return rc;
+  const bool reuse = before == ctx->scratch_bytes[scr] && pc.items_uploaded == bytes && pc.items_hash == h;
+  if (!reuse) {
+    // synchronous small copy: the plan changes only when the segment layout, the shard or the tile shape change
+    cudaError_t e = cudaMemcpyAsync(raw, base, bytes, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return ocg_fail(ctx, OCG_ERR_CUDA, "upload of the work plan failed: %s", cudaGetErrorString(e));
+    pc.items_uploaded = bytes;
+    pc.items_hash = h;
+  }
+  out->total_tiles = tile0, out->n_rows = (int)n_rows, out->n_slots = (int)n_slots;
+  out->d_rows = (const OcgRow*)raw;
+  out->d_prefix = (const long long*)((char*)raw + rows_bytes);
+  out->d_seg_tile = (const long long*)((char*)raw + rows_bytes + pre_bytes);
+  out->d_seg_off = out->d_seg_tile + n_seg + 1;
+  return OCG_OK;
+}
+
 extern "C" int ocg_self_gravity(ocg_ctx* ctx, const double* pos_dev, const double* mass_dev, int64_t n,
                                 const int64_t* seg_offsets_host, int32_t n_seg, double eps2, double G,
                                 int64_t tgt_begin, int64_t tgt_end, double* acc_dev, double* pot_dev,
@@ -302,45 +378,63 @@ extern "C" int ocg_self_gravity(ocg_ctx* ctx, const double* pos_dev, const doubl
   const int tpt = ocg_variant_tpt(variant);
   const int CT = ocg_variant_threads(variant) * tpt;
 
-  OcgClusterPlan plan;
   int rc;
+  float* tiles;
+  float4* tgt;
+  double* partial;
+  DirectParams p;
+  memset(&p, 0, sizeof(p));
+  p.out_stride = n;
+  p.n_tgt = n;
+  p.scale_val = scale;
+  const float e2s = guard ? 0.f : e2f * scale * scale;
+  if (ocg_variant_is_tp(variant)) {
+    // ---- target-paired kernel: stream-K rows, the row's last CTA writes the field (two launches: pack + kernel) ----
+    const long long grid = ocg_variant_slots(ctx, variant);
+    OcgClusterRows plan;
+    if ((rc = ocg_plan_cluster_rows(ctx, n, seg_offsets_host, n_seg, tgt_begin, tgt_end, CT, OCG_TS, grid, st, &plan))) return rc;
+    unsigned int* tickets;
+    rc = ocg_scratch(ctx, OCG_SCR_TILES, (size_t)plan.total_tiles * OCG_TILE_BYTES, (void**)&tiles);
+    if (!rc) rc = ocg_scratch(ctx, OCG_SCR_TGT, sizeof(float4) * (size_t)n, (void**)&tgt);
+    // always sized for the 4-component form and the largest slot count: a later call that also wants the potential
+    // (bound_center_of_mass after a captured step) must not move a buffer a CUDA graph has frozen
+    if (!rc) rc = ocg_scratch(ctx, OCG_SCR_PARTIAL, sizeof(double) * (size_t)plan.n_slots * 4 * (size_t)n, (void**)&partial);
+    if (!rc) rc = ocg_scratch(ctx, OCG_SCR_TICKETS, sizeof(unsigned int) * (size_t)(plan.n_rows > 0 ? plan.n_rows : 1), (void**)&tickets, true);
+    if (rc) return rc;
+    const long long nslots = plan.total_tiles * OCG_TS;
+    pack_cluster_kernel<<<(int)((nslots + 255) / 256), 256, 0, st>>>(pos_dev, mass_dev, n, plan.d_seg_off, plan.d_seg_tile, n_seg,
+                                                                    guard ? 0.f : e2f, scale, tiles, tgt);
+    OCG_CHECK_LAUNCH(ctx, "pack_cluster_kernel");
+    p.tiles = tiles, p.tgt = tgt, p.partial = partial;
+    p.sk.rows = plan.d_rows, p.sk.row_prefix = plan.d_prefix, p.sk.n_rows = plan.n_rows, p.sk.n_slots = plan.n_slots;
+    p.sk.n_tgt = n, p.sk.ct = CT, p.sk.nst_uniform = nullptr, p.sk.tickets = tickets;
+    p.out_acc = acc_dev, p.out_pot = pot_dev, p.out_n = n;
+    p.G = G, p.accumulate = 0, p.self_e2s = want_pot ? e2s : -1.f, p.m0_ptr = nullptr;
+    if (plan.n_rows == 0) return OCG_OK;
+    return ocg_launch_direct(ctx, p, variant, want_pot, guard, st);
+  }
+  // ---- source-paired kernels (few targets; the guarded eps2 == 0 form): (target tile x source chunk) items + finish ----
+  OcgClusterPlan plan;
   if ((rc = ocg_plan_cluster_items(ctx, n, seg_offsets_host, n_seg, tgt_begin, tgt_end, CT, OCG_TS,
                                    ocg_variant_slots(ctx, variant), st, &plan)))
     return rc;
   const long long total_tiles = plan.total_tiles, n_chunks = plan.n_chunks, n_items = plan.n_items;
-  const OcgWorkItem* d_items = plan.d_items;
-  const long long* d_seg_tile = plan.d_seg_tile;
-  const long long* d_seg_off = plan.d_seg_off;
-  float* tiles;
-  float4* tgt;
-  double* partial;
   rc = ocg_scratch(ctx, OCG_SCR_TILES, (size_t)total_tiles * OCG_TILE_BYTES, (void**)&tiles);
   if (!rc) rc = ocg_scratch(ctx, OCG_SCR_TGT, sizeof(float4) * (size_t)n, (void**)&tgt);
-  if (!rc) rc = ocg_scratch(ctx, OCG_SCR_PARTIAL, sizeof(double) * (size_t)n_chunks * NC * (size_t)n, (void**)&partial);
+  if (!rc) rc = ocg_scratch(ctx, OCG_SCR_PARTIAL, sizeof(double) * (size_t)n_chunks * 4 * (size_t)n, (void**)&partial);
   if (rc) return rc;
-
   {
     long long nslots = total_tiles * OCG_TS;
-    pack_cluster_kernel<<<(int)((nslots + 255) / 256), 256, 0, st>>>(pos_dev, mass_dev, n, d_seg_off, d_seg_tile,
+    pack_cluster_kernel<<<(int)((nslots + 255) / 256), 256, 0, st>>>(pos_dev, mass_dev, n, plan.d_seg_off, plan.d_seg_tile,
                                                                     n_seg, guard ? 0.f : e2f, scale, tiles, tgt);
     OCG_CHECK_LAUNCH(ctx, "pack_cluster_kernel");
   }
-  DirectParams p;
-  p.tiles = tiles;
-  p.tgt = tgt;
-  p.partial = partial;
-  p.out_stride = n;
-  p.items = d_items;
+  p.tiles = tiles, p.tgt = tgt, p.partial = partial;
+  p.items = plan.d_items;
   p.n_items = (int)n_items;
-  p.n_tgt = n;
-  p.n_ttiles = 0;
-  p.tiles_per_chunk = 0;
-  p.n_fast_tiles = nullptr;
-  p.scale_ptr = nullptr;
-  p.scale_val = scale;
   if ((rc = ocg_launch_direct(ctx, p, variant, want_pot, guard, st))) return rc;
-  finish_self_kernel<<<(int)((n_shard + 255) / 256), 256, 0, st>>>(partial, n, (int)n_chunks, NC, G, tgt_begin,
-                                                                  tgt_end, tgt, guard ? 0.f : e2f * scale * scale, scale, acc_dev, pot_dev);
+  finish_self_kernel<<<(int)((n_shard + 255) / 256), 256, 0, st>>>(partial, n, (int)n_chunks, NC, G, tgt_begin, tgt_end, tgt, e2s,
+                                                                  scale, acc_dev, pot_dev);
   OCG_CHECK_LAUNCH(ctx, "finish_self_kernel");
   return OCG_OK;
 }

@@ -73,6 +73,26 @@ def self_gravity_sharded(pos_local, gather_fn, acc_fn, n_total, group=None):
     return acc[:, a:b]
 
 
+def connect_comm(ctx, group=None, window_bytes=64 << 20):
+    """Set up the peer-memory exchange of include/ocg.h (ocg_comm_*) for `ctx` over the ranks of a torch.distributed
+    group: every rank allocates its window, the opaque handles are all-gathered with torch.distributed (any transport
+    would do: they are 128 plain bytes), every rank maps its peers.  Returns (rank, world).  Idempotent per ctx."""
+    import torch.distributed as dist
+    rank, world = _world(group)
+    if getattr(ctx, "comm_connected", False):
+        return rank, world
+    handle = ctx.comm_create(rank, world, window_bytes)
+    if world > 1:
+        handles = [None] * world
+        dist.all_gather_object(handles, handle, group=group)
+    else:
+        handles = [handle]
+    ctx.comm_connect(handles)
+    if world > 1:
+        dist.barrier(group=group)  # every rank has mapped every window before the first exchange kernel runs
+    return rank, world
+
+
 def allgather_particles(pos_local, n_total, group=None):
     """All-gather [3, n_local] blocks (possibly of unequal size) into [3, n_total] on every rank.
     Equal blocks (n_total divisible by the world size): ONE NCCL all-gather into a [world, 3, n_local] buffer and one

@@ -357,6 +357,102 @@ def test_bridge_cuda_graph_step_is_bit_identical(small_world, ctx):
     assert abs(t0 - t1) < 1e-12 and ft0 == ft1 and abs(t1 - nstep * dt) < 1e-12
 
 
+def _run_bridge_(field, cl, use_graph, nstep, dt, between=None):
+    from oc_nbody_b200.bridge import Bridge
+    from oc_nbody_b200.units import units
+    system = Bridge(timestep=dt | units.Myr, use_threading=False, use_cuda_graph=use_graph)
+    system.add_system(cl, (field,))
+    system.add_system(field)
+    for i in range(1, nstep + 1):
+        system.evolve_model(i * dt | units.Myr, timestep=dt | units.Myr)
+        if between is not None:
+            between(i, cl)
+    return system
+
+
+def test_bridge_cuda_graph_survives_scratch_growth_and_particle_removal(small_world, ctx):
+    """More than 4096 stars: the streaming K4 path, whose tiles / targets / partials / work plan live in ctx scratch that a
+    captured graph freezes.  Between replays the driver loop's own calls run on the same ctx — bound_center_of_mass()
+    (K4 WITH the potential: 4 partial components instead of 3) and clean_ejections() (the star count changes) — and a
+    larger foreign call grows the scratch buffers.  The graph must notice (ocg_capture_epoch) and re-capture; the
+    trajectory must equal the eager bridge's doing the same calls."""
+    import torch
+    from oc_nbody_b200.cluster import cluster_code
+    from oc_nbody_b200.synthetic import make_plummer_cluster
+    from oc_nbody_b200.units import units
+    field, _, _ = small_world
+    pos_pc, vel, mass = make_plummer_cluster(6000, seed=9)
+    center = np.array([8.0, 0.0, 0.0])
+    pos = pos_pc * 1e-3 + center[:, None]
+    pos[:, 17] += np.array([0.03, 0.0, 0.0])   # a star 30 pc out: clean_ejections removes it (and the halo beyond 10 pc)
+    dt, nstep = 0.05, 9
+    big = make_plummer_cluster(30000, seed=10)
+    big_pos, big_m = torch.from_numpy(big[0] * 1e-3 + center[:, None]).cuda(), torch.from_numpy(big[2]).cuda()
+    big_acc = torch.empty((3, 30000), dtype=torch.float64, device="cuda")
+    coms = {False: [], True: []}
+    out = {}
+    for use_graph in (False, True):
+        field.evolve_grid(center)
+        field.evolve_model(0.0 | units.Myr)
+        cl = cluster_code(mass, pos, vel, softening_pc=0.01, eject_cut=10.0, ctx=ctx)
+
+        def between(i, c, use_graph=use_graph):
+            if i in (4, 7):
+                coms[use_graph].append(c.bound_center_of_mass())
+            if i == 5:
+                c.clean_ejections()
+            if i == 6:   # a larger self-gravity call of someone else on the SAME ctx: scratch buffers are reallocated
+                c.ctx.self_gravity(big_pos, big_m, 1e-10, 4.3986004e-09, big_acc)
+        sysm = _run_bridge_(field, cl, use_graph, nstep, dt, between)
+        out[use_graph] = (cl.pos.cpu().numpy(), cl.vel.cpu().numpy(), cl.n, sysm.graph_captures, sysm.graph_replays)
+    (x0, v0, n0, c0, r0), (x1, v1, n1, c1, r1) = out[False], out[True]
+    assert n0 == n1 < 6000 and c0 == 0 and c1 >= 2 and r1 >= 3, (n0, n1, c1, r1)
+    assert np.max(np.abs(x0 - x1)) <= 1e-14 * 8.0 and np.max(np.abs(v0 - v1)) <= 1e-13 * np.max(np.abs(v0))
+    for a, b in zip(coms[False], coms[True]):
+        assert np.max(np.abs(a - b)) <= 1e-14 * 8.0
+
+
+def test_two_clusters_with_graphs_on_one_ctx(small_world, ctx):
+    """Two cluster codes stepped alternately, both captured as graphs, both on ONE shared ctx: each one's K4 uploads its own
+    work plan into the same device buffer.  A replay with the other cluster's plan resident would give wrong forces;
+    the capture epoch makes the bridge fall back to an eager step instead.  Reference: each cluster alone, eager, on a
+    ctx of its own."""
+    from oc_nbody_b200.cluster import cluster_code
+    from oc_nbody_b200.synthetic import make_plummer_cluster
+    from oc_nbody_b200.units import units
+    field, _, _ = small_world
+    center = np.array([8.0, 0.0, 0.0])
+    dt, nstep = 0.05, 6
+    sets = []
+    for n, seed in ((5000, 3), (7001, 4)):
+        p, v, m = make_plummer_cluster(n, seed=seed)
+        sets.append((m, p * 1e-3 + center[:, None], v))
+    ref = []
+    for m, x, v in sets:
+        field.evolve_grid(center)
+        field.evolve_model(0.0 | units.Myr)
+        cl = cluster_code(m, x, v, softening_pc=0.01)          # private ctx
+        assert cl.ctx is not ctx
+        _run_bridge_(field, cl, False, nstep, dt)
+        ref.append((cl.pos.cpu().numpy(), cl.vel.cpu().numpy()))
+    from oc_nbody_b200.bridge import Bridge
+    field.evolve_grid(center)
+    cls = [cluster_code(m, x, v, softening_pc=0.01, ctx=ctx) for m, x, v in sets]
+    systems = []
+    for cl in cls:
+        s = Bridge(timestep=dt | units.Myr, use_threading=False, use_cuda_graph=True)
+        s.add_system(cl, (field,))
+        s.add_system(field)
+        systems.append(s)
+    for i in range(1, nstep + 1):
+        for s in systems:
+            field.evolve_model((i - 1) * dt | units.Myr)   # both bridges share the field code: rewind it for the second
+            s.evolve_model(i * dt | units.Myr, timestep=dt | units.Myr)
+    for cl, (x, v) in zip(cls, ref):
+        assert np.max(np.abs(cl.pos.cpu().numpy() - x)) <= 1e-14 * 8.0
+        assert np.max(np.abs(cl.vel.cpu().numpy() - v)) <= 1e-13 * np.max(np.abs(v))
+
+
 def test_pykdgrav_compat_call_sites(ctx):
     """The reference's own three calls (gizmo_interface.py:561,564,566) through the drop-in module:
     tree = ConstructKDTree(r, m, soft); GetAccelParallel(grid, tree, G, theta); GetAccelParallel([centre], ...)."""

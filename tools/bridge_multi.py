@@ -26,6 +26,8 @@ def main():
     ap.add_argument("--graph", action="store_true", help="replay the sharded step (NCCL all-gathers included) as one CUDA graph")
     ap.add_argument("--integrator", default="leapfrog", choices=("leapfrog", "hermite"),
                     help="hermite: K6 (acc + jerk) target-sharded, positions AND velocities all-gathered per evaluation")
+    ap.add_argument("--exchange", default="peer", choices=("peer", "nccl"),
+                    help="peer: position gather fused into the tile pack over NVLink peer memory (ocg_self_gravity_sharded); nccl: all_gather + copy + pack")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -77,7 +79,7 @@ def main():
         run.replays = system.graph_replays
         return float(ms.item())
 
-    sh = sharded_cluster_code(mass, pos, vel, softening_pc=0.01, ctx=ctx, integrator=args.integrator)
+    sh = sharded_cluster_code(mass, pos, vel, softening_pc=0.01, ctx=ctx, integrator=args.integrator, exchange=args.exchange)
     # stage checks: the all-gather reproduces the full arrays; the first sharded force equals the unsharded one
     g_pos, g_vel = (t.cpu().numpy() for t in sh.gather_state())
     gather_ok = bool(np.array_equal(g_pos, pos) and np.array_equal(g_vel, vel))
@@ -93,9 +95,11 @@ def main():
     dx = float(np.max(np.abs(x_sh - x_1)) / np.max(np.abs(x_1 - center[:, None])))
     dv = float(np.max(np.abs(v_sh - v_1)) / np.max(np.abs(v_1)))
     ok = dx < 1e-10 and dv < 1e-10 and gather_ok and force_err < 1e-12
+    if getattr(sh, "_peer", False):
+        ctx.comm_status()
     print("rank %d: gather_ok %s force_err %.3e dx %.3e dv %.3e" % (rank, gather_ok, force_err, dx, dv), file=sys.stderr)
     if rank == 0:
-        print(json.dumps({"n_gpus": world, "n_stars": args.stars, "integrator": args.integrator, "cuda_graph": bool(args.graph), "graph_replays_last_run": getattr(run, "replays", 0), "steps": args.steps, "ms_per_bridge_step_sharded": ms_sharded,
+        print(json.dumps({"n_gpus": world, "n_stars": args.stars, "integrator": args.integrator, "exchange": "peer" if getattr(sh, "_peer", False) else "nccl", "cuda_graph": bool(args.graph), "graph_replays_last_run": getattr(run, "replays", 0), "steps": args.steps, "ms_per_bridge_step_sharded": ms_sharded,
                           "ms_per_bridge_step_single_gpu": ms_single, "max_rel_dx": dx, "max_rel_dv": dv, "match": ok,
                           "allgather_exact_rank0": gather_ok, "first_force_rel_err_rank0": force_err}))
     if world > 1:
