@@ -86,6 +86,22 @@ int ocg_recentre_f64(ocg_ctx* ctx, const double* pos_dev, const double* mass_dev
 /* out[i] = (float)in[i] */
 int ocg_cast_f64_f32(ocg_ctx* ctx, const double* in_dev, int64_t n, float* out_dev, void* stream);
 
+/* ---- K0b: source assembly on the device (gizmo_interface.py:297-304, 515-558) ----
+ * One species per call.  From the species' raw snapshot arrays — pos_dev fp64 [n][3] ('host.distance.principal'),
+ * mass_dev fp64 [n], id_dev int64 [n] or NULL, hsml_dev fp64 [n] ('smooth.length', pc; gas only) — keep the particles with
+ * id != exclude_id (the tracked star, :515) and |pos| < rmax (_clean_Rmag_, :297-304; rmax <= 0: no cut), give each its
+ * softening length in kpc by the reference's rule times soft_scale (1, or the Plummer-equivalent factor), recentre on
+ * `center` in fp64, round to fp32, and write the records at out_xyzm_dev[out_offset + j], out_soft_dev[out_offset + j] in
+ * the particles' own order: three calls with running offsets (star, dark, gas) produce the concatenation of :518-549.
+ * n_kept_host (HOST) receives the number kept; the call synchronises `stream`.                                      */
+#define OCG_SOFT_CONSTANT 0        /* soft = soft_param [kpc]                    (star/dark_softening_in_pc / 1000, :536-545) */
+#define OCG_SOFT_MASS_CUBE_ROOT 1  /* soft = (m / soft_param)^(1/3) / 1000       (star/dark_char_mass, :531-534, :540-543)     */
+#define OCG_SOFT_GAS_SMOOTHING 2   /* soft = 2.8 * hsml / 1000                   (gas, :547)                                   */
+int ocg_assemble_sources(ocg_ctx* ctx, const double* pos_dev, const double* mass_dev, const int64_t* id_dev,
+                         const double* hsml_dev, int64_t n, int64_t exclude_id, double rmax, int32_t soft_rule,
+                         double soft_param, double soft_scale, const double center[3], float* out_xyzm_dev,
+                         float* out_soft_dev, int64_t out_offset, int64_t* n_kept_host, void* stream);
+
 /* ---- K1: field build, softened direct sum ---------------------------------------------------
  * Replaces ConstructKDTree + GetAccelParallel (gizmo_interface.py:561,564,566) in the theta->0
  * limit:  acc[c][t] (+)= G * sum_s m_s K(|x_s-x_t|, soft_s) (x_s-x_t)[c]

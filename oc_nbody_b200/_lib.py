@@ -20,7 +20,7 @@ KERNELS = {"plummer": KERNEL_PLUMMER, "spline": KERNEL_SPLINE}
 # every symbol include/ocg.h declares (tests check the library exports them all)
 ABI_SYMBOLS = [
     "ocg_version", "ocg_create", "ocg_destroy", "ocg_last_error", "ocg_device_info", "ocg_launch_count", "ocg_capture_epoch",
-    "ocg_last_direct_kernel_ms", "ocg_set_kernel_timing", "ocg_last_direct_traffic_bytes", "ocg_recentre_f64", "ocg_cast_f64_f32",
+    "ocg_last_direct_kernel_ms", "ocg_set_kernel_timing", "ocg_last_direct_traffic_bytes", "ocg_recentre_f64", "ocg_cast_f64_f32", "ocg_assemble_sources",
     "ocg_field_direct", "ocg_frame_subtract", "ocg_field_build_host", "ocg_pack_planes", "ocg_grid_time_blend",
     "ocg_grid_interp", "ocg_grid_interp_multi", "ocg_grid_interp_nested", "ocg_pack_planes_indexed", "ocg_set_interp_weight_slots", "ocg_grid_interp_slot", "ocg_grid_interp_rbf", "ocg_self_gravity", "ocg_self_gravity_hermite", "ocg_hermite_predict", "ocg_hermite_correct", "ocg_bound_com", "ocg_eject_mask", "ocg_compact_rows", "ocg_kick", "ocg_drift", "ocg_axpy", "ocg_probe_throughput", "ocg_comm_create", "ocg_comm_connect", "ocg_comm_destroy", "ocg_comm_info", "ocg_comm_status", "ocg_comm_allreduce_f64", "ocg_self_gravity_sharded",
 ]
@@ -73,6 +73,8 @@ def load_library():
     L.ocg_last_direct_traffic_bytes.argtypes = [vp]
     L.ocg_recentre_f64.argtypes = [vp, vp, vp, i64, ctypes.POINTER(dbl), vp, vp]
     L.ocg_cast_f64_f32.argtypes = [vp, vp, i64, vp, vp]
+    L.ocg_assemble_sources.argtypes = [vp, vp, vp, vp, vp, i64, i64, dbl, i32, dbl, dbl, ctypes.POINTER(dbl), vp, vp, i64,
+                                       ctypes.POINTER(i64), vp]
     L.ocg_field_direct.argtypes = [vp, vp, vp, i64, vp, i64, ctypes.c_int, dbl, vp, vp, ctypes.c_int, vp]
     L.ocg_frame_subtract.argtypes = [vp, vp, i64, i64, vp]
     L.ocg_field_build_host.argtypes = [vp, vp, vp, vp, i64, vp, i64, ctypes.POINTER(dbl), i64, ctypes.c_int, dbl, vp, vp]
@@ -215,6 +217,18 @@ class Context:
 
     def cast_f64_f32(self, src, out):
         self._ck(self.lib.ocg_cast_f64_f32(self.h, _dptr(src), src.numel(), _dptr(out), self._stream()), "ocg_cast_f64_f32")
+
+    SOFT_RULES = {"constant": 0, "mass_cube_root": 1, "gas_smoothing": 2}
+
+    def assemble_sources(self, pos, mass, ids, hsml, exclude_id, rmax, rule, soft_param, soft_scale, center, out_xyzm, out_soft,
+                         out_offset=0):
+        """One species of the source assembly on the device (ocg_assemble_sources); returns the number of particles kept."""
+        kept = ctypes.c_int64(0)
+        self._ck(self.lib.ocg_assemble_sources(self.h, _dptr(pos), _dptr(mass), _dptr(ids), _dptr(hsml), pos.shape[0],
+                                               int(exclude_id), float(rmax), self.SOFT_RULES[rule], float(soft_param),
+                                               float(soft_scale), _vec3(center), _dptr(out_xyzm), _dptr(out_soft), int(out_offset),
+                                               ctypes.byref(kept), self._stream()), "ocg_assemble_sources")
+        return int(kept.value)
 
     def field_direct(self, src_xyzm, src_soft, tgt_xyzw, kernel, G, acc, pot=None, accumulate=False):
         n_src, n_tgt = src_xyzm.shape[0], tgt_xyzw.shape[0]

@@ -26,6 +26,7 @@ SOURCES = [
     ("rbf_interp", "rbf_interp.cu", []),
     ("cluster_ops", "cluster_ops.cu", []),
     ("comm", "comm.cu", []),
+    ("assemble", "assemble.cu", []),
 ]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

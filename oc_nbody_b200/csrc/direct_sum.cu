@@ -32,7 +32,7 @@
 // target box, or a source whose r^6 could leave the FP32 range for some target — or (b) accuracy
 // profits from it — it lies within the "precision radius" D of the target box, where single pair terms
 // are large compared with the net field and FP32 rounding of them would dominate the error budget.
-// D is the largest of 0.5, 0.35, 0.25, ... x (box extent) for which the NEAR set stays below a small cap
+// D is the largest of 4, 2.8, 2, 1.4, ... x (box extent) for which the NEAR set stays below a small cap
 // (so the FP64 work is <~1% of the total); it is chosen on the device from a distance histogram.
 //
 // All distances here are in SCALED units: lengths x scale, scale = 2^k with the largest extent of the
@@ -40,7 +40,7 @@
 //   [0..5]  target bbox as ordered ints: min xyz, max xyz (unscaled)
 //   [8] n_fast  [9] n_near  [10] n_fast_tiles  [11] scale (float bits)  [12] D^2 scaled (float bits)
 //   [13] M0 (float bits): power of two >= the largest source mass (mass-folded tiles, see tile_tpair MF)
-//   [16..31] histogram: hist[b] = #sources with scaled box distance < 0.5 * 2^(-b/2)
+//   [16..31] histogram: hist[b] = #sources with scaled box distance < 4 * 2^(-b/2)
 #define MISC_BBOX 0
 #define MISC_NFAST 8
 #define MISC_NNEAR 9
@@ -168,8 +168,8 @@ __global__ void __launch_bounds__(CLS_BLOCK) classify_hist_kernel(
     if (S.w > 0.f && isfinite(S.w)) mbits = __float_as_int(S.w);
     float d2 = box_dist2_scaled(S.x, S.y, S.z, misc, sc);
     if (!source_must_be_near(d2, (soft ? soft[i] : 0.f) * sc, kernel)) {
-      // every b with d < 0.5 * 2^(-b/2)  <=>  d2 < 0.25 * 2^-b
-      float lim = 0.25f;
+      // every b with d < 4 * 2^(-b/2)  <=>  d2 < 16 * 2^-b
+      float lim = 16.0f;
       for (int b = 0; b < MISC_NBINS && d2 < lim; ++b, lim *= 0.5f) atomicAdd(&h[b], 1);
     }
   }
@@ -182,7 +182,7 @@ __global__ void __launch_bounds__(CLS_BLOCK) classify_hist_kernel(
 
 // precise == 0: no precision radius (criterion (a) only).  Rounds M0 up to a power of two.
 __global__ void choose_radius_kernel(int* misc, int cap, int precise) {
-  float d2 = 0.f, lim = 0.25f;
+  float d2 = 0.f, lim = 16.0f;
   for (int b = 0; precise && b < MISC_NBINS; ++b, lim *= 0.5f)
     if (misc[MISC_HIST + b] <= cap) {
       d2 = lim;
@@ -609,6 +609,7 @@ static const DirectVariant g_variants[] = {
     /* 77 */ {"tpair-mf(+pot) np1 regacc minb2 unr2 swizzled fold32", 2, 2, false, OCG_TPMFP(1, false, 2, 2, OCG_CONSUMER_WARPS, 32), 0, 0, 2},  // production: MID_MF
     /* 78 */ {"tpair-mf(+pot) np1 regacc minb2 unr2 swizzled fold512", 2, 2, false, TUNE(OCG_TPMFP(1, false, 2, 2, OCG_CONSUMER_WARPS, 512)), 0, 0, 2},
     /* 79 */ {"tpair-mf(+pot) np1 regacc minb2 unr2 swizzled fold64", 2, 2, false, TUNE(OCG_TPMFP(1, false, 2, 2, OCG_CONSUMER_WARPS, 64)), 0, 0, 2},
+    /* 80 */ {"tpair-mf(+pot) np1 regacc minb2 unr2 swizzled fold16", 2, 2, false, TUNE(OCG_TPMFP(1, false, 2, 2, OCG_CONSUMER_WARPS, 16)), 0, 0, 2},
 };
 static const int g_n_variants = (int)(sizeof(g_variants) / sizeof(g_variants[0]));
 // Production choices (tools/probe.py sweeps on B200, profiles/r01_variant_sweep*.json, profiles/r02_fold_sweep.json):
@@ -652,6 +653,10 @@ int ocg_pick_variant(ocg_ctx* ctx, int64_t n_tgt, int64_t seg_len, bool guard, b
     return (n_tgt + ct - 1) / ct * src_tiles >= 4ll * ctx->sm_count * g_variants[v].minb;
   };
   if (guard) return (n_tgt >= 16384 && waste_ok(OCG_VARIANT_MID_GUARD)) ? OCG_VARIANT_MID_GUARD : OCG_VARIANT_SMALL;
+  // K4 (fine_tiles): clusters of >= 2048 stars always take the 512-target stream-K shape — stream-K balances any number of
+  // rows, and a target shard (ocg_self_gravity_sharded, or tgt_begin/tgt_end) must run the same kernel as the unsharded call
+  // so that an N-GPU trajectory reproduces the 1-GPU one bit for bit
+  if (fine_tiles) return (seg_len >= 2048 || waste_ok(OCG_VARIANT_MID)) ? OCG_VARIANT_MID : OCG_VARIANT_SMALL;
   // fine_tiles (K4): a cluster has few target tiles, so the 512-target kernel balances better over the SMs than the
   // 3072-target one although its inner loop is ~1 point slower (tools/probe_k4.py: 65.0 vs 63.0 % at N = 65 536,
   // 64.8 vs 57.4 % at 16 x 16 384)

@@ -41,6 +41,10 @@ _DEFAULTS = dict(
     # per-snapshot field caches in the reference's own file names and format (gizmo_interface.py:373-391,454-459,
     # 470-495): None = no caching.  The remaining keys only enter the cache file name.
     cache_directory=None, sim_name="synthetic", grid_seed=1776, Rmax=50.0, startnum=None, endnum=None, num_prior=0,
+    # source assembly (gizmo_interface.py:515-558): "device" = ocg_assemble_sources, the raw species arrays are uploaded once
+    # and cut / softened / concatenated / recentred / rounded on the GPU; "host" = numpy + ocg_field_build_host.
+    # clean_Rmax=True applies the reference's ingestion-time cut |pos| < Rmax (_clean_Rmag_, :297-304) during assembly.
+    source_assembly="device", clean_Rmax=False,
 )
 
 
@@ -156,13 +160,60 @@ class gizmo_field(object):
     def _populate_grid_acceleration_(self, snap, grid, want_pot=False):
         """One snapshot's field on the (shifted) grid, frame acceleration removed
         (gizmo_interface.py:512-573). Returns acc_x, acc_y, acc_z (, pot) as FP64 [Ngrid+1]."""
-        r, m, soft = self._source_arrays_(snap)
-        out = self.ctx.field_build_host(r, m, soft, grid.evolved_grid, grid.ss_evolved_position, grid.origin_row,
-                                        _lib.KERNELS[self.softening_kernel], self.G, want_pot=want_pot)
-        acc, pot = out if want_pot else (out, None)
+        if self.source_assembly == "device":
+            acc, pot = self._populate_device_(snap, grid, want_pot)
+        else:
+            if self.clean_Rmax:
+                raise ValueError("clean_Rmax needs source_assembly='device' (or call clean_Rmag(snap, Rmax) at ingestion)")
+            r, m, soft = self._source_arrays_(snap)
+            out = self.ctx.field_build_host(r, m, soft, grid.evolved_grid, grid.ss_evolved_position, grid.origin_row,
+                                            _lib.KERNELS[self.softening_kernel], self.G, want_pot=want_pot)
+            acc, pot = out if want_pot else (out, None)
         if want_pot:
             return acc[0], acc[1], acc[2], pot
         return acc[0], acc[1], acc[2]
+
+    def _species_rules_(self):
+        """(species, softening rule, parameter) in the reference's concatenation order (gizmo_interface.py:518-549)."""
+        star = (("mass_cube_root", float(self.star_char_mass)) if self.star_char_mass is not None
+                else ("constant", float(self.star_softening_in_pc) / 1000.0))
+        dark = (("mass_cube_root", float(self.dark_char_mass)) if self.dark_char_mass is not None
+                else ("constant", float(self.dark_softening_in_pc) / 1000.0))
+        return (("star",) + star, ("dark",) + dark, ("gas", "gas_smoothing", 0.0))
+
+    def _assemble_device_(self, snap, center):
+        """Source records on the device: FP32 (x, y, z, m) recentred on `center` + softening, star | dark | gas
+        (ocg_assemble_sources: tracked star dropped, optional Rmax cut, per-species softening).  Returns (xyzm, soft)."""
+        import torch
+        dev = torch.device("cuda", self.ctx.device)
+        n_max = sum(len(snap[sp]["mass"]) for sp in ("star", "dark", "gas"))
+        xyzm = torch.empty((n_max, 4), dtype=torch.float32, device=dev)
+        soft = torch.empty(n_max, dtype=torch.float32, device=dev)
+        scale = float(self.plummer_eps_over_h) if self.softening_kernel == "plummer" else 1.0
+        up = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a, dtype=dt)).to(dev)  # noqa: E731
+        off = 0
+        for sp, rule, param in self._species_rules_():
+            part = snap[sp]
+            ids = up(part["id"], np.int64) if sp == "star" else None
+            hsml = up(part["smooth.length"], np.float64) if sp == "gas" else None
+            off += self.ctx.assemble_sources(up(part.prop("host.distance.principal"), np.float64), up(part["mass"], np.float64), ids,
+                                             hsml, self.chosen_id, float(self.Rmax) if self.clean_Rmax else 0.0, rule, param, scale,
+                                             center, xyzm, soft, off)
+        return xyzm[:off], soft[:off]
+
+    def _populate_device_(self, snap, grid, want_pot):
+        import torch
+        dev = torch.device("cuda", self.ctx.device)
+        center = np.asarray(grid.ss_evolved_position, np.float64)
+        xyzm, soft = self._assemble_device_(snap, center)
+        n_tgt = len(grid)
+        tgt = torch.empty((n_tgt, 4), dtype=torch.float32, device=dev)
+        self.ctx.recentre_f64(torch.from_numpy(np.ascontiguousarray(grid.evolved_grid, dtype=np.float64)).to(dev), None, center, tgt)
+        acc = torch.empty((3, n_tgt), dtype=torch.float64, device=dev)
+        pot = torch.empty(n_tgt, dtype=torch.float64, device=dev) if want_pot else None
+        self.ctx.field_direct(xyzm, soft, tgt, _lib.KERNELS[self.softening_kernel], self.G, acc, pot)
+        self.ctx.frame_subtract(acc, grid.origin_row)
+        return acc.cpu().numpy(), (pot.cpu().numpy() if want_pot else None)
 
     def _make_grid_(self):
         """grid(...) [+ add_fine_grid(...)] exactly as gizmo_interface.py:412-419."""
@@ -231,16 +282,33 @@ class gizmo_field(object):
                 pickle.dump(np.asarray(a, np.float64), fh, protocol=4)
 
     def _init_grid_(self):
-        """Per-snapshot grid loop (gizmo_interface.py:393-510): load the snapshot's cached field or build it on the
-        GPU and write the cache in the reference's format.  (The reference's whole-``grid`` pickle, :395-398/:510, is
-        a pickle of ITS class and is not produced; the per-snapshot arrays are the expensive part.)"""
+        """Per-snapshot grid loop (gizmo_interface.py:393-510): the whole-grid cache first (:395-398), else per snapshot load
+        the cached field or build it on the GPU; both caches are written in the reference's own formats (cache_compat)."""
+        from . import cache_compat
         self.grid = self._make_grid_()
         if self.startnum is None:
             self.startnum = self.snapshots[0].snapshot["index"]
         if self.endnum is None:
             self.endnum = self.snapshots[-1].snapshot["index"]
-        ax, ay, az, ph = [], [], [], []
         self.cache_hits = 0
+        self.grid_cache_hit = False
+        grid_cache_file = self._grid_cache_name_()[1] if self.cache_directory is not None else None
+        if grid_cache_file is not None:
+            try:
+                cached = cache_compat.load_grid_pickle(grid_cache_file)
+                shape = (len(self.snapshots), len(self.grid))
+                pot_ok = (not self.with_potential) or (cached.snapshot_potential is not None and cached.snapshot_potential.shape == shape)
+                if np.array_equal(cached.init_grid, self.grid.init_grid) and cached.snapshot_acceleration_x.shape == shape and pot_ok:
+                    for k in ("snapshot_acceleration_x", "snapshot_acceleration_y", "snapshot_acceleration_z"):
+                        setattr(self.grid, k, getattr(cached, k))
+                    self.grid.snapshot_potential = cached.snapshot_potential if self.with_potential else None
+                    self.grid.gen_evolved_grid(self._origin)
+                    self.grid_cache_hit = True
+                    self._upload_planes_()
+                    return
+            except (OSError, ValueError, AttributeError, EOFError, ImportError, IndexError, KeyError, TypeError):
+                pass  # "couldnt find cached grid" (gizmo_interface.py:399-400): build it
+        ax, ay, az, ph = [], [], [], []
         for i, snap in enumerate(self.snapshots):
             self.grid.gen_evolved_grid(self.chosen_snapshot_positions[i])
             res = self._load_snapshot_cache_(snap.snapshot["index"], len(self.grid), self.with_potential)
@@ -257,6 +325,8 @@ class gizmo_field(object):
         self.grid.snapshot_acceleration_z = np.array(az)
         self.grid.snapshot_potential = np.array(ph) if self.with_potential else None
         self.grid.gen_evolved_grid(self._origin)
+        if grid_cache_file is not None:
+            cache_compat.dump_grid_pickle(self.grid, grid_cache_file)   # gizmo_interface.py:510
         self._upload_planes_()
 
     def set_snapshot_fields(self, acc_x, acc_y, acc_z, pot=None):

@@ -40,6 +40,27 @@ def main():
     out["n_cases"] = np.array(len(cases))
     np.savez_compressed(os.path.join(HERE, "grid_reference.npz"), **out)
 
+    # the reference's whole-grid cache (gizmo_interface.py:510: pickle.dump(self.grid, ..., protocol=4)) as its own class
+    # writes it: the real class registered under its real module path, a nested grid with stacked fields of 3 snapshots
+    import pickle
+    import sys
+    import types
+    spec2 = importlib.util.spec_from_file_location("oceanic.grid_cartesian", REF)
+    mod = importlib.util.module_from_spec(spec2)
+    spec2.loader.exec_module(mod)
+    pkg = types.ModuleType("oceanic")
+    pkg.grid_cartesian = mod
+    sys.modules["oceanic"], sys.modules["oceanic.grid_cartesian"] = pkg, mod
+    g = mod.grid(0.06, 0.06, 0.06, 0.012)
+    g.add_fine_grid(0.02, 0.02, 0.02, 0.005)
+    g.gen_evolved_grid(np.array([8.0, -0.25, 0.125]))
+    rng = np.random.default_rng(1776)
+    for c in "xyz":
+        setattr(g, "snapshot_acceleration_" + c, rng.normal(0.0, 1e-2, (3, len(g.init_grid))))
+    with open(os.path.join(HERE, "grid_cache_reference.pickle"), "wb") as fh:
+        pickle.dump(g, fh, protocol=4)
+    del sys.modules["oceanic"], sys.modules["oceanic.grid_cartesian"]
+
     # nested fine grid (grid.add_fine_grid, grid_cartesian.py:34-53,71-91): coarse args, fine args
     nested = [((0.6, 0.6, 0.6, 0.05), (0.1, 0.1, 0.1, 0.01)), ((0.6, 0.3, 0.45, 0.03), (0.2, 0.1, 0.12, 0.013)),
               ((0.6, 0.6, 0.6, 0.02), (0.02, 0.02, 0.02, 0.0021)), ((0.6, 0.6, 0.6, 0.6 / 16), (0.25, 0.25, 0.25, 0.25 / 9))]

@@ -256,3 +256,81 @@ def test_clean_Rmag_follows_the_reference_rule():
         assert len(snap[k]["id"]) == keep.sum()
     assert len(snap["gas"]["smooth.length"]) == len(snap["gas"]["mass"]) < n_gas_before
     assert snap.snapshot["index"] == 577
+
+
+def test_whole_grid_pickle_written_by_the_reference_loads(tmp_path):
+    """gizmo_interface.py:395-398,510: the whole-grid cache is a pickle of the reference's own class.  The committed fixture
+    was written by the REAL class (tests/golden/make_golden.py); it loads into our grid with the lattice bookkeeping
+    re-derived, and what we write back is the same pickle stream apart from our extra attributes."""
+    import pickle
+    import pickletools
+    from oc_nbody_b200 import cache_compat
+    path = os.path.join(ROOT, "tests", "golden", "grid_cache_reference.pickle")
+    g = cache_compat.load_grid_pickle(path)
+    assert type(g).__module__ == "oc_nbody_b200.grid_cartesian"
+    assert g.has_fine_grid and g.coarse_shape == (5, 5, 5) and g.fine_shape == (4, 4, 4)
+    assert g.snapshot_acceleration_x.shape == (3, len(g)) and g.snapshot_potential is None
+    assert np.array_equal(g.evolved_grid, g.init_grid + np.array([8.0, -0.25, 0.125]))
+    rng = np.random.default_rng(1776)
+    assert np.array_equal(g.snapshot_acceleration_x, rng.normal(0.0, 1e-2, (3, len(g))))
+    # write it back in the reference's format: the class global is the reference's module path, every attribute the
+    # reference's own pickle holds is there with equal values, and nothing of our bookkeeping leaks into it
+    out = tmp_path / "grid_rewritten"
+    cache_compat.dump_grid_pickle(g, str(out))
+    ops = [(op.name, arg) for op, arg, _ in pickletools.genops(out.read_bytes())]
+    assert ("GLOBAL", "oceanic.grid_cartesian grid") in ops
+    assert not any(op in ("GLOBAL", "STACK_GLOBAL") and arg and "oc_nbody_b200" in str(arg) for op, arg in ops)
+
+    class _Probe(pickle.Unpickler):  # read both streams as plain attribute dicts, whatever the class
+        def find_class(self, module, name):
+            if name == "grid":
+                return type("grid", (), {})
+            return super().find_class(module, name)
+    ref_state = _Probe(open(path, "rb")).load().__dict__
+    our_state = _Probe(open(str(out), "rb")).load().__dict__
+    assert set(ref_state) <= set(our_state) | {"x_n", "y_n", "z_n"}
+    for k, v in ref_state.items():
+        if k in our_state:
+            assert np.array_equal(np.asarray(v), np.asarray(our_state[k])), k
+    assert not set(our_state) & {"coarse_shape", "fine_shape", "coarse_keep_index", "coarse_hole_index", "fine_row0"}
+    # and our own file reads back
+    back = cache_compat.load_grid_pickle(str(out))
+    assert np.array_equal(back.snapshot_acceleration_z, g.snapshot_acceleration_z) and back.fine_row0 == g.fine_row0
+    # a pickle whose point list is not what its sizes generate is refused
+    bad = pickle.loads(pickle.dumps(back))
+    bad.init_grid = bad.init_grid + 1e-9
+    with open(str(tmp_path / "bad"), "wb") as fh:
+        pickle.dump(bad, fh, protocol=4)
+    with pytest.raises(ValueError, match="point list"):
+        cache_compat.load_grid_pickle(str(tmp_path / "bad"))
+
+
+def test_whole_grid_pickle_is_read_by_the_real_reference_class(tmp_path):
+    """Where the reference is present (the build container): its own plain pickle.load on our file yields ITS class."""
+    ref = "/root/reference/grid_cartesian.py"
+    if not os.path.exists(ref):
+        pytest.skip("/root/reference is not on this box")
+    import importlib.util
+    import pickle
+    import sys
+    import types
+    from oc_nbody_b200 import cache_compat
+    from oc_nbody_b200.grid_cartesian import grid
+    g = grid(0.06, 0.06, 0.06, 0.012)
+    g.gen_evolved_grid(np.array([8.0, 0.0, 0.0]))
+    g.snapshot_acceleration_x = g.snapshot_acceleration_y = g.snapshot_acceleration_z = np.ones((2, len(g)))
+    cache_compat.dump_grid_pickle(g, str(tmp_path / "grid_x"))
+    spec = importlib.util.spec_from_file_location("oceanic.grid_cartesian", ref)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    pkg = types.ModuleType("oceanic")
+    pkg.grid_cartesian = mod
+    sys.modules["oceanic"], sys.modules["oceanic.grid_cartesian"] = pkg, mod
+    try:
+        with open(str(tmp_path / "grid_x"), "rb") as fh:
+            r = pickle.load(fh)
+        assert type(r) is mod.grid and np.array_equal(r.init_grid, g.init_grid)
+        r.gen_evolved_grid(np.array([1.0, 2.0, 3.0]))   # the reference's own method works on the loaded object
+        assert np.array_equal(r.evolved_grid, g.init_grid + np.array([1.0, 2.0, 3.0]))
+    finally:
+        del sys.modules["oceanic"], sys.modules["oceanic.grid_cartesian"]

@@ -1,5 +1,7 @@
 """GPU integration: the plugin classes (field code, cluster code, Bridge) against the oracle pipeline.
 Config 1 of BASELINE.json in miniature: 1k-star Plummer cluster BRIDGE-kicked by a 16^3 grid field."""
+import os
+
 import numpy as np
 import pytest
 
@@ -451,6 +453,79 @@ def test_two_clusters_with_graphs_on_one_ctx(small_world, ctx):
     for cl, (x, v) in zip(cls, ref):
         assert np.max(np.abs(cl.pos.cpu().numpy() - x)) <= 1e-14 * 8.0
         assert np.max(np.abs(cl.vel.cpu().numpy() - v)) <= 1e-13 * np.max(np.abs(v))
+
+
+@pytest.mark.parametrize("opts", [dict(), dict(star_char_mass=7100.0, dark_char_mass=35000.0, softening_kernel="plummer"),
+                                  dict(clean_Rmax=True, Rmax=9.0)])
+def test_device_source_assembly_matches_the_host_rules(ctx, opts):
+    """ocg_assemble_sources (tracked star dropped, Rmax cut, per-species softening, star|dark|gas concatenation, FP64
+    recentring + FP32 rounding) against the host restatement of gizmo_interface.py:297-304,515-558 — records equal bit for
+    bit (the cube-root rule to 1 FP32 ulp: device pow vs numpy power) — and the field built from them equal to the
+    host-assembled build."""
+    from oc_nbody_b200.gizmo_field import clean_Rmag, gizmo_field
+    from oc_nbody_b200.synthetic import make_snapshot
+    snap = make_snapshot(30000, seed=5)
+    center = np.array([8.0, 0.0, 0.0])
+    base = dict(grid_x_size_in_kpc=0.06, grid_y_size_in_kpc=0.06, grid_z_size_in_kpc=0.06, grid_resolution=0.06 / 6)
+    base.update(opts)
+    chosen = int(snap["star"]["id"][123])
+    f_dev = gizmo_field(dict(base, source_assembly="device"), [snap], chosen_positions=center[None], chosen_id=chosen, ctx=ctx)
+    host_snap = make_snapshot(30000, seed=5)
+    if opts.get("clean_Rmax"):
+        n_before = sum(len(host_snap[k]["mass"]) for k in ("star", "dark", "gas"))
+        clean_Rmag(host_snap, 9.0)   # what the reference does at ingestion (gizmo_interface.py:254-255,297-304)
+        assert sum(len(host_snap[k]["mass"]) for k in ("star", "dark", "gas")) < n_before
+    f_host = gizmo_field(dict(base, source_assembly="host", clean_Rmax=False), [host_snap], chosen_positions=center[None],
+                         chosen_id=chosen, ctx=ctx)
+    r, m, soft = f_host._source_arrays_(host_snap)
+    want = oracle.recentre(r, m, center)
+    xyzm, dsoft = f_dev._assemble_device_(snap, center)
+    got, gsoft = xyzm.cpu().numpy(), dsoft.cpu().numpy()
+    assert got.shape == want.shape and np.array_equal(got, want)
+    if "star_char_mass" in opts:
+        assert np.max(np.abs(gsoft - soft.astype(np.float32)) / soft) <= 1.2e-7
+    else:
+        assert np.array_equal(gsoft, soft.astype(np.float32))
+    gd, gh = f_dev.grid, f_host.grid
+    for a, b in ((gd.snapshot_acceleration_x, gh.snapshot_acceleration_x), (gd.snapshot_acceleration_z, gh.snapshot_acceleration_z),
+                 (gd.snapshot_potential, gh.snapshot_potential)):
+        assert np.max(np.abs(a - b)) <= 1e-6 * np.max(np.abs(b)) if "star_char_mass" in opts else np.array_equal(a, b)
+
+
+def test_whole_grid_cache_and_interface_dump_round_trip(ctx, tmp_path):
+    """gizmo_interface.py:395-398,510 and oceanic_io.py:72-145: a second field code on the same cache directory loads the
+    whole-grid pickle (no GPU build), and dump_interface / load_interface reproduce the kick bit for bit."""
+    from oc_nbody_b200 import cache_compat
+    from oc_nbody_b200.gizmo_field import gizmo_field
+    from oc_nbody_b200.synthetic import advance_snapshot, make_snapshot
+    from oc_nbody_b200.units import units
+    snaps = [make_snapshot(20000, seed=1776)]
+    snaps.append(advance_snapshot(snaps[0], 23.0))
+    center = np.array([8.0, 0.0, 0.0])
+    opts = dict(grid_x_size_in_kpc=0.06, grid_y_size_in_kpc=0.06, grid_z_size_in_kpc=0.06, grid_resolution=0.06 / 6,
+                cache_directory=str(tmp_path / "cache"))
+    a = gizmo_field(opts, snaps, chosen_positions=np.tile(center, (2, 1)), ctx=ctx)
+    assert not a.grid_cache_hit and os.path.exists(a._grid_cache_name_()[1])
+    launches = ctx.launch_count()
+    b = gizmo_field(opts, snaps, chosen_positions=np.tile(center, (2, 1)), ctx=ctx)
+    assert b.grid_cache_hit and np.array_equal(b.grid.snapshot_acceleration_y, a.grid.snapshot_acceleration_y)
+    assert np.array_equal(b.grid.snapshot_potential, a.grid.snapshot_potential)
+    # only the plane upload ran on the GPU: no classify / direct-sum launches
+    assert ctx.launch_count() - launches < 10
+    a.output_directory = str(tmp_path)
+    a.evolve_grid(center)
+    out = cache_compat.dump_interface(a, "interface")
+    assert sorted(os.listdir(out)) == sorted(["evolved_grid", "init_grid", "interface", "grid_accx_interpolators",
+                                              "grid_accy_interpolators", "grid_accz_interpolators", "snapshot_acceleration_x.npz",
+                                              "snapshot_acceleration_y.npz", "snapshot_acceleration_z.npz", "snapshot_potential.npz"])
+    c = cache_compat.load_interface(out, ctx=ctx)
+    x = center[:, None] + np.random.default_rng(2).normal(0, 0.01, (3, 200))
+    for t in (0.0, 7.5):
+        a.evolve_model(t | units.Myr), c.evolve_model(t | units.Myr)
+        ga = a.get_gravity_at_point(0 | units.kpc, x[0] | units.kpc, x[1] | units.kpc, x[2] | units.kpc)
+        gc = c.get_gravity_at_point(0 | units.kpc, x[0] | units.kpc, x[1] | units.kpc, x[2] | units.kpc)
+        for u, v in zip(ga, gc):
+            assert np.array_equal(u.value_in(units.kms / units.Myr), v.value_in(units.kms / units.Myr))
 
 
 def test_pykdgrav_compat_call_sites(ctx):

@@ -35,10 +35,10 @@ def main():
     keep = np.arange(len(g)) != g.origin_row
     d_src, d_soft, d_tgt = (torch.from_numpy(np.ascontiguousarray(a)).cuda() for a in (s32, soft.astype(np.float32), t32))
     out = []
-    for variant in (77, 79, 78):
+    for variant in (80, 77, 79):
         if not ctx.variant_built(variant):
             continue
-        for cap in (4096, 16384, 65536, 262144):
+        for cap in (16384, 65536, 262144):
             ctx.debug_set("direct_variant", variant)
             ctx.debug_set("near_cap", cap)
             acc = torch.empty((3, len(g)), dtype=torch.float64, device="cuda")
