@@ -320,6 +320,20 @@ int ocg_hermite_correct(ocg_ctx* ctx, double* pos_dev, double* vel_dev, double* 
                         const double* jerk1_dev, int64_t n, double dt, double vel_to_len, double eta,
                         double* dt_min_dev, void* stream);
 
+/* ph4's individual BLOCK TIME STEPS (AMUSE ph4 behind oc_code.py:218-229; options.py:248-253): advance one cluster by
+ * `span` with every star on its own power-of-two step span / 2^k, k <= max_level (<= 20), chosen from the Aarseth criterion
+ * with accuracy parameter eta (start-up: eta |a| / |j|).  Per block step: t_next = min (t_i + dt_i); every star is predicted
+ * to t_next; acceleration and jerk of the ACTIVE stars (those that reach t_next) from ALL predicted stars (K6 over active
+ * targets x all sources); the active stars are corrected over their own step and pick their next one (halved as often as the
+ * criterion demands, doubled at most once, and only onto a commensurate time).  All stars arrive at t + span together.
+ * pos_dev, vel_dev fp64 [3][n] are advanced in place; acc_dev, jerk_dev fp64 [3][n] receive each star's end-of-step force
+ * (evaluated at the predicted end state, as the corrector uses it).
+ * The call synchronises `stream` once per block step (16 bytes come back to size the next launches).  Host counters
+ * (nullable): block steps taken, star-steps taken (sum of the active counts; a shared step would take n * 2^k_max).     */
+int ocg_hermite_block_evolve(ocg_ctx* ctx, double* pos_dev, double* vel_dev, const double* mass_dev, double* acc_dev,
+                             double* jerk_dev, int64_t n, double eps2, double G, double vel_to_len, double span, double eta,
+                             int32_t max_level, int64_t* n_block_steps_host, int64_t* n_star_steps_host, void* stream);
+
 /* ---- K5: BRIDGE kick / drift (amuse.couple.bridge kick + leapfrog drift, oc_nbody.py:56) ----
  * vel[c][i] += dt * acc[c][i]   ;   pos[c][i] += dt * vel[c][i] * vel_to_len
  * All fp64 [3][n] component-major; mul and add rounded separately (no FMA) so that a numpy

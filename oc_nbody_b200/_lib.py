@@ -22,7 +22,7 @@ ABI_SYMBOLS = [
     "ocg_version", "ocg_create", "ocg_destroy", "ocg_last_error", "ocg_device_info", "ocg_launch_count", "ocg_capture_epoch",
     "ocg_last_direct_kernel_ms", "ocg_set_kernel_timing", "ocg_last_direct_traffic_bytes", "ocg_recentre_f64", "ocg_cast_f64_f32", "ocg_assemble_sources",
     "ocg_field_direct", "ocg_frame_subtract", "ocg_field_build_host", "ocg_pack_planes", "ocg_grid_time_blend",
-    "ocg_grid_interp", "ocg_grid_interp_multi", "ocg_grid_interp_nested", "ocg_pack_planes_indexed", "ocg_set_interp_weight_slots", "ocg_grid_interp_slot", "ocg_grid_interp_rbf", "ocg_self_gravity", "ocg_self_gravity_hermite", "ocg_hermite_predict", "ocg_hermite_correct", "ocg_bound_com", "ocg_eject_mask", "ocg_compact_rows", "ocg_kick", "ocg_drift", "ocg_axpy", "ocg_probe_throughput", "ocg_comm_create", "ocg_comm_connect", "ocg_comm_destroy", "ocg_comm_info", "ocg_comm_status", "ocg_comm_allreduce_f64", "ocg_self_gravity_sharded",
+    "ocg_grid_interp", "ocg_grid_interp_multi", "ocg_grid_interp_nested", "ocg_pack_planes_indexed", "ocg_set_interp_weight_slots", "ocg_grid_interp_slot", "ocg_grid_interp_rbf", "ocg_self_gravity", "ocg_self_gravity_hermite", "ocg_hermite_predict", "ocg_hermite_correct", "ocg_hermite_block_evolve", "ocg_bound_com", "ocg_eject_mask", "ocg_compact_rows", "ocg_kick", "ocg_drift", "ocg_axpy", "ocg_probe_throughput", "ocg_comm_create", "ocg_comm_connect", "ocg_comm_destroy", "ocg_comm_info", "ocg_comm_status", "ocg_comm_allreduce_f64", "ocg_self_gravity_sharded",
 ]
 
 
@@ -94,6 +94,8 @@ def load_library():
     L.ocg_self_gravity_hermite.argtypes = [vp, vp, vp, vp, i64, vp, i32, dbl, dbl, dbl, i64, i64, vp, vp, vp, vp]
     L.ocg_hermite_predict.argtypes = [vp, vp, vp, vp, vp, i64, dbl, dbl, vp, vp, vp]
     L.ocg_hermite_correct.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, dbl, dbl, dbl, vp, vp]
+    L.ocg_hermite_block_evolve.argtypes = [vp, vp, vp, vp, vp, vp, i64, dbl, dbl, dbl, dbl, dbl, i32, ctypes.POINTER(i64),
+                                           ctypes.POINTER(i64), vp]
     L.ocg_debug_rbf_phase_cycles.argtypes = [vp, ctypes.POINTER(ctypes.c_double)]
     L.ocg_debug_set.argtypes = [vp, ctypes.c_int, i64]
     L.ocg_debug_variant_count.argtypes = [ctypes.c_int]
@@ -381,6 +383,15 @@ class Context:
                                               _dptr(vel_pred), _dptr(acc1), _dptr(jerk1), pos.shape[1], float(dt),
                                               float(vel_to_len), float(eta), _dptr(dt_min), self._stream()),
                  "ocg_hermite_correct")
+
+    def hermite_block_evolve(self, pos, vel, mass, acc, jerk, eps2, G, vel_to_len, span, eta=0.14, max_level=12):
+        """ph4's individual block time steps over `span`; returns (block steps, star-steps) taken."""
+        steps, star_steps = ctypes.c_int64(0), ctypes.c_int64(0)
+        self._ck(self.lib.ocg_hermite_block_evolve(self.h, _dptr(pos), _dptr(vel), _dptr(mass), _dptr(acc), _dptr(jerk), pos.shape[1],
+                                                   float(eps2), float(G), float(vel_to_len), float(span), float(eta), int(max_level),
+                                                   ctypes.byref(steps), ctypes.byref(star_steps), self._stream()),
+                 "ocg_hermite_block_evolve")
+        return int(steps.value), int(star_steps.value)
 
     def bound_com(self, pos, vel, mass, pot, pot_to_v2, out, seg_offsets=None, bound_mask=None):
         """out [n_seg, 8] fp64 device: bound-subset COM (3), bound mass, bound count, COM velocity (3)."""

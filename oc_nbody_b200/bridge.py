@@ -72,7 +72,8 @@ class Bridge(object):
         for cl, fld in (self.systems, self.systems[::-1]):
             if (self.partners[id(cl)] == (fld,) and self.partners[id(fld)] == () and hasattr(fld, "kick_device")
                     and hasattr(fld, "_time_planes_") and getattr(fld, "space_interpolation", "trilinear") == "trilinear"
-                    and type(cl).__name__ in ("cluster_code", "sharded_cluster_code") and hasattr(cl, "_evolve_device_")):
+                    and type(cl).__name__ in ("cluster_code", "sharded_cluster_code") and hasattr(cl, "_evolve_device_")
+                    and not getattr(cl, "block_steps", False)):  # block steps read back the schedule: not capturable
                 return cl, fld
         return None
 

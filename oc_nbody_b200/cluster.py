@@ -84,12 +84,18 @@ class cluster_code(object):
     one shared step."""
 
     def __init__(self, mass, pos, vel, softening_pc=0.01, substeps=1, eject_cut=None, ctx=None, integrator="leapfrog",
-                 eta=0.14):
+                 eta=0.14, block_steps=False, max_level=12):
         import torch
         if integrator not in ("leapfrog", "hermite"):
             raise ValueError("integrator must be 'leapfrog' or 'hermite', not %r" % (integrator,))
         self.integrator = integrator
         self.eta = float(eta)  # Aarseth accuracy parameter (ph4's timestep_parameter, default 0.14)
+        # ph4's individual block time steps (integrator="hermite" only): every star on its own step span / 2^k, k <= max_level
+        self.block_steps = bool(block_steps)
+        self.max_level = int(max_level)
+        if self.block_steps and integrator != "hermite":
+            raise ValueError("block_steps needs integrator='hermite'")
+        self.block_step_count = self.star_step_count = 0
         # a ctx of its own unless the caller shares one: a ctx is only scratch + settings, and a BRIDGE step captured as a
         # CUDA graph freezes the scratch addresses and the resident work plan (ocg_capture_epoch, include/ocg.h)
         self.ctx = ctx or _lib.private_context()
@@ -187,6 +193,13 @@ class cluster_code(object):
         """`substeps` shared 4th-order Hermite steps over `span` Myr (ph4's scheme without its block steps): force at the
         current state (the BRIDGE kick has just changed the velocities, so the jerk is always re-evaluated), then
         predict -> K6 at the predicted state -> correct.  Leaves the Aarseth step of the last step in self.dt_min."""
+        if self.block_steps:
+            bs, ss = self.ctx.hermite_block_evolve(self.pos, self.vel, self.mass, self.acc, self.jerk, self.parameters._eps2_kpc2,
+                                                   self.G, KMS_TO_KPC_PER_MYR, span, self.eta, self.max_level)
+            self.block_step_count += bs
+            self.star_step_count += ss
+            self._acc_valid = True
+            return
         h = span / self.substeps
         self._force_hermite_(self.pos, self.vel, self.acc, self.jerk)
         for _ in range(self.substeps):

@@ -406,10 +406,13 @@ __device__ __forceinline__ void near_pair(double dx, double dy, double dz, doubl
 }
 
 #define NEAR_BLOCK 128
+// grid = (target blocks, source slices).  One slice: the sums are added straight into acc / pot.  Several slices (few targets:
+// a 16^3 grid is 33 target blocks on 148 SMs): every slice writes its sums into near_partial[slice][NC][n_tgt] and
+// near_finish_kernel adds the slices in slice order — deterministic, unlike atomics.
 __global__ void __launch_bounds__(NEAR_BLOCK) near_sum_kernel(
     const float4* __restrict__ near_xyzm, const float* __restrict__ near_soft,
     const int* __restrict__ misc, const float4* __restrict__ tgt, long long n_tgt, int kernel,
-    double G, double* __restrict__ acc, double* __restrict__ pot) {
+    double G, double* __restrict__ acc, double* __restrict__ pot, double* __restrict__ near_partial) {
   const int n_near = misc[MISC_NNEAR];
   if (n_near == 0) return;
   __shared__ float4 sS[NEAR_BLOCK];
@@ -418,7 +421,10 @@ __global__ void __launch_bounds__(NEAR_BLOCK) near_sum_kernel(
   const float4 T = tgt[t < n_tgt ? t : n_tgt - 1];
   const double tx = T.x, ty = T.y, tz = T.z;
   double a0 = 0, a1 = 0, a2 = 0, ph = 0;
-  for (int base = 0; base < n_near; base += NEAR_BLOCK) {
+  // this slice's share of the near list, in whole staging blocks
+  const int nblk = (n_near + NEAR_BLOCK - 1) / NEAR_BLOCK;
+  const int b0 = (int)((long long)blockIdx.y * nblk / gridDim.y), b1 = (int)((long long)(blockIdx.y + 1) * nblk / gridDim.y);
+  for (int base = b0 * NEAR_BLOCK; base < b1 * NEAR_BLOCK; base += NEAR_BLOCK) {
     int i = base + threadIdx.x;
     __syncthreads();
     if (i < n_near) {
@@ -437,10 +443,27 @@ __global__ void __launch_bounds__(NEAR_BLOCK) near_sum_kernel(
     }
   }
   if (t < n_tgt) {
-    acc[t] += G * a0;
-    acc[n_tgt + t] += G * a1;
-    acc[2 * n_tgt + t] += G * a2;
-    if (pot) pot[t] += G * ph;
+    if (gridDim.y == 1) {
+      acc[t] += G * a0;
+      acc[n_tgt + t] += G * a1;
+      acc[2 * n_tgt + t] += G * a2;
+      if (pot) pot[t] += G * ph;
+    } else {
+      double* P = near_partial + (long long)blockIdx.y * 4 * n_tgt;
+      P[t] = a0, P[n_tgt + t] = a1, P[2 * n_tgt + t] = a2, P[3 * n_tgt + t] = ph;
+    }
+  }
+}
+__global__ void near_finish_kernel(const double* __restrict__ near_partial, int n_slices, const int* __restrict__ misc, long long n_tgt,
+                                   double G, double* __restrict__ acc, double* __restrict__ pot) {
+  if (misc[MISC_NNEAR] == 0) return;
+  const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (t >= n_tgt) return;
+  for (int c = 0; c < (pot ? 4 : 3); ++c) {
+    double s = 0.0;
+    for (int k = 0; k < n_slices; ++k) s += near_partial[((long long)k * 4 + c) * n_tgt + t];
+    if (c < 3) acc[(long long)c * n_tgt + t] += G * s;
+    else pot[t] += G * s;
   }
 }
 
@@ -606,10 +629,10 @@ static const DirectVariant g_variants[] = {
     /* 74 */ {"tpair-mf(+pot) np4 12w swizzled fold64", 8, 1, false, OCG_TPMFP(4, true, 1, 1, 12, 64), 8, 12, 2},  // production: BIG_MF_POT
     /* 75 */ {"tpair-mf(+pot) np5 8w swizzled fold64", 10, 1, false, TUNE(OCG_TPMFP(5, true, 1, 1, 8, 64)), 10, 8, 2},
     /* 76 */ {"tpair-mf(+pot) np4 12w swizzled fold512", 8, 1, false, TUNE(OCG_TPMFP(4, true, 1, 1, 12, 512)), 8, 12, 2},
-    /* 77 */ {"tpair-mf(+pot) np1 regacc minb2 unr2 swizzled fold32", 2, 2, false, OCG_TPMFP(1, false, 2, 2, OCG_CONSUMER_WARPS, 32), 0, 0, 2},  // production: MID_MF
+    /* 77 */ {"tpair-mf(+pot) np1 regacc minb2 unr2 swizzled fold32", 2, 2, false, TUNE(OCG_TPMFP(1, false, 2, 2, OCG_CONSUMER_WARPS, 32)), 0, 0, 2},
     /* 78 */ {"tpair-mf(+pot) np1 regacc minb2 unr2 swizzled fold512", 2, 2, false, TUNE(OCG_TPMFP(1, false, 2, 2, OCG_CONSUMER_WARPS, 512)), 0, 0, 2},
     /* 79 */ {"tpair-mf(+pot) np1 regacc minb2 unr2 swizzled fold64", 2, 2, false, TUNE(OCG_TPMFP(1, false, 2, 2, OCG_CONSUMER_WARPS, 64)), 0, 0, 2},
-    /* 80 */ {"tpair-mf(+pot) np1 regacc minb2 unr2 swizzled fold16", 2, 2, false, TUNE(OCG_TPMFP(1, false, 2, 2, OCG_CONSUMER_WARPS, 16)), 0, 0, 2},
+    /* 80 */ {"tpair-mf(+pot) np1 regacc minb2 unr2 swizzled fold16", 2, 2, false, OCG_TPMFP(1, false, 2, 2, OCG_CONSUMER_WARPS, 16), 0, 0, 2},  // production: MID_MF
 };
 static const int g_n_variants = (int)(sizeof(g_variants) / sizeof(g_variants[0]));
 // Production choices (tools/probe.py sweeps on B200, profiles/r01_variant_sweep*.json, profiles/r02_fold_sweep.json):
@@ -621,8 +644,9 @@ static const int g_n_variants = (int)(sizeof(g_variants) / sizeof(g_variants[0])
 #define OCG_VARIANT_BIG_MF 67     /* K1 >= 64k targets: mass-folded, w-swizzled tiles, 12 targets/thread, 8 warps, FOLD 64 */
 #define OCG_VARIANT_BIG_MF_POT 74 /* the same with the potential: 6-array tiles, 8 targets/thread, 12 warps, FOLD 64 */
 #define OCG_VARIANT_MID 27        /* >= 16k targets, plain tiles (K4): target-paired, 2 targets/thread              */
-#define OCG_VARIANT_MID_MF 77     /* K1 mid-size target counts: mass-folded, 2 targets/thread, register FP64 accumulators (a fold costs
-                                     12 instructions): FOLD 32, with or without potential */
+#define OCG_VARIANT_MID_MF 80     /* K1 mid-size target counts: mass-folded, 2 targets/thread, register FP64 accumulators (a fold costs
+                                     12 instructions): FOLD 16, with or without potential.  configs[0] (16^3 grid, 1e6 particles,
+                                     profiles/r02_accuracy_c0.json), tidal residual strict: FOLD 64 1.2e-5, 32 6.7e-6, 16 3.9e-6 */
 #define OCG_VARIANT_MID_GUARD 4   /* source-paired 2 targets/thread (carries the eps2 == 0 guarded form)          */
 #define OCG_VARIANT_SMALL 1       /* few targets: 1 target/thread spreads them over more CTAs (has guard form)    */
 
@@ -785,10 +809,12 @@ int ocg_direct_sum_impl(ocg_ctx* ctx, const float* src_xyzm, const float* src_so
     classify_hist_kernel<<<(int)n_cls_blocks, CLS_BLOCK, 0, st>>>(src4, src_soft, n_src, kernel, misc);
     OCG_CHECK_LAUNCH(ctx, "classify_hist_kernel");
     // cap the FP64 set at ~0.2% of the sources: its pair cost is ~4x the FP32 one, so the near pass stays ~1% of the call.
-    // Small snapshots (few, heavy particles: the reference's test_options scale) get a floor of 16384: their single pair
-    // terms are a larger share of the field, and the whole call is milliseconds anyway.
+    // Small snapshots (few, heavy particles: the reference's test_options scale) get a floor of 2^36 / n_src: their single
+    // pair terms are a larger share of the field (configs[0], 1e6 particles: tidal residual 1.1e-5 strict with 16384 near
+    // sources, 3.9e-6 with 65536, profiles/r02_accuracy_c0.json) and the whole call is milliseconds anyway.
     long long cap = ctx->knobs.near_cap > 0 ? ctx->knobs.near_cap : n_src / 512;
-    if (ctx->knobs.near_cap <= 0 && cap < 16384) cap = 16384;
+    const long long floor_cap = (1ll << 36) / (n_src > 0 ? n_src : 1);  // 68 719 at 1e6 particles, 6 871 at 1e7, everything below 2.6e5
+    if (ctx->knobs.near_cap <= 0 && cap < floor_cap) cap = floor_cap;
     choose_radius_kernel<<<1, 1, 0, st>>>(misc, (int)cap, ctx->knobs.precise_near);
     OCG_CHECK_LAUNCH(ctx, "choose_radius_kernel");
   }
@@ -835,9 +861,20 @@ int ocg_direct_sum_impl(ocg_ctx* ctx, const float* src_xyzm, const float* src_so
       finish_kernel<<<(int)nb, 256, 0, st>>>(partial, n_tgt, (int)n_chunks, NC, G, misc, n_tgt, acc, pot, accumulate, mf);
       OCG_CHECK_LAUNCH(ctx, "finish_kernel");
     }
-    long long nbn = (n_tgt + NEAR_BLOCK - 1) / NEAR_BLOCK;
-    near_sum_kernel<<<(int)nbn, NEAR_BLOCK, 0, st>>>(near_xyzm, near_soft, misc, tgt4, n_tgt, kernel, G, acc, pot);
+    const long long nbn = (n_tgt + NEAR_BLOCK - 1) / NEAR_BLOCK;
+    // few targets: cut the near list into slices so that the FP64 pass fills the machine (>= 4 CTAs per SM in flight)
+    long long slices = (4ll * ctx->sm_count + nbn - 1) / nbn;
+    if (slices > 64) slices = 64;
+    if (slices < 1) slices = 1;
+    double* near_partial = nullptr;
+    if (slices > 1 && (rc = ocg_scratch(ctx, OCG_SCR_NEARPART, (size_t)slices * 4 * n_tgt * sizeof(double), (void**)&near_partial))) return rc;
+    near_sum_kernel<<<dim3((unsigned)nbn, (unsigned)slices), NEAR_BLOCK, 0, st>>>(near_xyzm, near_soft, misc, tgt4, n_tgt, kernel, G, acc, pot,
+                                                                                 near_partial);
     OCG_CHECK_LAUNCH(ctx, "near_sum_kernel");
+    if (slices > 1) {
+      near_finish_kernel<<<(int)nb, 256, 0, st>>>(near_partial, (int)slices, misc, n_tgt, G, acc, pot);
+      OCG_CHECK_LAUNCH(ctx, "near_finish_kernel");
+    }
   }
   return OCG_OK;
 }

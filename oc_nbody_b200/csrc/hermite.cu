@@ -633,3 +633,271 @@ extern "C" int ocg_hermite_correct(ocg_ctx* ctx, double* pos_dev, double* vel_de
   OCG_CHECK_LAUNCH(ctx, "hermite_correct_kernel");
   return OCG_OK;
 }
+
+// =====================================================================================================
+// ph4's individual block time steps (oc_code.py:218-229 instantiates AMUSE ph4; options.py:248-253).
+//
+// Every star i carries its own time t_i and step dt_i = span / 2^k_i; all steps are powers of two of one span and every
+// star's time is a multiple of its step, so the stars synchronise at the end of the span.  One block step:
+//   t_next  = min_i (t_i + dt_i);  active = { i : t_i + dt_i == t_next }        (times are integer ticks: exact)
+//   predict EVERY star to t_next with its own elapsed time (Makino & Aarseth 1992 predictor)
+//   force (acc + jerk) on the ACTIVE stars from ALL predicted stars              (K6, active targets x all sources)
+//   correct the active stars over their own dt_i, set t_i = t_next, choose the next dt_i from the Aarseth criterion:
+//   halve while it exceeds the criterion; double (once) when the criterion allows 2 dt_i and t_next is a multiple of 2 dt_i.
+// The host loop reads back 16 bytes per block step (t_next, number of active stars) to size the launches.
+#define HB_LEVELS 20                      /* the span is 2^20 ticks: smallest step = span / 1 048 576 */
+#define HB_SPAN_TICKS (1ll << HB_LEVELS)
+
+struct HermiteBlockSel {
+  long long t_next;
+  int n_active;
+  int pad;
+};
+
+// first force done: per-star starting step dt = eta * |a| / |j| (Aarseth 1985), rounded down to a power-of-two fraction of
+// the span, at most the span and at most 2^max_level_up... (min_ticks = smallest allowed step)
+__global__ void hermite_block_init_kernel(const double* __restrict__ acc, const double* __restrict__ jerk, long long n, double eta,
+                                          double tick_len, long long min_ticks, long long* __restrict__ t_tick,
+                                          long long* __restrict__ dt_tick) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double a2 = 0.0, j2 = 0.0;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) a2 += acc[c * n + i] * acc[c * n + i], j2 += jerk[c * n + i] * jerk[c * n + i];
+  long long ticks = HB_SPAN_TICKS;
+  if (j2 > 0.0) {
+    const double dt = eta * sqrt(a2 / j2);
+    while (ticks > min_ticks && (double)ticks * tick_len > dt) ticks >>= 1;
+  }
+  t_tick[i] = 0;
+  dt_tick[i] = ticks;
+}
+
+// one CTA: t_next = min (t + dt), then the stable list of the stars that reach it
+__global__ void __launch_bounds__(1024) hermite_block_select_kernel(const long long* __restrict__ t_tick, const long long* __restrict__ dt_tick,
+                                                                    long long n, int* __restrict__ active_idx, HermiteBlockSel* __restrict__ sel) {
+  __shared__ long long s_min[32];
+  __shared__ int wtot[32];
+  __shared__ long long s_tnext;
+  __shared__ int s_base;
+  long long m = 0x7fffffffffffffffll;
+  for (long long i = threadIdx.x; i < n; i += 1024) {
+    const long long v = t_tick[i] + dt_tick[i];
+    m = v < m ? v : m;
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    const long long other = __shfl_xor_sync(0xffffffffu, m, o);
+    m = other < m ? other : m;
+  }
+  if ((threadIdx.x & 31) == 0) s_min[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    long long v = s_min[0];
+    for (int w = 1; w < 32; ++w) v = s_min[w] < v ? s_min[w] : v;
+    s_tnext = v;
+    s_base = 0;
+  }
+  __syncthreads();
+  const long long tn = s_tnext;
+  for (long long start = 0; start < n; start += 1024) {
+    const long long i = start + threadIdx.x;
+    const bool k = i < n && t_tick[i] + dt_tick[i] == tn;
+    const unsigned b = __ballot_sync(0xffffffffu, k);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) wtot[warp] = __popc(b);
+    __syncthreads();
+    int before = 0, all = 0;
+    for (int w = 0; w < 32; ++w) {
+      const int t = wtot[w];
+      if (w < warp) before += t;
+      all += t;
+    }
+    if (k) active_idx[s_base + before + __popc(b & ((1u << lane) - 1u))] = (int)i;
+    __syncthreads();
+    if (threadIdx.x == 0) s_base += all;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) sel->t_next = tn, sel->n_active = s_base, sel->pad = 0;
+}
+
+// predictor with per-star elapsed time: the operation order of hermite_predict_kernel, delta = (t_next - t_i) * tick_len
+__global__ void hermite_block_predict_kernel(const double* __restrict__ pos, const double* __restrict__ vel, const double* __restrict__ acc,
+                                             const double* __restrict__ jerk, const long long* __restrict__ t_tick, long long n,
+                                             const HermiteBlockSel* __restrict__ sel, double tick_len, double vel_to_len,
+                                             double* __restrict__ pos_p, double* __restrict__ vel_p) {
+  const long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (q >= 3 * n) return;
+  const long long i = q % n;
+  const double dt = (double)(sel->t_next - t_tick[i]) * tick_len;
+  const double c2 = dt * dt * 0.5, c3 = dt * dt * dt / 6.0;
+  const double v = vel[q], a = acc[q], j = jerk[q];
+  const double dx = __dadd_rn(__dadd_rn(__dmul_rn(v, dt), __dmul_rn(a, c2)), __dmul_rn(j, c3));
+  pos_p[q] = __dadd_rn(pos[q], __dmul_rn(dx, vel_to_len));
+  vel_p[q] = __dadd_rn(v, __dadd_rn(__dmul_rn(a, dt), __dmul_rn(j, c2)));
+}
+
+// compact float4 targets of the active stars out of the packed full arrays
+__global__ void hermite_block_gather_kernel(const float4* __restrict__ tgt_pos, const float4* __restrict__ tgt_vel,
+                                            const int* __restrict__ active_idx, int n_active, float4* __restrict__ out_pos,
+                                            float4* __restrict__ out_vel) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n_active) return;
+  const int i = active_idx[k];
+  out_pos[k] = tgt_pos[i], out_vel[k] = tgt_vel[i];
+}
+
+// corrector of the active stars (operation order of hermite_correct_kernel) + their next step
+__global__ void hermite_block_correct_kernel(double* __restrict__ pos, double* __restrict__ vel, double* __restrict__ acc0,
+                                             double* __restrict__ jerk0, const double* __restrict__ pos_p, const double* __restrict__ vel_p,
+                                             const double* __restrict__ acc1c, const double* __restrict__ jerk1c,
+                                             const int* __restrict__ active_idx, int n_active, long long n,
+                                             const HermiteBlockSel* __restrict__ sel, double tick_len, double vel_to_len, double eta,
+                                             long long min_ticks, long long* __restrict__ t_tick, long long* __restrict__ dt_tick) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n_active) return;
+  const long long i = active_idx[k];
+  const long long ticks = dt_tick[i], tn = sel->t_next;
+  const double dt = (double)ticks * tick_len;
+  const double dt2 = dt * dt, dt3 = dt2 * dt, i2 = 1.0 / dt2, i3 = 1.0 / dt3;
+  const double d3 = dt3 / 6.0, d4 = dt2 * dt2 / 24.0, d5 = dt2 * dt3 / 120.0, k6dt = 6.0 * dt;
+  double s_a = 0.0, s_j = 0.0, s_2 = 0.0, s_3 = 0.0;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const long long q = c * n + i;
+    const double a0 = acc0[q], j0 = jerk0[q], a1 = acc1c[(long long)c * n_active + k], j1 = jerk1c[(long long)c * n_active + k];
+    const double da = __dadd_rn(a0, -a1);
+    const double a2 = __dmul_rn(__dadd_rn(__dmul_rn(da, -6.0), -__dmul_rn(__dadd_rn(__dmul_rn(j0, 4.0), __dmul_rn(j1, 2.0)), dt)), i2);
+    const double a3 = __dmul_rn(__dadd_rn(__dmul_rn(da, 12.0), __dmul_rn(__dadd_rn(j0, j1), k6dt)), i3);
+    vel[q] = __dadd_rn(__dadd_rn(vel_p[q], __dmul_rn(a2, d3)), __dmul_rn(a3, d4));
+    pos[q] = __dadd_rn(pos_p[q], __dmul_rn(__dadd_rn(__dmul_rn(a2, d4), __dmul_rn(a3, d5)), vel_to_len));
+    acc0[q] = a1, jerk0[q] = j1;
+    const double a2e = a2 + dt * a3;
+    s_a += a1 * a1, s_j += j1 * j1, s_2 += a2e * a2e, s_3 += a3 * a3;
+  }
+  const double num = sqrt(s_a * s_2) + s_j, den = sqrt(s_j * s_3) + s_2;
+  long long next = ticks;
+  if (den > 0.0 && num > 0.0) {
+    const double want = sqrt(eta * num / den);
+    if (want < dt) {
+      while (next > min_ticks && (double)next * tick_len > want) next >>= 1;
+    } else if (want >= 2.0 * dt && 2 * next <= HB_SPAN_TICKS && tn % (2 * next) == 0) {
+      next <<= 1;
+    }
+  }
+  t_tick[i] = tn;
+  dt_tick[i] = next;
+}
+
+extern "C" int ocg_hermite_block_evolve(ocg_ctx* ctx, double* pos_dev, double* vel_dev, const double* mass_dev, double* acc_dev,
+                                        double* jerk_dev, int64_t n, double eps2, double G, double vel_to_len, double span, double eta,
+                                        int32_t max_level, int64_t* n_block_steps_host, int64_t* n_star_steps_host, void* stream) {
+  if (!ctx) return OCG_ERR_INVALID;
+  if (n < 1 || !pos_dev || !vel_dev || !mass_dev || !acc_dev || !jerk_dev)
+    return ocg_fail(ctx, OCG_ERR_INVALID, "ocg_hermite_block_evolve: bad arguments");
+  if (!(span > 0.0) || !(eta > 0.0) || !(eps2 >= 0.0) || max_level < 0 || max_level > HB_LEVELS)
+    return ocg_fail(ctx, OCG_ERR_INVALID, "ocg_hermite_block_evolve: span %g, eta %g, eps2 %g, max_level %d (0..%d)", span, eta, eps2,
+                    max_level, HB_LEVELS);
+  if (n > 0x7fffffffll) return ocg_fail(ctx, OCG_ERR_INVALID, "ocg_hermite_block_evolve: too many stars");
+  OcgDeviceGuard g(ctx->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  const double tick_len = span / (double)HB_SPAN_TICKS;
+  const long long min_ticks = HB_SPAN_TICKS >> max_level;
+  const float e2f = (float)eps2;
+  const bool guard = !(e2f > 0.f);
+  const float scale = hermite_scale(e2f), e2s = guard ? 0.f : e2f * scale * scale;
+  // ---- workspace: predicted state, per-star clocks, the active list, compact targets and forces
+  const size_t n8 = ((size_t)n + 7) & ~(size_t)7;
+  size_t off = 0;
+  auto carve = [&](size_t bytes) {
+    const size_t o = off;
+    off += (bytes + 255) & ~(size_t)255;
+    return o;
+  };
+  const size_t o_posp = carve(3 * n8 * 8), o_velp = carve(3 * n8 * 8), o_t = carve(n8 * 8), o_dt = carve(n8 * 8), o_idx = carve(n8 * 4),
+               o_acc1 = carve(3 * n8 * 8), o_jerk1 = carve(3 * n8 * 8), o_tp = carve(n8 * 16), o_tv = carve(n8 * 16), o_sel = carve(256),
+               o_seg = carve(256);
+  char* ws;
+  int rc = ocg_scratch(ctx, OCG_SCR_BLOCK, off, (void**)&ws);
+  if (rc) return rc;
+  double *pos_p = (double*)(ws + o_posp), *vel_p = (double*)(ws + o_velp), *acc1 = (double*)(ws + o_acc1), *jerk1 = (double*)(ws + o_jerk1);
+  long long *t_tick = (long long*)(ws + o_t), *dt_tick = (long long*)(ws + o_dt), *d_seg = (long long*)(ws + o_seg);
+  int* active = (int*)(ws + o_idx);
+  float4 *ctgt_pos = (float4*)(ws + o_tp), *ctgt_vel = (float4*)(ws + o_tv);
+  HermiteBlockSel* d_sel = (HermiteBlockSel*)(ws + o_sel);
+  const long long total_tiles = (n + HM_TS - 1) / HM_TS;
+  float* tiles;
+  float4* tgt;
+  double* partial;
+  unsigned int* tickets;
+  // shape: the production shape of the force kernel; rows in uniform mode (every row streams all tiles), no plan upload
+  int variant = ctx->knobs.hermite_variant;
+  if (variant >= HM_N_VARIANTS || variant < 0 || !g_hm_variants[variant].fn[0][0]) variant = HM_PRODUCTION;
+  const HermiteVariant& v = g_hm_variants[variant];
+  const int NTHR = 32 * v.nw, CT = 2 * v.np * NTHR;
+  const long long grid_ctas = (long long)ctx->sm_count * v.minb;
+  const long long max_rows = (n + CT - 1) / CT;
+  const long long n_slots = grid_ctas;  // a single row (few active stars) may be shared by every CTA; the slots are indexed
+                                        // with stride n_t, and sharers * n_t <= (CTAs + rows) * CT whatever n_t is
+  rc = ocg_scratch(ctx, OCG_SCR_TILES_HM, (size_t)total_tiles * HM_TILE_BYTES, (void**)&tiles);
+  if (!rc) rc = ocg_scratch(ctx, OCG_SCR_TGT_HM, 2 * sizeof(float4) * (size_t)n, (void**)&tgt);
+  if (!rc) rc = ocg_scratch(ctx, OCG_SCR_PARTIAL_HM, sizeof(double) * 7 * (size_t)(grid_ctas + max_rows + 1) * CT, (void**)&partial);
+  if (!rc) rc = ocg_scratch(ctx, OCG_SCR_TICKETS_HM, sizeof(unsigned int) * (size_t)(max_rows > 0 ? max_rows : 1), (void**)&tickets, true);
+  if (rc) return rc;
+  const long long h_seg[4] = {0, total_tiles, 0, n};  // seg_tile[2] | seg_off[2]
+  OCG_CUDA(ctx, cudaMemcpyAsync(d_seg, h_seg, sizeof(h_seg), cudaMemcpyHostToDevice, st));
+  OCG_CUDA(ctx, cudaStreamSynchronize(st));
+
+  hermite_fn fn = v.fn[0][guard];
+  const size_t smem = HM_NSTAGE * HM_TILE_BYTES + 128 + (size_t)6 * 2 * v.np * NTHR * sizeof(double);
+  OCG_CUDA(ctx, cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  // force on targets [0, n_t) of (tp, tv) from the sources (src_pos, src_vel): compact outputs [3][n_t]
+  auto force = [&](const double* src_pos, const double* src_vel, const int* idx, int n_t, double* out_acc, double* out_jerk) -> int {
+    const long long nslots = total_tiles * HM_TS;
+    pack_hermite_kernel<<<(int)((nslots + 255) / 256), 256, 0, st>>>(src_pos, src_vel, mass_dev, n, d_seg + 2, d_seg, 1, scale, tiles, tgt, tgt + n);
+    OCG_CHECK_LAUNCH(ctx, "pack_hermite_kernel");
+    const float4 *tp = tgt, *tv = tgt + n;
+    if (idx) {
+      hermite_block_gather_kernel<<<(n_t + 255) / 256, 256, 0, st>>>(tgt, tgt + n, idx, n_t, ctgt_pos, ctgt_vel);
+      OCG_CHECK_LAUNCH(ctx, "hermite_block_gather_kernel");
+      tp = ctgt_pos, tv = ctgt_vel;
+    }
+    HermiteParams p;
+    memset(&p, 0, sizeof(p));
+    p.tiles = tiles, p.tgt_pos = tp, p.tgt_vel = tv, p.partial = partial, p.out_stride = n_t;
+    p.sk.rows = nullptr, p.sk.row_prefix = nullptr, p.sk.n_rows = (n_t + CT - 1) / CT, p.sk.n_slots = (int)n_slots;
+    p.sk.n_tgt = n_t, p.sk.ct = CT, p.sk.nst_uniform = nullptr, p.sk.nst_value = (int)total_tiles, p.sk.tickets = tickets;
+    p.out_acc = out_acc, p.out_jerk = out_jerk, p.out_pot = nullptr, p.G = G, p.vel_to_len = vel_to_len;
+    p.e2s = e2s, p.scale = scale;
+    fn<<<(int)grid_ctas, NTHR, smem, st>>>(p);
+    OCG_CHECK_LAUNCH(ctx, "hermite_tp_kernel");
+    return OCG_OK;
+  };
+
+  // ---- start: force at the current state for every star (the BRIDGE kick has just changed the velocities), first steps
+  if ((rc = force(pos_dev, vel_dev, nullptr, (int)n, acc_dev, jerk_dev))) return rc;
+  hermite_block_init_kernel<<<(int)((n + 255) / 256), 256, 0, st>>>(acc_dev, jerk_dev, n, eta, tick_len, min_ticks, t_tick, dt_tick);
+  OCG_CHECK_LAUNCH(ctx, "hermite_block_init_kernel");
+  long long steps = 0, star_steps = 0;
+  for (;;) {
+    hermite_block_select_kernel<<<1, 1024, 0, st>>>(t_tick, dt_tick, n, active, d_sel);
+    OCG_CHECK_LAUNCH(ctx, "hermite_block_select_kernel");
+    HermiteBlockSel h;
+    OCG_CUDA(ctx, cudaMemcpyAsync(&h, d_sel, sizeof(h), cudaMemcpyDeviceToHost, st));
+    OCG_CUDA(ctx, cudaStreamSynchronize(st));
+    if (h.n_active <= 0 || h.t_next > HB_SPAN_TICKS)
+      return ocg_fail(ctx, OCG_ERR_CUDA, "ocg_hermite_block_evolve: block schedule broke (t_next %lld, %d active)", h.t_next, h.n_active);
+    hermite_block_predict_kernel<<<(int)((3 * n + 255) / 256), 256, 0, st>>>(pos_dev, vel_dev, acc_dev, jerk_dev, t_tick, n, d_sel, tick_len,
+                                                                            vel_to_len, pos_p, vel_p);
+    OCG_CHECK_LAUNCH(ctx, "hermite_block_predict_kernel");
+    if ((rc = force(pos_p, vel_p, active, h.n_active, acc1, jerk1))) return rc;
+    hermite_block_correct_kernel<<<(h.n_active + 255) / 256, 256, 0, st>>>(pos_dev, vel_dev, acc_dev, jerk_dev, pos_p, vel_p, acc1, jerk1,
+                                                                          active, h.n_active, n, d_sel, tick_len, vel_to_len, eta,
+                                                                          min_ticks, t_tick, dt_tick);
+    OCG_CHECK_LAUNCH(ctx, "hermite_block_correct_kernel");
+    ++steps, star_steps += h.n_active;
+    if (h.t_next == HB_SPAN_TICKS) break;  // every step divides the span: all stars arrive here together
+  }
+  if (n_block_steps_host) *n_block_steps_host = steps;
+  if (n_star_steps_host) *n_star_steps_host = star_steps;
+  return OCG_OK;
+}

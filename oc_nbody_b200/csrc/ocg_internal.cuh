@@ -33,7 +33,7 @@ struct OcgWorkItem {
 
 enum { OCG_SCR_TILES = 0, OCG_SCR_PARTIAL, OCG_SCR_NEAR, OCG_SCR_ITEMS, OCG_SCR_MISC, OCG_SCR_TGT,
        OCG_SCR_SRC, OCG_SCR_SOFT, OCG_SCR_F64A, OCG_SCR_F64B, OCG_SCR_F64C, OCG_SCR_OUT, OCG_SCR_COUNTS,
-       OCG_SCR_ITEMS_HM, OCG_SCR_TILES_HM, OCG_SCR_TGT_HM, OCG_SCR_PARTIAL_HM, OCG_SCR_TICKETS, OCG_SCR_TICKETS_HM,
+       OCG_SCR_ITEMS_HM, OCG_SCR_TILES_HM, OCG_SCR_TGT_HM, OCG_SCR_PARTIAL_HM, OCG_SCR_TICKETS, OCG_SCR_TICKETS_HM, OCG_SCR_NEARPART, OCG_SCR_BLOCK,
        OCG_SCR_N };
 
 // Tuning / test knobs of one ctx (include/ocg_debug.h: ocg_debug_set).  Defaults are the production behaviour.
@@ -48,7 +48,7 @@ struct OcgKnobs {
   int interp_variant;       // register bound of K3: 0 <=128, 1 <=80, 2 <=64 (production)
   int field_precision;      // 0 = FP32 pair arithmetic + FP64 accumulation (north_star), 1 = every pair in FP64
   int rbf_share;            // 1 = K7 shares one factorisation between stars with the same stencil pattern
-  long long near_cap;       // > 0: size limit of K1's FP64 precision-radius set (0 = max(16384, n_src / 512))
+  long long near_cap;       // > 0: size limit of K1's FP64 precision-radius set (0 = max(n_src / 512, 2^36 / n_src))
 };
 
 struct ocg_comm;  // comm.cu: the rank's exchange window and the mapped windows of its peers
@@ -131,7 +131,8 @@ struct StreamKParams {
   int n_slots;                  // slots per row in the partial buffer (>= the most CTAs any row is shared by)
   long long n_tgt;              // uniform mode: row r = targets [r*ct, min((r+1)*ct, n_tgt))
   int ct;
-  const int* nst_uniform;       // uniform mode: device count of source tiles every row streams
+  const int* nst_uniform;       // uniform mode: device count of source tiles every row streams ...
+  int nst_value;                // ... or, when that pointer is NULL, the count itself
   unsigned int* tickets;        // [n_rows]; zero on entry, zero again on exit
 };
 

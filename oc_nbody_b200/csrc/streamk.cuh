@@ -12,15 +12,16 @@
 #pragma once
 #include "ocg_internal.cuh"
 
+__device__ __forceinline__ long long sk_nst(const StreamKParams& k) { return k.nst_uniform ? (long long)(*k.nst_uniform) : (long long)k.nst_value; }
 __device__ __forceinline__ long long sk_units(const StreamKParams& k) {
-  return k.rows ? k.row_prefix[k.n_rows] : (long long)k.n_rows * (long long)(*k.nst_uniform);
+  return k.rows ? k.row_prefix[k.n_rows] : (long long)k.n_rows * sk_nst(k);
 }
 __device__ __forceinline__ long long sk_row_start(const StreamKParams& k, int r) {
-  return k.rows ? k.row_prefix[r] : (long long)r * (long long)(*k.nst_uniform);
+  return k.rows ? k.row_prefix[r] : (long long)r * sk_nst(k);
 }
 // the row holding unit u
 __device__ __forceinline__ int sk_find_row(const StreamKParams& k, long long u) {
-  if (!k.rows) return (int)(u / (long long)(*k.nst_uniform));
+  if (!k.rows) return (int)(u / sk_nst(k));
   int lo = 0, hi = k.n_rows;  // largest r with prefix[r] <= u
   while (hi - lo > 1) {
     const int mid = (lo + hi) >> 1;

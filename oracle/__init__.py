@@ -241,6 +241,66 @@ def hermite_evolve(pos, vel, mass, eps2, G, span, substeps, vel_to_len=1.0, eta=
     return pos, vel, dt_min
 
 
+def hermite_block_evolve(pos, vel, mass, eps2, G, span, vel_to_len=1.0, eta=0.14, max_level=12, force=None):
+    """ph4's individual block time steps over `span` (AMUSE ph4 behind oc_code.py:218-229), restated from Makino & Aarseth
+    (1992) / Aarseth (1985): per-star power-of-two steps span / 2^k (k <= max_level), t_next = min (t_i + dt_i), every star
+    predicted to t_next, force on the active stars from all predicted stars, corrector over the star's own step, next step
+    from the Aarseth criterion (halve as needed; double once, onto commensurate times only).  Times are integer ticks
+    (span = 2^20), exactly as ocg_hermite_block_evolve keeps them.  `force(pos, vel) -> (acc, jerk)` defaults to the FP64
+    oracle sum.  Returns (pos, vel, acc, jerk, block_steps, star_steps)."""
+    if force is None:
+        def force(x, v):
+            return self_gravity_hermite(x, v, mass, eps2, G, vel_to_len)
+    pos, vel = np.array(pos, np.float64), np.array(vel, np.float64)
+    n = pos.shape[1]
+    SPAN = 1 << 20
+    tick = span / SPAN
+    min_ticks = SPAN >> int(max_level)
+    acc, jerk = force(pos, vel)
+    a2, j2 = (acc * acc).sum(axis=0), (jerk * jerk).sum(axis=0)
+    dt_tick = np.full(n, SPAN, np.int64)
+    want = np.where(j2 > 0, eta * np.sqrt(a2 / np.where(j2 > 0, j2, 1.0)), np.inf)
+    for i in range(n):
+        while dt_tick[i] > min_ticks and dt_tick[i] * tick > want[i]:
+            dt_tick[i] >>= 1
+    t_tick = np.zeros(n, np.int64)
+    steps = star_steps = 0
+    while True:
+        tn = int((t_tick + dt_tick).min())
+        act = np.nonzero(t_tick + dt_tick == tn)[0]
+        d = (tn - t_tick) * tick
+        c2, c3 = d * d * 0.5, d * d * d / 6.0
+        dx = (vel * d + acc * c2) + jerk * c3
+        xp, vp = pos + dx * vel_to_len, vel + (acc * d + jerk * c2)
+        a1, j1 = force(xp, vp)
+        for i in act:
+            dt = dt_tick[i] * tick
+            dt2, dt3 = dt * dt, dt * dt * dt
+            da = acc[:, i] - a1[:, i]
+            A2 = (da * -6.0 - (jerk[:, i] * 4.0 + j1[:, i] * 2.0) * dt) * (1.0 / dt2)
+            A3 = (da * 12.0 + (jerk[:, i] + j1[:, i]) * (6.0 * dt)) * (1.0 / dt3)
+            vel[:, i] = (vp[:, i] + A2 * (dt3 / 6.0)) + A3 * (dt2 * dt2 / 24.0)
+            pos[:, i] = xp[:, i] + (A2 * (dt2 * dt2 / 24.0) + A3 * (dt2 * dt3 / 120.0)) * vel_to_len
+            acc[:, i], jerk[:, i] = a1[:, i], j1[:, i]
+            a2e = A2 + dt * A3
+            s_a, s_j, s_2, s_3 = (a1[:, i] ** 2).sum(), (j1[:, i] ** 2).sum(), (a2e ** 2).sum(), (A3 ** 2).sum()
+            num, den = np.sqrt(s_a * s_2) + s_j, np.sqrt(s_j * s_3) + s_2
+            nxt = int(dt_tick[i])
+            if den > 0 and num > 0:
+                w = np.sqrt(eta * num / den)
+                if w < dt:
+                    while nxt > min_ticks and nxt * tick > w:
+                        nxt >>= 1
+                elif w >= 2.0 * dt and 2 * nxt <= SPAN and tn % (2 * nxt) == 0:
+                    nxt <<= 1
+            t_tick[i], dt_tick[i] = tn, nxt
+        steps += 1
+        star_steps += len(act)
+        if tn == SPAN:
+            break
+    return pos, vel, acc, jerk, steps, star_steps
+
+
 def pack_planes(acc, pot=None):
     acc = _c(acc, np.float64)
     n = acc.shape[1]

@@ -134,3 +134,38 @@ def test_oracle_hermite_evolve_conserves_energy_of_a_small_cluster():
     x, v, dtm = oracle.hermite_evolve(pos, vel, mass, eps2, 1.0, 0.125, 64)
     assert abs(energy(x, v) - e0) < 1e-6 * abs(e0)  # FP32-rounded inputs to the force bound this, not the scheme
     assert 0.0 < dtm < 1.0
+
+
+def test_block_time_steps_kepler_orbit_and_equal_level_limit():
+    """ph4's individual block time steps, restated in the oracle (oracle.hermite_block_evolve): an e = 0.6 Kepler orbit
+    closes and conserves energy better as eta shrinks; with every star forced onto the smallest step the scheme is the
+    shared-step Hermite integrator bit for bit."""
+    G = 1.0
+    m = np.array([1.0, 1e-3])
+    e, a = 0.6, 1.0
+    mu = G * m.sum()
+    rp, vp = a * (1 - e), np.sqrt(mu * (1 + e) / (a * (1 - e)))
+    pos = np.array([[0.0, rp], [0.0, 0.0], [0.0, 0.0]])
+    vel = np.array([[0.0, 0.0], [0.0, vp], [0.0, 0.0]])
+    vel -= (vel * m).sum(axis=1, keepdims=True) / m.sum()
+    pos -= (pos * m).sum(axis=1, keepdims=True) / m.sum()
+    period = 2 * np.pi * np.sqrt(a ** 3 / mu)
+
+    def energy(x, v):
+        return 0.5 * (m * (v * v).sum(axis=0)).sum() - G * m[0] * m[1] / np.linalg.norm(x[:, 1] - x[:, 0])
+    e0 = energy(pos, vel)
+    errs = []
+    for eta in (0.02, 0.005):
+        x, v, acc, jerk, steps, star_steps = oracle.hermite_block_evolve(pos, vel, m, 0.0, G, period, 1.0, eta, 16)
+        errs.append((abs(energy(x, v) - e0) / abs(e0), np.linalg.norm((x[:, 1] - x[:, 0]) - (pos[:, 1] - pos[:, 0])), steps))
+        a_ref, j_ref = oracle.self_gravity_hermite(x, v, m, 0.0, G, 1.0)
+        # acc / jerk left behind are the scheme's own end-of-step force (evaluated at the PREDICTED end state)
+        assert np.max(np.abs(acc - a_ref)) <= 1e-3 * np.max(np.abs(a_ref)) and np.max(np.abs(jerk - j_ref)) <= 2e-2 * np.max(np.abs(j_ref))
+    assert errs[0][0] < 5e-6 and errs[1][0] < errs[0][0] / 20 and errs[1][1] < errs[0][1] / 8 and errs[1][2] > errs[0][2]
+    # steps shrink near pericentre: far fewer block steps than the smallest step taken would need as a shared step
+    x, v, _, _, steps, _ = oracle.hermite_block_evolve(pos, vel, m, 0.0, G, period, 1.0, 0.005, 16)
+    assert steps < 2 ** 12
+    # equal-level limit
+    xb, vb, _, _, steps, star_steps = oracle.hermite_block_evolve(pos, vel, m, 0.0, G, period / 8, 1.0, 1e-9, 6)
+    xs, vs, _ = oracle.hermite_evolve(pos, vel, m, 0.0, G, period / 8, 64, 1.0, 0.14)
+    assert steps == 64 and star_steps == 128 and np.array_equal(xb, xs) and np.array_equal(vb, vs)

@@ -293,13 +293,16 @@ def test_field_code_snapshot_caches_round_trip(ctx, tmp_path):
     opts = dict(grid_x_size_in_kpc=0.06, grid_y_size_in_kpc=0.06, grid_z_size_in_kpc=0.06, grid_resolution=0.06 / 5,
                 cache_directory=str(tmp_path / "cache"))
     a = gizmo_field(opts, snaps, ctx=ctx)
-    assert a.cache_hits == 0 and len(list((tmp_path / "cache").iterdir())) == 8
+    # 2 snapshots x (x, y, z, pot) + the whole-grid pickle (gizmo_interface.py:510)
+    assert a.cache_hits == 0 and not a.grid_cache_hit and len(list((tmp_path / "cache").iterdir())) == 9
+    os.remove(a._grid_cache_name_()[1])   # without the whole-grid file the per-snapshot caches serve the build
     b = gizmo_field(opts, snaps, ctx=ctx)
-    assert b.cache_hits == 2
+    assert b.cache_hits == 2 and not b.grid_cache_hit
     for k in ("snapshot_acceleration_x", "snapshot_acceleration_y", "snapshot_acceleration_z", "snapshot_potential"):
         assert np.array_equal(getattr(a.grid, k), getattr(b.grid, k))
-    c = gizmo_field(dict(opts, with_potential=False), snaps, ctx=ctx)
-    assert c.cache_hits == 2 and c.grid.snapshot_potential is None
+    c = gizmo_field(dict(opts, with_potential=False), snaps, ctx=ctx)   # b rewrote the whole-grid file: served from it
+    assert c.grid_cache_hit and c.cache_hits == 0 and c.grid.snapshot_potential is None
+    assert np.array_equal(c.grid.snapshot_acceleration_x, a.grid.snapshot_acceleration_x)
 
 
 @pytest.mark.parametrize("graph", [False, True])

@@ -120,7 +120,7 @@ def test_field_direct_edge_cases(ctx):
 # Shape ids of the streaming kernel (direct_sum.cu table; stable across builds).  The shipped library carries only the
 # production shapes; the sweep shapes and the timing experiments live in the separate OCG_TUNING build (tools/probe.py).
 PRODUCTION_PLAIN = [1, 4, 27, 31]      # SMALL, MID_GUARD, MID, BIG (plain tiles: K4, and K1 with mass folding off)
-PRODUCTION_MF_POT = [74, 77]           # BIG_MF_POT, MID_MF (mass-folded tiles, with or without potential)
+PRODUCTION_MF_POT = [74, 80]           # BIG_MF_POT, MID_MF (mass-folded tiles, with or without potential)
 PRODUCTION_MASS_FOLDED = [67] + PRODUCTION_MF_POT  # 67 = BIG_MF (no potential form)
 TIMING_EXPERIMENTS = list(range(37, 40)) + list(range(48, 58))  # wrong results by construction
 
@@ -164,6 +164,8 @@ def test_knobs_are_per_context():
     tgt = grid_targets(41)
     a, b = Context(0), Context(0)
     try:
+        for c in (a, b):
+            c.debug_set("precise_near", 0)  # 2100 sources would all fit the FP64 precision-radius set: keep them in the FP32 tiles
         a.debug_set("mass_fold", 0)
         ra, _ = run_k1(a, src, soft, tgt, oracle.KERNEL_PLUMMER)
         rb, _ = run_k1(b, src, soft, tgt, oracle.KERNEL_PLUMMER)
@@ -229,6 +231,7 @@ def test_field_direct_production_big_is_mass_folded(ctx):
     tgt = grid_targets(41)
     ref, pref = oracle.field_direct(src, soft, tgt, oracle.KERNEL_PLUMMER, G, want_pot=True)
     cond = oracle.field_direct_abs(src, soft, tgt, oracle.KERNEL_PLUMMER, G)
+    ctx.debug_set("near_cap", 64)  # 2100 sources would all fit the FP64 precision-radius set: keep most in the FP32 tiles
     a_mf, _ = run_k1(ctx, src, soft, tgt, oracle.KERNEL_PLUMMER, want_pot=False)
     a_mp, pot = run_k1(ctx, src, soft, tgt, oracle.KERNEL_PLUMMER, want_pot=True)
     assert rel_err(a_mf, ref, abs_sum=cond) <= TOL and rel_err(a_mp, ref, abs_sum=cond) <= TOL
@@ -239,6 +242,7 @@ def test_field_direct_production_big_is_mass_folded(ctx):
         a_pl, pot_pl = run_k1(ctx, src, soft, tgt, oracle.KERNEL_PLUMMER, want_pot=True)
     finally:
         ctx.debug_set("mass_fold", 1)
+        ctx.debug_set("near_cap", 0)
     assert np.array_equal(a_off, a_pl)     # mass folding off: the plain-tile kernel, potential or not
     assert not np.array_equal(a_mf, a_pl)  # two different kernels really ran
     assert rel_err(a_pl, ref, abs_sum=cond) <= TOL and rel_err_scalar(pot_pl, pref) <= TOL

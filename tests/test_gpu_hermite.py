@@ -217,6 +217,64 @@ def test_bridge_with_hermite_cluster_eager_equals_cuda_graph(ctx):
     assert np.max(np.abs(out[0][1] - out[1][1])) <= 1e-12 * 220.0
 
 
+def test_block_time_steps_equal_level_limit_is_the_shared_step_scheme(ctx):
+    """ocg_hermite_block_evolve with every star forced onto the smallest step (eta -> 0) takes exactly 2^k block steps of n
+    stars and reproduces cluster_code's shared-step Hermite run with substeps = 2^k (same force kernel, same predictor /
+    corrector arithmetic; the force over 'active targets x all sources' walks the tiles in another order, so equal to FP64
+    rounding of the sums)."""
+    from oc_nbody_b200.cluster import cluster_code
+    from oc_nbody_b200.units import units
+    n, k, span = 5000, 3, 0.02
+    pos, vel, mass = cluster(n, seed=12)
+    shared = cluster_code(mass, pos, vel, softening_pc=0.01, substeps=2 ** k, ctx=ctx, integrator="hermite")
+    shared.evolve_model(span | units.Myr)
+    block = cluster_code(mass, pos, vel, softening_pc=0.01, ctx=ctx, integrator="hermite", block_steps=True, eta=1e-12, max_level=k)
+    block.evolve_model(span | units.Myr)
+    assert block.block_step_count == 2 ** k and block.star_step_count == n * 2 ** k
+    xs, vs, xb, vb = (t.cpu().numpy() for t in (shared.pos, shared.vel, block.pos, block.vel))
+    assert np.max(np.abs(xb - xs)) <= 1e-15 * 8.0 * 4 and np.max(np.abs(vb - vs)) <= 1e-13 * np.max(np.abs(vs))
+
+
+def test_block_time_steps_match_the_oracle_and_save_work(ctx):
+    """A 400-star cluster with a hard binary in it: the GPU block-step run against the oracle's (FP64 forces; same schedule
+    arithmetic).  The binary sits on steps hundreds of times shorter than the bulk, so the star-steps taken are a small
+    fraction of what one shared step of the smallest size would cost; energy is conserved to the scheme's accuracy."""
+    from oc_nbody_b200.cluster import KMS_TO_KPC_PER_MYR, cluster_code
+    from oc_nbody_b200.units import units
+    n, span, eta, max_level = 400, 0.05, 0.02, 14
+    pos, vel, mass = cluster(n, seed=21)
+    # hard binary: stars 0 and 1 at 40 AU-ish (2e-4 pc) on a circular orbit about their barycentre
+    sep = 2e-7  # kpc
+    pos[:, 1] = pos[:, 0] + np.array([sep, 0.0, 0.0])
+    vc = np.sqrt(G * (mass[0] + mass[1]) / sep / KMS_TO_KPC_PER_MYR)  # km/s
+    vel[:, 1] = vel[:, 0] + np.array([0.0, vc, 0.0])
+    eps2 = (1e-5 * 1e-3) ** 2   # 1e-5 pc softening: the binary is resolved
+    cl = cluster_code(mass, pos, vel, softening_pc=1e-5, ctx=ctx, integrator="hermite", block_steps=True, eta=eta, max_level=max_level)
+
+    def energy(x, v):
+        _, _, pot = oracle.self_gravity_hermite(x, v, mass, eps2, G, VTL, want_pot=True)
+        vv = v - (v * mass).sum(axis=1, keepdims=True) / mass.sum()
+        return float((0.5 * mass * (vv * vv).sum(axis=0)).sum() + 0.5 * (mass * pot).sum() / KMS_TO_KPC_PER_MYR)
+    e0 = energy(pos, vel)
+    cl.evolve_model(span | units.Myr)
+    x, v = cl.pos.cpu().numpy(), cl.vel.cpu().numpy()
+    xo, vo, _, _, steps_o, star_o = oracle.hermite_block_evolve(pos, vel, mass, eps2, G, span, VTL, eta, max_level)
+    # the schedules agree to a few per cent (FP32 pair arithmetic can move a borderline step choice), far below a shared step's cost
+    assert abs(cl.block_step_count - steps_o) <= 0.05 * steps_o and abs(cl.star_step_count - star_o) <= 0.05 * star_o
+    smallest = span / 2 ** max_level
+    assert cl.block_step_count > 50 and cl.star_step_count < 0.05 * n * (span / smallest)
+    # single stars follow the oracle closely; the binary's phase is the sensitive quantity (hundreds of orbits): compare its
+    # barycentre and separation instead
+    rest = np.arange(2, n)
+    assert np.max(np.abs(x[:, rest] - xo[:, rest])) <= 1e-5 * np.max(np.abs(xo[:, rest] - pos[:, rest]))
+    bc = lambda q: (q[:, 0] * mass[0] + q[:, 1] * mass[1]) / (mass[0] + mass[1])  # noqa: E731
+    assert np.max(np.abs(bc(x) - bc(xo))) <= 1e-5 * np.max(np.abs(bc(xo) - bc(pos)))
+    assert abs(np.linalg.norm(x[:, 1] - x[:, 0]) - sep) <= 2e-2 * sep
+    assert abs(energy(x, v) - e0) <= 2e-4 * abs(e0)
+    with pytest.raises(ValueError):
+        cluster_code(mass, pos, vel, ctx=ctx, block_steps=True)
+
+
 def test_fullsize_65536_third_law_and_rows(ctx):
     """configs[2] size: N = 65 536.  Newton's third law for the acceleration AND the jerk (sum m a = sum m j = 0 up to
     rounding), and 150 rows against the oracle over all sources."""
