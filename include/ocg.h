@@ -239,6 +239,20 @@ int ocg_grid_interp_rbf(ocg_ctx* ctx, const ocg_grid_desc* grid, const double* f
                         double* tensor_out_dev, int32_t* status_out_dev, int64_t* neighbors_out_dev,
                         void* stream);
 
+/* The same interpolant on the reference's NESTED grid with BOTH levels searched (its default configuration,
+ * test_options:93-100): the point list is kept coarse points | fine lattice | origin row (grid_cartesian.py:71-91), and a
+ * star within a few fine cells of the fine-box surface has neighbours on both levels.  `coarse` / `fine`: the two lattices
+ * (same n_cluster and origin_dev); coarse_row_dev int32 [ncx*ncy*ncz]: the row of each coarse lattice node in the point
+ * list, -1 for the nodes the reference dropped; fine_row0: first fine row; field_dev fp64 [n_comp][n_cluster][n_point]
+ * over the WHOLE point list; neighbors_out_dev receives point-list rows.  Other arguments as ocg_grid_interp_rbf.
+ * Stars too far outside the grid for nclose points to be found get NaN and status bit 0.                          */
+int ocg_grid_interp_rbf_nested(ocg_ctx* ctx, const ocg_grid_desc* coarse, const ocg_grid_desc* fine,
+                               const int32_t* coarse_row_dev, int64_t fine_row0, int64_t n_point, const double* field_dev,
+                               int32_t n_comp, int32_t nclose, int32_t order, int32_t phs, int32_t include_origin,
+                               const double* star_x_dev, const double* star_y_dev, const double* star_z_dev,
+                               const int32_t* star_cluster_dev, int64_t n_star, double* out_dev, double* tensor_out_dev,
+                               int32_t* status_out_dev, int64_t* neighbors_out_dev, void* stream);
+
 /* K2 pack with a scatter: rec[index[i]] = float4(acc[0][i], acc[1][i], acc[2][i], pot[i]) for i < n.
  * Lays rows of the reference's point list (kept coarse points | fine lattice | origin row,
  * grid_cartesian.py:71-91) out as full-lattice node records.  acc_dev fp64 [3][n]; pot_dev [n] or NULL;

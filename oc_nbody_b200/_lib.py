@@ -22,7 +22,7 @@ ABI_SYMBOLS = [
     "ocg_version", "ocg_create", "ocg_destroy", "ocg_last_error", "ocg_device_info", "ocg_launch_count", "ocg_capture_epoch",
     "ocg_last_direct_kernel_ms", "ocg_set_kernel_timing", "ocg_last_direct_traffic_bytes", "ocg_recentre_f64", "ocg_cast_f64_f32", "ocg_assemble_sources",
     "ocg_field_direct", "ocg_frame_subtract", "ocg_field_build_host", "ocg_pack_planes", "ocg_grid_time_blend",
-    "ocg_grid_interp", "ocg_grid_interp_multi", "ocg_grid_interp_nested", "ocg_pack_planes_indexed", "ocg_set_interp_weight_slots", "ocg_grid_interp_slot", "ocg_grid_interp_rbf", "ocg_self_gravity", "ocg_self_gravity_hermite", "ocg_hermite_predict", "ocg_hermite_correct", "ocg_hermite_block_evolve", "ocg_bound_com", "ocg_eject_mask", "ocg_compact_rows", "ocg_kick", "ocg_drift", "ocg_axpy", "ocg_probe_throughput", "ocg_comm_create", "ocg_comm_connect", "ocg_comm_destroy", "ocg_comm_info", "ocg_comm_status", "ocg_comm_allreduce_f64", "ocg_self_gravity_sharded",
+    "ocg_grid_interp", "ocg_grid_interp_multi", "ocg_grid_interp_nested", "ocg_pack_planes_indexed", "ocg_set_interp_weight_slots", "ocg_grid_interp_slot", "ocg_grid_interp_rbf", "ocg_grid_interp_rbf_nested", "ocg_self_gravity", "ocg_self_gravity_hermite", "ocg_hermite_predict", "ocg_hermite_correct", "ocg_hermite_block_evolve", "ocg_bound_com", "ocg_eject_mask", "ocg_compact_rows", "ocg_kick", "ocg_drift", "ocg_axpy", "ocg_probe_throughput", "ocg_comm_create", "ocg_comm_connect", "ocg_comm_destroy", "ocg_comm_info", "ocg_comm_status", "ocg_comm_allreduce_f64", "ocg_self_gravity_sharded",
 ]
 
 
@@ -91,6 +91,7 @@ def load_library():
                                        i64, vp, vp, vp]
     L.ocg_self_gravity.argtypes = [vp, vp, vp, i64, vp, i32, dbl, dbl, i64, i64, vp, vp, vp]
     L.ocg_grid_interp_rbf.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp, i64, vp, vp, vp, vp, vp]
+    L.ocg_grid_interp_rbf_nested.argtypes = [vp, vp, vp, vp, i64, i64, vp, i32, i32, i32, i32, i32, vp, vp, vp, vp, i64, vp, vp, vp, vp, vp]
     L.ocg_self_gravity_hermite.argtypes = [vp, vp, vp, vp, i64, vp, i32, dbl, dbl, dbl, i64, i64, vp, vp, vp, vp]
     L.ocg_hermite_predict.argtypes = [vp, vp, vp, vp, vp, i64, dbl, dbl, vp, vp, vp]
     L.ocg_hermite_correct.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, dbl, dbl, dbl, vp, vp]
@@ -315,6 +316,18 @@ class Context:
                                               int(phs), 1 if include_origin else 0, 1 if embedded else 0, _dptr(sx), _dptr(sy), _dptr(sz),
                                               _dptr(star_cluster), sx.shape[0], _dptr(out), _dptr(tensor_out), _dptr(status_out),
                                               _dptr(neighbors_out), self._stream()), "ocg_grid_interp_rbf")
+
+    def grid_interp_rbf_nested(self, n, nodes, fine_n, fine_nodes, origin, coarse_row, fine_row0, field, sx, sy, sz, star_cluster, out,
+                               nclose=150, order=5, phs=3, include_origin=True, tensor_out=None, status_out=None, neighbors_out=None):
+        """K7 on the reference's nested grid, both levels searched (mixed-level stencils near the fine-box surface).
+        field fp64 [n_comp, n_cluster * n_point] over the whole point list; coarse_row int32 [n_coarse_lattice]."""
+        dc, df = self._grid_desc(n, nodes, origin), self._grid_desc(fine_n, fine_nodes, origin)
+        n_point = field.shape[1] // int(origin.shape[0])
+        self._ck(self.lib.ocg_grid_interp_rbf_nested(self.h, ctypes.byref(dc), ctypes.byref(df), _dptr(coarse_row), int(fine_row0),
+                                                     int(n_point), _dptr(field), int(field.shape[0]), int(nclose), int(order), int(phs),
+                                                     1 if include_origin else 0, _dptr(sx), _dptr(sy), _dptr(sz), _dptr(star_cluster),
+                                                     sx.shape[0], _dptr(out), _dptr(tensor_out), _dptr(status_out), _dptr(neighbors_out),
+                                                     self._stream()), "ocg_grid_interp_rbf_nested")
 
     def set_interp_weight_slots(self, weights, first_slot=0):
         """weights: sequence of up-to-4-element weight lists, written to constant-memory slots first_slot.. (stream-ordered)."""

@@ -27,7 +27,8 @@
 #define RBF_NRHS_MAX 4
 #define RBF_THREADS 256
 #define RBF_MAXIT 12
-#define RBF_CAND_MAX 4097 /* 16^3 lattice nodes + the origin row */
+#define RBF_CAND_MAX 4609 /* 16^3 lattice nodes + the origin row + an 8^3 window of the coarse level (nested grid) */
+#define RBF_FAR 1e300     /* distance^2 of a candidate slot that holds no point */
 #define RBF_NPHASE 6
 #define RBF_LDA 212 /* column stride of the factor matrix: a multiple of 4 (16-byte aligned column segments for LDS.128), 4-way
                         bank conflicts only on the O(N^2) row-wise accesses */
@@ -41,6 +42,14 @@ struct RbfParams {
   const double* field;    // [n_comp][n_cluster][n_node]
   long long comp_stride;  // n_cluster * n_node
   int n_comp, nclose, nmono, order, phs, include_origin, want_tensor, embedded;
+  // nested grid, both levels searched (ocg_grid_interp_rbf_nested): `n`/`node` describe the FINE lattice; the kept coarse
+  // points (grid_cartesian.py:71-81) are candidates too.  Rows of the reference's point list: kept coarse | fine | origin.
+  int mixed;
+  int cn[3];
+  const double* cnode[3];
+  const int* coarse_row;  // [cn0*cn1*cn2] row of a coarse lattice node in the point list, -1 = dropped (inside the fine box)
+  long long fine_row0;    // first fine row
+  long long n_point;      // rows of the point list (row stride of `field` per cluster)
   const double *sx, *sy, *sz;
   const int* scl;
   long long n_star;
@@ -114,14 +123,14 @@ __global__ void __launch_bounds__(RBF_THREADS, 1) rbf_interp_kernel(const RbfPar
   int* nbc = reinterpret_cast<int*>(q);                      // candidate ordinal of the m-th neighbour
   q += sizeof(int) * ncl;
   int* perm = reinterpret_cast<int*>(q);                     // row permutation of the factorisation
-  __shared__ int s_lo[3], s_cnt[3], s_cell[3], s_flag, s_conv[RBF_NRHS_MAX], s_C, s_pv[RBF_NB];
+  __shared__ int s_lo[3], s_cnt[3], s_cell[3], s_flag, s_conv[RBF_NRHS_MAX], s_C, s_pv[RBF_NB], s_clo[3], s_ccnt[3];
   __shared__ unsigned s_wkey[RBF_THREADS / 32];
   __shared__ __align__(16) float s_prow[2][RBF_NB];
   __shared__ double s_p[3], s_o[3], s_h, s_r2max, s_zprev[RBF_NRHS_MAX];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nrhs = p.want_tensor ? 4 : 1;
-  const long long n_node = (long long)p.n[0] * p.n[1] * p.n[2] + 1;
+  const long long n_node = p.mixed ? p.n_point : (long long)p.n[0] * p.n[1] * p.n[2] + 1;
 #ifdef OCG_TUNING
   long long t_phase = clock64();
   auto phase_done = [&](int which) {
@@ -150,6 +159,7 @@ __global__ void __launch_bounds__(RBF_THREADS, 1) rbf_interp_kernel(const RbfPar
       s_h = h;
     }
     __syncthreads();
+    // candidate order = point-list order (ties go to the lower row, as cKDTree's do): coarse window | fine window | origin
 
     // ---- 1. the nclose nearest grid points --------------------------------------------------------------
     for (int W = 8;; W += 4) {
@@ -163,14 +173,35 @@ __global__ void __launch_bounds__(RBF_THREADS, 1) rbf_interp_kernel(const RbfPar
           s_lo[d] = lo, s_cnt[d] = cnt;
           C *= cnt;
         }
-        s_C = C + (p.include_origin ? 1 : 0);
+        int CC = p.mixed ? 1 : 0;
+        for (int d = 0; d < 3; ++d) {
+          s_clo[d] = 0, s_ccnt[d] = 0;
+          if (p.mixed) {  // W/2 coarse nodes per axis around the star (4, 6, 8): grows with the fine window
+            const int cc = rbf_find_cell(p.cnode[d], p.cn[d], s_o[d], s_p[d]);
+            const int cnt = p.cn[d] < W / 2 ? p.cn[d] : W / 2;
+            int lo = cc - (W / 4 - 1);
+            if (lo > p.cn[d] - cnt) lo = p.cn[d] - cnt;
+            if (lo < 0) lo = 0;
+            s_clo[d] = lo, s_ccnt[d] = cnt;
+            CC *= cnt;
+          }
+        }
+        s_C = CC + C + (p.include_origin ? 1 : 0);
       }
       __syncthreads();
+      const int Cc = s_ccnt[0] * s_ccnt[1] * s_ccnt[2];
       const int C = s_C, cy = s_cnt[1], cz = s_cnt[2], Clat = s_cnt[0] * cy * cz;
       for (int c = tid; c < C; c += RBF_THREADS) {
         double qx, qy, qz;
-        if (c < Clat) {
-          const int ix = c / (cy * cz), iy = (c / cz) % cy, iz = c % cz;
+        bool present = true;
+        if (c < Cc) {  // a node of the coarse level: a point of the list only if it was kept
+          const int ccy = s_ccnt[1], ccz = s_ccnt[2];
+          const int ix = s_clo[0] + c / (ccy * ccz), iy = s_clo[1] + (c / ccz) % ccy, iz = s_clo[2] + c % ccz;
+          present = p.coarse_row[((long long)ix * p.cn[1] + iy) * p.cn[2] + iz] >= 0;
+          qx = __dadd_rn(p.cnode[0][ix], s_o[0]), qy = __dadd_rn(p.cnode[1][iy], s_o[1]), qz = __dadd_rn(p.cnode[2][iz], s_o[2]);
+        } else if (c < Cc + Clat) {
+          const int f = c - Cc;
+          const int ix = f / (cy * cz), iy = (f / cz) % cy, iz = f % cz;
           qx = __dadd_rn(p.node[0][s_lo[0] + ix], s_o[0]);
           qy = __dadd_rn(p.node[1][s_lo[1] + iy], s_o[1]);
           qz = __dadd_rn(p.node[2][s_lo[2] + iz], s_o[2]);
@@ -178,8 +209,9 @@ __global__ void __launch_bounds__(RBF_THREADS, 1) rbf_interp_kernel(const RbfPar
           qx = s_o[0], qy = s_o[1], qz = s_o[2];  // the appended origin row (grid_cartesian.py:66-67)
         }
         const double dx = __dadd_rn(qx, -s_p[0]), dy = __dadd_rn(qy, -s_p[1]), dz = __dadd_rn(qz, -s_p[2]);
-        cand[c] = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+        cand[c] = present ? __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz)) : RBF_FAR;
       }
+      if (tid == 0) s_r2max = RBF_FAR;  // stays there when the window holds fewer than nclose points: the window grows
       __syncthreads();
       for (int c = tid; c < C; c += RBF_THREADS) {
         const double key = cand[c];
@@ -204,6 +236,18 @@ __global__ void __launch_bounds__(RBF_THREADS, 1) rbf_interp_kernel(const RbfPar
           ok = ok && (b > 0.0 && b * b > s_r2max);
         }
       }
+      if (p.mixed) {  // ... nor a coarse node beyond its window
+        for (int d = 0; d < 3; ++d) {
+          if (s_clo[d] > 0) {
+            const double b = s_p[d] - (p.cnode[d][s_clo[d] - 1] + s_o[d]);
+            ok = ok && (b > 0.0 && b * b > s_r2max);
+          }
+          if (s_clo[d] + s_ccnt[d] < p.cn[d]) {
+            const double b = (p.cnode[d][s_clo[d] + s_ccnt[d]] + s_o[d]) - s_p[d];
+            ok = ok && (b > 0.0 && b * b > s_r2max);
+          }
+        }
+      }
       if (ok) break;
       if (W >= 16) {
         status |= 1;  // stencil truncated: the star is too far outside the grid for a 16-node window
@@ -211,7 +255,18 @@ __global__ void __launch_bounds__(RBF_THREADS, 1) rbf_interp_kernel(const RbfPar
       }
       __syncthreads();
     }
-    if (p.embedded) {
+    if (!(s_r2max < RBF_FAR)) {
+      // fewer than nclose points within reach (a star far outside the grid): no stencil, no value
+      for (int e = tid; e < p.n_comp; e += RBF_THREADS) {
+        p.out[(long long)e * p.n_star + s] = __longlong_as_double(0x7ff8000000000000ll);
+        if (p.tensor)
+          for (int r = 0; r < 3; ++r) p.tensor[((long long)r * p.n_comp + e) * p.n_star + s] = __longlong_as_double(0x7ff8000000000000ll);
+      }
+      if (tid == 0 && p.status) p.status[s] = status | 1;
+      __syncthreads();
+      continue;
+    }
+    if (p.embedded && !p.mixed) {
       // the lattice is the fine level of the reference's nested grid: every kept coarse point lies on or outside the
       // fine box, so the neighbours are all fine points iff the nclose-th one is closer than the box surface
       bool inside = true;
@@ -224,15 +279,21 @@ __global__ void __launch_bounds__(RBF_THREADS, 1) rbf_interp_kernel(const RbfPar
     }
     // coordinates of the neighbours, shifted to the star and scaled by the spacing, and their powers
     {
-      const int cy = s_cnt[1], cz = s_cnt[2], Clat = s_cnt[0] * cy * cz;
+      const int cy = s_cnt[1], cz = s_cnt[2], Clat = s_cnt[0] * cy * cz, Cc = s_ccnt[0] * s_ccnt[1] * s_ccnt[2];
       for (int m = tid; m < ncl; m += RBF_THREADS) {
         const int c = nbc[m];
         double qd[3];
         long long gi;
-        if (c < Clat) {
-          const int ix = s_lo[0] + c / (cy * cz), iy = s_lo[1] + (c / cz) % cy, iz = s_lo[2] + c % cz;
+        if (c < Cc) {
+          const int ccy = s_ccnt[1], ccz = s_ccnt[2];
+          const int ix = s_clo[0] + c / (ccy * ccz), iy = s_clo[1] + (c / ccz) % ccy, iz = s_clo[2] + c % ccz;
+          qd[0] = __dadd_rn(p.cnode[0][ix], s_o[0]), qd[1] = __dadd_rn(p.cnode[1][iy], s_o[1]), qd[2] = __dadd_rn(p.cnode[2][iz], s_o[2]);
+          gi = p.coarse_row[((long long)ix * p.cn[1] + iy) * p.cn[2] + iz];
+        } else if (c < Cc + Clat) {
+          const int f = c - Cc;
+          const int ix = s_lo[0] + f / (cy * cz), iy = s_lo[1] + (f / cz) % cy, iz = s_lo[2] + f % cz;
           qd[0] = __dadd_rn(p.node[0][ix], s_o[0]), qd[1] = __dadd_rn(p.node[1][iy], s_o[1]), qd[2] = __dadd_rn(p.node[2][iz], s_o[2]);
-          gi = ((long long)ix * p.n[1] + iy) * p.n[2] + iz;
+          gi = (p.mixed ? p.fine_row0 : 0) + ((long long)ix * p.n[1] + iy) * p.n[2] + iz;
         } else {
           qd[0] = s_o[0], qd[1] = s_o[1], qd[2] = s_o[2];
           gi = n_node - 1;
@@ -594,6 +655,51 @@ extern "C" int ocg_debug_rbf_phase_cycles(ocg_ctx* ctx, double* out6) {
   return OCG_OK;
 }
 
+static int rbf_launch(ocg_ctx* ctx, const char* who, RbfParams& p, const ocg_grid_desc* grid, const double* field_dev, int32_t n_comp,
+                      int32_t nclose, int32_t order, int32_t phs, int32_t include_origin, const double* star_x_dev,
+                      const double* star_y_dev, const double* star_z_dev, const int32_t* star_cluster_dev, int64_t n_star,
+                      double* out_dev, double* tensor_out_dev, int32_t* status_out_dev, int64_t* neighbors_out_dev, void* stream) {
+  if (!field_dev || !star_x_dev || !star_y_dev || !star_z_dev || !out_dev || !grid->origin_dev)
+    return ocg_fail(ctx, OCG_ERR_INVALID, "%s: NULL argument", who);
+  if (n_comp < 1 || n_comp > 4) return ocg_fail(ctx, OCG_ERR_INVALID, "%s: n_comp = %d outside [1,4]", who, n_comp);
+  if (order < 0 || order > 5) return ocg_fail(ctx, OCG_ERR_INVALID, "%s: order = %d outside [0,5]", who, order);
+  if (phs != 1 && phs != 3 && phs != 5 && phs != 7)
+    return ocg_fail(ctx, OCG_ERR_INVALID, "%s: basis phs%d not supported (odd polyharmonic splines phs1/3/5/7)", who, phs);
+  if (order < (phs - 1) / 2)
+    return ocg_fail(ctx, OCG_ERR_INVALID, "%s: phs%d needs order >= %d to be well posed", who, phs, (phs - 1) / 2);
+  int nm = 0;
+  // monomials of total degree <= order, by degree
+  for (int d = 0; d <= order; ++d)
+    for (int a = d; a >= 0; --a)
+      for (int b = d - a; b >= 0; --b) p.pw[nm][0] = (unsigned char)a, p.pw[nm][1] = (unsigned char)b, p.pw[nm][2] = (unsigned char)(d - a - b), ++nm;
+  if (nclose < nm || nclose + nm > RBF_NMAX)
+    return ocg_fail(ctx, OCG_ERR_INVALID, "%s: nclose = %d must lie in [%d, %d] for order %d", who, nclose, nm, RBF_NMAX - nm, order);
+  long long n_lat = 1;
+  for (int d = 0; d < 3; ++d) {
+    if (grid->n[d] < 2 || !grid->node_dev[d]) return ocg_fail(ctx, OCG_ERR_INVALID, "%s: bad grid axis %d", who, d);
+    p.n[d] = grid->n[d], p.node[d] = grid->node_dev[d];
+    n_lat *= grid->n[d];
+  }
+  if (!p.mixed && n_lat + (include_origin ? 1 : 0) < nclose)
+    return ocg_fail(ctx, OCG_ERR_INVALID, "%s: the grid has fewer than nclose = %d points", who, nclose);
+  p.n_cluster = grid->n_cluster < 1 ? 1 : grid->n_cluster;
+  p.origin = grid->origin_dev, p.field = field_dev;
+  p.comp_stride = (long long)p.n_cluster * (p.mixed ? p.n_point : n_lat + 1);
+  p.n_comp = n_comp, p.nclose = nclose, p.nmono = nm, p.order = order, p.phs = phs, p.include_origin = include_origin ? 1 : 0;
+  p.want_tensor = tensor_out_dev ? 1 : 0;
+  p.sx = star_x_dev, p.sy = star_y_dev, p.sz = star_z_dev, p.scl = star_cluster_dev, p.n_star = n_star;
+  p.out = out_dev, p.tensor = tensor_out_dev, p.status = status_out_dev, p.nb_out = (long long*)neighbors_out_dev;
+  OcgDeviceGuard g(ctx->device);
+  const size_t smem = rbf_smem_bytes(nclose + nm, nclose, order + 1);
+  if (smem > 227 * 1024)
+    return ocg_fail(ctx, OCG_ERR_INVALID, "%s: nclose = %d, order = %d need %zu bytes of shared memory", who, nclose, order, smem);
+  OCG_CUDA(ctx, cudaFuncSetAttribute((const void*)rbf_interp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int grid_dim = (int)(n_star < ctx->sm_count ? n_star : ctx->sm_count);
+  rbf_interp_kernel<<<grid_dim, RBF_THREADS, smem, (cudaStream_t)stream>>>(p);
+  OCG_CHECK_LAUNCH(ctx, "rbf_interp_kernel");
+  return OCG_OK;
+}
+
 extern "C" int ocg_grid_interp_rbf(ocg_ctx* ctx, const ocg_grid_desc* grid, const double* field_dev, int32_t n_comp,
                                    int32_t nclose, int32_t order, int32_t phs, int32_t include_origin, int32_t embedded,
                                    const double* star_x_dev, const double* star_y_dev, const double* star_z_dev,
@@ -602,46 +708,36 @@ extern "C" int ocg_grid_interp_rbf(ocg_ctx* ctx, const ocg_grid_desc* grid, cons
   if (!ctx) return OCG_ERR_INVALID;
   if (!grid || n_star < 0) return ocg_fail(ctx, OCG_ERR_INVALID, "ocg_grid_interp_rbf: bad arguments");
   if (n_star == 0) return OCG_OK;
-  if (!field_dev || !star_x_dev || !star_y_dev || !star_z_dev || !out_dev || !grid->origin_dev)
-    return ocg_fail(ctx, OCG_ERR_INVALID, "ocg_grid_interp_rbf: NULL argument");
-  if (n_comp < 1 || n_comp > 4) return ocg_fail(ctx, OCG_ERR_INVALID, "ocg_grid_interp_rbf: n_comp = %d outside [1,4]", n_comp);
-  if (order < 0 || order > 5) return ocg_fail(ctx, OCG_ERR_INVALID, "ocg_grid_interp_rbf: order = %d outside [0,5]", order);
-  if (phs != 1 && phs != 3 && phs != 5 && phs != 7)
-    return ocg_fail(ctx, OCG_ERR_INVALID, "ocg_grid_interp_rbf: basis phs%d not supported (odd polyharmonic splines phs1/3/5/7)", phs);
-  if (order < (phs - 1) / 2)
-    return ocg_fail(ctx, OCG_ERR_INVALID, "ocg_grid_interp_rbf: phs%d needs order >= %d to be well posed", phs, (phs - 1) / 2);
   RbfParams p;
-  int nm = 0;
-  // monomials of total degree <= order, by degree
-  for (int d = 0; d <= order; ++d)
-    for (int a = d; a >= 0; --a)
-      for (int b = d - a; b >= 0; --b) p.pw[nm][0] = (unsigned char)a, p.pw[nm][1] = (unsigned char)b, p.pw[nm][2] = (unsigned char)(d - a - b), ++nm;
-  if (nclose < nm || nclose + nm > RBF_NMAX)
-    return ocg_fail(ctx, OCG_ERR_INVALID, "ocg_grid_interp_rbf: nclose = %d must lie in [%d, %d] for order %d", nclose, nm,
-                    RBF_NMAX - nm, order);
-  long long n_lat = 1;
-  for (int d = 0; d < 3; ++d) {
-    if (grid->n[d] < 2 || !grid->node_dev[d]) return ocg_fail(ctx, OCG_ERR_INVALID, "ocg_grid_interp_rbf: bad grid axis %d", d);
-    p.n[d] = grid->n[d], p.node[d] = grid->node_dev[d];
-    n_lat *= grid->n[d];
-  }
-  if (n_lat + (include_origin ? 1 : 0) < nclose)
-    return ocg_fail(ctx, OCG_ERR_INVALID, "ocg_grid_interp_rbf: the grid has fewer than nclose = %d points", nclose);
-  p.n_cluster = grid->n_cluster < 1 ? 1 : grid->n_cluster;
-  p.origin = grid->origin_dev, p.field = field_dev, p.comp_stride = (long long)p.n_cluster * (n_lat + 1);
-  p.n_comp = n_comp, p.nclose = nclose, p.nmono = nm, p.order = order, p.phs = phs, p.include_origin = include_origin ? 1 : 0;
-  p.want_tensor = tensor_out_dev ? 1 : 0;
+  memset(&p, 0, sizeof(p));
   p.embedded = embedded ? 1 : 0;
-  p.sx = star_x_dev, p.sy = star_y_dev, p.sz = star_z_dev, p.scl = star_cluster_dev, p.n_star = n_star;
-  p.out = out_dev, p.tensor = tensor_out_dev, p.status = status_out_dev, p.nb_out = (long long*)neighbors_out_dev;
-  OcgDeviceGuard g(ctx->device);
-  const size_t smem = rbf_smem_bytes(nclose + nm, nclose, order + 1);
-  if (smem > 227 * 1024)
-    return ocg_fail(ctx, OCG_ERR_INVALID, "ocg_grid_interp_rbf: nclose = %d, order = %d need %zu bytes of shared memory", nclose,
-                    order, smem);
-  OCG_CUDA(ctx, cudaFuncSetAttribute((const void*)rbf_interp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int grid_dim = (int)(n_star < ctx->sm_count ? n_star : ctx->sm_count);
-  rbf_interp_kernel<<<grid_dim, RBF_THREADS, smem, (cudaStream_t)stream>>>(p);
-  OCG_CHECK_LAUNCH(ctx, "rbf_interp_kernel");
-  return OCG_OK;
+  return rbf_launch(ctx, "ocg_grid_interp_rbf", p, grid, field_dev, n_comp, nclose, order, phs, include_origin, star_x_dev, star_y_dev,
+                    star_z_dev, star_cluster_dev, n_star, out_dev, tensor_out_dev, status_out_dev, neighbors_out_dev, stream);
+}
+
+extern "C" int ocg_grid_interp_rbf_nested(ocg_ctx* ctx, const ocg_grid_desc* coarse, const ocg_grid_desc* fine,
+                                          const int32_t* coarse_row_dev, int64_t fine_row0, int64_t n_point, const double* field_dev,
+                                          int32_t n_comp, int32_t nclose, int32_t order, int32_t phs, int32_t include_origin,
+                                          const double* star_x_dev, const double* star_y_dev, const double* star_z_dev,
+                                          const int32_t* star_cluster_dev, int64_t n_star, double* out_dev, double* tensor_out_dev,
+                                          int32_t* status_out_dev, int64_t* neighbors_out_dev, void* stream) {
+  if (!ctx) return OCG_ERR_INVALID;
+  if (!coarse || !fine || !coarse_row_dev || n_star < 0 || fine_row0 < 0 || n_point < 1)
+    return ocg_fail(ctx, OCG_ERR_INVALID, "ocg_grid_interp_rbf_nested: bad arguments");
+  if (n_star == 0) return OCG_OK;
+  RbfParams p;
+  memset(&p, 0, sizeof(p));
+  p.mixed = 1, p.embedded = 1;
+  long long n_fine = 1;
+  for (int d = 0; d < 3; ++d) {
+    if (coarse->n[d] < 2 || !coarse->node_dev[d]) return ocg_fail(ctx, OCG_ERR_INVALID, "ocg_grid_interp_rbf_nested: bad coarse axis %d", d);
+    p.cn[d] = coarse->n[d], p.cnode[d] = coarse->node_dev[d];
+    n_fine *= fine->n[d];
+  }
+  if (fine_row0 + n_fine + 1 != n_point)
+    return ocg_fail(ctx, OCG_ERR_INVALID, "ocg_grid_interp_rbf_nested: point list of %lld rows is not %lld kept coarse + %lld fine + origin",
+                    (long long)n_point, (long long)fine_row0, n_fine);
+  p.coarse_row = coarse_row_dev, p.fine_row0 = fine_row0, p.n_point = n_point;
+  return rbf_launch(ctx, "ocg_grid_interp_rbf_nested", p, fine, field_dev, n_comp, nclose, order, phs, include_origin, star_x_dev,
+                    star_y_dev, star_z_dev, star_cluster_dev, n_star, out_dev, tensor_out_dev, status_out_dev, neighbors_out_dev, stream);
 }

@@ -499,7 +499,7 @@ class gizmo_field(object):
         """FP64 [4, n_node] device array of the time-evaluated grid fields (grid.evolved_acceleration_x/y/z and the
         potential, gizmo_interface.py:618-620) that the RBF interpolant reads; refreshed when the model time changes.
         Single lattice, linear in time: blended on the device (K2) with no host round trip.  Cubic in time or nested
-        grid: the host-side blend, uploaded (nested: the fine rows + origin row of the point list, see _interp_rbf_)."""
+        grid: the host-side blend, uploaded (nested: over the reference's whole point list, see _interp_rbf_)."""
         import torch
         d, g = self._dev, self.grid
         if self.time_interpolation == "linear" and not g.has_fine_grid:
@@ -513,17 +513,15 @@ class gizmo_field(object):
             return self._rbf_cache[1]
         blend = self._blend_()
         if getattr(self, "_rbf_cache", None) is None or self._rbf_cache[0] is not blend:
-            f = np.concatenate([blend[0], blend[1][None]], axis=0)
-            if g.has_fine_grid:
-                f = f[:, g.fine_row0:]
+            f = np.concatenate([blend[0], blend[1][None]], axis=0)   # nested grid: the WHOLE point list (both levels are searched)
             self._rbf_cache = (blend, torch.from_numpy(np.ascontiguousarray(f)).to(d["device"]))
         return self._rbf_cache[1]
 
     def _interp_rbf_(self, sx, sy, sz, want_pot, want_tensor):
         """K7: kNN(nclose) + RBF-PHS on the device; the last status vector is kept in self.rbf_status (status & 0xff
-        == 0: good).  On the nested grid the search runs over the fine lattice + origin row: exact for every star whose
-        nclose-th neighbour is closer than the surface of the fine box (all kept coarse points lie on or outside it);
-        other stars are flagged with status bit 3."""
+        == 0: good).  On the nested grid the search runs over BOTH levels of the reference's point list (kept coarse points,
+        fine lattice, origin row): a star within a few fine cells of the fine-box surface gets the mixed-level stencil
+        cKDTree.query would give it (gizmo_interface.py:661-675 over grid_cartesian.py:71-91)."""
         import torch
         d, g = self._dev, self.grid
         n = sx.shape[0]
@@ -533,14 +531,33 @@ class gizmo_field(object):
         self.rbf_status = torch.empty(n, dtype=torch.int32, device=d["device"])
         shape, nodes_h, nodes_d = (g.fine_shape, g.fine_nodes, d["fine_nodes"]) if g.has_fine_grid else (g.shape, g.nodes, d["nodes"])
         dup = all(len(a) % 2 == 1 and a[len(a) // 2] == 0.0 for a in nodes_h)  # the origin row duplicates a lattice node
-        self.ctx.grid_interp_rbf(shape, nodes_d, d["origin"], f, sx, sy, sz, None, out, nclose=self.nclose,
-                                 order=self.order, phs=self._rbf_phs, include_origin=not dup, tensor_out=tensor,
-                                 status_out=self.rbf_status, embedded=g.has_fine_grid)
+        if g.has_fine_grid:
+            if "coarse_row" not in d:
+                row = np.full(int(np.prod(g.coarse_shape)), -1, np.int32)
+                row[g.coarse_keep_index] = np.arange(len(g.coarse_keep_index), dtype=np.int32)
+                d["coarse_row"] = torch.from_numpy(row).to(d["device"])
+            self.ctx.grid_interp_rbf_nested(g.coarse_shape, d["nodes"], g.fine_shape, d["fine_nodes"], d["origin"], d["coarse_row"],
+                                            g.fine_row0, f, sx, sy, sz, None, out, nclose=self.nclose, order=self.order,
+                                            phs=self._rbf_phs, include_origin=not dup, tensor_out=tensor, status_out=self.rbf_status)
+        else:
+            self.ctx.grid_interp_rbf(shape, nodes_d, d["origin"], f, sx, sy, sz, None, out, nclose=self.nclose,
+                                     order=self.order, phs=self._rbf_phs, include_origin=not dup, tensor_out=tensor,
+                                     status_out=self.rbf_status)
+        # stars without a good stencil (status & 0xff != 0: too far outside the grid, clipped / ill-conditioned stencil) are
+        # counted on the device; rbf_bad_count reads the count back on demand and get_gravity_at_point warns about it
+        self._rbf_bad = (self.rbf_status & 0xff).ne(0).sum()
         acc, pot = out[:3], (out[3] if want_pot else None)
         if want_tensor:
             # [3 (d/dx_i), 3 (a_j), n] -> [9, n] with row 3*i + j, as K3's tensor output
             return acc, pot, tensor[:, :3, :].reshape(9, n)
         return acc, pot
+
+    @property
+    def rbf_bad_count(self):
+        """Stars of the last RBF evaluation whose stencil was truncated, ill-conditioned or singular (their values are not
+        to be trusted; NaN when no stencil existed at all)."""
+        b = getattr(self, "_rbf_bad", None)
+        return 0 if b is None else int(b.item())
 
     def _interp_device_(self, sx, sy, sz, want_pot, want_tensor=False):
         """K3 on device tensors (FP64 kpc). Returns acc [3,n], pot [n] or None (, tensor [9,n]) device tensors."""
@@ -577,6 +594,9 @@ class gizmo_field(object):
         if not (xs[0].shape == xs[1].shape == xs[2].shape):
             raise ValueError("x, y, z must have the same length")
         acc, pot = self._interp_device_(xs[0], xs[1], xs[2], want_pot)
+        if self.space_interpolation == "rbf" and self.rbf_bad_count:
+            import warnings
+            warnings.warn("%d of %d points have no trustworthy RBF stencil (rbf_status & 0xff != 0)" % (self.rbf_bad_count, xs[0].shape[0]))
         acc = acc.cpu().numpy()
         pot = pot.cpu().numpy() if want_pot else None
         return scalar, acc, pot

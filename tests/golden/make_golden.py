@@ -98,7 +98,9 @@ def main():
     from scipy.interpolate import RBFInterpolator
     from scipy.spatial import cKDTree
     out = {}
-    rbf_cases = [((0.05, 0.05, 0.05, 0.05 / 16), None), ((0.06, 0.06, 0.06, 0.06 / 8), (0.012, 0.012, 0.012, 0.012 / 14))]
+    rbf_cases = [((0.05, 0.05, 0.05, 0.05 / 16), None), ((0.06, 0.06, 0.06, 0.06 / 8), (0.012, 0.012, 0.012, 0.012 / 14)),
+                 # coarse spacing ~2x the fine one: stars near the fine-box surface get well-conditioned MIXED-LEVEL stencils
+                 ((0.06, 0.06, 0.06, 0.06 / 24), (0.0135, 0.0135, 0.0135, 0.0135 / 12))]
     origin = np.array([8.0, -0.25, 0.125])
     for k, (cargs, fargs) in enumerate(rbf_cases):
         g = ref.grid(*cargs)
@@ -109,8 +111,18 @@ def main():
         x, y, z = ((pts - origin) * 40.0).T
         fields = np.stack([np.sin(x) + y * z, np.cos(y) * x - 0.2 * z, x * x - z + 0.3 * y ** 3])   # ax, ay, az stand-ins
         rng = np.random.default_rng(1776 + k)
-        half = 0.012 if fargs is None else 0.0035
+        half = 0.012 if fargs is None else (0.0035 if k == 1 else 0.006)
         stars = origin + rng.uniform(-half, half, (24, 3))
+        if k == 2:
+            # MIXED-LEVEL stencils: stars within a few fine cells of the fine-box surface (inside and outside it), whose 150
+            # nearest points come from both the fine lattice and the kept coarse points (grid_cartesian.py:71-91)
+            L, hf = fargs[0], 2 * fargs[0] / (g.x_n - 1)
+            stars = stars[:8]
+            near = np.array([[L - 0.4 * hf, 0.3 * hf, -0.2 * hf], [-(L - 1.7 * hf), L - 0.9 * hf, 0.0], [L + 0.6 * hf, 0.1 * hf, 0.2 * hf],
+                             [L - 0.2 * hf, L - 0.3 * hf, L - 0.1 * hf], [0.5 * hf, -(L + 1.5 * hf), 2.2 * hf],
+                             [L - 2.5 * hf, -3.1 * hf, L - 0.5 * hf], [-(L + 0.2 * hf), -(L + 0.3 * hf), 0.4 * hf],
+                             [L + 2.0 * hf, L + 1.0 * hf, -(L + 0.5 * hf)]])
+            stars = np.concatenate([stars, origin + near])
         tree = cKDTree(pts)                                    # gizmo_interface.py:642
         _, ids = tree.query(stars, 150)                        # :654,664
         vals = np.empty((3, len(stars)))

@@ -95,4 +95,4 @@ def test_rbf_oracle_matches_the_golden_fixture():
         assert np.array_equal(np.sort(res["neighbors"].T, axis=1), nbr)
         assert np.max(np.abs(res["out"] - vals) / np.abs(vals).max(axis=1, keepdims=True)) <= 1e-9
         n += 1
-    assert n == 2
+    assert n == 3

@@ -200,8 +200,8 @@ def test_field_code_rbf_mode_matches_oracle_and_drives_the_bridge(ctx):
 
 def test_field_code_rbf_on_the_nested_grid(ctx):
     """The reference's default grid (coarse lattice with a fine lattice nested around the cluster, test_options:93-100):
-    the RBF search over the fine lattice + origin row equals the search over the reference's whole point list
-    (kept coarse + fine + origin) for stars inside the fine box; a star near its surface is flagged."""
+    the RBF kick searches both levels of the reference's point list (kept coarse + fine + origin) — also for a star beyond
+    the fine-box surface, whose stencil mixes the levels."""
     from oc_nbody_b200.gizmo_field import gizmo_field
     from oc_nbody_b200.synthetic import advance_snapshot, make_snapshot
     from oc_nbody_b200.units import units
@@ -211,42 +211,52 @@ def test_field_code_rbf_on_the_nested_grid(ctx):
     opts = dict(grid_x_size_in_kpc=0.06, grid_y_size_in_kpc=0.06, grid_z_size_in_kpc=0.06, grid_resolution=0.06 / 8, fine_grid=True,
                 grid_fine_x_size_in_kpc=0.012, grid_fine_y_size_in_kpc=0.012, grid_fine_z_size_in_kpc=0.012,
                 grid_fine_resolution=0.012 / 14, space_interpolation="rbf")
+    opts.update(grid_resolution=0.06 / 24, grid_fine_x_size_in_kpc=0.0135, grid_fine_y_size_in_kpc=0.0135, grid_fine_z_size_in_kpc=0.0135,
+                grid_fine_resolution=0.0135 / 12)   # coarse spacing ~2x the fine one: well-conditioned mixed-level stencils
     field = gizmo_field(opts, snaps, chosen_positions=np.tile(center, (2, 1)), ctx=ctx)
     field.evolve_grid(center)
     field.evolve_model(11.0 | units.Myr)
     g = field.grid
     assert g.has_fine_grid
     rng = np.random.default_rng(8)
-    p = center + rng.uniform(-0.004, 0.004, (12, 3))
-    p[-1] = center + np.array([0.0115, 0.0, 0.0])  # half a fine cell from the surface of the fine box: mixed-level stencil
+    p = center + rng.uniform(-0.002, 0.002, (12, 3))
+    p[-1] = center + np.array([0.0145, 0.0003, -0.0002])  # just beyond the surface of the fine box: mixed-level stencil
     ax, ay, az = field.get_gravity_at_point(0 | units.kpc, p[:, 0] | units.kpc, p[:, 1] | units.kpc, p[:, 2] | units.kpc)
     got = np.stack([c.value_in(units.kms / units.Myr) for c in (ax, ay, az)])
     st = field.rbf_status.cpu().numpy() & 0xff
-    assert np.all(st[:-1] == 0) and st[-1] & 8
+    assert np.all(st == 0) and field.rbf_bad_count == 0
     fld = np.concatenate([field.evolved_acceleration, field.evolved_potential[None]])
     h = g.fine_nodes[0][1] - g.fine_nodes[0][0]
-    ref = oracle.rbf_interp_points(g.evolved_grid, fld, p[:-1, 0], p[:-1, 1], p[:-1, 2], h, want_neighbors=True)
-    assert np.all(ref["neighbors"] >= g.fine_row0)  # every neighbour is a fine point or the origin row
-    assert close(got[:, :-1], ref["out"][:3], 1e-9)
+    ref = oracle.rbf_interp_points(g.evolved_grid, fld, p[:, 0], p[:, 1], p[:, 2], h, want_neighbors=True)
+    assert np.all(ref["neighbors"][:, :-1] >= g.fine_row0)  # inside the fine box: every neighbour a fine point or the origin row
+    assert np.any(ref["neighbors"][:, -1] < g.fine_row0)    # ... the last star's stencil reaches the coarse level
+    assert close(got, ref["out"][:3], 1e-9)
 
 
 def test_rbf_matches_the_golden_fixture(ctx):
     """K7 against tests/golden/rbf_reference.npz — cKDTree neighbours and scipy RBFInterpolator values on the point list of
-    the REAL grid class (single lattice, and the nested grid evaluated over its fine level)."""
+    the REAL grid class: a single lattice, the nested grid with every stencil inside the fine level, and the nested grid
+    with MIXED-LEVEL stencils (stars near the fine-box surface, up to 87 of the 150 neighbours on the coarse level)."""
     import torch
     from test_cpu_rbf import _golden_cases
+    mixed_seen = 0
     for g, origin, fields, stars, nbr, vals in _golden_cases():
-        nested = g.has_fine_grid
-        nodes = g.fine_nodes if nested else g.nodes
-        shape = g.fine_shape if nested else g.shape
-        f = fields[:, g.fine_row0:] if nested else fields
         n = stars.shape[0]
         out = torch.empty((3, n), dtype=torch.float64, device="cuda")
         st = torch.empty(n, dtype=torch.int32, device="cuda")
         nb = torch.empty((150, n), dtype=torch.int64, device="cuda")
-        ctx.grid_interp_rbf(shape, [dev(a) for a in nodes], dev(origin[None]), dev(f), dev(stars[:, 0]), dev(stars[:, 1]),
-                            dev(stars[:, 2]), None, out, status_out=st, neighbors_out=nb, embedded=nested)
+        sx, sy, sz = (dev(stars[:, k].copy()) for k in range(3))
+        if g.has_fine_grid:
+            row = np.full(int(np.prod(g.coarse_shape)), -1, np.int32)
+            row[g.coarse_keep_index] = np.arange(len(g.coarse_keep_index), dtype=np.int32)
+            ctx.grid_interp_rbf_nested(g.coarse_shape, [dev(a) for a in g.nodes], g.fine_shape, [dev(a) for a in g.fine_nodes],
+                                       dev(origin[None]), dev(row), g.fine_row0, dev(fields), sx, sy, sz, None, out, status_out=st,
+                                       neighbors_out=nb)
+            mixed_seen += int((nbr < g.fine_row0).any(axis=1).sum())
+        else:
+            ctx.grid_interp_rbf(g.shape, [dev(a) for a in g.nodes], dev(origin[None]), dev(fields), sx, sy, sz, None, out,
+                                status_out=st, neighbors_out=nb)
         assert np.all(st.cpu().numpy() & 0xff == 0)
-        got_nb = np.sort(nb.cpu().numpy().T, axis=1) + (g.fine_row0 if nested else 0)   # indices into the reference's point list
-        assert np.array_equal(got_nb, nbr)
+        assert np.array_equal(np.sort(nb.cpu().numpy().T, axis=1), nbr)   # rows of the reference's point list
         assert close(out.cpu().numpy(), vals, 1e-9)
+    assert mixed_seen >= 8
