@@ -96,7 +96,6 @@ struct InterpParams {
   double* tensor;  // [9][n_star]: tensor[3*i + j] = d a_j / d x_i (gizmo_interface.py:719-756), or NULL
   int* cell;
   int* level;      // [n_star]: 0 coarse, 1 fine, or NULL
-  int stage_off;   // doubles of dynamic shared memory before the per-thread prefetch slots (the node tables, if staged)
 };
 
 // Cell along one axis: i = searchsorted(node + o, x, side='right') - 1, clamped to [0, n-2].
@@ -121,16 +120,6 @@ __device__ __forceinline__ float lerp_rn_f(float a, float wa, float b, float wb)
   return __fadd_rn(__fmul_rn(a, wa), __fmul_rn(b, wb));
 }
 
-// cp.async (LDGSTS): global -> shared without passing through registers; completion tracked per thread in commit groups
-__device__ __forceinline__ void cp_async8(void* dst_smem, const void* src) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async4(void* dst_smem, const void* src) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all_but_one() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
-
 // One thread per star.  Arithmetic contract (identical in oracle/ocg_oracle.c: grid_interp_core):
 //   level     : (nested only) fine iff node2[0] + o <= x <= node2[n2-1] + o on all three axes        FP64 compares
 //   cell      : FP64 comparisons against node[i] + origin (bit-exact searchsorted)
@@ -139,15 +128,9 @@ __device__ __forceinline__ void cp_async_wait_all_but_one() { asm volatile("cp.a
 //   trilinear : z, then y, then x lerps of the 8 corner values, every op rounded to FP64        FP64
 //   tensor    : derivative of that trilinear form: differences of the z / y / x stage values times inv[i]
 // SMEM_NODES: node and inverse-spacing tables staged in shared memory (else read from global).
-// A star costs two dependent memory round trips — its position and cluster id, then the 8 x n_rec corner records — and the
-// kernel is bound by that latency, not by bytes (ncu: DRAM at 10 % of peak, long_scoreboard 13 per issue).  The first trip is
-// taken off the critical path: while a thread gathers the records of star s, cp.async brings the position and cluster id of
-// its NEXT star (s + grid stride) into a private shared-memory slot — no registers held across the gathers, which is what
-// made a register-level software pipeline spill at the 64-register occupancy the kernel needs.
 template <bool SMEM_NODES, int MINB, bool NESTED, bool TENSOR>
 __global__ void __launch_bounds__(256, MINB) grid_interp_kernel(const InterpParams p) {
   extern __shared__ double s_tab[];
-  double* stg = s_tab + p.stage_off;  // [2 buffers][x, y, z, cluster][256 threads]
   const double* nd[2][3];
   const double* iv[2][3];
   if (SMEM_NODES) {
@@ -176,24 +159,11 @@ __global__ void __launch_bounds__(256, MINB) grid_interp_kernel(const InterpPara
 #pragma unroll
   for (int r = 0; r < 4; ++r) wt[r] = p.w_slot >= 0 ? c_interp_w[p.w_slot][r] : p.w[r];
   // grid-stride over stars: the tables above are staged once per resident block, not once per 256 stars
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  auto prefetch = [&](long long s, int b) {
-    if (s < p.n_star) {
-      double* q = stg + (b * 4) * 256 + threadIdx.x;
-      cp_async8(q, p.sx + s), cp_async8(q + 256, p.sy + s), cp_async8(q + 512, p.sz + s);
-      if (p.scl) cp_async4(q + 768, p.scl + s);
-    }
-    cp_async_commit();  // (an empty group when there is no next star: keeps the group count uniform)
-  };
-  int buf = 0;
-  prefetch(blockIdx.x * (long long)blockDim.x + threadIdx.x, 0);
-  for (long long s = blockIdx.x * (long long)blockDim.x + threadIdx.x; s < p.n_star; s += stride, buf ^= 1) {
-    prefetch(s + stride, buf ^ 1);
-    cp_async_wait_all_but_one();  // this star's slot is complete; the next one's copy stays in flight
-    const double* q = stg + (buf * 4) * 256 + threadIdx.x;
-    const int cl = p.scl ? *reinterpret_cast<const int*>(q + 768) : 0;
+  for (long long s = blockIdx.x * (long long)blockDim.x + threadIdx.x; s < p.n_star;
+       s += (long long)gridDim.x * blockDim.x) {
+    const int cl = p.scl ? p.scl[s] : 0;
     const double* org = p.origin + 3 * (long long)cl;
-    const double pos[3] = {q[0], q[256], q[512]};
+    const double pos[3] = {p.sx[s], p.sy[s], p.sz[s]};
     int lv = 0;
     if (NESTED) {
       lv = 1;
@@ -336,8 +306,7 @@ static int interp_launch(ocg_ctx* ctx, const ocg_grid_desc* grid, const float* c
   if (fine) nn += (long long)fine->n[0] + fine->n[1] + fine->n[2];
   // persistent launch: as many blocks as are resident at once (a multiple of the SM count), grid-stride inside
   const bool in_smem = nn <= 2048;
-  p.stage_off = in_smem ? (int)(nn * 2) : 0;
-  const size_t smem = (size_t)p.stage_off * sizeof(double) + 2 * 4 * 256 * sizeof(double);  // tables | prefetch slots
+  const size_t smem = in_smem ? (size_t)nn * 2 * sizeof(double) : 0;
   typedef void (*interp_fn)(const InterpParams);
   static const interp_fn fns[3][2] = {
       {grid_interp_kernel<false, 2, false, false>, grid_interp_kernel<true, 2, false, false>},
