@@ -39,9 +39,11 @@ sys.path.insert(0, ROOT)
 FLOP_PER_INTERACTION = 20.0  # GPU-Gems-3 ch.31 convention, acc only
 # (grid, sources on this GPU) -> DRAM bytes moved by one launch of the streaming kernel (ncu --set full, profiles/)
 NCU_DRAM_BYTES_PER_LAUNCH = {
-    # profiles/r01_ncu_dram_bench_full.csv: 249 632 768 B read (tiles + targets; the 200 MB of tiles are re-read from L2)
-    # + 667 437 824 B written (FP64 chunk partials) = 0.1 % of HBM bandwidth over the 919 ms launch
-    (64, 10000000): 249632768 + 667437824,
+    # profiles/r02_ncu_dram_bench_full.csv: 361 487 104 B read (200 MB of tiles once — streamed in 32 MB passes that stay
+    # in L2 — + targets + shared-row partial slots read back) + 195 362 816 B written (partial slots + the FP64 field)
+    # = 0.06 GB/s-equivalent share: 0.01 % of HBM bandwidth over the 961 ms launch.  History: r01 917 MB (667 MB of chunk
+    # partials); stream-K without passes 9.14 GB (every row re-fetched the tiles from HBM, r02_ncu_dram_before_passes.csv)
+    (64, 10000000): 361487104 + 195362816,
 }
 G_KPC = 4.398600413517813e-09
 CENTER = np.array([8.0, 0.0, 0.0])
@@ -526,7 +528,7 @@ def main():
     ffma2 = ctx.probe_throughput(1)
     # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture of this same command
     # (dram__bytes_read.sum + dram__bytes_write.sum, profiles/); null when no capture exists for this configuration.
-    # traffic_model is what the launch must move: source tiles + targets once, FP64 chunk partials written once.
+    # traffic_model is what the launch must move: source tiles + targets once, the FP64 field, partial slots written + read once.
     traffic = NCU_DRAM_BYTES_PER_LAUNCH.get((args.grid, n_src))
     roofline = {"bound": "fp32", "achieved": achieved, "peak": nominal, "unit": "TFLOP/s", "frac": achieved / nominal,
                 "traffic": traffic, "traffic_model": ctx.last_direct_traffic_model(),

@@ -481,35 +481,50 @@ __global__ void __launch_bounds__(32 * NW, MINB) direct_sum_tp_kernel(const Dire
 
   const float scale = p.scale_ptr ? *p.scale_ptr : p.scale_val;
   __shared__ int s_last;
-  __shared__ long long s_sk[3];  // units of the launch, participating CTAs, end of this CTA's unit range: read back in
-                                 // the segment epilogue instead of being held in registers across the tile loop
-  // ---- stream-K: this CTA's share of the (target tile x source tile) units, see streamk.cuh ----
+  __shared__ long long s_sk[5];  // units of the pass, participating CTAs, end of this CTA's unit range, tiles per row in
+                                 // this pass, first tile of the pass: read back in the segment epilogue instead of
+                                 // being held in registers across the tile loop
+  // ---- stream-K: this CTA's share of the (target tile x source tile) units, pass by pass, see streamk.cuh ----
+  if (sk_units(p.sk) == 0) {  // nothing to stream (K1 with an empty fast set): the field of no sources is zero
+    if (!p.accumulate)
+      for (long long i = blockIdx.x * (long long)NTHR + tid; i < p.out_n; i += (long long)gridDim.x * NTHR) {
+        p.out_acc[i] = 0.0, p.out_acc[p.out_n + i] = 0.0, p.out_acc[2 * p.out_n + i] = 0.0;
+        if (POT) p.out_pot[i] = 0.0;
+      }
+    return;
+  }
+  int n_pass = 1;
+  if (!p.sk.rows) {
+    const long long nst_total = sk_nst(p.sk), cap = sk_pass_cap(p.sk, nst_total);
+    n_pass = (int)((nst_total + cap - 1) / cap);
+  }
+  for (int pass = 0; pass < n_pass; ++pass) {
   long long u;
   {
-    const long long U = sk_units(p.sk);
-    const long long G_ = sk_ctas(U, gridDim.x);  // CTAs that take part: every one of them gets at least one unit
-    if (U == 0) {  // nothing to stream (K1 with an empty fast set): the field of no sources is zero
-      if (!p.accumulate)
-        for (long long i = blockIdx.x * (long long)NTHR + tid; i < p.out_n; i += (long long)gridDim.x * NTHR) {
-          p.out_acc[i] = 0.0, p.out_acc[p.out_n + i] = 0.0, p.out_acc[2 * p.out_n + i] = 0.0;
-          if (POT) p.out_pot[i] = 0.0;
-        }
-      return;
+    long long nst_pass = 0, tile0 = 0;
+    if (!p.sk.rows) {
+      const long long nst_total = sk_nst(p.sk), cap = sk_pass_cap(p.sk, nst_total);
+      tile0 = pass * cap;
+      nst_pass = nst_total - tile0 < cap ? nst_total - tile0 : cap;
     }
+    const long long U = sk_units(p.sk, nst_pass);
+    const long long G_ = sk_ctas(U, gridDim.x);  // CTAs that take part: every one of them gets at least one unit
     u = blockIdx.x < G_ ? sk_first_unit(blockIdx.x, U, G_) : 0;
-    if (tid == 0) s_sk[0] = U, s_sk[1] = G_, s_sk[2] = blockIdx.x < G_ ? sk_first_unit(blockIdx.x + 1, U, G_) : 0;
+    __syncthreads();  // the previous pass's epilogue has read s_sk
+    if (tid == 0)
+      s_sk[0] = U, s_sk[1] = G_, s_sk[2] = blockIdx.x < G_ ? sk_first_unit(blockIdx.x + 1, U, G_) : 0, s_sk[3] = nst_pass, s_sk[4] = tile0;
     __syncthreads();
   }
-  for (int row = u < s_sk[2] ? sk_find_row(p.sk, u) : 0; u < s_sk[2]; ++row) {
+  for (int row = u < s_sk[2] ? sk_find_row(p.sk, u, s_sk[3]) : 0; u < s_sk[2]; ++row) {
     int tgt_count, tile_count;
     long long tgt_begin;
     const float* src;
     {
-      const long long rs = sk_row_start(p.sk, row), re = sk_row_start(p.sk, row + 1), u_end = s_sk[2];
+      const long long rs = sk_row_start(p.sk, row, s_sk[3]), re = sk_row_start(p.sk, row + 1, s_sk[3]), u_end = s_sk[2];
       long long tile_begin;
       tile_count = (int)((re < u_end ? re : u_end) - u);
       sk_row(p.sk, row, tgt_begin, tgt_count, tile_begin);
-      src = p.tiles + (tile_begin + (u - rs)) * (long long)TILE_FLOATS;
+      src = p.tiles + (tile_begin + s_sk[4] + (u - rs)) * (long long)TILE_FLOATS;
       u += tile_count;
     }
     if (tid == 0) {
@@ -583,10 +598,20 @@ __global__ void __launch_bounds__(32 * NW, MINB) direct_sum_tp_kernel(const Dire
 
     // ---- segment epilogue: who shares this row, and the final scaling (recomputed here, not carried over the loop) ----
     const long long U = s_sk[0], G_ = s_sk[1];
-    const long long rs = sk_row_start(p.sk, row), re = sk_row_start(p.sk, row + 1);
+    const long long rs = sk_row_start(p.sk, row, s_sk[3]), re = sk_row_start(p.sk, row + 1, s_sk[3]);
     const int first_cta = sk_cta_of(rs, U, G_);
-    const int n_sharers = sk_cta_of(re - 1, U, G_) - first_cta + 1;
-    const long long slot = (long long)blockIdx.x - first_cta;
+    int n_sharers = sk_cta_of(re - 1, U, G_) - first_cta + 1;
+    long long slot = (long long)blockIdx.x - first_cta;
+    if (n_pass > 1) {
+      // the row has sharers in every pass: slots pass-major, one ticket counter.  All passes but the last have `cap` tiles.
+      const long long nst_total = sk_nst(p.sk), cap = sk_pass_cap(p.sk, nst_total);
+      const long long Uf = p.sk.n_rows * cap, Gf = sk_ctas(Uf, gridDim.x);
+      const int sf = sk_sharers(row * cap, (row + 1) * cap, Uf, Gf);
+      const long long cl = nst_total - (n_pass - 1) * cap, Ul = p.sk.n_rows * cl, Gl = sk_ctas(Ul, gridDim.x);
+      const int sl = sk_sharers(row * cl, (row + 1) * cl, Ul, Gl);
+      slot += (long long)pass * sf;
+      n_sharers = (n_pass - 1) * sf + sl;
+    }
     {
       long long unused_tile;
       sk_row(p.sk, row, tgt_begin, tgt_count, unused_tile);  // re-read: not live across the tile loop
@@ -647,4 +672,5 @@ __global__ void __launch_bounds__(32 * NW, MINB) direct_sum_tp_kernel(const Dire
       }
     }
   }
+  }  // pass
 }

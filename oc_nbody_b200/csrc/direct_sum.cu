@@ -758,10 +758,14 @@ int ocg_direct_sum_impl(ocg_ctx* ctx, const float* src_xyzm, const float* src_so
   const long long slots = ocg_variant_slots(ctx, variant);
   const bool tp = variant_is_tp(g_variants[variant]);
   long long n_chunks, tiles_per_chunk = 0;
+  // source tiles per pass of the stream-K kernel: what stays in L2 while every CTA streams it (streamk.cuh, PASSES)
+  const long long pass_tiles = ctx->knobs.pass_bytes > 0 ? (ctx->knobs.pass_bytes + narr * OCG_TS * 4 - 1) / (narr * OCG_TS * 4) : 0;
+  const long long n_pass_max = pass_tiles > 0 && pass_tiles < n_tiles_max ? (n_tiles_max + pass_tiles - 1) / pass_tiles : 1;
   if (tp) {
-    // stream-K (streamk.cuh): a row of targets is shared by at most ceil(CTAs / rows) + 1 consecutive CTAs
+    // stream-K (streamk.cuh): a row of targets is shared by at most ceil(CTAs / rows) + 1 consecutive CTAs per pass
     n_chunks = (slots + n_ttiles - 1) / n_ttiles + 1;
     if (n_chunks > slots) n_chunks = slots;
+    n_chunks *= n_pass_max;
     if (n_ttiles > 0x7fffffffll) return ocg_fail(ctx, OCG_ERR_INVALID, "too many target tiles");
   } else {
     // (target tile x source chunk) items dealt round robin: aim for >= 64 equal-cost items per resident CTA slot
@@ -846,6 +850,7 @@ int ocg_direct_sum_impl(ocg_ctx* ctx, const float* src_xyzm, const float* src_so
   p.sk.n_tgt = n_tgt, p.sk.ct = CT;
   p.sk.nst_uniform = misc + MISC_NFAST_TILES;
   p.sk.tickets = tickets;
+  p.sk.tile_cap = n_pass_max > 1 ? (int)pass_tiles : 0;
   p.out_acc = acc, p.out_pot = pot, p.out_n = n_tgt;
   p.G = G, p.accumulate = accumulate, p.self_e2s = -1.f;
   p.m0_ptr = mf ? reinterpret_cast<const float*>(misc + MISC_M0) : nullptr;
@@ -853,7 +858,8 @@ int ocg_direct_sum_impl(ocg_ctx* ctx, const float* src_xyzm, const float* src_so
   // what the launch has to move through HBM: tiles and targets once, the FP64 field once, and for the rows shared by
   // several CTAs one partial slot per extra sharer (at most one extra sharer per CTA boundary)
   ctx->last_traffic_bytes = n_tiles_max * (long long)narr * OCG_TS * 4 + n_tgt * 16 + (long long)NC * n_tgt * 8 +
-                            (tp ? 2 * (slots < n_ttiles ? slots : n_ttiles) : n_chunks * n_tgt / CT) * (long long)NC * CT * 8;
+                            (tp ? 2 * n_pass_max * ((n_pass_max > 1 ? n_ttiles : 0) + (slots < n_ttiles ? slots : n_ttiles)) : n_chunks * n_tgt / CT) *
+                                (long long)NC * CT * 8;
 
   {
     long long nb = (n_tgt + 255) / 256;

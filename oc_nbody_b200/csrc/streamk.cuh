@@ -9,6 +9,14 @@
 // FP64 partial sums into its own slot, takes a ticket, and the CTA that takes the last ticket of a row adds the slots
 // IN SLOT ORDER (run-to-run deterministic) and writes the final field — no finish kernel, no (chunks x targets)
 // partial buffer (K1 at configs[1]: 667 MB of partials down to 19 MB).
+//
+// PASSES (uniform mode, K1): with more source tiles than the L2 holds (configs[1]: 200 MB of tiles, 86 rows) CTAs that
+// each stream their own 0.58 rows sit at 148 different places of the source array, and every tile is fetched from HBM
+// again for nearly every row (measured: 9.1 GB of DRAM reads per launch for 0.2 GB of tiles).  The source tiles are
+// therefore cut into passes of `tile_cap` tiles (32 MB); the CTAs split the units of pass 0, then those of pass 1, ...:
+// at any time they all stream the same 32 MB, which stays in L2.  A row then has sharers in every pass; they all write
+// slots (pass-major, CTA order within a pass) and take tickets of the same counter, and the last one adds the slots in
+// slot order as before.  No barrier between passes: the alignment only matters for locality, not for correctness.
 #pragma once
 #include "ocg_internal.cuh"
 
@@ -30,11 +38,28 @@ __device__ __forceinline__ int sk_find_row(const StreamKParams& k, long long u) 
   }
   return lo;
 }
+// ---- uniform mode with an explicit tile count per row (the tiles of one pass) ----
+__device__ __forceinline__ long long sk_pass_cap(const StreamKParams& k, long long nst_total) {
+  return (k.rows || k.tile_cap <= 0 || k.tile_cap >= nst_total) ? (nst_total > 0 ? nst_total : 1) : (long long)k.tile_cap;
+}
+__device__ __forceinline__ long long sk_units(const StreamKParams& k, long long nst) {
+  return k.rows ? k.row_prefix[k.n_rows] : (long long)k.n_rows * nst;
+}
+__device__ __forceinline__ long long sk_row_start(const StreamKParams& k, int r, long long nst) {
+  return k.rows ? k.row_prefix[r] : (long long)r * nst;
+}
+__device__ __forceinline__ int sk_find_row(const StreamKParams& k, long long u, long long nst) {
+  return k.rows ? sk_find_row(k, u) : (int)(u / nst);
+}
 // CTAs that take part: with fewer units than CTAs the surplus CTAs idle, so that the sharers of a row are consecutive
 __device__ __forceinline__ long long sk_ctas(long long U, long long grid) { return U < grid ? U : grid; }
 // first unit of CTA c, and the CTA that owns unit x:  b(c) = floor(c U / G);  c(x) = ceil((x + 1) G / U) - 1
 __device__ __forceinline__ long long sk_first_unit(long long c, long long U, long long G) { return (c * U) / G; }
 __device__ __forceinline__ int sk_cta_of(long long x, long long U, long long G) { return (int)(((x + 1) * G + U - 1) / U - 1); }
+
+__device__ __forceinline__ int sk_sharers(long long rs, long long re, long long U, long long G) {
+  return sk_cta_of(re - 1, U, G) - sk_cta_of(rs, U, G) + 1;
+}
 
 __device__ __forceinline__ void sk_row(const StreamKParams& k, int r, long long& tgt_begin, int& tgt_count, long long& tile_begin) {
   if (k.rows) {

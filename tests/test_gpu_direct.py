@@ -248,6 +248,36 @@ def test_field_direct_production_big_is_mass_folded(ctx):
     assert rel_err(a_pl, ref, abs_sum=cond) <= TOL and rel_err_scalar(pot_pl, pref) <= TOL
 
 
+@pytest.mark.parametrize("n_grid,want_pot", [(41, False), (41, True), (12, False), (4, True)])
+def test_field_direct_stream_k_passes(ctx, n_grid, want_pot):
+    """The source tiles are streamed in L2-sized passes (streamk.cuh, PASSES): with the pass shrunk to 3 tiles a 9-tile
+    problem takes 3-4 passes (the last one shorter), every row's slots span the passes, and the result is the single-pass
+    one to FP64 rounding, deterministic, and the oracle's to the parity tolerance."""
+    rng = np.random.default_rng(77)
+    src, soft = random_sources(rng, 4300, box=2.0)
+    tgt = grid_targets(n_grid)
+    ref, pref = oracle.field_direct(src, soft, tgt, oracle.KERNEL_PLUMMER, G, want_pot=True)
+    cond = oracle.field_direct_abs(src, soft, tgt, oracle.KERNEL_PLUMMER, G)
+    ctx.debug_set("near_cap", 512)  # keep most of the 4300 sources in the FP32 tiles (9 tiles)
+    try:
+        ctx.debug_set("pass_bytes", 0)
+        a1, p1 = run_k1(ctx, src, soft, tgt, oracle.KERNEL_PLUMMER, want_pot=want_pot)
+        ctx.debug_set("pass_bytes", 3 * 6 * 512 * 4)
+        a3, p3 = run_k1(ctx, src, soft, tgt, oracle.KERNEL_PLUMMER, want_pot=want_pot)
+        b3, _ = run_k1(ctx, src, soft, tgt, oracle.KERNEL_PLUMMER, want_pot=want_pot)
+        ctx.debug_set("pass_bytes", 1)  # one tile per pass
+        a9, p9 = run_k1(ctx, src, soft, tgt, oracle.KERNEL_PLUMMER, want_pot=want_pot)
+    finally:
+        ctx.debug_set("pass_bytes", 32 << 20)
+        ctx.debug_set("near_cap", 0)
+    assert np.array_equal(a3, b3)
+    scale = np.abs(a1).max()
+    assert np.max(np.abs(a3 - a1)) <= 1e-13 * scale and np.max(np.abs(a9 - a1)) <= 1e-13 * scale
+    assert rel_err(a3, ref, abs_sum=cond) <= TOL and rel_err(a9, ref, abs_sum=cond) <= TOL
+    if want_pot:
+        assert rel_err_scalar(p3, pref) <= TOL and rel_err_scalar(p9, pref) <= TOL
+
+
 def test_frame_subtract_and_host_form(ctx):
     import torch
     rng = np.random.default_rng(31)
