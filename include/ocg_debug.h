@@ -29,7 +29,7 @@ enum {
   OCG_KNOB_HERMITE_VARIANT = 5,    /* K6 kernel shape id, -1 = production (default)                                     */
   OCG_KNOB_HERMITE_SMALL_PATH = 6, /* 1 (default): fused one-launch K6 kernel for a single small cluster                */
   OCG_KNOB_INTERP_VARIANT = 7,     /* K3 register bound: 0 <= 128, 1 <= 80, 2 <= 64 registers (default 2)               */
-  OCG_KNOB_RBF_SHARE = 8,          /* 1 (default): K7 shares one factorisation between stars with equal stencil pattern  */
+  /* 8: retired (a factorisation shared between stars was measured and dropped) */
   OCG_KNOB_NEAR_CAP = 9,           /* size limit of K1's FP64 precision-radius set; 0 (default) = max(n_src / 512, 2^36 / n_src)  */
   OCG_KNOB_PASS_BYTES = 10         /* K1: bytes of source tiles per stream-K pass (L2 residency); 0 = one pass, default 32 MiB      */
 };

@@ -30,7 +30,7 @@ ABI_SYMBOLS = [
 DEBUG_SYMBOLS = ["ocg_debug_set", "ocg_debug_variant_count", "ocg_debug_variant_name", "ocg_debug_variant_built",
                  "ocg_debug_rbf_phase_cycles"]
 KNOBS = {"direct_variant": 0, "precise_near": 1, "mass_fold": 2, "small_cluster_path": 3, "host_chunk": 4,
-         "hermite_variant": 5, "hermite_small_path": 6, "interp_variant": 7, "rbf_share": 8, "near_cap": 9, "pass_bytes": 10}
+         "hermite_variant": 5, "hermite_small_path": 6, "interp_variant": 7, "near_cap": 9, "pass_bytes": 10}
 
 
 class OcgError(RuntimeError):

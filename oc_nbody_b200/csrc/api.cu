@@ -88,7 +88,6 @@ extern "C" int ocg_create(int device, ocg_ctx** out) {
   ctx->knobs.hermite_small_path = 1;
   ctx->knobs.interp_variant = 2;
   ctx->knobs.field_precision = 0;
-  ctx->knobs.rbf_share = 1;
   ctx->knobs.near_cap = 0;
   ctx->knobs.pass_bytes = 32ll << 20;
   ctx->sm_count = prop.multiProcessorCount;
@@ -185,7 +184,6 @@ extern "C" int ocg_debug_set(ocg_ctx* ctx, int knob, int64_t value) {
       if (value < 0 || value > 2) return ocg_fail(ctx, OCG_ERR_INVALID, "K3 register bound %lld outside 0..2", (long long)value);
       k.interp_variant = (int)value;
       return OCG_OK;
-    case OCG_KNOB_RBF_SHARE: k.rbf_share = value != 0; return OCG_OK;
     case OCG_KNOB_NEAR_CAP: k.near_cap = value > 0 ? value : 0; return OCG_OK;
     case OCG_KNOB_PASS_BYTES: k.pass_bytes = value > 0 ? value : 0; return OCG_OK;
     default: return ocg_fail(ctx, OCG_ERR_INVALID, "ocg_debug_set: unknown knob %d", knob);

@@ -398,7 +398,7 @@ struct HermiteVariant {
 #else
 #define HM_TUNE(...) {{nullptr, nullptr}, {nullptr, nullptr}}
 #endif
-#define HM_PRODUCTION 7
+#define HM_PRODUCTION 6
 static const HermiteVariant g_hm_variants[] = {
     {"np4 8w (2048-target tiles)", 4, 8, 1, HM_TUNE(HM_V(4, 8, 1, 1))},
     {"np3 8w (1536-target tiles)", 3, 8, 1, HM_TUNE(HM_V(3, 8, 1, 1))},
@@ -406,8 +406,8 @@ static const HermiteVariant g_hm_variants[] = {
     {"np2 12w (1536-target tiles)", 2, 12, 1, HM_TUNE(HM_V(2, 12, 1, 1))},
     {"np3 12w (2304-target tiles)", 3, 12, 1, HM_TUNE(HM_V(3, 12, 1, 1))},
     {"np4 8w unroll 2", 4, 8, 1, HM_TUNE(HM_V(4, 8, 2, 1))},
-    {"np1 8w x 2 CTA/SM (512-target tiles)", 1, 8, 2, HM_TUNE(HM_V(1, 8, 1, 2))},
-    {"np1 8w x 2 CTA/SM unroll 2", 1, 8, 2, HM_V(1, 8, 2, 2)},
+    {"np1 8w x 2 CTA/SM (512-target tiles)", 1, 8, 2, HM_V(1, 8, 1, 2)},
+    {"np1 8w x 2 CTA/SM unroll 2", 1, 8, 2, HM_TUNE(HM_V(1, 8, 2, 2))},
     {"np2 8w unroll 2", 2, 8, 1, HM_TUNE(HM_V(2, 8, 2, 1))},
     {"np1 4w x 3 CTA/SM (256-target tiles)", 1, 4, 3, HM_TUNE(HM_V(1, 4, 1, 3))},
 };

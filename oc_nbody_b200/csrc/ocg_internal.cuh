@@ -47,7 +47,6 @@ struct OcgKnobs {
   int hermite_small_path;   // 1 = one small cluster takes the fused single-launch K6 kernel
   int interp_variant;       // register bound of K3: 0 <=128, 1 <=80, 2 <=64 (production)
   int field_precision;      // 0 = FP32 pair arithmetic + FP64 accumulation (north_star), 1 = every pair in FP64
-  int rbf_share;            // 1 = K7 shares one factorisation between stars with the same stencil pattern
   long long pass_bytes;     // K1: bytes of source tiles per stream-K pass (0 = one pass); default 32 MB, a quarter of the L2
   long long near_cap;       // > 0: size limit of K1's FP64 precision-radius set (0 = max(n_src / 512, 2^36 / n_src))
 };

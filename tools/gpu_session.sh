@@ -7,8 +7,10 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm --format=csv > gpurun_out/sm
 timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -4 > gpurun_out/pytest.log; cat gpurun_out/pytest.log
 timeout 600 python bench.py --steps 5 > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err || exit 1
 timeout 600 python bench.py --impl reference --steps 2 --warmup 3 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err
+if [ -z "$SKIP_ACC" ]; then
 timeout 600 python tools/accuracy.py > gpurun_out/accuracy.log 2>&1
 timeout 300 python tools/accuracy_c0.py > gpurun_out/accuracy_c0.log 2>&1
+fi
 timeout 600 python tools/bench_extra.py > gpurun_out/bench_extra.log 2>&1 && cp gpurun_out/bench_extra.json gpurun_out/bench_extra_plain.json
 timeout 600 python tools/bench_hermite.py > gpurun_out/bench_hermite.log 2>&1
 timeout 600 python tools/bench_rbf.py > gpurun_out/bench_rbf.log 2>&1
@@ -17,7 +19,7 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --c
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:direct_sum_tp --launch-skip 4 -c 1 -o gpurun_out/prof_k1 -f \
     python bench.py --n-src 1e6 --steps 1 --warmup 3 --no-cpu-baseline --no-extras > gpurun_out/ncu_k1.log 2>&1
 # DRAM traffic of the full-size launch (roofline.traffic): only the two byte counters, one launch of the real configs[1] step
-timeout 900 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:direct_sum_tp \
+timeout 900 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,lts__t_bytes.sum,gpu__time_duration.sum --clock-control none -k regex:direct_sum_tp \
     --launch-skip 4 -c 1 --csv --log-file gpurun_out/ncu_dram_bench_full.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-extras \
     > gpurun_out/ncu_dram.log 2>&1
 timeout 200 python tools/bench_hermite.py --profile && timeout 600 ncu --set full --clock-control none --import-source on \
