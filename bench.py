@@ -426,6 +426,7 @@ def main():
     ctx.cast_f64_f32(h_eps.to(dev), d_eps)
     ctx.recentre_f64(h_tgt.to(dev), None, CENTER, d_tgt)
     acc = torch.empty((3, n_tgt), dtype=torch.float64, device=dev)
+    ctx.set_source_shards(world)  # the FP64 near set is sized for the whole build, 1/world of it on every rank
     torch.cuda.synchronize()
 
     def step_resident(subtract=True):

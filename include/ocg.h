@@ -73,6 +73,11 @@ int64_t ocg_capture_epoch(const ocg_ctx* ctx);
 double ocg_last_direct_kernel_ms(ocg_ctx* ctx);
 /* Enable(1)/disable(0) event timing around the direct-sum kernel (default off). */
 int ocg_set_kernel_timing(ocg_ctx* ctx, int enabled);
+/* Source-sharded field build (every rank sums its own shard of the snapshot particles over all targets, the
+ * partial fields are then added across ranks): tell this ctx that its ocg_field_direct / ocg_field_build_host calls see
+ * 1/n_shards of the sources.  The size limit of the FP64 near set (the sources inside the precision radius) is a property
+ * of the whole build; each rank takes 1/n_shards of it.  Default 1. */
+int ocg_set_source_shards(ocg_ctx* ctx, int32_t n_shards);
 /* Bytes the streaming kernel of the most recent ocg_field_direct call has to move through HBM (source tiles and
  * targets read once, FP64 chunk partials written once): the model bench.py prints beside the ncu-measured traffic. */
 int64_t ocg_last_direct_traffic_bytes(const ocg_ctx* ctx);

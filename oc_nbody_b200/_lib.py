@@ -20,7 +20,7 @@ KERNELS = {"plummer": KERNEL_PLUMMER, "spline": KERNEL_SPLINE}
 # every symbol include/ocg.h declares (tests check the library exports them all)
 ABI_SYMBOLS = [
     "ocg_version", "ocg_create", "ocg_destroy", "ocg_last_error", "ocg_device_info", "ocg_launch_count", "ocg_capture_epoch",
-    "ocg_last_direct_kernel_ms", "ocg_set_kernel_timing", "ocg_last_direct_traffic_bytes", "ocg_recentre_f64", "ocg_cast_f64_f32", "ocg_assemble_sources",
+    "ocg_last_direct_kernel_ms", "ocg_set_kernel_timing", "ocg_set_source_shards", "ocg_last_direct_traffic_bytes", "ocg_recentre_f64", "ocg_cast_f64_f32", "ocg_assemble_sources",
     "ocg_field_direct", "ocg_frame_subtract", "ocg_field_build_host", "ocg_pack_planes", "ocg_grid_time_blend",
     "ocg_grid_interp", "ocg_grid_interp_multi", "ocg_grid_interp_nested", "ocg_pack_planes_indexed", "ocg_set_interp_weight_slots", "ocg_grid_interp_slot", "ocg_grid_interp_rbf", "ocg_grid_interp_rbf_nested", "ocg_self_gravity", "ocg_self_gravity_hermite", "ocg_hermite_predict", "ocg_hermite_correct", "ocg_hermite_block_evolve", "ocg_bound_com", "ocg_eject_mask", "ocg_compact_rows", "ocg_kick", "ocg_drift", "ocg_axpy", "ocg_probe_throughput", "ocg_comm_create", "ocg_comm_connect", "ocg_comm_destroy", "ocg_comm_info", "ocg_comm_status", "ocg_comm_allreduce_f64", "ocg_self_gravity_sharded",
 ]
@@ -69,6 +69,7 @@ def load_library():
     L.ocg_last_direct_kernel_ms.restype = dbl
     L.ocg_last_direct_kernel_ms.argtypes = [vp]
     L.ocg_set_kernel_timing.argtypes = [vp, ctypes.c_int]
+    L.ocg_set_source_shards.argtypes = [vp, i32]
     L.ocg_last_direct_traffic_bytes.restype = i64
     L.ocg_last_direct_traffic_bytes.argtypes = [vp]
     L.ocg_recentre_f64.argtypes = [vp, vp, vp, i64, ctypes.POINTER(dbl), vp, vp]
@@ -199,6 +200,10 @@ class Context:
 
     def set_kernel_timing(self, on):
         self._ck(self.lib.ocg_set_kernel_timing(self.h, 1 if on else 0), "ocg_set_kernel_timing")
+
+    def set_source_shards(self, n_shards):
+        """This context sums 1/n_shards of the sources of a source-sharded field build (include/ocg.h)."""
+        self._ck(self.lib.ocg_set_source_shards(self.h, int(n_shards)), "ocg_set_source_shards")
 
     def last_direct_kernel_ms(self):
         return float(self.lib.ocg_last_direct_kernel_ms(self.h))

@@ -89,6 +89,7 @@ extern "C" int ocg_create(int device, ocg_ctx** out) {
   ctx->knobs.interp_variant = 2;
   ctx->knobs.field_precision = 0;
   ctx->knobs.near_cap = 0;
+  ctx->source_shards = 1;
   ctx->knobs.pass_bytes = 32ll << 20;
   ctx->sm_count = prop.multiProcessorCount;
   int khz = 0;
@@ -140,6 +141,13 @@ extern "C" int64_t ocg_capture_epoch(const ocg_ctx* ctx) {
                                        ctx->plan[1].items_hash, (unsigned long long)ctx->plan[1].items_uploaded};
   for (int i = 0; i < 5; ++i) h = (h ^ parts[i]) * 1099511628211ull;
   return (int64_t)(h >> 1);
+}
+
+extern "C" int ocg_set_source_shards(ocg_ctx* ctx, int32_t n_shards) {
+  if (!ctx) return OCG_ERR_INVALID;
+  if (n_shards < 1) return ocg_fail(ctx, OCG_ERR_INVALID, "ocg_set_source_shards: n_shards = %d", (int)n_shards);
+  ctx->source_shards = n_shards;
+  return OCG_OK;
 }
 
 extern "C" int ocg_set_kernel_timing(ocg_ctx* ctx, int enabled) {

@@ -373,9 +373,10 @@ extern "C" int ocg_self_gravity_sharded(ocg_ctx* ctx, const double* pos_local_de
   frexpf(sqrtf(e2f), &ex);
   float scale = ldexpf(1.0f, -8 - ex);  // eps at ~2^-8, as ocg_self_gravity
   if (!(scale > 0.f) || !isfinite(scale) || !(e2f * scale * scale > 0.f)) scale = 1.0f;
-  // always the 512-target stream-K shape: every rank must take the same path whatever its block size (they differ by one
-  // star at most, which must not flip a heuristic on one rank only), and stream-K balances any number of rows
-  const int variant = ocg_variant_cluster_tp();
+  // a target-paired stream-K shape (wide or mid rows by the shard's size, ocg_pick_variant); the exchange and the tile pack
+  // do not depend on it, so ranks whose block sizes differ by a star may even pick differently
+  int variant = ocg_pick_variant(ctx, b - a, n, /*guard=*/false, /*allow_mf=*/false, (n + OCG_TS - 1) / OCG_TS, /*fine_tiles=*/true);
+  if (!ocg_variant_is_tp(variant)) variant = ocg_variant_cluster_tp();
   const int CT = ocg_variant_threads(variant) * ocg_variant_tpt(variant);
   const long long grid = ocg_variant_slots(ctx, variant);
   int64_t seg[2] = {0, n};

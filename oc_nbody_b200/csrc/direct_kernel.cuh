@@ -655,18 +655,28 @@ __global__ void __launch_bounds__(32 * NW, MINB) direct_sum_tp_kernel(const Dire
           for (int c = 0; c < NC; ++c) p.partial[(slot * NC + c) * p.out_stride + tgt_begin + local] = own(t, c);
       }
       if (sk_last_of_row(p.sk, row, n_sharers, &s_last)) {
-        // last of the row's CTAs: add the slots in slot order (deterministic whatever the arrival order)
+        // last of the row's CTAs: add the slots in slot order (deterministic whatever the arrival order); two targets x NC
+        // components per step so that a slot costs one round trip to L2, not 2 NC dependent ones
 #pragma unroll
-        for (int t = 0; t < T; ++t) {
-          const int local = t * NTHR + tid;
-          if (local < tgt_count) {
-            const long long gi = tgt_begin + local;
+        for (int t = 0; t < T; t += 2) {
+          const int l0 = t * NTHR + tid, l1 = (t + 1) * NTHR + tid;
+          const long long g0 = tgt_begin + (l0 < tgt_count ? l0 : 0), g1 = tgt_begin + (l1 < tgt_count ? l1 : 0);
+          double sum[2][NC];
+#pragma unroll
+          for (int c = 0; c < NC; ++c) sum[0][c] = sum[1][c] = 0.0;
+#pragma unroll 2
+          for (int k = 0; k < n_sharers; ++k) {
+            const double* base = p.partial + (long long)k * NC * p.out_stride;
 #pragma unroll
             for (int c = 0; c < NC; ++c) {
-              double sum = 0.0;
-              for (int k = 0; k < n_sharers; ++k) sum += __ldcg(&p.partial[((long long)k * NC + c) * p.out_stride + gi]);
-              write_out(gi, c, sum);
+              sum[0][c] += __ldcg(base + c * p.out_stride + g0);
+              sum[1][c] += __ldcg(base + c * p.out_stride + g1);
             }
+          }
+#pragma unroll
+          for (int c = 0; c < NC; ++c) {
+            if (l0 < tgt_count) write_out(g0, c, sum[0][c]);
+            if (l1 < tgt_count) write_out(g1, c, sum[1][c]);
           }
         }
       }

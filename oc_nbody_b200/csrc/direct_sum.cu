@@ -575,7 +575,7 @@ static const DirectVariant g_variants[] = {
     /* 23 */ {"tpair np2 (4 tgt/thr) smemacc minb2 unr1", 4, 2, false, TUNE(OCG_TP(2, true, 2, 1)), 4},
     /* 24 */ {"tpair np4 (8 tgt/thr) smemacc minb2 unr1", 8, 2, false, TUNE(OCG_TP(4, true, 2, 1)), 8},
     /* 25 */ {"tpair np3 (6 tgt/thr) smemacc minb2 unr1", 6, 2, false, TUNE(OCG_TP(3, true, 2, 1)), 6},
-    /* 26 */ {"tpair np4 (8 tgt/thr) smemacc minb1 unr1", 8, 1, false, TUNE(OCG_TP(4, true, 1, 1)), 8},
+    /* 26 */ {"tpair np4 (8 tgt/thr) smemacc minb1 unr1", 8, 1, false, OCG_TP(4, true, 1, 1), 8},  // production: WIDE (K4)
     /* 27 */ {"tpair np1 (2 tgt/thr) regacc minb2 unr2", 2, 2, false, OCG_TP(1, false, 2, 2), 0},  // production: MID (K4)
     /* 28 */ {"tpair np2 (4 tgt/thr) regacc minb3 unr1", 4, 3, false, TUNE(OCG_TP(2, false, 3, 1)), 0},
     /* 29 */ {"tpair np4 smemacc 4w x minb3 (12 w/SM)", 8, 3, false, TUNE(OCG_TPW(4, true, 3, 1, 4)), 8, 4},
@@ -644,6 +644,9 @@ static const int g_n_variants = (int)(sizeof(g_variants) / sizeof(g_variants[0])
 #define OCG_VARIANT_BIG_MF 67     /* K1 >= 64k targets: mass-folded, w-swizzled tiles, 12 targets/thread, 8 warps, FOLD 64 */
 #define OCG_VARIANT_BIG_MF_POT 74 /* the same with the potential: 6-array tiles, 8 targets/thread, 12 warps, FOLD 64 */
 #define OCG_VARIANT_MID 27        /* >= 16k targets, plain tiles (K4): target-paired, 2 targets/thread              */
+#define OCG_VARIANT_WIDE 26       /* K4 with >= 6 tiles per CTA: plain tiles, 8 targets/thread, 8 warps, 1 CTA/SM (tools/probe_k4.py:
+                                     70.2 vs 66.8 % at N = 65 536, 68.1 vs 62.4 % at 256 x 4 096, 70.4 vs 65.9 % at 16 x 16 384; but
+                                     41.2 vs 46.2 % at N = 16 384 where a CTA gets fewer than two 2048-target tiles) */
 #define OCG_VARIANT_MID_MF 80     /* K1 mid-size target counts: mass-folded, 2 targets/thread, register FP64 accumulators (a fold costs
                                      12 instructions): FOLD 16, with or without potential.  configs[0] (16^3 grid, 1e6 particles,
                                      profiles/r02_accuracy_c0.json), tidal residual strict: FOLD 64 1.2e-5, 32 6.7e-6, 16 3.9e-6 */
@@ -677,10 +680,26 @@ int ocg_pick_variant(ocg_ctx* ctx, int64_t n_tgt, int64_t seg_len, bool guard, b
     return (n_tgt + ct - 1) / ct * src_tiles >= 4ll * ctx->sm_count * g_variants[v].minb;
   };
   if (guard) return (n_tgt >= 16384 && waste_ok(OCG_VARIANT_MID_GUARD)) ? OCG_VARIANT_MID_GUARD : OCG_VARIANT_SMALL;
-  // K4 (fine_tiles): clusters of >= 2048 stars always take the 512-target stream-K shape — stream-K balances any number of
-  // rows, and a target shard (ocg_self_gravity_sharded, or tgt_begin/tgt_end) must run the same kernel as the unsharded call
-  // so that an N-GPU trajectory reproduces the 1-GPU one bit for bit
-  if (fine_tiles) return (seg_len >= 2048 || waste_ok(OCG_VARIANT_MID)) ? OCG_VARIANT_MID : OCG_VARIANT_SMALL;
+  // K4 (fine_tiles): clusters of >= 2048 stars take a target-paired stream-K shape.  All of them accumulate a target's
+  // sources in the same order (FP32 runs of one tile, FP64 across tiles), so a target shard (ocg_self_gravity_sharded, or
+  // tgt_begin/tgt_end) may run another shape than the unsharded call and still reproduce it
+  if (fine_tiles) {
+    if (!(seg_len >= 2048 || waste_ok(OCG_VARIANT_MID))) return OCG_VARIANT_SMALL;
+    // wide (2048-target) or mid (512-target) rows: inner-loop rate x row fill x stream-K balance (units per CTA against the
+    // next integer), the wide shape only with >= 6 tiles per CTA to amortise its longer prologue and epilogue
+    auto model = [&](int v, double rate, double* per_cta) {
+      const long long ct = (long long)variant_threads(g_variants[v]) * g_variants[v].tpt;
+      const long long seg_tgt = seg_len < n_tgt ? seg_len : n_tgt;  // targets of one cluster in this call (a shard cuts one cluster)
+      const long long n_segs = (n_tgt + seg_tgt - 1) / seg_tgt, rows = n_segs * ((seg_tgt + ct - 1) / ct);
+      const double units = (double)rows * (double)src_tiles, g = (double)ctx->sm_count * g_variants[v].minb;
+      const double share = units / g, ceil_share = share > (long long)share ? (long long)share + 1.0 : share;
+      *per_cta = share;
+      return rate * ((double)n_tgt / (double)(rows * ct)) * (share / (ceil_share > 0 ? ceil_share : 1.0));
+    };
+    double wide_share, mid_share;
+    const double e_wide = model(OCG_VARIANT_WIDE, 0.70, &wide_share), e_mid = model(OCG_VARIANT_MID, 0.668, &mid_share);
+    return (g_variants[OCG_VARIANT_WIDE].fn[0][0] && wide_share >= 6.0 && e_wide > e_mid) ? OCG_VARIANT_WIDE : OCG_VARIANT_MID;
+  }
   // fine_tiles (K4): a cluster has few target tiles, so the 512-target kernel balances better over the SMs than the
   // 3072-target one although its inner loop is ~1 point slower (tools/probe_k4.py: 65.0 vs 63.0 % at N = 65 536,
   // 64.8 vs 57.4 % at 16 x 16 384)
@@ -816,9 +835,14 @@ int ocg_direct_sum_impl(ocg_ctx* ctx, const float* src_xyzm, const float* src_so
     // Small snapshots (few, heavy particles: the reference's test_options scale) get a floor of 2^36 / n_src: their single
     // pair terms are a larger share of the field (configs[0], 1e6 particles: tidal residual 1.1e-5 strict with 16384 near
     // sources, 3.9e-6 with 65536, profiles/r02_accuracy_c0.json) and the whole call is milliseconds anyway.
-    long long cap = ctx->knobs.near_cap > 0 ? ctx->knobs.near_cap : n_src / 512;
-    const long long floor_cap = (1ll << 36) / (n_src > 0 ? n_src : 1);  // 68 719 at 1e6 particles, 6 871 at 1e7, everything below 2.6e5
+    // A source shard of a build over P ranks (ocg_set_source_shards) takes 1/P of the limit of the WHOLE build, so that
+    // the union of the ranks' sets is the unsharded call's (strided shards have the same distance histogram / P) and the
+    // FP64 pass does not grow with P (before: 2^36 / n_shard made it 17 % of a rank's step at P = 8 on configs[1]).
+    const long long P = ctx->source_shards > 1 ? ctx->source_shards : 1, n_all = n_src * P;
+    long long cap = ctx->knobs.near_cap > 0 ? ctx->knobs.near_cap : n_all / 512;
+    const long long floor_cap = (1ll << 36) / (n_all > 0 ? n_all : 1);  // 68 719 at 1e6 particles, 6 871 at 1e7, everything below 2.6e5
     if (ctx->knobs.near_cap <= 0 && cap < floor_cap) cap = floor_cap;
+    if (ctx->knobs.near_cap <= 0) cap = (cap + P - 1) / P;
     choose_radius_kernel<<<1, 1, 0, st>>>(misc, (int)cap, ctx->knobs.precise_near);
     OCG_CHECK_LAUNCH(ctx, "choose_radius_kernel");
   }

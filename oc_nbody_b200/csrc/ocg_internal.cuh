@@ -65,6 +65,7 @@ struct ocg_ctx {
   size_t scratch_bytes[OCG_SCR_N];
   unsigned long long scratch_generation;  // bumped whenever a scratch buffer is (re)allocated: its address changed
   long long launches;
+  int source_shards;  // ocg_set_source_shards: this ctx sees 1/n of the sources of a source-sharded field build
   int timing;
   cudaEvent_t ev0, ev1;
   int ev_valid;

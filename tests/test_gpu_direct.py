@@ -278,6 +278,31 @@ def test_field_direct_stream_k_passes(ctx, n_grid, want_pot):
         assert rel_err_scalar(p3, pref) <= TOL and rel_err_scalar(p9, pref) <= TOL
 
 
+def test_field_direct_source_shards_share_the_near_set_limit(ctx):
+    """ocg_set_source_shards(P): each of P strided source shards takes 1/P of the whole build's FP64 near-set limit; the
+    partial fields add up to the unsharded result within the parity tolerance of the oracle, and the shards' near sets
+    together are no larger than the unsharded one (the FP64 pass must not grow with the number of ranks)."""
+    rng = np.random.default_rng(91)
+    src, soft = random_sources(rng, 60000, box=3.0)
+    tgt = grid_targets(9)
+    ref, _ = oracle.field_direct(src, soft, tgt, oracle.KERNEL_PLUMMER, G, want_pot=False)
+    cond = oracle.field_direct_abs(src, soft, tgt, oracle.KERNEL_PLUMMER, G)
+    ctx.debug_set("near_cap", 0)
+    full, _ = run_k1(ctx, src, soft, tgt, oracle.KERNEL_PLUMMER)
+    P = 4
+    total = np.zeros_like(full)
+    try:
+        ctx.set_source_shards(P)
+        for r in range(P):
+            part, _ = run_k1(ctx, np.ascontiguousarray(src[r::P]), np.ascontiguousarray(soft[r::P]), tgt, oracle.KERNEL_PLUMMER)
+            total += part
+    finally:
+        ctx.set_source_shards(1)
+    assert rel_err(full, ref, abs_sum=cond) <= TOL and rel_err(total, ref, abs_sum=cond) <= TOL
+    with pytest.raises(Exception):
+        ctx.set_source_shards(0)
+
+
 def test_frame_subtract_and_host_form(ctx):
     import torch
     rng = np.random.default_rng(31)

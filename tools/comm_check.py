@@ -55,7 +55,9 @@ def main():
     s32 = torch.from_numpy(oracle.recentre(pos[sl], mass[sl], CENTER)).to(dev)
     t32 = oracle.recentre(g.evolved_grid, None, CENTER)
     acc = torch.empty((3, len(g)), dtype=torch.float64, device=dev)
+    ctx.set_source_shards(world)
     ctx.field_direct(s32, torch.from_numpy(eps[sl].astype(np.float32)).to(dev), torch.from_numpy(t32).to(dev), 0, G_KPC, acc)
+    ctx.set_source_shards(1)
     ctx.comm_allreduce_f64(acc)
     torch.cuda.synchronize()
     ref = oracle.field_direct(oracle.recentre(pos, mass, CENTER), eps.astype(np.float32), t32, 0, G_KPC)

@@ -20,22 +20,26 @@ def main():
     dev = torch.device("cuda", 0)
     nominal = ctx.sm_count * 128 * 2 * ctx.sm_clock_khz * 1e3 / 1e12
     out = []
-    for name, nseg, npc in (("n65536", 1, 65536), ("256x4096", 256, 4096), ("n16384", 1, 16384), ("16x16384", 16, 16384)):
+    # "shardK": the K targets [0, K) of one 65 536-star cluster — what one rank of 65536/K runs in the sharded BRIDGE step
+    for name, nseg, npc in (("n65536", 1, 65536), ("256x4096", 256, 4096), ("n16384", 1, 16384), ("16x16384", 16, 16384),
+                            ("shard8192", 1, 65536), ("shard16384", 1, 65536), ("shard32768", 1, 65536), ("n20000", 1, 20000)):
+        shard = int(name[5:]) if name.startswith("shard") else None
         pos_pc, _, mass = make_plummer_cluster(npc)
         pos = np.concatenate([pos_pc * 1e-3 + np.array([[8.0 + 0.01 * k], [0.0], [0.0]]) for k in range(nseg)], axis=1)
         m = np.tile(mass, nseg)
         seg = np.arange(nseg + 1, dtype=np.int64) * npc
         d_pos, d_m = torch.from_numpy(np.ascontiguousarray(pos)).to(dev), torch.from_numpy(m).to(dev)
         a = torch.empty((3, nseg * npc), dtype=torch.float64, device=dev)
-        inter = float(nseg) * npc * npc
-        for v in [-1] + [x for x in list(range(21, 37)) + [0, 4, 69, 70, 71, 72, 73] if ctx.variant_built(x)]:
+        inter = float(nseg) * npc * npc if shard is None else float(shard) * npc
+        for v in [-1] + [x for x in ([26, 27] if shard or name == "n20000" else list(range(21, 37)) + [0, 4, 69, 70, 71, 72, 73]) if ctx.variant_built(x)]:
             ctx.debug_set("direct_variant", v)
             ts = []
             try:
                 for rep in range(8):
                     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                     e0.record()
-                    ctx.self_gravity(d_pos, d_m, (0.01e-3) ** 2, G_KPC_KMS_MYR, a, None, seg_offsets=seg if nseg > 1 else None)
+                    ctx.self_gravity(d_pos, d_m, (0.01e-3) ** 2, G_KPC_KMS_MYR, a, None, seg_offsets=seg if nseg > 1 else None,
+                                     tgt_begin=0, tgt_end=shard)
                     e1.record()
                     torch.cuda.synchronize()
                     if rep >= 2:
