@@ -114,6 +114,10 @@ extern "C" int ocg_destroy(ocg_ctx* ctx) {
     if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
   cudaEventDestroy(ctx->ev0);
   cudaEventDestroy(ctx->ev1);
+  if (ctx->w_ring) {
+    for (int i = 0; i < 16; ++i) cudaEventDestroy(ctx->w_ring_ev[i]);
+    cudaFreeHost(ctx->w_ring);
+  }
   free(ctx->plan[0].items_host);
   free(ctx->plan[1].items_host);
   free(ctx);

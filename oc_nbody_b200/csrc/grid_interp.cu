@@ -408,12 +408,22 @@ extern "C" int ocg_set_interp_weight_slots(ocg_ctx* ctx, const double* weights_h
     return ocg_fail(ctx, OCG_ERR_INVALID, "ocg_set_interp_weight_slots: slots [%d, %d) outside [0, %d)", first_slot,
                     first_slot + n_slots, OCG_W_SLOTS);
   OcgDeviceGuard g(ctx->device);
-  float w[OCG_W_SLOTS][4];
+  // staged through a small pinned ring owned by the ctx: the copy is then truly asynchronous (a pageable source makes the
+  // runtime wait for the stream — i.e. for the previous graph replay — before it returns), and the source outlives the call
+  constexpr int RING = 16;
+  if (!ctx->w_ring) {
+    OCG_CUDA(ctx, cudaHostAlloc((void**)&ctx->w_ring, sizeof(float) * RING * OCG_W_SLOTS * 4, cudaHostAllocDefault));
+    for (int i = 0; i < RING; ++i) OCG_CUDA(ctx, cudaEventCreateWithFlags(&ctx->w_ring_ev[i], cudaEventDisableTiming));
+    ctx->w_ring_head = 0;
+  }
+  const unsigned e = ctx->w_ring_head++ % RING;
+  if (ctx->w_ring_head > RING) OCG_CUDA(ctx, cudaEventSynchronize(ctx->w_ring_ev[e]));  // 16 steps behind: long complete
+  float* w = ctx->w_ring + (size_t)e * OCG_W_SLOTS * 4;
   for (int k = 0; k < n_slots; ++k)
-    for (int r = 0; r < 4; ++r) w[k][r] = (float)weights_host[4 * k + r];
-  // pageable source: the runtime stages it before returning, so `w` may live on this stack frame
+    for (int r = 0; r < 4; ++r) w[4 * k + r] = (float)weights_host[4 * k + r];
   OCG_CUDA(ctx, cudaMemcpyToSymbolAsync(c_interp_w, w, sizeof(float) * 4 * n_slots, sizeof(float) * 4 * first_slot,
                                         cudaMemcpyHostToDevice, (cudaStream_t)stream));
+  OCG_CUDA(ctx, cudaEventRecord(ctx->w_ring_ev[e], (cudaStream_t)stream));
   return OCG_OK;
 }
 

@@ -65,6 +65,10 @@ struct ocg_ctx {
   size_t scratch_bytes[OCG_SCR_N];
   unsigned long long scratch_generation;  // bumped whenever a scratch buffer is (re)allocated: its address changed
   long long launches;
+  // pinned staging ring of ocg_set_interp_weight_slots (a pageable source would make the copy synchronise the stream)
+  float* w_ring;                    // [OCG_W_RING][16] floats, cudaHostAlloc'd on first use
+  cudaEvent_t w_ring_ev[16];        // recorded after the copy out of entry i; waited on before entry i is rewritten
+  unsigned w_ring_head;
   int source_shards;  // ocg_set_source_shards: this ctx sees 1/n of the sources of a source-sharded field build
   int timing;
   cudaEvent_t ev0, ev1;

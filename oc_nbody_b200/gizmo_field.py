@@ -21,6 +21,8 @@ What runs where
 Snapshot ingestion (gizmo_analysis/h5py), starting-star selection and the axisymmetric/agama mode are out
 of scope: snapshots are handed in as dict-likes with the fields the reference reads.
 """
+import os
+
 import numpy as np
 
 from . import _lib
@@ -123,6 +125,7 @@ class gizmo_field(object):
         self._origin = np.zeros(3)
         self._bracket = (0, min(1, nsnap - 1), 0.0)
         self._blend_cache = None
+        self.cache_unverified = []   # cache files loaded without a provenance sidecar (_check_provenance_)
         self._dev = None
         if build:
             self._init_grid_()
@@ -252,12 +255,56 @@ class gizmo_field(object):
         name, _ = self._grid_cache_name_(snapshot_index)
         return tuple(str(self.cache_directory) + '/' + name.replace('snapshot', 'snapshot_' + c) for c in ('x', 'y', 'z', 'pot'))
 
+    # ---- provenance sidecars: the reference's cache names do not carry everything that changes the cached numbers ----
+    def _cache_provenance_(self):
+        """What produced a cached field beyond what the reference's file name encodes (round-1 advice): the softening
+        kernel and lengths and the summation method.  Written as <cache file name>.provenance.json beside the cache."""
+        def num(v):
+            return None if v is None else float(v)
+        return {"producer": "oc_nbody_b200 direct sum (FP32 pair arithmetic, FP64 accumulation)",
+                "softening_kernel": str(self.softening_kernel), "plummer_eps_over_h": num(self.plummer_eps_over_h),
+                "star_softening_in_pc": num(self.star_softening_in_pc), "dark_softening_in_pc": num(self.dark_softening_in_pc),
+                "star_char_mass": num(self.star_char_mass), "dark_char_mass": num(self.dark_char_mass)}
+
+    def _write_provenance_(self, cache_path):
+        import json
+        with open(cache_path + ".provenance.json", "w") as fh:
+            json.dump(self._cache_provenance_(), fh, indent=1, sort_keys=True)
+
+    def _check_provenance_(self, cache_path):
+        """True: the sidecar matches these settings.  False: it does not — the cache is ignored and rebuilt.  None: no
+        sidecar, i.e. a cache the reference wrote (or an older run): accepted as the reference accepts it, but recorded in
+        ``cache_unverified`` with a warning — its numbers come from the theta = 0.5 tree (~1e-3 relative) with the
+        reference's softening, whatever this run's options say."""
+        import json
+        import warnings
+        try:
+            with open(cache_path + ".provenance.json") as fh:
+                have = json.load(fh)
+        except (OSError, ValueError):
+            self.cache_unverified.append(cache_path)
+            if len(self.cache_unverified) == 1:
+                warnings.warn("field cache %s has no provenance sidecar (written by the reference?): its values are used as they "
+                              "are — tree-code accuracy, the writer's softening settings" % cache_path)
+            return None
+        want = self._cache_provenance_()
+        if have != want:
+            diff = sorted(k for k in set(have) | set(want) if have.get(k) != want.get(k))
+            warnings.warn("field cache %s was written with other settings (%s): rebuilding" % (cache_path, ", ".join(diff)))
+            return False
+        return True
+
     def _load_snapshot_cache_(self, snapshot_index, n_points, want_pot):
-        """Pickled FP64 [Ngrid+1] arrays the reference (or this code) wrote; None on any miss or shape mismatch."""
+        """Pickled FP64 [Ngrid+1] arrays the reference (or this code) wrote; None on any miss, shape mismatch, or a
+        provenance sidecar that names other softening settings."""
         import pickle
         if self.cache_directory is None:
             return None
         files = self._snapshot_cache_files_(snapshot_index)
+        if not all(os.path.exists(f) for f in files[:4 if want_pot else 3]):
+            return None
+        if self._check_provenance_(self._grid_cache_name_(snapshot_index)[1]) is False:
+            return None
         try:
             out = []
             for f in files[:4 if want_pot else 3]:
@@ -272,7 +319,6 @@ class gizmo_field(object):
 
     def _dump_snapshot_cache_(self, snapshot_index, arrays):
         """pickle protocol 4 of each array into its own file (gizmo_interface.py:454-459,490-495)."""
-        import os
         import pickle
         if self.cache_directory is None:
             return
@@ -280,6 +326,7 @@ class gizmo_field(object):
         for f, a in zip(self._snapshot_cache_files_(snapshot_index), arrays):
             with open(f, 'wb') as fh:
                 pickle.dump(np.asarray(a, np.float64), fh, protocol=4)
+        self._write_provenance_(self._grid_cache_name_(snapshot_index)[1])
 
     def _init_grid_(self):
         """Per-snapshot grid loop (gizmo_interface.py:393-510): the whole-grid cache first (:395-398), else per snapshot load
@@ -292,8 +339,9 @@ class gizmo_field(object):
             self.endnum = self.snapshots[-1].snapshot["index"]
         self.cache_hits = 0
         self.grid_cache_hit = False
+        self.cache_unverified = []
         grid_cache_file = self._grid_cache_name_()[1] if self.cache_directory is not None else None
-        if grid_cache_file is not None:
+        if grid_cache_file is not None and os.path.exists(grid_cache_file) and self._check_provenance_(grid_cache_file) is not False:
             try:
                 cached = cache_compat.load_grid_pickle(grid_cache_file)
                 shape = (len(self.snapshots), len(self.grid))
@@ -327,6 +375,7 @@ class gizmo_field(object):
         self.grid.gen_evolved_grid(self._origin)
         if grid_cache_file is not None:
             cache_compat.dump_grid_pickle(self.grid, grid_cache_file)   # gizmo_interface.py:510
+            self._write_provenance_(grid_cache_file)
         self._upload_planes_()
 
     def set_snapshot_fields(self, acc_x, acc_y, acc_z, pot=None):

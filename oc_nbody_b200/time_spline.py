@@ -24,8 +24,9 @@ def fit(times, values):
 
 def basis(knots, x, k=3):
     """Non-zero B-spline basis functions at x: returns (first, w[k+1]) with
-    spline(x) = sum_{j=0..k} w[j] * coef[first + j].  x is clamped to the interpolation interval, like splev with
-    ext=0 evaluates the end polynomials (the reference never leaves the snapshot range)."""
+    spline(x) = sum_{j=0..k} w[j] * coef[first + j].  x is clamped to the interpolation interval: outside the snapshot
+    range the spline is HELD at its end value (splev's default ext=0 would extrapolate the end polynomials instead; the
+    reference never leaves the snapshot range, gizmo_interface.py:607-620, so the two never differ on its path)."""
     t = np.asarray(knots, np.float64)
     n = len(t) - k - 1
     x = float(min(max(x, t[k]), t[n]))

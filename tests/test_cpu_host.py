@@ -204,8 +204,9 @@ def test_snapshot_cache_names_and_format_follow_the_reference(tmp_path):
     arrs = [rng.normal(size=4097) for _ in range(3)]
     for path, a in zip(files[:3], arrs):
         pickle.dump(a, open(path, "wb"), protocol=4)
-    got = f._load_snapshot_cache_(580, 4097, want_pot=False)
-    assert got is not None and all(np.array_equal(g, a) for g, a in zip(got, arrs))
+    with pytest.warns(UserWarning, match="no provenance sidecar"):   # the reference writes none: accepted, but flagged
+        got = f._load_snapshot_cache_(580, 4097, want_pot=False)
+    assert got is not None and all(np.array_equal(g, a) for g, a in zip(got, arrs)) and len(f.cache_unverified) == 1
     assert f._load_snapshot_cache_(580, 4096, want_pot=False) is None
     assert f._load_snapshot_cache_(580, 4097, want_pot=True) is None      # no potential file: recompute
     assert f._load_snapshot_cache_(581, 4097, want_pot=False) is None
@@ -213,6 +214,11 @@ def test_snapshot_cache_names_and_format_follow_the_reference(tmp_path):
     f._dump_snapshot_cache_(581, arrs + [arrs[0] * 2])
     for path, a in zip(f._snapshot_cache_files_(581), arrs + [arrs[0] * 2]):
         assert np.array_equal(pickle.load(open(path, "rb")), a)
+    # ... plus a sidecar naming what the file name does not: a later run with another softening kernel rebuilds
+    assert f._load_snapshot_cache_(581, 4097, want_pot=True) is not None
+    f.softening_kernel = "plummer" if f.softening_kernel != "plummer" else "spline"
+    with pytest.warns(UserWarning, match="other settings"):
+        assert f._load_snapshot_cache_(581, 4097, want_pot=True) is None
     f.cache_directory = None
     assert f._load_snapshot_cache_(580, 4097, want_pot=False) is None
 

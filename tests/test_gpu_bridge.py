@@ -293,8 +293,10 @@ def test_field_code_snapshot_caches_round_trip(ctx, tmp_path):
     opts = dict(grid_x_size_in_kpc=0.06, grid_y_size_in_kpc=0.06, grid_z_size_in_kpc=0.06, grid_resolution=0.06 / 5,
                 cache_directory=str(tmp_path / "cache"))
     a = gizmo_field(opts, snaps, ctx=ctx)
-    # 2 snapshots x (x, y, z, pot) + the whole-grid pickle (gizmo_interface.py:510)
-    assert a.cache_hits == 0 and not a.grid_cache_hit and len(list((tmp_path / "cache").iterdir())) == 9
+    # 2 snapshots x (x, y, z, pot) + the whole-grid pickle (gizmo_interface.py:510), + one provenance sidecar for each of the 3
+    names = sorted(p.name for p in (tmp_path / "cache").iterdir())
+    assert a.cache_hits == 0 and not a.grid_cache_hit and len(names) == 12
+    assert sum(n.endswith(".provenance.json") for n in names) == 3
     os.remove(a._grid_cache_name_()[1])   # without the whole-grid file the per-snapshot caches serve the build
     b = gizmo_field(opts, snaps, ctx=ctx)
     assert b.cache_hits == 2 and not b.grid_cache_hit
@@ -303,6 +305,20 @@ def test_field_code_snapshot_caches_round_trip(ctx, tmp_path):
     c = gizmo_field(dict(opts, with_potential=False), snaps, ctx=ctx)   # b rewrote the whole-grid file: served from it
     assert c.grid_cache_hit and c.cache_hits == 0 and c.grid.snapshot_potential is None
     assert np.array_equal(c.grid.snapshot_acceleration_x, a.grid.snapshot_acceleration_x)
+    assert a.cache_unverified == [] and b.cache_unverified == [] and c.cache_unverified == []
+    # other softening settings under the same (reference-format) file names: the sidecars say so and the caches are rebuilt
+    with pytest.warns(UserWarning, match="other settings"):
+        d = gizmo_field(dict(opts, softening_kernel="plummer"), snaps, ctx=ctx)
+    assert not d.grid_cache_hit and d.cache_hits == 0
+    assert not np.array_equal(d.grid.snapshot_acceleration_x, a.grid.snapshot_acceleration_x)
+    # a cache without sidecars (what the reference writes) is accepted as the reference accepts it, flagged and warned about
+    for p in (tmp_path / "cache").iterdir():
+        if p.name.endswith(".provenance.json"):
+            p.unlink()
+    with pytest.warns(UserWarning, match="no provenance sidecar"):
+        e = gizmo_field(dict(opts, softening_kernel="plummer"), snaps, ctx=ctx)
+    assert e.grid_cache_hit and len(e.cache_unverified) == 1
+    assert np.array_equal(e.grid.snapshot_acceleration_x, d.grid.snapshot_acceleration_x)
 
 
 @pytest.mark.parametrize("graph", [False, True])

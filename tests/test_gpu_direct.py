@@ -119,7 +119,7 @@ def test_field_direct_edge_cases(ctx):
 
 # Shape ids of the streaming kernel (direct_sum.cu table; stable across builds).  The shipped library carries only the
 # production shapes; the sweep shapes and the timing experiments live in the separate OCG_TUNING build (tools/probe.py).
-PRODUCTION_PLAIN = [1, 4, 27, 31]      # SMALL, MID_GUARD, MID, BIG (plain tiles: K4, and K1 with mass folding off)
+PRODUCTION_PLAIN = [1, 4, 26, 27, 31]  # SMALL, MID_GUARD, WIDE, MID, BIG (plain tiles: K4, and K1 with mass folding off)
 PRODUCTION_MF_POT = [74, 80]           # BIG_MF_POT, MID_MF (mass-folded tiles, with or without potential)
 PRODUCTION_MASS_FOLDED = [67] + PRODUCTION_MF_POT  # 67 = BIG_MF (no potential form)
 TIMING_EXPERIMENTS = list(range(37, 40)) + list(range(48, 58))  # wrong results by construction
@@ -285,7 +285,7 @@ def test_field_direct_source_shards_share_the_near_set_limit(ctx):
     rng = np.random.default_rng(91)
     src, soft = random_sources(rng, 60000, box=3.0)
     tgt = grid_targets(9)
-    ref, _ = oracle.field_direct(src, soft, tgt, oracle.KERNEL_PLUMMER, G, want_pot=False)
+    ref = oracle.field_direct(src, soft, tgt, oracle.KERNEL_PLUMMER, G, want_pot=False)
     cond = oracle.field_direct_abs(src, soft, tgt, oracle.KERNEL_PLUMMER, G)
     ctx.debug_set("near_cap", 0)
     full, _ = run_k1(ctx, src, soft, tgt, oracle.KERNEL_PLUMMER)

@@ -21,7 +21,7 @@ KEYS = [
 
 def main():
     for arg in sys.argv[1:]:
-        title, path = arg.split("=", 1)
+        title, path = arg.rsplit("=", 1)  # the title may hold "="
         raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
         rows = list(csv.reader(io.StringIO(raw)))
         hdr, units = rows[0], rows[1]
