@@ -534,7 +534,7 @@ def main():
     traffic = NCU_DRAM_BYTES_PER_LAUNCH.get((args.grid, n_src))
     roofline = {"bound": "fp32", "achieved": achieved, "peak": nominal, "unit": "TFLOP/s", "frac": achieved / nominal,
                 "traffic": traffic, "traffic_model": ctx.last_direct_traffic_model(),
-                "kernel": "direct_sum_tp_kernel (target-paired, mass-folded tiles, FP32 runs of 64 sources folded into FP64; K1 fast set)",
+                "kernel": "direct_sum_tp_kernel (target-paired, mass-folded tiles, FP32 runs of 64 sources folded into FP64, folds staggered between the warps of a scheduler; K1 fast set)",
                 "kernel_ms": k_ms, "kernel_share_of_step": k_ms / ms_per_step,
                 "bound_note": "FP32 FMA-pipe bound (north_star: no tensor cores; HBM traffic negligible)",
                 "peak_kind": "nominal FP32: %d SM x 128 lanes x 2 flop x %.3f GHz (MEASURED_PEAKS.json has no FP32 entry)" % (

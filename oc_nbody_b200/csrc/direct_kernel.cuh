@@ -367,10 +367,11 @@ __global__ void __launch_bounds__(OCG_CONSUMER_THREADS + (DED ? 32 : 0), MINB) d
 // The price is the rounding of xs' = fl(w*xs): relative error 2^-24 |xs|/|d| in d', bounded because every
 // source closer to the target box than the precision radius is in the FP64 NEAR set (direct_sum.cu).
 // FOLD: sources per call (one FP32 accumulation run); `stage` points at the first of them inside the tile.
-template <int NP, bool POT, int UNR, int DBG, int MF = 0, int FOLD = OCG_TS>
+// RT: the number of 4-source groups comes at run time (`nj`, staggered folds) instead of FOLD / 4.
+template <int NP, bool POT, int UNR, int DBG, int MF = 0, int FOLD = OCG_TS, bool RT = false>
 __device__ __forceinline__ void tile_tpair(const float* __restrict__ stage, const u64 (&ntx)[NP], const u64 (&nty)[NP],
                                            const u64 (&ntz)[NP], u64 (&ax)[NP], u64 (&ay)[NP], u64 (&az)[NP],
-                                           u64 (&ap)[NP]) {
+                                           u64 (&ap)[NP], int nj = FOLD / 4) {
   const float4* sx = reinterpret_cast<const float4*>(stage);
   const float4* sy = sx + OCG_TS / 4;
   const float4* sz = sy + OCG_TS / 4;
@@ -379,7 +380,7 @@ __device__ __forceinline__ void tile_tpair(const float* __restrict__ stage, cons
   const float4* sv = se + OCG_TS / 4;  // mass-folded tiles with potential: 6th array, 1/w = (m/M0)^1/2
   float4 X0 = sx[0], Y0 = sy[0], Z0 = sz[0], M0 = sm[0], E0 = se[0];
 #pragma unroll UNR
-  for (int j = 0; j < FOLD / 4; ++j) {
+  for (int j = 0; j < (RT ? nj : FOLD / 4); ++j) {
     float4 X, Y, Z, M, E, V = make_float4(0.f, 0.f, 0.f, 0.f);
     if (DBG & 2) {
       X = X0, Y = Y0, Z = Z0, M = M0, E = E0;
@@ -445,8 +446,11 @@ __device__ __forceinline__ void tile_tpair(const float* __restrict__ stage, cons
 //             accumulators after FOLD sources; the rounding error of the FP32 running sums grows linearly with FOLD and
 //             is THE error term of the kernel (tools/sim_fp32_error.py: with exact accumulation the tidal residual is
 //             good to 7e-7 strict, with FOLD = 512 to 7e-5), so FOLD is the accuracy/throughput knob.
+//   STAG    : 0 = every warp folds at the same source indices.  1 / 2 = half of the warps (1: warps >= NW/2, 2: odd warps)
+//             fold half a run later (their first and last run of a tile are FOLD/2 long), so that the two warps of a
+//             scheduler are not both in the latency-bound fold at the same time.
 template <int NP, bool POT, bool SMEMACC, int MINB, int UNR, int NW = OCG_CONSUMER_WARPS, int DBG = 0, int MF = 0,
-          int FOLD = OCG_TS>
+          int FOLD = OCG_TS, int STAG = 0>
 __global__ void __launch_bounds__(32 * NW, MINB) direct_sum_tp_kernel(const DirectParams p) {
   static_assert(OCG_TS % FOLD == 0 && FOLD % 4 == 0, "FOLD must divide the tile");
   constexpr int NTHR = 32 * NW;
@@ -561,17 +565,8 @@ __global__ void __launch_bounds__(32 * NW, MINB) direct_sum_tp_kernel(const Dire
         issue_tile(it + OCG_NSTAGE - 1, src + (long long)(k + OCG_NSTAGE - 1) * TILE_FLOATS);
       const uint32_t s = it % OCG_NSTAGE, ph = (it / OCG_NSTAGE) & 1u;
       mbar_wait(&full_bar[s], ph);
-#pragma unroll 1
-      for (int b = 0; b < OCG_TS / FOLD; ++b) {
-        u64 ax[NP], ay[NP], az[NP], ap[NP];
-#pragma unroll
-        for (int pp = 0; pp < NP; ++pp) ax[pp] = ay[pp] = az[pp] = ap[pp] = 0ull;
-        tile_tpair<NP, POT, UNR, DBG, MF, FOLD>(stage_base + s * TILE_FLOATS + b * FOLD, ntx, nty, ntz, ax, ay, az, ap);
-        if (b == OCG_TS / FOLD - 1) {  // the stage has been read: hand it back before folding
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&empty_bar[s]);
-        }
-        // fold this run's FP32 sums into the FP64 accumulators (lane lo -> target 2p, hi -> target 2p+1)
+      // fold one run's FP32 sums into the FP64 accumulators (lane lo -> target 2p, hi -> target 2p+1)
+      auto fold_run = [&](const u64 (&ax)[NP], const u64 (&ay)[NP], const u64 (&az)[NP], const u64 (&ap)[NP]) {
 #pragma unroll
         for (int pp = 0; pp < NP; ++pp) {
           float v[4][2];
@@ -592,6 +587,38 @@ __global__ void __launch_bounds__(32 * NW, MINB) direct_sum_tp_kernel(const Dire
               dacc[SMEMACC ? 0 : 2 * pp + 1][c] += a1;
             }
           }
+        }
+      };
+      if (STAG == 0) {
+#pragma unroll 1
+        for (int b = 0; b < OCG_TS / FOLD; ++b) {
+          u64 ax[NP], ay[NP], az[NP], ap[NP];
+#pragma unroll
+          for (int pp = 0; pp < NP; ++pp) ax[pp] = ay[pp] = az[pp] = ap[pp] = 0ull;
+          tile_tpair<NP, POT, UNR, DBG, MF, FOLD>(stage_base + s * TILE_FLOATS + b * FOLD, ntx, nty, ntz, ax, ay, az, ap);
+          if (b == OCG_TS / FOLD - 1) {  // the stage has been read: hand it back before folding
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty_bar[s]);
+          }
+          fold_run(ax, ay, az, ap);
+        }
+      } else {
+        const int warp = tid >> 5;
+        const bool late = STAG == 1 ? warp >= NW / 2 : (warp & 1);
+        int off = 0, len = late ? FOLD / 2 : FOLD;
+#pragma unroll 1
+        while (off < OCG_TS) {
+          u64 ax[NP], ay[NP], az[NP], ap[NP];
+#pragma unroll
+          for (int pp = 0; pp < NP; ++pp) ax[pp] = ay[pp] = az[pp] = ap[pp] = 0ull;
+          tile_tpair<NP, POT, UNR, DBG, MF, FOLD, true>(stage_base + s * TILE_FLOATS + off, ntx, nty, ntz, ax, ay, az, ap, len / 4);
+          off += len;
+          len = OCG_TS - off < FOLD ? OCG_TS - off : FOLD;
+          if (off >= OCG_TS) {
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty_bar[s]);
+          }
+          fold_run(ax, ay, az, ap);
         }
       }
     }

@@ -544,6 +544,12 @@ static inline bool variant_is_tp(const DirectVariant& v) { return !strncmp(v.nam
     {direct_sum_tp_kernel<NP, false, SMEMACC, MINB, UNR, NW, 0, 2, FOLD>, nullptr},                      \
     { direct_sum_tp_kernel<NP, true, SMEMACC, MINB, UNR, NW, 0, 2, FOLD>, nullptr }                      \
   }
+/* the same with staggered folds (STAG: which half of the warps folds half a run later) */
+#define OCG_TPMFS(NP, MINB, UNR, NW, FOLD, STAG)                                                         \
+  {                                                                                                      \
+    {direct_sum_tp_kernel<NP, false, true, MINB, UNR, NW, 0, 2, FOLD, STAG>, nullptr},                   \
+    { direct_sum_tp_kernel<NP, true, true, MINB, UNR, NW, 0, 2, FOLD, STAG>, nullptr }                   \
+  }
 #define OCG_TPD(NP, SMEMACC, MINB, UNR, NW, DBG)                                                         \
   {                                                                                                      \
     {direct_sum_tp_kernel<NP, false, SMEMACC, MINB, UNR, NW, DBG>, nullptr}, { nullptr, nullptr }        \
@@ -618,7 +624,7 @@ static const DirectVariant g_variants[] = {
     /* 65 */ {"tpair-mf np4 16w x minb1, swizzled", 8, 1, false, TUNE(OCG_TPMFX(4, true, 1, 1, 16, 0, 2)), 8, 16, 2},
     // ---- round 2: FP32 accumulation runs shorter than the tile (FOLD) ----
     /* 66 */ {"tpair-mf np6 8w swizzled fold128", 12, 1, false, TUNE(OCG_TPMFF(6, 1, 1, 8, 128)), 12, 8, 2},
-    /* 67 */ {"tpair-mf np6 8w swizzled fold64", 12, 1, false, OCG_TPMFF(6, 1, 1, 8, 64), 12, 8, 2},  // production: BIG_MF
+    /* 67 */ {"tpair-mf np6 8w swizzled fold64", 12, 1, false, TUNE(OCG_TPMFF(6, 1, 1, 8, 64)), 12, 8, 2},
     /* 68 */ {"tpair-mf np6 8w swizzled fold32", 12, 1, false, TUNE(OCG_TPMFF(6, 1, 1, 8, 32)), 12, 8, 2},
     /* 69 */ {"tpair np4 12w fold128", 8, 1, false, TUNE(OCG_TPWF(4, true, 1, 1, 12, 128)), 8, 12},
     /* 70 */ {"tpair np4 12w fold64", 8, 1, false, TUNE(OCG_TPWF(4, true, 1, 1, 12, 64)), 8, 12},
@@ -626,13 +632,18 @@ static const DirectVariant g_variants[] = {
     /* 72 */ {"tpair np1 regacc minb2 unr2 fold64", 2, 2, false, TUNE(OCG_TPWF(1, false, 2, 2, OCG_CONSUMER_WARPS, 64)), 0},
     /* 73 */ {"tpair np1 regacc minb2 unr2 fold128", 2, 2, false, TUNE(OCG_TPWF(1, false, 2, 2, OCG_CONSUMER_WARPS, 128)), 0},
     // ---- mass-folded tiles with a potential form (6-array tiles), and for the mid-size target counts ----
-    /* 74 */ {"tpair-mf(+pot) np4 12w swizzled fold64", 8, 1, false, OCG_TPMFP(4, true, 1, 1, 12, 64), 8, 12, 2},  // production: BIG_MF_POT
+    /* 74 */ {"tpair-mf(+pot) np4 12w swizzled fold64", 8, 1, false, TUNE(OCG_TPMFP(4, true, 1, 1, 12, 64)), 8, 12, 2},
     /* 75 */ {"tpair-mf(+pot) np5 8w swizzled fold64", 10, 1, false, TUNE(OCG_TPMFP(5, true, 1, 1, 8, 64)), 10, 8, 2},
     /* 76 */ {"tpair-mf(+pot) np4 12w swizzled fold512", 8, 1, false, TUNE(OCG_TPMFP(4, true, 1, 1, 12, 512)), 8, 12, 2},
     /* 77 */ {"tpair-mf(+pot) np1 regacc minb2 unr2 swizzled fold32", 2, 2, false, TUNE(OCG_TPMFP(1, false, 2, 2, OCG_CONSUMER_WARPS, 32)), 0, 0, 2},
     /* 78 */ {"tpair-mf(+pot) np1 regacc minb2 unr2 swizzled fold512", 2, 2, false, TUNE(OCG_TPMFP(1, false, 2, 2, OCG_CONSUMER_WARPS, 512)), 0, 0, 2},
     /* 79 */ {"tpair-mf(+pot) np1 regacc minb2 unr2 swizzled fold64", 2, 2, false, TUNE(OCG_TPMFP(1, false, 2, 2, OCG_CONSUMER_WARPS, 64)), 0, 0, 2},
     /* 80 */ {"tpair-mf(+pot) np1 regacc minb2 unr2 swizzled fold16", 2, 2, false, OCG_TPMFP(1, false, 2, 2, OCG_CONSUMER_WARPS, 16), 0, 0, 2},  // production: MID_MF
+    // ---- staggered folds: the two warps of a scheduler fold half a run apart ----
+    /* 81 */ {"tpair-mf(+pot) np6 8w fold64, warps >= 4 fold half a run later", 12, 1, false, OCG_TPMFS(6, 1, 1, 8, 64, 1), 12, 8, 2},  // production: BIG_MF
+    /* 82 */ {"tpair-mf np6 8w fold64, odd warps fold half a run later", 12, 1, false, TUNE(OCG_TPMFS(6, 1, 1, 8, 64, 2)), 12, 8, 2},
+    /* 83 */ {"tpair-mf(+pot) np4 12w fold64, odd warps fold half a run later", 8, 1, false, TUNE(OCG_TPMFS(4, 1, 1, 12, 64, 2)), 8, 12, 2},
+    /* 84 */ {"tpair-mf np6 8w fold32, warps >= 4 fold half a run later", 12, 1, false, TUNE(OCG_TPMFS(6, 1, 1, 8, 32, 1)), 12, 8, 2},
 };
 static const int g_n_variants = (int)(sizeof(g_variants) / sizeof(g_variants[0]));
 // Production choices (tools/probe.py sweeps on B200, profiles/r01_variant_sweep*.json, profiles/r02_fold_sweep.json):
@@ -641,8 +652,11 @@ static const int g_n_variants = (int)(sizeof(g_variants) / sizeof(g_variants[0])
 //   plain tiles  FOLD 512: 2.0e-4 at 64.9 %              | 128: 1.4e-4 at 60.6 % | 64: 1.4e-4 at 59.9 % (no gain: their error is
 //   the rounding of d = x_s - x_t, coherent over all sources of one binade; the mass-folded d' = fma(-x_t, w, w x_s) dithers it)
 #define OCG_VARIANT_BIG 31        /* >= 64k targets, plain tiles: 8 targets/thread, 12 warps (mass folding switched off) */
-#define OCG_VARIANT_BIG_MF 67     /* K1 >= 64k targets: mass-folded, w-swizzled tiles, 12 targets/thread, 8 warps, FOLD 64 */
-#define OCG_VARIANT_BIG_MF_POT 74 /* the same with the potential: 6-array tiles, 8 targets/thread, 12 warps, FOLD 64 */
+#define OCG_VARIANT_BIG_MF 81     /* K1 >= 64k targets: mass-folded, w-swizzled tiles, 12 targets/thread, 8 warps, FOLD 64, the second
+                                     warp of every scheduler folding half a run after the first (tools/probe.py, 262 145 targets x
+                                     1e6 sources: 77.4 % against 76.6 % with all warps folding together; with the potential 61.5 %
+                                     against 60.7 % for the 8-target 12-warp shape it replaces) */
+#define OCG_VARIANT_BIG_MF_POT 81 /* the same kernel's potential form (6-array tiles) */
 #define OCG_VARIANT_MID 27        /* >= 16k targets, plain tiles (K4): target-paired, 2 targets/thread              */
 #define OCG_VARIANT_WIDE 26       /* K4 with >= 6 tiles per CTA: plain tiles, 8 targets/thread, 8 warps, 1 CTA/SM (tools/probe_k4.py:
                                      70.2 vs 66.8 % at N = 65 536, 68.1 vs 62.4 % at 256 x 4 096, 70.4 vs 65.9 % at 16 x 16 384; but

@@ -77,11 +77,34 @@ __device__ __forceinline__ int rbf_find_cell(const double* __restrict__ node, in
   return i;
 }
 
+// Polyharmonic splines of rbf.basis (options.py:178-202): phs<k> = r^k for odd k, r^k log r for even k (0 at r = 0).
+// (The package flips the sign of every other one to keep them conditionally positive definite; the interpolant does not
+// depend on the sign.)  In coordinates scaled by h, r^k log r = h^k [y^k log y + log h * y^k]: the second part is a
+// polynomial of degree k in the coordinates whose contribution the side conditions sum_j lambda_j q(y_j) = 0 reduce to a
+// polynomial of degree <= k - order - 1, i.e. it is absorbed by the polynomial part when order >= k/2 — the same
+// condition that makes the interpolant well posed — so y^k log y is the basis function used here.
 __device__ __forceinline__ double rbf_phi(double r2, int phs) {
-  // r^phs for odd phs
-  double r = sqrt(r2), v = r;
-  for (int q = 1; q < phs; q += 2) v *= r2;
-  return v;
+  if (phs & 1) {
+    double r = sqrt(r2), v = r;
+    for (int q = 1; q < phs; q += 2) v *= r2;
+    return v;
+  }
+  if (!(r2 > 0.0)) return 0.0;
+  double v = r2;
+  for (int q = 2; q < phs; q += 2) v *= r2;
+  return 0.5 * v * log(r2);
+}
+// phi'(r) / r: the radial derivative over r, the factor of (x - y) in the gradient of phi(|x - y|)
+__device__ __forceinline__ double rbf_dphi_over_r(double r2, int phs) {
+  if (phs & 1) {
+    double g = phs == 1 ? (r2 > 0.0 ? 1.0 / sqrt(r2) : 0.0) : sqrt(r2);
+    for (int t = 3; t < phs; t += 2) g *= r2;
+    return (double)phs * g;
+  }
+  if (!(r2 > 0.0)) return 0.0;
+  double v = 1.0;
+  for (int q = 2; q < phs; q += 2) v *= r2;
+  return v * (0.5 * (double)phs * log(r2) + 1.0);
 }
 
 // Entries of the saddle-point matrix in FP64.  Y [3][ncl] scaled coordinates, PT [3][order+1][ncl] their powers.
@@ -473,11 +496,9 @@ __global__ void __launch_bounds__(RBF_THREADS, 1) rbf_interp_kernel(const RbfPar
         const double r2 = x * x + y * y + z * z;
         if (r == 0) v = rbf_phi(r2, p.phs);
         else {
-          // d/dx_a of phi(|x - y_m|) at x = 0: -phs |y|^(phs-2) y_a
+          // d/dx_a of phi(|x - y_m|) at x = 0: -(phi'(|y|) / |y|) y_a
           const double ya = r == 1 ? x : (r == 2 ? y : z);
-          double g = p.phs == 1 ? (r2 > 0.0 ? 1.0 / sqrt(r2) : 0.0) : sqrt(r2);
-          for (int t = 3; t < p.phs; t += 2) g *= r2;
-          v = -(double)p.phs * g * ya;
+          v = -rbf_dphi_over_r(r2, p.phs) * ya;
         }
       } else {
         const unsigned char* pw = p.pw[i - ncl];
@@ -663,10 +684,10 @@ static int rbf_launch(ocg_ctx* ctx, const char* who, RbfParams& p, const ocg_gri
     return ocg_fail(ctx, OCG_ERR_INVALID, "%s: NULL argument", who);
   if (n_comp < 1 || n_comp > 4) return ocg_fail(ctx, OCG_ERR_INVALID, "%s: n_comp = %d outside [1,4]", who, n_comp);
   if (order < 0 || order > 5) return ocg_fail(ctx, OCG_ERR_INVALID, "%s: order = %d outside [0,5]", who, order);
-  if (phs != 1 && phs != 3 && phs != 5 && phs != 7)
-    return ocg_fail(ctx, OCG_ERR_INVALID, "%s: basis phs%d not supported (odd polyharmonic splines phs1/3/5/7)", who, phs);
-  if (order < (phs - 1) / 2)
-    return ocg_fail(ctx, OCG_ERR_INVALID, "%s: phs%d needs order >= %d to be well posed", who, phs, (phs - 1) / 2);
+  if (phs < 1 || phs > 8)
+    return ocg_fail(ctx, OCG_ERR_INVALID, "%s: basis phs%d not supported (polyharmonic splines phs1 .. phs8)", who, phs);
+  if (order < phs / 2)  // odd k: (k - 1) / 2, even k: k / 2 (also what makes the even ones independent of the length unit)
+    return ocg_fail(ctx, OCG_ERR_INVALID, "%s: phs%d needs order >= %d to be well posed", who, phs, phs / 2);
   int nm = 0;
   // monomials of total degree <= order, by degree
   for (int d = 0; d <= order; ++d)

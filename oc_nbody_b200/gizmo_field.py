@@ -100,10 +100,13 @@ class gizmo_field(object):
             raise ValueError("space_interpolation must be 'trilinear' or 'rbf'")
         if self.space_interpolation == "rbf":
             basis = getattr(self.basis, "__name__", None) or str(self.basis)  # a name or an rbf.basis object (options.py:178-246)
-            if basis not in ("phs1", "phs3", "phs5", "phs7"):
-                raise NotImplementedError("space_interpolation='rbf' implements the odd polyharmonic splines phs1/3/5/7, not %r" % (basis,))
+            if basis not in ("phs1", "phs2", "phs3", "phs4", "phs5", "phs6", "phs7", "phs8"):
+                raise NotImplementedError("space_interpolation='rbf' implements the polyharmonic splines phs1 .. phs8 of "
+                                          "options.py:178-202, not the shape-parameter bases (%r)" % (basis,))
             self._rbf_phs = int(basis[3:])
             self.nclose, self.order = int(self.nclose), int(self.order)
+            if self.order < self._rbf_phs // 2:
+                raise ValueError("basis %s needs order >= %d (the interpolant is not well posed below)" % (basis, self._rbf_phs // 2))
         self.G = G_KPC_KMS_MYR  # kpc^2 km/s /Myr /Msun, the unit of gizmo_interface.py:70
         self._ctx = ctx  # created lazily: host-side logic (source assembly, time bracketing) needs no GPU
         self.snapshots = list(snapshots)

@@ -400,6 +400,22 @@ def rbf_monomial_powers(order):
     return [(a, b, d - a - b) for d in range(order + 1) for a in range(d, -1, -1) for b in range(d - a, -1, -1)]
 
 
+def rbf_phs(r, phs):
+    """rbf.basis.phs<k> up to sign (options.py:178-202): r^k for odd k, r^k log r for even k (0 at r = 0)."""
+    r = np.asarray(r, np.float64)
+    if phs % 2:
+        return r ** phs
+    return np.where(r > 0, r ** phs * np.log(np.where(r > 0, r, 1.0)), 0.0)
+
+
+def rbf_phs_dr_over_r(r, phs):
+    """phi'(r) / r."""
+    r = np.asarray(r, np.float64)
+    if phs % 2:
+        return phs * np.where(r > 0, r ** (phs - 2), 0.0) if phs == 1 else phs * r ** (phs - 2)
+    return np.where(r > 0, r ** (phs - 2) * (phs * np.log(np.where(r > 0, r, 1.0)) + 1.0), 0.0)
+
+
 def rbf_interp_points(pts, fields, sx, sy, sz, h, nclose=150, order=5, phs=3, want_tensor=False, want_neighbors=False):
     """kNN(nclose) + RBF-PHS interpolation of `fields` [n_comp, n_pts] given on an arbitrary point list `pts` [n_pts, 3]
     (what gizmo_interface.py:651-717 does on grid.evolved_grid, nested or not).  Brute-force neighbour search ordered by
@@ -423,15 +439,15 @@ def rbf_interp_points(pts, fields, sx, sy, sz, h, nclose=150, order=5, phs=3, wa
         y = (pts[ids] - p) / h
         r = np.sqrt(((y[:, None, :] - y[None, :, :]) ** 2).sum(axis=-1))
         P = np.prod(y[:, None, :] ** pw[None, :, :], axis=-1)
-        A = np.block([[r ** phs, P], [P.T, np.zeros((nm, nm))]])
+        A = np.block([[rbf_phs(r, phs), P], [P.T, np.zeros((nm, nm))]])
         rhs = np.concatenate([fields[:, ids].T, np.zeros((nm, fields.shape[0]))])
         sol = np.linalg.solve(A, rhs)            # [nclose + nm, n_comp]: weights, then polynomial coefficients
         r0 = np.sqrt((y * y).sum(axis=1))
-        out[:, s] = (r0 ** phs) @ sol[:nclose] + sol[nclose]    # every monomial but the constant vanishes at the star
+        out[:, s] = rbf_phs(r0, phs) @ sol[:nclose] + sol[nclose]    # every monomial but the constant vanishes at the star
         if want_tensor:
             for a in range(3):
-                # d/dx_a at the star: -phs |y|^(phs-2) y_a for the radial part, the coefficient of x_a for the polynomial
-                g = -phs * np.where(r0 > 0, r0 ** (phs - 2), 0.0) * y[:, a]
+                # d/dx_a at the star: -(phi'(|y|)/|y|) y_a for the radial part, the coefficient of x_a for the polynomial
+                g = -rbf_phs_dr_over_r(r0, phs) * y[:, a]
                 lin = [k for k in range(nm) if pw[k].sum() == 1 and pw[k][a] == 1]
                 tensor[a, :, s] = (g @ sol[:nclose] + (sol[nclose + lin[0]] if lin else 0.0)) / h
     res = dict(out=out)

@@ -239,6 +239,11 @@ def test_reference_algorithm_options_are_validated_on_the_host():
         pass
     phs5.__name__ = "phs5"
     assert gizmo_field(dict(base, space_interpolation="rbf", basis=phs5), [_Snap()], build=False)._rbf_phs == 5
+    assert gizmo_field(dict(base, space_interpolation="rbf", basis="phs8"), [_Snap()], build=False)._rbf_phs == 8
+    with pytest.raises(ValueError):          # phs8 needs order >= 4
+        gizmo_field(dict(base, space_interpolation="rbf", basis="phs8", order=3), [_Snap()], build=False)
+    with pytest.raises(NotImplementedError):  # the shape-parameter bases of options.py:203-246
+        gizmo_field(dict(base, space_interpolation="rbf", basis="mq"), [_Snap()], build=False)
     with pytest.raises(ValueError):
         gizmo_field(dict(base, space_interpolation="cubic"), [_Snap()], build=False)
     with pytest.raises(NotImplementedError):

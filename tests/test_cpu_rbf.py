@@ -41,6 +41,44 @@ def test_rbf_oracle_matches_scipy_rbfinterpolator_and_ckdtree():
     assert np.allclose(res5["out"][0], ref5, rtol=1e-8, atol=1e-10)
 
 
+def test_rbf_even_polyharmonic_splines():
+    """phs2/4/6/8 of options.py:178-202 (r^k log r).  phs2 is scipy's thin_plate_spline kernel; the others have no scipy
+    counterpart and are pinned through the property that fixes them: with order >= k/2 the interpolant does not depend on
+    the length unit (the oracle works in coordinates scaled by the spacing h; scaling by 1 or by 7 h must give the same
+    values), it reproduces polynomials up to its order, and its gradient is the finite-difference one."""
+    from scipy.interpolate import RBFInterpolator
+    nodes, o, pts = lattice()
+    f = smooth_fields(pts)
+    rng = np.random.default_rng(14)
+    p = o + rng.uniform(-0.012, 0.012, (4, 3))
+    res2 = oracle.rbf_interp(nodes, o, f, p[:, 0], p[:, 1], p[:, 2], nclose=100, order=3, phs=2, want_tensor=True)
+    for c in range(4):
+        ref = RBFInterpolator(pts, f[c], neighbors=100, kernel="thin_plate_spline", degree=3)(p)
+        assert np.allclose(res2["out"][c], ref, rtol=1e-9, atol=1e-11)
+    h = nodes[0][1] - nodes[0][0]
+    for phs, order, nclose in ((2, 1, 60), (4, 2, 80), (6, 4, 120), (8, 5, 150)):
+        a = oracle.rbf_interp_points(pts, f, p[:, 0], p[:, 1], p[:, 2], h, nclose, order, phs, want_tensor=True)
+        b = oracle.rbf_interp_points(pts, f, p[:, 0], p[:, 1], p[:, 2], 7.0 * h, nclose, order, phs, want_tensor=True)
+        scale = np.abs(f).max()
+        assert np.max(np.abs(a["out"] - b["out"])) <= 1e-7 * scale, phs
+        assert np.max(np.abs(a["tensor"] - b["tensor"])) <= 1e-5 * np.abs(a["tensor"]).max(), phs
+        # gradient against central differences of the interpolant itself (same stencil: the step is tiny)
+        eps = 1e-7
+        for ax in range(3):
+            dp = np.zeros(3)
+            dp[ax] = eps
+            hi = oracle.rbf_interp_points(pts, f, p[:1, 0] + dp[0], p[:1, 1] + dp[1], p[:1, 2] + dp[2], h, nclose, order, phs)["out"]
+            lo = oracle.rbf_interp_points(pts, f, p[:1, 0] - dp[0], p[:1, 1] - dp[1], p[:1, 2] - dp[2], h, nclose, order, phs)["out"]
+            fd = (hi[:, 0] - lo[:, 0]) / (2 * eps)
+            assert np.allclose(a["tensor"][ax][:, 0], fd, rtol=2e-4, atol=2e-4 * np.abs(a["tensor"]).max()), (phs, ax)
+    # polynomial reproduction with an even spline
+    x, y, z = (pts - o).T * 10.0
+    poly = np.stack([1.0 + x - 2 * y + 0.5 * z, x * y * z - y ** 2])
+    X, Y, Z = (p - o).T * 10.0
+    got = oracle.rbf_interp(nodes, o, poly, p[:, 0], p[:, 1], p[:, 2], nclose=120, order=3, phs=4)["out"]
+    assert np.allclose(got, np.stack([1.0 + X - 2 * Y + 0.5 * Z, X * Y * Z - Y ** 2]), rtol=0, atol=1e-9)
+
+
 def test_rbf_reproduces_polynomials_up_to_its_order_and_their_gradients():
     nodes, o, pts = lattice()
     x, y, z = (pts - o).T * 10.0

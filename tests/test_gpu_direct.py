@@ -120,8 +120,8 @@ def test_field_direct_edge_cases(ctx):
 # Shape ids of the streaming kernel (direct_sum.cu table; stable across builds).  The shipped library carries only the
 # production shapes; the sweep shapes and the timing experiments live in the separate OCG_TUNING build (tools/probe.py).
 PRODUCTION_PLAIN = [1, 4, 26, 27, 31]  # SMALL, MID_GUARD, WIDE, MID, BIG (plain tiles: K4, and K1 with mass folding off)
-PRODUCTION_MF_POT = [74, 80]           # BIG_MF_POT, MID_MF (mass-folded tiles, with or without potential)
-PRODUCTION_MASS_FOLDED = [67] + PRODUCTION_MF_POT  # 67 = BIG_MF (no potential form)
+PRODUCTION_MF_POT = [81, 80]           # BIG_MF (= BIG_MF_POT), MID_MF (mass-folded tiles, with or without potential)
+PRODUCTION_MASS_FOLDED = PRODUCTION_MF_POT
 TIMING_EXPERIMENTS = list(range(37, 40)) + list(range(48, 58))  # wrong results by construction
 
 

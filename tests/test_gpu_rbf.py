@@ -81,7 +81,8 @@ def test_rbf_reproduces_degree_five_polynomials(ctx):
     assert np.allclose(tensor[1], 10.0 * np.stack([-2 * np.ones_like(X), -9 * X * Y ** 2 * Z]), rtol=0, atol=1e-6)
 
 
-@pytest.mark.parametrize("nclose,order,phs", [(80, 3, 5), (150, 5, 1), (120, 4, 3), (60, 2, 3), (149, 5, 7)])
+@pytest.mark.parametrize("nclose,order,phs", [(80, 3, 5), (150, 5, 1), (120, 4, 3), (60, 2, 3), (149, 5, 7),
+                                              (100, 3, 2), (80, 2, 4), (120, 4, 6), (150, 5, 8), (150, 5, 4)])
 def test_rbf_other_options(ctx, nclose, order, phs):
     nodes, o, pts = lattice(n=12, half=0.06)
     f = fields_of(pts, o)[:3]
@@ -141,7 +142,8 @@ def test_rbf_argument_errors(ctx):
     p = o + np.zeros((2, 3))
     out = torch.empty((4, 2), dtype=torch.float64, device="cuda")
     args = ((8, 8, 8), [dev(a) for a in nodes], dev(o[None]), dev(f), dev(p[:, 0]), dev(p[:, 1]), dev(p[:, 2]), None, out)
-    for kw in (dict(nclose=151), dict(order=6), dict(phs=2), dict(nclose=30, order=5), dict(phs=7, order=2)):
+    for kw in (dict(nclose=151), dict(order=6), dict(phs=9), dict(phs=0), dict(nclose=30, order=5), dict(phs=7, order=2),
+               dict(phs=8, order=3)):
         with pytest.raises(OcgError):
             ctx.grid_interp_rbf(*args, **kw)
     small = lattice(n=4)

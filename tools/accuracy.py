@@ -23,8 +23,8 @@ from oc_nbody_b200 import default_context  # noqa: E402
 from util import rel_err  # noqa: E402
 
 # (shape id, FOLD, wants potential)
-SHAPES = [(58, 512, False), (66, 128, False), (67, 64, False), (68, 32, False),
-          (31, 512, True), (70, 64, True), (76, 512, True), (74, 64, True), (75, 64, True), (78, 512, True), (77, 64, True)]
+SHAPES = [(58, 512, False), (66, 128, False), (67, 64, False), (81, 64, False), (68, 32, False),
+          (31, 512, True), (70, 64, True), (76, 512, True), (74, 64, True), (81, 64, True), (75, 64, True), (78, 512, True), (77, 64, True)]
 
 
 def main():
