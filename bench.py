@@ -39,12 +39,12 @@ sys.path.insert(0, ROOT)
 FLOP_PER_INTERACTION = 20.0  # GPU-Gems-3 ch.31 convention, acc only
 # (grid, sources on this GPU) -> DRAM bytes moved by one launch of the streaming kernel (ncu --set full, profiles/)
 NCU_DRAM_BYTES_PER_LAUNCH = {
-    # profiles/r02_ncu_dram_bench_full.csv: 313 820 672 B read (200 MB of tiles once — streamed in 32 MB passes that stay
-    # in L2: lts__t_bytes 18.2 GB — + targets + the partial slots of the shared rows read back) + 107 895 296 B written
-    # (partial slots + the FP64 field): 0.006 % of HBM bandwidth over the 956 ms launch.  History: r01 917 MB (667 MB of
+    # profiles/r02_ncu_dram_bench_full.csv: 308 637 696 B read (200 MB of tiles once — streamed in 32 MB passes that stay
+    # in L2: lts__t_bytes 18.3 GB — + targets + the partial slots of the shared rows read back) + 107 409 408 B written
+    # (partial slots + the FP64 field): 0.006 % of HBM bandwidth over the 949 ms launch.  History: r01 917 MB (667 MB of
     # chunk partials); stream-K without passes 9.14 GB (every row re-fetched the tiles from HBM,
     # profiles/r02_ncu_dram_before_passes.csv)
-    (64, 10000000): 313820672 + 107895296,
+    (64, 10000000): 308637696 + 107409408,
 }
 G_KPC = 4.398600413517813e-09
 CENTER = np.array([8.0, 0.0, 0.0])

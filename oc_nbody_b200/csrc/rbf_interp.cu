@@ -83,8 +83,10 @@ __device__ __forceinline__ int rbf_find_cell(const double* __restrict__ node, in
 // polynomial of degree k in the coordinates whose contribution the side conditions sum_j lambda_j q(y_j) = 0 reduce to a
 // polynomial of degree <= k - order - 1, i.e. it is absorbed by the polynomial part when order >= k/2 — the same
 // condition that makes the interpolant well posed — so y^k log y is the basis function used here.
+// EVEN is a template parameter of the kernel: the odd splines (the reference's default phs3) keep their log-free code.
+template <bool EVEN>
 __device__ __forceinline__ double rbf_phi(double r2, int phs) {
-  if (phs & 1) {
+  if (!EVEN) {
     double r = sqrt(r2), v = r;
     for (int q = 1; q < phs; q += 2) v *= r2;
     return v;
@@ -95,8 +97,9 @@ __device__ __forceinline__ double rbf_phi(double r2, int phs) {
   return 0.5 * v * log(r2);
 }
 // phi'(r) / r: the radial derivative over r, the factor of (x - y) in the gradient of phi(|x - y|)
+template <bool EVEN>
 __device__ __forceinline__ double rbf_dphi_over_r(double r2, int phs) {
-  if (phs & 1) {
+  if (!EVEN) {
     double g = phs == 1 ? (r2 > 0.0 ? 1.0 / sqrt(r2) : 0.0) : sqrt(r2);
     for (int t = 3; t < phs; t += 2) g *= r2;
     return (double)phs * g;
@@ -108,15 +111,17 @@ __device__ __forceinline__ double rbf_dphi_over_r(double r2, int phs) {
 }
 
 // Entries of the saddle-point matrix in FP64.  Y [3][ncl] scaled coordinates, PT [3][order+1][ncl] their powers.
+template <bool EVEN>
 __device__ __forceinline__ double rbf_k(int i, int j, int ncl, const double* __restrict__ Y, int phs) {
   const double dx = Y[i] - Y[j], dy = Y[ncl + i] - Y[ncl + j], dz = Y[2 * ncl + i] - Y[2 * ncl + j];
-  return rbf_phi(dx * dx + dy * dy + dz * dz, phs);
+  return rbf_phi<EVEN>(dx * dx + dy * dy + dz * dz, phs);
 }
 __device__ __forceinline__ double rbf_p(int m, int k, int ncl, int np1, const double* __restrict__ PT, const RbfParams& p) {
   const unsigned char* pw = p.pw[k];
   return PT[(0 * np1 + pw[0]) * ncl + m] * PT[(1 * np1 + pw[1]) * ncl + m] * PT[(2 * np1 + pw[2]) * ncl + m];
 }
 
+template <bool EVEN>
 __global__ void __launch_bounds__(RBF_THREADS, 1) rbf_interp_kernel(const RbfParams p) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int ncl = p.nclose, N = p.nclose + p.nmono, np1 = p.order + 1;
@@ -340,7 +345,7 @@ __global__ void __launch_bounds__(RBF_THREADS, 1) rbf_interp_kernel(const RbfPar
     // ---- 2. assemble (FP64 -> FP32) and factorise ----------------------------------------------------------
     if (tid < ncl) {  // row of a data point: K | P
 #pragma unroll 4
-      for (int j = 0; j < ncl; ++j) A[j * RBF_LDA + tid] = (float)rbf_k(tid, j, ncl, Y, p.phs);
+      for (int j = 0; j < ncl; ++j) A[j * RBF_LDA + tid] = (float)rbf_k<EVEN>(tid, j, ncl, Y, p.phs);
 #pragma unroll 4
       for (int k = 0; k < p.nmono; ++k) A[(ncl + k) * RBF_LDA + tid] = (float)rbf_p(tid, k, ncl, np1, PT, p);
     } else if (tid < N) {  // row of a monomial: P' | 0
@@ -494,11 +499,11 @@ __global__ void __launch_bounds__(RBF_THREADS, 1) rbf_interp_kernel(const RbfPar
       if (i < ncl) {
         const double x = Y[i], y = Y[ncl + i], z = Y[2 * ncl + i];
         const double r2 = x * x + y * y + z * z;
-        if (r == 0) v = rbf_phi(r2, p.phs);
+        if (r == 0) v = rbf_phi<EVEN>(r2, p.phs);
         else {
           // d/dx_a of phi(|x - y_m|) at x = 0: -(phi'(|y|) / |y|) y_a
           const double ya = r == 1 ? x : (r == 2 ? y : z);
-          v = -rbf_dphi_over_r(r2, p.phs) * ya;
+          v = -rbf_dphi_over_r<EVEN>(r2, p.phs) * ya;
         }
       } else {
         const unsigned char* pw = p.pw[i - ncl];
@@ -523,7 +528,7 @@ __global__ void __launch_bounds__(RBF_THREADS, 1) rbf_interp_kernel(const RbfPar
           if (tid < ncl) {
 #pragma unroll 4
             for (int j = 0; j < ncl; ++j) {
-              const double e = rbf_k(tid, j, ncl, Y, p.phs);
+              const double e = rbf_k<EVEN>(tid, j, ncl, Y, p.phs);
 #pragma unroll
               for (int r = 0; r < RBF_NRHS_MAX; ++r)
                 if (r < nrhs) acc[r] += e * U[r * N + j];
@@ -714,9 +719,10 @@ static int rbf_launch(ocg_ctx* ctx, const char* who, RbfParams& p, const ocg_gri
   const size_t smem = rbf_smem_bytes(nclose + nm, nclose, order + 1);
   if (smem > 227 * 1024)
     return ocg_fail(ctx, OCG_ERR_INVALID, "%s: nclose = %d, order = %d need %zu bytes of shared memory", who, nclose, order, smem);
-  OCG_CUDA(ctx, cudaFuncSetAttribute((const void*)rbf_interp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  void (*kern)(const RbfParams) = (phs & 1) ? rbf_interp_kernel<false> : rbf_interp_kernel<true>;
+  OCG_CUDA(ctx, cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int grid_dim = (int)(n_star < ctx->sm_count ? n_star : ctx->sm_count);
-  rbf_interp_kernel<<<grid_dim, RBF_THREADS, smem, (cudaStream_t)stream>>>(p);
+  kern<<<grid_dim, RBF_THREADS, smem, (cudaStream_t)stream>>>(p);
   OCG_CHECK_LAUNCH(ctx, "rbf_interp_kernel");
   return OCG_OK;
 }
