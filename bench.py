@@ -227,8 +227,10 @@ def workload_config(args, n_gpus):
             "grid": args.grid, "n_targets": args.grid ** 3 + 1, "n_sources_total": args.n_src_total,
             "softening": "plummer, per-source epsilon", "scaling": args.scaling,
             "parallelism": "source-sharded (every n-th particle) + NCCL all-reduce(fp64) over the ranks; 1 rank = single GPU",
-            "l2_policy": "inputs larger than L2 at N=1 (%.0f MB of sources vs 126 MB L2); at N>1 the FP64 chunk partials "
-                         "(> 600 MB per step) flush L2 between steps" % (args.n_src_total * 20 / 1e6)}
+            "l2_policy": ("inputs larger than L2 (%.0f MB of source tiles per GPU vs 126 MB L2)" % (args.n_src_total * 20 / 1e6 / n_gpus)
+                          if args.n_src_total * 20 / n_gpus > 2 * 126e6 or (n_gpus == 1 and args.n_src_total * 20 > 126e6) else
+                          "L2 flushed before every timed step (a 256 MB buffer is overwritten, outside the step's CUDA events): "
+                          "%.0f MB of source tiles per GPU would fit the 126 MB L2" % (args.n_src_total * 20 / 1e6 / n_gpus))}
 
 
 def cpu_bridge_step_ms(n_stars, steps):
@@ -333,7 +335,8 @@ def bridge_step_times(ctx):
 
 def k4_roofline(ctx, nominal):
     """Second roofline entry (driver-run): K4 cluster self-gravity at configs[2]'s N = 65 536 (4.29e9 interactions per
-    evaluation), whole evaluation (pack + kernel + finish) timed with CUDA events, L2 flushed by the >126 MB partials."""
+    evaluation), whole evaluation (pack + stream-K kernel, two launches) timed with CUDA events; `frac_kernel_alone` from the
+    library's own events around the kernel.  The 1.3 MB of source tiles are L2-resident by design (every row streams them)."""
     import torch
     from oc_nbody_b200.synthetic import make_plummer_cluster
     n = 65536
@@ -357,7 +360,7 @@ def k4_roofline(ctx, nominal):
     ms, kms = float(np.median(ts)), float(np.median(ks))
     inter = float(n) * n
     ach = FLOP_PER_INTERACTION * inter / (ms * 1e-3) / 1e12
-    return {"bound": "fp32", "kernel": "K4 ocg_self_gravity, N = 65536 (configs[2]): pack + direct_sum_tp_kernel + finish",
+    return {"bound": "fp32", "kernel": "K4 ocg_self_gravity, N = 65536 (configs[2]): pack + direct_sum_tp_kernel (wide rows, stream-K, finish fused)",
             "achieved": ach, "peak": nominal, "unit": "TFLOP/s", "frac": ach / nominal, "traffic": None,
             "ms_per_evaluation": ms, "kernel_ms": kms, "frac_kernel_alone": FLOP_PER_INTERACTION * inter / (kms * 1e-3) / 1e12 / nominal,
             "interactions_per_launch": inter, "flop_per_interaction": FLOP_PER_INTERACTION}
@@ -456,17 +459,37 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    # timing rule: inputs larger than L2, or L2 flushed between timed iterations.  One rank's source tiles are
+    # n_src * 20 B: above the L2 at N = 1 on configs[1] (200 MB), below it once the snapshot is split over more ranks
+    need_flush = not (n_src * 20 > 2 * 126e6 or (world == 1 and n_src * 20 > 126e6))
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev) if need_flush else None
+
     def timed(fn, steps, kernel_ms=None):
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
-        e0.record()
-        for _ in range(steps):
-            fn()
-            if kernel_ms is not None:
-                kernel_ms.append(ctx.last_direct_kernel_ms())
-        e1.record()
-        barrier()
-        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if flush_buf is None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                fn()
+                if kernel_ms is not None:
+                    kernel_ms.append(ctx.last_direct_kernel_ms())
+            e1.record()
+            barrier()
+            total = e0.elapsed_time(e1)
+        else:  # per-step events, the flush between them untimed; the steps' device times are added up
+            evs = []
+            for _ in range(steps):
+                flush_buf.fill_(1)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                fn()
+                e1.record()
+                evs.append((e0, e1))
+                if kernel_ms is not None:
+                    kernel_ms.append(ctx.last_direct_kernel_ms())
+            barrier()
+            total = sum(a.elapsed_time(b) for a, b in evs)
+        ms = torch.tensor([total], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
@@ -494,7 +517,7 @@ def main():
                   "metric": "max_c |a - a_ref| / max(|a_ref,c|, 1e-3 ||a_ref||), FP64 oracle on the same FP32-rounded inputs",
                   "raw_field": rel_err(got_rows, ref),
                   "tidal_residual": rel_err((got_rows - got_rows[:, o:o + 1])[:, keep], (ref - ref[:, o:o + 1])[:, keep])}
-        parity["ok"] = bool(parity["raw_field"] <= 1e-5)
+        parity["ok"] = bool(parity["raw_field"] <= 1e-5 and parity["tidal_residual"] <= 1e-5)
         del s32, fp, fm, fe
 
     # ---- resident (device-timed) ----

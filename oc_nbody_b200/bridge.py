@@ -11,8 +11,8 @@ When both the kicked system and its partner are this package's GPU codes the kic
 (``partner.kick_device``): K3 gather + K5 update, no host copies.  Any other partner is kicked through the
 public ``get_gravity_at_point(eps, x, y, z)``.
 
-``use_cuda_graph=True``: for that device-resident pair the whole step (K3, K5, K4 with its pack and finish kernels,
-K5 ... — 10 launches) is captured once into a CUDA graph and replayed with ONE launch per step.  What changes from
+``use_cuda_graph=True``: for that device-resident pair the whole step (K3, K5, K4 = pack + stream-K kernel,
+K5 ... — 9 launches) is captured once into a CUDA graph and replayed with ONE launch per step.  What changes from
 step to step — the time-blend weights of the two half-kicks — lives in constant memory and is refreshed before each
 replay (ocg_set_interp_weight_slots); the grid origin is a device buffer.  The graph is re-captured when the
 bracketing snapshots, the particle count, the timestep or the capture epoch of a context (scratch reallocated, another

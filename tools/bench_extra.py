@@ -107,7 +107,7 @@ def main():
         med, best = timeit(k4)
         inter = float(nseg) * npc * npc
         out[name] = dict(ms_median=med, ms_best=best, interactions=inter, ginter_s=inter / med / 1e6,
-                         pct_fp32_peak=100 * 20 * inter / med / 1e9 / nominal, note="pack + kernel + finish per call")
+                         pct_fp32_peak=100 * 20 * inter / med / 1e9 / nominal, note="pack + kernel per call (finish fused into the kernel)")
 
     # ---- configs[3] as a whole: one BRIDGE step of 256 clusters x 4096 stars, each kicked by its own 32^3 grid ----
     from oc_nbody_b200.cluster import KMS_TO_KPC_PER_MYR

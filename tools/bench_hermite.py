@@ -77,7 +77,7 @@ def main():
                                 pct_fma_pipe_slots=100 * 2 * OPS * inter / med / 1e9 / nominal,
                                 kernel_pct_fp32_peak=(100 * FLOP * inter / kms / 1e9 / nominal) if kms > 0 else None)
         ctx.debug_set("hermite_variant", -1)
-        out[name] = dict(interactions=inter, note="pack + kernel + finish per call (small: one fused launch)", variants=res)
+        out[name] = dict(interactions=inter, note="pack + kernel per call, finish fused (small: one fused launch)", variants=res)
 
     # ---- the same force loop on the host cores (the oracle's FP64 OpenMP restatement; bounded sample of N = 65 536) ----
     if "--no-cpu-baseline" not in sys.argv:
