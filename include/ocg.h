@@ -309,6 +309,13 @@ int ocg_comm_allreduce_f64(ocg_ctx* ctx, double* buf_dev, int64_t n, void* strea
  * rank's target rows.  eps2 > 0.                                                                                    */
 int ocg_self_gravity_sharded(ocg_ctx* ctx, const double* pos_local_dev, const double* mass_all_dev, int64_t n, double eps2,
                              double G, double* acc_local_dev, double* pot_local_dev, void* stream);
+/* The same for the Hermite force (K6, oc_code.py:218-229 with ph4): the rank's block of positions AND velocities
+ * ([3][n_local] each) is published, all blocks are read through the mapped windows and packed into the 7-array tiles.
+ * acc_dev / jerk_dev ([3][n]) and pot_dev ([n] or NULL) are FULL-size arrays of which the rank's rows [a, b) are written
+ * (the layout ocg_self_gravity_hermite uses for a target range).  Needs a window of 144 * ceil(n / nranks) bytes. */
+int ocg_self_gravity_hermite_sharded(ocg_ctx* ctx, const double* pos_local_dev, const double* vel_local_dev,
+                                     const double* mass_all_dev, int64_t n, double eps2, double G, double vel_to_len,
+                                     double* acc_dev, double* jerk_dev, double* pot_dev, void* stream);
 
 /* ---- K6: Hermite force loop + 4th-order Hermite predictor / corrector ------
  * The arithmetic of the ph4 worker itself (4th-order Hermite, oc_code.py:218-229; options.py:248-253):

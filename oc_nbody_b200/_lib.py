@@ -22,7 +22,7 @@ ABI_SYMBOLS = [
     "ocg_version", "ocg_create", "ocg_destroy", "ocg_last_error", "ocg_device_info", "ocg_launch_count", "ocg_capture_epoch",
     "ocg_last_direct_kernel_ms", "ocg_set_kernel_timing", "ocg_set_source_shards", "ocg_last_direct_traffic_bytes", "ocg_recentre_f64", "ocg_cast_f64_f32", "ocg_assemble_sources",
     "ocg_field_direct", "ocg_frame_subtract", "ocg_field_build_host", "ocg_pack_planes", "ocg_grid_time_blend",
-    "ocg_grid_interp", "ocg_grid_interp_multi", "ocg_grid_interp_nested", "ocg_pack_planes_indexed", "ocg_set_interp_weight_slots", "ocg_grid_interp_slot", "ocg_grid_interp_rbf", "ocg_grid_interp_rbf_nested", "ocg_self_gravity", "ocg_self_gravity_hermite", "ocg_hermite_predict", "ocg_hermite_correct", "ocg_hermite_block_evolve", "ocg_bound_com", "ocg_eject_mask", "ocg_compact_rows", "ocg_kick", "ocg_drift", "ocg_axpy", "ocg_probe_throughput", "ocg_comm_create", "ocg_comm_connect", "ocg_comm_destroy", "ocg_comm_info", "ocg_comm_status", "ocg_comm_allreduce_f64", "ocg_self_gravity_sharded",
+    "ocg_grid_interp", "ocg_grid_interp_multi", "ocg_grid_interp_nested", "ocg_pack_planes_indexed", "ocg_set_interp_weight_slots", "ocg_grid_interp_slot", "ocg_grid_interp_rbf", "ocg_grid_interp_rbf_nested", "ocg_self_gravity", "ocg_self_gravity_hermite", "ocg_hermite_predict", "ocg_hermite_correct", "ocg_hermite_block_evolve", "ocg_bound_com", "ocg_eject_mask", "ocg_compact_rows", "ocg_kick", "ocg_drift", "ocg_axpy", "ocg_probe_throughput", "ocg_comm_create", "ocg_comm_connect", "ocg_comm_destroy", "ocg_comm_info", "ocg_comm_status", "ocg_comm_allreduce_f64", "ocg_self_gravity_sharded", "ocg_self_gravity_hermite_sharded",
 ]
 
 
@@ -117,6 +117,7 @@ def load_library():
     L.ocg_comm_status.argtypes = [vp, vp]
     L.ocg_comm_allreduce_f64.argtypes = [vp, vp, i64, vp]
     L.ocg_self_gravity_sharded.argtypes = [vp, vp, vp, i64, dbl, dbl, vp, vp, vp]
+    L.ocg_self_gravity_hermite_sharded.argtypes = [vp, vp, vp, vp, i64, dbl, dbl, dbl, vp, vp, vp, vp]
     L.ocg_probe_throughput.restype = dbl
     L.ocg_probe_throughput.argtypes = [vp, ctypes.c_int]
     _lib = L
@@ -470,6 +471,14 @@ class Context:
         self._ck(self.lib.ocg_self_gravity_sharded(self.h, _dptr(pos_local), _dptr(mass_all), mass_all.shape[0], float(eps2),
                                                    float(G), _dptr(acc_local), _dptr(pot_local), self._stream()),
                  "ocg_self_gravity_sharded")
+
+    def self_gravity_hermite_sharded(self, pos_local, vel_local, mass_all, eps2, G, vel_to_len, acc_all, jerk_all, pot_all=None):
+        """K6 for this rank's block of stars, positions + velocities gathered over peer memory inside the tile pack.  The
+        outputs are full-size [3, n] / [n] arrays of which the rank's rows [a, b) are written."""
+        self._ck(self.lib.ocg_self_gravity_hermite_sharded(self.h, _dptr(pos_local), _dptr(vel_local), _dptr(mass_all),
+                                                           mass_all.shape[0], float(eps2), float(G), float(vel_to_len),
+                                                           _dptr(acc_all), _dptr(jerk_all), _dptr(pot_all), self._stream()),
+                 "ocg_self_gravity_hermite_sharded")
 
     # ---- host-buffer call (numpy in, numpy out; H2D/D2H inside) ----
     def field_build_host(self, src_pos, src_mass, src_soft, tgt_pos, center, center_row, kernel, G, want_pot=False):

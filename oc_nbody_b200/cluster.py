@@ -317,9 +317,9 @@ class sharded_cluster_code(cluster_code):
 
     def __init__(self, mass, pos, vel, softening_pc=0.01, substeps=1, eject_cut=None, ctx=None, group=None,
                  integrator="leapfrog", eta=0.14, exchange="peer"):
-        """exchange="peer": the position gather of the leapfrog force runs over peer memory, fused into the tile pack
-        (ocg_self_gravity_sharded: 2 launches per evaluation); "nccl": torch.distributed all-gather + copy + K4 with a
-        target range (also what the Hermite force, which needs velocities too, uses)."""
+        """exchange="peer": the gather of the force evaluation runs over peer memory, fused into the tile pack
+        (ocg_self_gravity_sharded; ocg_self_gravity_hermite_sharded for positions + velocities: 2 launches per evaluation);
+        "nccl": torch.distributed all-gather + copy + the force kernel with a target range."""
         import torch.distributed as dist
         from .distributed import shard_range
         if exchange not in ("peer", "nccl"):
@@ -343,14 +343,22 @@ class sharded_cluster_code(cluster_code):
             self._jerk_all = torch.empty((3, self.n_total), dtype=torch.float64, device=self._dev)
         self.key = np.arange(self.a, self.b)
         self._peer = False
-        if exchange == "peer" and integrator == "leapfrog" and self.parameters._eps2_kpc2 > 0.0 and self.n_total // self.world >= 2048:
+        if exchange == "peer" and self.parameters._eps2_kpc2 > 0.0 and self.n_total // self.world >= 2048:
             from .distributed import connect_comm
-            connect_comm(self.ctx, group, window_bytes=max(1 << 20, 64 * (self.n_total // self.world + 1)))
+            # 2 x 3 doubles per star of a block for the K4 exchange + 2 x 6 behind them for the Hermite one
+            connect_comm(self.ctx, group, window_bytes=max(1 << 20, 160 * (self.n_total // self.world + 1)))
             self._peer = True
 
     def _force_hermite_(self, pos, vel, acc, jerk):
         """K6 for the rank's target block: positions AND velocities are all-gathered (the jerk needs both)."""
         from .distributed import allgather_particles
+        if self._peer:
+            # one kernel publishes this block's positions and velocities, reads the peers' over NVLink and packs the tiles
+            self.ctx.self_gravity_hermite_sharded(pos, vel, self.mass_all, self.parameters._eps2_kpc2, self.G, KMS_TO_KPC_PER_MYR,
+                                                  self._acc_all, self._jerk_all)
+            acc.copy_(self._acc_all[:, self.a:self.b])
+            jerk.copy_(self._jerk_all[:, self.a:self.b])
+            return
         pos_all = allgather_particles(pos, self.n_total, self.group).contiguous()
         vel_all = allgather_particles(vel, self.n_total, self.group).contiguous()
         self.ctx.self_gravity_hermite(pos_all, vel_all, self.mass_all, self.parameters._eps2_kpc2, self.G, KMS_TO_KPC_PER_MYR,

@@ -222,6 +222,62 @@ __global__ void __launch_bounds__(256) comm_gather_pack_kernel(CommPeers pr, con
   if (comm_last_cta(me, 4, &s_flag) && threadIdx.x == 0) me->epoch[0] = e;
 }
 
+// The same for K6 (hermite.cu): positions AND velocities are published ([6][n_local] per rank, channel 3 of the window
+// header), and the tiles are the 7-array Hermite tiles, recentred on star 0 in position and velocity exactly as
+// pack_hermite_kernel does for resident arrays.
+__global__ void __launch_bounds__(256) comm_gather_pack_hermite_kernel(CommPeers pr, const double* __restrict__ pos_local,
+                                                                       const double* __restrict__ vel_local,
+                                                                       const double* __restrict__ mass_all, long long n,
+                                                                       long long max_local, float scale, long long total_tiles,
+                                                                       float* __restrict__ tiles, float4* __restrict__ tgt_pos,
+                                                                       float4* __restrict__ tgt_vel) {
+  __shared__ int s_flag;
+  __shared__ unsigned long long s_epoch;
+  __shared__ double s_c[6];
+  CommHeader* me = hdr(pr.base[pr.rank]);
+  if (threadIdx.x == 0) s_epoch = me->epoch[3] + 1;
+  __syncthreads();
+  const unsigned long long e = s_epoch;
+  const int P = pr.nranks, r = pr.rank;
+  const long long a = shard_begin(n, P, r), n_local = shard_begin(n, P, r + 1) - a;
+  const long long tid = blockIdx.x * (long long)blockDim.x + threadIdx.x, nthr = (long long)gridDim.x * blockDim.x;
+  // its own region of the window, behind the two position buffers of the K4 exchange, double-buffered by epoch parity
+  const long long buf_off = 6 * max_local + (long long)(e & 1ull) * 6 * max_local;
+  double* mine = win_data(pr.base[r]) + buf_off;
+  for (long long i = tid; i < 3 * n_local; i += nthr) {
+    const long long c = i / n_local, k = i - c * n_local;
+    mine[c * max_local + k] = pos_local[i];
+    mine[(3 + c) * max_local + k] = vel_local[i];
+  }
+  if (comm_last_cta(me, 5, &s_flag) && threadIdx.x == 0) comm_signal_all(pr, 3, e);
+  if (threadIdx.x == 0) s_flag = comm_wait_all(pr, 3, e) ? 1 : 0;
+  __syncthreads();
+  const bool ok = s_flag != 0;
+  if (threadIdx.x < 6) s_c[threadIdx.x] = ok ? ld_peer(win_data(pr.base[0]) + buf_off + threadIdx.x * max_local) : 0.0;  // star 0
+  __syncthreads();
+  for (long long slot = tid; slot < total_tiles * HM_TS; slot += nthr) {
+    const long long tile = slot / HM_TS;
+    const int j = (int)(slot - tile * HM_TS);
+    float* T = tiles + tile * (long long)HM_TILE_FLOATS;
+    float v[HM_NARR] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (slot < n && ok) {
+      const int q = shard_owner(n, P, slot);
+      const double* src = win_data(pr.base[q]) + buf_off + (slot - shard_begin(n, P, q));
+      const float x = (float)(ld_peer(src) - s_c[0]), y = (float)(ld_peer(src + max_local) - s_c[1]);
+      const float z = (float)(ld_peer(src + 2 * max_local) - s_c[2]);
+      const float vx = (float)(ld_peer(src + 3 * max_local) - s_c[3]), vy = (float)(ld_peer(src + 4 * max_local) - s_c[4]);
+      const float vz = (float)(ld_peer(src + 5 * max_local) - s_c[5]);
+      const float m = (float)mass_all[slot];
+      v[0] = x * scale, v[1] = y * scale, v[2] = z * scale, v[3] = m, v[4] = vx, v[5] = vy, v[6] = vz;
+      tgt_pos[slot] = make_float4(x, y, z, m);
+      tgt_vel[slot] = make_float4(vx, vy, vz, 0.f);
+    }
+#pragma unroll
+    for (int c = 0; c < HM_NARR; ++c) T[c * HM_TS + j] = v[c];
+  }
+  if (comm_last_cta(me, 6, &s_flag) && threadIdx.x == 0) me->epoch[3] = e;
+}
+
 // ------------------------------------------------------------------------------- host side ----
 static int comm_check(ocg_ctx* ctx, const char* who) {
   if (!ctx) return OCG_ERR_INVALID;
@@ -409,4 +465,42 @@ extern "C" int ocg_self_gravity_sharded(ocg_ctx* ctx, const double* pos_local_de
   p.out_acc = acc_local_dev - a, p.out_pot = want_pot ? pot_local_dev - a : nullptr, p.out_n = n_local;
   p.G = G, p.accumulate = 0, p.self_e2s = want_pot ? e2f * scale * scale : -1.f, p.m0_ptr = nullptr;
   return ocg_launch_direct(ctx, p, variant, want_pot, /*guard=*/false, st);
+}
+
+// ---- K6 sharded: the position + velocity gather fused into the Hermite tile pack -------------------------------------
+struct HermiteGatherArgs {
+  const double *pos_local, *vel_local, *mass_all;
+  long long n, max_local;
+};
+static int hermite_gather_pack(ocg_ctx* ctx, void* user, float scale, long long total_tiles, float* tiles, float4* tgt_pos,
+                               float4* tgt_vel, cudaStream_t st) {
+  const HermiteGatherArgs* g = (const HermiteGatherArgs*)user;
+  long long nb = (total_tiles * HM_TS + 255) / 256;
+  if (nb > 2ll * ctx->sm_count) nb = 2ll * ctx->sm_count;  // all CTAs co-resident: they poll the peers inside the kernel
+  comm_gather_pack_hermite_kernel<<<(int)nb, 256, 0, st>>>(comm_peers(ctx->comm), g->pos_local, g->vel_local, g->mass_all, g->n,
+                                                          g->max_local, scale, total_tiles, tiles, tgt_pos, tgt_vel);
+  OCG_CHECK_LAUNCH(ctx, "comm_gather_pack_hermite_kernel");
+  return OCG_OK;
+}
+
+extern "C" int ocg_self_gravity_hermite_sharded(ocg_ctx* ctx, const double* pos_local_dev, const double* vel_local_dev,
+                                                const double* mass_all_dev, int64_t n, double eps2, double G, double vel_to_len,
+                                                double* acc_dev, double* jerk_dev, double* pot_dev, void* stream) {
+  int rc = comm_check(ctx, "ocg_self_gravity_hermite_sharded");
+  if (rc) return rc;
+  if (n < 1 || !pos_local_dev || !vel_local_dev || !mass_all_dev || !acc_dev || !jerk_dev)
+    return ocg_fail(ctx, OCG_ERR_INVALID, "ocg_self_gravity_hermite_sharded: bad arguments");
+  if (!(eps2 >= 0.0)) return ocg_fail(ctx, OCG_ERR_INVALID, "ocg_self_gravity_hermite_sharded: eps2 = %g must be >= 0", eps2);
+  ocg_comm* c = ctx->comm;
+  const int P = c->nranks, r = c->rank;
+  const long long a = shard_begin(n, P, r), b = shard_begin(n, P, r + 1);
+  const long long max_local = (n + P - 1) / P;
+  if (18 * max_local * 8 > c->window_bytes)
+    return ocg_fail(ctx, OCG_ERR_INVALID, "ocg_self_gravity_hermite_sharded: window of %lld bytes too small for %lld stars over %d ranks (need %lld)",
+                    c->window_bytes, (long long)n, P, 18 * max_local * 8);
+  OcgDeviceGuard g(ctx->device);
+  HermiteGatherArgs args = {pos_local_dev, vel_local_dev, mass_all_dev, (long long)n, max_local};
+  // every rank must launch the exchange kernel, also one whose block is empty
+  return ocg_hermite_force_packed(ctx, n, a, b, eps2, G, vel_to_len, acc_dev, jerk_dev, pot_dev, (cudaStream_t)stream,
+                                  hermite_gather_pack, &args);
 }

@@ -18,10 +18,6 @@
 
 #include <math.h>
 
-#define HM_TS 512
-#define HM_NARR 7 /* x | y | z | m | vx | vy | vz */
-#define HM_TILE_FLOATS (HM_NARR * HM_TS)
-#define HM_TILE_BYTES (HM_TILE_FLOATS * 4)
 #define HM_NSTAGE 3
 
 struct HermiteParams {
@@ -426,6 +422,79 @@ static float hermite_scale(float e2f) {
   return scale;
 }
 
+// The streaming path: work plan, scratch, tile pack (resident arrays, or `pack` for a cluster whose stars live on several
+// ranks), stream-K kernel.
+static int hermite_force_rows(ocg_ctx* ctx, const double* pos_dev, const double* vel_dev, const double* mass_dev, int64_t n,
+                              const int64_t* seg_offsets_host, int32_t n_seg, double eps2, double G, double vel_to_len,
+                              int64_t tgt_begin, int64_t tgt_end, double* acc_dev, double* jerk_dev, double* pot_dev,
+                              cudaStream_t st, ocg_hermite_pack_fn pack, void* pack_user) {
+  const bool want_pot = pot_dev != nullptr;
+  const int NC = want_pot ? 7 : 6;
+  const float e2f = (float)eps2;
+  const bool guard = !(e2f > 0.f);
+  const float scale = hermite_scale(e2f);
+  const float e2s = guard ? 0.f : e2f * scale * scale;
+  int variant = ctx->knobs.hermite_variant;
+  if (variant >= HM_N_VARIANTS || (variant >= 0 && !g_hm_variants[variant].fn[0][0])) variant = -1;
+  // measured on B200 (tools/bench_hermite.py, profiles/r01_bench_hermite.json): one target pair per thread, two
+  // 8-warp CTAs per SM (122 registers, 16 warps per SM), 4-source-group loop unrolled twice is the fastest shape at
+  // N = 65 536 (60.6 % of FP32 peak, kernel 62.2 %) and on batches of 4096-star clusters (59.9 %)
+  if (variant < 0) variant = HM_PRODUCTION;
+  const HermiteVariant& v = g_hm_variants[variant];
+  const int NTHR = 32 * v.nw, CT = 2 * v.np * NTHR;
+
+  const long long grid_ctas = (long long)ctx->sm_count * v.minb;
+  OcgClusterRows plan;
+  int rc;
+  if ((rc = ocg_plan_cluster_rows(ctx, n, seg_offsets_host, n_seg, tgt_begin, tgt_end, CT, HM_TS, grid_ctas, st, &plan, /*which=*/1)))
+    return rc;
+  float* tiles;
+  float4* tgt;
+  double* partial;
+  unsigned int* tickets;
+  // own scratch slots: a CUDA graph that captured this call must survive K4 calls (bound_center_of_mass) that would
+  // otherwise grow - i.e. reallocate - a shared buffer; the partials are always sized for the 7-component form
+  rc = ocg_scratch(ctx, OCG_SCR_TILES_HM, (size_t)plan.total_tiles * HM_TILE_BYTES, (void**)&tiles);
+  if (!rc) rc = ocg_scratch(ctx, OCG_SCR_TGT_HM, 2 * sizeof(float4) * (size_t)n, (void**)&tgt);
+  if (!rc) rc = ocg_scratch(ctx, OCG_SCR_PARTIAL_HM, sizeof(double) * (size_t)plan.n_slots * 7 * (size_t)n, (void**)&partial);
+  if (!rc) rc = ocg_scratch(ctx, OCG_SCR_TICKETS_HM, sizeof(unsigned int) * (size_t)(plan.n_rows > 0 ? plan.n_rows : 1), (void**)&tickets, true);
+  if (rc) return rc;
+  if (pack) {
+    if ((rc = pack(ctx, pack_user, scale, plan.total_tiles, tiles, tgt, tgt + n, st))) return rc;
+  } else {
+    const long long nslots = plan.total_tiles * HM_TS;
+    pack_hermite_kernel<<<(int)((nslots + 255) / 256), 256, 0, st>>>(pos_dev, vel_dev, mass_dev, n, plan.d_seg_off,
+                                                                    plan.d_seg_tile, n_seg, scale, tiles, tgt, tgt + n);
+    OCG_CHECK_LAUNCH(ctx, "pack_hermite_kernel");
+  }
+  if (plan.n_rows == 0) return OCG_OK;
+  HermiteParams p;
+  p.tiles = tiles, p.tgt_pos = tgt, p.tgt_vel = tgt + n, p.partial = partial, p.out_stride = n;
+  p.sk.rows = plan.d_rows, p.sk.row_prefix = plan.d_prefix, p.sk.n_rows = plan.n_rows, p.sk.n_slots = plan.n_slots;
+  p.sk.n_tgt = n, p.sk.ct = CT, p.sk.nst_uniform = nullptr, p.sk.tickets = tickets;
+  p.out_acc = acc_dev, p.out_jerk = jerk_dev, p.out_pot = pot_dev, p.G = G, p.vel_to_len = vel_to_len;
+  p.e2s = e2s, p.scale = scale;
+  hermite_fn fn = v.fn[want_pot][guard];
+  const size_t smem = HM_NSTAGE * HM_TILE_BYTES + 128 + (size_t)NC * 2 * v.np * NTHR * sizeof(double);
+  OCG_CUDA(ctx, cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (ctx->timing) OCG_CUDA(ctx, cudaEventRecord(ctx->ev0, st));
+  fn<<<(int)grid_ctas, NTHR, smem, st>>>(p);
+  OCG_CHECK_LAUNCH(ctx, "hermite_tp_kernel");
+  if (ctx->timing) {
+    OCG_CUDA(ctx, cudaEventRecord(ctx->ev1, st));
+    ctx->ev_valid = 1;
+  }
+  return OCG_OK;
+}
+
+int ocg_hermite_force_packed(ocg_ctx* ctx, int64_t n, int64_t tgt_begin, int64_t tgt_end, double eps2, double G,
+                             double vel_to_len, double* acc_dev, double* jerk_dev, double* pot_dev, cudaStream_t st,
+                             ocg_hermite_pack_fn pack, void* user) {
+  int64_t seg[2] = {0, n};
+  return hermite_force_rows(ctx, nullptr, nullptr, nullptr, n, seg, 1, eps2, G, vel_to_len, tgt_begin, tgt_end, acc_dev, jerk_dev,
+                            pot_dev, st, pack, user);
+}
+
 extern "C" int ocg_self_gravity_hermite(ocg_ctx* ctx, const double* pos_dev, const double* vel_dev, const double* mass_dev,
                                         int64_t n, const int64_t* seg_offsets_host, int32_t n_seg, double eps2, double G,
                                         double vel_to_len, int64_t tgt_begin, int64_t tgt_end, double* acc_dev,
@@ -473,55 +542,8 @@ extern "C" int ocg_self_gravity_hermite(ocg_ctx* ctx, const double* pos_dev, con
     return OCG_OK;
   }
 
-  int variant = ctx->knobs.hermite_variant;
-  if (variant >= HM_N_VARIANTS || (variant >= 0 && !g_hm_variants[variant].fn[0][0])) variant = -1;
-  // measured on B200 (tools/bench_hermite.py, profiles/r01_bench_hermite.json): one target pair per thread, two
-  // 8-warp CTAs per SM (122 registers, 16 warps per SM), 4-source-group loop unrolled twice is the fastest shape at
-  // N = 65 536 (60.6 % of FP32 peak, kernel 62.2 %) and on batches of 4096-star clusters (59.9 %)
-  if (variant < 0) variant = HM_PRODUCTION;
-  const HermiteVariant& v = g_hm_variants[variant];
-  const int NTHR = 32 * v.nw, CT = 2 * v.np * NTHR;
-
-  const long long grid_ctas = (long long)ctx->sm_count * v.minb;
-  OcgClusterRows plan;
-  int rc;
-  if ((rc = ocg_plan_cluster_rows(ctx, n, seg_offsets_host, n_seg, tgt_begin, tgt_end, CT, HM_TS, grid_ctas, st, &plan, /*which=*/1)))
-    return rc;
-  float* tiles;
-  float4* tgt;
-  double* partial;
-  unsigned int* tickets;
-  // own scratch slots: a CUDA graph that captured this call must survive K4 calls (bound_center_of_mass) that would
-  // otherwise grow - i.e. reallocate - a shared buffer; the partials are always sized for the 7-component form
-  rc = ocg_scratch(ctx, OCG_SCR_TILES_HM, (size_t)plan.total_tiles * HM_TILE_BYTES, (void**)&tiles);
-  if (!rc) rc = ocg_scratch(ctx, OCG_SCR_TGT_HM, 2 * sizeof(float4) * (size_t)n, (void**)&tgt);
-  if (!rc) rc = ocg_scratch(ctx, OCG_SCR_PARTIAL_HM, sizeof(double) * (size_t)plan.n_slots * 7 * (size_t)n, (void**)&partial);
-  if (!rc) rc = ocg_scratch(ctx, OCG_SCR_TICKETS_HM, sizeof(unsigned int) * (size_t)(plan.n_rows > 0 ? plan.n_rows : 1), (void**)&tickets, true);
-  if (rc) return rc;
-  {
-    const long long nslots = plan.total_tiles * HM_TS;
-    pack_hermite_kernel<<<(int)((nslots + 255) / 256), 256, 0, st>>>(pos_dev, vel_dev, mass_dev, n, plan.d_seg_off,
-                                                                    plan.d_seg_tile, n_seg, scale, tiles, tgt, tgt + n);
-    OCG_CHECK_LAUNCH(ctx, "pack_hermite_kernel");
-  }
-  if (plan.n_rows == 0) return OCG_OK;
-  HermiteParams p;
-  p.tiles = tiles, p.tgt_pos = tgt, p.tgt_vel = tgt + n, p.partial = partial, p.out_stride = n;
-  p.sk.rows = plan.d_rows, p.sk.row_prefix = plan.d_prefix, p.sk.n_rows = plan.n_rows, p.sk.n_slots = plan.n_slots;
-  p.sk.n_tgt = n, p.sk.ct = CT, p.sk.nst_uniform = nullptr, p.sk.tickets = tickets;
-  p.out_acc = acc_dev, p.out_jerk = jerk_dev, p.out_pot = pot_dev, p.G = G, p.vel_to_len = vel_to_len;
-  p.e2s = e2s, p.scale = scale;
-  hermite_fn fn = v.fn[want_pot][guard];
-  const size_t smem = HM_NSTAGE * HM_TILE_BYTES + 128 + (size_t)NC * 2 * v.np * NTHR * sizeof(double);
-  OCG_CUDA(ctx, cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  if (ctx->timing) OCG_CUDA(ctx, cudaEventRecord(ctx->ev0, st));
-  fn<<<(int)grid_ctas, NTHR, smem, st>>>(p);
-  OCG_CHECK_LAUNCH(ctx, "hermite_tp_kernel");
-  if (ctx->timing) {
-    OCG_CUDA(ctx, cudaEventRecord(ctx->ev1, st));
-    ctx->ev_valid = 1;
-  }
-  return OCG_OK;
+  return hermite_force_rows(ctx, pos_dev, vel_dev, mass_dev, n, seg_offsets_host, n_seg, eps2, G, vel_to_len, tgt_begin, tgt_end,
+                            acc_dev, jerk_dev, pot_dev, st, nullptr, nullptr);
 }
 
 // ------------------------------------------------------------------ predictor / corrector ----

@@ -189,6 +189,20 @@ struct OcgClusterRows {
   const long long* d_seg_tile;  // device [n_seg + 1]
   const long long* d_seg_off;   // device [n_seg + 1]
 };
+// ---- K6 (hermite.cu): tile format shared with the exchange layer (comm.cu) ----
+#define HM_TS 512
+#define HM_NARR 7 /* x | y | z | m | vx | vy | vz */
+#define HM_TILE_FLOATS (HM_NARR * HM_TS)
+#define HM_TILE_BYTES (HM_TILE_FLOATS * 4)
+// Fills the source tiles ([tile][7][HM_TS], positions times `scale`) and the float4 targets of ONE cluster of n stars,
+// recentred on star 0: pack_hermite_kernel for resident arrays, the peer-memory gather of comm.cu for a sharded cluster.
+typedef int (*ocg_hermite_pack_fn)(ocg_ctx* ctx, void* user, float scale, long long total_tiles, float* tiles,
+                                   float4* tgt_pos, float4* tgt_vel, cudaStream_t st);
+// K6 for the targets [tgt_begin, tgt_end) of one cluster of n stars whose tiles `pack` lays out; outputs [3][n] / [n].
+int ocg_hermite_force_packed(ocg_ctx* ctx, int64_t n, int64_t tgt_begin, int64_t tgt_end, double eps2, double G,
+                             double vel_to_len, double* acc_dev, double* jerk_dev, double* pot_dev, cudaStream_t st,
+                             ocg_hermite_pack_fn pack, void* user);
+
 int ocg_plan_cluster_rows(ocg_ctx* ctx, int64_t n, const int64_t* seg_offsets_host, int32_t n_seg, int64_t tgt_begin,
                           int64_t tgt_end, int ct, int ts, long long grid, cudaStream_t st, OcgClusterRows* out, int which = 0);
 

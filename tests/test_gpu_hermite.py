@@ -297,9 +297,11 @@ def test_fullsize_65536_third_law_and_rows(ctx):
     assert ea <= TOL and ej <= TOL and ep <= TOL
 
 
-def test_two_gpu_sharded_hermite_matches_single_gpu():
-    """K6 target-sharded over 2 GPUs: positions and velocities NCCL-all-gathered per force evaluation, predictor /
-    corrector local, Aarseth step all-reduced (tools/bridge_multi.py --integrator hermite)."""
+@pytest.mark.parametrize("exchange,graph", [("peer", False), ("peer", True), ("nccl", False)])
+def test_two_gpu_sharded_hermite_matches_single_gpu(exchange, graph):
+    """K6 target-sharded over 2 GPUs: positions and velocities gathered per force evaluation — over peer memory inside the
+    tile pack (ocg_self_gravity_hermite_sharded, also as a captured CUDA graph) or NCCL-all-gathered — predictor /
+    corrector local, Aarseth step all-reduced (tools/bridge_multi.py --integrator hermite): bit-identical to one GPU."""
     import json
     import os
     import subprocess
@@ -310,11 +312,12 @@ def test_two_gpu_sharded_hermite_matches_single_gpu():
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
            "--master-port", "29519", os.path.join(root, "tools", "bridge_multi.py"), "--stars", "8192", "--steps", "2",
-           "--integrator", "hermite"]
+           "--integrator", "hermite", "--exchange", exchange] + (["--graph"] if graph else [])
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
     line = json.loads([ln for ln in res.stdout.splitlines() if ln.startswith("{")][-1])
-    assert line["match"] and line["n_gpus"] == 2 and line["integrator"] == "hermite"
+    assert line["match"] and line["n_gpus"] == 2 and line["integrator"] == "hermite" and line["exchange"] == exchange
+    assert line["max_rel_dx"] == 0.0 and line["max_rel_dv"] <= 1e-15
 
 
 def test_driver_loop_with_hermite_graph_steps_and_k4_bookkeeping_between_them(ctx):
