@@ -288,9 +288,11 @@ int ocg_self_gravity(ocg_ctx* ctx, const double* pos_dev, const double* mass_dev
  *   1. ocg_comm_create  allocates this rank's window and fills an opaque OCG_COMM_HANDLE_BYTES handle;
  *   2. the caller all-gathers the handles by any means it has (MPI_Allgather, torch.distributed, a shared file);
  *   3. ocg_comm_connect maps the peers' windows (handles in rank order).
- * Every rank must then issue the same sequence of ocg_comm_* / *_sharded calls.  window_bytes: at least
- * 48 * ceil(n_stars / nranks) for ocg_self_gravity_sharded; the all-reduce works through whatever size it is given
- * (16 bytes per element for a single pass).  nranks <= 16.                                                        */
+ * Every rank must then issue the same sequence of ocg_comm_* / *_sharded calls.  The force exchanges work in the first
+ * half of the window, the all-reduce in the second (they may follow one another without a barrier).  window_bytes: at
+ * least 96 * ceil(n_stars / nranks) for ocg_self_gravity_sharded, 288 * ceil(n_stars / nranks) with the Hermite form;
+ * the all-reduce works through whatever size it is given (32 bytes per element for a single pass).  One sharded
+ * cluster per communicator.  nranks <= 16.                                                                          */
 #define OCG_COMM_HANDLE_BYTES 128
 int ocg_comm_create(ocg_ctx* ctx, int32_t rank, int32_t nranks, int64_t window_bytes, void* handle_out);
 int ocg_comm_connect(ocg_ctx* ctx, const void* all_handles /* [nranks][OCG_COMM_HANDLE_BYTES] */);
@@ -312,7 +314,7 @@ int ocg_self_gravity_sharded(ocg_ctx* ctx, const double* pos_local_dev, const do
 /* The same for the Hermite force (K6, oc_code.py:218-229 with ph4): the rank's block of positions AND velocities
  * ([3][n_local] each) is published, all blocks are read through the mapped windows and packed into the 7-array tiles.
  * acc_dev / jerk_dev ([3][n]) and pot_dev ([n] or NULL) are FULL-size arrays of which the rank's rows [a, b) are written
- * (the layout ocg_self_gravity_hermite uses for a target range).  Needs a window of 144 * ceil(n / nranks) bytes. */
+ * (the layout ocg_self_gravity_hermite uses for a target range). */
 int ocg_self_gravity_hermite_sharded(ocg_ctx* ctx, const double* pos_local_dev, const double* vel_local_dev,
                                      const double* mass_all_dev, int64_t n, double eps2, double G, double vel_to_len,
                                      double* acc_dev, double* jerk_dev, double* pot_dev, void* stream);

@@ -345,8 +345,9 @@ class sharded_cluster_code(cluster_code):
         self._peer = False
         if exchange == "peer" and self.parameters._eps2_kpc2 > 0.0 and self.n_total // self.world >= 2048:
             from .distributed import connect_comm
-            # 2 x 3 doubles per star of a block for the K4 exchange + 2 x 6 behind them for the Hermite one
-            connect_comm(self.ctx, group, window_bytes=max(1 << 20, 160 * (self.n_total // self.world + 1)))
+            # first half of the window: 2 x 3 doubles per star of a block for the K4 exchange + 2 x 6 behind them for the
+            # Hermite one; the second half belongs to the all-reduce
+            connect_comm(self.ctx, group, window_bytes=max(1 << 20, 320 * (self.n_total // self.world + 1)))
             self._peer = True
 
     def _force_hermite_(self, pos, vel, acc, jerk):

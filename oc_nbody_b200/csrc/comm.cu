@@ -115,9 +115,12 @@ __device__ __forceinline__ bool comm_last_cta(CommHeader* me, int t, int* s_flag
 }
 
 // ------------------------------------------------------------------------------ all-reduce ----
-// In place fp64 sum over the ranks of buf[0..m), m*8 <= half the window's data bytes.  Window data: [0, cap) this rank's
-// contribution, [cap, 2 cap) the slice this rank reduced.  Slice of rank q: [q*m/P, (q+1)*m/P).
-__global__ void __launch_bounds__(512) comm_allreduce_kernel(CommPeers pr, double* __restrict__ buf, long long m, long long cap) {
+// In place fp64 sum over the ranks of buf[0..m), m <= cap.  The all-reduce works in the SECOND half of the window's data
+// area (`half` doubles in), the force exchanges below in the first: a rank that runs ahead into an all-reduce must not
+// overwrite the positions a slower peer is still gathering.  Second half: [0, cap) this rank's contribution, [cap, 2 cap)
+// the slice this rank reduced.  Slice of rank q: [q*m/P, (q+1)*m/P).
+__global__ void __launch_bounds__(512) comm_allreduce_kernel(CommPeers pr, double* __restrict__ buf, long long m, long long cap,
+                                                             long long half) {
   __shared__ int s_flag;
   __shared__ unsigned long long s_epoch;
   CommHeader* me = hdr(pr.base[pr.rank]);
@@ -127,7 +130,7 @@ __global__ void __launch_bounds__(512) comm_allreduce_kernel(CommPeers pr, doubl
   const long long tid = blockIdx.x * (long long)blockDim.x + threadIdx.x, nthr = (long long)gridDim.x * blockDim.x;
   const int P = pr.nranks, r = pr.rank;
   // phase 1: publish my contribution
-  double* mine = win_data(pr.base[r]);
+  double* mine = win_data(pr.base[r]) + half;
   for (long long i = tid; i < m; i += nthr) mine[i] = buf[i];
   if (comm_last_cta(me, 0, &s_flag) && threadIdx.x == 0) comm_signal_all(pr, 1, e);
   // phase 2: reduce my slice over the ranks, in rank order
@@ -140,7 +143,7 @@ __global__ void __launch_bounds__(512) comm_allreduce_kernel(CommPeers pr, doubl
   if (ok1)
     for (long long i = s0 + tid; i < s1; i += nthr) {
       double s = 0.0;
-      for (int q = 0; q < P; ++q) s += ld_peer(win_data(pr.base[q]) + i);
+      for (int q = 0; q < P; ++q) s += ld_peer(win_data(pr.base[q]) + half + i);
       res[i - s0] = s;
     }
   if (comm_last_cta(me, 1, &s_flag) && threadIdx.x == 0) comm_signal_all(pr, 2, e);
@@ -152,7 +155,7 @@ __global__ void __launch_bounds__(512) comm_allreduce_kernel(CommPeers pr, doubl
   if (ok1 && ok2)
     for (int q = 0; q < P; ++q) {
       const long long q0 = (long long)q * m / P, q1 = (long long)(q + 1) * m / P;
-      const double* src = win_data(pr.base[q]) + cap;
+      const double* src = win_data(pr.base[q]) + half + cap;
       for (long long i = q0 + tid; i < q1; i += nthr) buf[i] = ld_peer(src + (i - q0));
     }
   // the last CTA to finish advances the epoch (every CTA has read it by now)
@@ -394,14 +397,14 @@ extern "C" int ocg_comm_allreduce_f64(ocg_ctx* ctx, double* buf_dev, int64_t n, 
   if (n == 0) return OCG_OK;
   ocg_comm* c = ctx->comm;
   OcgDeviceGuard g(ctx->device);
-  // window data: [0, cap) contribution, [cap, cap + ceil(cap / P)) reduced slice
-  const long long cap = (c->window_bytes / 8) / 2;
+  // second half of the window data: [0, cap) contribution, [cap, cap + ceil(cap / P)) reduced slice
+  const long long half = (c->window_bytes / 8) / 2, cap = half / 2;
   if (cap < c->nranks) return ocg_fail(ctx, OCG_ERR_INVALID, "ocg_comm_allreduce_f64: window too small (%lld bytes)", c->window_bytes);
   const CommPeers pr = comm_peers(c);
   int grid = ctx->sm_count;  // all CTAs co-resident: they poll the peers inside the kernel
   for (int64_t off = 0; off < n; off += cap) {
     const long long m = n - off < cap ? n - off : cap;
-    comm_allreduce_kernel<<<grid, 512, 0, (cudaStream_t)stream>>>(pr, buf_dev + off, m, cap);
+    comm_allreduce_kernel<<<grid, 512, 0, (cudaStream_t)stream>>>(pr, buf_dev + off, m, cap, half);
     OCG_CHECK_LAUNCH(ctx, "comm_allreduce_kernel");
   }
   return OCG_OK;
@@ -418,9 +421,9 @@ extern "C" int ocg_self_gravity_sharded(ocg_ctx* ctx, const double* pos_local_de
   const int P = c->nranks, r = c->rank;
   const long long a = shard_begin(n, P, r), b = shard_begin(n, P, r + 1), n_local = b - a;
   const long long max_local = (n + P - 1) / P;
-  if (2 * 3 * max_local * 8 > c->window_bytes)
+  if (2 * 3 * max_local * 8 > c->window_bytes / 2)  // the force exchanges own the first half of the window
     return ocg_fail(ctx, OCG_ERR_INVALID, "ocg_self_gravity_sharded: window of %lld bytes too small for %lld stars over %d ranks (need %lld)",
-                    c->window_bytes, (long long)n, P, 2 * 3 * max_local * 8);
+                    c->window_bytes, (long long)n, P, 2 * 2 * 3 * max_local * 8);
   OcgDeviceGuard g(ctx->device);
   cudaStream_t st = (cudaStream_t)stream;
   const bool want_pot = pot_local_dev != nullptr;
@@ -495,9 +498,9 @@ extern "C" int ocg_self_gravity_hermite_sharded(ocg_ctx* ctx, const double* pos_
   const int P = c->nranks, r = c->rank;
   const long long a = shard_begin(n, P, r), b = shard_begin(n, P, r + 1);
   const long long max_local = (n + P - 1) / P;
-  if (18 * max_local * 8 > c->window_bytes)
+  if (18 * max_local * 8 > c->window_bytes / 2)
     return ocg_fail(ctx, OCG_ERR_INVALID, "ocg_self_gravity_hermite_sharded: window of %lld bytes too small for %lld stars over %d ranks (need %lld)",
-                    c->window_bytes, (long long)n, P, 18 * max_local * 8);
+                    c->window_bytes, (long long)n, P, 2 * 18 * max_local * 8);
   OcgDeviceGuard g(ctx->device);
   HermiteGatherArgs args = {pos_local_dev, vel_local_dev, mass_all_dev, (long long)n, max_local};
   // every rank must launch the exchange kernel, also one whose block is empty

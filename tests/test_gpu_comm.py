@@ -20,7 +20,7 @@ G = 4.3986004e-09
 def comm_ctx():
     from oc_nbody_b200._lib import Context
     c = Context(0)
-    h = c.comm_create(0, 1, 1 << 20)
+    h = c.comm_create(0, 1, 2 << 20)   # first half: force exchanges (96 B per star of a block), second half: all-reduce
     assert len(h) == Context.COMM_HANDLE_BYTES
     c.comm_connect([h])
     yield c
@@ -30,7 +30,7 @@ def comm_ctx():
 def test_allreduce_single_rank_is_identity_and_chunks(comm_ctx):
     import torch
     rng = np.random.default_rng(5)
-    for n in (1, 1000, 65536, 200001):   # the last exceeds the 1 MiB window's single-pass capacity (65536 doubles): 4 passes
+    for n in (1, 1000, 65536, 200001):   # the last exceeds the 2 MiB window's single-pass capacity (65536 doubles): 4 passes
         x = rng.normal(size=n)
         d = dev(x)
         comm_ctx.comm_allreduce_f64(d)
