@@ -19,7 +19,8 @@ Workload
           host tensors (N>1): FP64 host buffers in, H2D, recentre, K1, [all-reduce], K1b, D2H of the field.
   parity_check : rows of the (all-reduced) raw field against the FP64 oracle over ALL shards, strict metric; the run
           fails when the raw field misses 1e-5.
-  roofline_k4, bridge_step, cpu_baseline.bridge_step (N=1): K4 at N = 65 536 and the BRIDGE step, GPU and CPU.
+  roofline_k4, roofline_k3, bridge_step, cpu_baseline.bridge_step (N=1): K4 at N = 65 536 (FP32 bound), K3 at configs[3]
+  (HBM bound) and the BRIDGE step, GPU and CPU.
   --impl reference : the reference's CPU path (the FP64 OpenMP port in oracle/, ALL host threads, also under torchrun)
           on a bounded sample of the same config.
 """
@@ -333,6 +334,48 @@ def bridge_step_times(ctx):
     return out
 
 
+def k3_roofline(ctx):
+    """Third roofline entry (driver-run), the HBM-bound kernel of the path: K3 (trilinear gather + time blend) at configs[3]
+    — 256 clusters x 4 096 stars, 32^3 grids, two snapshots — against the measured copy bandwidth of MEASURED_PEAKS.json.
+    Algorithmic bytes per launch: per star 24 B in + 24 B out, every 3-component plane once.  L2 flushed before
+    every launch (a 256 MB buffer is overwritten)."""
+    import torch
+    dev = torch.device("cuda", ctx.device)
+    try:
+        peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+        peak_kind = "MEASURED_PEAKS.json hbm_gbs (copy bandwidth measured on this pool)"
+    except Exception:  # noqa: BLE001
+        peak, peak_kind = 6454.0, "fallback: the pool's measured copy bandwidth recorded in round 1 (MEASURED_PEAKS.json absent)"
+    ncl, nstar, n = 256, 4096, 32
+    rng = np.random.default_rng(7)
+    nodes = [torch.from_numpy(np.linspace(-0.05, 0.05, n)).to(dev) for _ in range(3)]
+    rec = torch.randn((2, ncl, n ** 3 + 1, 4), dtype=torch.float32, device=dev)
+    ang = np.linspace(0, 2 * np.pi, ncl, endpoint=False)
+    origin = np.stack([8 * np.cos(ang), 8 * np.sin(ang), np.zeros(ncl)], 1)
+    scl = np.repeat(np.arange(ncl, dtype=np.int32), nstar)
+    p = origin[scl] + rng.normal(0, 0.004, (ncl * nstar, 3))
+    sx, sy, sz = (torch.from_numpy(np.ascontiguousarray(p[:, k])).to(dev) for k in range(3))
+    d_or, d_scl = torch.from_numpy(origin).to(dev), torch.from_numpy(scl).to(dev)
+    acc = torch.empty((3, ncl * nstar), dtype=torch.float64, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    ts = []
+    for i in range(23):
+        flush.fill_(i & 1)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        ctx.grid_interp((n, n, n), nodes, d_or, rec[0], rec[1], 0.37, sx, sy, sz, d_scl, acc, None)
+        e1.record()
+        torch.cuda.synchronize()
+        if i >= 3:
+            ts.append(e0.elapsed_time(e1))
+    ms = float(np.median(ts))
+    alg = ncl * (nstar * 48 + 2 * 3 * 4 * n ** 3)
+    ach = alg / ms / 1e6
+    return {"bound": "hbm", "kernel": "K3 grid_interp_kernel, configs[3]: 256 clusters x 4096 stars, 32^3 grids, 2 snapshots",
+            "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None, "peak_kind": peak_kind,
+            "ms_per_launch": ms, "algorithmic_bytes_per_launch": alg, "l2": "flushed before every launch"}
+
+
 def k4_roofline(ctx, nominal):
     """Second roofline entry (driver-run): K4 cluster self-gravity at configs[2]'s N = 65 536 (4.29e9 interactions per
     evaluation), whole evaluation (pack + stream-K kernel, two launches) timed with CUDA events; `frac_kernel_alone` from the
@@ -573,6 +616,12 @@ def main():
     extras = world == 1 and not args.no_extras
     bridge = bridge_step_times(ctx) if extras else None
     roofline_k4 = k4_roofline(ctx, nominal) if extras else None
+    roofline_k3 = None
+    if extras:
+        try:
+            roofline_k3 = k3_roofline(ctx)
+        except Exception as exc:  # noqa: BLE001  (an extra must never cost the headline line)
+            roofline_k3 = {"error": str(exc)[:200]}
     cpu = None
     if not args.no_cpu_baseline:
         import oracle
@@ -597,6 +646,7 @@ def main():
         "gpu_launches": launches,
         "roofline": roofline,
         "roofline_k4": roofline_k4,
+        "roofline_k3": roofline_k3,
         "cpu_baseline": cpu,
         "parity_check": parity,
         "pct_fp32_peak": 100.0 * achieved / nominal,
