@@ -458,8 +458,7 @@ extern "C" int ocg_self_gravity_sharded(ocg_ctx* ctx, const double* pos_local_de
     OCG_CHECK_LAUNCH(ctx, "comm_gather_pack_kernel");
   }
   if (plan.n_rows == 0) return OCG_OK;
-  DirectParams p;
-  memset(&p, 0, sizeof(p));
+  DirectParams p{};
   p.out_stride = n, p.n_tgt = n, p.scale_val = scale;
   p.tiles = tiles, p.tgt = tgt, p.partial = partial;
   p.sk.rows = plan.d_rows, p.sk.row_prefix = plan.d_prefix, p.sk.n_rows = plan.n_rows, p.sk.n_slots = plan.n_slots;

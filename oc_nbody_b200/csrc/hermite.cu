@@ -523,8 +523,6 @@ extern "C" int ocg_self_gravity_hermite(ocg_ctx* ctx, const double* pos_dev, con
 
   OcgDeviceGuard g(ctx->device);
   cudaStream_t st = (cudaStream_t)stream;
-  const bool want_pot = pot_dev != nullptr;
-  const int NC = want_pot ? 7 : 6;
   const float e2f = (float)eps2;
   const bool guard = !(e2f > 0.f);
   const float scale = hermite_scale(e2f);
@@ -883,8 +881,7 @@ extern "C" int ocg_hermite_block_evolve(ocg_ctx* ctx, double* pos_dev, double* v
       OCG_CHECK_LAUNCH(ctx, "hermite_block_gather_kernel");
       tp = ctgt_pos, tv = ctgt_vel;
     }
-    HermiteParams p;
-    memset(&p, 0, sizeof(p));
+    HermiteParams p{};
     p.tiles = tiles, p.tgt_pos = tp, p.tgt_vel = tv, p.partial = partial, p.out_stride = n_t;
     p.sk.rows = nullptr, p.sk.row_prefix = nullptr, p.sk.n_rows = (n_t + CT - 1) / CT, p.sk.n_slots = (int)n_slots;
     p.sk.n_tgt = n_t, p.sk.ct = CT, p.sk.nst_uniform = nullptr, p.sk.nst_value = (int)total_tiles, p.sk.tickets = tickets;

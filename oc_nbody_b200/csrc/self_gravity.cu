@@ -382,8 +382,7 @@ extern "C" int ocg_self_gravity(ocg_ctx* ctx, const double* pos_dev, const doubl
   float* tiles;
   float4* tgt;
   double* partial;
-  DirectParams p;
-  memset(&p, 0, sizeof(p));
+  DirectParams p{};
   p.out_stride = n;
   p.n_tgt = n;
   p.scale_val = scale;
