@@ -792,7 +792,10 @@ int ocg_direct_sum_impl(ocg_ctx* ctx, const float* src_xyzm, const float* src_so
   const bool tp = variant_is_tp(g_variants[variant]);
   long long n_chunks, tiles_per_chunk = 0;
   // source tiles per pass of the stream-K kernel: what stays in L2 while every CTA streams it (streamk.cuh, PASSES)
-  const long long pass_tiles = ctx->knobs.pass_bytes > 0 ? (ctx->knobs.pass_bytes + narr * OCG_TS * 4 - 1) / (narr * OCG_TS * 4) : 0;
+  long long pass_tiles = ctx->knobs.pass_bytes > 0 ? (ctx->knobs.pass_bytes + narr * OCG_TS * 4 - 1) / (narr * OCG_TS * 4) : 0;
+  // at most 64 passes: every pass adds a set of partial slots (scratch = passes x slots x field size), and beyond
+  // 64 x 32 MB of tiles (1e8 sources) what a longer pass re-reads from HBM is a negligible share of the call anyway
+  if (pass_tiles > 0 && (n_tiles_max + pass_tiles - 1) / pass_tiles > 64) pass_tiles = (n_tiles_max + 63) / 64;
   const long long n_pass_max = pass_tiles > 0 && pass_tiles < n_tiles_max ? (n_tiles_max + pass_tiles - 1) / pass_tiles : 1;
   if (tp) {
     // stream-K (streamk.cuh): a row of targets is shared by at most ceil(CTAs / rows) + 1 consecutive CTAs per pass
