@@ -345,3 +345,30 @@ def test_whole_grid_pickle_is_read_by_the_real_reference_class(tmp_path):
         assert np.array_equal(r.evolved_grid, g.init_grid + np.array([1.0, 2.0, 3.0]))
     finally:
         del sys.modules["oceanic"], sys.modules["oceanic.grid_cartesian"]
+
+
+def test_cache_compat_rejects_what_it_cannot_vouch_for(tmp_path):
+    """cache_compat's failure modes are loud: a pickle that is not a grid, a grid whose point list is not the one its sizes
+    generate, an `interface` file that is not our settings dict."""
+    import pickle
+    from oc_nbody_b200 import cache_compat
+    from oc_nbody_b200.grid_cartesian import grid
+    not_a_grid = tmp_path / "plain.pickle"
+    pickle.dump({"x": 1}, open(not_a_grid, "wb"), protocol=4)
+    with pytest.raises(ValueError, match="does not hold a grid"):
+        cache_compat.load_grid_pickle(str(not_a_grid))
+    g = grid(0.1, 0.1, 0.1, 0.05)
+    g.snapshot_acceleration_x = g.snapshot_acceleration_y = g.snapshot_acceleration_z = np.zeros((2, len(g)))
+    good = tmp_path / "grid.pickle"
+    cache_compat.dump_grid_pickle(g, str(good))
+    back = cache_compat.load_grid_pickle(str(good))
+    assert np.array_equal(back.init_grid, g.init_grid) and back.snapshot_acceleration_x.shape == (2, len(g))
+    g.init_grid = g.init_grid + 1e-3            # a point list its sizes do not generate
+    bad = tmp_path / "tampered.pickle"
+    cache_compat.dump_grid_pickle(g, str(bad))
+    with pytest.raises(ValueError, match="point list"):
+        cache_compat.load_grid_pickle(str(bad))
+    (tmp_path / "iface").mkdir()
+    pickle.dump([1, 2, 3], open(tmp_path / "iface" / "interface", "wb"), protocol=4)
+    with pytest.raises(ValueError, match="settings dict"):
+        cache_compat.load_interface(str(tmp_path / "iface"))
