@@ -280,17 +280,26 @@ class cluster_code(object):
         self.ctx.eject_mask(self.pos, 1000.0, float(self.eject_cut), keep)
         return self._compact_(keep)
 
-    def bound_center_of_mass(self, return_mask=False):
+    def bound_center_of_mass(self, return_mask=False, iterations=1):
         """Centre of mass (kpc) of the bound subset: E_i = |v_i - v_com|^2/2 + phi_i < 0
         (oc_nbody.py:60-61: particles.bound_subset().center_of_mass()).  K4 with the potential, then one reduction
-        kernel; only the 8-double result row comes back to the host."""
+        kernel; only the 8-double result row comes back to the host.
+
+        iterations = 1: v_com is the centre-of-mass velocity of ALL stars (one pass).  iterations > 1: v_com is re-taken
+        from the stars found bound and the test repeated until the bound set stops changing (at most `iterations` passes) —
+        once a tidal tail has developed, the escapers inside the ejection cut otherwise drag the frame away from the core
+        (AMUSE's own bound_subset works in the core's frame).  The potential is that of all stars either way."""
         import torch
         self.compute_self_gravity(want_pot=True)
         out = torch.empty((1, 8), dtype=torch.float64, device=self._dev)
-        mask = torch.empty(self.n, dtype=torch.uint8, device=self._dev) if return_mask else None
-        # pot is in kpc km/s /Myr; 1/KMS_TO_KPC_PER_MYR turns it into (km/s)^2
-        self.ctx.bound_com(self.pos, self.vel, self.mass, self.pot, 1.0 / KMS_TO_KPC_PER_MYR, out, None, mask)
-        res = out.cpu().numpy()[0]
+        want_mask = return_mask or iterations > 1
+        mask = torch.empty(self.n, dtype=torch.uint8, device=self._dev) if want_mask else None
+
+        def one_pass(weights):
+            # pot is in kpc km/s /Myr; 1/KMS_TO_KPC_PER_MYR turns it into (km/s)^2
+            self.ctx.bound_com(self.pos, self.vel, weights, self.pot, 1.0 / KMS_TO_KPC_PER_MYR, out, None, mask)
+            return mask
+        res = iterate_bound_subset(one_pass, self.pos, self.mass, out, iterations)
         self.n_bound, self.bound_mass = int(res[4]), float(res[3])
         return (res[:3], mask.cpu().numpy().astype(bool)) if return_mask else res[:3]
 
@@ -305,6 +314,30 @@ class cluster_code(object):
 
     def stop(self):
         pass
+
+
+def iterate_bound_subset(one_pass, pos, mass, out, iterations):
+    """The bound-subset iteration above the one-pass reduction kernel.  one_pass(weights) runs ocg_bound_com with `weights`
+    in place of the masses — the frame velocity is the weighted mean over ALL stars, so weights = mass * (previous mask)
+    makes it the bound set's — fills `out` ([1, 8]) and returns the device mask of ALL stars that pass the energy test.
+    Returns the 8-number row (numpy) for the final bound set: COM (3), bound mass, bound count, frame velocity (3)."""
+    import torch
+    mask = one_pass(mass)
+    if iterations <= 1:
+        return out.cpu().numpy()[0]
+    prev = mask.clone()
+    for _ in range(iterations - 1):
+        mask = one_pass(mass * prev.to(mass.dtype))
+        if torch.equal(mask, prev):
+            break
+        prev.copy_(mask)
+    res = out.cpu().numpy()[0].copy()
+    # the kernel's COM row weighs with mass * (previous mask): exact once the set has converged, else redo it for the
+    # final mask with the true masses
+    w = mass * mask.to(mass.dtype)
+    res[3], res[4] = float(w.sum().item()), float(mask.sum().item())
+    res[:3] = ((pos * w[None, :]).sum(dim=1) / w.sum()).cpu().numpy()
+    return res
 
 
 class sharded_cluster_code(cluster_code):

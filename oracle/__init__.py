@@ -495,16 +495,24 @@ def layout_nested(planes, n_coarse, keep_index, hole_index, hole_points, fine_no
     return coarse, fine
 
 
-def bound_com(pos, vel, mass, pot_v2):
+def bound_com(pos, vel, mass, pot_v2, iterations=1):
     """Bound subset and its centre of mass (oc_nbody.py:60-61, particles.bound_subset().center_of_mass()):
     E_i = |v_i - v_com|^2 / 2 + phi_i < 0 with v_com the velocity of the cluster's centre of mass; everything
-    counts when nothing is bound.  pos, vel [3, n]; pot_v2 [n] in velocity^2 units. Returns (com[3], mask[n], v_com[3])."""
+    counts when nothing is bound.  iterations > 1: v_com is re-taken from the stars found bound and the test repeated
+    until the set stops changing.  pos, vel [3, n]; pot_v2 [n] in velocity^2 units. Returns (com[3], mask[n], v_com[3])."""
     pos, vel, mass, pot_v2 = (np.asarray(a, np.float64) for a in (pos, vel, mass, pot_v2))
-    vcom = (vel * mass).sum(axis=1) / mass.sum()
-    dv = vel - vcom[:, None]
-    bound = 0.5 * (dv * dv).sum(axis=0) + pot_v2 < 0.0
-    if not bound.any():
-        bound[:] = True
+    w = mass.copy()
+    bound = None
+    for _ in range(max(1, iterations)):
+        vcom = (vel * w).sum(axis=1) / w.sum()
+        dv = vel - vcom[:, None]
+        new = 0.5 * (dv * dv).sum(axis=0) + pot_v2 < 0.0
+        if not new.any():
+            new[:] = True
+        if bound is not None and np.array_equal(new, bound):
+            break
+        bound = new
+        w = mass * bound
     return (pos[:, bound] * mass[bound]).sum(axis=1) / mass[bound].sum(), bound, vcom
 
 

@@ -372,3 +372,49 @@ def test_cache_compat_rejects_what_it_cannot_vouch_for(tmp_path):
     pickle.dump([1, 2, 3], open(tmp_path / "iface" / "interface", "wb"), protocol=4)
     with pytest.raises(ValueError, match="settings dict"):
         cache_compat.load_interface(str(tmp_path / "iface"))
+
+
+def test_iterated_bound_subset_logic_matches_the_oracle():
+    """cluster.iterate_bound_subset above a numpy stand-in for the one-pass reduction kernel (same contract as
+    ocg_bound_com: frame = weighted mean velocity of all stars, mask over all stars, COM weighted by the weights) against
+    oracle.bound_com(iterations=...) on a cluster with a one-sided tail of escapers: the tail drags the one-pass frame, the
+    iteration recovers the core's."""
+    import torch
+    import oracle
+    from oc_nbody_b200.cluster import iterate_bound_subset
+    from oc_nbody_b200.synthetic import make_plummer_cluster
+    pos_pc, vel, mass = make_plummer_cluster(1500, seed=3)
+    pos = pos_pc * 1e-3
+    tail = np.arange(0, 1500, 4)                       # a quarter of the stars stream away in +x
+    vel[0, tail] += 6.0
+    pos[0, tail] += 0.004
+    G = 4.3009125e-6                                    # kpc (km/s)^2 / Msun
+    _, phi = oracle.self_gravity(pos, mass, (0.01e-3) ** 2, G, want_pot=True)
+    t_pos, t_vel, t_mass, t_phi = (torch.from_numpy(np.ascontiguousarray(a)) for a in (pos, vel, mass, phi))
+    out = torch.empty((1, 8), dtype=torch.float64)
+    mask = torch.empty(1500, dtype=torch.uint8)
+    calls = []
+
+    def one_pass(weights):
+        w = weights.numpy()
+        vc = (vel * w).sum(axis=1) / w.sum()
+        e = 0.5 * ((vel - vc[:, None]) ** 2).sum(axis=0) + phi
+        bd = e < 0.0
+        if not bd.any():
+            bd[:] = True
+        mask.copy_(torch.from_numpy(bd.astype(np.uint8)))
+        wb = w * bd
+        row = np.concatenate([(pos * wb).sum(axis=1) / wb.sum() if wb.sum() > 0 else (pos * w).sum(axis=1) / w.sum(),
+                              [wb.sum(), bd.sum()], vc])
+        out.copy_(torch.from_numpy(row[None]))
+        calls.append(1)
+        return mask
+    one = iterate_bound_subset(one_pass, t_pos, t_mass, out, 1)
+    com1, m1, _ = oracle.bound_com(pos, vel, mass, phi, iterations=1)
+    assert len(calls) == 1 and np.allclose(one[:3], com1, rtol=1e-12, atol=1e-15) and int(one[4]) == m1.sum()
+    it = iterate_bound_subset(one_pass, t_pos, t_mass, out, 8)
+    com8, m8, _ = oracle.bound_com(pos, vel, mass, phi, iterations=8)
+    assert np.array_equal(mask.numpy().astype(bool), m8) and int(it[4]) == m8.sum()
+    assert np.allclose(it[:3], com8, rtol=1e-12, atol=1e-15) and np.isclose(it[3], mass[m8].sum())
+    assert m8.sum() != m1.sum()                        # the frame matters on this configuration
+    assert not m8[tail].any()                          # the escapers are out, whatever the one-pass frame said of them

@@ -284,6 +284,32 @@ def test_cluster_code_clean_ejections_and_bound_com(ctx):
     assert np.allclose(com - center, want_com - center, rtol=1e-6, atol=1e-12)
 
 
+def test_cluster_code_iterated_bound_subset(ctx):
+    """bound_center_of_mass(iterations=8): with a one-sided tail of escapers the frame is re-taken from the bound stars until
+    the set is stable; mask and centre of mass equal the oracle's iteration (that the iteration changes the answer on such a
+    configuration is shown on the CPU, tests/test_cpu_host.py::test_iterated_bound_subset_logic_matches_the_oracle)."""
+    from oc_nbody_b200.cluster import KMS_TO_KPC_PER_MYR, cluster_code
+    from oc_nbody_b200.synthetic import make_plummer_cluster
+    pos_pc, vel, mass = make_plummer_cluster(3000, seed=3)
+    center = np.array([8.0, 0.0, 0.0])
+    pos = pos_pc * 1e-3 + center[:, None]
+    tail = np.arange(0, 3000, 4)
+    vel[0, tail] += 6.0
+    pos[0, tail] += 0.004
+    cl = cluster_code(mass, pos, vel, softening_pc=0.01, ctx=ctx)
+    com1, mask1 = cl.bound_center_of_mass(return_mask=True)
+    com8, mask8 = cl.bound_center_of_mass(return_mask=True, iterations=8)
+    _, phi = oracle.self_gravity(pos, mass, (0.01e-3) ** 2, cl.G, want_pot=True)
+    w1, wm1, _ = oracle.bound_com(pos, vel, mass, phi / KMS_TO_KPC_PER_MYR)
+    w8, wm8, _ = oracle.bound_com(pos, vel, mass, phi / KMS_TO_KPC_PER_MYR, iterations=8)
+    print("bound stars, one pass / iterated:", int(wm1.sum()), int(wm8.sum()))
+    assert np.array_equal(mask1, wm1)
+    assert np.array_equal(mask8, wm8)
+    assert np.allclose(com1 - center, w1 - center, rtol=1e-6, atol=1e-12)
+    assert np.allclose(com8 - center, w8 - center, rtol=1e-6, atol=1e-12)
+    assert cl.n_bound == int(wm8.sum()) and np.isclose(cl.bound_mass, mass[wm8].sum())
+
+
 def test_field_code_snapshot_caches_round_trip(ctx, tmp_path):
     """Second construction with the same options is served from the reference-format caches, bit for bit."""
     from oc_nbody_b200.gizmo_field import gizmo_field
